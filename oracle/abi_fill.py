@@ -1,0 +1,155 @@
+"""Fill the C-ABI descriptors from the oracle's own parse of the reference inputs (TEST INFRASTRUCTURE).
+Used to (a) drive the CPU port / CUDA path with oracle-parsed data and (b) check the product's C++ loaders."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from qm_door_b200 import _abi
+from . import sqp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def model_desc(m):
+    d = _abi.ModelDesc()
+    d.nj = m.nj
+    depth = np.zeros(m.nj, dtype=np.int32)
+    for j in range(m.nj):
+        depth[j] = 0 if m.parent[j] < 0 else depth[m.parent[j]] + 1
+    _abi._set(d.parent, m.parent)
+    _abi._set(d.jtype, m.jtype)
+    _abi._set(d.depth, depth)
+    sub = [sum(1 << i for i in range(m.nj) if m.path[i, j]) for j in range(m.nj)]
+    pth = [sum(1 << k for k in range(m.nj) if m.path[j, k]) for j in range(m.nj)]
+    _abi._set(d.submask, np.array(sub, dtype=np.uint32))
+    _abi._set(d.pathmask, np.array(pth, dtype=np.uint32))
+    d.max_depth = int(depth.max())
+    _abi._set(d.foot_joint, m.foot_joint)
+    d.ee_joint = int(m.ee_joint)
+    _abi._set(d.axis, m.axis)
+    _abi._set(d.Rp, m.Rp.reshape(m.nj, 9))
+    _abi._set(d.pp, m.pp)
+    _abi._set(d.mass, m.mass)
+    _abi._set(d.com, m.com)
+    _abi._set(d.inertia, m.inertia.reshape(m.nj, 9))
+    _abi._set(d.foot_off, m.foot_off)
+    _abi._set(d.ee_off, m.ee_off)
+    _abi._set(d.ee_Roff, np.asarray(m.ee_Roff).reshape(9))
+    d.total_mass = m.total_mass
+    _abi._set(d.lower, np.nan_to_num(m.lower, neginf=-1e30))
+    _abi._set(d.upper, np.nan_to_num(m.upper, posinf=1e30))
+    _abi._set(d.effort, m.effort)
+    return d
+
+
+def problem_desc(m, P):
+    d = _abi.ProblemDesc()
+    _abi._set(d.Q, P.Q.reshape(-1))
+    _abi._set(d.R, sqp.input_cost_weight(m, P).reshape(-1))
+    for k in ("mu_ee_pos", "mu_ee_ori", "mu_fee_pos", "mu_fee_ori", "fric_mu", "fric_bar_mu", "fric_bar_delta",
+              "fric_reg", "fric_grip", "fric_hess_shift", "pos_bar_mu", "pos_bar_delta", "vel_bar_mu", "vel_bar_delta"):
+        setattr(d, k, float(getattr(P, k)))
+    for k in ("arm_pos_lo", "arm_pos_hi", "arm_vel_lo", "arm_vel_hi"):
+        _abi._set(getattr(d, k), getattr(P, k))
+    z = np.zeros(6)
+    d.box_offset = float(sqp.relaxed_barrier(z - P.arm_pos_lo, P.pos_bar_mu, P.pos_bar_delta)[0].sum()
+                         + sqp.relaxed_barrier(P.arm_pos_hi - z, P.pos_bar_mu, P.pos_bar_delta)[0].sum()
+                         + sqp.relaxed_barrier(z - P.arm_vel_lo, P.vel_bar_mu, P.vel_bar_delta)[0].sum()
+                         + sqp.relaxed_barrier(P.arm_vel_hi - z, P.vel_bar_mu, P.vel_bar_delta)[0].sum())
+    d.swing_liftoff_vel = P.swing["liftOffVelocity"]
+    d.swing_touchdown_vel = P.swing["touchDownVelocity"]
+    d.swing_height = P.swing["swingHeight"]
+    d.swing_time_scale = P.swing["swingTimeScale"]
+    d.gravity = 9.81
+    return d
+
+
+def solver_desc(P, horizon=None, dt=None, max_nodes=None, max_events=32, max_targets=2):
+    d = _abi.SolverDesc()
+    d.dt = P.sqp["dt"] if dt is None else dt
+    d.horizon = P.time_horizon if horizon is None else horizon
+    d.delta_tol, d.g_max, d.g_min = P.sqp["deltaTol"], P.sqp["g_max"], P.sqp["g_min"]
+    d.alpha_decay, d.alpha_min = P.sqp["alpha_decay"], P.sqp["alpha_min"]
+    d.gamma_c, d.armijo_factor = P.sqp["gamma_c"], P.sqp["armijoFactor"]
+    d.weak_eps, d.dt_min = 1e-6, 1e-8
+    n = int(round(d.horizon / d.dt))
+    d.max_nodes = (n + 1 + 24) if max_nodes is None else max_nodes
+    d.max_events = max_events
+    d.max_targets = max_targets
+    return d
+
+
+_cport = None
+
+
+def load_cport():
+    """Build (if stale) and load the CPU port shared library."""
+    global _cport
+    if _cport is not None:
+        return _cport
+    so = os.path.join(HERE, "cport", "libcport.so")
+    src = os.path.join(HERE, "cport", "cport.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "qm_door_b200", "csrc", f) for f in ("qm_core.h", "qm_types.h", "qm_mpc.h")]
+    deps = [p for p in deps if os.path.exists(p)]
+    if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
+        subprocess.check_call(["g++", "-O2", "-march=native", "-std=c++17", "-shared", "-fPIC", "-pthread",
+                               "-o", so, src])
+    _cport = C.CDLL(so)
+    return _cport
+
+
+class CPort:
+    """ctypes front-end of the CPU port (same call shape as the CUDA C-ABI, host buffers)."""
+
+    LS = dict(alpha=0, done=1, armijo=2, dxnorm=3, dunorm=4, base_merit=5, base_dyn=6, base_eq=7,
+              new_merit=8, new_dyn=9, new_eq=10, iters=11)
+
+    def __init__(self, md, pd, sd, B, threads=1):
+        self.lib = load_cport()
+        self.lib.cport_create.restype = C.c_void_p
+        self.md, self.pd, self.sd, self.B = md, pd, sd, B
+        self.NMAX, self.EMAX, self.KT = sd.max_nodes, sd.max_events, sd.max_targets
+        self.ctx = C.c_void_p(self.lib.cport_create(C.byref(md), C.byref(pd), C.byref(sd), B, threads))
+
+    def close(self):
+        if self.ctx:
+            self.lib.cport_destroy(self.ctx)
+            self.ctx = None
+
+    def reset(self):
+        self.lib.cport_reset(self.ctx)
+
+    def cycle(self, t0, x0, events, modes, nevents, target_t, target_x):
+        B, N = self.B, self.NMAX
+        dp = lambda a: a.ctypes.data_as(C.c_void_p)
+        t0 = np.ascontiguousarray(t0, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        events = np.ascontiguousarray(events, dtype=np.float64)
+        modes = np.ascontiguousarray(modes, dtype=np.int32)
+        nevents = np.ascontiguousarray(nevents, dtype=np.int32)
+        target_t = np.ascontiguousarray(target_t, dtype=np.float64)
+        target_x = np.ascontiguousarray(target_x, dtype=np.float64)
+        assert events.shape == (B, self.EMAX) and modes.shape == (B, self.EMAX + 1)
+        assert target_t.shape == (B, self.KT) and target_x.shape == (B, self.KT, 37)
+        out = dict(t=np.zeros((B, N)), x=np.zeros((B, N, 30)), u=np.zeros((B, N, 30)), n=np.zeros(B, dtype=np.int32),
+                   mode=np.zeros((B, N), dtype=np.int32), info=np.zeros((B, 16)), status=np.zeros(B, dtype=np.int32))
+        self.lib.cport_mpc_cycle(self.ctx, dp(t0), dp(x0), dp(events), dp(modes), dp(nevents), dp(target_t), dp(target_x),
+                                 dp(out["t"]), dp(out["x"]), dp(out["u"]), dp(out["n"]), dp(out["mode"]), dp(out["info"]),
+                                 dp(out["status"]))
+        return out
+
+
+def pack_schedules(schedules, EMAX):
+    """[(events, modes)] -> padded arrays (events padded with +1e30, modes with STANCE)."""
+    B = len(schedules)
+    ev = np.full((B, EMAX), 1e30)
+    md = np.full((B, EMAX + 1), 15, dtype=np.int32)
+    ne = np.zeros(B, dtype=np.int32)
+    for b, (e, m) in enumerate(schedules):
+        assert len(e) <= EMAX and len(m) == len(e) + 1
+        ev[b, :len(e)] = e
+        md[b, :len(m)] = m
+        ne[b] = len(e)
+    return ev, md, ne

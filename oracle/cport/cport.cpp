@@ -1,0 +1,134 @@
+// CPU port of the MPC hot path (TEST INFRASTRUCTURE / CPU baseline only; see oracle/__init__.py).
+// Host compilation of qm_door_b200/csrc/qm_core.h / qm_mpc.h / qm_buffers.h with the SerialGroup (every
+// bulk-synchronous phase executed by one thread), threaded over independent problems with std::thread.
+// Exposed to ctypes so tests can compare each routine with the NumPy oracle and bench.py can time a CPU
+// baseline ("kind": "port" — not the reference binary, which cannot be built here).
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "../../qm_door_b200/csrc/qm_buffers.h"
+
+using namespace qm;
+
+struct CportCtx {
+  qmb200_model_desc M;
+  qmb200_problem_desc P;
+  qmb200_solver_desc S;
+  MpcBuffers m;
+  int threads;
+};
+
+template <class F>
+static void parallel_for(int n, int threads, F f) {
+  if (threads <= 1 || n <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([=]() { for (int i = t; i < n; i += threads) f(i); });
+  for (auto& th : pool) th.join();
+}
+
+extern "C" {
+
+int cport_kin_ws_size() { return KW_SIZE; }
+int cport_tw_size() { return TW_SIZE; }
+int cport_sizes(int* out) {
+  out[0] = SB_SIZE; out[1] = PB_SIZE; out[2] = GB_SIZE; out[3] = PF_SIZE; out[4] = LS_SIZE; out[5] = TW_SIZE; out[6] = TI_SIZE;
+  return 7;
+}
+
+void cport_kin_eval(const qmb200_model_desc* M, const double* x, const double* u, int deriv, double* w) {
+  kin_eval(SerialGroup(), *M, x, u, deriv != 0, w);
+}
+
+void cport_transcribe_node(const qmb200_model_desc* M, const qmb200_problem_desc* P, double t, double dt, int mode,
+                           const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
+                           const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status) {
+  transcribe_node(SerialGroup(), *M, *P, t, dt, mode, zvel, tt, ts, kt, x, u, xn, W, WI, sb, pb, perf, status);
+}
+
+CportCtx* cport_create(const qmb200_model_desc* M, const qmb200_problem_desc* P, const qmb200_solver_desc* S, int B, int threads) {
+  CportCtx* c = new CportCtx();
+  c->M = *M; c->P = *P; c->S = *S; c->threads = threads;
+  c->m.B = B; c->m.NMAX = S->max_nodes; c->m.EMAX = S->max_events; c->m.KT = S->max_targets;
+  for_each_buffer(c->m, [](void** p, size_t bytes) { *p = calloc(1, bytes); });
+  return c;
+}
+
+void cport_destroy(CportCtx* c) {
+  for_each_buffer(c->m, [](void** p, size_t) { free(*p); });
+  delete c;
+}
+
+void cport_reset(CportCtx* c) { memset(c->m.nprev, 0, sizeof(int32_t) * c->m.B); }
+
+const MpcBuffers* cport_buffers(CportCtx* c) { return &c->m; }
+
+// One MPC cycle for the whole batch. Outputs [B][NMAX][..]; info [B][LS_SIZE].
+int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                    const int32_t* nevents, const double* target_t, const double* target_x, double* t_out, double* x_out,
+                    double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status) {
+  MpcBuffers& m = c->m;
+  const int B = m.B, NMAX = m.NMAX, E = m.EMAX, KT = m.KT;
+  memcpy(m.t0, t0, sizeof(double) * B);
+  memcpy(m.x0, x0, sizeof(double) * B * 30);
+  memcpy(m.events, events, sizeof(double) * B * E);
+  memcpy(m.modes, modes, sizeof(int32_t) * B * (E + 1));
+  memcpy(m.nevents, nevents, sizeof(int32_t) * B);
+  memcpy(m.target_t, target_t, sizeof(double) * B * KT);
+  memcpy(m.target_x, target_x, sizeof(double) * B * KT * QM_NTARGET);
+  const qmb200_model_desc& M = c->M; const qmb200_problem_desc& P = c->P; const qmb200_solver_desc& S = c->S;
+  parallel_for(B, c->threads, [&](int b) {
+    SerialGroup g;
+    std::vector<double> W(TW_SIZE > RW_SIZE ? TW_SIZE : RW_SIZE);
+    std::vector<int> WI(TI_SIZE);
+    const size_t o = (size_t)b * NMAX;
+    build_schedule(S, P, m.t0[b], m.events + (size_t)b * E, m.modes + (size_t)b * (E + 1), m.nevents[b], m.node_t + o,
+                   m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.nn + b, m.status + b);
+    const int nn = m.nn[b], n = nn - 1;
+    for (int cc = 0; cc < 60; ++cc)
+      init_guess_component(M, P, cc, m.x0 + 30 * b, nn, m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o,
+                           m.node_mode + o, m.nprev[b], m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30, m.xs + o * 30, m.us + o * 30);
+    const double* tt = m.target_t + (size_t)b * KT;
+    const double* ts = m.target_x + (size_t)b * KT * QM_NTARGET;
+    for (int k = 0; k <= n; ++k) {
+      double* sb = m.stage + (o + k) * SB_SIZE; double* pb = m.proj + (o + k) * PB_SIZE; double* pf = m.perf_base + (o + k) * PF_SIZE;
+      const double* x = m.xs + (o + k) * 30; const double* u = m.us + (o + k) * 30; const double* xn = m.xs + (o + k + 1) * 30;
+      if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, x, true, W.data(), sb, pf);
+      else if (m.node_flag[o + k] == EV_PRE) event_node(g, x, xn, sb, pb, pf);
+      else transcribe_node(g, M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
+                           x, u, xn, W.data(), WI.data(), sb, pb, pf, m.status + b);
+    }
+    solve_problem(g, m, b, W.data());
+    // filter line search
+    double* ls = m.ls + (size_t)b * LS_SIZE;
+    std::vector<double> xt(30), ut(30), xnt(30);
+    while (ls[LS_DONE] == 0.0) {
+      const double alpha = ls[LS_ALPHA];
+      for (int k = 0; k <= n; ++k) {
+        double* pf = m.perf_trial + (o + k) * PF_SIZE;
+        for (int i = 0; i < 30; ++i) {
+          xt[i] = m.xs[(o + k) * 30 + i] + alpha * m.dxs[(o + k) * 30 + i];
+          ut[i] = m.us[(o + k) * 30 + i] + alpha * m.dus[(o + k) * 30 + i];
+          if (k < n) xnt[i] = m.xs[(o + k + 1) * 30 + i] + alpha * m.dxs[(o + k + 1) * 30 + i];
+        }
+        if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, xt.data(), false, W.data(), nullptr, pf);
+        else if (m.node_flag[o + k] == EV_PRE) {
+          double d = 0.0;
+          for (int i = 0; i < 30; ++i) d += (xt[i] - xnt[i]) * (xt[i] - xnt[i]);
+          pf[PF_COST] = 0.0; pf[PF_DYN] = d; pf[PF_EQ] = 0.0;
+        } else perf_node(g, M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
+                         xt.data(), ut.data(), xnt.data(), W.data(), pf);
+      }
+      decide_problem(S, m, b);
+    }
+    for (int cc = 0; cc < 60; ++cc) finalize_component(m, b, cc, t_out, x_out, u_out);
+    if (n_out) n_out[b] = nn;
+    if (mode_out) for (int k = 0; k < nn; ++k) mode_out[o + k] = m.node_mode[o + k];
+    if (info) memcpy(info + (size_t)b * LS_SIZE, ls, sizeof(double) * LS_SIZE);
+    if (status) status[b] = m.status[b];
+  });
+  return 0;
+}
+
+}  // extern "C"

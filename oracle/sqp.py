@@ -259,18 +259,41 @@ def transcribe_node(prob, t, dt, x, u, xn):
     return dict(A=A, B=B, b=b, cost=cost, C=C, D=D, e=ev, mode=mode, dt=dt)
 
 
+def full_pivot_columns(D):
+    """Pivot columns chosen by Gaussian elimination with full pivoting (Eigen::FullPivLU order)."""
+    T = np.array(D, dtype=float)
+    nc = T.shape[0]
+    piv = []
+    for step in range(nc):
+        sub = np.abs(T[step:, :])
+        r, c = np.unravel_index(int(np.argmax(sub)), sub.shape)
+        r += step
+        assert sub.max() > 1e-12, "constraint Jacobian lost rank"
+        T[[step, r]] = T[[r, step]]
+        piv.append(int(c))
+        T[step + 1:] -= np.outer(T[step + 1:, c] / T[step, c], T[step])
+    return piv
+
+
 def project(node):
-    """[upstream] projectTranscription: du = Pu dut + Px dx + Pe with D Pu = 0, D Px = -C, D Pe = -e.
-    (Any null-space basis / particular solution gives the same (dx, du) optimum; here SVD based.)"""
+    """[upstream] projectTranscription with luConstraintProjection: du = Pu dut + Px dx + Pe,
+    D Pu = 0, D Px = -C, D Pe = -e.  Eigen::FullPivLU semantics: kernel() = [-Dp^-1 Df; I] on the
+    non-pivot columns, solve() = particular solution with the non-pivot variables at zero."""
     C, D, e = node["C"], node["D"], node["e"]
-    nc = D.shape[0]
-    U, s, Vt = np.linalg.svd(D)
-    assert s[-1] > 1e-9 * s[0], "constraint Jacobian lost rank"
-    Pu = Vt[nc:].T
-    Dp = np.linalg.pinv(D)
-    Px, Pe = -Dp @ C, -Dp @ e
+    nu = D.shape[1]
+    piv = full_pivot_columns(D)
+    free = [i for i in range(nu) if i not in piv]
+    Dp = D[:, piv]
+    Pu = np.zeros((nu, len(free)))
+    Px = np.zeros((nu, C.shape[1]))
+    Pe = np.zeros(nu)
+    Pu[free, np.arange(len(free))] = 1.0
+    Pu[piv, :] = -np.linalg.solve(Dp, D[:, free])
+    Px[piv, :] = -np.linalg.solve(Dp, C)
+    Pe[piv] = -np.linalg.solve(Dp, e)
+    out_extra = dict(piv=piv, free=free)
     A, B, b, c = node["A"], node["B"], node["b"], node["cost"]
-    out = dict(Pu=Pu, Px=Px, Pe=Pe, nut=Pu.shape[1])
+    out = dict(Pu=Pu, Px=Px, Pe=Pe, nut=Pu.shape[1], **out_extra)
     out["A"] = A + B @ Px
     out["B"] = B @ Pu
     out["b"] = b + B @ Pe

@@ -1,0 +1,201 @@
+// Batch buffers of the MPC cycle. The same layout is used in HBM by the CUDA path and on the heap by the CPU port.
+// Node axis has capacity NMAX per problem; all per-node arrays are [B][NMAX][...] row-major.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "qm_mpc.h"
+
+namespace qm {
+
+// per-problem line-search / summary record (doubles)
+enum {
+  LS_ALPHA = 0,      // step size being tried / accepted (0 if rejected)
+  LS_DONE = 1,       // 0 pending, 1 accepted, 2 rejected (no step)
+  LS_ARMIJO = 2,
+  LS_DXNORM = 3,
+  LS_DUNORM = 4,
+  LS_BASE_MERIT = 5, LS_BASE_DYN = 6, LS_BASE_EQ = 7,
+  LS_NEW_MERIT = 8, LS_NEW_DYN = 9, LS_NEW_EQ = 10,
+  LS_ITERS = 11,
+  LS_DX0SQ = 12,     // |x0 - xs[0]|^2
+  LS_SIZE = 16
+};
+
+struct MpcBuffers {
+  int B, NMAX, EMAX, KT;
+  // inputs (per cycle)
+  double* t0;          // [B]
+  double* x0;          // [B][30]
+  double* events;      // [B][EMAX]
+  int32_t* modes;      // [B][EMAX+1]
+  int32_t* nevents;    // [B]
+  double* target_t;    // [B][KT]
+  double* target_x;    // [B][KT][37]
+  // schedule
+  double* node_t;      // [B][NMAX] annotated node time
+  double* node_ts;     // [B][NMAX] interval start (post-event nodes shifted by weak_eps) = interpolation time
+  double* node_dt;     // [B][NMAX]
+  double* node_zvel;   // [B][NMAX][4]
+  int32_t* node_flag;  // [B][NMAX]
+  int32_t* node_mode;  // [B][NMAX]
+  int32_t* nn;         // [B] number of nodes
+  int32_t* status;     // [B]
+  // iterate and step
+  double* xs;          // [B][NMAX][30]
+  double* us;          // [B][NMAX][30]
+  double* dxs;         // [B][NMAX][30]
+  double* dus;         // [B][NMAX][30]
+  // LQ blocks
+  double* stage;       // [B][NMAX][SB_SIZE]
+  double* proj;        // [B][NMAX][PB_SIZE]
+  double* gain;        // [B][NMAX][GB_SIZE]
+  double* perf_base;   // [B][NMAX][PF_SIZE]
+  double* perf_trial;  // [B][NMAX][PF_SIZE]
+  double* ls;          // [B][LS_SIZE]
+  // warm start (previous primal solution, [upstream] PrimalSolution)
+  double* prev_t;      // [B][NMAX]
+  double* prev_x;      // [B][NMAX][30]
+  double* prev_u;      // [B][NMAX][30]
+  int32_t* nprev;      // [B]
+};
+
+template <class F>
+inline void for_each_buffer(MpcBuffers& m, F f) {
+  const size_t B = m.B, N = m.NMAX, E = m.EMAX, K = m.KT;
+  f((void**)&m.t0, B * sizeof(double));
+  f((void**)&m.x0, B * 30 * sizeof(double));
+  f((void**)&m.events, B * E * sizeof(double));
+  f((void**)&m.modes, B * (E + 1) * sizeof(int32_t));
+  f((void**)&m.nevents, B * sizeof(int32_t));
+  f((void**)&m.target_t, B * K * sizeof(double));
+  f((void**)&m.target_x, B * K * QM_NTARGET * sizeof(double));
+  f((void**)&m.node_t, B * N * sizeof(double));
+  f((void**)&m.node_ts, B * N * sizeof(double));
+  f((void**)&m.node_dt, B * N * sizeof(double));
+  f((void**)&m.node_zvel, B * N * 4 * sizeof(double));
+  f((void**)&m.node_flag, B * N * sizeof(int32_t));
+  f((void**)&m.node_mode, B * N * sizeof(int32_t));
+  f((void**)&m.nn, B * sizeof(int32_t));
+  f((void**)&m.status, B * sizeof(int32_t));
+  f((void**)&m.xs, B * N * 30 * sizeof(double));
+  f((void**)&m.us, B * N * 30 * sizeof(double));
+  f((void**)&m.dxs, B * N * 30 * sizeof(double));
+  f((void**)&m.dus, B * N * 30 * sizeof(double));
+  f((void**)&m.stage, B * N * SB_SIZE * sizeof(double));
+  f((void**)&m.proj, B * N * PB_SIZE * sizeof(double));
+  f((void**)&m.gain, B * N * GB_SIZE * sizeof(double));
+  f((void**)&m.perf_base, B * N * PF_SIZE * sizeof(double));
+  f((void**)&m.perf_trial, B * N * PF_SIZE * sizeof(double));
+  f((void**)&m.ls, B * LS_SIZE * sizeof(double));
+  f((void**)&m.prev_t, B * N * sizeof(double));
+  f((void**)&m.prev_x, B * N * 30 * sizeof(double));
+  f((void**)&m.prev_u, B * N * 30 * sizeof(double));
+  f((void**)&m.nprev, B * sizeof(int32_t));
+}
+
+// ---- per-problem steps that are serial in the node axis (one group per problem)
+
+// Backward Riccati sweep, forward rollout, step norms, baseline performance reduction. W >= RW_SIZE doubles.
+template <class G>
+QM_HDN void solve_problem(G g, const MpcBuffers& m, int b, double* W) {
+  const int NMAX = m.NMAX;
+  const int nn = m.nn[b];
+  const int n = nn - 1;
+  const double* stage = m.stage + (size_t)b * NMAX * SB_SIZE;
+  const double* proj = m.proj + (size_t)b * NMAX * PB_SIZE;
+  double* gain = m.gain + (size_t)b * NMAX * GB_SIZE;
+  double* dxs = m.dxs + (size_t)b * NMAX * 30;
+  double* dus = m.dus + (size_t)b * NMAX * 30;
+  const double* term = stage + (size_t)n * SB_SIZE;
+  QM_PFOR(g, idx, 900) W[RW_S + idx] = term[SB_Q + idx];
+  QM_PFOR(g, i, 30) W[RW_sv + i] = term[SB_q + i];
+  g.sync();
+  for (int k = n - 1; k >= 0; --k) riccati_stage(g, stage + (size_t)k * SB_SIZE, W, gain + (size_t)k * GB_SIZE, m.status + b);
+  // forward rollout
+  double* R = W;   // reuse: [0:30] dx, [30:60] dx next, [60:78] dut, [80] armijo
+  QM_PFOR(g, i, 30) { R[i] = m.x0[30 * b + i] - m.xs[((size_t)b * NMAX) * 30 + i]; }
+  if (g.tid() == 0) R[80] = 0.0;
+  g.sync();
+  for (int k = 0; k < n; ++k) {
+    QM_PFOR(g, i, 30) dxs[30 * k + i] = R[i];
+    rollout_stage(g, stage + (size_t)k * SB_SIZE, proj + (size_t)k * PB_SIZE, gain + (size_t)k * GB_SIZE, R, dus + 30 * k);
+    QM_PFOR(g, i, 30) R[i] = R[30 + i];
+    g.sync();
+  }
+  QM_PFOR(g, i, 30) { dxs[30 * n + i] = R[i]; dus[30 * n + i] = 0.0; }
+  g.sync();
+  if (g.tid() == 0) {
+    double arm = R[80];
+    for (int j = 0; j < 30; ++j) arm += term[SB_q + j] * R[j];
+    double sx = 0.0, su = 0.0;
+    for (int k = 0; k <= n; ++k)
+      for (int i = 0; i < 30; ++i) { sx += dxs[30 * k + i] * dxs[30 * k + i]; su += dus[30 * k + i] * dus[30 * k + i]; }
+    double d0 = 0.0;
+    for (int i = 0; i < 30; ++i) d0 += dxs[i] * dxs[i];
+    const double* pf = m.perf_base + (size_t)b * NMAX * PF_SIZE;
+    double c = 0.0, dy = d0, eq = 0.0;
+    for (int k = 0; k <= n; ++k) { c += pf[PF_SIZE * k + PF_COST]; dy += pf[PF_SIZE * k + PF_DYN]; eq += pf[PF_SIZE * k + PF_EQ]; }
+    double* ls = m.ls + (size_t)b * LS_SIZE;
+    ls[LS_ALPHA] = 1.0; ls[LS_DONE] = 0.0; ls[LS_ARMIJO] = arm; ls[LS_DXNORM] = sqrt(sx); ls[LS_DUNORM] = sqrt(su);
+    ls[LS_BASE_MERIT] = c; ls[LS_BASE_DYN] = dy; ls[LS_BASE_EQ] = eq; ls[LS_ITERS] = 0.0; ls[LS_DX0SQ] = d0;
+    ls[LS_NEW_MERIT] = c; ls[LS_NEW_DYN] = dy; ls[LS_NEW_EQ] = eq;
+  }
+  g.sync();
+}
+
+// Line-search decision for one problem (one thread). [upstream] SqpSolver::takeStep loop body.
+QM_HDN void decide_problem(const qmb200_solver_desc& S, const MpcBuffers& m, int b) {
+  double* ls = m.ls + (size_t)b * LS_SIZE;
+  if (ls[LS_DONE] != 0.0) return;
+  const int nn = m.nn[b];
+  const double alpha = ls[LS_ALPHA];
+  const double* pf = m.perf_trial + (size_t)b * m.NMAX * PF_SIZE;
+  double c = 0.0, dy = (1.0 - alpha) * (1.0 - alpha) * ls[LS_DX0SQ], eq = 0.0;
+  for (int k = 0; k < nn; ++k) { c += pf[PF_SIZE * k + PF_COST]; dy += pf[PF_SIZE * k + PF_DYN]; eq += pf[PF_SIZE * k + PF_EQ]; }
+  ls[LS_ITERS] += 1.0;
+  const double vb = sqrt(ls[LS_BASE_DYN] + ls[LS_BASE_EQ]), vn = sqrt(dy + eq);
+  bool nan = !(c == c) || !(vn == vn);
+  if (!nan && accept_step(S, ls[LS_BASE_MERIT], vb, c, vn, alpha * ls[LS_ARMIJO])) {
+    ls[LS_DONE] = 1.0; ls[LS_NEW_MERIT] = c; ls[LS_NEW_DYN] = dy; ls[LS_NEW_EQ] = eq;
+    return;
+  }
+  if (nan) m.status[b] |= ST_NAN;
+  const double a2 = alpha * S.alpha_decay;
+  if ((a2 * ls[LS_DXNORM] < S.delta_tol && a2 * ls[LS_DUNORM] < S.delta_tol) || a2 < S.alpha_min) {
+    ls[LS_DONE] = 2.0; ls[LS_ALPHA] = 0.0; m.status[b] |= ST_STEP_REJECTED;
+    return;
+  }
+  ls[LS_ALPHA] = a2;
+}
+
+// Accept the step and publish the primal solution ([upstream] toPrimalSolution); one thread per (problem, component c<60).
+QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out, double* x_out, double* u_out) {
+  const int NMAX = m.NMAX, nn = m.nn[b];
+  const double alpha = m.ls[(size_t)b * LS_SIZE + LS_ALPHA];
+  const size_t o = (size_t)b * NMAX;
+  if (c < 30) {
+    for (int k = 0; k < nn; ++k) {
+      const double v = m.xs[(o + k) * 30 + c] + alpha * m.dxs[(o + k) * 30 + c];
+      m.xs[(o + k) * 30 + c] = v; m.prev_x[(o + k) * 30 + c] = v;
+      if (x_out) x_out[(o + k) * 30 + c] = v;
+    }
+    if (c == 0) {
+      for (int k = 0; k < nn; ++k) { m.prev_t[o + k] = m.node_ts[o + k]; if (t_out) t_out[o + k] = m.node_ts[o + k]; }
+      m.nprev[b] = nn;
+    }
+  } else {
+    const int cu = c - 30;
+    double last = 0.0;
+    for (int k = 0; k < nn; ++k) {
+      double v;
+      if (k == nn - 1) v = last;                                   // repeat the last input
+      else if (m.node_flag[o + k] == EV_PRE && k > 0) v = last;    // pre-event node repeats the previous input
+      else v = m.us[(o + k) * 30 + cu] + alpha * m.dus[(o + k) * 30 + cu];
+      m.us[(o + k) * 30 + cu] = v; m.prev_u[(o + k) * 30 + cu] = v;
+      if (u_out) u_out[(o + k) * 30 + cu] = v;
+      last = v;
+    }
+  }
+}
+
+}  // namespace qm

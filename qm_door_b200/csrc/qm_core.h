@@ -1,0 +1,380 @@
+// Per-node numerics of the MPC hot path, written once as bulk-synchronous phases over a thread group.
+//   BlockGroup : all threads of a CTA, phases separated by __syncthreads()   (transcription, Riccati)
+//   WarpGroup  : one warp, phases separated by __syncwarp()                  (line-search evaluation)
+//   SerialGroup: one host thread executing every phase's iterations in order (CPU port / unit tests)
+// Communication between phases goes through the workspace arrays only (shared memory on the device),
+// so the same source is the CUDA kernel body and its scalar CPU restatement.
+//
+// Reference computations replaced (relative to /root/reference):
+//   kin_eval            QMPreComputation::request                qm_interface/src/QMPreComputation.cpp:73-88
+//   flow_rows           QMDynamicsAD::linearApproximation        qm_interface/src/dynamics/QMDynamicsAD.cpp:22-33
+//   constraint rows     NormalVelocityConstraintCppAd / zero velocity / zero force
+//                       qm_interface/src/constraint/NormalVelocityConstraintCppAd.cpp:37-66, QMInterface.cpp:116-131,324-339
+//   ee terms            EndEffectorConstraint                    qm_interface/src/constraint/EndEffectorConstraint.cpp:36-113
+//   cost                LeggedRobotStateInputQuadraticCost       qm_interface/include/qm_interface/cost/LeggedRobotQuadraticTrackingCost.h:34-40
+//   barriers            QMInterface.cpp:177-259 (arm limits), :344-358 (friction cone)
+//   RK2 / projection / Riccati / line search: [upstream] ocs2_sqp, driven from QMController.cpp:288-289,323
+#pragma once
+#include <math.h>
+#include "qm_types.h"
+
+#if defined(__CUDACC__)
+#define QM_HD __host__ __device__ __forceinline__
+#define QM_HDN __host__ __device__
+#else
+#define QM_HD inline
+#define QM_HDN inline
+#endif
+
+namespace qm {
+
+// ------------------------------------------------------------------------------------------ groups
+struct SerialGroup {
+  QM_HD int tid() const { return 0; }
+  QM_HD int nt() const { return 1; }
+  QM_HD void sync() const {}
+};
+#if defined(__CUDACC__)
+struct BlockGroup {
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int nt() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct WarpGroup {
+  __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int nt() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+#endif
+#define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())
+
+// ------------------------------------------------------------------------------------------ small vector helpers
+QM_HD void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+QM_HD void cross3_add(const double* a, const double* b, double* c) {
+  c[0] += a[1] * b[2] - a[2] * b[1];
+  c[1] += a[2] * b[0] - a[0] * b[2];
+  c[2] += a[0] * b[1] - a[1] * b[0];
+}
+// symmetric 3x3 stored as (xx, xy, xz, yy, yz, zz) times vector
+QM_HD void sym3_mul(const double* s, const double* v, double* o) {
+  o[0] = s[0] * v[0] + s[1] * v[1] + s[2] * v[2];
+  o[1] = s[1] * v[0] + s[3] * v[1] + s[4] * v[2];
+  o[2] = s[2] * v[0] + s[4] * v[1] + s[5] * v[2];
+}
+
+// ------------------------------------------------------------------------------------------ kinematics workspace
+// Offsets (in doubles) into the kinematics workspace.
+enum {
+  KW_R = 0,                          // [24][9]  world rotation of joint frames
+  KW_P = KW_R + QM_NJ * 9,           // [24][3]  world origin of joint frames
+  KW_AX = KW_P + QM_NJ * 3,          // [24][3]  world joint axis
+  KW_BODY = KW_AX + QM_NJ * 3,       // [24][10] per body: m, m*c[3], I0[6] (rot. inertia about world origin)
+  KW_COMP = KW_BODY + QM_NJ * 10,    // [24][10] same, summed over the subtree of each joint
+  KW_ACM = KW_COMP + QM_NJ * 10,     // [6][24]  centroidal momentum matrix
+  KW_SV = KW_ACM + 6 * QM_NJ,        // [24][6]  S_j v_j  -> reused for subtree momenta
+  KW_V = KW_SV + QM_NJ * 6,          // [24][6]  spatial velocity (w, vO) of each body, world origin
+  KW_HB = KW_V + QM_NJ * 6,          // [24][6]  body momentum (L0, p)
+  KW_DH = KW_HB + QM_NJ * 6,         // [6][24]  d(A v)/dq at fixed v (centroidal)
+  KW_FPOS = KW_DH + 6 * QM_NJ,       // [4][3]
+  KW_FVEL = KW_FPOS + 12,            // [4][3]
+  KW_FJ = KW_FVEL + 12,              // [4][3][24] foot linear Jacobians
+  KW_DFV = KW_FJ + 12 * QM_NJ,       // [4][3][24] d(J_i v)/dq at fixed v
+  KW_EEP = KW_DFV + 12 * QM_NJ,      // [3]
+  KW_EER = KW_EEP + 3,               // [9]
+  KW_EEJ = KW_EER + 9,               // [6][24] ee Jacobian [linear; angular]
+  KW_COM = KW_EEJ + 6 * QM_NJ,       // [3]
+  KW_ABINV = KW_COM + 3,             // [36]
+  KW_VEL = KW_ABINV + 36,            // [24] generalized velocity
+  KW_RHS = KW_VEL + QM_NJ,           // [6]
+  KW_SIZE = KW_RHS + 6 + 2
+};
+
+// spatial motion vector of joint j (world coordinates, reference point = world origin): (w, vO)
+QM_HD void joint_S(const qmb200_model_desc& M, const double* w, int j, double* S) {
+  const double* a = w + KW_AX + 3 * j;
+  if (M.jtype[j] == 1) {
+    S[0] = a[0]; S[1] = a[1]; S[2] = a[2];
+    cross3(w + KW_P + 3 * j, a, S + 3);
+  } else {
+    S[0] = S[1] = S[2] = 0.0;
+    S[3] = a[0]; S[4] = a[1]; S[5] = a[2];
+  }
+}
+// momentum (L0, p) of inertia (m, h=m*c, I0) moving with (w, vO)
+QM_HD void inertia_mul(const double* I, const double* V, double* h) {
+  double t[3];
+  sym3_mul(I + 4, V, h);              // I0 w
+  cross3_add(I + 1, V + 3, h);        // + h x vO
+  cross3(V, I + 1, t);                // w x h
+  h[3] = I[0] * V[3] + t[0];
+  h[4] = I[0] * V[4] + t[1];
+  h[5] = I[0] * V[5] + t[2];
+}
+
+// Forward kinematics + centroidal quantities of one configuration, optionally with the generalized
+// velocity implied by (x,u) and the q-derivatives at fixed velocity needed for the linearisation.
+//   q = x[6:30];   u != nullptr -> velocity level;   deriv -> KW_DH / KW_DFV as well
+template <class G>
+QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, bool deriv, double* w) {
+  const double* q = x + 6;
+  // P1: placements, level by level
+  for (int d = 0; d <= M.max_depth; ++d) {
+    QM_PFOR(g, j, QM_NJ) {
+      if (M.depth[j] != d) continue;
+      double Rpar[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ppar[3] = {0, 0, 0};
+      const int par = M.parent[j];
+      if (par >= 0) {
+        for (int k = 0; k < 9; ++k) Rpar[k] = w[KW_R + 9 * par + k];
+        for (int k = 0; k < 3; ++k) ppar[k] = w[KW_P + 3 * par + k];
+      }
+      double R0[9], p0[3], aw[3];
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c)
+          R0[3 * r + c] = Rpar[3 * r] * M.Rp[j][c] + Rpar[3 * r + 1] * M.Rp[j][3 + c] + Rpar[3 * r + 2] * M.Rp[j][6 + c];
+        p0[r] = ppar[r] + Rpar[3 * r] * M.pp[j][0] + Rpar[3 * r + 1] * M.pp[j][1] + Rpar[3 * r + 2] * M.pp[j][2];
+      }
+      const double ax = M.axis[j][0], ay = M.axis[j][1], az = M.axis[j][2];
+      for (int r = 0; r < 3; ++r) aw[r] = R0[3 * r] * ax + R0[3 * r + 1] * ay + R0[3 * r + 2] * az;
+      double* Rj = w + KW_R + 9 * j;
+      double* pj = w + KW_P + 3 * j;
+      if (M.jtype[j] == 1) {
+        double s, c;
+        sincos(q[j], &s, &c);
+        const double v = 1.0 - c;
+        // Rodrigues: I + s K + (1-c) K^2, K = skew(axis)
+        const double Rq[9] = {c + v * ax * ax,      v * ax * ay - s * az, v * ax * az + s * ay,
+                              v * ax * ay + s * az, c + v * ay * ay,      v * ay * az - s * ax,
+                              v * ax * az - s * ay, v * ay * az + s * ax, c + v * az * az};
+        for (int r = 0; r < 3; ++r)
+          for (int cc = 0; cc < 3; ++cc)
+            Rj[3 * r + cc] = R0[3 * r] * Rq[cc] + R0[3 * r + 1] * Rq[3 + cc] + R0[3 * r + 2] * Rq[6 + cc];
+        for (int r = 0; r < 3; ++r) pj[r] = p0[r];
+      } else {
+        for (int k = 0; k < 9; ++k) Rj[k] = R0[k];
+        for (int r = 0; r < 3; ++r) pj[r] = p0[r] + aw[r] * q[j];
+      }
+      for (int r = 0; r < 3; ++r) w[KW_AX + 3 * j + r] = aw[r];
+    }
+    g.sync();
+  }
+  // P2: body inertial quantities about the world origin
+  QM_PFOR(g, j, QM_NJ) {
+    const double* R = w + KW_R + 9 * j;
+    const double m = M.mass[j];
+    double c[3];
+    for (int r = 0; r < 3; ++r)
+      c[r] = w[KW_P + 3 * j + r] + R[3 * r] * M.com[j][0] + R[3 * r + 1] * M.com[j][1] + R[3 * r + 2] * M.com[j][2];
+    double RI[9];
+    for (int r = 0; r < 3; ++r)
+      for (int cc = 0; cc < 3; ++cc)
+        RI[3 * r + cc] = R[3 * r] * M.inertia[j][cc] + R[3 * r + 1] * M.inertia[j][3 + cc] + R[3 * r + 2] * M.inertia[j][6 + cc];
+    double Iw[9];
+    for (int r = 0; r < 3; ++r)
+      for (int cc = 0; cc < 3; ++cc)
+        Iw[3 * r + cc] = RI[3 * r] * R[3 * cc] + RI[3 * r + 1] * R[3 * cc + 1] + RI[3 * r + 2] * R[3 * cc + 2];
+    const double cc2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+    double* b = w + KW_BODY + 10 * j;
+    b[0] = m; b[1] = m * c[0]; b[2] = m * c[1]; b[3] = m * c[2];
+    b[4] = Iw[0] + m * (cc2 - c[0] * c[0]);
+    b[5] = Iw[1] - m * c[0] * c[1];
+    b[6] = Iw[2] - m * c[0] * c[2];
+    b[7] = Iw[4] + m * (cc2 - c[1] * c[1]);
+    b[8] = Iw[5] - m * c[1] * c[2];
+    b[9] = Iw[8] + m * (cc2 - c[2] * c[2]);
+  }
+  // frame positions (independent of the body phase)
+  QM_PFOR(g, f, QM_NFEET + 1) {
+    if (f < QM_NFEET) {
+      const int b = M.foot_joint[f];
+      const double* R = w + KW_R + 9 * b;
+      for (int r = 0; r < 3; ++r)
+        w[KW_FPOS + 3 * f + r] = w[KW_P + 3 * b + r] + R[3 * r] * M.foot_off[f][0] + R[3 * r + 1] * M.foot_off[f][1] + R[3 * r + 2] * M.foot_off[f][2];
+    } else {
+      const int b = M.ee_joint;
+      const double* R = w + KW_R + 9 * b;
+      for (int r = 0; r < 3; ++r) {
+        w[KW_EEP + r] = w[KW_P + 3 * b + r] + R[3 * r] * M.ee_off[0] + R[3 * r + 1] * M.ee_off[1] + R[3 * r + 2] * M.ee_off[2];
+        for (int c = 0; c < 3; ++c)
+          w[KW_EER + 3 * r + c] = R[3 * r] * M.ee_Roff[c] + R[3 * r + 1] * M.ee_Roff[3 + c] + R[3 * r + 2] * M.ee_Roff[6 + c];
+      }
+    }
+  }
+  g.sync();
+  // P3: composite (subtree) inertias
+  QM_PFOR(g, j, QM_NJ) {
+    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t mask = M.submask[j];
+    for (int i = 0; i < QM_NJ; ++i)
+      if ((mask >> i) & 1u)
+        for (int k = 0; k < 10; ++k) acc[k] += w[KW_BODY + 10 * i + k];
+    for (int k = 0; k < 10; ++k) w[KW_COMP + 10 * j + k] = acc[k];
+    if (j == 0)
+      for (int r = 0; r < 3; ++r) w[KW_COM + r] = acc[1 + r] / acc[0];
+  }
+  g.sync();
+  // P4: centroidal momentum matrix columns, frame Jacobian columns
+  QM_PFOR(g, j, QM_NJ) {
+    double S[6], h[6], t[3];
+    joint_S(M, w, j, S);
+    inertia_mul(w + KW_COMP + 10 * j, S, h);
+    cross3(w + KW_COM, h + 3, t);
+    w[KW_ACM + 0 * QM_NJ + j] = h[3];
+    w[KW_ACM + 1 * QM_NJ + j] = h[4];
+    w[KW_ACM + 2 * QM_NJ + j] = h[5];
+    w[KW_ACM + 3 * QM_NJ + j] = h[0] - t[0];
+    w[KW_ACM + 4 * QM_NJ + j] = h[1] - t[1];
+    w[KW_ACM + 5 * QM_NJ + j] = h[2] - t[2];
+    for (int f = 0; f < QM_NFEET + 1; ++f) {
+      const int b = (f < QM_NFEET) ? M.foot_joint[f] : M.ee_joint;
+      const double* pos = (f < QM_NFEET) ? (w + KW_FPOS + 3 * f) : (w + KW_EEP);
+      double col[3] = {0, 0, 0}, ang[3] = {0, 0, 0};
+      if ((M.pathmask[b] >> j) & 1u) {
+        // velocity of the frame origin per unit joint rate: vO + w x pos
+        cross3(S, pos, col);
+        col[0] += S[3]; col[1] += S[4]; col[2] += S[5];
+        ang[0] = S[0]; ang[1] = S[1]; ang[2] = S[2];
+      }
+      if (f < QM_NFEET) {
+        for (int r = 0; r < 3; ++r) w[KW_FJ + (3 * f + r) * QM_NJ + j] = col[r];
+      } else {
+        for (int r = 0; r < 3; ++r) {
+          w[KW_EEJ + r * QM_NJ + j] = col[r];
+          w[KW_EEJ + (3 + r) * QM_NJ + j] = ang[r];
+        }
+      }
+    }
+  }
+  g.sync();
+  if (u == nullptr) return;
+  // P6: generalized velocity  v = [Ab^-1 (m h_n - A_j v_j); v_j]   ([upstream] getPinocchioJointVelocity)
+  QM_PFOR(g, r, 6) {
+    double acc = M.total_mass * x[r];
+    for (int l = 0; l < 18; ++l) acc -= w[KW_ACM + r * QM_NJ + 6 + l] * u[12 + l];
+    w[KW_RHS + r] = acc;
+  }
+  QM_PFOR(g, l, 18) w[KW_VEL + 6 + l] = u[12 + l];
+  if (g.tid() == 0) {
+    // [upstream] computeFloatingBaseCentroidalMomentumMatrixInverse: Ab = [m I, Ab12; 0, Ab22]
+    const double* A = w + KW_ACM;
+    const double mass = A[0];
+    const double a = A[3 * QM_NJ + 3], b = A[3 * QM_NJ + 4], c = A[3 * QM_NJ + 5];
+    const double d = A[4 * QM_NJ + 3], e = A[4 * QM_NJ + 4], f = A[4 * QM_NJ + 5];
+    const double gg = A[5 * QM_NJ + 3], hh = A[5 * QM_NJ + 4], ii = A[5 * QM_NJ + 5];
+    const double det = a * (e * ii - f * hh) - b * (d * ii - f * gg) + c * (d * hh - e * gg);
+    const double id = 1.0 / det;
+    const double inv[9] = {(e * ii - f * hh) * id, (c * hh - b * ii) * id, (b * f - c * e) * id,
+                           (f * gg - d * ii) * id, (a * ii - c * gg) * id, (c * d - a * f) * id,
+                           (d * hh - e * gg) * id, (b * gg - a * hh) * id, (a * e - b * d) * id};
+    double* Bi = w + KW_ABINV;
+    for (int k = 0; k < 36; ++k) Bi[k] = 0.0;
+    for (int r = 0; r < 3; ++r) {
+      Bi[6 * r + r] = 1.0 / mass;
+      for (int cc = 0; cc < 3; ++cc) {
+        Bi[6 * (3 + r) + 3 + cc] = inv[3 * r + cc];
+        double acc = 0.0;
+        for (int k = 0; k < 3; ++k) acc += A[r * QM_NJ + 3 + k] * inv[3 * k + cc];
+        Bi[6 * r + 3 + cc] = -acc / mass;
+      }
+    }
+  }
+  g.sync();
+  QM_PFOR(g, r, 6) {
+    double acc = 0.0;
+    for (int c = 0; c < 6; ++c) acc += w[KW_ABINV + 6 * r + c] * w[KW_RHS + c];
+    w[KW_VEL + r] = acc;
+  }
+  g.sync();
+  // P7: spatial velocities and body momenta
+  QM_PFOR(g, j, QM_NJ) {
+    double S[6];
+    joint_S(M, w, j, S);
+    const double vj = w[KW_VEL + j];
+    for (int k = 0; k < 6; ++k) w[KW_SV + 6 * j + k] = S[k] * vj;
+  }
+  g.sync();
+  QM_PFOR(g, j, QM_NJ) {
+    double V[6] = {0, 0, 0, 0, 0, 0};
+    const uint32_t mask = M.pathmask[j];
+    for (int k = 0; k < QM_NJ; ++k)
+      if ((mask >> k) & 1u)
+        for (int c = 0; c < 6; ++c) V[c] += w[KW_SV + 6 * k + c];
+    for (int c = 0; c < 6; ++c) w[KW_V + 6 * j + c] = V[c];
+    inertia_mul(w + KW_BODY + 10 * j, V, w + KW_HB + 6 * j);
+  }
+  g.sync();
+  // foot velocities
+  QM_PFOR(g, f, QM_NFEET) {
+    const double* V = w + KW_V + 6 * M.foot_joint[f];
+    double t[3];
+    cross3(V, w + KW_FPOS + 3 * f, t);
+    for (int r = 0; r < 3; ++r) w[KW_FVEL + 3 * f + r] = V[3 + r] + t[r];
+  }
+  if (!deriv) {
+    g.sync();
+    return;
+  }
+  // P8: subtree momenta (into KW_SV)
+  g.sync();
+  QM_PFOR(g, j, QM_NJ) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const uint32_t mask = M.submask[j];
+    for (int i = 0; i < QM_NJ; ++i)
+      if ((mask >> i) & 1u)
+        for (int c = 0; c < 6; ++c) acc[c] += w[KW_HB + 6 * i + c];
+    for (int c = 0; c < 6; ++c) w[KW_SV + 6 * j + c] = acc[c];
+  }
+  g.sync();
+  // P9: d(A v)/dq_k and d(J_i v)/dq_k at fixed generalized velocity
+  QM_PFOR(g, k, QM_NJ) {
+    double S[6], X[6], IX[6], dL[3], dp[3], t[3];
+    joint_S(M, w, k, S);
+    const double* Vk = w + KW_V + 6 * k;
+    const double* H = w + KW_SV + 6 * k;       // (L0, p) of the subtree
+    // X = S x V_k (motion cross product)
+    cross3(S, Vk, X);
+    cross3(S, Vk + 3, X + 3);
+    cross3_add(S + 3, Vk, X + 3);
+    inertia_mul(w + KW_COMP + 10 * k, X, IX);
+    // S x* H : (w x L0 + vO x p ; w x p)
+    cross3(S, H, dL);
+    cross3_add(S + 3, H + 3, dL);
+    cross3(S, H + 3, dp);
+    for (int r = 0; r < 3; ++r) { dL[r] -= IX[r]; dp[r] -= IX[3 + r]; }
+    // to the centroidal frame: L = L0 - c x p
+    const double* ptot = w + KW_SV + 3;        // linear momentum of the whole tree (joint 0 subtree)
+    double dc[3];
+    for (int r = 0; r < 3; ++r) dc[r] = w[KW_ACM + r * QM_NJ + k] / M.total_mass;
+    cross3(dc, ptot, t);
+    double t2[3];
+    cross3(w + KW_COM, dp, t2);
+    for (int r = 0; r < 3; ++r) {
+      w[KW_DH + r * QM_NJ + k] = dp[r];
+      w[KW_DH + (3 + r) * QM_NJ + k] = dL[r] - t[r] - t2[r];
+    }
+    for (int f = 0; f < QM_NFEET; ++f) {
+      const int b = M.foot_joint[f];
+      double du[3] = {0, 0, 0};
+      if ((M.pathmask[b] >> k) & 1u) {
+        const double* Vb = w + KW_V + 6 * b;
+        double D[6], Y[6];
+        for (int c = 0; c < 6; ++c) D[c] = Vb[c] - Vk[c];
+        cross3(S, D, Y);
+        cross3(S, D + 3, Y + 3);
+        cross3_add(S + 3, D, Y + 3);
+        const double* pos = w + KW_FPOS + 3 * f;
+        double dpos[3] = {w[KW_FJ + (3 * f) * QM_NJ + k], w[KW_FJ + (3 * f + 1) * QM_NJ + k], w[KW_FJ + (3 * f + 2) * QM_NJ + k]};
+        cross3(Y, pos, du);
+        cross3_add(Vb, dpos, du);
+        du[0] += Y[3]; du[1] += Y[4]; du[2] += Y[5];
+      }
+      for (int r = 0; r < 3; ++r) w[KW_DFV + (3 * f + r) * QM_NJ + k] = du[r];
+    }
+  }
+  g.sync();
+}
+
+}  // namespace qm

@@ -1,0 +1,75 @@
+// POD descriptors shared by the host library, the CUDA kernels and the C-ABI (include/qmb200.h).
+// Layouts follow SURVEY.md App. A: state x[30] = [normalized momentum(6); base pos(3); ZYX Euler(3); joints(18)],
+// input u[30] = [contact forces LF,RF,LH,RH (12); joint velocities (18)].
+#pragma once
+#include <stdint.h>
+
+#define QM_NX 30
+#define QM_NU 30
+#define QM_NJ 24          // one-DoF joints: 3 prismatic + 3 revolute (ZYX Euler root) + 18 actuated
+#define QM_NFEET 4
+#define QM_NUT 18         // max reduced input dimension after projection (14 + #stance feet)
+#define QM_NCV 12         // max velocity-constraint rows (3*#stance + #swing)
+#define QM_NTARGET 37     // target knot: [x_ref(30); ee position(3); ee quaternion xyzw(4)]
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// Rigid-body tree. Replaces the pinocchio::Model built at qm_interface/src/QMInterface.cpp:408-416.
+typedef struct qmb200_model_desc {
+  int32_t nj;
+  int32_t parent[QM_NJ];     // -1 = world
+  int32_t jtype[QM_NJ];      // 0 prismatic, 1 revolute
+  int32_t depth[QM_NJ];
+  uint32_t submask[QM_NJ];   // bit i set  <=> body i lies in the subtree of joint j (j included)
+  uint32_t pathmask[QM_NJ];  // bit k set  <=> joint k is an ancestor-or-self of joint j
+  int32_t max_depth;
+  int32_t foot_joint[QM_NFEET];
+  int32_t ee_joint;
+  double axis[QM_NJ][3];     // joint axis, joint frame
+  double Rp[QM_NJ][9];       // joint frame placement in parent body frame (row major)
+  double pp[QM_NJ][3];
+  double mass[QM_NJ];
+  double com[QM_NJ][3];      // body frame
+  double inertia[QM_NJ][9];  // about com, body frame
+  double foot_off[QM_NFEET][3];
+  double ee_off[3];
+  double ee_Roff[9];
+  double total_mass;
+  double lower[QM_NJ], upper[QM_NJ], effort[QM_NJ];
+} qmb200_model_desc;
+
+// Optimal-control-problem constants. Replaces what QMInterface::setupOptimalControlProblem
+// (qm_interface/src/QMInterface.cpp:79-142) extracts from task.info / reference.info.
+typedef struct qmb200_problem_desc {
+  double Q[QM_NX * QM_NX];         // task.info:193-234
+  double R[QM_NU * QM_NU];         // J'R J already applied (QMInterface.cpp:274-299)
+  double mu_ee_pos, mu_ee_ori;     // "endEffector"      task.info:236-240
+  double mu_fee_pos, mu_fee_ori;   // "finalEndEffector" task.info:241-246
+  double fric_mu, fric_bar_mu, fric_bar_delta;  // task.info:291-298
+  double fric_reg, fric_grip, fric_hess_shift;  // [upstream] FrictionConeConstraint::Config defaults
+  double pos_bar_mu, pos_bar_delta, vel_bar_mu, vel_bar_delta;  // task.info:300-316
+  double arm_pos_lo[6], arm_pos_hi[6], arm_vel_lo[6], arm_vel_hi[6];
+  double box_offset;               // StateInputSoftBoxConstraint::initializeOffset(0,0,0) (QMInterface.cpp:257)
+  double swing_liftoff_vel, swing_touchdown_vel, swing_height, swing_time_scale;  // task.info:24-31
+  double gravity;                  // 9.81
+} qmb200_problem_desc;
+
+// Solver settings. task.info:76-93 (sqp) and :139-149 (mpc) + [upstream] sqp::Settings defaults.
+typedef struct qmb200_solver_desc {
+  double dt;            // sqp.dt
+  double horizon;       // mpc.timeHorizon
+  double delta_tol, g_max, g_min;
+  double alpha_decay, alpha_min, gamma_c, armijo_factor;
+  double weak_eps;      // ocs2::numeric_traits::weakEpsilon
+  double dt_min;        // 10 * limitEpsilon
+  int32_t max_nodes;    // capacity of the node axis (>= horizon/dt + 1 + 2*events in horizon)
+  int32_t max_events;   // capacity of a problem's mode schedule
+  int32_t max_targets;  // capacity of target knots
+  int32_t reserved;
+} qmb200_solver_desc;
+
+#ifdef __cplusplus
+}
+#endif
