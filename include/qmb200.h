@@ -1,0 +1,91 @@
+/* qmb200 — C-ABI of the B200-native MPC + WBC hot path of danisotelo/qm_door.
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, and returns an int status (0 = OK,
+ * negative = call-level failure, see qmb200_last_error).  Per-problem failures are reported through the
+ * `status` output arrays (bit flags QMB200_ST_*).  Citations are relative to the reference checkout.
+ *
+ *   qmb200_create / destroy          <- QMInterface ctor + setupOptimalControlProblem
+ *                                       (qm_interface/src/QMInterface.cpp:37-74, 79-142) and the SqpMpc object built in
+ *                                       QMController::setupMpc (qm_controllers/src/QMController.cpp:287-307)
+ *   qmb200_mpc_cycle_batch[_dev]     <- MPC_MRT_Interface::advanceMpc() -> SqpSolver::run for B independent problems
+ *                                       (QMController.cpp:316-333, :119-122)
+ *   qmb200_mpc_reset                 <- coldStart / resetMpcNode semantics (task.info:143)
+ *   qmb200_evaluate_policy_batch     <- MPC_MRT_Interface::evaluatePolicy (QMController.cpp:140-143)
+ *   qmb200_load_urdf                 <- centroidal_model::createPinocchioInterface(urdf, jointNames) (QMInterface.cpp:408-416)
+ *   qmb200_load_problem              <- loadData / loadEigenMatrix calls on task.info and reference.info
+ *                                       (QMInterface.cpp:65-73,85,152-156,199-234,291,306,395-397)
+ *   qmb200_load_gait / tile_schedule <- loadModeSequenceTemplate + GaitSchedule tiling (QMInterface.cpp:455-480,
+ *                                       qm_controllers/src/GaitTopicPublisher.cpp:31-44, config/gait.info)
+ *
+ * Array layouts (row-major): state x[30], input u[30], target knot[37] as in SURVEY.md App. A.1;
+ * the node axis of every trajectory output has capacity solver.max_nodes (NMAX) per problem and n_out[b] valid entries.
+ */
+#ifndef QMB200_H
+#define QMB200_H
+#include <stdint.h>
+#include "../qm_door_b200/csrc/qm_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qmb200_ctx qmb200_ctx;
+
+enum {
+  QMB200_ST_OK = 0,
+  QMB200_ST_GRID_OVERFLOW = 1,
+  QMB200_ST_BAD_SCHEDULE = 2,
+  QMB200_ST_RANK = 4,
+  QMB200_ST_CHOL = 8,
+  QMB200_ST_NAN = 16,
+  QMB200_ST_STEP_REJECTED = 32
+};
+#define QMB200_INFO_SIZE 16   /* per-problem info record: alpha, done, armijo, |dx|, |du|, base(merit,dyn,eq), new(merit,dyn,eq), iters */
+#define QMB200_NUM_KERNELS 8  /* schedule, init_guess, transcribe, solve, trial, decide, finalize, policy */
+
+int qmb200_version(void);
+const char* qmb200_last_error(void);
+int qmb200_device_count(void);
+
+/* ---- host-side ingestion of the reference's input files (no GPU needed) */
+int qmb200_load_urdf(const char* urdf_path, qmb200_model_desc* model);
+int qmb200_load_problem(const char* task_info, const char* reference_info, const qmb200_model_desc* model,
+                        qmb200_problem_desc* problem, qmb200_solver_desc* solver, double* initial_state30);
+int qmb200_load_gait(const char* gait_info, const char* gait_name, int32_t capacity, double* switching_times,
+                     int32_t* modes, int32_t* num_modes);
+int qmb200_tile_schedule(const double* switching_times, const int32_t* modes, int32_t num_modes, double t_insert,
+                         double t_upper, int32_t capacity, double* events, int32_t* mode_sequence, int32_t* num_events);
+
+/* ---- context: owns every device buffer (LQ blocks, warm start) for `batch` problems on `device` */
+int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* problem, const qmb200_solver_desc* solver,
+                  int32_t batch, int32_t device, qmb200_ctx** out);
+int qmb200_destroy(qmb200_ctx* ctx);
+int qmb200_mpc_reset(qmb200_ctx* ctx);
+int qmb200_sync(qmb200_ctx* ctx);
+
+/* One SQP cycle for every problem of the batch, HOST buffers (copies inside the call, returns when results are on the host).
+ *  t0[B] x0[B][30] events[B][EMAX] modes[B][EMAX+1] nevents[B] target_t[B][KT] target_x[B][KT][37]
+ *  -> t_out[B][NMAX] x_out[B][NMAX][30] u_out[B][NMAX][30] n_out[B] mode_out[B][NMAX] info[B][16] status[B]   (outputs may be NULL) */
+int qmb200_mpc_cycle_batch(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                           const int32_t* nevents, const double* target_t, const double* target_x, double* t_out,
+                           double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status);
+/* Same with DEVICE buffers; asynchronous on the context's stream except for the line-search hand-shake. */
+int qmb200_mpc_cycle_batch_dev(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events,
+                               const int32_t* modes, const int32_t* nevents, const double* target_t, const double* target_x,
+                               double* t_out, double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info,
+                               int32_t* status);
+
+/* Linear interpolation of the stored policy at t[B] (host buffers): x_des[B][30], u_des[B][30], mode[B]. */
+int qmb200_evaluate_policy_batch(qmb200_ctx* ctx, const double* t, double* x_des, double* u_des, int32_t* mode);
+
+/* Kernel timing (CUDA events on the context's stream): accumulated ms and launch counts per kernel since the last reset. */
+int qmb200_set_profiling(qmb200_ctx* ctx, int32_t enable);
+int qmb200_get_kernel_times(qmb200_ctx* ctx, double* total_ms, int64_t* launches, int32_t reset);
+const char* qmb200_kernel_name(int32_t index);
+void* qmb200_stream(qmb200_ctx* ctx);
+int64_t qmb200_device_bytes(qmb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

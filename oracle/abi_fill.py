@@ -94,7 +94,7 @@ def load_cport():
     deps = [src] + [os.path.join(HERE, "..", "qm_door_b200", "csrc", f) for f in ("qm_core.h", "qm_types.h", "qm_mpc.h")]
     deps = [p for p in deps if os.path.exists(p)]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
-        subprocess.check_call(["g++", "-O2", "-march=native", "-std=c++17", "-shared", "-fPIC", "-pthread",
+        subprocess.check_call(["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-pthread",
                                "-o", so, src])
     _cport = C.CDLL(so)
     return _cport

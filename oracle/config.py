@@ -10,6 +10,7 @@
 * load_problem    : every constant of SURVEY.md App. A the hot path consumes.
 """
 import math
+import os
 import re
 import xml.etree.ElementTree as ET
 
@@ -322,3 +323,53 @@ def load_problem(task_path, reference_path, gait_path, model):
         modes=[MODE_NAMES[mname] for mname in load_list(r, "initialModeSchedule.modeSequence")],
         events=[float(v) for v in load_list(r, "initialModeSchedule.eventTimes")])
     return P
+
+
+# ----------------------------------------------------------------------------- fixtures (the GPU box has no /root/reference)
+def dump_fixture(model, P, path):
+    """Write the parsed model + problem constants as JSON (generated by tools/gen_fixtures.py in the build container)."""
+    import json
+    md = {k: getattr(model, k).tolist() for k in ("parent", "jtype", "axis", "Rp", "pp", "mass", "com", "inertia",
+                                                   "lower", "upper", "effort")}
+    md["lower"] = [(-1e30 if not np.isfinite(v) else v) for v in md["lower"]]
+    md["upper"] = [(1e30 if not np.isfinite(v) else v) for v in md["upper"]]
+    md["names"] = model.names
+    md["frames"] = {k: [int(v[0]), np.asarray(v[1]).tolist(), np.asarray(v[2]).tolist()] for k, v in model.frames.items()}
+    pd = {}
+    for k, v in vars(P).items():
+        pd[k] = v.tolist() if isinstance(v, np.ndarray) else v
+    with open(path, "w") as fh:
+        json.dump(dict(model=md, problem=pd), fh, indent=0)
+
+
+def load_fixture(path):
+    import json
+    with open(path) as fh:
+        d = json.load(fh)
+    m = RobotModel()
+    for k in ("parent", "jtype", "axis", "Rp", "pp", "mass", "com", "inertia", "lower", "upper", "effort"):
+        setattr(m, k, d["model"][k])
+    m.names = d["model"]["names"]
+    m.frames = {k: (int(v[0]), np.array(v[1]), np.array(v[2])) for k, v in d["model"]["frames"].items()}
+    m.finalize()
+    P = Problem()
+    for k, v in d["problem"].items():
+        setattr(P, k, np.array(v) if isinstance(v, list) and k not in ("gait_list",) else v)
+    return m, P
+
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def load_default():
+    """Model + problem from the reference checkout when present (build container), else from the committed fixture."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    fixture = os.path.join(here, "..", "tests", "golden", "oracle_inputs.json")
+    urdf = os.path.join(REFERENCE_ROOT, "qm_description/urdf/quadruped_manipulator/robot.urdf")
+    if os.path.exists(urdf):
+        m = load_urdf_model(urdf)
+        cfg = os.path.join(REFERENCE_ROOT, "qm_controllers/config")
+        P = load_problem(os.path.join(cfg, "task.info"), os.path.join(cfg, "reference.info"), os.path.join(cfg, "gait.info"), m)
+        return m, P
+    return load_fixture(fixture)

@@ -80,21 +80,22 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
   const qmb200_model_desc& M = c->M; const qmb200_problem_desc& P = c->P; const qmb200_solver_desc& S = c->S;
   parallel_for(B, c->threads, [&](int b) {
     SerialGroup g;
-    std::vector<double> W(TW_SIZE > RW_SIZE ? TW_SIZE : RW_SIZE);
+    std::vector<double> W((int)TW_SIZE > (int)RW_SIZE ? (int)TW_SIZE : (int)RW_SIZE);
     std::vector<int> WI(TI_SIZE);
     const size_t o = (size_t)b * NMAX;
     build_schedule(S, P, m.t0[b], m.events + (size_t)b * E, m.modes + (size_t)b * (E + 1), m.nevents[b], m.node_t + o,
                    m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.nn + b, m.status + b);
     const int nn = m.nn[b], n = nn - 1;
     for (int cc = 0; cc < 60; ++cc)
-      init_guess_component(M, P, cc, m.x0 + 30 * b, nn, m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o,
+      init_guess_component(M, P, S.weak_eps, cc, m.x0 + 30 * b, nn, m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o,
                            m.node_mode + o, m.nprev[b], m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30, m.xs + o * 30, m.us + o * 30);
     const double* tt = m.target_t + (size_t)b * KT;
     const double* ts = m.target_x + (size_t)b * KT * QM_NTARGET;
     for (int k = 0; k <= n; ++k) {
       double* sb = m.stage + (o + k) * SB_SIZE; double* pb = m.proj + (o + k) * PB_SIZE; double* pf = m.perf_base + (o + k) * PF_SIZE;
       const double* x = m.xs + (o + k) * 30; const double* u = m.us + (o + k) * 30; const double* xn = m.xs + (o + k + 1) * 30;
-      if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, x, true, W.data(), sb, pf);
+      if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, x, W.data() + TW_KIN, W.data() + TW_REF,
+                                 W.data() + TW_E6, W.data() + TW_DQ, W.data() + TW_JE, sb, pf);
       else if (m.node_flag[o + k] == EV_PRE) event_node(g, x, xn, sb, pb, pf);
       else transcribe_node(g, M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
                            x, u, xn, W.data(), WI.data(), sb, pb, pf, m.status + b);
@@ -112,7 +113,8 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
           ut[i] = m.us[(o + k) * 30 + i] + alpha * m.dus[(o + k) * 30 + i];
           if (k < n) xnt[i] = m.xs[(o + k + 1) * 30 + i] + alpha * m.dxs[(o + k + 1) * 30 + i];
         }
-        if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, xt.data(), false, W.data(), nullptr, pf);
+        if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, xt.data(), W.data() + PW_KIN, W.data() + PW_REF,
+                                 W.data() + PW_E6, W.data() + PW_DQ, (double*)nullptr, (double*)nullptr, pf);
         else if (m.node_flag[o + k] == EV_PRE) {
           double d = 0.0;
           for (int i = 0; i < 30; ++i) d += (xt[i] - xnt[i]) * (xt[i] - xnt[i]);

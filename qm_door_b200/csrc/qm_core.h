@@ -48,6 +48,15 @@ struct WarpGroup {
 #endif
 #define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())
 
+// several CTAs (nodes) of one problem may flag the same status word
+QM_HD void status_or(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------ small vector helpers
 QM_HD void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];

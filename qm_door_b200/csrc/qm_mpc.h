@@ -137,7 +137,7 @@ QM_HDN void build_schedule(const qmb200_solver_desc& S, const qmb200_problem_des
 }
 
 // [upstream] multiple_shooting::initializeStateInputTrajectories; one thread per (problem, component c<60).
-QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_problem_desc& P, int c, const double* x0, int nn,
+QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_problem_desc& P, double weak_eps, int c, const double* x0, int nn,
                                  const double* node_t, const int32_t* node_flag, const double* node_ts, const double* node_dt,
                                  const int32_t* node_mode, int nprev, const double* prev_t, const double* prev_x,
                                  const double* prev_u, double* xs, double* us) {
@@ -156,7 +156,7 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
     xs[c] = xc;
     for (int k = 0; k < n; ++k) {
       if (node_flag[k] != EV_PRE) {
-        const double t = node_ts[k], tn = node_ts[k] + node_dt[k];
+        const double t = node_ts[k], tn = node_t[k + 1] - (node_flag[k + 1] == EV_PRE ? weak_eps : 0.0);
         if (!(t > till_u || tn > till_x)) {
           int i; double a;
           time_segment(tn, prev_t, nprev, &i, &a);
@@ -170,7 +170,7 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
     for (int k = 0; k < n; ++k) {
       double uc = 0.0;
       if (node_flag[k] != EV_PRE) {
-        const double t = node_ts[k], tn = node_ts[k] + node_dt[k];
+        const double t = node_ts[k], tn = node_t[k + 1] - (node_flag[k + 1] == EV_PRE ? weak_eps : 0.0);
         if (t > till_u || tn > till_x) {
           // QMInitializer::compute (qm_interface/src/initialization/QMInitializer.cpp:33-41): weight compensation
           const int md = node_mode[k];
@@ -747,7 +747,7 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
   }
   if (g.tid() == 0) {
     sb[SB_NUT] = (double)nut;
-    if (WI[TI_STATUS]) *status_out |= WI[TI_STATUS];
+    if (WI[TI_STATUS]) status_or(status_out, WI[TI_STATUS]);
   }
   g.sync();
 }
@@ -767,22 +767,23 @@ QM_HDN void event_node(G g, const double* x, const double* xn, double* sb, doubl
 }
 
 // Terminal node: "finalEndEffector" soft constraint only (QMInterface.cpp:104), Gauss-Newton.
+// kw: kinematics workspace, ref: RF_SIZE, e6: 8, dq: 10, JE: [6][24] or nullptr (value only), sb may be nullptr when JE is.
 template <class G>
 QM_HDN void terminal_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, int mode, const double* tt,
-                          const double* ts, int kt, const double* x, bool deriv, double* W, double* sb, double* perf) {
-  double* kw = W + TW_KIN;
-  if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, W + TW_REF);
+                          const double* ts, int kt, const double* x, double* kw, double* ref, double* e6, double* dq, double* JE,
+                          double* sb, double* perf) {
+  const bool deriv = JE != nullptr;
+  if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, ref);
   kin_eval(g, M, x, (const double*)nullptr, false, kw);
-  ee_terms(g, kw, W + TW_REF, W + TW_E6, W + TW_DQ, deriv ? (W + TW_JE) : (double*)nullptr);
+  ee_terms(g, kw, ref, e6, dq, JE);
   if (g.tid() == 0) {
-    const double* e = W + TW_E6;
+    const double* e = e6;
     perf[PF_COST] = 0.5 * P.mu_fee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_fee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
     perf[PF_DYN] = 0.0; perf[PF_EQ] = 0.0;
     if (deriv) sb[SB_NUT] = 0.0;
   }
   if (deriv) {
-    const double* JE = W + TW_JE;
-    const double* e = W + TW_E6;
+    const double* e = e6;
     QM_PFOR(g, idx, 900) {
       const int i = idx / 30, j = idx % 30;
       double acc = 0.0;
@@ -915,7 +916,7 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
       if (g.tid() == 0) {
         double d = Gm[QM_NUT * c + c];
         for (int k = 0; k < c; ++k) d -= Gm[QM_NUT * c + k] * Gm[QM_NUT * c + k];
-        if (!(d > 0.0)) { *status |= ST_CHOL; d = 1e-300; }
+        if (!(d > 0.0)) { status_or(status, ST_CHOL); d = 1e-300; }
         Gm[QM_NUT * c + c] = sqrt(d);
       }
       g.sync();

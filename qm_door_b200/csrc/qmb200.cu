@@ -1,0 +1,412 @@
+// sm_100a kernels + context + C-ABI of the MPC cycle (see include/qmb200.h for the reference interfaces replaced).
+//
+// Launch map of one cycle (B problems, NMAX node capacity):
+//   k_schedule   <<<ceil(B/128), 128>>>      thread per problem: time grid, modes, swing references
+//   k_init_guess <<<B, 64>>>                 thread per state/input component: warm start interpolation
+//   k_transcribe <<<(NMAX, B), 128>>>        CTA per node: kinematics x2, LQ approximation, projection -> stage/proj blocks
+//   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
+//   k_trial      <<<(NMAX/4, B), 128>>>      warp per node: value-only evaluation of the trial step
+//   k_decide     <<<ceil(B/128), 128>>>      thread per problem: filter line-search acceptance
+//   k_finalize   <<<B, 64>>>                 thread per component: publish primal solution + warm start
+// There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/qmb200.h"
+#include "qm_buffers.h"
+
+using namespace qm;
+
+extern "C" void qmb200_set_error_(const char* msg);   // qm_host.cpp (shared error slot behind qmb200_last_error)
+static int fail(const std::string& msg) { qmb200_set_error_(msg.c_str()); return -1; }
+#define CUDA_OK(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+enum { KN_SCHEDULE = 0, KN_INIT, KN_TRANSCRIBE, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY };
+static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_transcribe", "k_solve",
+                                                       "k_trial",    "k_decide",     "k_finalize",   "k_policy"};
+
+// ------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= m.B) return;
+  const size_t o = (size_t)b * m.NMAX;
+  build_schedule(*S, *P, m.t0[b], m.events + (size_t)b * m.EMAX, m.modes + (size_t)b * (m.EMAX + 1), m.nevents[b],
+                 m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.nn + b,
+                 m.status + b);
+}
+
+__global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
+                                                    const qmb200_solver_desc* S) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= 60) return;
+  const size_t o = (size_t)b * m.NMAX;
+  init_guess_component(*M, *P, S->weak_eps, c, m.x0 + 30 * b, m.nn[b], m.node_t + o, m.node_flag + o, m.node_ts + o,
+                       m.node_dt + o, m.node_mode + o, m.nprev[b], m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30,
+                       m.xs + o * 30, m.us + o * 30);
+}
+
+constexpr int kTranscribeSmemDoubles = TW_SIZE + 96;
+constexpr size_t kTranscribeSmemBytes = kTranscribeSmemDoubles * sizeof(double) + TI_SIZE * sizeof(int);
+
+__global__ void __launch_bounds__(128) k_transcribe(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  const int nn = m.nn[b];
+  if (k >= nn) return;
+  extern __shared__ double smem[];
+  double* W = smem;
+  double* xin = smem + TW_SIZE;                 // x[30], u[30], xn[30]
+  int* WI = (int*)(smem + kTranscribeSmemDoubles);
+  const size_t o = (size_t)b * m.NMAX + k;
+  const int n = nn - 1;
+  BlockGroup g;
+  for (int i = threadIdx.x; i < 90; i += blockDim.x) {
+    double v;
+    if (i < 30) v = m.xs[o * 30 + i];
+    else if (i < 60) v = m.us[o * 30 + i - 30];
+    else v = (k < n) ? m.xs[(o + 1) * 30 + i - 60] : 0.0;
+    xin[i] = v;
+  }
+  __syncthreads();
+  double* sb = m.stage + o * SB_SIZE;
+  double* pb = m.proj + o * PB_SIZE;
+  double* pf = m.perf_base + o * PF_SIZE;
+  const double* tt = m.target_t + (size_t)b * m.KT;
+  const double* ts = m.target_x + (size_t)b * m.KT * QM_NTARGET;
+  if (k == n) {
+    terminal_node(g, *M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, xin, W + TW_KIN, W + TW_REF, W + TW_E6, W + TW_DQ,
+                  W + TW_JE, sb, pf);
+  } else if (m.node_flag[o] == EV_PRE) {
+    event_node(g, xin, xin + 60, sb, pb, pf);
+  } else {
+    transcribe_node(g, *M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, xin, xin + 30,
+                    xin + 60, W, WI, sb, pb, pf, m.status + b);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_solve(MpcBuffers m) {
+  extern __shared__ double smem[];
+  solve_problem(BlockGroup(), m, blockIdx.x, smem);
+}
+
+constexpr int kTrialWarps = 4;
+constexpr int kTrialWarpDoubles = PW_SIZE + 96;
+constexpr size_t kTrialSmemBytes = (size_t)kTrialWarps * kTrialWarpDoubles * sizeof(double);
+
+__global__ void __launch_bounds__(128) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kTrialWarps + warp, b = blockIdx.y;
+  const double* ls = m.ls + (size_t)b * LS_SIZE;
+  if (ls[LS_DONE] != 0.0) return;
+  const int nn = m.nn[b];
+  if (k >= nn) return;
+  extern __shared__ double smem[];
+  double* W = smem + (size_t)warp * kTrialWarpDoubles;
+  double* xin = W + PW_SIZE;
+  const double alpha = ls[LS_ALPHA];
+  const size_t o = (size_t)b * m.NMAX + k;
+  const int n = nn - 1;
+  WarpGroup g;
+  for (int i = lane; i < 90; i += 32) {
+    double v;
+    if (i < 30) v = m.xs[o * 30 + i] + alpha * m.dxs[o * 30 + i];
+    else if (i < 60) v = m.us[o * 30 + i - 30] + alpha * m.dus[o * 30 + i - 30];
+    else v = (k < n) ? m.xs[(o + 1) * 30 + i - 60] + alpha * m.dxs[(o + 1) * 30 + i - 60] : 0.0;
+    xin[i] = v;
+  }
+  __syncwarp();
+  double* pf = m.perf_trial + o * PF_SIZE;
+  const double* tt = m.target_t + (size_t)b * m.KT;
+  const double* ts = m.target_x + (size_t)b * m.KT * QM_NTARGET;
+  if (k == n) {
+    terminal_node(g, *M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, xin, W + PW_KIN, W + PW_REF, W + PW_E6, W + PW_DQ,
+                  (double*)nullptr, (double*)nullptr, pf);
+  } else if (m.node_flag[o] == EV_PRE) {
+    if (lane == 0) {
+      double d = 0.0;
+      for (int i = 0; i < 30; ++i) d += (xin[i] - xin[60 + i]) * (xin[i] - xin[60 + i]);
+      pf[PF_COST] = 0.0; pf[PF_DYN] = d; pf[PF_EQ] = 0.0;
+    }
+  } else {
+    perf_node(g, *M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, xin, xin + 30, xin + 60,
+              W, pf);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= m.B) return;
+  decide_problem(*S, m, b);
+  if (m.ls[(size_t)b * LS_SIZE + LS_DONE] == 0.0) atomicAdd(pending, 1);
+}
+
+__global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= 60) return;
+  finalize_component(m, b, c, t_out, x_out, u_out);
+}
+
+// [upstream] MPC_MRT_Interface::evaluatePolicy with a FeedforwardController: linear interpolation of (x*, u*) at t.
+__global__ void __launch_bounds__(64) k_policy(MpcBuffers m, const double* t, double* x_des, double* u_des, int32_t* mode) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c >= 60) return;
+  const size_t o = (size_t)b * m.NMAX;
+  const int np = m.nprev[b];
+  int i; double a;
+  time_segment(t[b], m.prev_t + o, np, &i, &a);
+  const int i2 = (np > 1) ? i + 1 : i;
+  if (c < 30) x_des[30 * b + c] = a * m.prev_x[(o + i) * 30 + c] + (1.0 - a) * m.prev_x[(o + i2) * 30 + c];
+  else u_des[30 * b + c - 30] = a * m.prev_u[(o + i) * 30 + c - 30] + (1.0 - a) * m.prev_u[(o + i2) * 30 + c - 30];
+  if (c == 0) mode[b] = m.modes[(size_t)b * (m.EMAX + 1) + mode_index(m.events + (size_t)b * m.EMAX, m.nevents[b], t[b])];
+}
+
+// ------------------------------------------------------------------------------------------ context
+struct qmb200_ctx {
+  int device = 0;
+  int B = 0;
+  qmb200_model_desc hM;
+  qmb200_problem_desc hP;
+  qmb200_solver_desc hS;
+  qmb200_model_desc* dM = nullptr;
+  qmb200_problem_desc* dP = nullptr;
+  qmb200_solver_desc* dS = nullptr;
+  MpcBuffers m;          // ctx-owned device buffers
+  int* d_pending = nullptr;
+  int* h_pending = nullptr;   // pinned
+  cudaStream_t stream = nullptr;
+  int64_t bytes = 0;
+  bool profiling = false;
+  double kernel_ms[QMB200_NUM_KERNELS] = {0};
+  int64_t kernel_launches[QMB200_NUM_KERNELS] = {0};
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+static cudaEvent_t get_event(qmb200_ctx* c) {
+  if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct KernelTimer {
+  qmb200_ctx* c; int id; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(qmb200_ctx* c_, int id_) : c(c_), id(id_) {
+    c->kernel_launches[id]++;
+    if (c->profiling) { e0 = get_event(c); e1 = get_event(c); cudaEventRecord(e0, c->stream); }
+  }
+  ~KernelTimer() {
+    if (c->profiling) { cudaEventRecord(e1, c->stream); c->pending_events.push_back({id, {e0, e1}}); }
+  }
+};
+
+static void harvest_events(qmb200_ctx* c) {
+  for (auto& pe : c->pending_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) c->kernel_ms[pe.first] += ms;
+    c->event_pool.push_back(pe.second.first);
+    c->event_pool.push_back(pe.second.second);
+  }
+  c->pending_events.clear();
+}
+
+static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, double* u_out) {
+  const int B = m.B, NMAX = m.NMAX;
+  cudaStream_t st = c->stream;
+  { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->dP); }
+  { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
+  { KernelTimer kt(c, KN_TRANSCRIBE); k_transcribe<<<dim3(NMAX, B), 128, kTranscribeSmemBytes, st>>>(m, c->dM, c->dP); }
+  { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, 128, RW_SIZE * sizeof(double), st>>>(m); }
+  CUDA_OK(cudaGetLastError());
+  const int max_iters = 24;
+  for (int it = 0; it < max_iters; ++it) {
+    CUDA_OK(cudaMemsetAsync(c->d_pending, 0, sizeof(int), st));
+    { KernelTimer kt(c, KN_TRIAL); k_trial<<<dim3((NMAX + kTrialWarps - 1) / kTrialWarps, B), 128, kTrialSmemBytes, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_DECIDE); k_decide<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending); }
+    CUDA_OK(cudaMemcpyAsync(c->h_pending, c->d_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (*c->h_pending == 0) break;
+  }
+  { KernelTimer kt(c, KN_FINALIZE); k_finalize<<<B, 64, 0, st>>>(m, t_out, x_out, u_out); }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int qmb200_version(void) { return 100; }
+const char* qmb200_kernel_name(int32_t i) { return (i >= 0 && i < QMB200_NUM_KERNELS) ? kKernelNames[i] : ""; }
+
+int qmb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* problem, const qmb200_solver_desc* solver,
+                  int32_t batch, int32_t device, qmb200_ctx** out) {
+  if (!model || !problem || !solver || !out) return fail("qmb200_create: null argument");
+  if (batch <= 0) return fail("qmb200_create: batch must be positive");
+  if (model->nj != QM_NJ) return fail("qmb200_create: model must have 24 one-DoF joints (6 floating base + 18 actuated)");
+  if (solver->max_nodes < 3 || solver->max_events < 1 || solver->max_targets < 1) return fail("qmb200_create: bad capacities");
+  if (qmb200_device_count() <= 0) return fail("qmb200_create: no CUDA device available (this library has no CPU fallback)");
+  CUDA_OK(cudaSetDevice(device));
+  qmb200_ctx* c = new qmb200_ctx();
+  c->device = device; c->B = batch; c->hM = *model; c->hP = *problem; c->hS = *solver;
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
+  CUDA_OK(cudaMalloc(&c->dP, sizeof(*problem)));
+  CUDA_OK(cudaMalloc(&c->dS, sizeof(*solver)));
+  CUDA_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(c->dP, problem, sizeof(*problem), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(c->dS, solver, sizeof(*solver), cudaMemcpyHostToDevice));
+  c->m.B = batch; c->m.NMAX = solver->max_nodes; c->m.EMAX = solver->max_events; c->m.KT = solver->max_targets;
+  cudaError_t err = cudaSuccess;
+  int64_t total = 0;
+  for_each_buffer(c->m, [&](void** p, size_t bytes) {
+    if (err != cudaSuccess) { *p = nullptr; return; }
+    err = cudaMalloc(p, bytes);
+    if (err == cudaSuccess) { err = cudaMemset(*p, 0, bytes); total += (int64_t)bytes; }
+  });
+  if (err != cudaSuccess) { qmb200_destroy(c); return fail(std::string("qmb200_create: device allocation failed: ") + cudaGetErrorString(err)); }
+  c->bytes = total;
+  CUDA_OK(cudaMalloc(&c->d_pending, sizeof(int)));
+  CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int)));
+  CUDA_OK(cudaFuncSetAttribute(k_transcribe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTranscribeSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_trial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrialSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RW_SIZE * sizeof(double))));
+  *out = c;
+  return 0;
+}
+
+int qmb200_destroy(qmb200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  harvest_events(c);
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  for_each_buffer(c->m, [](void** p, size_t) { if (*p) cudaFree(*p); *p = nullptr; });
+  if (c->dM) cudaFree(c->dM);
+  if (c->dP) cudaFree(c->dP);
+  if (c->dS) cudaFree(c->dS);
+  if (c->d_pending) cudaFree(c->d_pending);
+  if (c->h_pending) cudaFreeHost(c->h_pending);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int qmb200_mpc_reset(qmb200_ctx* c) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemsetAsync(c->m.nprev, 0, sizeof(int32_t) * c->B, c->stream));
+  return 0;
+}
+
+int qmb200_sync(qmb200_ctx* c) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  harvest_events(c);
+  return 0;
+}
+
+void* qmb200_stream(qmb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t qmb200_device_bytes(qmb200_ctx* c) { return c ? c->bytes : 0; }
+
+int qmb200_set_profiling(qmb200_ctx* c, int32_t enable) {
+  if (!c) return fail("null ctx");
+  c->profiling = enable != 0;
+  return 0;
+}
+
+int qmb200_get_kernel_times(qmb200_ctx* c, double* total_ms, int64_t* launches, int32_t reset) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  harvest_events(c);
+  for (int i = 0; i < QMB200_NUM_KERNELS; ++i) {
+    if (total_ms) total_ms[i] = c->kernel_ms[i];
+    if (launches) launches[i] = c->kernel_launches[i];
+    if (reset) { c->kernel_ms[i] = 0.0; c->kernel_launches[i] = 0; }
+  }
+  return 0;
+}
+
+int qmb200_mpc_cycle_batch_dev(qmb200_ctx* c, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                               const int32_t* nevents, const double* target_t, const double* target_x, double* t_out,
+                               double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status) {
+  if (!c) return fail("null ctx");
+  if (!t0 || !x0 || !events || !modes || !nevents || !target_t || !target_x) return fail("qmb200_mpc_cycle_batch_dev: null input");
+  CUDA_OK(cudaSetDevice(c->device));
+  MpcBuffers m = c->m;
+  m.t0 = (double*)t0; m.x0 = (double*)x0; m.events = (double*)events; m.modes = (int32_t*)modes; m.nevents = (int32_t*)nevents;
+  m.target_t = (double*)target_t; m.target_x = (double*)target_x;
+  // keep the schedule for evaluate_policy (mode lookup)
+  CUDA_OK(cudaMemcpyAsync(c->m.events, events, sizeof(double) * c->B * m.EMAX, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->m.modes, modes, sizeof(int32_t) * c->B * (m.EMAX + 1), cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->m.nevents, nevents, sizeof(int32_t) * c->B, cudaMemcpyDeviceToDevice, c->stream));
+  if (run_cycle(c, m, t_out, x_out, u_out) != 0) return -1;
+  const size_t BN = (size_t)c->B * m.NMAX;
+  if (n_out) CUDA_OK(cudaMemcpyAsync(n_out, m.nn, sizeof(int32_t) * c->B, cudaMemcpyDeviceToDevice, c->stream));
+  if (mode_out) CUDA_OK(cudaMemcpyAsync(mode_out, m.node_mode, sizeof(int32_t) * BN, cudaMemcpyDeviceToDevice, c->stream));
+  if (info) CUDA_OK(cudaMemcpyAsync(info, m.ls, sizeof(double) * c->B * LS_SIZE, cudaMemcpyDeviceToDevice, c->stream));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, m.status, sizeof(int32_t) * c->B, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int qmb200_mpc_cycle_batch(qmb200_ctx* c, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                           const int32_t* nevents, const double* target_t, const double* target_x, double* t_out, double* x_out,
+                           double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status) {
+  if (!c) return fail("null ctx");
+  if (!t0 || !x0 || !events || !modes || !nevents || !target_t || !target_x) return fail("qmb200_mpc_cycle_batch: null input");
+  CUDA_OK(cudaSetDevice(c->device));
+  MpcBuffers& m = c->m;
+  const size_t B = c->B, BN = B * m.NMAX;
+  cudaStream_t st = c->stream;
+  CUDA_OK(cudaMemcpyAsync(m.t0, t0, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(m.x0, x0, sizeof(double) * B * 30, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(m.events, events, sizeof(double) * B * m.EMAX, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(m.modes, modes, sizeof(int32_t) * B * (m.EMAX + 1), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(m.nevents, nevents, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(m.target_t, target_t, sizeof(double) * B * m.KT, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(m.target_x, target_x, sizeof(double) * B * m.KT * QM_NTARGET, cudaMemcpyHostToDevice, st));
+  if (run_cycle(c, m, nullptr, nullptr, nullptr) != 0) return -1;
+  if (t_out) CUDA_OK(cudaMemcpyAsync(t_out, m.prev_t, sizeof(double) * BN, cudaMemcpyDeviceToHost, st));
+  if (x_out) CUDA_OK(cudaMemcpyAsync(x_out, m.prev_x, sizeof(double) * BN * 30, cudaMemcpyDeviceToHost, st));
+  if (u_out) CUDA_OK(cudaMemcpyAsync(u_out, m.prev_u, sizeof(double) * BN * 30, cudaMemcpyDeviceToHost, st));
+  if (n_out) CUDA_OK(cudaMemcpyAsync(n_out, m.nn, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  if (mode_out) CUDA_OK(cudaMemcpyAsync(mode_out, m.node_mode, sizeof(int32_t) * BN, cudaMemcpyDeviceToHost, st));
+  if (info) CUDA_OK(cudaMemcpyAsync(info, m.ls, sizeof(double) * B * LS_SIZE, cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, m.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  harvest_events(c);
+  return 0;
+}
+
+int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, double* u_des, int32_t* mode) {
+  if (!c || !t || !x_des || !u_des || !mode) return fail("qmb200_evaluate_policy_batch: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t B = c->B;
+  double *dt = nullptr, *dx = nullptr, *du = nullptr; int32_t* dm = nullptr;
+  CUDA_OK(cudaMallocAsync(&dt, sizeof(double) * B, c->stream));
+  CUDA_OK(cudaMallocAsync(&dx, sizeof(double) * B * 30, c->stream));
+  CUDA_OK(cudaMallocAsync(&du, sizeof(double) * B * 30, c->stream));
+  CUDA_OK(cudaMallocAsync(&dm, sizeof(int32_t) * B, c->stream));
+  CUDA_OK(cudaMemcpyAsync(dt, t, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+  { KernelTimer kt(c, KN_POLICY); k_policy<<<(unsigned)B, 64, 0, c->stream>>>(c->m, dt, dx, du, dm); }
+  CUDA_OK(cudaMemcpyAsync(x_des, dx, sizeof(double) * B * 30, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(u_des, du, sizeof(double) * B * 30, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(mode, dm, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaFreeAsync(dt, c->stream)); CUDA_OK(cudaFreeAsync(dx, c->stream));
+  CUDA_OK(cudaFreeAsync(du, c->stream)); CUDA_OK(cudaFreeAsync(dm, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // extern "C"
