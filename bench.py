@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — MPC-cycles/s of the qm_door hot path on B200 (BASELINE.json metric, config 2).
+
+A "step" is one full SQP MPC cycle (schedule -> transcription -> Riccati -> filter line search -> policy) of the whole
+batch: AlienGo+Z1, horizon 1.0 s at dt 0.01 s (N = 100 intervals + gait-event nodes), trot, 1024 independent perturbed
+initial states per GPU, warm-started and advanced by 0.01 s per step.
+
+  python bench.py [--gpus N --steps K --warmup W]          this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                    the CPU implementation of the same path on the host cores
+                                                            (oracle/cport: the reference binary cannot be built here)
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MPC-cycles/sec (N=100, 24-state, batch=1024) at 1/2/4/8 B200 vs CPU ref"
+UNIT = "MPC-cycles/s"
+BATCH_PER_GPU = 1024
+HORIZON, DT = 1.0, 0.01
+CYCLE_DT = 0.01
+
+
+def workload_config(n_gpus):
+    return {"workload": "config 2: AlienGo+Z1 nx=30 nu=30, horizon 1.0 s / dt 0.01 s (N=100 + gait-event nodes), trot, "
+                        "batch=1024 independent perturbed initial states per GPU, warm start, t0 += 0.01 s per step, "
+                        "1 SQP iteration + filter line search per cycle",
+            "batch_per_gpu": BATCH_PER_GPU, "horizon_s": HORIZON, "dt_s": DT, "gait": "trot",
+            "parallelism": "independent problems sharded across %d GPU(s)%s" % (
+                n_gpus, ", one NCCL all-gather of the policy per cycle" if n_gpus > 1 else ""),
+            "l2_policy": "working set per step (4.9 GB of LQ blocks) is larger than the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- algorithmic bytes
+def transcribe_bytes_per_node(nut):
+    """Doubles k_transcribe must move per intermediate node: reads x,u,x_next (90); writes the projected LQ block
+    (A 900, B 30*nut, b 30, Q 900, P 30*nut, R nut^2, q 30, r nut, 1) and the projection (Pu 30*nut, Px 900, Pe 30)."""
+    return 8 * (90 + 900 + 30 * nut + 30 + 900 + 30 * nut + nut * nut + 30 + nut + 1 + 30 * nut + 900 + 30 + 3)
+
+
+def cycle_bytes_per_node(nut):
+    """SURVEY.md §8(d) whole-cycle figure: 10 118 doubles = 80 944 B per node for trot (nut = 16)."""
+    return 8 * ((900 + 30 * nut + 30) + (900 + nut * nut + 30 * nut + 30 + nut + 1) + (30 * nut + 900 + 30) + (30 * nut + nut) + 120)
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    cores = os.cpu_count() or 1
+    sample = 128
+    W = workload.Workload(sample, horizon=HORIZON, dt=DT, t_span=CYCLE_DT * (args.steps + args.warmup + 2))
+    cp = abi_fill.CPort(W.model, W.problem, W.solver, sample, threads=cores)
+    step = 0
+    for _ in range(args.warmup):
+        cp.cycle(np.full(sample, CYCLE_DT * step), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+        step += 1
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cp.cycle(np.full(sample, CYCLE_DT * step), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+        step += 1
+    el = time.perf_counter() - t
+    value = sample * args.steps / el
+    desc = "%d problems of the same workload per step (1/8 of one GPU batch), %d steps, all %d host threads" % (sample, args.steps, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "CPU restatement (oracle/cport, g++ -O3, std::thread over problems) — not the reference "
+                                 "binary: OCS2/Pinocchio/HPIPM are not vendored and cannot be built in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline_sample():
+    """Bounded CPU-port sample for the GPU arm's JSON line (rank 0, N=1): 128 problems x (1 warm-up + 3 cycles)."""
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    cores = os.cpu_count() or 1
+    sample, steps = 128, 3
+    W = workload.Workload(sample, horizon=HORIZON, dt=DT)
+    cp = abi_fill.CPort(W.model, W.problem, W.solver, sample, threads=cores)
+    cp.cycle(np.zeros(sample), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    t = time.perf_counter()
+    for s in range(1, steps + 1):
+        cp.cycle(np.full(sample, CYCLE_DT * s), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    el = time.perf_counter() - t
+    cp.close()
+    return {"value": sample * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d problems x %d warm-started cycles of config 2 on %d threads (oracle/cport)" % (sample, steps, cores)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = BATCH_PER_GPU
+    total_steps = args.steps + args.warmup
+    W = workload.Workload(B, horizon=HORIZON, dt=DT, seed=20261017 + rank, t_span=CYCLE_DT * (2 * total_steps + 4))
+    ctx = q.MpcContext(W.model, W.problem, W.solver, B, device=local_rank)
+    NMAX = W.solver.max_nodes
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    dev = torch.device("cuda", local_rank)
+    f64, i32 = torch.float64, torch.int32
+    d = dict(t0=torch.zeros(B, dtype=f64, device=dev), x0=torch.from_numpy(W.x0).to(dev),
+             events=torch.from_numpy(W.events).to(dev), modes=torch.from_numpy(W.modes).to(dev),
+             nevents=torch.from_numpy(W.nevents).to(dev), tt=torch.from_numpy(W.target_t).to(dev),
+             tx=torch.from_numpy(W.target_x).to(dev))
+    o = dict(t=torch.zeros(B, NMAX, dtype=f64, device=dev), x=torch.zeros(B, NMAX, 30, dtype=f64, device=dev),
+             u=torch.zeros(B, NMAX, 30, dtype=f64, device=dev), n=torch.zeros(B, dtype=i32, device=dev),
+             mode=torch.zeros(B, NMAX, dtype=i32, device=dev), info=torch.zeros(B, q.INFO_SIZE, dtype=f64, device=dev),
+             status=torch.zeros(B, dtype=i32, device=dev))
+    policy = torch.zeros(B, NMAX, 61, dtype=f64, device=dev)          # packed (t, x, u) shard for the all-gather
+    gathered = torch.zeros(world, B, NMAX, 61, dtype=f64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step_dev(k):
+        with torch.cuda.stream(stream):
+            d["t0"].fill_(CYCLE_DT * k)
+            ctx.cycle_dev(d["t0"], d["x0"], d["events"], d["modes"], d["nevents"], d["tt"], d["tx"], o["t"], o["x"], o["u"],
+                          o["n"], o["mode"], o["info"], o["status"])
+            if world > 1:
+                policy[..., 0] = o["t"]
+                policy[..., 1:31] = o["x"]
+                policy[..., 31:61] = o["u"]
+                dist.all_gather_into_tensor(gathered, policy)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    k = 0
+    for _ in range(args.warmup):
+        step_dev(k)
+        k += 1
+    ctx.sync()
+    ctx.kernel_times(reset=True)
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    for _ in range(args.steps):
+        step_dev(k)
+        k += 1
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    kt = ctx.kernel_times(reset=True)
+    ctx.set_profiling(False)
+    status = o["status"].cpu().numpy()
+    bad = int(((status & ~32) != 0).sum())
+    nn = o["n"].cpu().numpy()
+    modes_last = o["mode"].cpu().numpy()
+    alpha_mean = float(o["info"][:, 0].mean().item())
+
+    # ---- end-to-end timing through the host-buffer C-ABI call (pinned host inputs, policy read back)
+    ctx.reset()
+    ctx.sync()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h = dict(x0=pin(W.x0), events=pin(W.events), modes=pin(W.modes), nevents=pin(W.nevents), tt=pin(W.target_t), tx=pin(W.target_x))
+    ht0 = pin(np.zeros(B))
+    hout = ctx.alloc_outputs(pinned=True)
+    h2d = sum(a.nbytes for a in h.values()) + ht0.nbytes
+    d2h = sum(hout[key].nbytes for key in ("t", "x", "u", "n", "mode", "info", "status"))
+    k = 0
+    for _ in range(args.warmup):
+        ht0[:] = CYCLE_DT * k
+        ctx.cycle(ht0, h["x0"], h["events"], h["modes"], h["nevents"], h["tt"], h["tx"], out=hout)
+        k += 1
+    barrier()
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        ht0[:] = CYCLE_DT * k
+        ctx.cycle(ht0, h["x0"], h["events"], h["modes"], h["nevents"], h["tt"], h["tx"], out=hout)
+        k += 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t_start
+    e2e_bad = int(((hout["status"] & ~32) != 0).sum())
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0].item()), float(times[1].item())
+    if rank == 0:
+        total = B * world
+        value = total * args.steps / (dev_ms * 1e-3)
+        e2e = total * args.steps / (e2e_ms * 1e-3)
+        # dominant kernel roofline (k_transcribe): algorithmic bytes of the nodes actually transcribed / mean launch time
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        by_name = max(kt.items(), key=lambda kv: kv[1][0])
+        dom = "k_transcribe"
+        ms_dom = kt[dom][0] / max(1, kt[dom][1])
+        nodes_bytes = 0
+        for b in range(B):
+            for kk in range(nn[b] - 1):
+                md = int(modes_last[b, kk])
+                nodes_bytes += transcribe_bytes_per_node(14 + bin(md & 15).count("1"))
+        achieved = nodes_bytes / (ms_dom * 1e-3) / 1e9
+        cyc_bytes = sum(cycle_bytes_per_node(16) for _ in range(1)) * float(nn.sum() - B)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps, "failed_problems": e2e_bad},
+            "gpu_launches": int(sum(v[1] for v in kt.values())),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": int(nodes_bytes),
+                         "slowest_kernel_by_total_time": by_name[0],
+                         "cycle_level": {"algorithmic_bytes_per_step": int(cyc_bytes),
+                                         "achieved_gbs": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
+                                         "frac": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
+                                         "note": "SURVEY.md 8(d): 80 944 B per node (trot) x nodes of the batch; the cycle is "
+                                                 "FP64-FMA / dependency bound (Riccati, projection), not HBM bound"}},
+            "kernel_ms_per_step": {kname: v[0] / args.steps for kname, v in kt.items() if v[1]},
+            "failed_problems": bad, "mean_step_size": alpha_mean,
+            "nodes_per_problem": [int(nn.min()), int(nn.max())],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
+               "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__), "--gpus",
+               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        raise SystemExit(subprocess.call(cmd))
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

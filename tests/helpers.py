@@ -1,0 +1,47 @@
+import glob
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "mpc_cycle_*.npz")))
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def solver_for(solver, horizon, dt, max_events=40):
+    import ctypes
+    s = type(solver)()
+    ctypes.memmove(ctypes.byref(s), ctypes.byref(solver), ctypes.sizeof(s))
+    s.horizon, s.dt = float(horizon), float(dt)
+    s.max_nodes = int(round(horizon / dt)) + 1 + 12
+    s.max_events = max_events
+    s.max_targets = 2
+    return s
+
+
+def check_against_golden(make_backend, path, tol_x=1e-8, tol_u=1e-8):
+    """make_backend(solver_desc, B) -> object with .cycle(t0, x0, events, modes, nevents, tt, tx) -> dict, .close()."""
+    g = np.load(path)
+    B = g["x0"].shape[0]
+    be = make_backend(float(g["horizon"]), float(g["dt"]), B)
+    cycles = g["t"].shape[0]
+    worst = 0.0
+    for c in range(cycles):
+        out = be.cycle(np.full(B, 0.01 * c), g["x0"], g["events"], g["modes"], g["nevents"], g["target_t"], g["target_x"])
+        assert (out["status"] == 0).all(), out["status"]
+        assert np.array_equal(out["n"], g["n"][c])                      # node counts: bit exact
+        for b in range(B):
+            n = out["n"][b]
+            assert np.array_equal(out["mode"][b, :n], g["mode"][c, b, :n])   # contact-schedule / mode indices: bit exact
+            assert np.array_equal(out["t"][b, :n], g["t"][c, b, :n])         # node times: bit exact
+            ex, eu = rel_l2(out["x"][b, :n], g["x"][c, b, :n]), rel_l2(out["u"][b, :n], g["u"][c, b, :n])
+            worst = max(worst, ex, eu)
+            assert ex < tol_x and eu < tol_u, (path, c, b, ex, eu)
+            assert out["info"][b, 0] == g["alpha"][c, b]
+            assert np.allclose(out["info"][b, [2, 5, 6, 7, 8, 9, 10]], g["perf"][c, b], rtol=1e-7, atol=1e-12)
+    be.close()
+    return worst

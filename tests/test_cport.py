@@ -1,0 +1,109 @@
+"""CPU port (host compilation of the kernels' per-node routines) against the NumPy oracle and its golden vectors.
+This is what pins the arithmetic of csrc/qm_core.h / qm_mpc.h without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, check_against_golden, rel_l2, solver_for
+from oracle import abi_fill, centroidal as ce, gait as G, rbd, scenarios, sqp
+
+
+@pytest.fixture(scope="module")
+def cport_factory(descs):
+    model, problem, solver, _ = descs
+
+    def make(horizon, dt, B):
+        return abi_fill.CPort(model, problem, solver_for(solver, horizon, dt), B)
+    return make
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.split("mpc_cycle_")[-1][:-4])
+def test_cycle_matches_golden(cport_factory, path):
+    assert check_against_golden(cport_factory, path) < 1e-8
+
+
+def test_kinematics_and_analytic_derivatives(descs, oracle_inputs):
+    """kin_eval: FK, CMM, frame Jacobians and the analytic d(Av)/dq, d(Jv)/dq against complex-step differentiation."""
+    from qm_door_b200.csrc_offsets import KW
+    model, _, _, _ = descs
+    m, P = oracle_inputs
+    lib = abi_fill.load_cport()
+    rng = np.random.default_rng(1)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for trial in range(3):
+        x = P.x_init + 0.3 * rng.standard_normal(30)
+        u = 3 * rng.standard_normal(30)
+        w = np.zeros(lib.cport_kin_ws_size())
+        lib.cport_kin_eval(C.byref(model), dp(x), dp(u), 1, dp(w))
+        nk = ce.node_kinematics(m, x, u)
+        get = lambda k, n, shp: w[KW[k]:KW[k] + n].reshape(shp)
+        assert rel_l2(get("ACM", 144, (6, 24)), nk["A"]) < 1e-13
+        assert rel_l2(get("FPOS", 12, (4, 3)), nk["foot_pos"]) < 1e-13
+        assert rel_l2(get("FVEL", 12, (4, 3)), nk["foot_vel"]) < 1e-12
+        assert rel_l2(get("VEL", 24, (24,)), nk["v"]) < 1e-12
+        assert rel_l2(get("EER", 9, (3, 3)), nk["ee_rot"]) < 1e-13
+        v, q = nk["v"], x[6:]
+
+        def hfun(qc):
+            A, _ = rbd.centroidal_momentum_matrix(m, rbd.kinematics(m, qc))
+            return (A @ v[..., None])[..., 0]
+
+        def fvfun(qc):
+            k = rbd.kinematics(m, qc)
+            return np.concatenate([(rbd.point_jacobian(m, k, m.foot_joint[i], rbd.frame_position(m, k, m.foot_joint[i], m.foot_off[i]))
+                                    @ v[..., None])[..., 0] for i in range(4)], -1)
+        assert rel_l2(get("DH", 144, (6, 24)), ce.cstep_jacobian(hfun, q)) < 1e-12
+        assert rel_l2(get("DFV", 288, (12, 24)), ce.cstep_jacobian(fvfun, q)) < 1e-12
+        assert rel_l2(get("EEJ", 144, (6, 24)), rbd.frame_jacobian6(m, nk["kin"], m.ee_joint, m.ee_off)) < 1e-13
+
+
+def test_fresh_cycle_against_oracle_with_ee_target_motion(descs, oracle_inputs):
+    """A case the golden files do not hold: moving end-effector target (position lerp + quaternion slerp), pace gait."""
+    model, problem, solver, _ = descs
+    m, P = oracle_inputs
+    B, hor = 2, 0.08
+    x0s, phase = scenarios.perturbed_states(m, P, B, seed=99)
+    tt, ts = scenarios.standing_target(m, P)
+    ts = ts.copy()
+    tt = np.array([0.0, 0.5])
+    ts[1, 30:33] += [0.05, -0.03, 0.02]
+    ang = 0.3
+    ts[1, 33:37] = ce.quat_slerp(ts[0, 33:37], np.array([np.sin(ang / 2), 0, 0, np.cos(ang / 2)]), 0.7)
+    ts[1, 33:37] /= np.linalg.norm(ts[1, 33:37])
+    ts[1, 6] += 0.1
+    sd = solver_for(solver, hor, 0.01)
+    scheds = [G.tile_schedule(P.gaits["pace"], -1.2 - phase[b], 1.2) for b in range(B)]
+    ev, md, ne = abi_fill.pack_schedules(scheds, sd.max_events)
+    cp = abi_fill.CPort(model, problem, sd, B)
+    probs = [sqp.MpcProblem(m, P, ev[b, :ne[b]], md[b, :ne[b] + 1], tt, ts, horizon=hor, dt=0.01) for b in range(B)]
+    for c in range(2):
+        out = cp.cycle(np.full(B, 0.01 * c), x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)))
+        for b in range(B):
+            _, xs, us, info = sqp.mpc_cycle(probs[b], 0.01 * c, x0s[b])
+            n = info["n"] + 1
+            assert out["n"][b] == n and np.array_equal(out["mode"][b, :n], info["modes"])
+            assert rel_l2(out["x"][b, :n], xs) < 1e-8 and rel_l2(out["u"][b, :n], us) < 1e-8
+    cp.close()
+
+
+def test_error_statuses(descs):
+    """Schedules that do not cover the horizon / node-capacity overflow are flagged per problem, not crashed on."""
+    model, problem, solver, x_init = descs
+    sd = solver_for(solver, 0.1, 0.01)
+    B = 2
+    cp = abi_fill.CPort(model, problem, sd, B)
+    ev = np.full((B, sd.max_events), 1e30); md = np.full((B, sd.max_events + 1), 15, dtype=np.int32)
+    ev[:, 0] = -1.0
+    ne = np.array([1, 1], dtype=np.int32)                  # single event in the past: schedule ends before the horizon
+    knot = np.concatenate([x_init, [0.6, 0, 0.8, 0, 0, 0, 1]])
+    out = cp.cycle(np.zeros(B), np.tile(x_init, (B, 1)), ev, md, ne, np.tile([0.0, 1.0], (B, 1)), np.tile(knot, (B, 2, 1)))
+    assert (out["status"] & 2).all()
+    cp.close()
+    sd2 = solver_for(solver, 0.3, 0.01)
+    sd2.max_nodes = 12                                      # too small for 30 intervals
+    cp = abi_fill.CPort(model, problem, sd2, B)
+    ev[:, 0] = -1.0; ev[:, 1] = 5.0; ne[:] = 2
+    out = cp.cycle(np.zeros(B), np.tile(x_init, (B, 1)), ev, md, ne, np.tile([0.0, 1.0], (B, 1)), np.tile(knot, (B, 2, 1)))
+    assert (out["status"] & 1).all() and (out["n"] <= 12).all()
+    cp.close()

@@ -1,0 +1,157 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle's golden vectors, the live oracle and
+the CPU port; plus size-independent properties at BASELINE.json's full size (B = 1024, N = 100)."""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, check_against_golden, rel_l2, solver_for
+
+pytestmark = pytest.mark.gpu
+
+POLICY_TOL = 1e-4      # BASELINE.json north_star: policy within 1e-4 rel-L2 of the reference path
+EXPECTED_TOL = 1e-8    # what FP64 end-to-end actually delivers
+
+
+@pytest.fixture(scope="module")
+def cuda_factory(descs):
+    import qm_door_b200 as q
+    model, problem, solver, _ = descs
+
+    def make(horizon, dt, B):
+        return q.MpcContext(model, problem, solver_for(solver, horizon, dt), B)
+    return make
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.split("mpc_cycle_")[-1][:-4])
+def test_cycle_matches_golden(cuda_factory, path):
+    worst = check_against_golden(cuda_factory, path, tol_x=EXPECTED_TOL, tol_u=EXPECTED_TOL)
+    assert worst < POLICY_TOL
+
+
+def test_cycle_matches_live_oracle(descs):
+    """Fresh seeded inputs, live NumPy oracle (a few seconds): warm-started cycles incl. event nodes."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    from oracle import config, sqp
+    W = workload.Workload(2, horizon=0.15, dt=0.01, seed=4242)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    m, P = config.load_default()
+    probs = [sqp.MpcProblem(m, P, W.events[b, :W.nevents[b]], W.modes[b, :W.nevents[b] + 1], W.target_t[b], W.target_x[b],
+                            horizon=0.15, dt=0.01) for b in range(W.B)]
+    for c in range(3):
+        out = ctx.cycle(np.full(W.B, 0.01 * c), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+        for b in range(W.B):
+            _, xs, us, info = sqp.mpc_cycle(probs[b], 0.01 * c, W.x0[b])
+            n = info["n"] + 1
+            assert out["n"][b] == n and np.array_equal(out["mode"][b, :n], info["modes"])
+            assert rel_l2(out["x"][b, :n], xs) < EXPECTED_TOL and rel_l2(out["u"][b, :n], us) < EXPECTED_TOL
+            assert out["info"][b, 0] == info["alpha"]
+    # evaluatePolicy: linear interpolation of the stored policy + planned mode
+    tq = np.array([0.0234, 0.0871])
+    xd, ud, md = ctx.evaluate_policy(tq)
+    for b in range(W.B):
+        xo, uo, mo = sqp.evaluate_policy(probs[b], tq[b])
+        assert rel_l2(xd[b], xo) < EXPECTED_TOL and rel_l2(ud[b], uo) < EXPECTED_TOL and md[b] == mo
+    ctx.close()
+
+
+def test_full_size_against_cpu_port_and_properties(descs):
+    """BASELINE config 2 at full size: B = 1024, N = 100. Every problem is compared with the CPU port (the oracle finishes a
+    subset in seconds: 64 problems), and the whole batch is checked through size-independent properties."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    from oracle import abi_fill
+    B = 1024
+    W = workload.Workload(B, horizon=1.0, dt=0.01)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, B)
+    sub = 64
+    cp = abi_fill.CPort(W.model, W.problem, W.solver, sub, threads=8)
+    viol_prev = None
+    for c in range(3):
+        t0 = np.full(B, 0.01 * c)
+        out = ctx.cycle(t0, W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+        ref = cp.cycle(t0[:sub], W.x0[:sub], W.events[:sub], W.modes[:sub], W.nevents[:sub], W.target_t[:sub], W.target_x[:sub])
+        assert ((out["status"] & ~32) == 0).all()
+        assert np.array_equal(out["n"][:sub], ref["n"]) and np.array_equal(out["mode"][:sub], ref["mode"])
+        assert np.array_equal(out["t"][:sub], ref["t"])
+        for b in range(sub):
+            n = out["n"][b]
+            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < EXPECTED_TOL
+            assert rel_l2(out["u"][b, :n], ref["u"][b, :n]) < 1e-7
+        assert np.array_equal(out["info"][:sub, 0], ref["info"][:, 0])          # accepted step sizes
+        # properties over the whole batch
+        info = out["info"]
+        n = out["n"]
+        assert (n >= 101).all() and (n <= W.solver.max_nodes).all()
+        acc = info[:, 1] == 1
+        assert acc.mean() > 0.95
+        # accepted steps passed the filter: either constraint violation or merit decreased
+        vb = np.sqrt(info[:, 6] + info[:, 7]); vn = np.sqrt(info[:, 9] + info[:, 10])
+        assert ((vn[acc] < vb[acc]) | (info[acc, 8] < info[acc, 5])).all()
+        # first state of the policy equals the measured state when a full step is taken (dx0 = x0 - x[0])
+        full = acc & (info[:, 0] == 1.0)
+        assert np.abs(out["x"][full, 0] - W.x0[full]).max() < 1e-12
+        # swing feet carry no force; mode ids of every node are valid gait modes of the trot template
+        for b in range(0, B, 37):
+            for k in range(n[b] - 1):
+                md = out["mode"][b, k]
+                assert md in (9, 6, 15)
+                if full[b]:
+                    for leg in range(4):
+                        if not (md >> (3 - leg)) & 1:
+                            assert np.abs(out["u"][b, k, 3 * leg:3 * leg + 3]).max() < 1e-9
+        viol_prev = vn
+    ctx.close()
+    cp.close()
+
+
+def test_idempotent_and_reset(descs):
+    """Same inputs after reset() -> bit-identical outputs (deterministic reductions); without reset the warm start is used."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    W = workload.Workload(8, horizon=0.3, dt=0.01, seed=5)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    a = ctx.cycle(np.zeros(8), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    b = ctx.cycle(np.full(8, 0.01), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    ctx.reset()
+    c = ctx.cycle(np.zeros(8), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    assert np.array_equal(a["x"], c["x"]) and np.array_equal(a["u"], c["u"])
+    assert not np.array_equal(a["x"], b["x"])
+    ctx.close()
+
+
+def test_device_pointer_entry_matches_host_entry(descs):
+    import torch
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    W = workload.Workload(16, horizon=0.2, dt=0.01, seed=6)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    ref = ctx.cycle(np.zeros(16), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    ctx.reset()
+    dev = torch.device("cuda", 0)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    N = W.solver.max_nodes
+    o = dict(t=torch.zeros(16, N, dtype=torch.float64, device=dev), x=torch.zeros(16, N, 30, dtype=torch.float64, device=dev),
+             u=torch.zeros(16, N, 30, dtype=torch.float64, device=dev), n=torch.zeros(16, dtype=torch.int32, device=dev))
+    ctx.cycle_dev(T(np.zeros(16)), T(W.x0), T(W.events), T(W.modes), T(W.nevents), T(W.target_t), T(W.target_x),
+                  o["t"], o["x"], o["u"], o["n"])
+    ctx.sync()
+    assert np.array_equal(o["x"].cpu().numpy(), ref["x"]) and np.array_equal(o["u"].cpu().numpy(), ref["u"])
+    assert np.array_equal(o["n"].cpu().numpy(), ref["n"])
+    ctx.close()
+
+
+def test_error_statuses_on_device(descs):
+    import qm_door_b200 as q
+    model, problem, solver, x_init = descs
+    sd = solver_for(solver, 0.1, 0.01)
+    B = 2
+    ctx = q.MpcContext(model, problem, sd, B)
+    ev = np.full((B, sd.max_events), 1e30); md = np.full((B, sd.max_events + 1), 15, dtype=np.int32)
+    ev[:, 0] = -1.0
+    ne = np.array([1, 1], dtype=np.int32)
+    knot = np.concatenate([x_init, [0.6, 0, 0.8, 0, 0, 0, 1]])
+    out = ctx.cycle(np.zeros(B), np.tile(x_init, (B, 1)), ev, md, ne, np.tile([0.0, 1.0], (B, 1)), np.tile(knot, (B, 2, 1)))
+    assert (out["status"] & 2).all()
+    with pytest.raises(ValueError):
+        ctx.cycle(np.zeros(B + 1), np.tile(x_init, (B, 1)), ev, md, ne, np.tile([0.0, 1.0], (B, 1)), np.tile(knot, (B, 2, 1)))
+    ctx.close()
