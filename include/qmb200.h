@@ -85,6 +85,32 @@ const char* qmb200_kernel_name(int32_t index);
 void* qmb200_stream(qmb200_ctx* ctx);
 int64_t qmb200_device_bytes(qmb200_ctx* ctx);
 
+/* ---- whole-body controller (second half of the hot path)
+ *   qmb200_wbc_create / destroy    <- HierarchicalWbc construction + loadTasksSetting in QMController::setupWbc
+ *                                     (qm_controllers/src/QMController.cpp:273-277, qm_wbc/src/WbcBase.cpp:22-72,597-627)
+ *   qmb200_load_wbc                <- WbcBase::loadTasksSetting + the dynamic_reconfigure defaults (qm_wbc/cfg/wbcWigeht.cfg:7-47)
+ *   qmb200_wbc_batch[_dev]         <- WbcBase::update(stateDesired, inputDesired, rbdStateMeasured, mode, period, time)
+ *                                     (qm_wbc/include/qm_wbc/WbcBase.h:31-32, called at QMController.cpp:147), B independent solves:
+ *                                     x_des[B][30] u_des[B][30] rbd[B][55] mode[B] period[B] time[B] -> cmd[B][54] = [accelerations(24);
+ *                                     contact forces(12); joint torques(18)], status[B] (QMB200_WST_* bits)
+ *   qmb200_wbc_reset               <- inputLast_ = 0 (WbcBase.cpp:41): the finite-difference joint acceleration state, per solve */
+typedef struct qmb200_wbc_ctx qmb200_wbc_ctx;
+enum { QMB200_WST_OK = 0, QMB200_WST_QP_MAX_ITER = 1, QMB200_WST_DEGENERATE = 2, QMB200_WST_NAN = 4, QMB200_WST_BAD_MODE = 8 };
+
+int qmb200_load_wbc(const char* task_info, const qmb200_model_desc* model, qmb200_wbc_desc* wbc);
+int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc, int32_t batch, int32_t device,
+                      qmb200_wbc_ctx** out);
+int qmb200_wbc_destroy(qmb200_wbc_ctx* ctx);
+int qmb200_wbc_reset(qmb200_wbc_ctx* ctx);
+int qmb200_wbc_set_gains(qmb200_wbc_ctx* ctx, const qmb200_wbc_desc* wbc);   /* dynamic_reconfigure callback equivalent */
+int qmb200_wbc_batch(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                     const double* period, const double* time, double* cmd, int32_t* status);
+int qmb200_wbc_batch_dev(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                         const double* period, const double* time, double* cmd, int32_t* status);
+int qmb200_wbc_sync(qmb200_wbc_ctx* ctx);
+void* qmb200_wbc_stream(qmb200_wbc_ctx* ctx);
+int qmb200_wbc_kernel_time(qmb200_wbc_ctx* ctx, double* total_ms, int64_t* launches, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

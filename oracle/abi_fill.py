@@ -81,6 +81,38 @@ def solver_desc(P, horizon=None, dt=None, max_nodes=None, max_events=32, max_tar
     return d
 
 
+def wbc_desc(m, P, gains=None, mpc_variant=False):
+    from . import wbc
+    g = dict(wbc.DEFAULT_GAINS if gains is None else gains)
+    d = _abi.WbcDesc()
+    d.kp_swing, d.kd_swing = g["kp_swing"], g["kd_swing"]
+    d.kp_base_height, d.kd_base_height = g["baseHeightKp"], g["baseHeightKd"]
+    d.kp_base_linear, d.kd_base_linear = g["kp_base_linear"], g["kd_base_linear"]
+    d.kp_base_angular, d.kd_base_angular = g["kp_base_angular"], g["kd_base_angular"]
+    for k in ("kp_arm_joint", "kd_arm_joint", "kp_ee_linear", "kd_ee_linear", "kp_ee_angular", "kd_ee_angular"):
+        _abi._set(getattr(d, k), g[k])
+    d.friction_mu = P.friction_wbc
+    _abi._set(d.tau_max, m.effort[6:])
+    d.swing_weight, d.init_time, d.gravity = 100.0, 10.0, 9.81
+    d.mpc_variant = int(mpc_variant)
+    return d
+
+
+def cport_wbc(md, wd, xd, ud, rbdm, mode, period, time, u_last, threads=1):
+    lib = load_cport()
+    B = xd.shape[0]
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    xd, ud, rbdm = (np.ascontiguousarray(a, dtype=np.float64) for a in (xd, ud, rbdm))
+    mode = np.ascontiguousarray(mode, dtype=np.int32)
+    period = np.ascontiguousarray(np.broadcast_to(period, (B,)), dtype=np.float64)
+    time = np.ascontiguousarray(np.broadcast_to(time, (B,)), dtype=np.float64)
+    cmd = np.zeros((B, 54))
+    status = np.zeros(B, dtype=np.int32)
+    lib.cport_wbc_batch(C.byref(md), C.byref(wd), B, dp(xd), dp(ud), dp(rbdm), dp(mode), dp(period), dp(time), dp(u_last),
+                        dp(cmd), dp(status), threads)
+    return cmd, status
+
+
 _cport = None
 
 
@@ -91,7 +123,7 @@ def load_cport():
         return _cport
     so = os.path.join(HERE, "cport", "libcport.so")
     src = os.path.join(HERE, "cport", "cport.cpp")
-    deps = [src] + [os.path.join(HERE, "..", "qm_door_b200", "csrc", f) for f in ("qm_core.h", "qm_types.h", "qm_mpc.h")]
+    deps = [src] + [os.path.join(HERE, "..", "qm_door_b200", "csrc", f) for f in ("qm_core.h", "qm_types.h", "qm_mpc.h", "qm_buffers.h", "qm_wbc.h")]
     deps = [p for p in deps if os.path.exists(p)]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.check_call(["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-pthread",

@@ -134,3 +134,28 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------- WBC
+#include "../../qm_door_b200/csrc/qm_wbc.h"
+
+extern "C" {
+
+int cport_wbc_ws_size() { return WW_SIZE; }
+
+// B whole-body-control solves; u_last [B][30] is the per-solve inputLast_ state (read, then overwritten with ud).
+int cport_wbc_batch(const qmb200_model_desc* M, const qmb200_wbc_desc* C, int B, const double* xd, const double* ud,
+                    const double* rbd, const int32_t* mode, const double* period, const double* time, double* u_last,
+                    double* cmd, int32_t* status, int threads) {
+  parallel_for(B, threads, [&](int b) {
+    std::vector<double> W(WW_SIZE);
+    std::vector<int> WI(WI_SIZE);
+    int st = 0;
+    wbc_update(SerialGroup(), *M, *C, xd + 30 * b, ud + 30 * b, rbd + 55 * b, mode[b], period[b], time[b], u_last + 30 * b,
+               W.data(), WI.data(), cmd + 54 * b, &st);
+    status[b] = st;
+    memcpy(u_last + 30 * b, ud + 30 * b, sizeof(double) * 30);
+  });
+  return 0;
+}
+
+}  // extern "C"

@@ -72,26 +72,26 @@ class Task:
 
 
 # ----------------------------------------------------------------------------- exact strictly convex QP: min 1/2 x'Hx + c'x  s.t. C x <= d
-def solve_qp_gi(Hfac, c, C, d, max_iter=500, tol=1e-9, tol_degenerate=1e-6):
+def solve_qp_gi(Hfac, c, C, d, max_iter=2000, tol=1e-10, tol_degenerate=1e-7):
     """Goldfarb-Idnani dual active set. Hfac = Jm with Jm' H Jm = I (so the nearly singular Hessians of HoQp, which carry a
-    1e-12 regularisation, are handled through their square-root factor). Returns (x, active set, iterations)."""
-    n = Hfac.shape[0]
-    Ct = -(C @ Hfac)             # rows: normals of  n' y >= b  in the y = Jm^-1 x coordinates
-    bt = -np.asarray(d, dtype=float)
-    y = -(Hfac.T @ c)
+    1e-12 regularisation, are handled through their square-root factor: step directions are formed in the scaled
+    coordinates, the iterate and the constraint residuals are kept in the original ones). Returns (x, active set, iterations)."""
+    C = np.asarray(C, dtype=float)
+    d = np.asarray(d, dtype=float)
+    Ct = -(C @ Hfac)             # normals of  n'y >= b  in the scaled coordinates x = Jm y
+    x = -(Hfac @ (Hfac.T @ c))   # unconstrained minimiser
     act, u = [], np.zeros(0)
     it = 0
-    scale = 1.0 + np.abs(bt)
-    ignored = []     # constraints violated by less than tol_degenerate whose normal is dependent on the active set:
-    #                  the hierarchy hands the previous level's active rows down with exactly zero slack, so the next
-    #                  level's feasible set is degenerate up to rounding (qpOASES absorbs this in its own tolerances)
+    scale = 1.0 + np.abs(d)
+    ignored = []     # rows violated by less than tol_degenerate whose normal depends on the active set: the hierarchy hands
+    #                  the previous level's active rows down with zero slack, so the feasible set is degenerate up to rounding
     while True:
-        s = Ct @ y - bt
+        s = d - C @ x            # >= 0 when satisfied
         s[act] = 0.0
         s[ignored] = 0.0
         p = int(np.argmin(s / scale))
         if s[p] / scale[p] >= -tol:
-            return Hfac @ y, act, it
+            return x, act, it
         nplus = Ct[p]
         uplus = np.concatenate([u, [0.0]])
         while True:
@@ -104,16 +104,17 @@ def solve_qp_gi(Hfac, c, C, d, max_iter=500, tol=1e-9, tol_degenerate=1e-6):
                 dv = Q.T @ nplus
                 r = np.linalg.solve(R[:q, :q], dv[:q])
                 z = Q[:, q:] @ dv[q:]
+                dn2 = float(dv[q:] @ dv[q:])
             else:
                 r = np.zeros(0)
                 z = nplus.copy()
-            zn = float(z @ nplus)
+                dn2 = float(z @ z)
             t1, l = np.inf, -1
             for j in range(q):
                 if r[j] > 1e-14 * (1 + abs(uplus[j])) and uplus[j] / r[j] < t1:
                     t1, l = uplus[j] / r[j], j
-            sp = float(nplus @ y - bt[p])
-            t2 = -sp / zn if zn > 1e-13 * float(nplus @ nplus) else np.inf
+            sp = float(d[p] - C[p] @ x)
+            t2 = -sp / dn2 if dn2 > 1e-26 * float(nplus @ nplus) else np.inf
             t = min(t1, t2)
             if not np.isfinite(t):
                 if abs(sp) < tol_degenerate * scale[p]:
@@ -122,7 +123,7 @@ def solve_qp_gi(Hfac, c, C, d, max_iter=500, tol=1e-9, tol_degenerate=1e-6):
                     break
                 raise RuntimeError("GI: infeasible QP")
             if np.isfinite(t2):
-                y = y + t * z
+                x = x + t * (Hfac @ z)
             uplus = uplus + t * np.concatenate([-r, [1.0]])
             if t == t2:
                 act.append(p)

@@ -192,3 +192,72 @@ def tile_schedule(switching_times, modes, t_insert, t_upper, capacity):
     _check(lib().qmb200_tile_schedule(_p(sw), _p(md), len(md), C.c_double(t_insert), C.c_double(t_upper), capacity,
                                       _p(ev), _p(ms), C.byref(n)))
     return ev, ms, n.value
+
+
+# ----------------------------------------------------------------------------- whole-body controller
+from ._abi import WbcDesc  # noqa: E402,F401
+
+
+def load_wbc(model, task_info=DEFAULT_TASK):
+    """Gains (qm_wbc/cfg/wbcWigeht.cfg defaults), torque limits and friction coefficient (WbcBase::loadTasksSetting)."""
+    w = WbcDesc()
+    _check(lib().qmb200_load_wbc(task_info.encode(), C.byref(model), C.byref(w)))
+    return w
+
+
+class WbcContext:
+    """Mirror of qm::WbcBase / HierarchicalWbc for a batch of independent solves:
+    update() has the argument meaning of WbcBase::update (qm_wbc/include/qm_wbc/WbcBase.h:31-32) and returns [x*(36); tau(18)]."""
+
+    def __init__(self, model, wbc, batch, device=0):
+        self.L = lib()
+        self.L.qmb200_wbc_stream.restype = C.c_void_p
+        self.B = batch
+        h = C.c_void_p()
+        _check(self.L.qmb200_wbc_create(C.byref(model), C.byref(wbc), batch, device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.qmb200_wbc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        _check(self.L.qmb200_wbc_reset(self.h))
+
+    def set_gains(self, wbc):
+        _check(self.L.qmb200_wbc_set_gains(self.h, C.byref(wbc)))
+
+    @property
+    def stream(self):
+        return self.L.qmb200_wbc_stream(self.h)
+
+    def update(self, x_des, u_des, rbd, mode, period, time, cmd=None, status=None):
+        B = self.B
+        x_des = np.ascontiguousarray(x_des, dtype=np.float64)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64)
+        rbd = np.ascontiguousarray(rbd, dtype=np.float64)
+        mode = np.ascontiguousarray(mode, dtype=np.int32)
+        period = np.ascontiguousarray(np.broadcast_to(period, (B,)), dtype=np.float64)
+        time = np.ascontiguousarray(np.broadcast_to(time, (B,)), dtype=np.float64)
+        if x_des.shape != (B, 30) or u_des.shape != (B, 30) or rbd.shape != (B, 55) or mode.shape != (B,):
+            raise ValueError("x_des, u_des must be [B,30], rbd [B,55], mode [B]")
+        cmd = np.zeros((B, 54)) if cmd is None else cmd
+        status = np.zeros(B, dtype=np.int32) if status is None else status
+        _check(self.L.qmb200_wbc_batch(self.h, _p(x_des), _p(u_des), _p(rbd), _p(mode), _p(period), _p(time), _p(cmd), _p(status)))
+        return cmd, status
+
+    def update_dev(self, x_des, u_des, rbd, mode, period, time, cmd, status):
+        dp = lambda t: C.c_void_p(t.data_ptr())
+        _check(self.L.qmb200_wbc_batch_dev(self.h, dp(x_des), dp(u_des), dp(rbd), dp(mode), dp(period), dp(time), dp(cmd), dp(status)))
+
+    def sync(self):
+        _check(self.L.qmb200_wbc_sync(self.h))
+
+    def kernel_time(self, reset=False):
+        ms = C.c_double()
+        n = C.c_int64()
+        _check(self.L.qmb200_wbc_kernel_time(self.h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value

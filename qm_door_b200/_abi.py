@@ -64,6 +64,22 @@ class SolverDesc(C.Structure):
     ]
 
 
+class WbcDesc(C.Structure):
+    _fields_ = [
+        ("kp_swing", C.c_double), ("kd_swing", C.c_double),
+        ("kp_base_height", C.c_double), ("kd_base_height", C.c_double),
+        ("kp_base_linear", C.c_double), ("kd_base_linear", C.c_double),
+        ("kp_base_angular", C.c_double), ("kd_base_angular", C.c_double),
+        ("kp_arm_joint", C.c_double * 6), ("kd_arm_joint", C.c_double * 6),
+        ("kp_ee_linear", C.c_double * 3), ("kd_ee_linear", C.c_double * 3),
+        ("kp_ee_angular", C.c_double * 3), ("kd_ee_angular", C.c_double * 3),
+        ("friction_mu", C.c_double),
+        ("tau_max", C.c_double * 18),
+        ("swing_weight", C.c_double), ("init_time", C.c_double), ("gravity", C.c_double),
+        ("mpc_variant", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 def _set(arr, values):
     a = np.ctypeslib.as_array(arr)
     a[...] = np.asarray(values).reshape(a.shape)

@@ -99,7 +99,8 @@ enum {
   KW_ABINV = KW_COM + 3,             // [36]
   KW_VEL = KW_ABINV + 36,            // [24] generalized velocity
   KW_RHS = KW_VEL + QM_NJ,           // [6]
-  KW_SIZE = KW_RHS + 6 + 2
+  KW_F = KW_RHS + 6,                 // [24][6] composite momentum per unit joint rate I^c_j S_j = (L0, p)  (CRBA columns)
+  KW_SIZE = ((KW_F + 6 * QM_NJ + 3) / 4) * 4
 };
 
 // spatial motion vector of joint j (world coordinates, reference point = world origin): (w, vO)
@@ -124,12 +125,9 @@ QM_HD void inertia_mul(const double* I, const double* V, double* h) {
   h[5] = I[0] * V[5] + t[2];
 }
 
-// Forward kinematics + centroidal quantities of one configuration, optionally with the generalized
-// velocity implied by (x,u) and the q-derivatives at fixed velocity needed for the linearisation.
-//   q = x[6:30];   u != nullptr -> velocity level;   deriv -> KW_DH / KW_DFV as well
+// Position level: placements, composite inertias, centroidal momentum matrix, frame positions and Jacobians. q[24].
 template <class G>
-QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, bool deriv, double* w) {
-  const double* q = x + 6;
+QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, double* w) {
   // P1: placements, level by level
   for (int d = 0; d <= M.max_depth; ++d) {
     QM_PFOR(g, j, QM_NJ) {
@@ -237,6 +235,7 @@ QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const dou
     w[KW_ACM + 3 * QM_NJ + j] = h[0] - t[0];
     w[KW_ACM + 4 * QM_NJ + j] = h[1] - t[1];
     w[KW_ACM + 5 * QM_NJ + j] = h[2] - t[2];
+    for (int c = 0; c < 6; ++c) w[KW_F + 6 * j + c] = h[c];
     for (int f = 0; f < QM_NFEET + 1; ++f) {
       const int b = (f < QM_NFEET) ? M.foot_joint[f] : M.ee_joint;
       const double* pos = (f < QM_NFEET) ? (w + KW_FPOS + 3 * f) : (w + KW_EEP);
@@ -258,8 +257,12 @@ QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const dou
     }
   }
   g.sync();
-  if (u == nullptr) return;
-  // P6: generalized velocity  v = [Ab^-1 (m h_n - A_j v_j); v_j]   ([upstream] getPinocchioJointVelocity)
+}
+
+// Generalized velocity implied by the centroidal state/input: v = [Ab^-1 (m h_n - A_j v_j); v_j]
+// ([upstream] CentroidalModelPinocchioMapping::getPinocchioJointVelocity). Needs kin_positions first.
+template <class G>
+QM_HDN void centroidal_velocity(G g, const qmb200_model_desc& M, const double* x, const double* u, double* w) {
   QM_PFOR(g, r, 6) {
     double acc = M.total_mass * x[r];
     for (int l = 0; l < 18; ++l) acc -= w[KW_ACM + r * QM_NJ + 6 + l] * u[12 + l];
@@ -297,6 +300,12 @@ QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const dou
     w[KW_VEL + r] = acc;
   }
   g.sync();
+}
+
+// Velocity level (KW_VEL given): spatial velocities, body momenta, foot velocities and, if deriv, the q-derivatives
+// at fixed generalized velocity d(A v)/dq (KW_DH) and d(J_i v)/dq (KW_DFV).
+template <class G>
+QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* w) {
   // P7: spatial velocities and body momenta
   QM_PFOR(g, j, QM_NJ) {
     double S[6];
@@ -384,6 +393,17 @@ QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const dou
     }
   }
   g.sync();
+}
+
+// Forward kinematics + centroidal quantities of one configuration, optionally with the generalized
+// velocity implied by (x,u) and the q-derivatives at fixed velocity needed for the linearisation.
+//   q = x[6:30];   u != nullptr -> velocity level;   deriv -> KW_DH / KW_DFV as well
+template <class G>
+QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, bool deriv, double* w) {
+  kin_positions(g, M, x + 6, w);
+  if (u == nullptr) return;
+  centroidal_velocity(g, M, x, u, w);
+  kin_velocities(g, M, deriv, w);
 }
 
 }  // namespace qm

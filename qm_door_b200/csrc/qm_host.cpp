@@ -522,4 +522,26 @@ int qmb200_tile_schedule(const double* sw, const int32_t* tmodes, int32_t nm, do
   });
 }
 
+// WbcBase::loadTasksSetting (qm_wbc/src/WbcBase.cpp:597-627) + default gains of qm_wbc/cfg/wbcWigeht.cfg:7-47
+int qmb200_load_wbc(const char* task_info, const qmb200_model_desc* M, qmb200_wbc_desc* C) {
+  return guarded([&]() {
+    if (!task_info || !M || !C) throw std::invalid_argument("qmb200_load_wbc: null argument");
+    InfoNode t = parse_info(task_info);
+    memset(C, 0, sizeof(*C));
+    C->kp_swing = 350; C->kd_swing = 37;
+    C->kp_base_height = 400; C->kd_base_height = 140;
+    C->kp_base_linear = 400; C->kd_base_linear = 100;
+    C->kp_base_angular = 400; C->kd_base_angular = 140;
+    const double kpj[6] = {4000, 4200, 4000, 4000, 4200, 6000};
+    for (int i = 0; i < 6; ++i) { C->kp_arm_joint[i] = kpj[i]; C->kd_arm_joint[i] = 75; }
+    for (int i = 0; i < 3; ++i) { C->kp_ee_linear[i] = 3000; C->kd_ee_linear[i] = 75; C->kp_ee_angular[i] = 2000; C->kd_ee_angular[i] = 75; }
+    C->friction_mu = t.num("frictionConeTask.frictionCoefficient");
+    for (int i = 0; i < 18; ++i) C->tau_max[i] = M->effort[6 + i];
+    C->swing_weight = 100.0;   // HierarchicalWbc.cpp:29
+    C->init_time = 10.0;       // HierarchicalWbc.cpp:32
+    C->gravity = 9.81;
+    C->mpc_variant = 0;
+  });
+}
+
 }  // extern "C"

@@ -376,7 +376,7 @@ QM_HD double barrier_cost(const qmb200_problem_desc& P, int mode, const double* 
 // ------------------------------------------------------------------------------------------ transcription workspace
 enum {
   TW_KIN = 0,                       // kinematics workspace; later reused for RPX / RPU
-  TW_FR1 = TW_KIN + 2388,           // [9][60]
+  TW_FR1 = TW_KIN + KW_SIZE,           // [9][60]
   TW_FR2 = TW_FR1 + 540,            // [9][60]
   TW_RPX = TW_KIN,                  // [30][30] alias (kinematics dead)
   TW_RPU = TW_KIN + 900,            // [30][18] alias
@@ -803,7 +803,7 @@ QM_HDN void terminal_node(G g, const qmb200_model_desc& M, const qmb200_problem_
 
 // ------------------------------------------------------------------------------------------ line-search node evaluation
 // Value-only evaluation of one intermediate node ([upstream] computeIntermediatePerformance): needs W of size PW_SIZE.
-enum { PW_KIN = 0, PW_REF = 2388, PW_F1 = PW_REF + RF_SIZE, PW_F2 = PW_F1 + 30, PW_X2 = PW_F2 + 30, PW_E6 = PW_X2 + 30,
+enum { PW_KIN = 0, PW_REF = KW_SIZE, PW_F1 = PW_REF + RF_SIZE, PW_F2 = PW_F1 + 30, PW_X2 = PW_F2 + 30, PW_E6 = PW_X2 + 30,
        PW_DQ = PW_E6 + 8, PW_DX = PW_DQ + 10, PW_DU = PW_DX + 30, PW_TQ = PW_DU + 30, PW_TR = PW_TQ + 30, PW_SCAL = PW_TR + 30,
        PW_SIZE = PW_SCAL + 4 };
 template <class G>

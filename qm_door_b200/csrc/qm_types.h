@@ -70,6 +70,25 @@ typedef struct qmb200_solver_desc {
   int32_t reserved;
 } qmb200_solver_desc;
 
+// Whole-body-controller gains and limits. Defaults: qm_wbc/cfg/wbcWigeht.cfg:7-47 (delivered by WbcBase::dynamicCallback,
+// qm_wbc/src/WbcBase.cpp:74-121), torque limits and friction coefficient from WbcBase::loadTasksSetting (WbcBase.cpp:597-627).
+typedef struct qmb200_wbc_desc {
+  double kp_swing, kd_swing;
+  double kp_base_height, kd_base_height;
+  double kp_base_linear, kd_base_linear;
+  double kp_base_angular, kd_base_angular;
+  double kp_arm_joint[6], kd_arm_joint[6];
+  double kp_ee_linear[3], kd_ee_linear[3];
+  double kp_ee_angular[3], kd_ee_angular[3];
+  double friction_mu;          // task.info frictionConeTask.frictionCoefficient
+  double tau_max[18];          // URDF effort limits in joint order
+  double swing_weight;         // 100 (HierarchicalWbc.cpp:29)
+  double init_time;            // 10 s: before it level 1 is the arm-joint tracking task (HierarchicalWbc.cpp:32-43)
+  double gravity;
+  int32_t mpc_variant;         // 0: HierarchicalWbc, 1: HierarchicalMpcWbc task stack
+  int32_t reserved;
+} qmb200_wbc_desc;
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,876 @@
+// WBC half of the hot path: rigid-body dynamics of the measured / desired configurations, the task stack and the
+// hierarchical QP, in the same phase-structured style as qm_core.h (one thread group per solve).
+// Reference computations replaced (relative to /root/reference):
+//   wbc_dynamics      WbcBase::updateMeasured / updateDesired          qm_wbc/src/WbcBase.cpp:146-238   (Pinocchio crba, nle, J, dJ, dccrba)
+//   wbc_tasks         the formulate* task builders + Task operators    qm_wbc/src/WbcBase.cpp:240-578, qm_wbc/include/qm_wbc/Task.h:17-66
+//   wbc_solve         HoQp (3 nested levels) + qpOASES                 qm_wbc/src/HoQp.cpp:12-158, HierarchicalWbc.cpp:18-44, HierarchicalMpcWbc.cpp:18-34
+//   torque recovery   WbcBase::updateCmd                               qm_wbc/src/WbcBase.cpp:580-595
+// Every level's QP is strictly convex (HoQp.cpp:66,72-75), so its solution is unique; it is computed here by
+//   level 0 : Newton iteration on the slack-eliminated piecewise-quadratic  1/2|A z - b|^2 + eps/2 |z|^2 + 1/2 |(D z - f)+|^2
+//             with Householder least squares (stable for the 1e-12 regularisation of HoQp.cpp:66)
+//   level 1,2: dual active-set method (Goldfarb & Idnani) in the null-space coordinates of the levels above.
+#pragma once
+#include "qm_core.h"
+
+namespace qm {
+
+enum { WST_OK = 0, WST_QP_MAX_ITER = 1, WST_DEGENERATE = 2, WST_NAN = 4, WST_BAD_MODE = 8 };
+
+enum { WB_NX = 36, WB_ND0 = 56, WB_NA1 = 22, WB_NA2 = 14, WB_MAXW = 36, WB_QR_ROWS = 92, WB_QR_LD = 37 };
+#define QM_WBC_EPS 1e-12        // HoQp.cpp:66
+
+// ---- workspace (doubles)
+enum {
+  WW_A0 = 0,                         // [18][36]
+  WW_B0 = WW_A0 + 18 * 36,           // [18]
+  WW_D0 = WW_B0 + 18,                // [56][36]
+  WW_F0 = WW_D0 + 56 * 36,           // [56]
+  WW_V0 = WW_F0 + 56,                // [56]  level-0 slack solution
+  WW_HJ = WW_V0 + 56,                // [18]
+  WW_A1 = WW_HJ + 18,                // [22][36]
+  WW_B1 = WW_A1 + 22 * 36,           // [22]
+  WW_A2 = WW_B1 + 22,                // [14][36]
+  WW_B2 = WW_A2 + 14 * 36,           // [14]
+  WW_X = WW_B2 + 14,                 // [36]
+  WW_Z0 = WW_X + 36,                 // [36][18]
+  WW_Z1 = WW_Z0 + 36 * 18,           // [36][12]
+  WW_SCR = ((WW_Z1 + 36 * 12 + 3) / 4) * 4,
+  // scratch, dynamics phase
+  WA_KIN = WW_SCR,
+  WA_ACC = WA_KIN + KW_SIZE,         // [24][6] bias spatial acceleration of each body (qdd = 0, no gravity)
+  WA_FB = WA_ACC + 144,              // [24][6] per-joint terms, then body forces (n, f)
+  WA_M = WA_FB + 144,                // [24][24]
+  WA_NLE = WA_M + 576,               // [24]
+  WA_JF = WA_NLE + 24,               // [12][24]
+  WA_DJV = WA_JF + 288,              // [12]
+  WA_JBA = WA_DJV + 12,              // [3][24]
+  WA_DJBV = WA_JBA + 72,             // [3] (+1)
+  WA_JEE = WA_DJBV + 4,              // [6][24]
+  WA_DJEE = WA_JEE + 144,            // [6] (+2)
+  WA_MEAS = WA_DJEE + 8,             // q[24] v[24] fpos[12] fvel[12] eep[3] eev[6] eeR[9] = 90
+  WA_DES = WA_MEAS + 92,             // q[24] v[24] bacc[6] fpos[12] fvel[12] eep[3] eev[3] eeR[9] = 93
+  WA_END = WA_DES + 96,
+  // scratch, solver phase (aliases the dynamics phase)
+  WS_QR = WW_SCR,                    // [92][37] stacked least-squares matrix | rhs
+  WS_Q = WS_QR + WB_QR_ROWS * WB_QR_LD,   // [36][36]
+  WS_RES = WS_Q + 36 * 36,           // [56] constraint residuals
+  WS_VH = WS_RES + 56,               // [92] Householder vector
+  WS_WJ = WS_VH + 92,                // [37]
+  WS_GA = WS_WJ + 40,                // [22][18]  A Z of the current level
+  WS_GB = WS_GA + 22 * 18,           // [22]
+  WS_GG = WS_GB + 22,                // [56][18]  D0 Z
+  WS_Gg = WS_GG + 56 * 18,           // [56]
+  WS_J = WS_Gg + 56,                 // [18][18]
+  WS_RF = WS_J + 324,                // [18][18]
+  WS_Z = WS_RF + 324,                // [18]
+  WS_D = WS_Z + 18,                  // [18]
+  WS_RR = WS_D + 18,                 // [18]
+  WS_ZD = WS_RR + 18,                // [18]
+  WS_NP = WS_ZD + 18,                // [18]
+  WS_U = WS_NP + 18,                 // [60]
+  WS_CN = WS_U + 60,                 // [40] column norms / misc
+  WS_END = WS_CN + 40,
+  WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
+};
+enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_SIZE = 240 };
+// WI_SC scalars: [0] nW changed flag, [1] rank, [2] n1, [3] n2, [4] iq, [5] ip, [6] status, [7] r1, [8] r2, [9] nD0, [10] done
+
+QM_HD void rot_zyx(const double* e, double* R) {
+  double sz, cz, sy, cy, sx, cx;
+  sincos(e[0], &sz, &cz); sincos(e[1], &sy, &cy); sincos(e[2], &sx, &cx);
+  R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
+  R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
+  R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
+}
+// [upstream] rotationErrorInWorld(Rref, Rcur): rotation vector of Rref Rcur^T
+QM_HD void rotation_error_world(const double* Rr, const double* Rc, double* e) {
+  double R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = Rr[3 * i] * Rc[3 * j] + Rr[3 * i + 1] * Rc[3 * j + 1] + Rr[3 * i + 2] * Rc[3 * j + 2];
+  const double sk[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  double c = 0.5 * (R[0] + R[4] + R[8] - 1.0);
+  c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+  const double th = acos(c);
+  const double k = (th < 1e-8) ? 0.5 : th / (2.0 * sin(th));
+  e[0] = k * sk[0]; e[1] = k * sk[1]; e[2] = k * sk[2];
+}
+// spatial motion cross product  X = A x B
+QM_HD void crm(const double* A, const double* B, double* X) {
+  cross3(A, B, X);
+  cross3(A, B + 3, X + 3);
+  cross3_add(A + 3, B, X + 3);
+}
+
+// Bias accelerations (qdd = 0, no gravity) and body forces of the configuration whose position/velocity level is in kw.
+// FB_i = I_i (acc_i + a_g) + V_i x* (I_i V_i)   with a_g = (0; 0, 0, grav) (grav = 9.81 for RNEA, 0 for momentum rates)
+template <class G>
+QM_HDN void bias_forces(G g, const qmb200_model_desc& M, const double* kw, double grav, double* acc, double* fb) {
+  QM_PFOR(g, k, QM_NJ) {
+    double S[6], X[6];
+    joint_S(M, kw, k, S);
+    crm(kw + KW_V + 6 * k, S, X);
+    const double vk = kw[KW_VEL + k];
+    for (int c = 0; c < 6; ++c) fb[6 * k + c] = X[c] * vk;
+  }
+  g.sync();
+  QM_PFOR(g, i, QM_NJ) {
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    const uint32_t mask = M.pathmask[i];
+    for (int k = 0; k < QM_NJ; ++k)
+      if ((mask >> k) & 1u)
+        for (int c = 0; c < 6; ++c) a[c] += fb[6 * k + c];
+    for (int c = 0; c < 6; ++c) acc[6 * i + c] = a[c];
+  }
+  g.sync();
+  QM_PFOR(g, i, QM_NJ) {
+    double a[6], h[6];
+    for (int c = 0; c < 6; ++c) a[c] = acc[6 * i + c];
+    a[5] += grav;
+    inertia_mul(kw + KW_BODY + 10 * i, a, h);
+    const double* V = kw + KW_V + 6 * i;
+    const double* hb = kw + KW_HB + 6 * i;
+    cross3_add(V, hb, h);            // w x L0
+    cross3_add(V + 3, hb + 3, h);    // + vO x p
+    cross3_add(V, hb + 3, h + 3);    // w x p
+    for (int c = 0; c < 6; ++c) fb[6 * i + c] = h[c];
+  }
+  g.sync();
+}
+
+// classical acceleration (qdd = 0) of a point p moving with body b: aO + wd x p + w x v_p
+QM_HD void point_bias_accel(const double* acc_b, const double* V_b, const double* p, double* out) {
+  double vp[3], t[3];
+  cross3(V_b, p, vp);
+  vp[0] += V_b[3]; vp[1] += V_b[4]; vp[2] += V_b[5];
+  cross3(acc_b, p, t);
+  cross3_add(V_b, vp, t);
+  out[0] = acc_b[3] + t[0]; out[1] = acc_b[4] + t[1]; out[2] = acc_b[5] + t[2];
+}
+
+// updateMeasured + updateDesired. rbd[55] measured state, xd/ud[30] MPC policy sample, u_last[30] (stateful inputLast_).
+template <class G>
+QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* rbd, const double* xd,
+                         const double* ud, const double* u_last, double period, double* W) {
+  double* kw = W + WA_KIN;
+  double* ms = W + WA_MEAS;
+  double* ds = W + WA_DES;
+  // ---- measured (WbcBase.cpp:146-203)
+  if (g.tid() == 0) {
+    for (int k = 0; k < 3; ++k) { ms[k] = rbd[3 + k]; ms[3 + k] = rbd[k]; ms[24 + k] = rbd[27 + k]; }
+    for (int k = 0; k < 18; ++k) { ms[6 + k] = rbd[6 + k]; ms[30 + k] = rbd[30 + k]; }
+    // [upstream] getEulerAnglesZyxDerivativesFromGlobalAngularVelocity
+    double sz, cz, sy, cy;
+    sincos(ms[3], &sz, &cz); sincos(ms[4], &sy, &cy);
+    const double wx = rbd[24], wy = rbd[25], wz = rbd[26];
+    const double dxr = (cz * wx + sz * wy) / cy;
+    ms[24 + 3] = wz + sy * dxr;
+    ms[24 + 4] = -sz * wx + cz * wy;
+    ms[24 + 5] = dxr;
+  }
+  g.sync();
+  kin_positions(g, M, ms, kw);
+  QM_PFOR(g, k, QM_NJ) kw[KW_VEL + k] = ms[24 + k];
+  g.sync();
+  kin_velocities(g, M, false, kw);
+  bias_forces(g, M, kw, C.gravity, W + WA_ACC, W + WA_FB);
+  QM_PFOR(g, j, QM_NJ) {     // nle = S_j . sum of subtree forces (RNEA backward pass)
+    double f[6] = {0, 0, 0, 0, 0, 0}, S[6];
+    const uint32_t mask = M.submask[j];
+    for (int i = 0; i < QM_NJ; ++i)
+      if ((mask >> i) & 1u)
+        for (int c = 0; c < 6; ++c) f[c] += W[WA_FB + 6 * i + c];
+    joint_S(M, kw, j, S);
+    W[WA_NLE + j] = S[0] * f[0] + S[1] * f[1] + S[2] * f[2] + S[3] * f[3] + S[4] * f[4] + S[5] * f[5];
+  }
+  QM_PFOR(g, idx, 576) {     // CRBA: M_ij = S_j . (I^c_i S_i) for j on the path of i
+    const int i = idx / 24, j = idx % 24;
+    double v = 0.0, S[6];
+    if ((M.pathmask[i] >> j) & 1u) {
+      joint_S(M, kw, j, S);
+      const double* F = kw + KW_F + 6 * i;
+      v = S[0] * F[0] + S[1] * F[1] + S[2] * F[2] + S[3] * F[3] + S[4] * F[4] + S[5] * F[5];
+    } else if ((M.pathmask[j] >> i) & 1u) {
+      joint_S(M, kw, i, S);
+      const double* F = kw + KW_F + 6 * j;
+      v = S[0] * F[0] + S[1] * F[1] + S[2] * F[2] + S[3] * F[3] + S[4] * F[4] + S[5] * F[5];
+    }
+    W[WA_M + idx] = v;
+  }
+  QM_PFOR(g, idx, 288) W[WA_JF + idx] = kw[KW_FJ + idx];
+  QM_PFOR(g, idx, 144) W[WA_JEE + idx] = kw[KW_EEJ + idx];
+  QM_PFOR(g, idx, 72) {      // angular Jacobian of the base frame (joint 5)
+    const int r = idx / 24, k = idx % 24;
+    W[WA_JBA + idx] = (((M.pathmask[5] >> k) & 1u) && M.jtype[k] == 1) ? kw[KW_AX + 3 * k + r] : 0.0;
+  }
+  QM_PFOR(g, f, 6) {
+    if (f < 4) {
+      const int b = M.foot_joint[f];
+      point_bias_accel(W + WA_ACC + 6 * b, kw + KW_V + 6 * b, kw + KW_FPOS + 3 * f, W + WA_DJV + 3 * f);
+      for (int r = 0; r < 3; ++r) { ms[48 + 3 * f + r] = kw[KW_FPOS + 3 * f + r]; ms[60 + 3 * f + r] = kw[KW_FVEL + 3 * f + r]; }
+    } else if (f == 4) {
+      for (int r = 0; r < 3; ++r) W[WA_DJBV + r] = W[WA_ACC + 6 * 5 + r];
+    } else {
+      const int b = M.ee_joint;
+      const double* Vb = kw + KW_V + 6 * b;
+      const double* p = kw + KW_EEP;
+      point_bias_accel(W + WA_ACC + 6 * b, Vb, p, W + WA_DJEE);
+      // angular part with the base-orientation columns 3..5 of dJ removed (WbcBase.cpp:553-557)
+      double wd[3] = {W[WA_ACC + 6 * b], W[WA_ACC + 6 * b + 1], W[WA_ACC + 6 * b + 2]};
+      for (int k = 3; k < 6; ++k) {
+        double t[3];
+        cross3(kw + KW_V + 6 * k, kw + KW_AX + 3 * k, t);
+        for (int r = 0; r < 3; ++r) wd[r] -= t[r] * kw[KW_VEL + k];
+      }
+      double vp[3];
+      cross3(Vb, p, vp);
+      for (int r = 0; r < 3; ++r) {
+        W[WA_DJEE + 3 + r] = wd[r];
+        ms[72 + r] = p[r];
+        ms[75 + r] = Vb[3 + r] + vp[r];
+        ms[78 + r] = Vb[r];
+      }
+      for (int r = 0; r < 9; ++r) ms[81 + r] = kw[KW_EER + r];
+    }
+  }
+  g.sync();
+  // ---- desired (WbcBase.cpp:205-238)
+  kin_positions(g, M, xd + 6, kw);
+  centroidal_velocity(g, M, xd, ud, kw);
+  kin_velocities(g, M, false, kw);
+  bias_forces(g, M, kw, 0.0, W + WA_ACC, W + WA_FB);
+  if (g.tid() == 0) {
+    // Adot v = d/dt(A) v: total momentum rate with qdd = 0, moved to the centre of mass
+    double L[3] = {0, 0, 0}, p[3] = {0, 0, 0}, t[3];
+    for (int i = 0; i < QM_NJ; ++i)
+      for (int r = 0; r < 3; ++r) { L[r] += W[WA_FB + 6 * i + r]; p[r] += W[WA_FB + 6 * i + 3 + r]; }
+    cross3(kw + KW_COM, p, t);
+    double rhs[6];
+    // m * getNormalizedCentroidalMomentumRate(input)
+    double fs[3] = {0, 0, 0}, ts[3] = {0, 0, 0};
+    for (int ft = 0; ft < 4; ++ft) {
+      double arm[3];
+      for (int r = 0; r < 3; ++r) { arm[r] = kw[KW_FPOS + 3 * ft + r] - kw[KW_COM + r]; fs[r] += ud[3 * ft + r]; }
+      cross3_add(arm, ud + 3 * ft, ts);
+    }
+    fs[2] -= M.total_mass * C.gravity;
+    for (int r = 0; r < 3; ++r) { rhs[r] = fs[r] - p[r]; rhs[3 + r] = ts[r] - (L[r] - t[r]); }
+    for (int l = 0; l < 18; ++l) {
+      const double ja = (ud[12 + l] - u_last[12 + l]) / period;      // stateful inputLast_ (WbcBase.cpp:224-225)
+      for (int r = 0; r < 6; ++r) rhs[r] -= kw[KW_ACM + r * QM_NJ + 6 + l] * ja;
+    }
+    for (int r = 0; r < 6; ++r) {
+      double a = 0.0;
+      for (int c = 0; c < 6; ++c) a += kw[KW_ABINV + 6 * r + c] * rhs[c];
+      ds[48 + r] = a;
+    }
+    const int b = M.ee_joint;
+    const double* Vb = kw + KW_V + 6 * b;
+    double vp[3];
+    cross3(Vb, kw + KW_EEP, vp);
+    for (int r = 0; r < 3; ++r) { ds[78 + r] = kw[KW_EEP + r]; ds[81 + r] = Vb[3 + r] + vp[r]; }
+    for (int r = 0; r < 9; ++r) ds[84 + r] = kw[KW_EER + r];
+  }
+  QM_PFOR(g, k, QM_NJ) { ds[k] = xd[6 + k]; ds[24 + k] = kw[KW_VEL + k]; }
+  QM_PFOR(g, idx, 12) { ds[54 + idx] = kw[KW_FPOS + idx]; ds[66 + idx] = kw[KW_FVEL + idx]; }
+  g.sync();
+}
+
+// The task stack (WbcBase.cpp:240-578 and the stacks of HierarchicalWbc.cpp:23-43 / HierarchicalMpcWbc.cpp:23-31).
+// Row counts to WI_SC: [7] r1, [8] r2, [9] nD0.
+template <class G>
+QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* ud, int mode, double time,
+                      double* W, int* WI) {
+  const double* ms = W + WA_MEAS;
+  const double* ds = W + WA_DES;
+  const int nc = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
+  const int nsw = 4 - nc;
+  const bool init_stack = (!C.mpc_variant) && (time < C.init_time);
+  const int r1 = C.mpc_variant ? (6 + 3 * nsw) : (init_stack ? 6 : 10 + 3 * nsw);
+  const int r2 = C.mpc_variant ? 12 : 14;
+  const int nD0 = 36 + 5 * nc + 3 * nsw;
+  if (g.tid() == 0) { WI[WI_SC + 7] = r1; WI[WI_SC + 8] = r2; WI[WI_SC + 9] = nD0; }
+  QM_PFOR(g, idx, 18 * 36) W[WW_A0 + idx] = 0.0;
+  QM_PFOR(g, idx, 56 * 36) W[WW_D0 + idx] = 0.0;
+  QM_PFOR(g, idx, 22 * 36) W[WW_A1 + idx] = 0.0;
+  QM_PFOR(g, idx, 14 * 36) W[WW_A2 + idx] = 0.0;
+  QM_PFOR(g, idx, 56) { W[WW_F0 + idx] = 0.0; W[WW_V0 + idx] = 0.0; }
+  g.sync();
+  // level 0, equality rows: floating-base EoM (6), no contact motion (3 nc), zero swing force (3 nsw)
+  QM_PFOR(g, idx, 18 * 36) {
+    const int r = idx / 36, c = idx % 36;
+    double v = 0.0;
+    if (r < 6) {
+      v = (c < 24) ? W[WA_M + 24 * r + c] : -W[WA_JF + (c - 24) * 24 + r];
+    } else {
+      // map row -> (foot, component)
+      int rr = r - 6;
+      if (rr < 3 * nc) {
+        int j = rr / 3, d = rr % 3, ft = 0, cnt = 0;
+        for (int f2 = 0; f2 < 4; ++f2) if ((mode >> (3 - f2)) & 1) { if (cnt == j) { ft = f2; break; } ++cnt; }
+        if (c < 24) v = W[WA_JF + (3 * ft + d) * 24 + c];
+      } else {
+        rr -= 3 * nc;
+        int j = rr / 3, d = rr % 3, ft = 0, cnt = 0;
+        for (int f2 = 0; f2 < 4; ++f2) if (!((mode >> (3 - f2)) & 1)) { if (cnt == j) { ft = f2; break; } ++cnt; }
+        if (c == 24 + 3 * ft + d) v = 1.0;
+      }
+    }
+    W[WW_A0 + idx] = v;
+  }
+  QM_PFOR(g, r, 18) {
+    double v = 0.0;
+    if (r < 6) v = -W[WA_NLE + r];
+    else if (r - 6 < 3 * nc) {
+      int j = (r - 6) / 3, d = (r - 6) % 3, ft = 0, cnt = 0;
+      for (int f2 = 0; f2 < 4; ++f2) if ((mode >> (3 - f2)) & 1) { if (cnt == j) { ft = f2; break; } ++cnt; }
+      v = -W[WA_DJV + 3 * ft + d];
+    }
+    W[WW_B0 + r] = v;
+    W[WW_HJ + r] = W[WA_NLE + 6 + r];
+  }
+  // level 0, inequality rows: torque limits (36), friction pyramid (5 nc), 3 nsw all-zero rows (WbcBase.cpp:458)
+  QM_PFOR(g, idx, 18 * 36) {
+    const int l = idx / 36, c = idx % 36;
+    const double v = (c < 24) ? W[WA_M + 24 * (6 + l) + c] : -W[WA_JF + (c - 24) * 24 + 6 + l];
+    W[WW_D0 + idx] = v;
+    W[WW_D0 + 18 * 36 + idx] = -v;
+  }
+  QM_PFOR(g, l, 18) {
+    W[WW_F0 + l] = C.tau_max[l] - W[WA_NLE + 6 + l];
+    W[WW_F0 + 18 + l] = C.tau_max[l] + W[WA_NLE + 6 + l];
+  }
+  QM_PFOR(g, idx, 5 * 4) {
+    const int j = idx / 5, k = idx % 5;
+    if (j < nc) {
+      int ft = 0, cnt = 0;
+      for (int f2 = 0; f2 < 4; ++f2) if ((mode >> (3 - f2)) & 1) { if (cnt == j) { ft = f2; break; } ++cnt; }
+      double* row = W + WW_D0 + (36 + 5 * j + k) * 36 + 24 + 3 * ft;
+      const double mu = C.friction_mu;
+      if (k == 0) { row[2] = -1.0; }
+      else if (k == 1) { row[0] = 1.0; row[2] = -mu; }
+      else if (k == 2) { row[0] = -1.0; row[2] = -mu; }
+      else if (k == 3) { row[1] = 1.0; row[2] = -mu; }
+      else { row[1] = -1.0; row[2] = -mu; }
+    }
+  }
+  // level 1 / level 2 rows (one thread per scalar right-hand side group; matrices are copies of Jacobian rows)
+  if (g.tid() == 0) {
+    const double* qm = ms; const double* vm = ms + 24;
+    const double* qd = ds; const double* vd = ds + 24;
+    const double* bacc = ds + 48;
+    double* A1 = W + WW_A1; double* b1 = W + WW_B1;
+    double* A2 = W + WW_A2; double* b2 = W + WW_B2;
+    int row = 0;
+    if (init_stack) {
+      for (int i = 0; i < 6; ++i) {       // formulateArmJointNomalTrackingTask
+        A1[(row + i) * 36 + 18 + i] = 1.0;
+        b1[row + i] = C.kp_arm_joint[i] * (qd[18 + i] - qm[18 + i]) + C.kd_arm_joint[i] * (vd[18 + i] - vm[18 + i]);
+      }
+      row += 6;
+    } else {
+      // base height
+      A1[row * 36 + 2] = 1.0;
+      b1[row] = bacc[2] + C.kp_base_height * (qd[2] - qm[2]) + C.kd_base_height * (vd[2] - vm[2]);
+      ++row;
+      // base angular
+      {
+        double sz, cz, sy, cy;
+        sincos(qm[3], &sz, &cz); sincos(qm[4], &sy, &cy);
+        const double T[9] = {0, -sz, cy * cz, 0, cz, cy * sz, 1, 0, -sy};
+        const double dz = vd[3], dy = vd[4];
+        const double Td[9] = {0, -cz * dz, -sy * cz * dy - cy * sz * dz, 0, -sz * dz, -sy * sz * dy + cy * cz * dz, 0, 0, -cy * dy};
+        double Rm[9], Rd[9], err[3];
+        rot_zyx(qm + 3, Rm);
+        rot_zyx(qd + 3, Rd);
+        rotation_error_world(Rd, Rm, err);
+        for (int r = 0; r < 3; ++r) {
+          double wm = 0, wdv = 0, acc = 0;
+          for (int c = 0; c < 3; ++c) {
+            wm += T[3 * r + c] * vm[3 + c];
+            wdv += T[3 * r + c] * vd[3 + c];
+            acc += T[3 * r + c] * bacc[3 + c] + Td[3 * r + c] * vd[3 + c];
+          }
+          for (int c = 0; c < 24; ++c) A1[(row + r) * 36 + c] = W[WA_JBA + 24 * r + c];
+          b1[row + r] = acc + C.kp_base_angular * err[r] + C.kd_base_angular * (wdv - wm) - W[WA_DJBV + r];
+        }
+        row += 3;
+      }
+      if (C.mpc_variant) {
+        for (int r = 0; r < 2; ++r) {
+          A1[(row + r) * 36 + r] = 1.0;
+          b1[row + r] = bacc[r] + C.kp_base_linear * (qd[r] - qm[r]) + C.kd_base_linear * (vd[r] - vm[r]);
+        }
+        row += 2;
+      } else {
+        for (int r = 0; r < 3; ++r) {   // ee linear
+          for (int c = 0; c < 24; ++c) A1[(row + r) * 36 + c] = W[WA_JEE + 24 * r + c];
+          b1[row + r] = C.kp_ee_linear[r] * (ds[78 + r] - ms[72 + r]) + C.kd_ee_linear[r] * (ds[81 + r] - ms[75 + r]) - W[WA_DJEE + r];
+        }
+        row += 3;
+        double err[3];
+        rotation_error_world(ds + 84, ms + 81, err);
+        for (int r = 0; r < 3; ++r) {   // ee angular, base-orientation columns zeroed
+          for (int c = 0; c < 24; ++c) A1[(row + r) * 36 + c] = (c >= 3 && c < 6) ? 0.0 : W[WA_JEE + 24 * (3 + r) + c];
+          b1[row + r] = C.kp_ee_angular[r] * err[r] - C.kd_ee_angular[r] * ms[78 + r] - W[WA_DJEE + 3 + r];
+        }
+        row += 3;
+      }
+      for (int ft = 0; ft < 4; ++ft) {  // swing legs, weighted (Task::operator*)
+        if ((mode >> (3 - ft)) & 1) continue;
+        for (int d = 0; d < 3; ++d) {
+          const double acc = C.kp_swing * (ds[54 + 3 * ft + d] - ms[48 + 3 * ft + d]) + C.kd_swing * (ds[66 + 3 * ft + d] - ms[60 + 3 * ft + d]);
+          for (int c = 0; c < 24; ++c) A1[(row + d) * 36 + c] = C.swing_weight * W[WA_JF + (3 * ft + d) * 24 + c];
+          b1[row + d] = C.swing_weight * (acc - W[WA_DJV + 3 * ft + d]);
+        }
+        row += 3;
+      }
+    }
+    // level 2: contact force (12) [+ base linear (2)]
+    for (int i = 0; i < 12; ++i) { A2[i * 36 + 24 + i] = 1.0; b2[i] = ud[i]; }
+    if (!C.mpc_variant)
+      for (int r = 0; r < 2; ++r) {
+        A2[(12 + r) * 36 + r] = 1.0;
+        b2[12 + r] = bacc[r] + C.kp_base_linear * (qd[r] - qm[r]) + C.kd_base_linear * (vd[r] - vm[r]);
+      }
+  }
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------ dense helpers
+// Householder triangularisation of the m x (n+1) matrix A (row major, ld): columns 0..n-1 are reduced, column n (rhs)
+// is transformed along. On exit the upper triangle holds R and A[0:n][n] = Q'rhs. vh/wj: scratch.
+template <class G>
+QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj) {
+  const int steps = (m - 1 < n) ? m - 1 : n;
+  for (int k = 0; k < steps; ++k) {
+    if (g.tid() == 0) {
+      double s = 0.0;
+      for (int i = k; i < m; ++i) s += A[i * ld + k] * A[i * ld + k];
+      const double nrm = sqrt(s);
+      const double akk = A[k * ld + k];
+      const double alpha = (akk >= 0.0) ? -nrm : nrm;
+      vh[k] = akk - alpha;
+      // beta = 2 / (v'v) with v'v = s - akk^2 + (akk - alpha)^2
+      const double vv = s - akk * akk + vh[k] * vh[k];
+      wj[ld] = (vv > 0.0) ? 2.0 / vv : 0.0;
+      wj[ld + 1] = alpha;
+    }
+    QM_PFOR(g, i, m - k - 1) vh[k + 1 + i] = A[(k + 1 + i) * ld + k];
+    g.sync();
+    const double beta = wj[ld];
+    QM_PFOR(g, jj, n - k) {            // columns k+1..n (rhs included)
+      const int j = k + 1 + jj;
+      double s = 0.0;
+      for (int i = k; i < m; ++i) s += vh[i] * A[i * ld + j];
+      wj[j] = beta * s;
+    }
+    g.sync();
+    QM_PFOR(g, idx, (m - k) * (n - k)) {
+      const int i = k + idx / (n - k), j = k + 1 + idx % (n - k);
+      A[i * ld + j] -= vh[i] * wj[j];
+    }
+    if (g.tid() == 0) A[k * ld + k] = wj[ld + 1];
+    QM_PFOR(g, i, m - k - 1) A[(k + 1 + i) * ld + k] = 0.0;
+    g.sync();
+  }
+}
+
+// back substitution R z = c (R n x n upper in A, c = A[:, n]); one thread
+QM_HD void back_substitute(const double* A, int n, int ld, double* z) {
+  for (int i = n - 1; i >= 0; --i) {
+    double s = A[i * ld + n];
+    for (int j = i + 1; j < n; ++j) s -= A[i * ld + j] * z[j];
+    const double d = A[i * ld + i];
+    z[i] = (d != 0.0) ? s / d : 0.0;
+  }
+}
+
+// Orthonormal basis of the kernel of Abar (r x n, row major ld_a): Householder QR with column pivoting of Abar' (n x r).
+// Q (n x n) is formed explicitly in Qm; the kernel basis is its last n - rank columns. Returns rank via *rank_out.
+template <class G>
+QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double* T, double* Qm, double* vh, double* cn, int* perm,
+                         int* rank_out) {
+  // T = Abar' (n x r), ld = r
+  QM_PFOR(g, idx, n * r) { const int i = idx / r, j = idx % r; T[i * r + j] = Abar[j * ld_a + i]; }
+  QM_PFOR(g, idx, n * n) Qm[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+  g.sync();
+  const int steps = (n < r) ? n : r;
+  int rank = 0;
+  double first = 0.0;
+  for (int k = 0; k < steps; ++k) {
+    QM_PFOR(g, j, r - k) {
+      double s = 0.0;
+      for (int i = k; i < n; ++i) s += T[i * r + k + j] * T[i * r + k + j];
+      cn[k + j] = s;
+    }
+    g.sync();
+    if (g.tid() == 0) {
+      int best = k;
+      for (int j = k + 1; j < r; ++j) if (cn[j] > cn[best]) best = j;
+      perm[0] = best;
+    }
+    g.sync();
+    const int pj = perm[0];
+    const double nrm2 = cn[pj];
+    if (k == 0) first = nrm2;
+    if (!(nrm2 > 1e-18 * (first > 1.0 ? first : 1.0))) break;
+    if (pj != k) {
+      QM_PFOR(g, i, n) { const double t = T[i * r + k]; T[i * r + k] = T[i * r + pj]; T[i * r + pj] = t; }
+      g.sync();
+    }
+    ++rank;
+    if (k >= n - 1) break;              // last row: nothing to reflect
+    const double akk = T[k * r + k];
+    const double nrm = sqrt(nrm2);
+    const double alpha = (akk >= 0.0) ? -nrm : nrm;
+    const double vk = akk - alpha;
+    const double vv = nrm2 - akk * akk + vk * vk;
+    const double beta = (vv > 0.0) ? 2.0 / vv : 0.0;
+    QM_PFOR(g, i, n - k) vh[k + i] = (i == 0) ? vk : T[(k + i) * r + k];
+    g.sync();
+    // T <- H T (columns k..r-1),  Q <- Q H (all rows)
+    QM_PFOR(g, jj, r - k) {
+      const int j = k + jj;
+      double s = 0.0;
+      for (int i = k; i < n; ++i) s += vh[i] * T[i * r + j];
+      s *= beta;
+      for (int i = k; i < n; ++i) T[i * r + j] -= vh[i] * s;
+    }
+    QM_PFOR(g, i, n) {
+      double s = 0.0;
+      for (int c = k; c < n; ++c) s += Qm[i * n + c] * vh[c];
+      s *= beta;
+      for (int c = k; c < n; ++c) Qm[i * n + c] -= s * vh[c];
+    }
+    g.sync();
+  }
+  if (g.tid() == 0) *rank_out = rank;
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------ level 0
+// min 1/2|A0 z - b0|^2 + eps/2 |z|^2 + 1/2 |(D0 z - f0)+|^2  by Newton iteration on the active set of violated rows.
+template <class G>
+QM_HDN void wbc_level0(G g, double* W, int* WI) {
+  const int nD0 = WI[WI_SC + 9];
+  const int ld = WB_QR_LD;
+  double* QR = W + WS_QR;
+  QM_PFOR(g, i, 56) WI[WI_INW + i] = 0;
+  if (g.tid() == 0) WI[WI_SC + 10] = 0;
+  g.sync();
+  for (int iter = 0; iter < 40; ++iter) {
+    if (g.tid() == 0) {                    // active row list
+      int nw = 0;
+      for (int i = 0; i < nD0 && nw < WB_MAXW; ++i) if (WI[WI_INW + i]) WI[WI_PERM + nw++] = i;
+      WI[WI_SC + 0] = nw;
+    }
+    g.sync();
+    const int nw = WI[WI_SC + 0];
+    const int m = nw + 18 + 36;
+    // rows: active inequality rows, equality rows, sqrt(eps) I (large rows first: stable for the tiny regularisation)
+    QM_PFOR(g, idx, m * ld) {
+      const int r = idx / ld, c = idx % ld;
+      double v;
+      if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? W[WW_D0 + 36 * i + c] : W[WW_F0 + i]; }
+      else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? W[WW_A0 + 36 * i + c] : W[WW_B0 + i]; }
+      else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
+      QR[idx] = v;
+    }
+    g.sync();
+    householder_ls(g, QR, m, 36, ld, W + WS_VH, W + WS_WJ);
+    if (g.tid() == 0) back_substitute(QR, 36, ld, W + WW_X);
+    g.sync();
+    QM_PFOR(g, i, nD0) {
+      double s = -W[WW_F0 + i];
+      for (int c = 0; c < 36; ++c) s += W[WW_D0 + 36 * i + c] * W[WW_X + c];
+      W[WS_RES + i] = s;
+    }
+    g.sync();
+    if (g.tid() == 0) {
+      int changed = 0;
+      for (int i = 0; i < nD0; ++i) {
+        const double tol = 1e-9 * (1.0 + fabs(W[WW_F0 + i]));
+        const int in = WI[WI_INW + i];
+        const int nw_in = in ? (W[WS_RES + i] > -tol) : (W[WS_RES + i] > tol);
+        if (nw_in != in) { WI[WI_INW + i] = nw_in; ++changed; }
+      }
+      WI[WI_SC + 10] = (changed == 0);
+      if (changed && iter == 39) WI[WI_SC + 6] |= WST_QP_MAX_ITER;
+    }
+    g.sync();
+    if (WI[WI_SC + 10]) break;
+  }
+  QM_PFOR(g, i, 56) W[WW_V0 + i] = (i < nD0 && W[WS_RES + i] > 0.0) ? W[WS_RES + i] : 0.0;
+  g.sync();
+}
+
+// ------------------------------------------------------------------------------------------ levels 1, 2
+// min 1/2|Ab z - bb|^2 + eps/2|z|^2  s.t.  Gg z <= gg   (n <= 18 unknowns, r rows, nD0 inequality rows)
+// Goldfarb-Idnani dual active set; J = R^-1 from the Householder factor of [Ab; sqrt(eps) I]. z returned in WS_Z.
+template <class G>
+QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
+  const int ld = n + 1;
+  double* QR = W + WS_QR;
+  double* J = W + WS_J;
+  double* RF = W + WS_RF;
+  const int m = r + n;
+  QM_PFOR(g, idx, m * ld) {
+    const int i = idx / ld, c = idx % ld;
+    double v;
+    if (i < r) v = (c < n) ? W[WS_GA + 18 * i + c] : W[WS_GB + i];
+    else v = (c == i - r) ? 1e-6 : 0.0;
+    QR[idx] = v;
+  }
+  g.sync();
+  householder_ls(g, QR, m, n, ld, W + WS_VH, W + WS_WJ);
+  if (g.tid() == 0) back_substitute(QR, n, ld, W + WS_Z);
+  // J = R^-1 (upper triangular), column by column
+  QM_PFOR(g, c, n) {
+    for (int i = n - 1; i >= 0; --i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int j = i + 1; j <= c; ++j) s -= QR[i * ld + j] * J[j * 18 + c];
+      J[i * 18 + c] = (i <= c) ? s / QR[i * ld + i] : 0.0;
+    }
+  }
+  g.sync();
+  if (g.tid() == 0) { WI[WI_SC + 4] = 0; WI[WI_SC + 10] = 0; }
+  QM_PFOR(g, i, 56) WI[WI_IGN + i] = 0;
+  g.sync();
+  for (int outer = 0; outer < 200; ++outer) {
+    // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible)
+    QM_PFOR(g, i, nD0) {
+      double s = W[WS_Gg + i];
+      for (int c = 0; c < n; ++c) s -= W[WS_GG + 18 * i + c] * W[WS_Z + c];
+      W[WS_RES + i] = s;
+    }
+    g.sync();
+    if (g.tid() == 0) {
+      // ---- one full GI major iteration (serial; n <= 18)
+      int iq = WI[WI_SC + 4];
+      int* act = WI + WI_ACT;
+      double* u = W + WS_U;
+      double* z = W + WS_Z;
+      double* d = W + WS_D;
+      double* rr = W + WS_RR;
+      double* zd = W + WS_ZD;
+      double* np = W + WS_NP;
+      int ip = -1;
+      double worst = 0.0;
+      for (int i = 0; i < nD0; ++i) {
+        if (WI[WI_IGN + i]) continue;
+        bool is_act = false;
+        for (int k = 0; k < iq; ++k) if (act[k] == i) { is_act = true; break; }
+        if (is_act) continue;
+        const double sc = 1.0 + fabs(W[WS_Gg + i]);
+        const double viol = W[WS_RES + i] / sc;
+        if (viol < -1e-9 && viol < worst) { worst = viol; ip = i; }
+      }
+      if (ip < 0) { WI[WI_SC + 10] = 1; }
+      else {
+        for (int c = 0; c < n; ++c) np[c] = -W[WS_GG + 18 * ip + c];
+        u[iq] = 0.0;
+        double cip = W[WS_RES + ip];
+        for (int inner = 0; inner < 200; ++inner) {
+          // d = J' np ; zd = J[:, iq:] d[iq:] ; rr = RF^-1 d[:iq]
+          for (int c = 0; c < n; ++c) { double s = 0.0; for (int i = 0; i < n; ++i) s += J[i * 18 + c] * np[i]; d[c] = s; }
+          for (int i = 0; i < n; ++i) { double s = 0.0; for (int c = iq; c < n; ++c) s += J[i * 18 + c] * d[c]; zd[i] = s; }
+          for (int i = iq - 1; i >= 0; --i) {
+            double s = d[i];
+            for (int j = i + 1; j < iq; ++j) s -= RF[i * 18 + j] * rr[j];
+            rr[i] = s / RF[i * 18 + i];
+          }
+          double t1 = 1e300; int l = -1;
+          for (int k = 0; k < iq; ++k)
+            if (rr[k] > 1e-14 * (1.0 + fabs(u[k])) && u[k] / rr[k] < t1) { t1 = u[k] / rr[k]; l = k; }
+          double zn = 0.0, nn2 = 0.0;
+          for (int i = 0; i < n; ++i) { zn += zd[i] * np[i]; nn2 += np[i] * np[i]; }
+          double t2 = 1e300;
+          // in the J-scaled metric |J' np|^2 = np' H^-1 np; a direction exists iff the null-space part of d is non-zero
+          double dn2 = 0.0, dall = 0.0;
+          for (int c = 0; c < n; ++c) { dall += d[c] * d[c]; if (c >= iq) dn2 += d[c] * d[c]; }
+          if (dn2 > 1e-26 * dall && zn > 0.0) t2 = -cip / zn;
+          const double t = (t1 < t2) ? t1 : t2;
+          if (t >= 1e300) {
+            // dependent normal and no constraint to drop: infeasible up to rounding -> ignore a marginally violated row
+            if (fabs(cip) < 1e-6 * (1.0 + fabs(W[WS_Gg + ip]))) WI[WI_IGN + ip] = 1;
+            else { WI[WI_SC + 6] |= WST_DEGENERATE; WI[WI_IGN + ip] = 1; }
+            break;
+          }
+          if (t2 < 1e300) for (int i = 0; i < n; ++i) z[i] += t * zd[i];
+          for (int k = 0; k < iq; ++k) u[k] -= t * rr[k];
+          u[iq] += t;
+          if (t == t2) {
+            // add constraint ip: Givens rotations zero d[iq+1..n-1], applied to the columns of J
+            for (int j = n - 1; j > iq; --j) {
+              const double a = d[j - 1], b = d[j];
+              if (b == 0.0) continue;
+              const double h = hypot(a, b);
+              const double cs = a / h, sn = b / h;
+              d[j - 1] = h; d[j] = 0.0;
+              for (int i = 0; i < n; ++i) {
+                const double x1 = J[i * 18 + j - 1], x2 = J[i * 18 + j];
+                J[i * 18 + j - 1] = cs * x1 + sn * x2;
+                J[i * 18 + j] = -sn * x1 + cs * x2;
+              }
+            }
+            for (int i = 0; i <= iq; ++i) RF[i * 18 + iq] = d[i];
+            act[iq] = ip;
+            ++iq;
+            break;
+          }
+          // drop constraint l and continue with the same ip
+          for (int k = l; k < iq - 1; ++k) {
+            act[k] = act[k + 1]; u[k] = u[k + 1];
+            for (int i = 0; i <= k + 1; ++i) RF[i * 18 + k] = RF[i * 18 + k + 1];
+          }
+          u[iq - 1] = u[iq];
+          --iq;
+          for (int k = l; k < iq; ++k) {   // restore the triangle: rotate rows k, k+1 of RF (columns of J)
+            const double a = RF[k * 18 + k], b = RF[(k + 1) * 18 + k];
+            if (b == 0.0) continue;
+            const double h = hypot(a, b);
+            const double cs = a / h, sn = b / h;
+            for (int c = k; c < iq; ++c) {
+              const double x1 = RF[k * 18 + c], x2 = RF[(k + 1) * 18 + c];
+              RF[k * 18 + c] = cs * x1 + sn * x2;
+              RF[(k + 1) * 18 + c] = -sn * x1 + cs * x2;
+            }
+            for (int i = 0; i < n; ++i) {
+              const double x1 = J[i * 18 + k], x2 = J[i * 18 + k + 1];
+              J[i * 18 + k] = cs * x1 + sn * x2;
+              J[i * 18 + k + 1] = -sn * x1 + cs * x2;
+            }
+          }
+          cip = W[WS_Gg + ip];
+          for (int c = 0; c < n; ++c) cip -= W[WS_GG + 18 * ip + c] * z[c];
+          if (inner == 199) WI[WI_SC + 6] |= WST_QP_MAX_ITER;
+        }
+        WI[WI_SC + 4] = iq;
+      }
+      if (outer == 199) WI[WI_SC + 6] |= WST_QP_MAX_ITER;
+    }
+    g.sync();
+    if (WI[WI_SC + 10]) break;
+  }
+}
+
+// HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
+template <class G>
+QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
+  const int r1 = WI[WI_SC + 7], r2 = WI[WI_SC + 8], nD0 = WI[WI_SC + 9];
+  if (g.tid() == 0) WI[WI_SC + 6] = 0;
+  g.sync();
+  // ---- level 0
+  wbc_level0(g, W, WI);
+  kernel_basis(g, W + WW_A0, 18, 36, 36, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1);
+  const int n1 = 36 - WI[WI_SC + 1];
+  QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + (36 - n1) + c] : 0.0; }
+  g.sync();
+  // ---- level 1 in the coordinates x = x0 + Z0 z
+  int n2 = 0;
+  if (n1 > 0) {
+    QM_PFOR(g, idx, r1 * 18) {
+      const int i = idx / 18, c = idx % 18;
+      double s = 0.0;
+      if (c < n1) for (int k = 0; k < 36; ++k) s += W[WW_A1 + 36 * i + k] * W[WW_Z0 + 18 * k + c];
+      W[WS_GA + idx] = s;
+    }
+    QM_PFOR(g, i, r1) {
+      double s = W[WW_B1 + i];
+      for (int k = 0; k < 36; ++k) s -= W[WW_A1 + 36 * i + k] * W[WW_X + k];
+      W[WS_GB + i] = s;
+    }
+    QM_PFOR(g, idx, nD0 * 18) {
+      const int i = idx / 18, c = idx % 18;
+      double s = 0.0;
+      if (c < n1) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * W[WW_Z0 + 18 * k + c];
+      W[WS_GG + idx] = s;
+    }
+    QM_PFOR(g, i, nD0) {
+      double s = W[WW_F0 + i] + W[WW_V0 + i];
+      for (int k = 0; k < 36; ++k) s -= W[WW_D0 + 36 * i + k] * W[WW_X + k];
+      W[WS_Gg + i] = s;
+    }
+    g.sync();
+    wbc_gi(g, n1, r1, nD0, W, WI);
+    QM_PFOR(g, k, 36) {
+      double s = 0.0;
+      for (int c = 0; c < n1; ++c) s += W[WW_Z0 + 18 * k + c] * W[WS_Z + c];
+      W[WW_X + k] += s;
+    }
+    g.sync();
+    // kernel of A1 Z0 -> Z1 = Z0 N1
+    kernel_basis(g, W + WS_GA, r1, n1, 18, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1);
+    n2 = n1 - WI[WI_SC + 1];
+    if (n2 > 12) n2 = 12;
+    QM_PFOR(g, idx, 36 * 12) {
+      const int i = idx / 12, c = idx % 12;
+      double s = 0.0;
+      if (c < n2) for (int k = 0; k < n1; ++k) s += W[WW_Z0 + 18 * i + k] * W[WS_Q + n1 * k + (n1 - n2) + c];
+      W[WW_Z1 + idx] = s;
+    }
+    g.sync();
+  }
+  // ---- level 2 in the coordinates x = x1 + Z1 z
+  if (n2 > 0) {
+    QM_PFOR(g, idx, r2 * 18) {
+      const int i = idx / 18, c = idx % 18;
+      double s = 0.0;
+      if (c < n2) for (int k = 0; k < 36; ++k) s += W[WW_A2 + 36 * i + k] * W[WW_Z1 + 12 * k + c];
+      W[WS_GA + idx] = s;
+    }
+    QM_PFOR(g, i, r2) {
+      double s = W[WW_B2 + i];
+      for (int k = 0; k < 36; ++k) s -= W[WW_A2 + 36 * i + k] * W[WW_X + k];
+      W[WS_GB + i] = s;
+    }
+    QM_PFOR(g, idx, nD0 * 18) {
+      const int i = idx / 18, c = idx % 18;
+      double s = 0.0;
+      if (c < n2) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * W[WW_Z1 + 12 * k + c];
+      W[WS_GG + idx] = s;
+    }
+    QM_PFOR(g, i, nD0) {
+      double s = W[WW_F0 + i] + W[WW_V0 + i];
+      for (int k = 0; k < 36; ++k) s -= W[WW_D0 + 36 * i + k] * W[WW_X + k];
+      W[WS_Gg + i] = s;
+    }
+    g.sync();
+    wbc_gi(g, n2, r2, nD0, W, WI);
+    QM_PFOR(g, k, 36) {
+      double s = 0.0;
+      for (int c = 0; c < n2; ++c) s += W[WW_Z1 + 12 * k + c] * W[WS_Z + c];
+      W[WW_X + k] += s;
+    }
+    g.sync();
+  }
+  // ---- torque recovery: tau = [M_j, -J_j'] x + h_j   (rows 0..17 of D0)
+  QM_PFOR(g, i, 54) {
+    double v;
+    if (i < 36) v = W[WW_X + i];
+    else {
+      const int l = i - 36;
+      v = W[WW_HJ + l];
+      for (int c = 0; c < 36; ++c) v += W[WW_D0 + 36 * l + c] * W[WW_X + c];
+    }
+    cmd[i] = v;
+  }
+  if (g.tid() == 0) {
+    int st = WI[WI_SC + 6];
+    for (int i = 0; i < 36; ++i) if (!(W[WW_X + i] == W[WW_X + i])) st |= WST_NAN;
+    *status = st;
+  }
+  g.sync();
+}
+
+// One whole-body-control solve: WbcBase::update + HierarchicalWbc::update.
+template <class G>
+QM_HDN void wbc_update(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* xd, const double* ud,
+                       const double* rbd, int mode, double period, double time, const double* u_last, double* W, int* WI,
+                       double* cmd, int* status) {
+  wbc_dynamics(g, M, C, rbd, xd, ud, u_last, period, W);
+  wbc_tasks(g, M, C, ud, mode & 15, time, W, WI);
+  wbc_solve(g, W, WI, cmd, status);
+}
+
+}  // namespace qm

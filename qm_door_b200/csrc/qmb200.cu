@@ -410,3 +410,169 @@ int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, 
 }
 
 }  // extern "C"
+
+// ============================================================================================ whole-body controller
+#include "qm_wbc.h"
+
+constexpr int kWbcInDoubles = 30 + 30 + 56 + 32;   // xd, ud, rbd (padded), u_last (padded)
+constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
+
+// CTA per solve: rigid-body dynamics of both configurations, task stack, 3-level hierarchical QP, torque recovery.
+__global__ void __launch_bounds__(128) k_wbc(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
+                                              const double* ud, const double* rbd, const int32_t* mode, const double* period,
+                                              const double* time, double* u_last, double* cmd, int32_t* status) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  extern __shared__ double smem[];
+  double* W = smem;
+  double* in = smem + WW_SIZE;
+  int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
+  for (int i = threadIdx.x; i < 30; i += blockDim.x) { in[i] = xd[30 * b + i]; in[30 + i] = ud[30 * b + i]; in[116 + i] = u_last[30 * b + i]; }
+  for (int i = threadIdx.x; i < 55; i += blockDim.x) in[60 + i] = rbd[55 * b + i];
+  __syncthreads();
+  wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode[b], period[b], time[b], in + 116, W, WI, cmd + 54 * b, status + b);
+  for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
+}
+
+struct qmb200_wbc_ctx {
+  int device = 0, B = 0;
+  qmb200_model_desc* dM = nullptr;
+  qmb200_wbc_desc* dC = nullptr;
+  double *xd = nullptr, *ud = nullptr, *rbd = nullptr, *period = nullptr, *time = nullptr, *u_last = nullptr, *cmd = nullptr;
+  int32_t *mode = nullptr, *status = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double total_ms = 0.0;
+  int64_t launches = 0;
+  bool pending = false;
+};
+
+static void wbc_harvest(qmb200_wbc_ctx* c) {
+  if (c->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->e0, c->e1) == cudaSuccess) c->total_ms += ms;
+    c->pending = false;
+  }
+}
+
+static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, const double* rbd, const int32_t* mode,
+                      const double* period, const double* time, double* cmd, int32_t* status) {
+  wbc_harvest(c);
+  CUDA_OK(cudaEventRecord(c->e0, c->stream));
+  k_wbc<<<c->B, 128, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, cmd, status);
+  CUDA_OK(cudaEventRecord(c->e1, c->stream));
+  CUDA_OK(cudaGetLastError());
+  c->pending = true;
+  c->launches++;
+  return 0;
+}
+
+extern "C" {
+
+int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc, int32_t batch, int32_t device,
+                      qmb200_wbc_ctx** out) {
+  if (!model || !wbc || !out) return fail("qmb200_wbc_create: null argument");
+  if (batch <= 0) return fail("qmb200_wbc_create: batch must be positive");
+  if (model->nj != QM_NJ) return fail("qmb200_wbc_create: model must have 24 one-DoF joints");
+  if (qmb200_device_count() <= 0) return fail("qmb200_wbc_create: no CUDA device available (this library has no CPU fallback)");
+  CUDA_OK(cudaSetDevice(device));
+  qmb200_wbc_ctx* c = new qmb200_wbc_ctx();
+  c->device = device; c->B = batch;
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&c->e0));
+  CUDA_OK(cudaEventCreate(&c->e1));
+  CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
+  CUDA_OK(cudaMalloc(&c->dC, sizeof(*wbc)));
+  CUDA_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(c->dC, wbc, sizeof(*wbc), cudaMemcpyHostToDevice));
+  const size_t B = batch;
+  CUDA_OK(cudaMalloc(&c->xd, B * 30 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->ud, B * 30 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->rbd, B * 55 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->period, B * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->time, B * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->u_last, B * 30 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->cmd, B * 54 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
+  CUDA_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));
+  CUDA_OK(cudaMemset(c->u_last, 0, B * 30 * sizeof(double)));
+  CUDA_OK(cudaFuncSetAttribute(k_wbc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+  *out = c;
+  return 0;
+}
+
+int qmb200_wbc_destroy(qmb200_wbc_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->mode, c->status};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->e0) cudaEventDestroy(c->e0);
+  if (c->e1) cudaEventDestroy(c->e1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int qmb200_wbc_reset(qmb200_wbc_ctx* c) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemsetAsync(c->u_last, 0, (size_t)c->B * 30 * sizeof(double), c->stream));
+  return 0;
+}
+
+int qmb200_wbc_set_gains(qmb200_wbc_ctx* c, const qmb200_wbc_desc* wbc) {
+  if (!c || !wbc) return fail("qmb200_wbc_set_gains: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));     // gains are snapshotted between solves, never mid-solve
+  CUDA_OK(cudaMemcpy(c->dC, wbc, sizeof(*wbc), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int qmb200_wbc_sync(qmb200_wbc_ctx* c) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  wbc_harvest(c);
+  return 0;
+}
+
+void* qmb200_wbc_stream(qmb200_wbc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int qmb200_wbc_kernel_time(qmb200_wbc_ctx* c, double* total_ms, int64_t* launches, int32_t reset) {
+  if (!c) return fail("null ctx");
+  if (qmb200_wbc_sync(c) != 0) return -1;
+  if (total_ms) *total_ms = c->total_ms;
+  if (launches) *launches = c->launches;
+  if (reset) { c->total_ms = 0.0; c->launches = 0; }
+  return 0;
+}
+
+int qmb200_wbc_batch_dev(qmb200_wbc_ctx* c, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                         const double* period, const double* time, double* cmd, int32_t* status) {
+  if (!c || !x_des || !u_des || !rbd || !mode || !period || !time || !cmd || !status) return fail("qmb200_wbc_batch_dev: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  return wbc_launch(c, x_des, u_des, rbd, mode, period, time, cmd, status);
+}
+
+int qmb200_wbc_batch(qmb200_wbc_ctx* c, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
+                     const double* period, const double* time, double* cmd, int32_t* status) {
+  if (!c || !x_des || !u_des || !rbd || !mode || !period || !time || !cmd) return fail("qmb200_wbc_batch: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t B = c->B;
+  cudaStream_t st = c->stream;
+  CUDA_OK(cudaMemcpyAsync(c->xd, x_des, B * 30 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->ud, u_des, B * 30 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->rbd, rbd, B * 55 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->mode, mode, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->period, period, B * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->time, time, B * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (wbc_launch(c, c->xd, c->ud, c->rbd, c->mode, c->period, c->time, c->cmd, c->status) != 0) return -1;
+  CUDA_OK(cudaMemcpyAsync(cmd, c->cmd, B * 54 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, c->status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  wbc_harvest(c);
+  return 0;
+}
+
+}  // extern "C"

@@ -64,3 +64,55 @@ def nominal_ee_pose():
     # rotation about y by (q2 + q3 + q4) composed with joint1 (z), joint5 (z), joint6 (x) at zero -> pure y rotation
     ang = 1.11 - 0.69 - 0.40
     return np.array([0.6253031727266175, 0.0, 0.8300452360692332, 0.0, np.sin(ang / 2), 0.0, np.cos(ang / 2)])
+
+
+def rbd_from_state(q, v):
+    """rbdState[55] layout of qm_estimation/src/StateEstimateBase.cpp:29-102 from generalized coordinates / Euler-rate velocities."""
+    q, v = np.asarray(q), np.asarray(v)
+    r = np.zeros(q.shape[:-1] + (55,))
+    r[..., 0:3], r[..., 3:6], r[..., 6:24] = q[..., 3:6], q[..., 0:3], q[..., 6:24]
+    z, y = q[..., 3], q[..., 4]
+    dz, dy, dx = v[..., 3], v[..., 4], v[..., 5]
+    r[..., 24] = -np.sin(z) * dy + np.cos(y) * np.cos(z) * dx      # world angular velocity from ZYX Euler rates
+    r[..., 25] = np.cos(z) * dy + np.cos(y) * np.sin(z) * dx
+    r[..., 26] = dz - np.sin(y) * dx
+    r[..., 27:30] = v[..., 0:3]
+    r[..., 30:48] = v[..., 6:24]
+    return r
+
+
+class WbcWorkload:
+    """BASELINE config 5: B whole-body-control solves, contact pattern uniform over the 16 modes, measured
+    state = nominal pose + perturbation with velocities U(-vel, vel), desired = nominal + small perturbation with
+    weight-compensating forces, period 1 ms, time 11 s (steady-state task stack)."""
+
+    def __init__(self, B, seed=20261020, vel=0.5, time=11.0, period=0.001):
+        from . import load_wbc
+        rng = np.random.default_rng(seed)
+        self.model = load_model()
+        _, _, self.x_init = load_problem(self.model)
+        self.wbc = load_wbc(self.model)
+        self.B = B
+        self.mode = rng.integers(0, 16, B).astype(np.int32)
+        q = np.tile(self.x_init[6:], (B, 1))
+        q[:, 0:2] += rng.uniform(-0.05, 0.05, (B, 2))
+        q[:, 2] += rng.uniform(-0.02, 0.02, B)
+        q[:, 3:6] += rng.uniform(-0.1, 0.1, (B, 3))
+        q[:, 6:] += rng.uniform(-0.1, 0.1, (B, 18))
+        v = rng.uniform(-vel, vel, (B, 24))
+        self.rbd = rbd_from_state(q, v)
+        self.x_des = np.tile(self.x_init, (B, 1))
+        self.x_des[:, 0:6] += rng.uniform(-0.05, 0.05, (B, 6))
+        self.x_des[:, 6:] += rng.uniform(-0.02, 0.02, (B, 24))
+        self.u_des = np.zeros((B, 30))
+        m, g = self.model.total_mass, 9.81
+        for b in range(B):
+            md = int(self.mode[b])
+            ns = bin(md).count("1")
+            for leg in range(4):
+                if (md >> (3 - leg)) & 1:
+                    self.u_des[b, 3 * leg + 2] = m * g / ns
+        self.u_des[:, 12:] += rng.uniform(-0.1, 0.1, (B, 18))
+        self.u_last = self.u_des + rng.uniform(-1e-3, 1e-3, (B, 30))   # previous MPC input (inputLast_), applied as a warm-up call
+        self.period = np.full(B, period)
+        self.time = np.full(B, time)

@@ -1,0 +1,183 @@
+"""Whole-body controller: oracle self-consistency, CPU port vs oracle / golden vectors (no GPU), CUDA path vs the same (gpu)."""
+import numpy as np
+import pytest
+
+from helpers import ROOT, rel_l2
+
+GOLD = ROOT + "/tests/golden/wbc_config5.npz"
+TOL = 1e-6          # (x*, tau) 1e-6 on converged instances
+EXPECTED = 1e-8
+
+
+def run_backend(update, g):
+    """update(variant, idx, x_des, u_des, rbd, mode, period, time, u_last) -> cmd for the selected rows."""
+    cmd = np.zeros_like(g["cmd"])
+    for variant in (0, 1):
+        idx = np.where(g["variant"] == variant)[0]
+        cmd[idx] = update(variant, idx, g["x_des"][idx], g["u_des"][idx], g["rbd"][idx], g["mode"][idx], g["period"][idx],
+                          g["time"][idx], g["u_last"][idx])
+    return cmd
+
+
+def check_golden(cmd, g, tol):
+    """Every solve within `tol`; the typical solve far below it. (All-feet-in-the-air stacks leave the lowest level rank
+    deficient, where only the 1e-12 regularisation selects the solution: those solves carry ~1e-7 of rounding.)"""
+    errs = np.array([rel_l2(cmd[b], g["cmd"][b]) for b in range(cmd.shape[0])])
+    assert errs.max() < tol, (int(errs.argmax()), int(g["mode"][errs.argmax()]), errs.max())
+    assert np.median(errs) < 1e-10, np.median(errs)
+    return errs.max()
+
+
+def test_static_stance_physics(oracle_inputs):
+    """nominal stance, zero velocity, weight-compensating MPC input: feet carry the weight, hierarchy holds."""
+    from oracle import sqp, wbc
+    m, P = oracle_inputs
+    x = P.x_init.copy()
+    u = sqp.weight_compensating_input(m, 15)
+    O = wbc.Wbc(m, P)
+    O.input_last = u.copy()
+    cmd, dbg = O.update(x, u, wbc.rbd_from_state(m, x, np.zeros(24)), 15, 0.002, 11.0, return_debug=True)
+    fz = cmd[24:36].reshape(4, 3)[:, 2]
+    assert (fz > 0).all() and abs(fz.sum() - m.total_mass * 9.81) < 0.05 * m.total_mass * 9.81
+    assert np.abs(cmd[36:]).max() < 35.278              # torques within limits
+    l0, l1, l2 = dbg["levels"]
+    t0, t1, _ = dbg["tasks"]
+    # strict hierarchy: lower levels do not change the residual of higher ones
+    assert abs(np.linalg.norm(t0.a @ l0.x - t0.b) - np.linalg.norm(t0.a @ l2.x - t0.b)) < 1e-8
+    assert abs(np.linalg.norm(t1.a @ l1.x - t1.b) - np.linalg.norm(t1.a @ l2.x - t1.b)) < 1e-7
+    assert (t0.d @ l2.x - t0.f - l0.v).max() < 1e-8      # level-0 inequalities (relaxed by their slack) still hold
+    # equations of motion: M a + h = S' tau + J' f
+    M = dbg["M"]
+    lhs = M["M"] @ cmd[:24] + M["nle"]
+    rhs = np.concatenate([np.zeros(6), cmd[36:]]) + M["J"].T @ cmd[24:36]
+    assert np.abs(lhs - rhs).max() < 1e-6
+
+
+def test_oracle_qp_solver_kkt():
+    """The exact dual active-set QP solver of the oracle against KKT conditions on random strictly convex QPs."""
+    from scipy.optimize import nnls
+    from oracle.wbc import solve_qp_gi
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        n, mc = int(rng.integers(2, 10)), int(rng.integers(1, 25))
+        A = rng.standard_normal((n + 2, n))
+        H = A.T @ A + 1e-3 * np.eye(n)
+        c = 3 * rng.standard_normal(n)
+        Cm = rng.standard_normal((mc, n))
+        d = Cm @ rng.standard_normal(n) + rng.uniform(0, 1, mc)
+        x, act, it = solve_qp_gi(np.linalg.inv(np.linalg.cholesky(H)).T, c, Cm, d)
+        g, slack = H @ x + c, d - Cm @ x
+        a = np.where(slack < 1e-8)[0]
+        rn = nnls(Cm[a].T, -g)[1] if len(a) else np.linalg.norm(g)
+        assert rn < 1e-7 * max(1.0, np.linalg.norm(c)) and slack.min() > -1e-8
+
+
+def test_cport_matches_golden(descs):
+    """CPU port of the WBC kernels (level-0 Newton + null-space GI) == oracle (reference QP formulation + GI on it)."""
+    import qm_door_b200 as q
+    from oracle import abi_fill
+    model = descs[0]
+    g = np.load(GOLD)
+    assert (g["iters"].sum(1) > 0).sum() > 10          # the fixture exercises active inequality constraints
+
+    def update(variant, idx, xd, ud, rbd, mode, period, time, ul):
+        w = q.load_wbc(model)
+        w.mpc_variant = variant
+        cmd, st = abi_fill.cport_wbc(model, w, xd, ud, rbd, mode, period, time, ul.copy())
+        assert (st == 0).all(), st
+        return cmd
+    assert check_golden(run_backend(update, g), g, TOL) < TOL
+
+
+def test_cport_stateful_input_last(descs, oracle_inputs):
+    """inputLast_ is per-solve state: two consecutive calls use (u2 - u1)/period as joint acceleration (WbcBase.cpp:224-225)."""
+    import qm_door_b200 as q
+    from oracle import abi_fill, wbc
+    from qm_door_b200 import workload
+    m, P = oracle_inputs
+    W = workload.WbcWorkload(4, seed=3, vel=0.05)
+    ul = np.zeros((4, 30))
+    abi_fill.cport_wbc(W.model, W.wbc, W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time, ul)
+    assert np.array_equal(ul, W.u_des)
+    u2 = W.u_des.copy()
+    u2[:, 12:] += 1e-4
+    cmd, st = abi_fill.cport_wbc(W.model, W.wbc, W.x_des, u2, W.rbd, W.mode, W.period, W.time, ul)
+    for b in range(4):
+        O = wbc.Wbc(m, P)
+        O.update(W.x_des[b], W.u_des[b], W.rbd[b], int(W.mode[b]), W.period[b], W.time[b])
+        ref = O.update(W.x_des[b], u2[b], W.rbd[b], int(W.mode[b]), W.period[b], W.time[b])
+        assert rel_l2(cmd[b], ref) < EXPECTED
+
+
+@pytest.mark.gpu
+def test_cuda_matches_golden(descs):
+    import qm_door_b200 as q
+    model = descs[0]
+    g = np.load(GOLD)
+
+    def update(variant, idx, xd, ud, rbd, mode, period, time, ul):
+        w = q.load_wbc(model)
+        w.mpc_variant = variant
+        ctx = q.WbcContext(model, w, len(idx))
+        ctx.update(xd, ul, rbd, mode, period, time)          # warm-up call installs inputLast_ = u_last
+        cmd, st = ctx.update(xd, ud, rbd, mode, period, time)
+        assert (st == 0).all(), st
+        ctx.close()
+        return cmd
+    assert check_golden(run_backend(update, g), g, TOL) < TOL
+
+
+@pytest.mark.gpu
+def test_cuda_full_size_against_cpu_port_and_properties(descs):
+    """BASELINE config 5 at full size (B = 65 536): a 512-solve subset against the CPU port, every solve through properties."""
+    import qm_door_b200 as q
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    B = 65536
+    W = workload.WbcWorkload(B)
+    ctx = q.WbcContext(W.model, W.wbc, B)
+    ctx.update(W.x_des, W.u_last, W.rbd, W.mode, W.period, W.time)
+    cmd, st = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)
+    assert (st & ~2 == 0).all()                               # WST_DEGENERATE (tight inherited rows) is informational
+    sub = 512
+    ul = W.u_last[:sub].copy()
+    ref, _ = abi_fill.cport_wbc(W.model, W.wbc, W.x_des[:sub], W.u_des[:sub], W.rbd[:sub], W.mode[:sub], W.period[:sub], W.time[:sub], ul, threads=8)
+    errs = np.array([rel_l2(cmd[b], ref[b]) for b in range(sub)])
+    assert np.median(errs) < 1e-10 and errs.max() < TOL
+    # properties: swing feet carry no force, stance feet inside the friction pyramid, torques within limits
+    f = cmd[:, 24:36].reshape(B, 4, 3)
+    tau = cmd[:, 36:]
+    tau_max = np.ctypeslib.as_array(W.wbc.tau_max)
+    for leg in range(4):
+        stance = ((W.mode >> (3 - leg)) & 1).astype(bool)
+        assert np.abs(f[~stance, leg]).max() < 1e-6
+        fz = f[stance, leg, 2]
+        assert fz.min() > -1e-6
+        assert (np.abs(f[stance, leg, 0]) <= W.wbc.friction_mu * fz + 1e-6).all()
+    ok = st == 0
+    assert (np.abs(tau[ok]) <= tau_max + 1e-6).mean() > 0.999
+    assert np.isfinite(cmd).all()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_reset_and_device_entry(descs):
+    import torch
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    W = workload.WbcWorkload(32, seed=9)
+    ctx = q.WbcContext(W.model, W.wbc, 32)
+    a, _ = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)
+    b, _ = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)     # inputLast_ now equals u_des
+    ctx.reset()
+    c, _ = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)
+    assert np.array_equal(a, c) and not np.array_equal(a, b)
+    ctx.reset()
+    dev = torch.device("cuda", 0)
+    T = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    cmd = torch.zeros(32, 54, dtype=torch.float64, device=dev)
+    st = torch.zeros(32, dtype=torch.int32, device=dev)
+    ctx.update_dev(T(W.x_des), T(W.u_des), T(W.rbd), T(W.mode), T(W.period), T(W.time), cmd, st)
+    ctx.sync()
+    assert np.array_equal(cmd.cpu().numpy(), a)
+    ctx.close()

@@ -50,5 +50,31 @@ def main():
         print(name, "nodes", NN.max(), "alpha", AL.ravel())
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def wbc_golden():
+    """WBC golden vectors: 48 solves of config-5 style inputs (all 16 contact patterns, both task stacks, t < 10 s stack)."""
+    from oracle import wbc
+    from qm_door_b200 import workload
+    m, P = config.load_default()
+    W = workload.WbcWorkload(48, seed=20261020)
+    W.mode[:16] = np.arange(16)
+    W.time[32:40] = 5.0                      # arm-joint tracking stack (HierarchicalWbc.cpp:32-36)
+    variant = np.zeros(48, dtype=np.int32)
+    variant[40:] = 1                         # HierarchicalMpcWbc stack
+    cmd = np.zeros((48, 54))
+    iters = np.zeros((48, 3), dtype=np.int32)
+    for b in range(48):
+        O = wbc.Wbc(m, P, mpc_variant=bool(variant[b]))
+        O.input_last = W.u_last[b].copy()
+        cmd[b], dbg = O.update(W.x_des[b], W.u_des[b], W.rbd[b], int(W.mode[b]), W.period[b], W.time[b], return_debug=True)
+        iters[b] = [l.iterations for l in dbg["levels"]]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "wbc_config5.npz"), x_des=W.x_des, u_des=W.u_des, rbd=W.rbd,
+                        mode=W.mode, period=W.period, time=W.time, u_last=W.u_last, variant=variant, cmd=cmd, iters=iters)
+    print("wbc golden: active-set iterations per level (max)", iters.max(0), "solves with active constraints", int((iters.sum(1) > 0).sum()))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "wbc":
+    wbc_golden()
