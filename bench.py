@@ -148,7 +148,7 @@ def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import qm_door_b200 as q
-    from qm_door_b200 import workload
+    from qm_door_b200 import distributed as D, workload
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -181,10 +181,8 @@ def run_gpu(args, rank, world, local_rank):
             ctx.cycle_dev(d["t0"], d["x0"], d["events"], d["modes"], d["nevents"], d["tt"], d["tx"], o["t"], o["x"], o["u"],
                           o["n"], o["mode"], o["info"], o["status"])
             if world > 1:
-                policy[..., 0] = o["t"]
-                policy[..., 1:31] = o["x"]
-                policy[..., 31:61] = o["u"]
-                dist.all_gather_into_tensor(gathered, policy)
+                D.pack_policy(o["t"], o["x"], o["u"], out=policy)
+                D.allgather_policy(policy, gathered)
 
     def barrier():
         torch.cuda.synchronize()
