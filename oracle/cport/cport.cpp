@@ -100,7 +100,8 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
       else transcribe_node(g, M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
                            x, u, xn, W.data(), WI.data(), sb, pb, pf, m.status + b);
     }
-    solve_problem(g, m, b, W.data());
+    DirectFetch fetch;
+    solve_problem(g, fetch, m, b, W.data());
     // filter line search
     double* ls = m.ls + (size_t)b * LS_SIZE;
     std::vector<double> xt(30), ut(30), xnt(30);

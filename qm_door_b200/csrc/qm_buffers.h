@@ -95,9 +95,18 @@ inline void for_each_buffer(MpcBuffers& m, F f) {
 
 // ---- per-problem steps that are serial in the node axis (one group per problem)
 
+// How solve_problem gets at a per-node block: in place (host / plain loads) or staged into shared memory by the kernel
+// (k_solve: cp.async.bulk + mbarrier). request() up to three blocks, wait(), then ptr(slot) until the next request.
+struct DirectFetch {
+  const double* p[3];
+  template <class G> QM_HD void request(G, int slot, const double* gptr, int) { p[slot] = gptr; }
+  template <class G> QM_HD void wait(G) {}
+  QM_HD const double* ptr(int slot) const { return p[slot]; }
+};
+
 // Backward Riccati sweep, forward rollout, step norms, baseline performance reduction. W >= RW_SIZE doubles.
-template <class G>
-QM_HDN void solve_problem(G g, const MpcBuffers& m, int b, double* W) {
+template <class G, class F>
+QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W) {
   const int NMAX = m.NMAX;
   const int nn = m.nn[b];
   const int n = nn - 1;
@@ -110,7 +119,11 @@ QM_HDN void solve_problem(G g, const MpcBuffers& m, int b, double* W) {
   QM_PFOR(g, idx, 900) W[RW_S + idx] = term[SB_Q + idx];
   QM_PFOR(g, i, 30) W[RW_sv + i] = term[SB_q + i];
   g.sync();
-  for (int k = n - 1; k >= 0; --k) riccati_stage(g, stage + (size_t)k * SB_SIZE, W, gain + (size_t)k * GB_SIZE, m.status + b);
+  for (int k = n - 1; k >= 0; --k) {
+    fetch.request(g, 0, stage + (size_t)k * SB_SIZE, SB_SIZE);
+    fetch.wait(g);
+    riccati_stage(g, fetch.ptr(0), W, gain + (size_t)k * GB_SIZE, m.status + b);
+  }
   // forward rollout
   double* R = W;   // reuse: [0:30] dx, [30:60] dx next, [60:78] dut, [80] armijo
   QM_PFOR(g, i, 30) { R[i] = m.x0[30 * b + i] - m.xs[((size_t)b * NMAX) * 30 + i]; }
@@ -118,7 +131,11 @@ QM_HDN void solve_problem(G g, const MpcBuffers& m, int b, double* W) {
   g.sync();
   for (int k = 0; k < n; ++k) {
     QM_PFOR(g, i, 30) dxs[30 * k + i] = R[i];
-    rollout_stage(g, stage + (size_t)k * SB_SIZE, proj + (size_t)k * PB_SIZE, gain + (size_t)k * GB_SIZE, R, dus + 30 * k);
+    fetch.request(g, 0, stage + (size_t)k * SB_SIZE, SB_SIZE);
+    fetch.request(g, 1, proj + (size_t)k * PB_SIZE, PB_SIZE);
+    fetch.request(g, 2, gain + (size_t)k * GB_SIZE, GB_SIZE);
+    fetch.wait(g);
+    rollout_stage(g, fetch.ptr(0), fetch.ptr(1), fetch.ptr(2), R, dus + 30 * k);
     QM_PFOR(g, i, 30) R[i] = R[30 + i];
     g.sync();
   }

@@ -860,57 +860,92 @@ QM_HDN void perf_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc
 }
 
 // ------------------------------------------------------------------------------------------ Riccati
-enum { RW_S = 0, RW_SA = 900, RW_SB = 1800, RW_H = RW_SB + 540, RW_G = RW_H + 540, RW_K = RW_G + 324,
-       RW_sv = RW_K + 540, RW_sb = RW_sv + 30, RW_gv = RW_sb + 30, RW_kf = RW_gv + 18, RW_SIZE = RW_kf + 18 + 4 };
+// Workspace. K aliases SB (SB is dead once G, H are formed); LI holds L^-1 of the Cholesky factor.
+enum { RW_S = 0, RW_SA = 900, RW_SB = 1800, RW_K = RW_SB, RW_H = RW_SB + 540, RW_G = RW_H + 540, RW_LI = RW_G + 324,
+       RW_sv = RW_LI + 324, RW_sb = RW_sv + 30, RW_gv = RW_sb + 30, RW_kf = RW_gv + 18, RW_SIZE = RW_kf + 18 };
+
+// 3x3 register tile of C = X Y (X: m x kd row-major ldx, Y: kd x n row-major ldy), accumulated into acc[9]
+#define QM_TILE3(acc, XP, ldx, YP, ldy, i0, j0, kd)                                                        \
+  do {                                                                                                     \
+    for (int k_ = 0; k_ < (kd); ++k_) {                                                                    \
+      const double x0_ = (XP)[((i0) + 0) * (ldx) + k_], x1_ = (XP)[((i0) + 1) * (ldx) + k_], x2_ = (XP)[((i0) + 2) * (ldx) + k_]; \
+      const double y0_ = (YP)[k_ * (ldy) + (j0)], y1_ = (YP)[k_ * (ldy) + (j0) + 1], y2_ = (YP)[k_ * (ldy) + (j0) + 2];           \
+      acc[0] += x0_ * y0_; acc[1] += x0_ * y1_; acc[2] += x0_ * y2_;                                       \
+      acc[3] += x1_ * y0_; acc[4] += x1_ * y1_; acc[5] += x1_ * y2_;                                       \
+      acc[6] += x2_ * y0_; acc[7] += x2_ * y1_; acc[8] += x2_ * y2_;                                       \
+    }                                                                                                      \
+  } while (0)
+// same with X used transposed: C = X' Y (X: kd x m row-major ldx)
+#define QM_TILE3_T(acc, XP, ldx, YP, ldy, i0, j0, kd)                                                      \
+  do {                                                                                                     \
+    for (int k_ = 0; k_ < (kd); ++k_) {                                                                    \
+      const double x0_ = (XP)[k_ * (ldx) + (i0)], x1_ = (XP)[k_ * (ldx) + (i0) + 1], x2_ = (XP)[k_ * (ldx) + (i0) + 2]; \
+      const double y0_ = (YP)[k_ * (ldy) + (j0)], y1_ = (YP)[k_ * (ldy) + (j0) + 1], y2_ = (YP)[k_ * (ldy) + (j0) + 2]; \
+      acc[0] += x0_ * y0_; acc[1] += x0_ * y1_; acc[2] += x0_ * y2_;                                       \
+      acc[3] += x1_ * y0_; acc[4] += x1_ * y1_; acc[5] += x1_ * y2_;                                       \
+      acc[6] += x2_ * y0_; acc[7] += x2_ * y1_; acc[8] += x2_ * y2_;                                       \
+    }                                                                                                      \
+  } while (0)
 
 // One backward stage. st = stage block (shared or global), S/s updated in place, K/kff written to gb.
+// All dense products use 3x3 register tiles (6 loads per 9 FMAs); padded input columns (a >= nut) are zero in the block.
 template <class G>
 QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* status) {
   const int nut = (int)st[SB_NUT];
+  const int nt3 = (nut + 2) / 3;                 // column tiles of the reduced input
   const double* A = st + SB_A; const double* B = st + SB_B; const double* b = st + SB_b;
   double* S = W + RW_S; double* s = W + RW_sv;
-  QM_PFOR(g, i, 30) {
-    double acc = s[i];
-    for (int j = 0; j < 30; ++j) acc += S[30 * i + j] * b[j];
-    W[RW_sb + i] = acc;
-  }
-  QM_PFOR(g, idx, 900) {
-    const int i = idx / 30, j = idx % 30;
-    double acc = 0.0;
-    for (int k = 0; k < 30; ++k) acc += S[30 * i + k] * A[30 * k + j];
-    W[RW_SA + idx] = acc;
-  }
-  QM_PFOR(g, idx, 30 * QM_NUT) {
-    const int i = idx / QM_NUT, a = idx % QM_NUT;
-    double acc = 0.0;
-    if (a < nut) for (int k = 0; k < 30; ++k) acc += S[30 * i + k] * B[QM_NUT * k + a];
-    W[RW_SB + idx] = acc;
+  // ---- P1: SA = S A, SB = S B, sb = s + S b
+  QM_PFOR(g, item, 100 + 10 * nt3 + 10) {
+    if (item < 100) {
+      const int i0 = 3 * (item / 10), j0 = 3 * (item % 10);
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      QM_TILE3(acc, S, 30, A, 30, i0, j0, 30);
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_SA + 30 * (i0 + r) + j0 + c] = acc[3 * r + c];
+    } else if (item < 100 + 10 * nt3) {
+      const int it = item - 100;
+      const int i0 = 3 * (it / nt3), j0 = 3 * (it % nt3);
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      QM_TILE3(acc, S, 30, B, QM_NUT, i0, j0, 30);
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_SB + QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
+    } else {
+      const int i0 = 3 * (item - 100 - 10 * nt3);
+      for (int r = 0; r < 3; ++r) {
+        double acc = s[i0 + r];
+        for (int j = 0; j < 30; ++j) acc += S[30 * (i0 + r) + j] * b[j];
+        W[RW_sb + i0 + r] = acc;
+      }
+    }
   }
   g.sync();
   if (nut > 0) {
-    QM_PFOR(g, idx, QM_NUT * QM_NUT) {
-      const int a = idx / QM_NUT, c = idx % QM_NUT;
-      if (a < nut && c < nut) {
-        double acc = st[SB_R + idx];
-        for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_SB + QM_NUT * k + c];
-        W[RW_G + idx] = acc;
+    // ---- P2: G = R + B' SB, H = P + B' SA, g = r + B' sb
+    QM_PFOR(g, item, nt3 * nt3 + nt3 * 10 + nt3) {
+      if (item < nt3 * nt3) {
+        const int i0 = 3 * (item / nt3), j0 = 3 * (item % nt3);
+        double acc[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_R + QM_NUT * (i0 + r) + j0 + c];
+        QM_TILE3_T(acc, B, QM_NUT, W + RW_SB, QM_NUT, i0, j0, 30);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_G + QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
+      } else if (item < nt3 * nt3 + nt3 * 10) {
+        const int it = item - nt3 * nt3;
+        const int i0 = 3 * (it / 10), j0 = 3 * (it % 10);
+        double acc[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_P + 30 * (i0 + r) + j0 + c];
+        QM_TILE3_T(acc, B, QM_NUT, W + RW_SA, 30, i0, j0, 30);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_H + 30 * (i0 + r) + j0 + c] = acc[3 * r + c];
+      } else {
+        const int i0 = 3 * (item - nt3 * nt3 - nt3 * 10);
+        for (int r = 0; r < 3; ++r) {
+          const int a = i0 + r;
+          double acc = (a < nut) ? st[SB_r + a] : 0.0;
+          for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_sb + k];
+          W[RW_gv + a] = acc;
+        }
       }
-    }
-    QM_PFOR(g, idx, QM_NUT * 30) {
-      const int a = idx / 30, j = idx % 30;
-      if (a < nut) {
-        double acc = st[SB_P + idx];
-        for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_SA + 30 * k + j];
-        W[RW_H + idx] = acc;
-      }
-    }
-    QM_PFOR(g, a, nut) {
-      double acc = st[SB_r + a];
-      for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_sb + k];
-      W[RW_gv + a] = acc;
     }
     g.sync();
-    // Cholesky G = L L' (lower triangle in place)
+    // ---- P3: Cholesky G = L L' (lower triangle in place)
     double* Gm = W + RW_G;
     for (int c = 0; c < nut; ++c) {
       if (g.tid() == 0) {
@@ -928,50 +963,89 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
       }
       g.sync();
     }
-    // K = -G^-1 H, kff = -G^-1 g : one column per thread
-    QM_PFOR(g, j, 31) {
-      double y[QM_NUT];
-      for (int a = 0; a < nut; ++a) {
-        double v = (j < 30) ? W[RW_H + 30 * a + j] : W[RW_gv + a];
-        for (int k = 0; k < a; ++k) v -= Gm[QM_NUT * a + k] * y[k];
-        y[a] = v / Gm[QM_NUT * a + a];
+    // ---- P4: LI = L^-1 (column per thread), Ginv = LI' LI (overwrites G), K = -Ginv H, kff = -Ginv g (tiled)
+    QM_PFOR(g, c, QM_NUT) {
+      for (int i = 0; i < QM_NUT; ++i) {
+        double v = 0.0;
+        if (c < nut && i < nut && i >= c) {
+          v = (i == c) ? 1.0 : 0.0;
+          for (int k = c; k < i; ++k) v -= Gm[QM_NUT * i + k] * W[RW_LI + QM_NUT * k + c];
+          v /= Gm[QM_NUT * i + i];
+        }
+        W[RW_LI + QM_NUT * i + c] = v;
       }
-      for (int a = nut - 1; a >= 0; --a) {
-        double v = y[a];
-        for (int k = a + 1; k < nut; ++k) v -= Gm[QM_NUT * k + a] * y[k];
-        y[a] = v / Gm[QM_NUT * a + a];
+    }
+    g.sync();
+    QM_PFOR(g, item, nt3 * nt3) {
+      const int i0 = 3 * (item / nt3), j0 = 3 * (item % nt3);
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const int k0 = (i0 > j0) ? i0 : j0;              // LI is lower triangular: rows k >= max(i, j) contribute
+      for (int k = k0; k < 3 * nt3; ++k) {
+        const double x0 = W[RW_LI + QM_NUT * k + i0], x1 = W[RW_LI + QM_NUT * k + i0 + 1], x2 = W[RW_LI + QM_NUT * k + i0 + 2];
+        const double y0 = W[RW_LI + QM_NUT * k + j0], y1 = W[RW_LI + QM_NUT * k + j0 + 1], y2 = W[RW_LI + QM_NUT * k + j0 + 2];
+        acc[0] += x0 * y0; acc[1] += x0 * y1; acc[2] += x0 * y2;
+        acc[3] += x1 * y0; acc[4] += x1 * y1; acc[5] += x1 * y2;
+        acc[6] += x2 * y0; acc[7] += x2 * y1; acc[8] += x2 * y2;
       }
-      for (int a = 0; a < nut; ++a) {
-        if (j < 30) W[RW_K + 30 * a + j] = -y[a];
-        else W[RW_kf + a] = -y[a];
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Gm[QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
+    }
+    g.sync();
+    QM_PFOR(g, item, nt3 * 10 + nt3) {
+      if (item < nt3 * 10) {
+        const int i0 = 3 * (item / 10), j0 = 3 * (item % 10);
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        QM_TILE3(acc, Gm, QM_NUT, W + RW_H, 30, i0, j0, nut);
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_K + 30 * (i0 + r) + j0 + c] = -acc[3 * r + c];
+      } else {
+        const int i0 = 3 * (item - nt3 * 10);
+        for (int r = 0; r < 3; ++r) {
+          double acc = 0.0;
+          for (int k = 0; k < nut; ++k) acc += Gm[QM_NUT * (i0 + r) + k] * W[RW_gv + k];
+          W[RW_kf + i0 + r] = -acc;
+        }
       }
     }
     g.sync();
   }
-  // S <- Q + A' S A + H' K ;  s <- q + A' (s + S b) + H' kff
-  QM_PFOR(g, idx, 900) {
-    const int i = idx / 30, j = idx % 30;
-    double acc = st[SB_Q + idx];
-    for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_SA + 30 * k + j];
-    for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_K + 30 * a + j];
-    S[idx] = acc;
-  }
-  QM_PFOR(g, i, 30) {
-    double acc = st[SB_q + i];
-    for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
-    for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_kf + a];
-    s[i] = acc;
+  // ---- P5: S <- Q + A' SA + H' K (upper-triangle tiles, mirrored and symmetrised);  s <- q + A' sb + H' kff
+  QM_PFOR(g, item, 55 + 10) {
+    if (item < 55) {
+      int ti = 0, r_ = item;
+      while (r_ >= 10 - ti) { r_ -= 10 - ti; ++ti; }
+      const int tj = ti + r_;
+      const int i0 = 3 * ti, j0 = 3 * tj;
+      double acc[9];
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_Q + 30 * (i0 + r) + j0 + c];
+      QM_TILE3_T(acc, A, 30, W + RW_SA, 30, i0, j0, 30);
+      if (nut > 0) QM_TILE3_T(acc, W + RW_H, 30, W + RW_K, 30, i0, j0, nut);
+      if (ti == tj) {
+        // diagonal tile: symmetrise inside the tile
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) S[30 * (i0 + r) + j0 + c] = 0.5 * (acc[3 * r + c] + acc[3 * c + r]);
+      } else {
+        // off-diagonal tile: the mirrored tile (j0, i0) equals Q' + ... computed from the lower triangle of Q; average both
+        double low[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) low[3 * r + c] = st[SB_Q + 30 * (j0 + c) + i0 + r] - st[SB_Q + 30 * (i0 + r) + j0 + c];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            const double v = acc[3 * r + c] + 0.5 * low[3 * r + c];
+            S[30 * (i0 + r) + j0 + c] = v;
+            S[30 * (j0 + c) + i0 + r] = v;
+          }
+      }
+    } else {
+      const int i0 = 3 * (item - 55);
+      for (int r = 0; r < 3; ++r) {
+        const int i = i0 + r;
+        double acc = st[SB_q + i];
+        for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
+        for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_kf + a];
+        s[i] = acc;
+      }
+    }
   }
   QM_PFOR(g, idx, QM_NUT * 30) gb[GB_K + idx] = (idx / 30 < nut) ? W[RW_K + idx] : 0.0;
   QM_PFOR(g, a, QM_NUT) gb[GB_KFF + a] = (a < nut) ? W[RW_kf + a] : 0.0;
-  g.sync();
-  QM_PFOR(g, idx, 435) {     // symmetrise: pairs i<j
-    int i = 0, r = idx;
-    while (r >= 29 - i) { r -= 29 - i; ++i; }
-    const int j = i + 1 + r;
-    const double v = 0.5 * (S[30 * i + j] + S[30 * j + i]);
-    S[30 * i + j] = v; S[30 * j + i] = v;
-  }
   g.sync();
 }
 

@@ -89,9 +89,72 @@ __global__ void __launch_bounds__(128) k_transcribe(MpcBuffers m, const qmb200_m
   }
 }
 
+// ---- TMA staging of the per-node blocks for the serial sweeps (cp.async.bulk global -> shared, completion on an mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct TmaFetch {
+  double* buf[3];          // shared-memory destinations (16-byte aligned)
+  uint64_t* bar;           // mbarrier in shared memory
+  uint32_t phase;          // parity of the next completion
+  uint32_t pending_bytes;  // thread 0 only
+  const double* src[3];
+  uint32_t bytes[3];
+  int nreq;
+
+  __device__ void init(double* b0, double* b1, double* b2, uint64_t* mbar) {
+    buf[0] = b0; buf[1] = b1; buf[2] = b2; bar = mbar; phase = 0; nreq = 0;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void request(BlockGroup, int slot, const double* gptr, int ndoubles) {
+    if (threadIdx.x == 0) { src[nreq] = gptr; bytes[nreq] = (uint32_t)ndoubles * 8u; }
+    // slot order == request order for every caller (0, then 1, 2)
+    (void)slot;
+    ++nreq;
+  }
+  __device__ __forceinline__ void wait(BlockGroup) {
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int i = 0; i < nreq; ++i) total += bytes[i];
+      // order earlier generic-proxy reads of the buffers before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
+      for (int i = 0; i < nreq; ++i)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf[i])),
+                     "l"(src[i]), "r"(bytes[i]), "r"(smem_u32(bar))
+                     : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(phase)
+          : "memory");
+    }
+    phase ^= 1u;
+    nreq = 0;
+  }
+  __device__ __forceinline__ const double* ptr(int slot) const { return buf[slot]; }
+};
+
+// shared memory of k_solve: [stage block | Riccati workspace | mbarrier]; the forward sweep stages proj / gain blocks
+// into the (then idle) upper part of the Riccati workspace
+constexpr int kSolveFwdOff = 96;     // rollout scratch occupies W[0:81]
+static_assert(kSolveFwdOff + PB_SIZE + GB_SIZE <= RW_SIZE, "forward staging must fit in the Riccati workspace");
+constexpr size_t kSolveSmemBytes = (size_t)(SB_SIZE + RW_SIZE + 2) * sizeof(double);
+
 __global__ void __launch_bounds__(128) k_solve(MpcBuffers m) {
-  extern __shared__ double smem[];
-  solve_problem(BlockGroup(), m, blockIdx.x, smem);
+  extern __shared__ __align__(16) double smem[];
+  double* stagebuf = smem;
+  double* W = smem + SB_SIZE;
+  uint64_t* bar = (uint64_t*)(smem + SB_SIZE + RW_SIZE);
+  TmaFetch fetch;
+  fetch.init(stagebuf, W + kSolveFwdOff, W + kSolveFwdOff + PB_SIZE, bar);
+  solve_problem(BlockGroup(), fetch, m, blockIdx.x, W);
 }
 
 constexpr int kTrialWarps = 4;
@@ -221,7 +284,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->dP); }
   { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
   { KernelTimer kt(c, KN_TRANSCRIBE); k_transcribe<<<dim3(NMAX, B), 128, kTranscribeSmemBytes, st>>>(m, c->dM, c->dP); }
-  { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, 128, RW_SIZE * sizeof(double), st>>>(m); }
+  { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, 128, kSolveSmemBytes, st>>>(m); }
   CUDA_OK(cudaGetLastError());
   const int max_iters = 24;
   for (int it = 0; it < max_iters; ++it) {
@@ -279,7 +342,7 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int)));
   CUDA_OK(cudaFuncSetAttribute(k_transcribe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTranscribeSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_trial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrialSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RW_SIZE * sizeof(double))));
+  CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
   *out = c;
   return 0;
 }
