@@ -29,21 +29,41 @@
 namespace qm {
 
 // ------------------------------------------------------------------------------------------ groups
+// A group can split into a `narrow` part (dependency-chain work: kinematics tree, pivoting) and the `rest` (wide
+// independent work) that run concurrently between two full-group syncs.
 struct SerialGroup {
   QM_HD int tid() const { return 0; }
   QM_HD int nt() const { return 1; }
   QM_HD void sync() const {}
+  QM_HD bool narrow_active() const { return true; }
+  QM_HD bool rest_active() const { return true; }
+  QM_HD SerialGroup narrow() const { return *this; }
+  QM_HD SerialGroup rest() const { return *this; }
 };
 #if defined(__CUDACC__)
-struct BlockGroup {
-  __device__ __forceinline__ int tid() const { return threadIdx.x; }
-  __device__ __forceinline__ int nt() const { return blockDim.x; }
-  __device__ __forceinline__ void sync() const { __syncthreads(); }
-};
 struct WarpGroup {
   __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
   __device__ __forceinline__ int nt() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ bool narrow_active() const { return true; }
+  __device__ __forceinline__ bool rest_active() const { return true; }
+  __device__ __forceinline__ WarpGroup narrow() const { return *this; }
+  __device__ __forceinline__ WarpGroup rest() const { return *this; }
+};
+// warps 1.. of the CTA, synchronised with named barrier 1
+struct RestGroup {
+  __device__ __forceinline__ int tid() const { return threadIdx.x - 32; }
+  __device__ __forceinline__ int nt() const { return blockDim.x - 32; }
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
+};
+struct BlockGroup {
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int nt() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ bool narrow_active() const { return threadIdx.x < 32; }
+  __device__ __forceinline__ bool rest_active() const { return threadIdx.x >= 32; }
+  __device__ __forceinline__ WarpGroup narrow() const { return WarpGroup(); }
+  __device__ __forceinline__ RestGroup rest() const { return RestGroup(); }
 };
 #endif
 #define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())

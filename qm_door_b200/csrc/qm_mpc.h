@@ -425,22 +425,49 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
                             const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status_out) {
   double* kw = W + TW_KIN;
   const double m = M.total_mass;
-  if (g.tid() == 0) {
-    node_reference(M, P, t, mode, tt, ts, kt, W + TW_REF);
-    WI[TI_STATUS] = 0;
-  }
-  // ---- first dynamics evaluation at (x,u) and everything else that lives at (x,u)
-  kin_eval(g, M, x, u, true, kw);
-  flow_rows(g, M, P.gravity, kw, x, u, W + TW_F1, W + TW_FR1);
-  ee_terms(g, kw, W + TW_REF, W + TW_E6, W + TW_DQ, W + TW_JE);
-  // constraint rows [Dv | C | e] for the velocity constraints (QMInterface.cpp:116-131)
-  if (g.tid() == 0) {
-    int nv = 0;
-    for (int ft = 0; ft < 4; ++ft) nv += ((mode >> (3 - ft)) & 1) ? 3 : 1;
-    WI[TI_NV] = nv;
+  int nvc = 0;
+  for (int ft = 0; ft < 4; ++ft) nvc += ((mode >> (3 - ft)) & 1) ? 3 : 1;
+  const int nv = nvc;                 // velocity-constraint rows: 3 per stance foot, 1 per swing foot
+  // ---- A. narrow: kinematics at (x,u) with derivatives | rest: references, deviations, barrier terms
+  if (g.narrow_active()) kin_eval(g.narrow(), M, x, u, true, kw);
+  if (g.rest_active()) {
+    auto r = g.rest();
+    if (r.tid() == 0) {
+      node_reference(M, P, t, mode, tt, ts, kt, W + TW_REF);
+      WI[TI_STATUS] = 0;
+      WI[TI_NV] = nv;
+    }
+    r.sync();
+    QM_PFOR(r, i, 30) {
+      W[TW_DX + i] = x[i] - W[TW_REF + RF_X + i];
+      W[TW_DU + i] = u[i] - W[TW_REF + RF_U + i];
+    }
+    QM_PFOR(r, ft, 4) {
+      if ((mode >> (3 - ft)) & 1) cone_terms(P, u + 3 * ft, W + TW_CONE + 10 * ft);
+    }
+    QM_PFOR(r, i, 12) {
+      double v1, a1, b1, v2, a2, b2;
+      if (i < 6) {
+        relaxed_barrier(x[24 + i] - P.arm_pos_lo[i], P.pos_bar_mu, P.pos_bar_delta, &v1, &a1, &b1);
+        relaxed_barrier(P.arm_pos_hi[i] - x[24 + i], P.pos_bar_mu, P.pos_bar_delta, &v2, &a2, &b2);
+      } else {
+        relaxed_barrier(u[18 + i] - P.arm_vel_lo[i - 6], P.vel_bar_mu, P.vel_bar_delta, &v1, &a1, &b1);
+        relaxed_barrier(P.arm_vel_hi[i - 6] - u[18 + i], P.vel_bar_mu, P.vel_bar_delta, &v2, &a2, &b2);
+      }
+      W[TW_BOX + 2 * i] = a1 - a2;
+      W[TW_BOX + 2 * i + 1] = b1 + b2;
+    }
+    r.sync();
+    QM_PFOR(r, i, 60) {
+      double acc = 0.0;
+      if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * W[TW_DX + j]; W[TW_TQ + i] = acc; }
+      else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * W[TW_DU + j]; W[TW_TR + ii] = acc; }
+    }
   }
   g.sync();
-  const int nv = WI[TI_NV];
+  // ---- B. all: flow map rows, end-effector terms, constraint rows [Dv | C | e] (QMInterface.cpp:116-131), x2
+  flow_rows(g, M, P.gravity, kw, x, u, W + TW_F1, W + TW_FR1);
+  ee_terms(g, kw, W + TW_REF, W + TW_E6, W + TW_DQ, W + TW_JE);
   {
     const double* Fr1 = W + TW_FR1;
     QM_PFOR(g, idx, nv * 49) {
@@ -468,60 +495,36 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
       W[TW_T + idx] = v;
     }
   }
-  // cost helper vectors
-  QM_PFOR(g, i, 30) {
-    W[TW_DX + i] = x[i] - W[TW_REF + RF_X + i];
-    W[TW_DU + i] = u[i] - W[TW_REF + RF_U + i];
-  }
-  QM_PFOR(g, ft, 4) {
-    if ((mode >> (3 - ft)) & 1) cone_terms(P, u + 3 * ft, W + TW_CONE + 10 * ft);
-  }
-  QM_PFOR(g, i, 12) {
-    double v1, a1, b1, v2, a2, b2;
-    if (i < 6) {
-      relaxed_barrier(x[24 + i] - P.arm_pos_lo[i], P.pos_bar_mu, P.pos_bar_delta, &v1, &a1, &b1);
-      relaxed_barrier(P.arm_pos_hi[i] - x[24 + i], P.pos_bar_mu, P.pos_bar_delta, &v2, &a2, &b2);
-    } else {
-      relaxed_barrier(u[18 + i] - P.arm_vel_lo[i - 6], P.vel_bar_mu, P.vel_bar_delta, &v1, &a1, &b1);
-      relaxed_barrier(P.arm_vel_hi[i - 6] - u[18 + i], P.vel_bar_mu, P.vel_bar_delta, &v2, &a2, &b2);
-    }
-    W[TW_BOX + 2 * i] = a1 - a2;
-    W[TW_BOX + 2 * i + 1] = b1 + b2;
-  }
-  g.sync();
-  QM_PFOR(g, i, 60) {
-    double acc = 0.0;
-    if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * W[TW_DX + j]; W[TW_TQ + i] = acc; }
-    else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * W[TW_DU + j]; W[TW_TR + ii] = acc; }
-  }
-  g.sync();
-  if (g.tid() == 0) {
-    // baseline performance of this node (cost value, equality-constraint SSE)
-    double c0 = barrier_cost(P, mode, x, u);
-    for (int i = 0; i < 30; ++i) c0 += 0.5 * (W[TW_DX + i] * W[TW_TQ + i] + W[TW_DU + i] * W[TW_TR + i]);
-    const double* e = W + TW_E6;
-    c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
-    double eq = 0.0;
-    for (int r = 0; r < nv; ++r) eq += W[TW_T + 49 * r + 48] * W[TW_T + 49 * r + 48];
-    double shift = 0.0;
-    for (int ft = 0; ft < 4; ++ft) {
-      if ((mode >> (3 - ft)) & 1) shift += W[TW_CONE + 10 * ft + 8] * (-P.fric_hess_shift);
-      else eq += u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
-    }
-    W[TW_SCAL + 0] = c0; W[TW_SCAL + 1] = eq; W[TW_SCAL + 2] = shift;
-  }
   QM_PFOR(g, i, 30) W[TW_X2 + i] = x[i] + dt * W[TW_F1 + i];
   g.sync();
-  // ---- cost quadratic approximation (forward Euler, * dt)
-  {
+  // ---- C. narrow: kinematics at (x + dt f1, u) ([upstream] RK2 sensitivity integrator = Heun)
+  //         rest: baseline performance scalars, cost quadratic approximation (forward Euler, * dt)
+  if (g.narrow_active()) kin_eval(g.narrow(), M, W + TW_X2, u, true, kw);
+  if (g.rest_active()) {
+    auto r = g.rest();
+    if (r.tid() == 0) {
+      double c0 = barrier_cost(P, mode, x, u);
+      for (int i = 0; i < 30; ++i) c0 += 0.5 * (W[TW_DX + i] * W[TW_TQ + i] + W[TW_DU + i] * W[TW_TR + i]);
+      const double* e = W + TW_E6;
+      c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
+      double eq = 0.0;
+      for (int rr = 0; rr < nv; ++rr) eq += W[TW_T + 49 * rr + 48] * W[TW_T + 49 * rr + 48];
+      double shift = 0.0;
+      for (int ft = 0; ft < 4; ++ft) {
+        if ((mode >> (3 - ft)) & 1) shift += W[TW_CONE + 10 * ft + 8] * (-P.fric_hess_shift);
+        else eq += u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
+      }
+      W[TW_SCAL + 0] = c0; W[TW_SCAL + 1] = eq; W[TW_SCAL + 2] = shift;
+    }
+    r.sync();
     const double* JE = W + TW_JE;
     const double shift = W[TW_SCAL + 2];
-    QM_PFOR(g, idx, 900) {
+    QM_PFOR(r, idx, 900) {
       const int i = idx / 30, j = idx % 30;
       double qv = P.Q[idx];
       if (i >= 6 && j >= 6) {
         double acc = 0.0;
-        for (int r = 0; r < 6; ++r) acc += (r < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[r * QM_NJ + i - 6] * JE[r * QM_NJ + j - 6];
+        for (int rr = 0; rr < 6; ++rr) acc += (rr < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[rr * QM_NJ + i - 6] * JE[rr * QM_NJ + j - 6];
         qv += acc;
       }
       double rv = P.R[idx];
@@ -541,11 +544,11 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
       W[TW_Q + idx] = dt * qv;
       W[TW_R + idx] = dt * rv;
     }
-    QM_PFOR(g, i, 30) {
+    QM_PFOR(r, i, 30) {
       double qv = W[TW_TQ + i], rv = W[TW_TR + i];
       if (i >= 6) {
         const double* e = W + TW_E6;
-        for (int r = 0; r < 6; ++r) qv += (r < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[r * QM_NJ + i - 6] * e[r];
+        for (int rr = 0; rr < 6; ++rr) qv += (rr < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[rr * QM_NJ + i - 6] * e[rr];
       }
       if (i >= 24) { qv += W[TW_BOX + 2 * (i - 24)]; rv += W[TW_BOX + 2 * (i - 18)]; }
       if (i < 12 && ((mode >> (3 - i / 3)) & 1)) { const double* c = W + TW_CONE + 10 * (i / 3); rv += c[8] * c[1 + i % 3]; }
@@ -554,8 +557,7 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
     }
   }
   g.sync();
-  // ---- second dynamics evaluation at (x + dt f1, u)   ([upstream] RK2 sensitivity integrator = Heun)
-  kin_eval(g, M, W + TW_X2, u, true, kw);
+  // ---- D. all: second flow map rows, discrete dynamics A, B, b
   flow_rows(g, M, P.gravity, kw, W + TW_X2, u, W + TW_F2, W + TW_FR2);
   {
     const double* F1 = W + TW_FR1;
@@ -586,60 +588,65 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
     QM_PFOR(g, i, 30) W[TW_b + i] = x[i] + hdt * (W[TW_F1 + i] + W[TW_F2 + i]) - xn[i];
   }
   g.sync();
-  if (g.tid() == 0) {
-    double dyn = 0.0;
-    for (int i = 0; i < 30; ++i) dyn += W[TW_b + i] * W[TW_b + i];
-    perf[PF_COST] = dt * W[TW_SCAL + 0];
-    perf[PF_DYN] = dt * dyn;
-    perf[PF_EQ] = dt * W[TW_SCAL + 1];
-  }
-  // ---- projection: Gauss-Jordan with full pivoting on Dv  ([upstream] luConstraintProjection)
-  for (int step = 0; step < nv; ++step) {
-    QM_PFOR(g, r, nv) {
-      double best = -1.0; int arg = 0;
-      if (r >= step) {
-        for (int c = 0; c < 18; ++c) { const double a = fabs(W[TW_T + 49 * r + c]); if (a > best) { best = a; arg = c; } }
+  // ---- E. narrow: projection by Gauss-Jordan with full pivoting on Dv ([upstream] luConstraintProjection)
+  //         rest: performance record, clear the projection matrices (PX aliases the now dead FR1/FR2)
+  if (g.narrow_active()) {
+    auto w0 = g.narrow();
+    for (int step = 0; step < nv; ++step) {
+      QM_PFOR(w0, r, nv) {
+        double best = -1.0; int arg = 0;
+        if (r >= step) {
+          for (int c = 0; c < 18; ++c) { const double a = fabs(W[TW_T + 49 * r + c]); if (a > best) { best = a; arg = c; } }
+        }
+        W[TW_ROWBEST + r] = best; WI[TI_ROWARG + r] = arg;
       }
-      W[TW_ROWBEST + r] = best; WI[TI_ROWARG + r] = arg;
-    }
-    g.sync();
-    if (g.tid() == 0) {
-      int pr = step; double best = W[TW_ROWBEST + step];
-      for (int r = step + 1; r < nv; ++r) if (W[TW_ROWBEST + r] > best) { best = W[TW_ROWBEST + r]; pr = r; }
-      WI[TI_PR] = pr; WI[TI_PC] = WI[TI_ROWARG + pr]; WI[TI_PIVCOL + step] = WI[TI_ROWARG + pr];
-      if (!(best > 1e-12)) WI[TI_STATUS] |= ST_RANK;
-    }
-    g.sync();
-    const int pr = WI[TI_PR], pc = WI[TI_PC];
-    if (pr != step) {
-      QM_PFOR(g, c, 49) { const double a = W[TW_T + 49 * step + c]; W[TW_T + 49 * step + c] = W[TW_T + 49 * pr + c]; W[TW_T + 49 * pr + c] = a; }
-      g.sync();
-    }
-    QM_PFOR(g, r, nv) W[TW_FAC + r] = W[TW_T + 49 * r + pc];
-    g.sync();
-    {
+      w0.sync();
+      if (w0.tid() == 0) {
+        int pr = step; double best = W[TW_ROWBEST + step];
+        for (int r = step + 1; r < nv; ++r) if (W[TW_ROWBEST + r] > best) { best = W[TW_ROWBEST + r]; pr = r; }
+        WI[TI_PR] = pr; WI[TI_PC] = WI[TI_ROWARG + pr]; WI[TI_PIVCOL + step] = WI[TI_ROWARG + pr];
+        if (!(best > 1e-12)) WI[TI_STATUS] |= ST_RANK;
+      }
+      w0.sync();
+      const int pr = WI[TI_PR], pc = WI[TI_PC];
+      if (pr != step) {
+        QM_PFOR(w0, c, 49) { const double a = W[TW_T + 49 * step + c]; W[TW_T + 49 * step + c] = W[TW_T + 49 * pr + c]; W[TW_T + 49 * pr + c] = a; }
+        w0.sync();
+      }
+      QM_PFOR(w0, r, nv) W[TW_FAC + r] = W[TW_T + 49 * r + pc];
+      w0.sync();
       const double ipiv = 1.0 / W[TW_FAC + step];
-      QM_PFOR(g, idx, nv * 49) {
+      QM_PFOR(w0, idx, nv * 49) {
         const int r = idx / 49, c = idx % 49;
         if (r != step) W[TW_T + idx] -= W[TW_FAC + r] * ipiv * W[TW_T + 49 * step + c];
       }
-      g.sync();
-      QM_PFOR(g, c, 49) W[TW_T + 49 * step + c] *= ipiv;
-      g.sync();
+      w0.sync();
+      QM_PFOR(w0, c, 49) W[TW_T + 49 * step + c] *= ipiv;
+      w0.sync();
+    }
+    if (w0.tid() == 0) {
+      for (int l = 0; l < 18; ++l) WI[TI_ISPIV + l] = 0;
+      for (int p = 0; p < nv; ++p) WI[TI_ISPIV + WI[TI_PIVCOL + p]] = 1;
+      int a = 0;
+      for (int ft = 0; ft < 4; ++ft)
+        if ((mode >> (3 - ft)) & 1) { WI[TI_FCOLS + a] = 3 * ft; WI[TI_FCOLS + a + 1] = 3 * ft + 1; WI[TI_FCOLS + a + 2] = 3 * ft + 2; a += 3; }
+      for (int l = 0; l < 18; ++l) if (!WI[TI_ISPIV + l]) WI[TI_FCOLS + a++] = 12 + l;
+      WI[TI_NUT] = a;
     }
   }
-  if (g.tid() == 0) {
-    for (int l = 0; l < 18; ++l) WI[TI_ISPIV + l] = 0;
-    for (int p = 0; p < nv; ++p) WI[TI_ISPIV + WI[TI_PIVCOL + p]] = 1;
-    int a = 0;
-    for (int ft = 0; ft < 4; ++ft)
-      if ((mode >> (3 - ft)) & 1) { WI[TI_FCOLS + a] = 3 * ft; WI[TI_FCOLS + a + 1] = 3 * ft + 1; WI[TI_FCOLS + a + 2] = 3 * ft + 2; a += 3; }
-    for (int l = 0; l < 18; ++l) if (!WI[TI_ISPIV + l]) WI[TI_FCOLS + a++] = 12 + l;
-    WI[TI_NUT] = a;
+  if (g.rest_active()) {
+    auto r = g.rest();
+    if (r.tid() == 0) {
+      double dyn = 0.0;
+      for (int i = 0; i < 30; ++i) dyn += W[TW_b + i] * W[TW_b + i];
+      perf[PF_COST] = dt * W[TW_SCAL + 0];
+      perf[PF_DYN] = dt * dyn;
+      perf[PF_EQ] = dt * W[TW_SCAL + 1];
+    }
+    QM_PFOR(r, idx, 900) W[TW_PX + idx] = 0.0;
+    QM_PFOR(r, idx, 540) W[TW_PU + idx] = 0.0;
+    QM_PFOR(r, i, 30) W[TW_PE + i] = (i < 12 && !((mode >> (3 - i / 3)) & 1)) ? -u[i] : 0.0;
   }
-  QM_PFOR(g, idx, 900) W[TW_PX + idx] = 0.0;
-  QM_PFOR(g, idx, 540) W[TW_PU + idx] = 0.0;
-  QM_PFOR(g, i, 30) W[TW_PE + i] = (i < 12 && !((mode >> (3 - i / 3)) & 1)) ? -u[i] : 0.0;
   g.sync();
   const int nut = WI[TI_NUT];
   QM_PFOR(g, idx, nv * 49) {
