@@ -100,7 +100,8 @@ inline void for_each_buffer(MpcBuffers& m, F f) {
 struct DirectFetch {
   const double* p[3];
   template <class G> QM_HD void request(G, int slot, const double* gptr, int) { p[slot] = gptr; }
-  template <class G> QM_HD void wait(G) {}
+  template <class G> QM_HD void issue(G) {}     // start the requested copies (all threads past their last read of the buffers)
+  template <class G> QM_HD void wait(G) {}      // requested blocks are readable through ptr()
   QM_HD const double* ptr(int slot) const { return p[slot]; }
 };
 
@@ -119,10 +120,12 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W) 
   QM_PFOR(g, idx, 900) W[RW_S + idx] = term[SB_Q + idx];
   QM_PFOR(g, i, 30) W[RW_sv + i] = term[SB_q + i];
   g.sync();
+  if (n > 0) { fetch.request(g, 0, stage + (size_t)(n - 1) * SB_SIZE, SB_SIZE); fetch.issue(g); }
   for (int k = n - 1; k >= 0; --k) {
-    fetch.request(g, 0, stage + (size_t)k * SB_SIZE, SB_SIZE);
     fetch.wait(g);
-    riccati_stage(g, fetch.ptr(0), W, gain + (size_t)k * GB_SIZE, m.status + b);
+    const int nut = riccati_stage_a(g, fetch.ptr(0), W, m.status + b);
+    if (k > 0) { fetch.request(g, 0, stage + (size_t)(k - 1) * SB_SIZE, SB_SIZE); fetch.issue(g); }   // stage buffer is free: prefetch
+    riccati_stage_b(g, nut, W, gain + (size_t)k * GB_SIZE);
   }
   // forward rollout
   double* R = W;   // reuse: [0:30] dx, [30:60] dx next, [60:78] dut, [80] armijo
@@ -134,6 +137,7 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W) 
     fetch.request(g, 0, stage + (size_t)k * SB_SIZE, SB_SIZE);
     fetch.request(g, 1, proj + (size_t)k * PB_SIZE, PB_SIZE);
     fetch.request(g, 2, gain + (size_t)k * GB_SIZE, GB_SIZE);
+    fetch.issue(g);
     fetch.wait(g);
     rollout_stage(g, fetch.ptr(0), fetch.ptr(1), fetch.ptr(2), R, dus + 30 * k);
     QM_PFOR(g, i, 30) R[i] = R[30 + i];

@@ -894,10 +894,50 @@ enum { RW_S = 0, RW_SA = 900, RW_SB = 1800, RW_K = RW_SB, RW_H = RW_SB + 540, RW
     }                                                                                                      \
   } while (0)
 
-// One backward stage. st = stage block (shared or global), S/s updated in place, K/kff written to gb.
+#if defined(__CUDACC__)
+// In-place inverse of the symmetric positive definite n x n matrix Gm (shared memory, leading dimension QM_NUT, n <= 18)
+// by one warp: Gauss-Jordan elimination without pivoting, column j of the matrix held in the registers of lane j, the
+// multipliers of each pivot step broadcast with warp shuffles (no shared-memory round trips on the dependency chain).
+__device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, int* status) {
+  const int lane = threadIdx.x & 31;
+  const bool active = lane < n;
+  double r[QM_NUT];
+#pragma unroll
+  for (int i = 0; i < QM_NUT; ++i) r[i] = (active && i < n) ? Gm[QM_NUT * i + lane] : ((i == lane) ? 1.0 : 0.0);
+  bool bad = false;
+#pragma unroll
+  for (int c = 0; c < QM_NUT; ++c) {
+    if (c < n) {                                   // uniform across the warp
+      const double acc = __shfl_sync(0xffffffffu, r[c], c);      // pivot a_cc lives in lane c, register c
+      if (!(acc > 0.0)) bad = true;
+      const double p = 1.0 / acc;
+      const double rc = r[c];                      // a_cj of this lane's column
+#pragma unroll
+      for (int i = 0; i < QM_NUT; ++i) {
+        if (i != c) {
+          const double m = __shfl_sync(0xffffffffu, r[i], c) * p;   // multiplier a_ic / a_cc from lane c
+          r[i] = (lane == c) ? -m : r[i] - m * rc;
+        }
+      }
+      r[c] = (lane == c) ? p : rc * p;
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < QM_NUT; ++i) if (i < n) Gm[QM_NUT * i + lane] = r[i];
+  }
+  if (bad && lane == 0) status_or(status, ST_CHOL);
+}
+#endif
+
+// One backward stage, in two halves so the caller can re-use the stage buffer (prefetch the next block) in between.
 // All dense products use 3x3 register tiles (6 loads per 9 FMAs); padded input columns (a >= nut) are zero in the block.
+//   riccati_stage_a: SA = S A, SB = S B, sb;  G, H, g;  then concurrently
+//                    narrow: Cholesky G = L L', L^-1, G^-1 = L^-T L^-1      (dependency chain, one warp)
+//                    rest  : S <- Q + A' SA (symmetric tiles), s <- q + A' sb (largest product, independent of the gains)
+//   riccati_stage_b: K = -G^-1 H, kff = -G^-1 g;  S += H' K (symmetrised), s += H' kff;  gains to HBM
 template <class G>
-QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* status) {
+QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
   const int nut = (int)st[SB_NUT];
   const int nt3 = (nut + 2) / 3;                 // column tiles of the reduced input
   const double* A = st + SB_A; const double* B = st + SB_B; const double* b = st + SB_b;
@@ -925,8 +965,8 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
     }
   }
   g.sync();
+  // ---- P2: G = R + B' SB, H = P + B' SA, g = r + B' sb
   if (nut > 0) {
-    // ---- P2: G = R + B' SB, H = P + B' SA, g = r + B' sb
     QM_PFOR(g, item, nt3 * nt3 + nt3 * 10 + nt3) {
       if (item < nt3 * nt3) {
         const int i0 = 3 * (item / nt3), j0 = 3 * (item % nt3);
@@ -952,26 +992,31 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
       }
     }
     g.sync();
-    // ---- P3: Cholesky G = L L' (lower triangle in place)
+  }
+  // ---- P3 narrow: Ginv = G^-1 in place. Device: register/shuffle Gauss-Jordan on one warp; host: Cholesky route.
+#if defined(__CUDA_ARCH__)
+  if (g.narrow_active() && nut > 0) spd_inverse_warp(W + RW_G, nut, status);
+#else
+  if (g.narrow_active() && nut > 0) {
+    auto w0 = g.narrow();
     double* Gm = W + RW_G;
     for (int c = 0; c < nut; ++c) {
-      if (g.tid() == 0) {
+      if (w0.tid() == 0) {
         double d = Gm[QM_NUT * c + c];
         for (int k = 0; k < c; ++k) d -= Gm[QM_NUT * c + k] * Gm[QM_NUT * c + k];
         if (!(d > 0.0)) { status_or(status, ST_CHOL); d = 1e-300; }
         Gm[QM_NUT * c + c] = sqrt(d);
       }
-      g.sync();
-      QM_PFOR(g, ii, nut - c - 1) {
+      w0.sync();
+      QM_PFOR(w0, ii, nut - c - 1) {
         const int i = c + 1 + ii;
         double v = Gm[QM_NUT * i + c];
         for (int k = 0; k < c; ++k) v -= Gm[QM_NUT * i + k] * Gm[QM_NUT * c + k];
         Gm[QM_NUT * i + c] = v / Gm[QM_NUT * c + c];
       }
-      g.sync();
+      w0.sync();
     }
-    // ---- P4: LI = L^-1 (column per thread), Ginv = LI' LI (overwrites G), K = -Ginv H, kff = -Ginv g (tiled)
-    QM_PFOR(g, c, QM_NUT) {
+    QM_PFOR(w0, c, QM_NUT) {
       for (int i = 0; i < QM_NUT; ++i) {
         double v = 0.0;
         if (c < nut && i < nut && i >= c) {
@@ -982,8 +1027,8 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
         W[RW_LI + QM_NUT * i + c] = v;
       }
     }
-    g.sync();
-    QM_PFOR(g, item, nt3 * nt3) {
+    w0.sync();
+    QM_PFOR(w0, item, nt3 * nt3) {
       const int i0 = 3 * (item / nt3), j0 = 3 * (item % nt3);
       double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       const int k0 = (i0 > j0) ? i0 : j0;              // LI is lower triangular: rows k >= max(i, j) contribute
@@ -996,7 +1041,52 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
       }
       for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Gm[QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
     }
-    g.sync();
+  }
+#endif
+  // ---- P3 rest: S <- Q + A' SA on the upper-triangle tiles (mirrored); s <- q + A' sb.  (S, s were consumed in P1.)
+  if (g.rest_active()) {
+    auto r_ = g.rest();
+    QM_PFOR(r_, item, 55 + 10) {
+      if (item < 55) {
+        int ti = 0, rem = item;
+        while (rem >= 10 - ti) { rem -= 10 - ti; ++ti; }
+        const int tj = ti + rem;
+        const int i0 = 3 * ti, j0 = 3 * tj;
+        double acc[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_Q + 30 * (i0 + r) + j0 + c];
+        QM_TILE3_T(acc, A, 30, W + RW_SA, 30, i0, j0, 30);
+        if (ti == tj) {
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[30 * (i0 + r) + j0 + c] = acc[3 * r + c];
+        } else {
+          // mirrored tile carries the lower triangle of Q so that the later symmetrisation averages Q exactly
+          for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+              S[30 * (i0 + r) + j0 + c] = acc[3 * r + c];
+              S[30 * (j0 + c) + i0 + r] = acc[3 * r + c] + (st[SB_Q + 30 * (j0 + c) + i0 + r] - st[SB_Q + 30 * (i0 + r) + j0 + c]);
+            }
+        }
+      } else {
+        const int i0 = 3 * (item - 55);
+        for (int r = 0; r < 3; ++r) {
+          const int i = i0 + r;
+          double acc = st[SB_q + i];
+          for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
+          s[i] = acc;
+        }
+      }
+    }
+  }
+  g.sync();
+  return nut;
+}
+
+template <class G>
+QM_HDN void riccati_stage_b(G g, int nut, double* W, double* gb) {
+  const int nt3 = (nut + 2) / 3;
+  double* S = W + RW_S; double* s = W + RW_sv;
+  double* Gm = W + RW_G;
+  if (nut > 0) {
+    // ---- P4: K = -Ginv H, kff = -Ginv g
     QM_PFOR(g, item, nt3 * 10 + nt3) {
       if (item < nt3 * 10) {
         const int i0 = 3 * (item / 10), j0 = 3 * (item % 10);
@@ -1014,28 +1104,23 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
     }
     g.sync();
   }
-  // ---- P5: S <- Q + A' SA + H' K (upper-triangle tiles, mirrored and symmetrised);  s <- q + A' sb + H' kff
+  // ---- P5: S <- sym(S + H' K), s += H' kff; gains to HBM
   QM_PFOR(g, item, 55 + 10) {
     if (item < 55) {
-      int ti = 0, r_ = item;
-      while (r_ >= 10 - ti) { r_ -= 10 - ti; ++ti; }
-      const int tj = ti + r_;
+      int ti = 0, rem = item;
+      while (rem >= 10 - ti) { rem -= 10 - ti; ++ti; }
+      const int tj = ti + rem;
       const int i0 = 3 * ti, j0 = 3 * tj;
-      double acc[9];
-      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_Q + 30 * (i0 + r) + j0 + c];
-      QM_TILE3_T(acc, A, 30, W + RW_SA, 30, i0, j0, 30);
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       if (nut > 0) QM_TILE3_T(acc, W + RW_H, 30, W + RW_K, 30, i0, j0, nut);
       if (ti == tj) {
-        // diagonal tile: symmetrise inside the tile
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) S[30 * (i0 + r) + j0 + c] = 0.5 * (acc[3 * r + c] + acc[3 * c + r]);
+        double t[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) t[3 * r + c] = S[30 * (i0 + r) + j0 + c] + acc[3 * r + c];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[30 * (i0 + r) + j0 + c] = 0.5 * (t[3 * r + c] + t[3 * c + r]);
       } else {
-        // off-diagonal tile: the mirrored tile (j0, i0) equals Q' + ... computed from the lower triangle of Q; average both
-        double low[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) low[3 * r + c] = st[SB_Q + 30 * (j0 + c) + i0 + r] - st[SB_Q + 30 * (i0 + r) + j0 + c];
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) {
-            const double v = acc[3 * r + c] + 0.5 * low[3 * r + c];
+            const double v = 0.5 * (S[30 * (i0 + r) + j0 + c] + S[30 * (j0 + c) + i0 + r]) + acc[3 * r + c];
             S[30 * (i0 + r) + j0 + c] = v;
             S[30 * (j0 + c) + i0 + r] = v;
           }
@@ -1044,8 +1129,7 @@ QM_HDN void riccati_stage(G g, const double* st, double* W, double* gb, int* sta
       const int i0 = 3 * (item - 55);
       for (int r = 0; r < 3; ++r) {
         const int i = i0 + r;
-        double acc = st[SB_q + i];
-        for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
+        double acc = s[i];
         for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_kf + a];
         s[i] = acc;
       }

@@ -115,7 +115,7 @@ struct TmaFetch {
     (void)slot;
     ++nreq;
   }
-  __device__ __forceinline__ void wait(BlockGroup) {
+  __device__ __forceinline__ void issue(BlockGroup) {
     if (threadIdx.x == 0) {
       uint32_t total = 0;
       for (int i = 0; i < nreq; ++i) total += bytes[i];
@@ -127,6 +127,9 @@ struct TmaFetch {
                      "l"(src[i]), "r"(bytes[i]), "r"(smem_u32(bar))
                      : "memory");
     }
+    nreq = 0;
+  }
+  __device__ __forceinline__ void wait(BlockGroup) {
     uint32_t done = 0;
     while (!done) {
       asm volatile(
@@ -136,7 +139,6 @@ struct TmaFetch {
           : "memory");
     }
     phase ^= 1u;
-    nreq = 0;
   }
   __device__ __forceinline__ const double* ptr(int slot) const { return buf[slot]; }
 };
@@ -147,7 +149,10 @@ constexpr int kSolveFwdOff = 96;     // rollout scratch occupies W[0:81]
 static_assert(kSolveFwdOff + PB_SIZE + GB_SIZE <= RW_SIZE, "forward staging must fit in the Riccati workspace");
 constexpr size_t kSolveSmemBytes = (size_t)(SB_SIZE + RW_SIZE + 2) * sizeof(double);
 
-__global__ void __launch_bounds__(128) k_solve(MpcBuffers m) {
+#ifndef QM_SOLVE_THREADS
+#define QM_SOLVE_THREADS 192
+#endif
+__global__ void __launch_bounds__(QM_SOLVE_THREADS) k_solve(MpcBuffers m) {
   extern __shared__ __align__(16) double smem[];
   double* stagebuf = smem;
   double* W = smem + SB_SIZE;
@@ -284,7 +289,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->dP); }
   { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
   { KernelTimer kt(c, KN_TRANSCRIBE); k_transcribe<<<dim3(NMAX, B), 128, kTranscribeSmemBytes, st>>>(m, c->dM, c->dP); }
-  { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, 128, kSolveSmemBytes, st>>>(m); }
+  { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
   CUDA_OK(cudaGetLastError());
   const int max_iters = 24;
   for (int it = 0; it < max_iters; ++it) {
