@@ -82,11 +82,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------- algorithmic bytes (DESIGN.md §4)
-def transcribe_bytes_per_node(nut):
-    """Doubles k_transcribe must move per intermediate node: reads x,u,x_next (90); writes the projected LQ block
-    (A 900, B 30*nut, b 30, Q 900, P 30*nut, R nut^2, q 30, r nut, 1) and the projection (Pu 30*nut, Px 900, Pe 30)."""
-    return 8 * (90 + 900 + 30 * nut + 30 + 900 + 30 * nut + nut * nut + 30 + nut + 1 + 30 * nut + 900 + 30 + 3)
+# ----------------------------------------------------------------------------- algorithmic bytes (DESIGN.md §3)
+def kernel_bytes_per_node(kernel, nut):
+    """Doubles a kernel must move per intermediate node with reduced input dimension nut (nv = 26 - nut velocity rows).
+    stage = projected LQ block actually used (A 900, B 30 nut, b 30, Q 900, P 30 nut, R nut^2, q 30, r nut, 1);
+    proj = (Pu 30 nut, Px 900, Pe 30); gain = (K 30 nut, kff nut); kin1/kin2 = products of the two kinematics evaluations."""
+    nv = 26 - nut
+    stage = 900 + 30 * nut + 30 + 900 + 30 * nut + nut * nut + 30 + nut + 1
+    proj = 30 * nut + 900 + 30
+    gain = 30 * nut + nut
+    kin1 = 540 + 30 + 30 + 49 * nv + 144 + 8
+    kin2 = 540 + 30
+    d = {"k_kin1": 60 + kin1, "k_kin2": 60 + kin2, "k_lq": 90 + kin1 + kin2 + stage + proj + 3,
+         "k_solve": 2 * stage + proj + 2 * gain + 60, "k_trial": 150 + 3}[kernel]
+    return 8 * d
 
 
 def cycle_bytes_per_node(nut):
@@ -259,14 +268,14 @@ def run_gpu(args, rank, world, local_rank):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        by_name = max(kt.items(), key=lambda kv: kv[1][0])
-        dom = "k_transcribe"
+        modeled = ("k_kin1", "k_kin2", "k_lq", "k_solve", "k_trial")
+        dom = max(modeled, key=lambda kn: kt[kn][0])                 # dominant kernel by total time in the timed region
         ms_dom = kt[dom][0] / max(1, kt[dom][1])
         nodes_bytes = 0
         for b in range(B):
             for kk in range(nn[b] - 1):
                 md = int(modes_last[b, kk])
-                nodes_bytes += transcribe_bytes_per_node(14 + bin(md & 15).count("1"))
+                nodes_bytes += kernel_bytes_per_node(dom, 14 + bin(md & 15).count("1"))
         achieved = nodes_bytes / (ms_dom * 1e-3) / 1e9
         cyc_bytes = sum(cycle_bytes_per_node(16) for _ in range(1)) * float(nn.sum() - B)
         line = {
@@ -279,7 +288,7 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": int(nodes_bytes),
-                         "slowest_kernel_by_total_time": by_name[0],
+                         "share_of_step": kt[dom][0] / max(1e-9, sum(v[0] for v in kt.values())),
                          "cycle_level": {"algorithmic_bytes_per_step": int(cyc_bytes),
                                          "achieved_gbs": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
                                          "frac": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak,

@@ -49,6 +49,7 @@ struct MpcBuffers {
   double* stage;       // [B][NMAX][SB_SIZE]
   double* proj;        // [B][NMAX][PB_SIZE]
   double* gain;        // [B][NMAX][GB_SIZE]
+  double* kin;         // [B][NMAX][KS_SIZE] kinematics products handed from k_kin1/k_kin2 to k_lq
   double* perf_base;   // [B][NMAX][PF_SIZE]
   double* perf_trial;  // [B][NMAX][PF_SIZE]
   double* ls;          // [B][LS_SIZE]
@@ -84,6 +85,7 @@ inline void for_each_buffer(MpcBuffers& m, F f) {
   f((void**)&m.stage, B * N * SB_SIZE * sizeof(double));
   f((void**)&m.proj, B * N * PB_SIZE * sizeof(double));
   f((void**)&m.gain, B * N * GB_SIZE * sizeof(double));
+  f((void**)&m.kin, B * N * KS_SIZE * sizeof(double));
   f((void**)&m.perf_base, B * N * PF_SIZE * sizeof(double));
   f((void**)&m.perf_trial, B * N * PF_SIZE * sizeof(double));
   f((void**)&m.ls, B * LS_SIZE * sizeof(double));

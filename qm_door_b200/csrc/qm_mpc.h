@@ -388,8 +388,8 @@ enum {
   TW_PU = TW_R + 900,               // [30][18]
   TW_T = TW_PU + 540,               // [12][49] = [Dv | C | e]
   TW_JE = TW_T + 588,               // [6][24]
-  TW_REF = TW_JE + 144,             // RF_SIZE
-  TW_F1 = TW_REF + RF_SIZE,         // 30
+  TW_REF = TW_JE + 144,             // RF_SIZE (+ 10 scratch for the ee rotation map)
+  TW_F1 = TW_REF + RF_SIZE + 10,    // 30
   TW_F2 = TW_F1 + 30,
   TW_X2 = TW_F2 + 30,
   TW_b = TW_X2 + 30,
@@ -404,7 +404,8 @@ enum {
   TW_DQ = TW_E6 + 8,                // 9 (+1)
   TW_CONE = TW_DQ + 10,             // [4][10]
   TW_BOX = TW_CONE + 40,            // [12][2]: gradient, hessian of the arm boxes (6 position, 6 velocity)
-  TW_ROWBEST = TW_BOX + 24,         // 12
+  TW_BOXV = TW_BOX + 24,            // [12] their values
+  TW_ROWBEST = TW_BOXV + 12,        // 12
   TW_FAC = TW_ROWBEST + 12,         // 12
   TW_SCAL = TW_FAC + 12,            // misc scalars: [0] cost value, [1] eq sse, [2] shift term
   TW_SIZE = TW_SCAL + 8
@@ -418,58 +419,40 @@ enum {                               // integer workspace
   TI_SIZE = 68
 };
 
-// One intermediate node: linear-quadratic transcription + projection, results to HBM blocks sb / pb, perf[PF_*].
+// Intermediate products of one node handed from the kinematics evaluations to the LQ assembly. In the fused (host)
+// path they live in the transcription workspace; in the split CUDA path k_kin writes them to HBM (KS_* layout) and
+// k_lq stages them into shared memory with one bulk copy.
+struct NodeIO {
+  double* fr1; double* fr2;   // [9][60] non-trivial rows of [df/dx | df/du] at (x,u) and (x + dt f1, u)
+  double* f1;  double* f2;    // [30] flow map values
+  double* x2;                 // [30] x + dt f1
+  double* T;                  // [12][49] velocity-constraint rows [Dv | C | e]
+  double* je;                 // [6][24] end-effector error Jacobian
+  double* e6;                 // [8] end-effector error (6), [6] = sum of squared velocity-constraint values
+};
+enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = 1758, KS_E6 = 1902, KS_SIZE = 1912 };
+QM_HD NodeIO node_io_at(double* base) {
+  NodeIO io;
+  io.fr1 = base + KS_FR1; io.fr2 = base + KS_FR2; io.f1 = base + KS_F1; io.f2 = base + KS_F2;
+  io.x2 = base + KS_X2; io.T = base + KS_T; io.je = base + KS_JE; io.e6 = base + KS_E6;
+  return io;
+}
+
+// Kinematics at (x,u) with derivatives: flow map rows, end-effector terms, constraint rows (QMInterface.cpp:116-131), x2.
+// kw: kinematics workspace; scr: RF_SIZE + 10 doubles of scratch.
 template <class G>
-QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
-                            const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
-                            const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status_out) {
-  double* kw = W + TW_KIN;
-  const double m = M.total_mass;
+QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
+                       const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
+                       double* kw, double* scr, NodeIO io) {
   int nvc = 0;
   for (int ft = 0; ft < 4; ++ft) nvc += ((mode >> (3 - ft)) & 1) ? 3 : 1;
   const int nv = nvc;                 // velocity-constraint rows: 3 per stance foot, 1 per swing foot
-  // ---- A. narrow: kinematics at (x,u) with derivatives | rest: references, deviations, barrier terms
-  if (g.narrow_active()) kin_eval(g.narrow(), M, x, u, true, kw);
-  if (g.rest_active()) {
-    auto r = g.rest();
-    if (r.tid() == 0) {
-      node_reference(M, P, t, mode, tt, ts, kt, W + TW_REF);
-      WI[TI_STATUS] = 0;
-      WI[TI_NV] = nv;
-    }
-    r.sync();
-    QM_PFOR(r, i, 30) {
-      W[TW_DX + i] = x[i] - W[TW_REF + RF_X + i];
-      W[TW_DU + i] = u[i] - W[TW_REF + RF_U + i];
-    }
-    QM_PFOR(r, ft, 4) {
-      if ((mode >> (3 - ft)) & 1) cone_terms(P, u + 3 * ft, W + TW_CONE + 10 * ft);
-    }
-    QM_PFOR(r, i, 12) {
-      double v1, a1, b1, v2, a2, b2;
-      if (i < 6) {
-        relaxed_barrier(x[24 + i] - P.arm_pos_lo[i], P.pos_bar_mu, P.pos_bar_delta, &v1, &a1, &b1);
-        relaxed_barrier(P.arm_pos_hi[i] - x[24 + i], P.pos_bar_mu, P.pos_bar_delta, &v2, &a2, &b2);
-      } else {
-        relaxed_barrier(u[18 + i] - P.arm_vel_lo[i - 6], P.vel_bar_mu, P.vel_bar_delta, &v1, &a1, &b1);
-        relaxed_barrier(P.arm_vel_hi[i - 6] - u[18 + i], P.vel_bar_mu, P.vel_bar_delta, &v2, &a2, &b2);
-      }
-      W[TW_BOX + 2 * i] = a1 - a2;
-      W[TW_BOX + 2 * i + 1] = b1 + b2;
-    }
-    r.sync();
-    QM_PFOR(r, i, 60) {
-      double acc = 0.0;
-      if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * W[TW_DX + j]; W[TW_TQ + i] = acc; }
-      else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * W[TW_DU + j]; W[TW_TR + ii] = acc; }
-    }
-  }
-  g.sync();
-  // ---- B. all: flow map rows, end-effector terms, constraint rows [Dv | C | e] (QMInterface.cpp:116-131), x2
-  flow_rows(g, M, P.gravity, kw, x, u, W + TW_F1, W + TW_FR1);
-  ee_terms(g, kw, W + TW_REF, W + TW_E6, W + TW_DQ, W + TW_JE);
+  if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, scr);
+  kin_eval(g, M, x, u, true, kw);
+  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1);
+  ee_terms(g, kw, scr, io.e6, scr + RF_SIZE, io.je);
   {
-    const double* Fr1 = W + TW_FR1;
+    const double* Fr1 = io.fr1;
     QM_PFOR(g, idx, nv * 49) {
       const int row = idx / 49, c = idx % 49;
       // map row -> (foot, component)
@@ -492,32 +475,133 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
         v = kw[KW_FVEL + 3 * ft + d];
         if (!((mode >> (3 - ft)) & 1)) v -= zvel[ft];       // normal velocity: v_z - zdot_ref (QMPreComputation.cpp:56-71)
       }
-      W[TW_T + idx] = v;
+      io.T[idx] = v;
     }
   }
-  QM_PFOR(g, i, 30) W[TW_X2 + i] = x[i] + dt * W[TW_F1 + i];
+  QM_PFOR(g, i, 30) io.x2[i] = x[i] + dt * io.f1[i];
   g.sync();
-  // ---- C. narrow: kinematics at (x + dt f1, u) ([upstream] RK2 sensitivity integrator = Heun)
-  //         rest: baseline performance scalars, cost quadratic approximation (forward Euler, * dt)
-  if (g.narrow_active()) kin_eval(g.narrow(), M, W + TW_X2, u, true, kw);
+  if (g.tid() == 0) {
+    double eq = 0.0;
+    for (int rr = 0; rr < nv; ++rr) eq += io.T[49 * rr + 48] * io.T[49 * rr + 48];
+    io.e6[6] = eq;
+  }
+  g.sync();
+}
+
+// Kinematics at (x + dt f1, u) with derivatives ([upstream] RK2 sensitivity integrator = Heun): second flow map rows.
+template <class G>
+QM_HDN void node_eval2(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, const double* u, double* kw, NodeIO io) {
+  kin_eval(g, M, io.x2, u, true, kw);
+  flow_rows(g, M, P.gravity, kw, io.x2, u, io.f2, io.fr2);
+}
+
+// LQ assembly of one intermediate node from the kinematics products: cost quadratic approximation, discrete dynamics,
+// constraint projection, change of input variables; results to the HBM blocks sb / pb and perf[PF_*].
+template <class G>
+QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
+                    const double* tt, const double* ts, int kt, const double* x, const double* u, const double* xn,
+                    double* W, int* WI, NodeIO io, double* sb, double* pb, double* perf, int* status_out) {
+  const double m = M.total_mass;
+  int nvc = 0;
+  for (int ft = 0; ft < 4; ++ft) nvc += ((mode >> (3 - ft)) & 1) ? 3 : 1;
+  const int nv = nvc;
+  double* T = io.T;
+  // ---- L1 narrow: projection by Gauss-Jordan with full pivoting on Dv ([upstream] luConstraintProjection)
+  if (g.narrow_active()) {
+    auto w0 = g.narrow();
+    if (w0.tid() == 0) WI[TI_STATUS] = 0;
+    for (int step = 0; step < nv; ++step) {
+      QM_PFOR(w0, r, nv) {
+        double best = -1.0; int arg = 0;
+        if (r >= step) {
+          for (int c = 0; c < 18; ++c) { const double a = fabs(T[49 * r + c]); if (a > best) { best = a; arg = c; } }
+        }
+        W[TW_ROWBEST + r] = best; WI[TI_ROWARG + r] = arg;
+      }
+      w0.sync();
+      if (w0.tid() == 0) {
+        int pr = step; double best = W[TW_ROWBEST + step];
+        for (int r = step + 1; r < nv; ++r) if (W[TW_ROWBEST + r] > best) { best = W[TW_ROWBEST + r]; pr = r; }
+        WI[TI_PR] = pr; WI[TI_PC] = WI[TI_ROWARG + pr]; WI[TI_PIVCOL + step] = WI[TI_ROWARG + pr];
+        if (!(best > 1e-12)) WI[TI_STATUS] |= ST_RANK;
+      }
+      w0.sync();
+      const int pr = WI[TI_PR], pc = WI[TI_PC];
+      if (pr != step) {
+        QM_PFOR(w0, c, 49) { const double a = T[49 * step + c]; T[49 * step + c] = T[49 * pr + c]; T[49 * pr + c] = a; }
+        w0.sync();
+      }
+      QM_PFOR(w0, r, nv) W[TW_FAC + r] = T[49 * r + pc];
+      w0.sync();
+      const double ipiv = 1.0 / W[TW_FAC + step];
+      QM_PFOR(w0, idx, nv * 49) {
+        const int r = idx / 49, c = idx % 49;
+        if (r != step) T[idx] -= W[TW_FAC + r] * ipiv * T[49 * step + c];
+      }
+      w0.sync();
+      QM_PFOR(w0, c, 49) T[49 * step + c] *= ipiv;
+      w0.sync();
+    }
+    if (w0.tid() == 0) {
+      for (int l = 0; l < 18; ++l) WI[TI_ISPIV + l] = 0;
+      for (int p = 0; p < nv; ++p) WI[TI_ISPIV + WI[TI_PIVCOL + p]] = 1;
+      int a = 0;
+      for (int ft = 0; ft < 4; ++ft)
+        if ((mode >> (3 - ft)) & 1) { WI[TI_FCOLS + a] = 3 * ft; WI[TI_FCOLS + a + 1] = 3 * ft + 1; WI[TI_FCOLS + a + 2] = 3 * ft + 2; a += 3; }
+      for (int l = 0; l < 18; ++l) if (!WI[TI_ISPIV + l]) WI[TI_FCOLS + a++] = 12 + l;
+      WI[TI_NUT] = a;
+      WI[TI_NV] = nv;
+    }
+  }
+  // ---- L1 rest: references, barrier terms, cost quadratic approximation (forward Euler, * dt), discrete dynamics
   if (g.rest_active()) {
     auto r = g.rest();
+    if (r.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, W + TW_REF);
+    r.sync();
+    QM_PFOR(r, i, 30) {
+      W[TW_DX + i] = x[i] - W[TW_REF + RF_X + i];
+      W[TW_DU + i] = u[i] - W[TW_REF + RF_U + i];
+    }
+    QM_PFOR(r, ft, 4) {
+      if ((mode >> (3 - ft)) & 1) cone_terms(P, u + 3 * ft, W + TW_CONE + 10 * ft);
+    }
+    QM_PFOR(r, i, 12) {
+      double v1, a1, b1, v2, a2, b2;
+      if (i < 6) {
+        relaxed_barrier(x[24 + i] - P.arm_pos_lo[i], P.pos_bar_mu, P.pos_bar_delta, &v1, &a1, &b1);
+        relaxed_barrier(P.arm_pos_hi[i] - x[24 + i], P.pos_bar_mu, P.pos_bar_delta, &v2, &a2, &b2);
+      } else {
+        relaxed_barrier(u[18 + i] - P.arm_vel_lo[i - 6], P.vel_bar_mu, P.vel_bar_delta, &v1, &a1, &b1);
+        relaxed_barrier(P.arm_vel_hi[i - 6] - u[18 + i], P.vel_bar_mu, P.vel_bar_delta, &v2, &a2, &b2);
+      }
+      W[TW_BOX + 2 * i] = a1 - a2;
+      W[TW_BOX + 2 * i + 1] = b1 + b2;
+      W[TW_BOXV + i] = v1 + v2;
+    }
+    r.sync();
+    QM_PFOR(r, i, 60) {
+      double acc = 0.0;
+      if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * W[TW_DX + j]; W[TW_TQ + i] = acc; }
+      else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * W[TW_DU + j]; W[TW_TR + ii] = acc; }
+    }
+    r.sync();
     if (r.tid() == 0) {
-      double c0 = barrier_cost(P, mode, x, u);
+      // baseline performance of this node: cost value, equality-constraint SSE
+      double c0 = -P.box_offset;
+      for (int i = 0; i < 12; ++i) c0 += W[TW_BOXV + i];
       for (int i = 0; i < 30; ++i) c0 += 0.5 * (W[TW_DX + i] * W[TW_TQ + i] + W[TW_DU + i] * W[TW_TR + i]);
-      const double* e = W + TW_E6;
+      const double* e = io.e6;
       c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
-      double eq = 0.0;
-      for (int rr = 0; rr < nv; ++rr) eq += W[TW_T + 49 * rr + 48] * W[TW_T + 49 * rr + 48];
+      double eq = io.e6[6];
       double shift = 0.0;
       for (int ft = 0; ft < 4; ++ft) {
-        if ((mode >> (3 - ft)) & 1) shift += W[TW_CONE + 10 * ft + 8] * (-P.fric_hess_shift);
+        if ((mode >> (3 - ft)) & 1) { shift += W[TW_CONE + 10 * ft + 8] * (-P.fric_hess_shift); c0 += W[TW_CONE + 10 * ft + 7]; }
         else eq += u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
       }
       W[TW_SCAL + 0] = c0; W[TW_SCAL + 1] = eq; W[TW_SCAL + 2] = shift;
     }
     r.sync();
-    const double* JE = W + TW_JE;
+    const double* JE = io.je;
     const double shift = W[TW_SCAL + 2];
     QM_PFOR(r, idx, 900) {
       const int i = idx / 30, j = idx % 30;
@@ -547,7 +631,7 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
     QM_PFOR(r, i, 30) {
       double qv = W[TW_TQ + i], rv = W[TW_TR + i];
       if (i >= 6) {
-        const double* e = W + TW_E6;
+        const double* e = io.e6;
         for (int rr = 0; rr < 6; ++rr) qv += (rr < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[rr * QM_NJ + i - 6] * e[rr];
       }
       if (i >= 24) { qv += W[TW_BOX + 2 * (i - 24)]; rv += W[TW_BOX + 2 * (i - 18)]; }
@@ -555,87 +639,35 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
       W[TW_QV + i] = dt * qv;
       W[TW_RV + i] = dt * rv;
     }
-  }
-  g.sync();
-  // ---- D. all: second flow map rows, discrete dynamics A, B, b
-  flow_rows(g, M, P.gravity, kw, W + TW_X2, u, W + TW_F2, W + TW_FR2);
-  {
-    const double* F1 = W + TW_FR1;
-    const double* F2 = W + TW_FR2;
-    const double hdt = 0.5 * dt;
-    QM_PFOR(g, idx, 900) {
-      const int i = idx / 30, j = idx % 30;
-      double av = (i == j) ? 1.0 : 0.0, bv = 0.0;
-      if (i >= 3 && i < 12) {
-        const int r = i - 3;
-        double pa = 0.0, pb2 = 0.0;
-        for (int s = 0; s < 9; ++s) {
-          pa += F2[r * 60 + 3 + s] * F1[s * 60 + j];
-          pb2 += F2[r * 60 + 3 + s] * F1[s * 60 + 30 + j];
+    {
+      const double* F1 = io.fr1;
+      const double* F2 = io.fr2;
+      const double hdt = 0.5 * dt;
+      QM_PFOR(r, idx, 900) {
+        const int i = idx / 30, j = idx % 30;
+        double av = (i == j) ? 1.0 : 0.0, bv = 0.0;
+        if (i >= 3 && i < 12) {
+          const int rr = i - 3;
+          double pa = 0.0, pb2 = 0.0;
+          for (int s2 = 0; s2 < 9; ++s2) {
+            pa += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + j];
+            pb2 += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + 30 + j];
+          }
+          if (j < 12) pb2 += F2[rr * 60 + (j % 3)] / m;
+          else pb2 += F2[rr * 60 + j];
+          av += hdt * (F1[rr * 60 + j] + F2[rr * 60 + j] + dt * pa);
+          bv = hdt * (F1[rr * 60 + 30 + j] + F2[rr * 60 + 30 + j] + dt * pb2);
+        } else if (i < 3) {
+          bv = (j < 12 && (j % 3) == i) ? dt / m : 0.0;
+        } else {
+          bv = (j == i) ? dt : 0.0;
         }
-        if (j < 12) pb2 += F2[r * 60 + (j % 3)] / m;
-        else pb2 += F2[r * 60 + j];
-        av += hdt * (F1[r * 60 + j] + F2[r * 60 + j] + dt * pa);
-        bv = hdt * (F1[r * 60 + 30 + j] + F2[r * 60 + 30 + j] + dt * pb2);
-      } else if (i < 3) {
-        bv = (j < 12 && (j % 3) == i) ? dt / m : 0.0;
-      } else {
-        bv = (j == i) ? dt : 0.0;
+        W[TW_A + idx] = av;
+        W[TW_B + idx] = bv;
       }
-      W[TW_A + idx] = av;
-      W[TW_B + idx] = bv;
+      QM_PFOR(r, i, 30) W[TW_b + i] = x[i] + hdt * (io.f1[i] + io.f2[i]) - xn[i];
     }
-    QM_PFOR(g, i, 30) W[TW_b + i] = x[i] + hdt * (W[TW_F1 + i] + W[TW_F2 + i]) - xn[i];
-  }
-  g.sync();
-  // ---- E. narrow: projection by Gauss-Jordan with full pivoting on Dv ([upstream] luConstraintProjection)
-  //         rest: performance record, clear the projection matrices (PX aliases the now dead FR1/FR2)
-  if (g.narrow_active()) {
-    auto w0 = g.narrow();
-    for (int step = 0; step < nv; ++step) {
-      QM_PFOR(w0, r, nv) {
-        double best = -1.0; int arg = 0;
-        if (r >= step) {
-          for (int c = 0; c < 18; ++c) { const double a = fabs(W[TW_T + 49 * r + c]); if (a > best) { best = a; arg = c; } }
-        }
-        W[TW_ROWBEST + r] = best; WI[TI_ROWARG + r] = arg;
-      }
-      w0.sync();
-      if (w0.tid() == 0) {
-        int pr = step; double best = W[TW_ROWBEST + step];
-        for (int r = step + 1; r < nv; ++r) if (W[TW_ROWBEST + r] > best) { best = W[TW_ROWBEST + r]; pr = r; }
-        WI[TI_PR] = pr; WI[TI_PC] = WI[TI_ROWARG + pr]; WI[TI_PIVCOL + step] = WI[TI_ROWARG + pr];
-        if (!(best > 1e-12)) WI[TI_STATUS] |= ST_RANK;
-      }
-      w0.sync();
-      const int pr = WI[TI_PR], pc = WI[TI_PC];
-      if (pr != step) {
-        QM_PFOR(w0, c, 49) { const double a = W[TW_T + 49 * step + c]; W[TW_T + 49 * step + c] = W[TW_T + 49 * pr + c]; W[TW_T + 49 * pr + c] = a; }
-        w0.sync();
-      }
-      QM_PFOR(w0, r, nv) W[TW_FAC + r] = W[TW_T + 49 * r + pc];
-      w0.sync();
-      const double ipiv = 1.0 / W[TW_FAC + step];
-      QM_PFOR(w0, idx, nv * 49) {
-        const int r = idx / 49, c = idx % 49;
-        if (r != step) W[TW_T + idx] -= W[TW_FAC + r] * ipiv * W[TW_T + 49 * step + c];
-      }
-      w0.sync();
-      QM_PFOR(w0, c, 49) W[TW_T + 49 * step + c] *= ipiv;
-      w0.sync();
-    }
-    if (w0.tid() == 0) {
-      for (int l = 0; l < 18; ++l) WI[TI_ISPIV + l] = 0;
-      for (int p = 0; p < nv; ++p) WI[TI_ISPIV + WI[TI_PIVCOL + p]] = 1;
-      int a = 0;
-      for (int ft = 0; ft < 4; ++ft)
-        if ((mode >> (3 - ft)) & 1) { WI[TI_FCOLS + a] = 3 * ft; WI[TI_FCOLS + a + 1] = 3 * ft + 1; WI[TI_FCOLS + a + 2] = 3 * ft + 2; a += 3; }
-      for (int l = 0; l < 18; ++l) if (!WI[TI_ISPIV + l]) WI[TI_FCOLS + a++] = 12 + l;
-      WI[TI_NUT] = a;
-    }
-  }
-  if (g.rest_active()) {
-    auto r = g.rest();
+    r.sync();
     if (r.tid() == 0) {
       double dyn = 0.0;
       for (int i = 0; i < 30; ++i) dyn += W[TW_b + i] * W[TW_b + i];
@@ -643,6 +675,7 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
       perf[PF_DYN] = dt * dyn;
       perf[PF_EQ] = dt * W[TW_SCAL + 1];
     }
+    // clear the projection matrices (in the fused layout PX aliases FR1/FR2, which are dead from here on)
     QM_PFOR(r, idx, 900) W[TW_PX + idx] = 0.0;
     QM_PFOR(r, idx, 540) W[TW_PU + idx] = 0.0;
     QM_PFOR(r, i, 30) W[TW_PE + i] = (i < 12 && !((mode >> (3 - i / 3)) & 1)) ? -u[i] : 0.0;
@@ -652,14 +685,14 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
   QM_PFOR(g, idx, nv * 49) {
     const int p = idx / 49, c = idx % 49;
     const int ip = 12 + WI[TI_PIVCOL + p];
-    if (c >= 18 && c < 48) W[TW_PX + 30 * ip + c - 18] = -W[TW_T + idx];
-    else if (c == 48) W[TW_PE + ip] = -W[TW_T + idx];
+    if (c >= 18 && c < 48) W[TW_PX + 30 * ip + c - 18] = -T[idx];
+    else if (c == 48) W[TW_PE + ip] = -T[idx];
   }
   QM_PFOR(g, idx, nv * QM_NUT) {
     const int p = idx / QM_NUT, a = idx % QM_NUT;
     if (a < nut) {
       const int fc = WI[TI_FCOLS + a];
-      if (fc >= 12) W[TW_PU + QM_NUT * (12 + WI[TI_PIVCOL + p]) + a] = -W[TW_T + 49 * p + fc - 12];
+      if (fc >= 12) W[TW_PU + QM_NUT * (12 + WI[TI_PIVCOL + p]) + a] = -T[49 * p + fc - 12];
     }
   }
   g.sync();
@@ -757,6 +790,19 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
     if (WI[TI_STATUS]) status_or(status_out, WI[TI_STATUS]);
   }
   g.sync();
+}
+
+// Fused form (host port / tests): both kinematics evaluations and the LQ assembly on one workspace.
+template <class G>
+QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
+                            const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
+                            const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status_out) {
+  NodeIO io;
+  io.fr1 = W + TW_FR1; io.fr2 = W + TW_FR2; io.f1 = W + TW_F1; io.f2 = W + TW_F2; io.x2 = W + TW_X2;
+  io.T = W + TW_T; io.je = W + TW_JE; io.e6 = W + TW_E6;
+  node_eval1(g, M, P, t, dt, mode, zvel, tt, ts, kt, x, u, W + TW_KIN, W + TW_REF, io);
+  node_eval2(g, M, P, u, W + TW_KIN, io);
+  node_lq(g, M, P, t, dt, mode, tt, ts, kt, x, u, xn, W, WI, io, sb, pb, perf, status_out);
 }
 
 // Pre-event node: identity jump map, no input, no cost ([upstream] setupEventNode).

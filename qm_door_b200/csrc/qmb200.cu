@@ -3,7 +3,9 @@
 // Launch map of one cycle (B problems, NMAX node capacity):
 //   k_schedule   <<<ceil(B/128), 128>>>      thread per problem: time grid, modes, swing references
 //   k_init_guess <<<B, 64>>>                 thread per state/input component: warm start interpolation
-//   k_transcribe <<<(NMAX, B), 128>>>        CTA per node: kinematics x2, LQ approximation, projection -> stage/proj blocks
+//   k_kin<1>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x,u), constraint rows, ee terms -> kin scratch
+//   k_kin<2>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
+//   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
 //   k_trial      <<<(NMAX/4, B), 128>>>      warp per node: value-only evaluation of the trial step
 //   k_decide     <<<ceil(B/128), 128>>>      thread per problem: filter line-search acceptance
@@ -27,9 +29,9 @@ static int fail(const std::string& msg) { qmb200_set_error_(msg.c_str()); return
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
-enum { KN_SCHEDULE = 0, KN_INIT, KN_TRANSCRIBE, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY };
-static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_transcribe", "k_solve",
-                                                       "k_trial",    "k_decide",     "k_finalize",   "k_policy"};
+enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY };
+static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_kin1",     "k_kin2",    "k_lq",
+                                                       "k_solve",    "k_trial",      "k_decide",   "k_finalize", "k_policy"};
 
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
@@ -51,26 +53,64 @@ __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_mo
                        m.xs + o * 30, m.us + o * 30);
 }
 
-constexpr int kTranscribeSmemDoubles = TW_SIZE + 96;
-constexpr size_t kTranscribeSmemBytes = kTranscribeSmemDoubles * sizeof(double) + TI_SIZE * sizeof(int);
+// ---- transcription = two kinematics kernels (warp per node: the kinematic tree is a dependency chain, so many
+//      independent chains per SM) + one LQ assembly kernel (CTA per node: wide small-matrix work)
+constexpr int kKinWarps = 2;
+constexpr int kKinWarpDoubles = KW_SIZE + RF_SIZE + 12 + 60;
+constexpr size_t kKinSmemBytes = (size_t)kKinWarps * kKinWarpDoubles * sizeof(double);
 
-__global__ void __launch_bounds__(128) k_transcribe(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+template <int EVAL>
+__global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kKinWarps + warp, b = blockIdx.y;
+  const int n = m.nn[b] - 1;
+  if (k >= n) return;                                   // terminal node and padding: nothing to evaluate
+  const size_t o = (size_t)b * m.NMAX + k;
+  if (m.node_flag[o] == EV_PRE) return;                 // event node: identity jump map
+  extern __shared__ double smem[];
+  double* kw = smem + (size_t)warp * kKinWarpDoubles;
+  double* scr = kw + KW_SIZE;
+  double* xin = scr + RF_SIZE + 12;                     // x[30], u[30]
+  NodeIO io = node_io_at(m.kin + o * KS_SIZE);
+  WarpGroup g;
+  for (int i = lane; i < 60; i += 32) xin[i] = (i < 30) ? ((EVAL == 1) ? m.xs[o * 30 + i] : io.x2[i]) : m.us[o * 30 + i - 30];
+  __syncwarp();
+  if (EVAL == 1) {
+    node_eval1(g, *M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, m.target_t + (size_t)b * m.KT,
+               m.target_x + (size_t)b * m.KT * QM_NTARGET, m.KT, xin, xin + 30, kw, scr, io);
+  } else {
+    io.x2 = xin;
+    node_eval2(g, *M, *P, xin + 30, kw, io);
+  }
+}
+
+constexpr int kLqSmemDoubles = TW_SIZE + 96;
+constexpr size_t kLqSmemBytes = kLqSmemDoubles * sizeof(double) + TI_SIZE * sizeof(int);
+
+__global__ void __launch_bounds__(128) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
   const int k = blockIdx.x, b = blockIdx.y;
   const int nn = m.nn[b];
   if (k >= nn) return;
   extern __shared__ double smem[];
   double* W = smem;
   double* xin = smem + TW_SIZE;                 // x[30], u[30], xn[30]
-  int* WI = (int*)(smem + kTranscribeSmemDoubles);
+  int* WI = (int*)(smem + kLqSmemDoubles);
   const size_t o = (size_t)b * m.NMAX + k;
   const int n = nn - 1;
   BlockGroup g;
+  const bool regular = (k < n) && (m.node_flag[o] != EV_PRE);
   for (int i = threadIdx.x; i < 90; i += blockDim.x) {
     double v;
     if (i < 30) v = m.xs[o * 30 + i];
     else if (i < 60) v = m.us[o * 30 + i - 30];
     else v = (k < n) ? m.xs[(o + 1) * 30 + i - 60] : 0.0;
     xin[i] = v;
+  }
+  if (regular) {
+    // stage the kinematics products of this node into the (otherwise unused) kinematics region of the workspace
+    const double2* src = reinterpret_cast<const double2*>(m.kin + o * KS_SIZE);
+    double2* dst = reinterpret_cast<double2*>(W + TW_KIN);
+    for (int i = threadIdx.x; i < KS_SIZE / 2; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
   double* sb = m.stage + o * SB_SIZE;
@@ -81,11 +121,11 @@ __global__ void __launch_bounds__(128) k_transcribe(MpcBuffers m, const qmb200_m
   if (k == n) {
     terminal_node(g, *M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, xin, W + TW_KIN, W + TW_REF, W + TW_E6, W + TW_DQ,
                   W + TW_JE, sb, pf);
-  } else if (m.node_flag[o] == EV_PRE) {
+  } else if (!regular) {
     event_node(g, xin, xin + 60, sb, pb, pf);
   } else {
-    transcribe_node(g, *M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, xin, xin + 30,
-                    xin + 60, W, WI, sb, pb, pf, m.status + b);
+    node_lq(g, *M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], tt, ts, m.KT, xin, xin + 30, xin + 60, W, WI,
+            node_io_at(W + TW_KIN), sb, pb, pf, m.status + b);
   }
 }
 
@@ -288,7 +328,9 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   cudaStream_t st = c->stream;
   { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->dP); }
   { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
-  { KernelTimer kt(c, KN_TRANSCRIBE); k_transcribe<<<dim3(NMAX, B), 128, kTranscribeSmemBytes, st>>>(m, c->dM, c->dP); }
+  { KernelTimer kt(c, KN_KIN1); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+  { KernelTimer kt(c, KN_KIN2); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+  { KernelTimer kt(c, KN_LQ); k_lq<<<dim3(NMAX, B), 128, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
   { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
   CUDA_OK(cudaGetLastError());
   const int max_iters = 24;
@@ -345,7 +387,9 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   c->bytes = total;
   CUDA_OK(cudaMalloc(&c->d_pending, sizeof(int)));
   CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int)));
-  CUDA_OK(cudaFuncSetAttribute(k_transcribe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTranscribeSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_trial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrialSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
   *out = c;
