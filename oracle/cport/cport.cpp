@@ -83,9 +83,10 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
     std::vector<double> W((int)TW_SIZE > (int)RW_SIZE ? (int)TW_SIZE : (int)RW_SIZE);
     std::vector<int> WI(TI_SIZE);
     const size_t o = (size_t)b * NMAX;
-    build_schedule(S, P, m.t0[b], m.events + (size_t)b * E, m.modes + (size_t)b * (E + 1), m.nevents[b], m.node_t + o,
-                   m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.nn + b, m.status + b);
+    build_grid(S, m.t0[b], m.events + (size_t)b * E, m.nevents[b], m.node_t + o, m.node_flag + o, m.nn + b, m.status + b);
     const int nn = m.nn[b], n = nn - 1;
+    annotate_schedule(g, S, P, m.events + (size_t)b * E, m.modes + (size_t)b * (E + 1), m.nevents[b], nn, m.node_t + o,
+                      m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.status + b);
     for (int cc = 0; cc < 60; ++cc)
       init_guess_component(M, P, S.weak_eps, cc, m.x0 + 30 * b, nn, m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o,
                            m.node_mode + o, m.nprev[b], m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30, m.xs + o * 30, m.us + o * 30);

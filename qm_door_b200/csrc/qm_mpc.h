@@ -98,10 +98,9 @@ QM_HD double swing_z_velocity(const qmb200_problem_desc& P, const double* events
   return cubic_velocity(t, tm, hm, 0.0, tf, 0.0, scaling * P.swing_touchdown_vel);
 }
 
-// [upstream] timeDiscretizationWithEvents + per-node annotations; one thread per problem.
-QM_HDN void build_schedule(const qmb200_solver_desc& S, const qmb200_problem_desc& P, double t0, const double* events,
-                           const int32_t* modes, int nev, double* node_t, int32_t* node_flag, double* node_ts,
-                           double* node_dt, int32_t* node_mode, double* node_zvel, int32_t* nn_out, int32_t* status) {
+// [upstream] timeDiscretizationWithEvents; one thread per problem (serial by construction).
+QM_HDN void build_grid(const qmb200_solver_desc& S, double t0, const double* events, int nev, double* node_t,
+                       int32_t* node_flag, int32_t* nn_out, int32_t* status) {
   const int NMAX = S.max_nodes;
   const double tf = t0 + S.horizon;
   int n = 0, st = 0;
@@ -122,7 +121,17 @@ QM_HDN void build_schedule(const qmb200_solver_desc& S, const qmb200_problem_des
     }
   }
   if (nev < 1 || events[nev - 1] < tf) st |= ST_BAD_SCHEDULE;   // schedule must extend past the horizon
-  for (int i = 0; i < n; ++i) {
+  *nn_out = n;
+  *status = st;
+}
+
+// Per-node annotations of the grid (interval start / duration, mode id, swing references): independent over nodes.
+template <class G>
+QM_HDN void annotate_schedule(G g, const qmb200_solver_desc& S, const qmb200_problem_desc& P, const double* events,
+                              const int32_t* modes, int nev, int n, const double* node_t, const int32_t* node_flag,
+                              double* node_ts, double* node_dt, int32_t* node_mode, double* node_zvel, int32_t* status) {
+  QM_PFOR(g, i, n) {
+    int st = 0;
     const double ts = node_t[i] + (node_flag[i] == EV_POST ? S.weak_eps : 0.0);
     node_ts[i] = ts;
     double dt = 0.0;
@@ -131,9 +140,9 @@ QM_HDN void build_schedule(const qmb200_solver_desc& S, const qmb200_problem_des
     const int md = modes[mode_index(events, nev, ts)];
     node_mode[i] = md;
     for (int leg = 0; leg < 4; ++leg) node_zvel[4 * i + leg] = swing_z_velocity(P, events, modes, nev, leg, ts, &st);
+    if (st) status_or(status, st);
   }
-  *nn_out = n;
-  *status = st;
+  g.sync();
 }
 
 // [upstream] multiple_shooting::initializeStateInputTrajectories; one thread per (problem, component c<60).
@@ -145,12 +154,16 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
   const double till_x = has_prev ? prev_t[nprev - 1] : node_t[0];
   const double till_u = has_prev ? prev_t[nprev - 2] : node_t[0];
   const int n = nn - 1;
+  // query times increase with the node index, so the interpolation segment is searched monotonically:
+  // `part` = number of previous-solution times strictly below the query (LinearInterpolation::timeSegment, lower_bound)
+  int part = 0;
   if (c < 30) {
     double xc;
     const double t_init = node_ts[0];
     if (t_init < till_x) {
-      int i; double a;
-      time_segment(t_init, prev_t, nprev, &i, &a);
+      while (part < nprev && prev_t[part] < t_init) ++part;
+      const int i = (part == 0) ? 0 : part - 1;        // t_init < till_x = prev_t[last] => i < last
+      const double a = (part == 0 && !(t_init == prev_t[0])) ? 1.0 : (prev_t[i + 1] - t_init) / (prev_t[i + 1] - prev_t[i]);
       xc = a * prev_x[30 * i + c] + (1.0 - a) * prev_x[30 * (i + 1) + c];
     } else xc = x0[c];
     xs[c] = xc;
@@ -158,8 +171,11 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
       if (node_flag[k] != EV_PRE) {
         const double t = node_ts[k], tn = node_t[k + 1] - (node_flag[k + 1] == EV_PRE ? weak_eps : 0.0);
         if (!(t > till_u || tn > till_x)) {
+          while (part < nprev && prev_t[part] < tn) ++part;
           int i; double a;
-          time_segment(tn, prev_t, nprev, &i, &a);
+          if (part == 0) { i = 0; a = (tn == prev_t[0]) ? (prev_t[1] - tn) / (prev_t[1] - prev_t[0]) : 1.0; }
+          else if (part - 1 < nprev - 1) { i = part - 1; a = (prev_t[i + 1] - tn) / (prev_t[i + 1] - prev_t[i]); }
+          else { i = nprev - 2; a = 0.0; }
           xc = a * prev_x[30 * i + c] + (1.0 - a) * prev_x[30 * (i + 1) + c];
         }
       }
@@ -177,8 +193,11 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
           const int ns = ((md >> 3) & 1) + ((md >> 2) & 1) + ((md >> 1) & 1) + (md & 1);
           if (cu < 12 && (cu % 3) == 2 && ((md >> (3 - cu / 3)) & 1)) uc = M.total_mass * P.gravity / ns;
         } else {
+          while (part < nprev && prev_t[part] < t) ++part;
           int i; double a;
-          time_segment(t, prev_t, nprev, &i, &a);
+          if (part == 0) { i = 0; a = (t == prev_t[0]) ? (prev_t[1] - t) / (prev_t[1] - prev_t[0]) : 1.0; }
+          else if (part - 1 < nprev - 1) { i = part - 1; a = (prev_t[i + 1] - t) / (prev_t[i + 1] - prev_t[i]); }
+          else { i = nprev - 2; a = 0.0; }
           uc = a * prev_u[30 * i + cu] + (1.0 - a) * prev_u[30 * (i + 1) + cu];
         }
       }

@@ -1,7 +1,7 @@
 // sm_100a kernels + context + C-ABI of the MPC cycle (see include/qmb200.h for the reference interfaces replaced).
 //
 // Launch map of one cycle (B problems, NMAX node capacity):
-//   k_schedule   <<<ceil(B/128), 128>>>      thread per problem: time grid, modes, swing references
+//   k_schedule   <<<ceil(B/4), 128>>>        warp per problem: time grid (lane 0), then modes / swing references per node
 //   k_init_guess <<<B, 64>>>                 thread per state/input component: warm start interpolation
 //   k_kin<1>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x,u), constraint rows, ee terms -> kin scratch
 //   k_kin<2>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
@@ -35,12 +35,16 @@ static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_gue
 
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // warp per problem: lane 0 builds the (inherently serial) time grid, then the lanes annotate the nodes in parallel
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= m.B) return;
   const size_t o = (size_t)b * m.NMAX;
-  build_schedule(*S, *P, m.t0[b], m.events + (size_t)b * m.EMAX, m.modes + (size_t)b * (m.EMAX + 1), m.nevents[b],
-                 m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.nn + b,
-                 m.status + b);
+  const double* ev = m.events + (size_t)b * m.EMAX;
+  const int32_t* md = m.modes + (size_t)b * (m.EMAX + 1);
+  if ((threadIdx.x & 31) == 0) build_grid(*S, m.t0[b], ev, m.nevents[b], m.node_t + o, m.node_flag + o, m.nn + b, m.status + b);
+  __syncwarp();
+  annotate_schedule(WarpGroup(), *S, *P, ev, md, m.nevents[b], m.nn[b], m.node_t + o, m.node_flag + o, m.node_ts + o,
+                    m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.status + b);
 }
 
 __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
@@ -326,7 +330,7 @@ static void harvest_events(qmb200_ctx* c) {
 static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, double* u_out) {
   const int B = m.B, NMAX = m.NMAX;
   cudaStream_t st = c->stream;
-  { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->dP); }
+  { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
   { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
   { KernelTimer kt(c, KN_KIN1); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
   { KernelTimer kt(c, KN_KIN2); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }

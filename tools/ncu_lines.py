@@ -25,7 +25,10 @@ for ln in dis:
         off2line[int(m.group(1), 16)] = cur
 raw = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], text=True, stderr=subprocess.DEVNULL)
 rows = list(csv.reader(raw.splitlines()))
-hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+sel = int(os.environ.get("NCU_SECTION", "0"))          # which matching launch (several kernels may match the regex)
+hi = his[sel]
+rows = rows[:his[sel + 1] - 1] if sel + 1 < len(his) else rows
 H = rows[hi]
 ia, isamp, iinst = H.index("Address"), H.index("# Samples"), H.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(H) if h.startswith("stall_") and "Not Issued" not in h]
