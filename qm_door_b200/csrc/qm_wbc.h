@@ -72,7 +72,7 @@ enum {
   WS_END = WS_CN + 40,
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
-enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_SIZE = 240 };
+enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_SIZE = 244 };
 // WI_SC scalars: [0] nW changed flag, [1] rank, [2] n1, [3] n2, [4] iq, [5] ip, [6] status, [7] r1, [8] r2, [9] nD0, [10] done
 
 QM_HD void rot_zyx(const double* e, double* R) {
@@ -604,6 +604,169 @@ QM_HDN void wbc_level0(G g, double* W, int* WI) {
   g.sync();
 }
 
+// Goldfarb-Idnani iteration on a group (see wbc_gi). State: z (WS_Z), J (WS_J), RF (WS_RF), multipliers u (WS_U),
+// active list (WI_ACT), iq (WI_SC+4). Scratch scalars in WS_CN: [0] t, [1] cip, [20..38] cs, [40..58]... see below.
+enum { GI_T = 0, GI_CIP = 1, GI_CS = 2, GI_SN = 20 };          // offsets into WS_CN (40 doubles): t, c_ip, cs[18], sn[18]
+enum { GI_ACTION = 11, GI_L = 12, GI_NROT = 13 };              // offsets into WI_SC: 0 add, 1 drop, 2 skip/ignore, 3 done
+template <class G>
+QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
+  double* J = W + WS_J;
+  double* RF = W + WS_RF;
+  int* act = WI + WI_ACT;
+  double* u = W + WS_U;
+  double* z = W + WS_Z;
+  double* d = W + WS_D;
+  double* rr = W + WS_RR;
+  double* zd = W + WS_ZD;
+  double* np = W + WS_NP;
+  double* sc = W + WS_CN;
+  int total = 0;
+  for (int outer = 0; outer < 200; ++outer) {
+    // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible)
+    QM_PFOR(w0, i, nD0) {
+      double s = W[WS_Gg + i];
+      for (int c = 0; c < n; ++c) s -= W[WS_GG + 18 * i + c] * z[c];
+      W[WS_RES + i] = s;
+    }
+    w0.sync();
+    if (w0.tid() == 0) {
+      const int iq = WI[WI_SC + 4];
+      int ip = -1;
+      double worst = 0.0;
+      for (int i = 0; i < nD0; ++i) {
+        if (WI[WI_IGN + i]) continue;
+        bool is_act = false;
+        for (int k = 0; k < iq; ++k) if (act[k] == i) { is_act = true; break; }
+        if (is_act) continue;
+        const double viol = W[WS_RES + i] / (1.0 + fabs(W[WS_Gg + i]));
+        if (viol < -1e-9 && viol < worst) { worst = viol; ip = i; }
+      }
+      WI[WI_SC + 5] = ip;
+      if (ip >= 0) { u[iq] = 0.0; sc[GI_CIP] = W[WS_RES + ip]; }
+    }
+    w0.sync();
+    const int ip = WI[WI_SC + 5];
+    if (ip < 0) break;
+    QM_PFOR(w0, c, n) np[c] = -W[WS_GG + 18 * ip + c];
+    w0.sync();
+    for (int inner = 0; inner < 200; ++inner) {
+      const int iq = WI[WI_SC + 4];
+      // d = J' np
+      QM_PFOR(w0, c, n) { double s = 0.0; for (int i = 0; i < n; ++i) s += J[i * 18 + c] * np[i]; d[c] = s; }
+      w0.sync();
+      // zd = J[:, iq:] d[iq:]  (lanes), rr = RF^-1 d[:iq] (lane 0)
+      QM_PFOR(w0, i, n) { double s = 0.0; for (int c = iq; c < n; ++c) s += J[i * 18 + c] * d[c]; zd[i] = s; }
+      if (w0.tid() == 0) {
+        for (int i = iq - 1; i >= 0; --i) {
+          double s = d[i];
+          for (int j = i + 1; j < iq; ++j) s -= RF[i * 18 + j] * rr[j];
+          rr[i] = s / RF[i * 18 + i];
+        }
+        double t1 = 1e300; int l = -1;
+        for (int k = 0; k < iq; ++k)
+          if (rr[k] > 1e-14 * (1.0 + fabs(u[k])) && u[k] / rr[k] < t1) { t1 = u[k] / rr[k]; l = k; }
+        double dn2 = 0.0, dall = 0.0;
+        for (int c = 0; c < n; ++c) { dall += d[c] * d[c]; if (c >= iq) dn2 += d[c] * d[c]; }
+        const double cip = sc[GI_CIP];
+        double t2 = 1e300;
+        if (dn2 > 1e-26 * dall) t2 = -cip / dn2;          // z' np = |d2|^2 in the J-scaled metric
+        const double t = (t1 < t2) ? t1 : t2;
+        int action;
+        if (t >= 1e300) {
+          // dependent normal and nothing to drop: infeasible up to rounding -> ignore a marginally violated row
+          if (!(fabs(cip) < 1e-6 * (1.0 + fabs(W[WS_Gg + ip])))) WI[WI_SC + 6] |= WST_DEGENERATE;
+          WI[WI_IGN + ip] = 1;
+          action = 2;
+        } else {
+          sc[GI_T] = t;
+          WI[WI_SC + 14] = (t2 < 1e300);                   // primal step exists
+          action = (t == t2) ? 0 : 1;
+          WI[GI_L + WI_SC] = l;
+          if (action == 0) {
+            // Givens rotations that zero d[iq+1..n-1] (bottom up); coefficients for the row-parallel update of J
+            for (int j = n - 1; j > iq; --j) {
+              const double a = d[j - 1], b2 = d[j];
+              double cs = 1.0, sn = 0.0;
+              if (b2 != 0.0) { const double h = hypot(a, b2); cs = a / h; sn = b2 / h; d[j - 1] = h; d[j] = 0.0; }
+              sc[GI_CS + j] = cs; sc[GI_SN + j] = sn;
+            }
+          }
+        }
+        WI[WI_SC + GI_ACTION] = action;
+      }
+      w0.sync();
+      const int action = WI[WI_SC + GI_ACTION];
+      if (action == 2) break;
+      const double t = sc[GI_T];
+      if (WI[WI_SC + 14]) QM_PFOR(w0, i, n) z[i] += t * zd[i];
+      QM_PFOR(w0, k, iq) u[k] -= t * rr[k];
+      if (w0.tid() == 0) u[iq] += t;
+      w0.sync();
+      if (action == 0) {
+        // add constraint ip
+        QM_PFOR(w0, i, n) {
+          for (int j = n - 1; j > iq; --j) {
+            const double cs = sc[GI_CS + j], sn = sc[GI_SN + j];
+            const double x1 = J[i * 18 + j - 1], x2 = J[i * 18 + j];
+            J[i * 18 + j - 1] = cs * x1 + sn * x2;
+            J[i * 18 + j] = -sn * x1 + cs * x2;
+          }
+        }
+        QM_PFOR(w0, i, iq + 1) RF[i * 18 + iq] = d[i];
+        if (w0.tid() == 0) { act[iq] = ip; WI[WI_SC + 4] = iq + 1; }
+        w0.sync();
+        break;
+      }
+      // drop constraint l and continue with the same ip
+      const int l = WI[WI_SC + GI_L];
+      if (w0.tid() == 0) {
+        for (int k = l; k < iq - 1; ++k) {
+          act[k] = act[k + 1]; u[k] = u[k + 1];
+          for (int i = 0; i <= k + 1; ++i) RF[i * 18 + k] = RF[i * 18 + k + 1];
+        }
+        u[iq - 1] = u[iq];
+        const int q2 = iq - 1;
+        for (int k = l; k < q2; ++k) {   // restore the triangle: rotate rows k, k+1 of RF
+          const double a = RF[k * 18 + k], b2 = RF[(k + 1) * 18 + k];
+          double cs = 1.0, sn = 0.0;
+          if (b2 != 0.0) {
+            const double h = hypot(a, b2);
+            cs = a / h; sn = b2 / h;
+            for (int c = k; c < q2; ++c) {
+              const double x1 = RF[k * 18 + c], x2 = RF[(k + 1) * 18 + c];
+              RF[k * 18 + c] = cs * x1 + sn * x2;
+              RF[(k + 1) * 18 + c] = -sn * x1 + cs * x2;
+            }
+          }
+          sc[GI_CS + k] = cs; sc[GI_SN + k] = sn;
+        }
+        WI[WI_SC + 4] = q2;
+      }
+      w0.sync();
+      {
+        const int q2 = WI[WI_SC + 4];
+        QM_PFOR(w0, i, n) {             // same rotations on the columns k, k+1 of J, row-parallel
+          for (int k = l; k < q2; ++k) {
+            const double cs = sc[GI_CS + k], sn = sc[GI_SN + k];
+            const double x1 = J[i * 18 + k], x2 = J[i * 18 + k + 1];
+            J[i * 18 + k] = cs * x1 + sn * x2;
+            J[i * 18 + k + 1] = -sn * x1 + cs * x2;
+          }
+        }
+        if (w0.tid() == 0) {
+          double cip = W[WS_Gg + ip];
+          for (int c = 0; c < n; ++c) cip -= W[WS_GG + 18 * ip + c] * z[c];
+          sc[GI_CIP] = cip;
+        }
+      }
+      w0.sync();
+      if (++total > 400) { if (w0.tid() == 0) WI[WI_SC + 6] |= WST_QP_MAX_ITER; break; }
+    }
+    if (total > 400) break;
+  }
+  w0.sync();
+}
+
 // ------------------------------------------------------------------------------------------ levels 1, 2
 // min 1/2|Ab z - bb|^2 + eps/2|z|^2  s.t.  Gg z <= gg   (n <= 18 unknowns, r rows, nD0 inequality rows)
 // Goldfarb-Idnani dual active set; J = R^-1 from the Householder factor of [Ab; sqrt(eps) I]. z returned in WS_Z.
@@ -612,7 +775,6 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
   const int ld = n + 1;
   double* QR = W + WS_QR;
   double* J = W + WS_J;
-  double* RF = W + WS_RF;
   const int m = r + n;
   QM_PFOR(g, idx, m * ld) {
     const int i = idx / ld, c = idx % ld;
@@ -636,122 +798,10 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
   if (g.tid() == 0) { WI[WI_SC + 4] = 0; WI[WI_SC + 10] = 0; }
   QM_PFOR(g, i, 56) WI[WI_IGN + i] = 0;
   g.sync();
-  for (int outer = 0; outer < 200; ++outer) {
-    // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible)
-    QM_PFOR(g, i, nD0) {
-      double s = W[WS_Gg + i];
-      for (int c = 0; c < n; ++c) s -= W[WS_GG + 18 * i + c] * W[WS_Z + c];
-      W[WS_RES + i] = s;
-    }
-    g.sync();
-    if (g.tid() == 0) {
-      // ---- one full GI major iteration (serial; n <= 18)
-      int iq = WI[WI_SC + 4];
-      int* act = WI + WI_ACT;
-      double* u = W + WS_U;
-      double* z = W + WS_Z;
-      double* d = W + WS_D;
-      double* rr = W + WS_RR;
-      double* zd = W + WS_ZD;
-      double* np = W + WS_NP;
-      int ip = -1;
-      double worst = 0.0;
-      for (int i = 0; i < nD0; ++i) {
-        if (WI[WI_IGN + i]) continue;
-        bool is_act = false;
-        for (int k = 0; k < iq; ++k) if (act[k] == i) { is_act = true; break; }
-        if (is_act) continue;
-        const double sc = 1.0 + fabs(W[WS_Gg + i]);
-        const double viol = W[WS_RES + i] / sc;
-        if (viol < -1e-9 && viol < worst) { worst = viol; ip = i; }
-      }
-      if (ip < 0) { WI[WI_SC + 10] = 1; }
-      else {
-        for (int c = 0; c < n; ++c) np[c] = -W[WS_GG + 18 * ip + c];
-        u[iq] = 0.0;
-        double cip = W[WS_RES + ip];
-        for (int inner = 0; inner < 200; ++inner) {
-          // d = J' np ; zd = J[:, iq:] d[iq:] ; rr = RF^-1 d[:iq]
-          for (int c = 0; c < n; ++c) { double s = 0.0; for (int i = 0; i < n; ++i) s += J[i * 18 + c] * np[i]; d[c] = s; }
-          for (int i = 0; i < n; ++i) { double s = 0.0; for (int c = iq; c < n; ++c) s += J[i * 18 + c] * d[c]; zd[i] = s; }
-          for (int i = iq - 1; i >= 0; --i) {
-            double s = d[i];
-            for (int j = i + 1; j < iq; ++j) s -= RF[i * 18 + j] * rr[j];
-            rr[i] = s / RF[i * 18 + i];
-          }
-          double t1 = 1e300; int l = -1;
-          for (int k = 0; k < iq; ++k)
-            if (rr[k] > 1e-14 * (1.0 + fabs(u[k])) && u[k] / rr[k] < t1) { t1 = u[k] / rr[k]; l = k; }
-          double zn = 0.0, nn2 = 0.0;
-          for (int i = 0; i < n; ++i) { zn += zd[i] * np[i]; nn2 += np[i] * np[i]; }
-          double t2 = 1e300;
-          // in the J-scaled metric |J' np|^2 = np' H^-1 np; a direction exists iff the null-space part of d is non-zero
-          double dn2 = 0.0, dall = 0.0;
-          for (int c = 0; c < n; ++c) { dall += d[c] * d[c]; if (c >= iq) dn2 += d[c] * d[c]; }
-          if (dn2 > 1e-26 * dall && zn > 0.0) t2 = -cip / zn;
-          const double t = (t1 < t2) ? t1 : t2;
-          if (t >= 1e300) {
-            // dependent normal and no constraint to drop: infeasible up to rounding -> ignore a marginally violated row
-            if (fabs(cip) < 1e-6 * (1.0 + fabs(W[WS_Gg + ip]))) WI[WI_IGN + ip] = 1;
-            else { WI[WI_SC + 6] |= WST_DEGENERATE; WI[WI_IGN + ip] = 1; }
-            break;
-          }
-          if (t2 < 1e300) for (int i = 0; i < n; ++i) z[i] += t * zd[i];
-          for (int k = 0; k < iq; ++k) u[k] -= t * rr[k];
-          u[iq] += t;
-          if (t == t2) {
-            // add constraint ip: Givens rotations zero d[iq+1..n-1], applied to the columns of J
-            for (int j = n - 1; j > iq; --j) {
-              const double a = d[j - 1], b = d[j];
-              if (b == 0.0) continue;
-              const double h = hypot(a, b);
-              const double cs = a / h, sn = b / h;
-              d[j - 1] = h; d[j] = 0.0;
-              for (int i = 0; i < n; ++i) {
-                const double x1 = J[i * 18 + j - 1], x2 = J[i * 18 + j];
-                J[i * 18 + j - 1] = cs * x1 + sn * x2;
-                J[i * 18 + j] = -sn * x1 + cs * x2;
-              }
-            }
-            for (int i = 0; i <= iq; ++i) RF[i * 18 + iq] = d[i];
-            act[iq] = ip;
-            ++iq;
-            break;
-          }
-          // drop constraint l and continue with the same ip
-          for (int k = l; k < iq - 1; ++k) {
-            act[k] = act[k + 1]; u[k] = u[k + 1];
-            for (int i = 0; i <= k + 1; ++i) RF[i * 18 + k] = RF[i * 18 + k + 1];
-          }
-          u[iq - 1] = u[iq];
-          --iq;
-          for (int k = l; k < iq; ++k) {   // restore the triangle: rotate rows k, k+1 of RF (columns of J)
-            const double a = RF[k * 18 + k], b = RF[(k + 1) * 18 + k];
-            if (b == 0.0) continue;
-            const double h = hypot(a, b);
-            const double cs = a / h, sn = b / h;
-            for (int c = k; c < iq; ++c) {
-              const double x1 = RF[k * 18 + c], x2 = RF[(k + 1) * 18 + c];
-              RF[k * 18 + c] = cs * x1 + sn * x2;
-              RF[(k + 1) * 18 + c] = -sn * x1 + cs * x2;
-            }
-            for (int i = 0; i < n; ++i) {
-              const double x1 = J[i * 18 + k], x2 = J[i * 18 + k + 1];
-              J[i * 18 + k] = cs * x1 + sn * x2;
-              J[i * 18 + k + 1] = -sn * x1 + cs * x2;
-            }
-          }
-          cip = W[WS_Gg + ip];
-          for (int c = 0; c < n; ++c) cip -= W[WS_GG + 18 * ip + c] * z[c];
-          if (inner == 199) WI[WI_SC + 6] |= WST_QP_MAX_ITER;
-        }
-        WI[WI_SC + 4] = iq;
-      }
-      if (outer == 199) WI[WI_SC + 6] |= WST_QP_MAX_ITER;
-    }
-    g.sync();
-    if (WI[WI_SC + 10]) break;
-  }
+  // The active-set iteration is a dependency chain: it runs on the narrow group (one warp) with lane-parallel vector
+  // operations (J' n, J2 d2, row-wise Givens updates of J) and lane-0 scalar decisions; the rest of the CTA waits.
+  if (g.narrow_active()) gi_iterate(g.narrow(), n, nD0, W, WI);
+  g.sync();
 }
 
 // HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
