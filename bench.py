@@ -254,6 +254,38 @@ def run_gpu(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t_start
     e2e_bad = int(((hout["status"] & ~32) != 0).sum())
 
+    # ---- secondary metric (BASELINE config 5): whole-body-control solves/s, B = 65 536 contact configurations, rank 0 only
+    wbc_line = None
+    if rank == 0 and not args.no_wbc:
+        WW = workload.WbcWorkload(65536)
+        wctx = q.WbcContext(WW.model, WW.wbc, WW.B, device=local_rank)
+        wstream = torch.cuda.ExternalStream(wctx.stream, device=local_rank)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        wd = dict(x=T(WW.x_des), u=T(WW.u_des), ul=T(WW.u_last), r=T(WW.rbd), m=T(WW.mode), p=T(WW.period), t=T(WW.time))
+        wcmd = torch.zeros(WW.B, 54, dtype=f64, device=dev)
+        wst = torch.zeros(WW.B, dtype=i32, device=dev)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            wctx.update_dev(wd["x"], wd["ul"], wd["r"], wd["m"], wd["p"], wd["t"], wcmd, wst)
+        wctx.sync()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        with torch.cuda.stream(wstream):
+            w0.record(wstream)
+            for i in range(reps):
+                wctx.update_dev(wd["x"], wd["u"] if i % 2 == 0 else wd["ul"], wd["r"], wd["m"], wd["p"], wd["t"], wcmd, wst)
+            w1.record(wstream)
+        wctx.sync()
+        torch.cuda.synchronize()
+        wms = w0.elapsed_time(w1) / reps
+        wbad = int(((wst.cpu().numpy() & ~2) != 0).sum())
+        wbc_line = {"metric": "WBC-solves/s (HierarchicalWbc 3-level stack, batch=65536 contact configurations)",
+                    "value": WW.B / (wms * 1e-3), "unit": "WBC-solves/s", "ms_per_batch": wms, "batch": WW.B,
+                    "failed_solves": wbad, "kernel": "k_wbc",
+                    "algorithmic_bytes_per_solve": 1376, "achieved_gbs": WW.B * 1376 / (wms * 1e-3) / 1e9,
+                    "note": "fused dynamics + task stack + hierarchical QP per CTA; FP64 / active-set latency bound, not HBM bound"}
+        wctx.close()
+
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -277,6 +309,10 @@ def run_gpu(args, rank, world, local_rank):
                 md = int(modes_last[b, kk])
                 nodes_bytes += kernel_bytes_per_node(dom, 14 + bin(md & 15).count("1"))
         achieved = nodes_bytes / (ms_dom * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")       # DRAM bytes per launch from the committed ncu capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
         cyc_bytes = sum(cycle_bytes_per_node(16) for _ in range(1)) * float(nn.sum() - B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -286,7 +322,7 @@ def run_gpu(args, rank, world, local_rank):
                     "ms_per_step": e2e_ms / args.steps, "failed_problems": e2e_bad},
             "gpu_launches": int(sum(v[1] for v in kt.values())),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": int(nodes_bytes),
                          "share_of_step": kt[dom][0] / max(1e-9, sum(v[0] for v in kt.values())),
                          "cycle_level": {"algorithmic_bytes_per_step": int(cyc_bytes),
@@ -298,6 +334,8 @@ def run_gpu(args, rank, world, local_rank):
             "failed_problems": bad, "mean_step_size": alpha_mean,
             "nodes_per_problem": [int(nn.min()), int(nn.max())],
         }
+        if wbc_line is not None:
+            line["secondary"] = wbc_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))
@@ -314,6 +352,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wbc", action="store_true", help="skip the secondary WBC-solves/s measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb2
 constexpr int kLqSmemDoubles = TW_SIZE + 96;
 constexpr size_t kLqSmemBytes = kLqSmemDoubles * sizeof(double) + TI_SIZE * sizeof(int);
 
-__global__ void __launch_bounds__(128) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+#ifndef QM_LQ_THREADS
+#define QM_LQ_THREADS 256
+#endif
+__global__ void __launch_bounds__(QM_LQ_THREADS) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
   const int k = blockIdx.x, b = blockIdx.y;
   const int nn = m.nn[b];
   if (k >= nn) return;
@@ -334,7 +337,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
   { KernelTimer kt(c, KN_KIN1); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
   { KernelTimer kt(c, KN_KIN2); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
-  { KernelTimer kt(c, KN_LQ); k_lq<<<dim3(NMAX, B), 128, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
+  { KernelTimer kt(c, KN_LQ); k_lq<<<dim3(NMAX, B), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
   { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
   CUDA_OK(cudaGetLastError());
   const int max_iters = 24;
