@@ -41,6 +41,9 @@ def model_desc(m):
     _abi._set(d.lower, np.nan_to_num(m.lower, neginf=-1e30))
     _abi._set(d.upper, np.nan_to_num(m.upper, posinf=1e30))
     _abi._set(d.effort, m.effort)
+    std = [(0, (1, 0, 0)), (0, (0, 1, 0)), (0, (0, 0, 1)), (1, (0, 0, 1)), (1, (0, 1, 0)), (1, (1, 0, 0))]
+    d.root6_standard = int(all(m.parent[k] == k - 1 and m.jtype[k] == std[k][0] and np.array_equal(m.axis[k], std[k][1])
+                               and np.array_equal(m.Rp[k], np.eye(3)) and not m.pp[k].any() for k in range(6)))
     return d
 
 

@@ -30,6 +30,8 @@ class ModelDesc(C.Structure):
         ("lower", C.c_double * NJ),
         ("upper", C.c_double * NJ),
         ("effort", C.c_double * NJ),
+        ("root6_standard", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

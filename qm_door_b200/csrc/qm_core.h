@@ -98,6 +98,7 @@ QM_HD void sym3_mul(const double* s, const double* v, double* o) {
 // ------------------------------------------------------------------------------------------ kinematics workspace
 // Offsets (in doubles) into the kinematics workspace.
 enum {
+  // ---- value level (needed by every evaluation); KW_VSIZE doubles suffice when no Jacobians / derivatives are requested
   KW_R = 0,                          // [24][9]  world rotation of joint frames
   KW_P = KW_R + QM_NJ * 9,           // [24][3]  world origin of joint frames
   KW_AX = KW_P + QM_NJ * 3,          // [24][3]  world joint axis
@@ -107,19 +108,21 @@ enum {
   KW_SV = KW_ACM + 6 * QM_NJ,        // [24][6]  S_j v_j  -> reused for subtree momenta
   KW_V = KW_SV + QM_NJ * 6,          // [24][6]  spatial velocity (w, vO) of each body, world origin
   KW_HB = KW_V + QM_NJ * 6,          // [24][6]  body momentum (L0, p)
-  KW_DH = KW_HB + QM_NJ * 6,         // [6][24]  d(A v)/dq at fixed v (centroidal)
-  KW_FPOS = KW_DH + 6 * QM_NJ,       // [4][3]
+  KW_FPOS = KW_HB + QM_NJ * 6,       // [4][3]
   KW_FVEL = KW_FPOS + 12,            // [4][3]
-  KW_FJ = KW_FVEL + 12,              // [4][3][24] foot linear Jacobians
-  KW_DFV = KW_FJ + 12 * QM_NJ,       // [4][3][24] d(J_i v)/dq at fixed v
-  KW_EEP = KW_DFV + 12 * QM_NJ,      // [3]
+  KW_EEP = KW_FVEL + 12,             // [3]
   KW_EER = KW_EEP + 3,               // [9]
-  KW_EEJ = KW_EER + 9,               // [6][24] ee Jacobian [linear; angular]
-  KW_COM = KW_EEJ + 6 * QM_NJ,       // [3]
+  KW_COM = KW_EER + 9,               // [3]
   KW_ABINV = KW_COM + 3,             // [36]
   KW_VEL = KW_ABINV + 36,            // [24] generalized velocity
   KW_RHS = KW_VEL + QM_NJ,           // [6]
-  KW_F = KW_RHS + 6,                 // [24][6] composite momentum per unit joint rate I^c_j S_j = (L0, p)  (CRBA columns)
+  KW_VSIZE = ((KW_RHS + 6 + 3) / 4) * 4,
+  // ---- Jacobian / derivative level
+  KW_FJ = KW_VSIZE,                  // [4][3][24] foot linear Jacobians
+  KW_EEJ = KW_FJ + 12 * QM_NJ,       // [6][24] ee Jacobian [linear; angular]
+  KW_DH = KW_EEJ + 6 * QM_NJ,        // [6][24]  d(A v)/dq at fixed v (centroidal)
+  KW_DFV = KW_DH + 6 * QM_NJ,        // [4][3][24] d(J_i v)/dq at fixed v
+  KW_F = KW_DFV + 12 * QM_NJ,        // [24][6] composite momentum per unit joint rate I^c_j S_j = (L0, p)  (CRBA columns)
   KW_SIZE = ((KW_F + 6 * QM_NJ + 3) / 4) * 4
 };
 
@@ -147,9 +150,38 @@ QM_HD void inertia_mul(const double* I, const double* V, double* h) {
 
 // Position level: placements, composite inertias, centroidal momentum matrix, frame positions and Jacobians. q[24].
 template <class G>
-QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, double* w) {
-  // P1: placements, level by level
-  for (int d = 0; d <= M.max_depth; ++d) {
+QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, double* w, bool jac = true) {
+  // P1: placements. A standard floating base (joints 0..5) is placed in closed form by its six lanes at once
+  //     (R = Rz(yaw) Ry(pitch) Rx(roll), p = base position); the remaining joints level by level.
+  int d0 = 0;
+  if (M.root6_standard) {
+    QM_PFOR(g, j, 6) {
+      double sz, cz, sy, cy, sx, cx;
+      sincos(q[3], &sz, &cz); sincos(q[4], &sy, &cy); sincos(q[5], &sx, &cx);
+      double* Rj = w + KW_R + 9 * j;
+      double* pj = w + KW_P + 3 * j;
+      double* aj = w + KW_AX + 3 * j;
+      pj[0] = q[0]; pj[1] = (j >= 1) ? q[1] : 0.0; pj[2] = (j >= 2) ? q[2] : 0.0;
+      if (j <= 2) {
+        for (int k = 0; k < 9; ++k) Rj[k] = (k % 4 == 0) ? 1.0 : 0.0;
+        aj[0] = (j == 0); aj[1] = (j == 1); aj[2] = (j == 2);
+      } else if (j == 3) {
+        Rj[0] = cz; Rj[1] = -sz; Rj[2] = 0; Rj[3] = sz; Rj[4] = cz; Rj[5] = 0; Rj[6] = 0; Rj[7] = 0; Rj[8] = 1;
+        aj[0] = 0; aj[1] = 0; aj[2] = 1;
+      } else if (j == 4) {
+        Rj[0] = cz * cy; Rj[1] = -sz; Rj[2] = cz * sy; Rj[3] = sz * cy; Rj[4] = cz; Rj[5] = sz * sy; Rj[6] = -sy; Rj[7] = 0; Rj[8] = cy;
+        aj[0] = -sz; aj[1] = cz; aj[2] = 0;
+      } else {
+        Rj[0] = cz * cy; Rj[1] = cz * sy * sx - sz * cx; Rj[2] = cz * sy * cx + sz * sx;
+        Rj[3] = sz * cy; Rj[4] = sz * sy * sx + cz * cx; Rj[5] = sz * sy * cx - cz * sx;
+        Rj[6] = -sy;     Rj[7] = cy * sx;                Rj[8] = cy * cx;
+        aj[0] = cz * cy; aj[1] = sz * cy; aj[2] = -sy;
+      }
+    }
+    g.sync();
+    d0 = 6;
+  }
+  for (int d = d0; d <= M.max_depth; ++d) {
     QM_PFOR(g, j, QM_NJ) {
       if (M.depth[j] != d) continue;
       double Rpar[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ppar[3] = {0, 0, 0};
@@ -255,6 +287,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
     w[KW_ACM + 3 * QM_NJ + j] = h[0] - t[0];
     w[KW_ACM + 4 * QM_NJ + j] = h[1] - t[1];
     w[KW_ACM + 5 * QM_NJ + j] = h[2] - t[2];
+    if (!jac) continue;                 // value-only evaluation: the workspace ends at KW_VSIZE
     for (int c = 0; c < 6; ++c) w[KW_F + 6 * j + c] = h[c];
     for (int f = 0; f < QM_NFEET + 1; ++f) {
       const int b = (f < QM_NFEET) ? M.foot_joint[f] : M.ee_joint;
@@ -419,8 +452,9 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
 // velocity implied by (x,u) and the q-derivatives at fixed velocity needed for the linearisation.
 //   q = x[6:30];   u != nullptr -> velocity level;   deriv -> KW_DH / KW_DFV as well
 template <class G>
-QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, bool deriv, double* w) {
-  kin_positions(g, M, x + 6, w);
+QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, bool deriv, double* w,
+                     bool jac = true) {
+  kin_positions(g, M, x + 6, w, jac || deriv);
   if (u == nullptr) return;
   centroidal_velocity(g, M, x, u, w);
   kin_velocities(g, M, deriv, w);

@@ -335,6 +335,16 @@ void finalize_model(qmb200_model_desc* M) {
   }
   M->total_mass = 0;
   for (int j = 0; j < QM_NJ; ++j) M->total_mass += M->mass[j];
+  // standard floating base? (lets the kinematics place joints 0..5 in closed form instead of walking the chain)
+  static const int kType[6] = {0, 0, 0, 1, 1, 1};
+  static const double kAxis[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 1}, {0, 1, 0}, {1, 0, 0}};
+  bool stdroot = true;
+  for (int k = 0; k < 6; ++k) {
+    stdroot = stdroot && M->parent[k] == k - 1 && M->jtype[k] == kType[k];
+    for (int c = 0; c < 3; ++c) stdroot = stdroot && M->axis[k][c] == kAxis[k][c] && M->pp[k][c] == 0.0;
+    for (int c = 0; c < 9; ++c) stdroot = stdroot && M->Rp[k][c] == ((c % 4 == 0) ? 1.0 : 0.0);
+  }
+  M->root6_standard = stdroot ? 1 : 0;
 }
 
 template <class F>

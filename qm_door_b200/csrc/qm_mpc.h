@@ -211,7 +211,7 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
 // f (30) and, if Fr != nullptr, the nine non-trivial rows (f rows 3..11) of [df/dx | df/du] as Fr[9][60].
 template <class G>
 QM_HDN void flow_rows(G g, const qmb200_model_desc& M, double gravity, const double* w, const double* x, const double* u,
-                      double* f, double* Fr) {
+                      double* f, double* Fr, double* vb_shadow = nullptr) {
   const double m = M.total_mass;
   QM_PFOR(g, i, 30) {
     double v;
@@ -267,6 +267,7 @@ QM_HDN void flow_rows(G g, const qmb200_model_desc& M, double gravity, const dou
         }
       }
       Fr[idx] = v;
+      if (vb_shadow != nullptr && r >= 3) vb_shadow[idx - 180] = v;   // rows of v_b = A_b^-1(...) kept close for the constraint rows
     }
   }
   g.sync();
@@ -468,10 +469,11 @@ QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_des
   const int nv = nvc;                 // velocity-constraint rows: 3 per stance foot, 1 per swing foot
   if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, scr);
   kin_eval(g, M, x, u, true, kw);
-  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1);
+  // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) placement arrays R | P | AX of the workspace
+  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_R);
   ee_terms(g, kw, scr, io.e6, scr + RF_SIZE, io.je);
   {
-    const double* Fr1 = io.fr1;
+    const double* Fr1 = kw + KW_R - 180;   // Fr1[(3 + cc) * 60 + c] -> shadow[cc * 60 + c]
     QM_PFOR(g, idx, nv * 49) {
       const int row = idx / 49, c = idx % 49;
       // map row -> (foot, component)
@@ -846,7 +848,7 @@ QM_HDN void terminal_node(G g, const qmb200_model_desc& M, const qmb200_problem_
                           double* sb, double* perf) {
   const bool deriv = JE != nullptr;
   if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, ref);
-  kin_eval(g, M, x, (const double*)nullptr, false, kw);
+  kin_eval(g, M, x, (const double*)nullptr, false, kw, deriv);      // Jacobians only when the Gauss-Newton terms are wanted
   ee_terms(g, kw, ref, e6, dq, JE);
   if (g.tid() == 0) {
     const double* e = e6;
@@ -875,7 +877,7 @@ QM_HDN void terminal_node(G g, const qmb200_model_desc& M, const qmb200_problem_
 
 // ------------------------------------------------------------------------------------------ line-search node evaluation
 // Value-only evaluation of one intermediate node ([upstream] computeIntermediatePerformance): needs W of size PW_SIZE.
-enum { PW_KIN = 0, PW_REF = KW_SIZE, PW_F1 = PW_REF + RF_SIZE, PW_F2 = PW_F1 + 30, PW_X2 = PW_F2 + 30, PW_E6 = PW_X2 + 30,
+enum { PW_KIN = 0, PW_REF = KW_VSIZE, PW_F1 = PW_REF + RF_SIZE, PW_F2 = PW_F1 + 30, PW_X2 = PW_F2 + 30, PW_E6 = PW_X2 + 30,
        PW_DQ = PW_E6 + 8, PW_DX = PW_DQ + 10, PW_DU = PW_DX + 30, PW_TQ = PW_DU + 30, PW_TR = PW_TQ + 30, PW_SCAL = PW_TR + 30,
        PW_SIZE = PW_SCAL + 4 };
 template <class G>
@@ -884,7 +886,7 @@ QM_HDN void perf_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc
                       const double* xn, double* W, double* perf) {
   double* kw = W + PW_KIN;
   if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, W + PW_REF);
-  kin_eval(g, M, x, u, false, kw);
+  kin_eval(g, M, x, u, false, kw, false);
   flow_rows(g, M, P.gravity, kw, x, u, W + PW_F1, (double*)nullptr);
   ee_terms(g, kw, W + PW_REF, W + PW_E6, W + PW_DQ, (double*)nullptr);
   QM_PFOR(g, i, 30) {
@@ -916,7 +918,7 @@ QM_HDN void perf_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc
     W[PW_SCAL + 0] = c0; W[PW_SCAL + 1] = eq;
   }
   g.sync();
-  kin_eval(g, M, W + PW_X2, u, false, kw);
+  kin_eval(g, M, W + PW_X2, u, false, kw, false);
   flow_rows(g, M, P.gravity, kw, W + PW_X2, u, W + PW_F2, (double*)nullptr);
   if (g.tid() == 0) {
     double dyn = 0.0;

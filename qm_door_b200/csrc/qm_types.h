@@ -38,6 +38,8 @@ typedef struct qmb200_model_desc {
   double ee_Roff[9];
   double total_mass;
   double lower[QM_NJ], upper[QM_NJ], effort[QM_NJ];
+  int32_t root6_standard;    // joints 0..5 are the standard floating base (prismatic x,y,z; revolute z,y,x; identity placements)
+  int32_t reserved;
 } qmb200_model_desc;
 
 // Optimal-control-problem constants. Replaces what QMInterface::setupOptimalControlProblem

@@ -7,7 +7,7 @@
 //   k_kin<2>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
 //   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
-//   k_trial      <<<(NMAX/4, B), 128>>>      warp per node: value-only evaluation of the trial step
+//   k_trial      <<<(NMAX/2, B), 64>>>       warp per node: value-only evaluation of the trial step (small value-level workspace)
 //   k_decide     <<<ceil(B/128), 128>>>      thread per problem: filter line-search acceptance
 //   k_finalize   <<<B, 64>>>                 thread per component: publish primal solution + warm start
 // There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
@@ -209,11 +209,11 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS) k_solve(MpcBuffers m) {
   solve_problem(BlockGroup(), fetch, m, blockIdx.x, W);
 }
 
-constexpr int kTrialWarps = 4;
+constexpr int kTrialWarps = 2;
 constexpr int kTrialWarpDoubles = PW_SIZE + 96;
 constexpr size_t kTrialSmemBytes = (size_t)kTrialWarps * kTrialWarpDoubles * sizeof(double);
 
-__global__ void __launch_bounds__(128) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+__global__ void __launch_bounds__(32 * kTrialWarps) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * kTrialWarps + warp, b = blockIdx.y;
   const double* ls = m.ls + (size_t)b * LS_SIZE;
@@ -343,7 +343,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   const int max_iters = 24;
   for (int it = 0; it < max_iters; ++it) {
     CUDA_OK(cudaMemsetAsync(c->d_pending, 0, sizeof(int), st));
-    { KernelTimer kt(c, KN_TRIAL); k_trial<<<dim3((NMAX + kTrialWarps - 1) / kTrialWarps, B), 128, kTrialSmemBytes, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_TRIAL); k_trial<<<dim3((NMAX + kTrialWarps - 1) / kTrialWarps, B), 32 * kTrialWarps, kTrialSmemBytes, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_DECIDE); k_decide<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending); }
     CUDA_OK(cudaMemcpyAsync(c->h_pending, c->d_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
