@@ -155,3 +155,44 @@ def test_error_statuses_on_device(descs):
     with pytest.raises(ValueError):
         ctx.cycle(np.zeros(B + 1), np.tile(x_init, (B, 1)), ev, md, ne, np.tile([0.0, 1.0], (B, 1)), np.tile(knot, (B, 2, 1)))
     ctx.close()
+
+
+def test_gait_library_batch_against_cpu_port(descs):
+    """BASELINE config 4 shape: the 11 moving gaits of gait.info x seeds in ONE batch (different constraint counts and event
+    patterns per problem, incl. flight phases), 3 warm-started cycles, every problem against the CPU port."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    from oracle import abi_fill
+    gaits = ["trot", "standing_trot", "flying_trot", "pace", "standing_pace", "dynamic_walk", "static_walk", "amble",
+             "lindyhop", "skipping", "pawup"]
+    per = 4
+    B = len(gaits) * per
+    hor = 0.5
+    base = workload.Workload(B, horizon=hor, dt=0.01, seed=20261019, max_events=48, max_nodes=51 + 2 * 24)
+    rng = np.random.default_rng(20261019)
+    base.x0[:, 0:6] += rng.uniform(-0.3, 0.3, (B, 6))                 # external base momentum kick (SURVEY §8d config 4)
+    for gi, name in enumerate(gaits):
+        sw, md = q.load_gait(name)
+        for s in range(per):
+            b = gi * per + s
+            ev, ms, ne = q.tile_schedule(sw, md, -np.ceil(hor / sw[-1]) * sw[-1] - base.phase[b], 0.1 + 2.0 * hor, 48)
+            base.events[b], base.modes[b], base.nevents[b] = ev, ms, ne
+    ctx = q.MpcContext(base.model, base.problem, base.solver, B)
+    cp = abi_fill.CPort(base.model, base.problem, base.solver, B, threads=8)
+    seen_modes = set()
+    for c in range(3):
+        t0 = np.full(B, 0.01 * c)
+        out = ctx.cycle(t0, base.x0, base.events, base.modes, base.nevents, base.target_t, base.target_x)
+        ref = cp.cycle(t0, base.x0, base.events, base.modes, base.nevents, base.target_t, base.target_x)
+        assert np.array_equal(out["status"], ref["status"]) and ((out["status"] & ~32) == 0).all(), (out["status"], ref["status"])
+        assert np.array_equal(out["n"], ref["n"])
+        for b in range(B):
+            n = out["n"][b]
+            assert np.array_equal(out["mode"][b, :n], ref["mode"][b, :n]) and np.array_equal(out["t"][b, :n], ref["t"][b, :n])
+            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < EXPECTED_TOL, (gaits[b // per], c)
+            assert rel_l2(out["u"][b, :n], ref["u"][b, :n]) < 1e-7, (gaits[b // per], c)
+            seen_modes.update(int(v) for v in out["mode"][b, :n])
+        assert np.array_equal(out["info"][:, 0], ref["info"][:, 0])
+    assert 0 in seen_modes and 15 in seen_modes and len(seen_modes) >= 10      # flight, full stance and most contact patterns
+    ctx.close()
+    cp.close()

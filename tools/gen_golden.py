@@ -54,6 +54,41 @@ if __name__ == "__main__" and len(sys.argv) == 1:
     main()
 
 
+def backtracking_golden():
+    """A case where the filter line search rejects the full step (alpha = 0.5): problems 34, 66, 94 of the seed-123 batch
+    (horizon 0.3 s, trot), cycles 0..3 with warm start. Found with the CPU port, generated with the NumPy oracle."""
+    from qm_door_b200 import workload
+    m, P = config.load_default()
+    W = workload.Workload(256, horizon=0.3, dt=0.01, seed=123)
+    pick = [34, 66, 94]
+    cycles = 4
+    outs = []
+    for b in pick:
+        ne = W.nevents[b]
+        prob = sqp.MpcProblem(m, P, W.events[b, :ne], W.modes[b, :ne + 1], W.target_t[b], W.target_x[b], horizon=0.3, dt=0.01)
+        for c in range(cycles):
+            outs.append((pick.index(b), c) + sqp.mpc_cycle(prob, 0.01 * c, W.x0[b]))
+    B = len(pick)
+    nmax = max(len(o[2]) for o in outs)
+    T = np.zeros((cycles, B, nmax)); X = np.zeros((cycles, B, nmax, 30)); U = np.zeros((cycles, B, nmax, 30))
+    NN = np.zeros((cycles, B), dtype=np.int32); MD = np.zeros((cycles, B, nmax), dtype=np.int32)
+    AL = np.zeros((cycles, B)); PERF = np.zeros((cycles, B, 7))
+    for b, c, tout, xs, us, info in outs:
+        n = len(tout)
+        T[c, b, :n], X[c, b, :n], U[c, b, :n], NN[c, b], MD[c, b, :n] = tout, xs, us, n, info["modes"]
+        AL[c, b] = info["alpha"]
+        PERF[c, b] = [info["armijo"], info["base"]["merit"], info["base"]["dyn"], info["base"]["eq"],
+                      info["new"]["merit"], info["new"]["dyn"], info["new"]["eq"]]
+    EM = 40
+    events = np.full((B, EM), 1e30); modes = np.full((B, EM + 1), 15, dtype=np.int32)
+    events[:, :W.events.shape[1]] = W.events[pick]; modes[:, :W.modes.shape[1]] = W.modes[pick]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mpc_cycle_trot_backtracking.npz"), gait="trot", horizon=0.3, dt=0.01,
+                        x0=W.x0[pick], events=events, modes=modes, nevents=W.nevents[pick], target_t=W.target_t[pick],
+                        target_x=W.target_x[pick], t=T, x=X, u=U, n=NN, mode=MD, alpha=AL, perf=PERF)
+    print("backtracking golden: alpha", AL)
+    assert (AL < 1.0).any()
+
+
 def wbc_golden():
     """WBC golden vectors: 48 solves of config-5 style inputs (all 16 contact patterns, both task stacks, t < 10 s stack)."""
     from oracle import wbc
@@ -78,3 +113,5 @@ def wbc_golden():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "wbc":
     wbc_golden()
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "backtracking":
+    backtracking_golden()
