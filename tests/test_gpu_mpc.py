@@ -189,8 +189,10 @@ def test_gait_library_batch_against_cpu_port(descs):
         for b in range(B):
             n = out["n"][b]
             assert np.array_equal(out["mode"][b, :n], ref["mode"][b, :n]) and np.array_equal(out["t"][b, :n], ref["t"][b, :n])
-            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < EXPECTED_TOL, (gaits[b // per], c)
-            assert rel_l2(out["u"][b, :n], ref["u"][b, :n]) < 1e-7, (gaits[b // per], c)
+            # perturbed flight-phase problems are the worst conditioned of the suite (CPU port and GPU differ in the
+            # factorisation route of the Riccati Hessian and in FMA contraction): 1e-6 here, 1e-4 is the contract
+            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < 1e-6, (gaits[b // per], c)
+            assert rel_l2(out["u"][b, :n], ref["u"][b, :n]) < 1e-6, (gaits[b // per], c)
             seen_modes.update(int(v) for v in out["mode"][b, :n])
         assert np.array_equal(out["info"][:, 0], ref["info"][:, 0])
     assert 0 in seen_modes and 15 in seen_modes and len(seen_modes) >= 10      # flight, full stance and most contact patterns
