@@ -49,12 +49,16 @@ struct WarpGroup {
   __device__ __forceinline__ bool rest_active() const { return true; }
   __device__ __forceinline__ WarpGroup narrow() const { return *this; }
   __device__ __forceinline__ WarpGroup rest() const { return *this; }
+  __device__ __forceinline__ int warp() const { return 0; }
+  __device__ __forceinline__ int nwarps() const { return 1; }
 };
 // warps 1.. of the CTA, synchronised with named barrier 1
 struct RestGroup {
   __device__ __forceinline__ int tid() const { return threadIdx.x - 32; }
   __device__ __forceinline__ int nt() const { return blockDim.x - 32; }
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
+  __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) - 1; }
+  __device__ __forceinline__ int nwarps() const { return (blockDim.x >> 5) - 1; }
 };
 struct BlockGroup {
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
@@ -64,6 +68,8 @@ struct BlockGroup {
   __device__ __forceinline__ bool rest_active() const { return threadIdx.x >= 32; }
   __device__ __forceinline__ WarpGroup narrow() const { return WarpGroup(); }
   __device__ __forceinline__ RestGroup rest() const { return RestGroup(); }
+  __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
+  __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
 };
 #endif
 #define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())
@@ -93,6 +99,64 @@ QM_HD void sym3_mul(const double* s, const double* v, double* o) {
   o[0] = s[0] * v[0] + s[1] * v[1] + s[2] * v[2];
   o[1] = s[1] * v[0] + s[3] * v[1] + s[4] * v[2];
   o[2] = s[2] * v[0] + s[4] * v[1] + s[5] * v[2];
+}
+
+// ------------------------------------------------------------------------------------------ small dense products
+// C[m x n] = C0 + alpha * op(X) Y      op(X) = X (m x k, row-major ldx) or X' (X stored k x m) ; Y: k x n (ldy).
+// Device: FP64 tensor-core tiles (mma.sync.m8n8k4.f64 = SASS DMMA.8x8x4, 256 FMA per warp instruction) with edge
+// predication instead of padding; each warp of the group owns (tile row, up to TJ tile columns) units so an X fragment is
+// loaded once per k-step. Host: plain loops. C0 may alias C (each element is read and written by the same thread).
+#if defined(__CUDACC__)
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+#endif
+template <int TJ, bool xT, class G>
+QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double* Y, int ldy, const double* C0, int ld0,
+               double alpha, double* C, int ldc) {
+#if defined(__CUDA_ARCH__)
+  const int lane = threadIdx.x & 31;
+  const int tm = (m + 7) >> 3, tn = (n + 7) >> 3;
+  const int gj = (tn + TJ - 1) / TJ;
+  const int r = lane >> 2, q = lane & 3;
+  for (int unit = g.warp(); unit < tm * gj; unit += g.nwarps()) {
+    const int i0 = (unit / gj) << 3, j0 = (unit % gj) * TJ * 8;
+    double acc[TJ][2];
+#pragma unroll
+    for (int t = 0; t < TJ; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    const int i = i0 + r;
+    const bool iok = i < m;
+    const double* xp = xT ? (X + i + q * ldx) : (X + i * ldx + q);     // advances by 4 rows (xT) / 4 columns per k-step
+    const int xstep = xT ? 4 * ldx : 4;
+    const double* yp = Y + q * ldy + j0 + r;
+    for (int k0 = 0; k0 < k; k0 += 4, xp += xstep, yp += 4 * ldy) {
+      const bool kok = (k0 + q) < k;
+      const double a = (iok && kok) ? *xp : 0.0;
+#pragma unroll
+      for (int t = 0; t < TJ; ++t) {
+        if (j0 + 8 * t < n) {                     // warp-uniform
+          const double b = (kok && (j0 + 8 * t + r) < n) ? yp[8 * t] : 0.0;
+          dmma884(acc[t][0], acc[t][1], a, b);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TJ; ++t) {
+      const int j = j0 + 8 * t + 2 * q;
+      if (i < m && j0 + 8 * t < n) {
+        if (j < n) C[i * ldc + j] = (C0 ? C0[i * ld0 + j] : 0.0) + alpha * acc[t][0];
+        if (j + 1 < n) C[i * ldc + j + 1] = (C0 ? C0[i * ld0 + j + 1] : 0.0) + alpha * acc[t][1];
+      }
+    }
+  }
+#else
+  QM_PFOR(g, idx, m * n) {
+    const int i = idx / n, j = idx % n;
+    double acc = 0.0;
+    for (int kk = 0; kk < k; ++kk) acc += (xT ? X[kk * ldx + i] : X[i * ldx + kk]) * Y[kk * ldy + j];
+    C[i * ldc + j] = (C0 ? C0[i * ld0 + j] : 0.0) + alpha * acc;
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ kinematics workspace

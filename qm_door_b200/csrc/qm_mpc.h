@@ -1006,57 +1006,25 @@ __device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, int* status)
 template <class G>
 QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
   const int nut = (int)st[SB_NUT];
-  const int nt3 = (nut + 2) / 3;                 // column tiles of the reduced input
   const double* A = st + SB_A; const double* B = st + SB_B; const double* b = st + SB_b;
   double* S = W + RW_S; double* s = W + RW_sv;
   // ---- P1: SA = S A, SB = S B, sb = s + S b
-  QM_PFOR(g, item, 100 + 10 * nt3 + 10) {
-    if (item < 100) {
-      const int i0 = 3 * (item / 10), j0 = 3 * (item % 10);
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      QM_TILE3(acc, S, 30, A, 30, i0, j0, 30);
-      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_SA + 30 * (i0 + r) + j0 + c] = acc[3 * r + c];
-    } else if (item < 100 + 10 * nt3) {
-      const int it = item - 100;
-      const int i0 = 3 * (it / nt3), j0 = 3 * (it % nt3);
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      QM_TILE3(acc, S, 30, B, QM_NUT, i0, j0, 30);
-      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_SB + QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
-    } else {
-      const int i0 = 3 * (item - 100 - 10 * nt3);
-      for (int r = 0; r < 3; ++r) {
-        double acc = s[i0 + r];
-        for (int j = 0; j < 30; ++j) acc += S[30 * (i0 + r) + j] * b[j];
-        W[RW_sb + i0 + r] = acc;
-      }
-    }
+  mm<4, false>(g, 30, 30, 30, S, 30, A, 30, (const double*)nullptr, 0, 1.0, W + RW_SA, 30);
+  if (nut > 0) mm<3, false>(g, 30, nut, 30, S, 30, B, QM_NUT, (const double*)nullptr, 0, 1.0, W + RW_SB, QM_NUT);
+  QM_PFOR(g, i, 30) {
+    double acc = s[i];
+    for (int j = 0; j < 30; ++j) acc += S[30 * i + j] * b[j];
+    W[RW_sb + i] = acc;
   }
   g.sync();
   // ---- P2: G = R + B' SB, H = P + B' SA, g = r + B' sb
   if (nut > 0) {
-    QM_PFOR(g, item, nt3 * nt3 + nt3 * 10 + nt3) {
-      if (item < nt3 * nt3) {
-        const int i0 = 3 * (item / nt3), j0 = 3 * (item % nt3);
-        double acc[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_R + QM_NUT * (i0 + r) + j0 + c];
-        QM_TILE3_T(acc, B, QM_NUT, W + RW_SB, QM_NUT, i0, j0, 30);
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_G + QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
-      } else if (item < nt3 * nt3 + nt3 * 10) {
-        const int it = item - nt3 * nt3;
-        const int i0 = 3 * (it / 10), j0 = 3 * (it % 10);
-        double acc[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_P + 30 * (i0 + r) + j0 + c];
-        QM_TILE3_T(acc, B, QM_NUT, W + RW_SA, 30, i0, j0, 30);
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_H + 30 * (i0 + r) + j0 + c] = acc[3 * r + c];
-      } else {
-        const int i0 = 3 * (item - nt3 * nt3 - nt3 * 10);
-        for (int r = 0; r < 3; ++r) {
-          const int a = i0 + r;
-          double acc = (a < nut) ? st[SB_r + a] : 0.0;
-          for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_sb + k];
-          W[RW_gv + a] = acc;
-        }
-      }
+    mm<3, true>(g, nut, nut, 30, B, QM_NUT, W + RW_SB, QM_NUT, st + SB_R, QM_NUT, 1.0, W + RW_G, QM_NUT);
+    mm<4, true>(g, nut, 30, 30, B, QM_NUT, W + RW_SA, 30, st + SB_P, 30, 1.0, W + RW_H, 30);
+    QM_PFOR(g, a, nut) {
+      double acc = st[SB_r + a];
+      for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_sb + k];
+      W[RW_gv + a] = acc;
     }
     g.sync();
   }
@@ -1083,10 +1051,10 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
       }
       w0.sync();
     }
-    QM_PFOR(w0, c, QM_NUT) {
-      for (int i = 0; i < QM_NUT; ++i) {
+    QM_PFOR(w0, c, nut) {
+      for (int i = 0; i < nut; ++i) {
         double v = 0.0;
-        if (c < nut && i < nut && i >= c) {
+        if (i >= c) {
           v = (i == c) ? 1.0 : 0.0;
           for (int k = c; k < i; ++k) v -= Gm[QM_NUT * i + k] * W[RW_LI + QM_NUT * k + c];
           v /= Gm[QM_NUT * i + i];
@@ -1095,52 +1063,22 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
       }
     }
     w0.sync();
-    QM_PFOR(w0, item, nt3 * nt3) {
-      const int i0 = 3 * (item / nt3), j0 = 3 * (item % nt3);
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      const int k0 = (i0 > j0) ? i0 : j0;              // LI is lower triangular: rows k >= max(i, j) contribute
-      for (int k = k0; k < 3 * nt3; ++k) {
-        const double x0 = W[RW_LI + QM_NUT * k + i0], x1 = W[RW_LI + QM_NUT * k + i0 + 1], x2 = W[RW_LI + QM_NUT * k + i0 + 2];
-        const double y0 = W[RW_LI + QM_NUT * k + j0], y1 = W[RW_LI + QM_NUT * k + j0 + 1], y2 = W[RW_LI + QM_NUT * k + j0 + 2];
-        acc[0] += x0 * y0; acc[1] += x0 * y1; acc[2] += x0 * y2;
-        acc[3] += x1 * y0; acc[4] += x1 * y1; acc[5] += x1 * y2;
-        acc[6] += x2 * y0; acc[7] += x2 * y1; acc[8] += x2 * y2;
-      }
-      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Gm[QM_NUT * (i0 + r) + j0 + c] = acc[3 * r + c];
+    QM_PFOR(w0, idx, nut * nut) {       // Ginv = LI' LI
+      const int i = idx / nut, j = idx % nut;
+      double acc = 0.0;
+      for (int k = (i > j ? i : j); k < nut; ++k) acc += W[RW_LI + QM_NUT * k + i] * W[RW_LI + QM_NUT * k + j];
+      Gm[QM_NUT * i + j] = acc;
     }
   }
 #endif
-  // ---- P3 rest: S <- Q + A' SA on the upper-triangle tiles (mirrored); s <- q + A' sb.  (S, s were consumed in P1.)
+  // ---- P3 rest: S <- Q + A' SA ; s <- q + A' sb   (S, s were consumed in P1; symmetrised at the end of the stage)
   if (g.rest_active()) {
     auto r_ = g.rest();
-    QM_PFOR(r_, item, 55 + 10) {
-      if (item < 55) {
-        int ti = 0, rem = item;
-        while (rem >= 10 - ti) { rem -= 10 - ti; ++ti; }
-        const int tj = ti + rem;
-        const int i0 = 3 * ti, j0 = 3 * tj;
-        double acc[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[3 * r + c] = st[SB_Q + 30 * (i0 + r) + j0 + c];
-        QM_TILE3_T(acc, A, 30, W + RW_SA, 30, i0, j0, 30);
-        if (ti == tj) {
-          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[30 * (i0 + r) + j0 + c] = acc[3 * r + c];
-        } else {
-          // mirrored tile carries the lower triangle of Q so that the later symmetrisation averages Q exactly
-          for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) {
-              S[30 * (i0 + r) + j0 + c] = acc[3 * r + c];
-              S[30 * (j0 + c) + i0 + r] = acc[3 * r + c] + (st[SB_Q + 30 * (j0 + c) + i0 + r] - st[SB_Q + 30 * (i0 + r) + j0 + c]);
-            }
-        }
-      } else {
-        const int i0 = 3 * (item - 55);
-        for (int r = 0; r < 3; ++r) {
-          const int i = i0 + r;
-          double acc = st[SB_q + i];
-          for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
-          s[i] = acc;
-        }
-      }
+    mm<2, true>(r_, 30, 30, 30, A, 30, W + RW_SA, 30, st + SB_Q, 30, 1.0, S, 30);
+    QM_PFOR(r_, i, 30) {
+      double acc = st[SB_q + i];
+      for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
+      s[i] = acc;
     }
   }
   g.sync();
@@ -1149,61 +1087,35 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
 
 template <class G>
 QM_HDN void riccati_stage_b(G g, int nut, double* W, double* gb) {
-  const int nt3 = (nut + 2) / 3;
   double* S = W + RW_S; double* s = W + RW_sv;
   double* Gm = W + RW_G;
   if (nut > 0) {
     // ---- P4: K = -Ginv H, kff = -Ginv g
-    QM_PFOR(g, item, nt3 * 10 + nt3) {
-      if (item < nt3 * 10) {
-        const int i0 = 3 * (item / 10), j0 = 3 * (item % 10);
-        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        QM_TILE3(acc, Gm, QM_NUT, W + RW_H, 30, i0, j0, nut);
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) W[RW_K + 30 * (i0 + r) + j0 + c] = -acc[3 * r + c];
-      } else {
-        const int i0 = 3 * (item - nt3 * 10);
-        for (int r = 0; r < 3; ++r) {
-          double acc = 0.0;
-          for (int k = 0; k < nut; ++k) acc += Gm[QM_NUT * (i0 + r) + k] * W[RW_gv + k];
-          W[RW_kf + i0 + r] = -acc;
-        }
-      }
+    mm<4, false>(g, nut, 30, nut, Gm, QM_NUT, W + RW_H, 30, (const double*)nullptr, 0, -1.0, W + RW_K, 30);
+    QM_PFOR(g, a, nut) {
+      double acc = 0.0;
+      for (int k = 0; k < nut; ++k) acc += Gm[QM_NUT * a + k] * W[RW_gv + k];
+      W[RW_kf + a] = -acc;
     }
     g.sync();
-  }
-  // ---- P5: S <- sym(S + H' K), s += H' kff; gains to HBM
-  QM_PFOR(g, item, 55 + 10) {
-    if (item < 55) {
-      int ti = 0, rem = item;
-      while (rem >= 10 - ti) { rem -= 10 - ti; ++ti; }
-      const int tj = ti + rem;
-      const int i0 = 3 * ti, j0 = 3 * tj;
-      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      if (nut > 0) QM_TILE3_T(acc, W + RW_H, 30, W + RW_K, 30, i0, j0, nut);
-      if (ti == tj) {
-        double t[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) t[3 * r + c] = S[30 * (i0 + r) + j0 + c] + acc[3 * r + c];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[30 * (i0 + r) + j0 + c] = 0.5 * (t[3 * r + c] + t[3 * c + r]);
-      } else {
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) {
-            const double v = 0.5 * (S[30 * (i0 + r) + j0 + c] + S[30 * (j0 + c) + i0 + r]) + acc[3 * r + c];
-            S[30 * (i0 + r) + j0 + c] = v;
-            S[30 * (j0 + c) + i0 + r] = v;
-          }
-      }
-    } else {
-      const int i0 = 3 * (item - 55);
-      for (int r = 0; r < 3; ++r) {
-        const int i = i0 + r;
-        double acc = s[i];
-        for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_kf + a];
-        s[i] = acc;
-      }
+    // ---- P5: S += H' K, s += H' kff
+    mm<4, true>(g, 30, 30, nut, W + RW_H, 30, W + RW_K, 30, S, 30, 1.0, S, 30);
+    QM_PFOR(g, i, 30) {
+      double acc = s[i];
+      for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_kf + a];
+      s[i] = acc;
     }
   }
   QM_PFOR(g, idx, QM_NUT * 30) gb[GB_K + idx] = (idx / 30 < nut) ? W[RW_K + idx] : 0.0;
   QM_PFOR(g, a, QM_NUT) gb[GB_KFF + a] = (a < nut) ? W[RW_kf + a] : 0.0;
+  g.sync();
+  QM_PFOR(g, idx, 435) {     // symmetrise: pairs i < j
+    int i = 0, r = idx;
+    while (r >= 29 - i) { r -= 29 - i; ++i; }
+    const int j = i + 1 + r;
+    const double v = 0.5 * (S[30 * i + j] + S[30 * j + i]);
+    S[30 * i + j] = v; S[30 * j + i] = v;
+  }
   g.sync();
 }
 

@@ -197,9 +197,9 @@ static_assert(kSolveFwdOff + PB_SIZE + GB_SIZE <= RW_SIZE, "forward staging must
 constexpr size_t kSolveSmemBytes = (size_t)(SB_SIZE + RW_SIZE + 2) * sizeof(double);
 
 #ifndef QM_SOLVE_THREADS
-#define QM_SOLVE_THREADS 192
+#define QM_SOLVE_THREADS 128
 #endif
-__global__ void __launch_bounds__(QM_SOLVE_THREADS) k_solve(MpcBuffers m) {
+__global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
   extern __shared__ __align__(16) double smem[];
   double* stagebuf = smem;
   double* W = smem + SB_SIZE;

@@ -75,7 +75,9 @@ def test_full_size_against_cpu_port_and_properties(descs):
         for b in range(sub):
             n = out["n"][b]
             assert np.array_equal(out["mode"][b, :n], ref["mode"][b, :n]) and np.array_equal(out["t"][b, :n], ref["t"][b, :n])
-            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < EXPECTED_TOL
+            # N = 100 chains: the GPU's tensor-core products / register Gauss-Jordan and the CPU port's scalar loops differ in
+            # summation order; 1e-7 here (golden-vector tests at small N hold 1e-8; the contract is 1e-4)
+            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < 1e-7
             assert rel_l2(out["u"][b, :n], ref["u"][b, :n]) < 1e-7
         assert np.array_equal(out["info"][:sub, 0], ref["info"][:, 0])          # accepted step sizes
         # properties over the whole batch
