@@ -427,8 +427,9 @@ enum {
   TW_BOXV = TW_BOX + 24,            // [12] their values
   TW_ROWBEST = TW_BOXV + 12,        // 12
   TW_FAC = TW_ROWBEST + 12,         // 12
-  TW_SCAL = TW_FAC + 12,            // misc scalars: [0] cost value, [1] eq sse, [2] shift term
-  TW_SIZE = TW_SCAL + 8
+  TW_SCAL = TW_FAC + 12,            // misc scalars
+  TW_AUX = TW_SCAL + 8,             // NA_SIZE: references / barrier terms of the node in the fused (host) path
+  TW_SIZE = TW_AUX + 144
 };
 enum {                               // integer workspace
   TI_ROWARG = 0,                    // 12
@@ -449,12 +450,16 @@ struct NodeIO {
   double* T;                  // [12][49] velocity-constraint rows [Dv | C | e]
   double* je;                 // [6][24] end-effector error Jacobian
   double* e6;                 // [8] end-effector error (6), [6] = sum of squared velocity-constraint values
+  double* aux;                // [NA_SIZE] references and barrier terms of the node (functions of t, x, u only)
 };
-enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = 1758, KS_E6 = 1902, KS_SIZE = 1912 };
+// aux layout: reference (x_ref, u_nominal, ee pose), friction-cone terms per foot, arm box gradients / Hessians / values
+enum { NA_REF = 0, NA_CONE = RF_SIZE, NA_BOX = NA_CONE + 40, NA_BOXV = NA_BOX + 24, NA_SIZE = NA_BOXV + 12 };
+enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = 1758, KS_E6 = 1902, KS_AUX = 1910,
+       KS_SIZE = ((KS_AUX + NA_SIZE + 3) / 4) * 4 };
 QM_HD NodeIO node_io_at(double* base) {
   NodeIO io;
   io.fr1 = base + KS_FR1; io.fr2 = base + KS_FR2; io.f1 = base + KS_F1; io.f2 = base + KS_F2;
-  io.x2 = base + KS_X2; io.T = base + KS_T; io.je = base + KS_JE; io.e6 = base + KS_E6;
+  io.x2 = base + KS_X2; io.T = base + KS_T; io.je = base + KS_JE; io.e6 = base + KS_E6; io.aux = base + KS_AUX;
   return io;
 }
 
@@ -468,6 +473,25 @@ QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_des
   for (int ft = 0; ft < 4; ++ft) nvc += ((mode >> (3 - ft)) & 1) ? 3 : 1;
   const int nv = nvc;                 // velocity-constraint rows: 3 per stance foot, 1 per swing foot
   if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, scr);
+  // barrier terms of the node: friction cones of the stance feet, arm position / velocity boxes (independent lanes)
+  QM_PFOR(g, it, 16) {
+    if (it < 4) {
+      if ((mode >> (3 - it)) & 1) cone_terms(P, u + 3 * it, io.aux + NA_CONE + 10 * it);
+    } else {
+      const int i = it - 4;
+      double v1, a1, b1, v2, a2, b2;
+      if (i < 6) {
+        relaxed_barrier(x[24 + i] - P.arm_pos_lo[i], P.pos_bar_mu, P.pos_bar_delta, &v1, &a1, &b1);
+        relaxed_barrier(P.arm_pos_hi[i] - x[24 + i], P.pos_bar_mu, P.pos_bar_delta, &v2, &a2, &b2);
+      } else {
+        relaxed_barrier(u[18 + i] - P.arm_vel_lo[i - 6], P.vel_bar_mu, P.vel_bar_delta, &v1, &a1, &b1);
+        relaxed_barrier(P.arm_vel_hi[i - 6] - u[18 + i], P.vel_bar_mu, P.vel_bar_delta, &v2, &a2, &b2);
+      }
+      io.aux[NA_BOX + 2 * i] = a1 - a2;
+      io.aux[NA_BOX + 2 * i + 1] = b1 + b2;
+      io.aux[NA_BOXV + i] = v1 + v2;
+    }
+  }
   kin_eval(g, M, x, u, true, kw);
   // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) placement arrays R | P | AX of the workspace
   flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_R);
@@ -500,6 +524,7 @@ QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_des
     }
   }
   QM_PFOR(g, i, 30) io.x2[i] = x[i] + dt * io.f1[i];
+  QM_PFOR(g, i, RF_SIZE) io.aux[NA_REF + i] = scr[i];
   g.sync();
   if (g.tid() == 0) {
     double eq = 0.0;
@@ -574,56 +599,23 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
       WI[TI_NV] = nv;
     }
   }
-  // ---- L1 rest: references, barrier terms, cost quadratic approximation (forward Euler, * dt), discrete dynamics
+  // ---- L1 rest: cost quadratic approximation (forward Euler, * dt), discrete dynamics. References and barrier terms
+  //      come with the kinematics products (io.aux), so no serial work sits in front of the wide assembly.
   if (g.rest_active()) {
     auto r = g.rest();
-    if (r.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, W + TW_REF);
-    r.sync();
-    QM_PFOR(r, i, 30) {
-      W[TW_DX + i] = x[i] - W[TW_REF + RF_X + i];
-      W[TW_DU + i] = u[i] - W[TW_REF + RF_U + i];
-    }
-    QM_PFOR(r, ft, 4) {
-      if ((mode >> (3 - ft)) & 1) cone_terms(P, u + 3 * ft, W + TW_CONE + 10 * ft);
-    }
-    QM_PFOR(r, i, 12) {
-      double v1, a1, b1, v2, a2, b2;
-      if (i < 6) {
-        relaxed_barrier(x[24 + i] - P.arm_pos_lo[i], P.pos_bar_mu, P.pos_bar_delta, &v1, &a1, &b1);
-        relaxed_barrier(P.arm_pos_hi[i] - x[24 + i], P.pos_bar_mu, P.pos_bar_delta, &v2, &a2, &b2);
-      } else {
-        relaxed_barrier(u[18 + i] - P.arm_vel_lo[i - 6], P.vel_bar_mu, P.vel_bar_delta, &v1, &a1, &b1);
-        relaxed_barrier(P.arm_vel_hi[i - 6] - u[18 + i], P.vel_bar_mu, P.vel_bar_delta, &v2, &a2, &b2);
-      }
-      W[TW_BOX + 2 * i] = a1 - a2;
-      W[TW_BOX + 2 * i + 1] = b1 + b2;
-      W[TW_BOXV + i] = v1 + v2;
-    }
-    r.sync();
+    const double* ref = io.aux + NA_REF;
+    const double* CONE = io.aux + NA_CONE;
+    const double* BOX = io.aux + NA_BOX;
     QM_PFOR(r, i, 60) {
       double acc = 0.0;
-      if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * W[TW_DX + j]; W[TW_TQ + i] = acc; }
-      else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * W[TW_DU + j]; W[TW_TR + ii] = acc; }
+      if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * (x[j] - ref[RF_X + j]); W[TW_TQ + i] = acc; }
+      else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * (u[j] - ref[RF_U + j]); W[TW_TR + ii] = acc; }
     }
     r.sync();
-    if (r.tid() == 0) {
-      // baseline performance of this node: cost value, equality-constraint SSE
-      double c0 = -P.box_offset;
-      for (int i = 0; i < 12; ++i) c0 += W[TW_BOXV + i];
-      for (int i = 0; i < 30; ++i) c0 += 0.5 * (W[TW_DX + i] * W[TW_TQ + i] + W[TW_DU + i] * W[TW_TR + i]);
-      const double* e = io.e6;
-      c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
-      double eq = io.e6[6];
-      double shift = 0.0;
-      for (int ft = 0; ft < 4; ++ft) {
-        if ((mode >> (3 - ft)) & 1) { shift += W[TW_CONE + 10 * ft + 8] * (-P.fric_hess_shift); c0 += W[TW_CONE + 10 * ft + 7]; }
-        else eq += u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
-      }
-      W[TW_SCAL + 0] = c0; W[TW_SCAL + 1] = eq; W[TW_SCAL + 2] = shift;
-    }
-    r.sync();
+    double shift = 0.0;
+    for (int ft = 0; ft < 4; ++ft) if ((mode >> (3 - ft)) & 1) shift += CONE[10 * ft + 8] * (-P.fric_hess_shift);
     const double* JE = io.je;
-    const double shift = W[TW_SCAL + 2];
+
     QM_PFOR(r, idx, 900) {
       const int i = idx / 30, j = idx % 30;
       double qv = P.Q[idx];
@@ -635,10 +627,10 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
       double rv = P.R[idx];
       if (i == j) {
         qv += shift; rv += shift;
-        if (i >= 24) { qv += W[TW_BOX + 2 * (i - 24) + 1]; rv += W[TW_BOX + 2 * (i - 18) + 1]; }
+        if (i >= 24) { qv += BOX[2 * (i - 24) + 1]; rv += BOX[2 * (i - 18) + 1]; }
       }
       if (i < 12 && j < 12 && (i / 3) == (j / 3) && ((mode >> (3 - i / 3)) & 1)) {
-        const double* c = W + TW_CONE + 10 * (i / 3);
+        const double* c = CONE + 10 * (i / 3);
         const int a = i % 3, b = j % 3;
         double H = 0.0;
         if (a == 0 && b == 0) H = c[4];
@@ -655,8 +647,8 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
         const double* e = io.e6;
         for (int rr = 0; rr < 6; ++rr) qv += (rr < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[rr * QM_NJ + i - 6] * e[rr];
       }
-      if (i >= 24) { qv += W[TW_BOX + 2 * (i - 24)]; rv += W[TW_BOX + 2 * (i - 18)]; }
-      if (i < 12 && ((mode >> (3 - i / 3)) & 1)) { const double* c = W + TW_CONE + 10 * (i / 3); rv += c[8] * c[1 + i % 3]; }
+      if (i >= 24) { qv += BOX[2 * (i - 24)]; rv += BOX[2 * (i - 18)]; }
+      if (i < 12 && ((mode >> (3 - i / 3)) & 1)) { const double* c = CONE + 10 * (i / 3); rv += c[8] * c[1 + i % 3]; }
       W[TW_QV + i] = dt * qv;
       W[TW_RV + i] = dt * rv;
     }
@@ -690,11 +682,22 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
     }
     r.sync();
     if (r.tid() == 0) {
+      // baseline performance of this node: cost value, dynamics defect and equality-constraint SSE
+      double c0 = -P.box_offset;
+      for (int i = 0; i < 12; ++i) c0 += io.aux[NA_BOXV + i];
+      for (int i = 0; i < 30; ++i) c0 += 0.5 * ((x[i] - ref[RF_X + i]) * W[TW_TQ + i] + (u[i] - ref[RF_U + i]) * W[TW_TR + i]);
+      const double* e = io.e6;
+      c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
+      double eq = io.e6[6];
+      for (int ft = 0; ft < 4; ++ft) {
+        if ((mode >> (3 - ft)) & 1) c0 += CONE[10 * ft + 7];
+        else eq += u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
+      }
       double dyn = 0.0;
       for (int i = 0; i < 30; ++i) dyn += W[TW_b + i] * W[TW_b + i];
-      perf[PF_COST] = dt * W[TW_SCAL + 0];
+      perf[PF_COST] = dt * c0;
       perf[PF_DYN] = dt * dyn;
-      perf[PF_EQ] = dt * W[TW_SCAL + 1];
+      perf[PF_EQ] = dt * eq;
     }
     // clear the projection matrices (in the fused layout PX aliases FR1/FR2, which are dead from here on)
     QM_PFOR(r, idx, 900) W[TW_PX + idx] = 0.0;
@@ -820,7 +823,7 @@ QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_proble
                             const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status_out) {
   NodeIO io;
   io.fr1 = W + TW_FR1; io.fr2 = W + TW_FR2; io.f1 = W + TW_F1; io.f2 = W + TW_F2; io.x2 = W + TW_X2;
-  io.T = W + TW_T; io.je = W + TW_JE; io.e6 = W + TW_E6;
+  io.T = W + TW_T; io.je = W + TW_JE; io.e6 = W + TW_E6; io.aux = W + TW_AUX;
   node_eval1(g, M, P, t, dt, mode, zvel, tt, ts, kt, x, u, W + TW_KIN, W + TW_REF, io);
   node_eval2(g, M, P, u, W + TW_KIN, io);
   node_lq(g, M, P, t, dt, mode, tt, ts, kt, x, u, xn, W, WI, io, sb, pb, perf, status_out);
