@@ -41,7 +41,7 @@ enum {
   QMB200_ST_STEP_REJECTED = 32
 };
 #define QMB200_INFO_SIZE 16   /* per-problem info record: alpha, done, armijo, |dx|, |du|, base(merit,dyn,eq), new(merit,dyn,eq), iters */
-#define QMB200_NUM_KERNELS 10 /* schedule, init_guess, kin1, kin2, lq, solve, trial, decide, finalize, policy */
+#define QMB200_NUM_KERNELS 11 /* schedule, init_guess, kin1, kin2, lq, solve, trial, decide, finalize, policy, proj */
 
 int qmb200_version(void);
 const char* qmb200_last_error(void);

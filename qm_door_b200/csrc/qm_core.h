@@ -73,6 +73,10 @@ struct BlockGroup {
 };
 #endif
 #define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())
+// two-level loop without index division: rows over the warps of the group, columns over the lanes
+#define QM_PFOR2(g, i, ni, c, nc)                                              \
+  for (int i = (g).tid() >> 5; i < (ni); i += ((g).nt() + 31) >> 5)            \
+    for (int c = (g).tid() & 31; c < (nc); c += ((g).nt() < 32 ? (g).nt() : 32))
 
 // several CTAs (nodes) of one problem may flag the same status word
 QM_HD void status_or(int* p, int v) {
@@ -80,6 +84,29 @@ QM_HD void status_or(int* p, int v) {
   atomicOr(p, v);
 #else
   *p |= v;
+#endif
+}
+
+// out(r, init(r) + sum_{j < len} term(r, j)) for r < nrows. Device: four lanes per row, partial sums combined with
+// shuffles (the group size is a multiple of 32); host: one loop.
+template <class G, class FI, class FT, class FO>
+QM_HDN void rows_dot(G g, int nrows, int len, FI init, FT term, FO out) {
+#if defined(__CUDA_ARCH__)
+  for (int base = 0; base < 4 * nrows; base += g.nt()) {
+    const int t = base + g.tid(), r = t >> 2, part = t & 3;
+    const bool valid = r < nrows;
+    double acc = 0.0;
+    if (valid) for (int j = part; j < len; j += 4) acc += term(r, j);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (valid && part == 0) out(r, init(r) + acc);
+  }
+#else
+  QM_PFOR(g, r, nrows) {
+    double acc = 0.0;
+    for (int j = 0; j < len; ++j) acc += term(r, j);
+    out(r, init(r) + acc);
+  }
 #endif
 }
 
@@ -113,18 +140,30 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #endif
 template <int TJ, bool xT, class G>
 QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double* Y, int ldy, const double* C0, int ld0,
-               double alpha, double* C, int ldc) {
+               double alpha, double* C, int ldc, int rot = 0) {
 #if defined(__CUDA_ARCH__)
   const int lane = threadIdx.x & 31;
   const int tm = (m + 7) >> 3, tn = (n + 7) >> 3;
   const int gj = (tn + TJ - 1) / TJ;
   const int r = lane >> 2, q = lane & 3;
-  for (int unit = g.warp(); unit < tm * gj; unit += g.nwarps()) {
-    const int i0 = (unit / gj) << 3, j0 = (unit % gj) * TJ * 8;
-    double acc[TJ][2];
-#pragma unroll
-    for (int t = 0; t < TJ; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+  // `rot` rotates the unit -> warp assignment so that products issued back to back spread over all warps
+  const int nw = g.nwarps();
+  int w0 = g.warp() - rot;
+  while (w0 < 0) w0 += nw;
+  for (int unit = w0; unit < tm * gj; unit += nw) {
+    int ti = 0, tj = unit;                                        // unit / gj, unit % gj without the division sequence (tm <= 4)
+    while (tj >= gj) { tj -= gj; ++ti; }
+    const int i0 = ti << 3, j0 = tj * TJ * 8;
+    double acc[TJ][2], c0v[TJ][2];
     const int i = i0 + r;
+    // the C0 operands are requested before the product loop so that their latency (HBM blocks) overlaps the tiles
+#pragma unroll
+    for (int t = 0; t < TJ; ++t) {
+      acc[t][0] = 0.0; acc[t][1] = 0.0;
+      const int j = j0 + 8 * t + 2 * q;
+      c0v[t][0] = (C0 && i < m && j < n) ? C0[i * ld0 + j] : 0.0;
+      c0v[t][1] = (C0 && i < m && j + 1 < n) ? C0[i * ld0 + j + 1] : 0.0;
+    }
     const bool iok = i < m;
     const double* xp = xT ? (X + i + q * ldx) : (X + i * ldx + q);     // advances by 4 rows (xT) / 4 columns per k-step
     const int xstep = xT ? 4 * ldx : 4;
@@ -144,8 +183,8 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
     for (int t = 0; t < TJ; ++t) {
       const int j = j0 + 8 * t + 2 * q;
       if (i < m && j0 + 8 * t < n) {
-        if (j < n) C[i * ldc + j] = (C0 ? C0[i * ld0 + j] : 0.0) + alpha * acc[t][0];
-        if (j + 1 < n) C[i * ldc + j + 1] = (C0 ? C0[i * ld0 + j + 1] : 0.0) + alpha * acc[t][1];
+        if (j < n) C[i * ldc + j] = c0v[t][0] + alpha * acc[t][0];
+        if (j + 1 < n) C[i * ldc + j + 1] = c0v[t][1] + alpha * acc[t][1];
       }
     }
   }

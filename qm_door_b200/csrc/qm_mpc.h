@@ -30,12 +30,20 @@ enum {
   SB_NUT = SB_r + QM_NUT,            // reduced input dimension of this node (as double)
   SB_SIZE = 3296
 };
+// Projection of one node, compact: only the nv rows of the eliminated (pivot) joint velocities are stored.
+//   du[12 + pivcol[p]] = PX[p] . dx + PU[p] . dut + PEC[p]      (p < nv)
+//   du[fcols[a]]       = dut[a]                                  (a < nut; stance-foot forces and free joint velocities)
+//   du[i]              = PEF[i]                                  (swing-foot force components: -u_i)
+// role[i] (int32, i < 30): p for a pivot row, 32 + a for a free input, 64 otherwise; then nv, nut.
 enum {
-  PB_PU = 0,                         // [30][18]
-  PB_PX = PB_PU + 30 * QM_NUT,       // [30][30]
-  PB_PE = PB_PX + 900,               // [30]
-  PB_SIZE = 1472
+  PB_PX = 0,                         // [16][30]
+  PB_PU = PB_PX + 16 * 30,           // [16][18]
+  PB_PEC = PB_PU + 16 * QM_NUT,      // [16]
+  PB_PEF = PB_PEC + 16,              // [12]
+  PB_ROLE = PB_PEF + 12,             // 32 x int32
+  PB_SIZE = PB_ROLE + 16
 };
+enum { ROLE_FREE = 32, ROLE_NONE = 64 };
 enum { GB_K = 0, GB_KFF = 30 * QM_NUT, GB_SIZE = 560 };   // K [18][30], kff [18]
 enum { PF_COST = 0, PF_DYN = 1, PF_EQ = 2, PF_SIZE = 4 };
 
@@ -394,73 +402,204 @@ QM_HD double barrier_cost(const qmb200_problem_desc& P, int mode, const double* 
 }
 
 // ------------------------------------------------------------------------------------------ transcription workspace
+enum { PI_PIV = 0, PI_STATUS = 16, PI_NUT = 17, PI_NV = 18, PI_SEL = 20, PI_POS = 50, PI_SIZE = 80 };   // int32 index record
 enum {
-  TW_KIN = 0,                       // kinematics workspace; later reused for RPX / RPU
-  TW_FR1 = TW_KIN + KW_SIZE,           // [9][60]
-  TW_FR2 = TW_FR1 + 540,            // [9][60]
-  TW_RPX = TW_KIN,                  // [30][30] alias (kinematics dead)
-  TW_RPU = TW_KIN + 900,            // [30][18] alias
-  TW_A = TW_FR2 + 540,              // [30][30]
-  TW_B = TW_A + 900,
-  TW_Q = TW_B + 900,
-  TW_R = TW_Q + 900,
-  TW_PX = TW_FR1,                   // [30][30] alias (FR1/FR2 dead once A, B are assembled)
-  TW_PU = TW_R + 900,               // [30][18]
-  TW_T = TW_PU + 540,               // [12][49] = [Dv | C | e]
-  TW_JE = TW_T + 588,               // [6][24]
+  TW_KIN = 0,                       // kinematics workspace (fused path) / staged kinematics products (split path)
+  TW_A = TW_KIN + KW_SIZE + 16,     // [30][30]
+  TW_BPM = TW_A + 900,              // [30][30] B with columns permuted [pivots | frees | dropped]
+  TW_RPM = TW_BPM + 900,            // [<=30][30] R with rows [pivots | frees] and columns permuted
+  TW_T2 = TW_RPM + 900,             // [16][49] = Dinv [Dv | C | e]: row p expresses joint velocity piv[p]
+  TW_PUC = TW_T2 + 784,             // [16][18] pivot rows of Pu (reduced-input columns)
+  TW_b = TW_PUC + 288,              // 30
+  TW_QV = TW_b + 30,                // q
+  TW_RV = TW_QV + 30,               // r
+  TW_PEP = TW_RV + 30,              // Pe in permuted order (30)
+  TW_TQ = TW_PEP + 30,              // Q dx
+  TW_TR = TW_TQ + 30,               // R du
+  TW_RP = TW_TR + 30,               // r' = r + R Pe, rows [pivots | frees]
+  TW_RED = TW_RP + 30,              // 4: reduction scratch
+  TW_LQ_SIZE = TW_RED + 4,          // what the split path (k_lq) needs: the rest lives in the staged kinematics products
+  // RPX [<=30][30] (rows [pivots; frees] of R Px) takes the place of the flow-map rows fr1 | fr2 once A, B are assembled,
+  // RPU [<=30][18] the place of the constraint rows T once T2 is formed.
+  TW_JE = TW_LQ_SIZE,               // [6][24]  (fused path / terminal node: k_lq's terminal CTA places these over BPM)
   TW_REF = TW_JE + 144,             // RF_SIZE (+ 10 scratch for the ee rotation map)
-  TW_F1 = TW_REF + RF_SIZE + 10,    // 30
+  TW_E6 = TW_REF + RF_SIZE + 10,    // 6 (+2 pad)
+  TW_DQ = TW_E6 + 8,                // 9 (+1)
+  TW_FR1 = TW_DQ + 10,              // [9][60]   (fused path only from here on)
+  TW_FR2 = TW_FR1 + 540,            // [9][60]
+  TW_F1 = TW_FR2 + 540,             // 30
   TW_F2 = TW_F1 + 30,
   TW_X2 = TW_F2 + 30,
-  TW_b = TW_X2 + 30,
-  TW_QV = TW_b + 30,                // q
-  TW_RV = TW_QV + 30,               // r -> r'
-  TW_PE = TW_RV + 30,
-  TW_DX = TW_PE + 30,               // x - x_ref
-  TW_DU = TW_DX + 30,
-  TW_TQ = TW_DU + 30,               // Q dx
-  TW_TR = TW_TQ + 30,               // R du
-  TW_E6 = TW_TR + 30,               // 6 (+2 pad)
-  TW_DQ = TW_E6 + 8,                // 9 (+1)
-  TW_CONE = TW_DQ + 10,             // [4][10]
-  TW_BOX = TW_CONE + 40,            // [12][2]: gradient, hessian of the arm boxes (6 position, 6 velocity)
-  TW_BOXV = TW_BOX + 24,            // [12] their values
-  TW_ROWBEST = TW_BOXV + 12,        // 12
-  TW_FAC = TW_ROWBEST + 12,         // 12
-  TW_SCAL = TW_FAC + 12,            // misc scalars
-  TW_AUX = TW_SCAL + 8,             // NA_SIZE: references / barrier terms of the node in the fused (host) path
-  TW_SIZE = TW_AUX + 144
+  TW_T = TW_X2 + 30,                // [16][49] = [Dv | C | e]
+  TW_AUX = TW_T + 784,              // NA_SIZE
+  TW_DINV = TW_AUX + 144,           // [16][16]
+  TW_PIV = TW_DINV + 256,           // PI_SIZE x int32
+  TW_SIZE = TW_PIV + PI_SIZE / 2
 };
-enum {                               // integer workspace
-  TI_ROWARG = 0,                    // 12
-  TI_PIVCOL = 12,                   // 12: joint-velocity column eliminated by row p
-  TI_FCOLS = 24,                    // 18: input index of reduced input a
-  TI_ISPIV = 42,                    // 18
-  TI_NV = 60, TI_NUT = 61, TI_PR = 62, TI_PC = 63, TI_STATUS = 64,
-  TI_SIZE = 68
-};
+enum { TI_SIZE = 4 };                // integer workspace (unused by the LQ assembly: the index record comes with the pivots)
 
 // Intermediate products of one node handed from the kinematics evaluations to the LQ assembly. In the fused (host)
-// path they live in the transcription workspace; in the split CUDA path k_kin writes them to HBM (KS_* layout) and
-// k_lq stages them into shared memory with one bulk copy.
+// path they live in the transcription workspace; in the split CUDA path k_kin / k_proj write them to HBM (KS_* layout)
+// and k_lq stages them into shared memory.
 struct NodeIO {
   double* fr1; double* fr2;   // [9][60] non-trivial rows of [df/dx | df/du] at (x,u) and (x + dt f1, u)
   double* f1;  double* f2;    // [30] flow map values
   double* x2;                 // [30] x + dt f1
-  double* T;                  // [12][49] velocity-constraint rows [Dv | C | e]
+  double* T;                  // [nv][49] velocity-constraint rows [Dv | C | e]
   double* je;                 // [6][24] end-effector error Jacobian
   double* e6;                 // [8] end-effector error (6), [6] = sum of squared velocity-constraint values
   double* aux;                // [NA_SIZE] references and barrier terms of the node (functions of t, x, u only)
+  double* dinv;               // [16][16] inverse of the pivot block of Dv (rows / columns in constraint-row order)
+  int* piv;                   // PI_* index record: pivots, status bits, nut, nv, permutation sel / pos of the inputs
 };
 // aux layout: reference (x_ref, u_nominal, ee pose), friction-cone terms per foot, arm box gradients / Hessians / values
 enum { NA_REF = 0, NA_CONE = RF_SIZE, NA_BOX = NA_CONE + 40, NA_BOXV = NA_BOX + 24, NA_SIZE = NA_BOXV + 12 };
-enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = 1758, KS_E6 = 1902, KS_AUX = 1910,
-       KS_SIZE = ((KS_AUX + NA_SIZE + 3) / 4) * 4 };
+enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = KS_T + 784, KS_E6 = KS_JE + 144,
+       KS_AUX = KS_E6 + 8, KS_DINV = ((KS_AUX + NA_SIZE + 3) / 4) * 4, KS_PIV = KS_DINV + 256, KS_SIZE = KS_PIV + PI_SIZE / 2 };
+static_assert((int)KS_SIZE <= (int)KW_SIZE + 16 && KS_SIZE % 2 == 0, "staged kinematics products must fit the kinematics region");
 QM_HD NodeIO node_io_at(double* base) {
   NodeIO io;
   io.fr1 = base + KS_FR1; io.fr2 = base + KS_FR2; io.f1 = base + KS_F1; io.f2 = base + KS_F2;
   io.x2 = base + KS_X2; io.T = base + KS_T; io.je = base + KS_JE; io.e6 = base + KS_E6; io.aux = base + KS_AUX;
+  io.dinv = base + KS_DINV; io.piv = (int*)(base + KS_PIV);
   return io;
+}
+
+QM_HD int velocity_rows(int mode) {      // velocity-constraint rows: 3 per stance foot, 1 per swing foot
+  int nv = 0;
+  for (int ft = 0; ft < 4; ++ft) nv += ((mode >> (3 - ft)) & 1) ? 3 : 1;
+  return nv;
+}
+
+// ------------------------------------------------------------------------------------------ constraint projection pivots
+// [upstream] luConstraintProjection on the joint-velocity block Dv [nv][18] of the velocity constraints: Gauss-Jordan
+// with full pivoting, carried out as an in-place inversion without row exchanges. Results: piv[p] = joint-velocity
+// column eliminated by constraint row p, Dinv = (Dv[:, piv])^-1 so that Dinv [Dv | C | e] has unit pivot columns.
+// Pivot choice: largest magnitude among unused rows / columns; ties -> smallest row, then smallest column.
+#if defined(__CUDACC__)
+template <int PR>
+__device__ __forceinline__ void gj_pivot_step(double (&a)[16], int nv, int pc, int lane) {
+  const double p = __shfl_sync(0xffffffffu, a[PR], pc);
+  const double ip = 1.0 / p;
+  const double arow = a[PR] * ip;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i != PR && i < nv) {                       // nv is warp-uniform
+      const double f = __shfl_sync(0xffffffffu, a[i], pc);
+      a[i] = (lane == pc) ? -f * ip : a[i] - f * arow;
+    }
+  }
+  a[PR] = (lane == pc) ? ip : arow;
+}
+// One warp; column c of Dv in the registers of lane c (rows = register index), multipliers broadcast with shuffles.
+__device__ __forceinline__ void projection_pivots_warp(const double* T, int mode, double* Dinv, int* piv) {
+  const int nv = velocity_rows(mode);
+  const int lane = threadIdx.x & 31;
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (lane < 18 && i < nv) ? T[49 * i + lane] : 0.0;
+  unsigned rows_used = 0;
+  bool col_used = false, bad = false;
+  int myrow = -1;
+  for (int s = 0; s < nv; ++s) {
+    double best = -1.0;
+    int arg = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nv && !((rows_used >> i) & 1u)) { const double v = fabs(a[i]); if (v > best) { best = v; arg = i; } }
+    if (lane >= 18 || col_used) best = -1.0;
+    int key = arg * 32 + lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int ok = __shfl_xor_sync(0xffffffffu, key, off);
+      if (ob > best || (ob == best && ok < key)) { best = ob; key = ok; }
+    }
+    const int pr = key >> 5, pc = key & 31;
+    if (!(best > 1e-12)) bad = true;
+    switch (pr) {
+      case 0: gj_pivot_step<0>(a, nv, pc, lane); break;    case 1: gj_pivot_step<1>(a, nv, pc, lane); break;
+      case 2: gj_pivot_step<2>(a, nv, pc, lane); break;    case 3: gj_pivot_step<3>(a, nv, pc, lane); break;
+      case 4: gj_pivot_step<4>(a, nv, pc, lane); break;    case 5: gj_pivot_step<5>(a, nv, pc, lane); break;
+      case 6: gj_pivot_step<6>(a, nv, pc, lane); break;    case 7: gj_pivot_step<7>(a, nv, pc, lane); break;
+      case 8: gj_pivot_step<8>(a, nv, pc, lane); break;    case 9: gj_pivot_step<9>(a, nv, pc, lane); break;
+      case 10: gj_pivot_step<10>(a, nv, pc, lane); break;  case 11: gj_pivot_step<11>(a, nv, pc, lane); break;
+      case 12: gj_pivot_step<12>(a, nv, pc, lane); break;  case 13: gj_pivot_step<13>(a, nv, pc, lane); break;
+      case 14: gj_pivot_step<14>(a, nv, pc, lane); break;  default: gj_pivot_step<15>(a, nv, pc, lane); break;
+    }
+    rows_used |= 1u << pr;
+    if (lane == pc) { col_used = true; myrow = pr; }
+  }
+  if (myrow >= 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if (i < nv) Dinv[16 * i + myrow] = a[i];
+    piv[PI_PIV + myrow] = lane;
+  }
+  // index record: inputs ordered [pivot joint velocities (row order) | free inputs: stance forces, free joint velocities | dropped]
+  const unsigned freemask = __ballot_sync(0xffffffffu, lane < 18 && !col_used);
+  const int nst = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
+  const int nut = 3 * nst + __popc(freemask);
+  if (lane < 18) {
+    const int c = col_used ? myrow : nv + 3 * nst + __popc(freemask & ((1u << lane) - 1u));
+    piv[PI_SEL + c] = 12 + lane; piv[PI_POS + 12 + lane] = c;
+  }
+  if (lane < 12) {
+    const int ft = lane / 3;
+    int before = 0;                                  // stance feet before this foot
+    for (int f2 = 0; f2 < ft; ++f2) before += (mode >> (3 - f2)) & 1;
+    const int c = ((mode >> (3 - ft)) & 1) ? nv + 3 * before + lane % 3 : nv + nut + 3 * (ft - before) + lane % 3;
+    piv[PI_SEL + c] = lane; piv[PI_POS + lane] = c;
+  }
+  if (lane == 0) { piv[PI_STATUS] = bad ? ST_RANK : 0; piv[PI_NUT] = nut; piv[PI_NV] = nv; }
+}
+#endif
+// Scalar statement of the same elimination (CPU port).
+QM_HDN void projection_pivots_serial(const double* T, int mode, double* Dinv, int* piv) {
+  const int nv = velocity_rows(mode);
+  double a[16][18];
+  for (int i = 0; i < 16; ++i) for (int c = 0; c < 18; ++c) a[i][c] = (i < nv) ? T[49 * i + c] : 0.0;
+  unsigned rows_used = 0, cols_used = 0;
+  int rowof[18];
+  for (int c = 0; c < 18; ++c) rowof[c] = -1;
+  bool bad = false;
+  for (int s = 0; s < nv; ++s) {
+    double best = -1.0; int pr = 0, pc = 0;
+    for (int i = 0; i < nv; ++i) {
+      if ((rows_used >> i) & 1u) continue;
+      for (int c = 0; c < 18; ++c) {
+        if ((cols_used >> c) & 1u) continue;
+        const double v = fabs(a[i][c]);
+        if (v > best) { best = v; pr = i; pc = c; }
+      }
+    }
+    if (!(best > 1e-12)) bad = true;
+    const double ip = 1.0 / a[pr][pc];
+    double arow[18];
+    for (int c = 0; c < 18; ++c) arow[c] = a[pr][c] * ip;
+    for (int i = 0; i < nv; ++i) {
+      if (i == pr) continue;
+      const double f = a[i][pc];
+      for (int c = 0; c < 18; ++c) a[i][c] = (c == pc) ? -f * ip : a[i][c] - f * arow[c];
+    }
+    for (int c = 0; c < 18; ++c) a[pr][c] = (c == pc) ? ip : arow[c];
+    rows_used |= 1u << pr; cols_used |= 1u << pc;
+    rowof[pc] = pr;
+  }
+  for (int c = 0; c < 18; ++c)
+    if (rowof[c] >= 0) {
+      for (int i = 0; i < nv; ++i) Dinv[16 * i + rowof[c]] = a[i][c];
+      piv[PI_PIV + rowof[c]] = c;
+    }
+  int pos = nv;
+  for (int p = 0; p < nv; ++p) piv[PI_SEL + p] = 12 + piv[PI_PIV + p];
+  for (int ft = 0; ft < 4; ++ft)
+    if ((mode >> (3 - ft)) & 1) for (int d = 0; d < 3; ++d) piv[PI_SEL + pos++] = 3 * ft + d;
+  for (int c = 0; c < 18; ++c) if (rowof[c] < 0) piv[PI_SEL + pos++] = 12 + c;
+  const int nut = pos - nv;
+  for (int ft = 0; ft < 4; ++ft)
+    if (!((mode >> (3 - ft)) & 1)) for (int d = 0; d < 3; ++d) piv[PI_SEL + pos++] = 3 * ft + d;
+  for (int c = 0; c < 30; ++c) piv[PI_POS + piv[PI_SEL + c]] = c;
+  piv[PI_STATUS] = bad ? ST_RANK : 0; piv[PI_NUT] = nut; piv[PI_NV] = nv;
 }
 
 // Kinematics at (x,u) with derivatives: flow map rows, end-effector terms, constraint rows (QMInterface.cpp:116-131), x2.
@@ -543,80 +682,43 @@ QM_HDN void node_eval2(G g, const qmb200_model_desc& M, const qmb200_problem_des
 
 // LQ assembly of one intermediate node from the kinematics products: cost quadratic approximation, discrete dynamics,
 // constraint projection, change of input variables; results to the HBM blocks sb / pb and perf[PF_*].
+// The change of variables du = Pu dut + Px dx + Pe ([upstream] changeOfInputVariables) only involves the nv pivot rows
+// of Px / Pu, so every product is a [.. x nv] x [nv x ..] tile product (mm: FP64 tensor-core tiles on the device).
+// B and R are assembled directly with their input index permuted to [pivots | frees | dropped] (index record io.piv),
+// Q directly in its HBM block, where the tile product then adds the projection term.
 template <class G>
 QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
                     const double* tt, const double* ts, int kt, const double* x, const double* u, const double* xn,
                     double* W, int* WI, NodeIO io, double* sb, double* pb, double* perf, int* status_out) {
   const double m = M.total_mass;
-  int nvc = 0;
-  for (int ft = 0; ft < 4; ++ft) nvc += ((mode >> (3 - ft)) & 1) ? 3 : 1;
-  const int nv = nvc;
-  double* T = io.T;
-  // ---- L1 narrow: projection by Gauss-Jordan with full pivoting on Dv ([upstream] luConstraintProjection)
-  if (g.narrow_active()) {
-    auto w0 = g.narrow();
-    if (w0.tid() == 0) WI[TI_STATUS] = 0;
-    for (int step = 0; step < nv; ++step) {
-      QM_PFOR(w0, r, nv) {
-        double best = -1.0; int arg = 0;
-        if (r >= step) {
-          for (int c = 0; c < 18; ++c) { const double a = fabs(T[49 * r + c]); if (a > best) { best = a; arg = c; } }
-        }
-        W[TW_ROWBEST + r] = best; WI[TI_ROWARG + r] = arg;
-      }
-      w0.sync();
-      if (w0.tid() == 0) {
-        int pr = step; double best = W[TW_ROWBEST + step];
-        for (int r = step + 1; r < nv; ++r) if (W[TW_ROWBEST + r] > best) { best = W[TW_ROWBEST + r]; pr = r; }
-        WI[TI_PR] = pr; WI[TI_PC] = WI[TI_ROWARG + pr]; WI[TI_PIVCOL + step] = WI[TI_ROWARG + pr];
-        if (!(best > 1e-12)) WI[TI_STATUS] |= ST_RANK;
-      }
-      w0.sync();
-      const int pr = WI[TI_PR], pc = WI[TI_PC];
-      if (pr != step) {
-        QM_PFOR(w0, c, 49) { const double a = T[49 * step + c]; T[49 * step + c] = T[49 * pr + c]; T[49 * pr + c] = a; }
-        w0.sync();
-      }
-      QM_PFOR(w0, r, nv) W[TW_FAC + r] = T[49 * r + pc];
-      w0.sync();
-      const double ipiv = 1.0 / W[TW_FAC + step];
-      QM_PFOR(w0, idx, nv * 49) {
-        const int r = idx / 49, c = idx % 49;
-        if (r != step) T[idx] -= W[TW_FAC + r] * ipiv * T[49 * step + c];
-      }
-      w0.sync();
-      QM_PFOR(w0, c, 49) T[49 * step + c] *= ipiv;
-      w0.sync();
-    }
-    if (w0.tid() == 0) {
-      for (int l = 0; l < 18; ++l) WI[TI_ISPIV + l] = 0;
-      for (int p = 0; p < nv; ++p) WI[TI_ISPIV + WI[TI_PIVCOL + p]] = 1;
-      int a = 0;
-      for (int ft = 0; ft < 4; ++ft)
-        if ((mode >> (3 - ft)) & 1) { WI[TI_FCOLS + a] = 3 * ft; WI[TI_FCOLS + a + 1] = 3 * ft + 1; WI[TI_FCOLS + a + 2] = 3 * ft + 2; a += 3; }
-      for (int l = 0; l < 18; ++l) if (!WI[TI_ISPIV + l]) WI[TI_FCOLS + a++] = 12 + l;
-      WI[TI_NUT] = a;
-      WI[TI_NV] = nv;
-    }
-  }
-  // ---- L1 rest: cost quadratic approximation (forward Euler, * dt), discrete dynamics. References and barrier terms
-  //      come with the kinematics products (io.aux), so no serial work sits in front of the wide assembly.
-  if (g.rest_active()) {
-    auto r = g.rest();
-    const double* ref = io.aux + NA_REF;
-    const double* CONE = io.aux + NA_CONE;
-    const double* BOX = io.aux + NA_BOX;
-    QM_PFOR(r, i, 60) {
-      double acc = 0.0;
-      if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * (x[j] - ref[RF_X + j]); W[TW_TQ + i] = acc; }
-      else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * (u[j] - ref[RF_U + j]); W[TW_TR + ii] = acc; }
-    }
-    r.sync();
+  const int nv = io.piv[PI_NV], nut = io.piv[PI_NUT], nsel = nv + nut;
+  const int* SEL = io.piv + PI_SEL;
+  const int* POS = io.piv + PI_POS;
+  const double* T = io.T;
+  const double* ref = io.aux + NA_REF;
+  const double* CONE = io.aux + NA_CONE;
+  const double* BOX = io.aux + NA_BOX;
+  double* T2 = W + TW_T2;
+  double* BPM = W + TW_BPM;
+  double* RPM = W + TW_RPM;
+  double* RPX = io.fr1;                                          // valid from L3 on (fr1 | fr2 are dead then)
+  double* RPU = io.T;                                            // valid from L3 on (T is dead once T2 is formed)
+  // ---- L1: T2 = Dinv T; Q dx, R du
+  mm<1, false>(g, nv, 49, nv, io.dinv, 16, T, 49, (const double*)nullptr, 0, 1.0, T2, 49);
+  rows_dot(g, 60, 30, [](int) { return 0.0; },
+           [&](int i, int j) {
+             const double* wrow = P.Q + 30 * i;                   // P.R follows P.Q in the descriptor
+             const double* xv = (i < 30) ? x : u;
+             return wrow[j] * (xv[j] - ref[(i < 30 ? RF_X : RF_U) + j]);
+           },
+           [&](int i, double v) { W[TW_TQ + i] = v; });           // TW_TR follows TW_TQ
+  g.sync();
+  // ---- L2: cost quadratic approximation (forward Euler, * dt), discrete dynamics (Heun sensitivities), projection block
+  {
     double shift = 0.0;
     for (int ft = 0; ft < 4; ++ft) if ((mode >> (3 - ft)) & 1) shift += CONE[10 * ft + 8] * (-P.fric_hess_shift);
     const double* JE = io.je;
-
-    QM_PFOR(r, idx, 900) {
+    QM_PFOR(g, idx, 900) {
       const int i = idx / 30, j = idx % 30;
       double qv = P.Q[idx];
       if (i >= 6 && j >= 6) {
@@ -638,10 +740,11 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
         else if (a + b == 1) H = c[5];
         rv += c[9] * c[1 + a] * c[1 + b] + c[8] * H;
       }
-      W[TW_Q + idx] = dt * qv;
-      W[TW_R + idx] = dt * rv;
+      sb[SB_Q + idx] = dt * qv;
+      const int pi = POS[i];
+      if (pi < nsel) RPM[30 * pi + POS[j]] = dt * rv;
     }
-    QM_PFOR(r, i, 30) {
+    QM_PFOR(g, i, 30) {
       double qv = W[TW_TQ + i], rv = W[TW_TR + i];
       if (i >= 6) {
         const double* e = io.e6;
@@ -652,188 +755,147 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
       W[TW_QV + i] = dt * qv;
       W[TW_RV + i] = dt * rv;
     }
-    {
-      const double* F1 = io.fr1;
-      const double* F2 = io.fr2;
-      const double hdt = 0.5 * dt;
-      QM_PFOR(r, idx, 900) {
-        const int i = idx / 30, j = idx % 30;
-        double av = (i == j) ? 1.0 : 0.0, bv = 0.0;
-        if (i >= 3 && i < 12) {
-          const int rr = i - 3;
-          double pa = 0.0, pb2 = 0.0;
-          for (int s2 = 0; s2 < 9; ++s2) {
-            pa += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + j];
-            pb2 += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + 30 + j];
-          }
-          if (j < 12) pb2 += F2[rr * 60 + (j % 3)] / m;
-          else pb2 += F2[rr * 60 + j];
-          av += hdt * (F1[rr * 60 + j] + F2[rr * 60 + j] + dt * pa);
-          bv = hdt * (F1[rr * 60 + 30 + j] + F2[rr * 60 + 30 + j] + dt * pb2);
-        } else if (i < 3) {
-          bv = (j < 12 && (j % 3) == i) ? dt / m : 0.0;
-        } else {
-          bv = (j == i) ? dt : 0.0;
+    const double* F1 = io.fr1;
+    const double* F2 = io.fr2;
+    const double hdt = 0.5 * dt;
+    QM_PFOR(g, idx, 900) {
+      const int i = idx / 30, j = idx % 30;
+      double av = (i == j) ? 1.0 : 0.0, bv = 0.0;
+      if (i >= 3 && i < 12) {
+        const int rr = i - 3;
+        double pa = 0.0, pb2 = 0.0;
+        for (int s2 = 0; s2 < 9; ++s2) {
+          pa += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + j];
+          pb2 += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + 30 + j];
         }
-        W[TW_A + idx] = av;
-        W[TW_B + idx] = bv;
+        if (j < 12) pb2 += F2[rr * 60 + (j % 3)] / m;
+        else pb2 += F2[rr * 60 + j];
+        av += hdt * (F1[rr * 60 + j] + F2[rr * 60 + j] + dt * pa);
+        bv = hdt * (F1[rr * 60 + 30 + j] + F2[rr * 60 + 30 + j] + dt * pb2);
+      } else if (i < 3) {
+        bv = (j < 12 && (j % 3) == i) ? dt / m : 0.0;
+      } else {
+        bv = (j == i) ? dt : 0.0;
       }
-      QM_PFOR(r, i, 30) W[TW_b + i] = x[i] + hdt * (io.f1[i] + io.f2[i]) - xn[i];
+      W[TW_A + idx] = av;
+      BPM[30 * i + POS[j]] = bv;
     }
-    r.sync();
-    if (r.tid() == 0) {
-      // baseline performance of this node: cost value, dynamics defect and equality-constraint SSE
-      double c0 = -P.box_offset;
+    QM_PFOR(g, i, 30) W[TW_b + i] = x[i] + hdt * (io.f1[i] + io.f2[i]) - xn[i];
+    // Pe (permuted): pivot joint velocities from the velocity-constraint rows, frees 0, dropped swing-foot forces -u
+    QM_PFOR(g, c, 30) W[TW_PEP + c] = (c < nv) ? -T2[49 * c + 48] : ((c < nsel) ? 0.0 : -u[SEL[c]]);
+    QM_PFOR2(g, p, nv, a, QM_NUT) {
+      double v = 0.0;
+      if (a < nut) { const int fc = SEL[nv + a]; if (fc >= 12) v = -T2[49 * p + fc - 12]; }
+      W[TW_PUC + QM_NUT * p + a] = v;
+      pb[PB_PU + QM_NUT * p + a] = v;
+    }
+    QM_PFOR2(g, p, nv, j, 30) pb[PB_PX + 30 * p + j] = -T2[49 * p + 18 + j];     // rows >= nv are never read (role)
+    QM_PFOR(g, p, nv) pb[PB_PEC + p] = -T2[49 * p + 48];
+    QM_PFOR(g, i, 12) pb[PB_PEF + i] = ((mode >> (3 - i / 3)) & 1) ? 0.0 : -u[i];
+    int* role = (int*)(pb + PB_ROLE);
+    QM_PFOR(g, i, 32) {
+      int v;
+      if (i == 30) v = nv;
+      else if (i == 31) v = nut;
+      else { const int c = POS[i]; v = (c < nv) ? c : ((c < nsel) ? ROLE_FREE + c - nv : ROLE_NONE); }
+      role[i] = v;
+    }
+  }
+  g.sync();
+  // ---- L3: r' = r + R Pe, b~ = b + B Pe; baseline performance; A~ = A + B Px, B~ = B Pu, rows [pivots; frees] of R Px, R Pu
+  rows_dot(g, nsel + 30, 30, [&](int i) { return (i < nsel) ? W[TW_RV + SEL[i]] : W[TW_b + i - nsel]; },
+           [&](int i, int c) { return ((i < nsel) ? RPM[30 * i + c] : BPM[30 * (i - nsel) + c]) * W[TW_PEP + c]; },
+           [&](int i, double v) { if (i < nsel) W[TW_RP + i] = v; else sb[SB_b + i - nsel] = v; });
+  {
+    // baseline performance of this node: cost value, dynamics defect and equality-constraint SSE
+    const double* e = io.e6;
+#if defined(__CUDA_ARCH__)
+    if (g.warp() == g.nwarps() - 1) {
+      const int lane = threadIdx.x & 31;
+      double c0 = 0.0, dyn = 0.0;
+      if (lane < 30) {
+        c0 = 0.5 * ((x[lane] - ref[RF_X + lane]) * W[TW_TQ + lane] + (u[lane] - ref[RF_U + lane]) * W[TW_TR + lane]);
+        dyn = W[TW_b + lane] * W[TW_b + lane];
+        if (lane < 12) c0 += io.aux[NA_BOXV + lane];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, off); dyn += __shfl_xor_sync(0xffffffffu, dyn, off); }
+      if (lane == 0) { W[TW_RED] = c0; W[TW_RED + 1] = dyn; }
+      __syncwarp();
+    }
+    if (g.tid() == g.nt() - 1) {
+      double c0 = W[TW_RED] - P.box_offset, dyn = W[TW_RED + 1];
+#else
+    {
+      double c0 = -P.box_offset, dyn = 0.0;
       for (int i = 0; i < 12; ++i) c0 += io.aux[NA_BOXV + i];
       for (int i = 0; i < 30; ++i) c0 += 0.5 * ((x[i] - ref[RF_X + i]) * W[TW_TQ + i] + (u[i] - ref[RF_U + i]) * W[TW_TR + i]);
-      const double* e = io.e6;
+      for (int i = 0; i < 30; ++i) dyn += W[TW_b + i] * W[TW_b + i];
+#endif
       c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
       double eq = io.e6[6];
       for (int ft = 0; ft < 4; ++ft) {
         if ((mode >> (3 - ft)) & 1) c0 += CONE[10 * ft + 7];
         else eq += u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
       }
-      double dyn = 0.0;
-      for (int i = 0; i < 30; ++i) dyn += W[TW_b + i] * W[TW_b + i];
       perf[PF_COST] = dt * c0;
       perf[PF_DYN] = dt * dyn;
       perf[PF_EQ] = dt * eq;
     }
-    // clear the projection matrices (in the fused layout PX aliases FR1/FR2, which are dead from here on)
-    QM_PFOR(r, idx, 900) W[TW_PX + idx] = 0.0;
-    QM_PFOR(r, idx, 540) W[TW_PU + idx] = 0.0;
-    QM_PFOR(r, i, 30) W[TW_PE + i] = (i < 12 && !((mode >> (3 - i / 3)) & 1)) ? -u[i] : 0.0;
+  }
+  const double* PXn = T2 + 18;                                   // -Px pivot rows, leading dimension 49
+  mm<2, false>(g, 30, 30, nv, BPM, 30, PXn, 49, W + TW_A, 30, -1.0, sb + SB_A, 30, 0);
+  mm<2, false>(g, nsel, 30, nv, RPM, 30, PXn, 49, (const double*)nullptr, 0, -1.0, RPX, 30, 8);
+  if (nut > 0) {
+    mm<3, false>(g, 30, nut, nv, BPM, 30, W + TW_PUC, QM_NUT, BPM + nv, 30, 1.0, sb + SB_B, QM_NUT, 16);
+    mm<3, false>(g, nsel, nut, nv, RPM, 30, W + TW_PUC, QM_NUT, RPM + nv, 30, 1.0, RPU, QM_NUT, 20);
   }
   g.sync();
-  const int nut = WI[TI_NUT];
-  QM_PFOR(g, idx, nv * 49) {
-    const int p = idx / 49, c = idx % 49;
-    const int ip = 12 + WI[TI_PIVCOL + p];
-    if (c >= 18 && c < 48) W[TW_PX + 30 * ip + c - 18] = -T[idx];
-    else if (c == 48) W[TW_PE + ip] = -T[idx];
-  }
-  QM_PFOR(g, idx, nv * QM_NUT) {
-    const int p = idx / QM_NUT, a = idx % QM_NUT;
-    if (a < nut) {
-      const int fc = WI[TI_FCOLS + a];
-      if (fc >= 12) W[TW_PU + QM_NUT * (12 + WI[TI_PIVCOL + p]) + a] = -T[49 * p + fc - 12];
-    }
-  }
-  g.sync();
-  QM_PFOR(g, a, nut) W[TW_PU + QM_NUT * WI[TI_FCOLS + a] + a] = 1.0;
-  // r' = r + R Pe ;  b~ = b + B Pe
-  QM_PFOR(g, i, 60) {
-    double acc = 0.0;
-    if (i < 30) { for (int j = 0; j < 30; ++j) acc += W[TW_R + 30 * i + j] * W[TW_PE + j]; W[TW_TR + i] = W[TW_RV + i] + acc; }
-    else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += W[TW_B + 30 * ii + j] * W[TW_PE + j]; sb[SB_b + ii] = W[TW_b + ii] + acc; }
-  }
-  g.sync();
-  // ---- change of input variables  du = Pu dut + Px dx + Pe   ([upstream] changeOfInputVariables), sparse in the pivot rows
-  QM_PFOR(g, idx, 900) {
-    const int i = idx / 30, j = idx % 30;
-    double a = W[TW_A + idx], rp = 0.0;
-    for (int p = 0; p < nv; ++p) {
-      const int ip = 12 + WI[TI_PIVCOL + p];
-      const double px = W[TW_PX + 30 * ip + j];
-      a += W[TW_B + 30 * i + ip] * px;
-      rp += W[TW_R + 30 * i + ip] * px;
-    }
-    sb[SB_A + idx] = a;
-    W[TW_RPX + idx] = rp;
-    pb[PB_PX + idx] = W[TW_PX + idx];
-  }
-  QM_PFOR(g, idx, 30 * QM_NUT) {
-    const int i = idx / QM_NUT, a = idx % QM_NUT;
-    double bv = 0.0, rv = 0.0;
-    if (a < nut) {
-      const int fc = WI[TI_FCOLS + a];
-      bv = W[TW_B + 30 * i + fc];
-      rv = W[TW_R + 30 * i + fc];
-      if (fc >= 12)
-        for (int p = 0; p < nv; ++p) {
-          const int ip = 12 + WI[TI_PIVCOL + p];
-          const double pu = W[TW_PU + QM_NUT * ip + a];
-          bv += W[TW_B + 30 * i + ip] * pu;
-          rv += W[TW_R + 30 * i + ip] * pu;
-        }
-    }
-    sb[SB_B + idx] = bv;
-    W[TW_RPU + idx] = rv;
-    pb[PB_PU + idx] = W[TW_PU + idx];
-  }
-  QM_PFOR(g, i, 30) pb[PB_PE + i] = W[TW_PE + i];
-  g.sync();
-  QM_PFOR(g, idx, 900) {
-    const int i = idx / 30, j = idx % 30;
-    double qv = W[TW_Q + idx];
-    for (int p = 0; p < nv; ++p) {
-      const int ip = 12 + WI[TI_PIVCOL + p];
-      qv += W[TW_PX + 30 * ip + i] * W[TW_RPX + 30 * ip + j];
-    }
-    sb[SB_Q + idx] = qv;
-  }
-  QM_PFOR(g, idx, QM_NUT * 30) {
-    const int a = idx / 30, j = idx % 30;
-    double pv = 0.0;
-    if (a < nut) {
-      const int fc = WI[TI_FCOLS + a];
-      pv = W[TW_RPX + 30 * fc + j];
-      if (fc >= 12)
-        for (int p = 0; p < nv; ++p) { const int ip = 12 + WI[TI_PIVCOL + p]; pv += W[TW_PU + QM_NUT * ip + a] * W[TW_RPX + 30 * ip + j]; }
-    }
-    sb[SB_P + idx] = pv;
-  }
-  QM_PFOR(g, idx, QM_NUT * QM_NUT) {
-    const int a = idx / QM_NUT, b = idx % QM_NUT;
-    double rv = 0.0;
-    if (a < nut && b < nut) {
-      const int fc = WI[TI_FCOLS + a];
-      rv = W[TW_RPU + QM_NUT * fc + b];
-      if (fc >= 12)
-        for (int p = 0; p < nv; ++p) { const int ip = 12 + WI[TI_PIVCOL + p]; rv += W[TW_PU + QM_NUT * ip + a] * W[TW_RPU + QM_NUT * ip + b]; }
-    }
-    sb[SB_R + idx] = rv;
+  // ---- L4: Q~ = Q + Px' R Px, P~ = Pu' R Px, R~ = Pu' R Pu, q~ = q + Px' r', r~ = Pu' r'
+  mm<2, true>(g, 30, 30, nv, PXn, 49, RPX, 30, sb + SB_Q, 30, -1.0, sb + SB_Q, 30, 0);
+  if (nut > 0) {
+    mm<2, true>(g, nut, 30, nv, W + TW_PUC, QM_NUT, RPX, 30, RPX + 30 * nv, 30, 1.0, sb + SB_P, 30, 8);
+    mm<3, true>(g, nut, nut, nv, W + TW_PUC, QM_NUT, RPU, QM_NUT, RPU + QM_NUT * nv, QM_NUT, 1.0, sb + SB_R, QM_NUT, 14);
   }
   QM_PFOR(g, j, 30) {
     double qv = W[TW_QV + j];
-    for (int p = 0; p < nv; ++p) { const int ip = 12 + WI[TI_PIVCOL + p]; qv += W[TW_PX + 30 * ip + j] * W[TW_TR + ip]; }
+    for (int p = 0; p < nv; ++p) qv -= PXn[49 * p + j] * W[TW_RP + p];
     sb[SB_q + j] = qv;
   }
-  QM_PFOR(g, a, QM_NUT) {
-    double rv = 0.0;
-    if (a < nut) {
-      const int fc = WI[TI_FCOLS + a];
-      rv = W[TW_TR + fc];
-      if (fc >= 12)
-        for (int p = 0; p < nv; ++p) { const int ip = 12 + WI[TI_PIVCOL + p]; rv += W[TW_PU + QM_NUT * ip + a] * W[TW_TR + ip]; }
-    }
+  QM_PFOR(g, a, nut) {
+    double rv = W[TW_RP + nv + a];
+    for (int p = 0; p < nv; ++p) rv += W[TW_PUC + QM_NUT * p + a] * W[TW_RP + p];
     sb[SB_r + a] = rv;
   }
   if (g.tid() == 0) {
     sb[SB_NUT] = (double)nut;
-    if (WI[TI_STATUS]) status_or(status_out, WI[TI_STATUS]);
+    if (io.piv[PI_STATUS]) status_or(status_out, io.piv[PI_STATUS]);
   }
   g.sync();
 }
 
-// Fused form (host port / tests): both kinematics evaluations and the LQ assembly on one workspace.
+// Fused form (host port / tests): both kinematics evaluations, the projection pivots and the LQ assembly on one workspace.
 template <class G>
 QM_HDN void transcribe_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
                             const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
                             const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status_out) {
   NodeIO io;
   io.fr1 = W + TW_FR1; io.fr2 = W + TW_FR2; io.f1 = W + TW_F1; io.f2 = W + TW_F2; io.x2 = W + TW_X2;
-  io.T = W + TW_T; io.je = W + TW_JE; io.e6 = W + TW_E6; io.aux = W + TW_AUX;
+  io.T = W + TW_T; io.je = W + TW_JE; io.e6 = W + TW_E6; io.aux = W + TW_AUX; io.dinv = W + TW_DINV; io.piv = (int*)(W + TW_PIV);
   node_eval1(g, M, P, t, dt, mode, zvel, tt, ts, kt, x, u, W + TW_KIN, W + TW_REF, io);
   node_eval2(g, M, P, u, W + TW_KIN, io);
+  if (g.tid() == 0) projection_pivots_serial(io.T, mode, io.dinv, io.piv);
+  g.sync();
   node_lq(g, M, P, t, dt, mode, tt, ts, kt, x, u, xn, W, WI, io, sb, pb, perf, status_out);
 }
 
 // Pre-event node: identity jump map, no input, no cost ([upstream] setupEventNode).
 template <class G>
 QM_HDN void event_node(G g, const double* x, const double* xn, double* sb, double* pb, double* perf) {
-  QM_PFOR(g, idx, 900) { sb[SB_A + idx] = (idx / 30 == idx % 30) ? 1.0 : 0.0; sb[SB_Q + idx] = 0.0; pb[PB_PX + idx] = 0.0; }
-  QM_PFOR(g, i, 30) { sb[SB_b + i] = x[i] - xn[i]; sb[SB_q + i] = 0.0; pb[PB_PE + i] = 0.0; }
+  QM_PFOR(g, idx, 900) { sb[SB_A + idx] = (idx / 30 == idx % 30) ? 1.0 : 0.0; sb[SB_Q + idx] = 0.0; }
+  QM_PFOR(g, i, 30) { sb[SB_b + i] = x[i] - xn[i]; sb[SB_q + i] = 0.0; }
+  QM_PFOR(g, i, 12) pb[PB_PEF + i] = 0.0;
+  { int* role = (int*)(pb + PB_ROLE); QM_PFOR(g, i, 32) role[i] = (i < 30) ? ROLE_NONE : 0; }
   if (g.tid() == 0) {
     sb[SB_NUT] = 0.0;
     double d = 0.0;
@@ -1122,7 +1184,7 @@ QM_HDN void riccati_stage_b(G g, int nut, double* W, double* gb) {
   g.sync();
 }
 
-// One forward stage: dut = K dx + kff; du = Pu dut + Px dx + Pe; dx+ = A dx + B dut + b; armijo += q.dx + r.dut
+// One forward stage: dut = K dx + kff; du from the compact projection block; dx+ = A dx + B dut + b; armijo += q.dx + r.dut
 // W: [0:30] dx, [30:60] dx next, [60:78] dut, [80] armijo accumulator
 template <class G>
 QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double* gb, double* W, double* du_out) {
@@ -1134,11 +1196,17 @@ QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double*
     dut[a] = acc;
   }
   g.sync();
+  const int* role = (const int*)(pb + PB_ROLE);
   QM_PFOR(g, i, 60) {
     if (i < 30) {
-      double acc = pb[PB_PE + i];
-      for (int j = 0; j < 30; ++j) acc += pb[PB_PX + 30 * i + j] * dx[j];
-      for (int a = 0; a < nut; ++a) acc += pb[PB_PU + QM_NUT * i + a] * dut[a];
+      const int rl = role[i];
+      double acc;
+      if (rl < ROLE_FREE) {
+        acc = pb[PB_PEC + rl];
+        for (int j = 0; j < 30; ++j) acc += pb[PB_PX + 30 * rl + j] * dx[j];
+        for (int a = 0; a < nut; ++a) acc += pb[PB_PU + QM_NUT * rl + a] * dut[a];
+      } else if (rl < ROLE_NONE) acc = dut[rl - ROLE_FREE];
+      else acc = (i < 12) ? pb[PB_PEF + i] : 0.0;
       du_out[i] = (nut > 0) ? acc : 0.0;
     } else {
       const int ii = i - 30;

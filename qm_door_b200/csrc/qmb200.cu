@@ -5,6 +5,7 @@
 //   k_init_guess <<<B, 64>>>                 thread per state/input component: warm start interpolation
 //   k_kin<1>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x,u), constraint rows, ee terms -> kin scratch
 //   k_kin<2>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
+//   k_proj       <<<(NMAX/4, B), 128>>>      warp per node, side stream beside k_kin<2>: projection pivots (register Gauss-Jordan)
 //   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
 //   k_trial      <<<(NMAX/2, B), 64>>>       warp per node: value-only evaluation of the trial step (small value-level workspace)
@@ -29,9 +30,9 @@ static int fail(const std::string& msg) { qmb200_set_error_(msg.c_str()); return
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
-enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY };
-static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_kin1",     "k_kin2",    "k_lq",
-                                                       "k_solve",    "k_trial",      "k_decide",   "k_finalize", "k_policy"};
+enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY, KN_PROJ };
+static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_kin1",   "k_kin2",     "k_lq",    "k_solve",
+                                                       "k_trial",    "k_decide",     "k_finalize", "k_policy", "k_proj"};
 
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
@@ -88,24 +89,46 @@ __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb2
   }
 }
 
-constexpr int kLqSmemDoubles = TW_SIZE + 96;
+// ---- projection pivots: warp per node, register-resident Gauss-Jordan with full pivoting (runs beside k_kin<2>)
+constexpr int kProjWarps = 4;
+__global__ void __launch_bounds__(32 * kProjWarps) k_proj(MpcBuffers m) {
+  const int k = blockIdx.x * kProjWarps + (threadIdx.x >> 5), b = blockIdx.y;
+  if (k >= m.nn[b] - 1) return;
+  const size_t o = (size_t)b * m.NMAX + k;
+  if (m.node_flag[o] == EV_PRE) return;
+  double* base = m.kin + o * KS_SIZE;
+  projection_pivots_warp(base + KS_T, m.node_mode[o], base + KS_DINV, (int*)(base + KS_PIV));
+}
+
+constexpr int kLqSmemDoubles = TW_LQ_SIZE + 96;
 constexpr size_t kLqSmemBytes = kLqSmemDoubles * sizeof(double) + TI_SIZE * sizeof(int);
 
 #ifndef QM_LQ_THREADS
 #define QM_LQ_THREADS 256
 #endif
-__global__ void __launch_bounds__(QM_LQ_THREADS) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+__global__ void __launch_bounds__(QM_LQ_THREADS, 4) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
   const int k = blockIdx.x, b = blockIdx.y;
   const int nn = m.nn[b];
   if (k >= nn) return;
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* W = smem;
-  double* xin = smem + TW_SIZE;                 // x[30], u[30], xn[30]
+  double* xin = smem + TW_LQ_SIZE;              // x[30], u[30], xn[30]
   int* WI = (int*)(smem + kLqSmemDoubles);
   const size_t o = (size_t)b * m.NMAX + k;
   const int n = nn - 1;
   BlockGroup g;
   const bool regular = (k < n) && (m.node_flag[o] != EV_PRE);
+  __shared__ uint64_t bar;
+  if (regular && threadIdx.x == 0) {
+    // stage the kinematics products of this node into the kinematics region of the workspace: one bulk copy (TMA)
+    const uint32_t ba = (uint32_t)__cvta_generic_to_shared(&bar), bytes = KS_SIZE * sizeof(double);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(W + TW_KIN)), "l"(m.kin + o * KS_SIZE), "r"(bytes), "r"(ba)
+                 : "memory");
+  }
   for (int i = threadIdx.x; i < 90; i += blockDim.x) {
     double v;
     if (i < 30) v = m.xs[o * 30 + i];
@@ -113,21 +136,22 @@ __global__ void __launch_bounds__(QM_LQ_THREADS) k_lq(MpcBuffers m, const qmb200
     else v = (k < n) ? m.xs[(o + 1) * 30 + i - 60] : 0.0;
     xin[i] = v;
   }
-  if (regular) {
-    // stage the kinematics products of this node into the (otherwise unused) kinematics region of the workspace
-    const double2* src = reinterpret_cast<const double2*>(m.kin + o * KS_SIZE);
-    double2* dst = reinterpret_cast<double2*>(W + TW_KIN);
-    for (int i = threadIdx.x; i < KS_SIZE / 2; i += blockDim.x) dst[i] = src[i];
-  }
   __syncthreads();
+  if (regular) {
+    const uint32_t ba = (uint32_t)__cvta_generic_to_shared(&bar);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(ba) : "memory");
+  }
   double* sb = m.stage + o * SB_SIZE;
   double* pb = m.proj + o * PB_SIZE;
   double* pf = m.perf_base + o * PF_SIZE;
   const double* tt = m.target_t + (size_t)b * m.KT;
   const double* ts = m.target_x + (size_t)b * m.KT * QM_NTARGET;
   if (k == n) {
-    terminal_node(g, *M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, xin, W + TW_KIN, W + TW_REF, W + TW_E6, W + TW_DQ,
-                  W + TW_JE, sb, pf);
+    terminal_node(g, *M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, xin, W + TW_KIN, W + TW_BPM, W + TW_BPM + 80, W + TW_BPM + 88,
+                  W + TW_BPM + 100, sb, pf);
   } else if (!regular) {
     event_node(g, xin, xin + 60, sb, pb, pf);
   } else {
@@ -294,6 +318,8 @@ struct qmb200_ctx {
   int* d_pending = nullptr;
   int* h_pending = nullptr;   // pinned
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;      // k_proj runs here, concurrently with k_kin<2>
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t bytes = 0;
   bool profiling = false;
   double kernel_ms[QMB200_NUM_KERNELS] = {0};
@@ -310,13 +336,13 @@ static cudaEvent_t get_event(qmb200_ctx* c) {
 }
 
 struct KernelTimer {
-  qmb200_ctx* c; int id; cudaEvent_t e0 = nullptr, e1 = nullptr;
-  KernelTimer(qmb200_ctx* c_, int id_) : c(c_), id(id_) {
+  qmb200_ctx* c; int id; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(qmb200_ctx* c_, int id_, cudaStream_t st_ = nullptr) : c(c_), id(id_), st(st_ ? st_ : c_->stream) {
     c->kernel_launches[id]++;
-    if (c->profiling) { e0 = get_event(c); e1 = get_event(c); cudaEventRecord(e0, c->stream); }
+    if (c->profiling) { e0 = get_event(c); e1 = get_event(c); cudaEventRecord(e0, st); }
   }
   ~KernelTimer() {
-    if (c->profiling) { cudaEventRecord(e1, c->stream); c->pending_events.push_back({id, {e0, e1}}); }
+    if (c->profiling) { cudaEventRecord(e1, st); c->pending_events.push_back({id, {e0, e1}}); }
   }
 };
 
@@ -336,7 +362,12 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
   { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
   { KernelTimer kt(c, KN_KIN1); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+  CUDA_OK(cudaEventRecord(c->ev_fork, st));
+  CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  { KernelTimer kt(c, KN_PROJ, c->side); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, B), 32 * kProjWarps, 0, c->side>>>(m); }
+  CUDA_OK(cudaEventRecord(c->ev_join, c->side));
   { KernelTimer kt(c, KN_KIN2); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+  CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
   { KernelTimer kt(c, KN_LQ); k_lq<<<dim3(NMAX, B), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
   { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
   CUDA_OK(cudaGetLastError());
@@ -376,6 +407,9 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   qmb200_ctx* c = new qmb200_ctx();
   c->device = device; c->B = batch; c->hM = *model; c->hP = *problem; c->hS = *solver;
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
   CUDA_OK(cudaMalloc(&c->dP, sizeof(*problem)));
   CUDA_OK(cudaMalloc(&c->dS, sizeof(*solver)));
@@ -415,6 +449,9 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->dS) cudaFree(c->dS);
   if (c->d_pending) cudaFree(c->d_pending);
   if (c->h_pending) cudaFreeHost(c->h_pending);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
