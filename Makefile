@@ -14,3 +14,7 @@ oracle/cport/libcport.so: oracle/cport/cport.cpp $(HDR)
 
 clean:
 	rm -f qm_door_b200/libqmb200.so oracle/cport/libcport.so
+
+# development build with per-phase cycle counters (tools/phase_timing.py)
+dbg: $(SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -DQM_PHASE_TIMING -shared -o qm_door_b200/libqmb200_dbg.so $(SRC)

@@ -102,7 +102,7 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
                            x, u, xn, W.data(), WI.data(), sb, pb, pf, m.status + b);
     }
     DirectFetch fetch;
-    solve_problem(g, fetch, m, b, W.data());
+    solve_problem(g, fetch, m, b, W.data(), W.data());
     // filter line search
     double* ls = m.ls + (size_t)b * LS_SIZE;
     std::vector<double> xt(30), ut(30), xnt(30);

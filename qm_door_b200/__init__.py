@@ -13,7 +13,7 @@ from . import _abi
 from ._abi import ModelDesc, ProblemDesc, SolverDesc  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqmb200.so")
+LIB_PATH = os.environ.get("QMB200_LIB_PATH", os.path.join(_HERE, "libqmb200.so"))   # override: development builds only
 INFO_SIZE = 16
 KERNEL_NAMES = ["k_schedule", "k_init_guess", "k_kin1", "k_kin2", "k_lq", "k_solve", "k_trial", "k_decide", "k_finalize", "k_policy", "k_proj"]
 INFO = dict(alpha=0, done=1, armijo=2, dxnorm=3, dunorm=4, base_merit=5, base_dyn=6, base_eq=7,

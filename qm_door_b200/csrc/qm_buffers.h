@@ -97,19 +97,28 @@ inline void for_each_buffer(MpcBuffers& m, F f) {
 
 // ---- per-problem steps that are serial in the node axis (one group per problem)
 
-// How solve_problem gets at a per-node block: in place (host / plain loads) or staged into shared memory by the kernel
-// (k_solve: cp.async.bulk + mbarrier). request() up to three blocks, wait(), then ptr(slot) until the next request.
+// How solve_problem gets at the per-node blocks: in place (host / plain loads) or staged into shared memory by the kernel
+// (k_solve: cp.async.bulk + mbarrier). Backward: one stage block in flight; forward: two slots (the blocks of stage
+// k + 1 are requested before stage k is processed).
+enum { FWD_SLOT_SIZE = SB_FWD_SIZE + PB_SIZE + GB_SIZE };
 struct DirectFetch {
-  const double* p[3];
-  template <class G> QM_HD void request(G, int slot, const double* gptr, int) { p[slot] = gptr; }
-  template <class G> QM_HD void issue(G) {}     // start the requested copies (all threads past their last read of the buffers)
-  template <class G> QM_HD void wait(G) {}      // requested blocks are readable through ptr()
-  QM_HD const double* ptr(int slot) const { return p[slot]; }
+  const double* bp;
+  const double* fp[2][3];
+  template <class G> QM_HD void bwd_request(G, const double* stage) { bp = stage; }
+  template <class G> QM_HD const double* bwd_wait(G) { return bp; }
+  template <class G> QM_HD void publish(G) {}       // gains written by this group become visible to its own fetches
+  template <class G> QM_HD void fwd_request(G, int slot, const double* stage, const double* proj, const double* gain) {
+    fp[slot][0] = stage; fp[slot][1] = proj; fp[slot][2] = gain;
+  }
+  template <class G> QM_HD void fwd_wait(G, int slot, const double** st, const double** pb, const double** gb) {
+    *st = fp[slot][0]; *pb = fp[slot][1]; *gb = fp[slot][2];
+  }
 };
 
-// Backward Riccati sweep, forward rollout, step norms, baseline performance reduction. W >= RW_SIZE doubles.
+// Backward Riccati sweep, forward rollout, step norms, baseline performance reduction.
+// W: Riccati workspace (>= RW_SIZE doubles); R: forward scratch (>= 96 doubles; may alias W when nothing is staged over it).
 template <class G, class F>
-QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W) {
+QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, double* R) {
   const int NMAX = m.NMAX;
   const int nn = m.nn[b];
   const int n = nn - 1;
@@ -119,34 +128,41 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W) 
   double* dxs = m.dxs + (size_t)b * NMAX * 30;
   double* dus = m.dus + (size_t)b * NMAX * 30;
   const double* term = stage + (size_t)n * SB_SIZE;
+  if (n > 0) fetch.bwd_request(g, stage + (size_t)(n - 1) * SB_SIZE);
   QM_PFOR(g, idx, 900) W[RW_S + idx] = term[SB_Q + idx];
   QM_PFOR(g, i, 30) W[RW_sv + i] = term[SB_q + i];
   g.sync();
-  if (n > 0) { fetch.request(g, 0, stage + (size_t)(n - 1) * SB_SIZE, SB_SIZE); fetch.issue(g); }
   for (int k = n - 1; k >= 0; --k) {
-    fetch.wait(g);
-    const int nut = riccati_stage_a(g, fetch.ptr(0), W, m.status + b);
-    if (k > 0) { fetch.request(g, 0, stage + (size_t)(k - 1) * SB_SIZE, SB_SIZE); fetch.issue(g); }   // stage buffer is free: prefetch
+    QM_TICK(-1);
+    const double* st = fetch.bwd_wait(g);
+    QM_TICK(0);
+    const int nut = riccati_stage_a(g, st, W, m.status + b);
+    if (k > 0) fetch.bwd_request(g, stage + (size_t)(k - 1) * SB_SIZE);      // stage buffer is free: prefetch
     riccati_stage_b(g, nut, W, gain + (size_t)k * GB_SIZE);
   }
-  // forward rollout
-  double* R = W;   // reuse: [0:30] dx, [30:60] dx next, [60:78] dut, [80] armijo
+  // forward rollout: [0:30] dx, [30:48] dut, [48:78] dx next, [80] armijo
+  fetch.publish(g);
+  g.sync();
+  QM_TICK(-1);
+  if (n > 0) fetch.fwd_request(g, 0, stage, proj, gain);
   QM_PFOR(g, i, 30) { R[i] = m.x0[30 * b + i] - m.xs[((size_t)b * NMAX) * 30 + i]; }
   if (g.tid() == 0) R[80] = 0.0;
   g.sync();
   for (int k = 0; k < n; ++k) {
+    if (k + 1 < n) fetch.fwd_request(g, (k + 1) & 1, stage + (size_t)(k + 1) * SB_SIZE, proj + (size_t)(k + 1) * PB_SIZE, gain + (size_t)(k + 1) * GB_SIZE);
     QM_PFOR(g, i, 30) dxs[30 * k + i] = R[i];
-    fetch.request(g, 0, stage + (size_t)k * SB_SIZE, SB_SIZE);
-    fetch.request(g, 1, proj + (size_t)k * PB_SIZE, PB_SIZE);
-    fetch.request(g, 2, gain + (size_t)k * GB_SIZE, GB_SIZE);
-    fetch.issue(g);
-    fetch.wait(g);
-    rollout_stage(g, fetch.ptr(0), fetch.ptr(1), fetch.ptr(2), R, dus + 30 * k);
-    QM_PFOR(g, i, 30) R[i] = R[30 + i];
+    const double *st, *pb, *gb;
+    QM_TICK(10);
+    fetch.fwd_wait(g, k & 1, &st, &pb, &gb);
+    QM_TICK(11);
+    rollout_stage(g, st, pb, gb, R, dus + 30 * k);
+    QM_PFOR(g, i, 30) R[i] = R[48 + i];
     g.sync();
+    QM_TICK(12);
   }
   QM_PFOR(g, i, 30) { dxs[30 * n + i] = R[i]; dus[30 * n + i] = 0.0; }
   g.sync();
+  // step norms and baseline performance: sequential sums in a fixed order (bit-reproducible)
   if (g.tid() == 0) {
     double arm = R[80];
     for (int j = 0; j < 30; ++j) arm += term[SB_q + j] * R[j];

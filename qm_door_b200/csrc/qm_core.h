@@ -28,6 +28,24 @@
 
 namespace qm {
 
+// Development aid (-DQM_PHASE_TIMING): thread 0 of CTA 0 accumulates the cycles between consecutive ticks per phase id.
+#if defined(QM_PHASE_TIMING) && defined(__CUDACC__)
+__device__ unsigned long long qm_dbg[32];
+__device__ unsigned long long qm_dbg_last;
+#endif
+#if defined(QM_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define QM_TICK(id)                                                                    \
+  do {                                                                                 \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {                      \
+      const unsigned long long t_ = clock64();                                         \
+      if ((id) >= 0) qm_dbg[(id)] += t_ - qm_dbg_last;                                 \
+      qm_dbg_last = t_;                                                                \
+    }                                                                                  \
+  } while (0)
+#else
+#define QM_TICK(id) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------ groups
 // A group can split into a `narrow` part (dependency-chain work: kinematics tree, pivoting) and the `rest` (wide
 // independent work) that run concurrently between two full-group syncs.
@@ -39,6 +57,8 @@ struct SerialGroup {
   QM_HD bool rest_active() const { return true; }
   QM_HD SerialGroup narrow() const { return *this; }
   QM_HD SerialGroup rest() const { return *this; }
+  QM_HD void rest_signal() const {}      // rest -> narrow hand-over inside a split phase (see BlockGroup)
+  QM_HD void narrow_wait() const {}
 };
 #if defined(__CUDACC__)
 struct WarpGroup {
@@ -49,25 +69,34 @@ struct WarpGroup {
   __device__ __forceinline__ bool rest_active() const { return true; }
   __device__ __forceinline__ WarpGroup narrow() const { return *this; }
   __device__ __forceinline__ WarpGroup rest() const { return *this; }
+  __device__ __forceinline__ void rest_signal() const { __syncwarp(); }
+  __device__ __forceinline__ void narrow_wait() const {}
   __device__ __forceinline__ int warp() const { return 0; }
   __device__ __forceinline__ int nwarps() const { return 1; }
 };
-// warps 1.. of the CTA, synchronised with named barrier 1
+// all warps of the CTA but the narrow one, synchronised with named barrier 1
 struct RestGroup {
-  __device__ __forceinline__ int tid() const { return threadIdx.x - 32; }
+  int nwid;                                      // the narrow warp (excluded)
+  __device__ __forceinline__ int warp() const { const int w = threadIdx.x >> 5; return w - (w > nwid ? 1 : 0); }
+  __device__ __forceinline__ int tid() const { return warp() * 32 + (threadIdx.x & 31); }
   __device__ __forceinline__ int nt() const { return blockDim.x - 32; }
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x - 32) : "memory"); }
-  __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) - 1; }
   __device__ __forceinline__ int nwarps() const { return (blockDim.x >> 5) - 1; }
 };
+// The narrow warp can be chosen per CTA (k_solve rotates it with the CTA index: warp w issues on sub-partition w % 4,
+// so the serial chains of co-resident CTAs do not all land on the same FP64 pipe).
 struct BlockGroup {
+  int nwid = 0;
   __device__ __forceinline__ int tid() const { return threadIdx.x; }
   __device__ __forceinline__ int nt() const { return blockDim.x; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
-  __device__ __forceinline__ bool narrow_active() const { return threadIdx.x < 32; }
-  __device__ __forceinline__ bool rest_active() const { return threadIdx.x >= 32; }
+  __device__ __forceinline__ bool narrow_active() const { return (threadIdx.x >> 5) == nwid; }
+  __device__ __forceinline__ bool rest_active() const { return (threadIdx.x >> 5) != nwid; }
   __device__ __forceinline__ WarpGroup narrow() const { return WarpGroup(); }
-  __device__ __forceinline__ RestGroup rest() const { return RestGroup(); }
+  __device__ __forceinline__ RestGroup rest() const { return RestGroup{nwid}; }
+  // hand-over inside a split phase: every rest thread signals once its part is written, the narrow warp waits (named barrier 2)
+  __device__ __forceinline__ void rest_signal() const { asm volatile("bar.arrive 2, %0;" ::"r"(blockDim.x) : "memory"); }
+  __device__ __forceinline__ void narrow_wait() const { asm volatile("bar.sync 2, %0;" ::"r"(blockDim.x) : "memory"); }
   __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
   __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
 };
@@ -138,7 +167,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 #endif
-template <int TJ, bool xT, class G>
+// Flags: MM_UP  : C is symmetric, only tiles on or above the diagonal are formed (TJ must be 1, m == n);
+//        MM_XSYM: X is a symmetric matrix that is read from its upper triangle only (not with xT).
+enum { MM_UP = 1, MM_XSYM = 2 };
+template <int TJ, bool xT, int FLAGS = 0, class G>
 QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double* Y, int ldy, const double* C0, int ld0,
                double alpha, double* C, int ldc, int rot = 0) {
 #if defined(__CUDA_ARCH__)
@@ -150,9 +182,11 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
   const int nw = g.nwarps();
   int w0 = g.warp() - rot;
   while (w0 < 0) w0 += nw;
-  for (int unit = w0; unit < tm * gj; unit += nw) {
-    int ti = 0, tj = unit;                                        // unit / gj, unit % gj without the division sequence (tm <= 4)
-    while (tj >= gj) { tj -= gj; ++ti; }
+  const int nunits = (FLAGS & MM_UP) ? (tm * (tm + 1)) / 2 : tm * gj;
+  for (int unit = w0; unit < nunits; unit += nw) {
+    int ti = 0, tj = unit;                                        // unit -> (tile row, tile column group) without divisions
+    if (FLAGS & MM_UP) { while (tj >= tn - ti) { tj -= tn - ti; ++ti; } tj += ti; }
+    else { while (tj >= gj) { tj -= gj; ++ti; } }
     const int i0 = ti << 3, j0 = tj * TJ * 8;
     double acc[TJ][2], c0v[TJ][2];
     const int i = i0 + r;
@@ -170,7 +204,9 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
     const double* yp = Y + q * ldy + j0 + r;
     for (int k0 = 0; k0 < k; k0 += 4, xp += xstep, yp += 4 * ldy) {
       const bool kok = (k0 + q) < k;
-      const double a = (iok && kok) ? *xp : 0.0;
+      double a;
+      if ((FLAGS & MM_XSYM) && !xT) { const int kk = k0 + q; a = (iok && kok) ? ((kk < i) ? X[kk * ldx + i] : X[i * ldx + kk]) : 0.0; }
+      else a = (iok && kok) ? *xp : 0.0;
 #pragma unroll
       for (int t = 0; t < TJ; ++t) {
         if (j0 + 8 * t < n) {                     // warp-uniform
@@ -191,8 +227,15 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
 #else
   QM_PFOR(g, idx, m * n) {
     const int i = idx / n, j = idx % n;
+    if ((FLAGS & MM_UP) && (j >> 3) < (i >> 3)) continue;
     double acc = 0.0;
-    for (int kk = 0; kk < k; ++kk) acc += (xT ? X[kk * ldx + i] : X[i * ldx + kk]) * Y[kk * ldy + j];
+    for (int kk = 0; kk < k; ++kk) {
+      double xv;
+      if (xT) xv = X[kk * ldx + i];
+      else if ((FLAGS & MM_XSYM) && kk < i) xv = X[kk * ldx + i];
+      else xv = X[i * ldx + kk];
+      acc += xv * Y[kk * ldy + j];
+    }
     C[i * ldc + j] = (C0 ? C0[i * ld0 + j] : 0.0) + alpha * acc;
   }
 #endif

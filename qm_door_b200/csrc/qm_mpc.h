@@ -22,14 +22,16 @@ enum {
   SB_A = 0,                          // [30][30]
   SB_B = SB_A + 900,                 // [30][18]
   SB_b = SB_B + 30 * QM_NUT,         // [30]
-  SB_Q = SB_b + 30,                  // [30][30]
-  SB_P = SB_Q + 900,                 // [18][30]
-  SB_R = SB_P + 30 * QM_NUT,         // [18][18]
-  SB_q = SB_R + QM_NUT * QM_NUT,     // [30]
+  SB_q = SB_b + 30,                  // [30]
   SB_r = SB_q + 30,                  // [18]
   SB_NUT = SB_r + QM_NUT,            // reduced input dimension of this node (as double)
-  SB_SIZE = 3296
+  SB_FWD_SIZE = SB_NUT + 2,          // the forward rollout needs [A | B | b | q | r | nut] only
+  SB_Q = SB_FWD_SIZE,                // [30][30]
+  SB_P = SB_Q + 900,                 // [18][30]
+  SB_R = SB_P + 30 * QM_NUT,         // [18][18]
+  SB_SIZE = SB_R + QM_NUT * QM_NUT
 };
+static_assert(SB_SIZE % 2 == 0 && SB_FWD_SIZE % 2 == 0, "bulk copies move multiples of 16 bytes");
 // Projection of one node, compact: only the nv rows of the eliminated (pivot) joint velocities are stored.
 //   du[12 + pivcol[p]] = PX[p] . dx + PU[p] . dut + PEC[p]      (p < nv)
 //   du[fcols[a]]       = dut[a]                                  (a < nut; stance-foot forces and free joint velocities)
@@ -999,38 +1001,18 @@ QM_HDN void perf_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc
 }
 
 // ------------------------------------------------------------------------------------------ Riccati
-// Workspace. K aliases SB (SB is dead once G, H are formed); LI holds L^-1 of the Cholesky factor.
+// Workspace. S is kept as a symmetric matrix of which only the tiles on or above the diagonal are valid (MM_UP / MM_XSYM);
+// K aliases SB (SB is dead once G is formed); LI holds L^-1 of the Cholesky factor (host route only).
 enum { RW_S = 0, RW_SA = 900, RW_SB = 1800, RW_K = RW_SB, RW_H = RW_SB + 540, RW_G = RW_H + 540, RW_LI = RW_G + 324,
-       RW_sv = RW_LI + 324, RW_sb = RW_sv + 30, RW_gv = RW_sb + 30, RW_kf = RW_gv + 18, RW_SIZE = RW_kf + 18 };
-
-// 3x3 register tile of C = X Y (X: m x kd row-major ldx, Y: kd x n row-major ldy), accumulated into acc[9]
-#define QM_TILE3(acc, XP, ldx, YP, ldy, i0, j0, kd)                                                        \
-  do {                                                                                                     \
-    for (int k_ = 0; k_ < (kd); ++k_) {                                                                    \
-      const double x0_ = (XP)[((i0) + 0) * (ldx) + k_], x1_ = (XP)[((i0) + 1) * (ldx) + k_], x2_ = (XP)[((i0) + 2) * (ldx) + k_]; \
-      const double y0_ = (YP)[k_ * (ldy) + (j0)], y1_ = (YP)[k_ * (ldy) + (j0) + 1], y2_ = (YP)[k_ * (ldy) + (j0) + 2];           \
-      acc[0] += x0_ * y0_; acc[1] += x0_ * y1_; acc[2] += x0_ * y2_;                                       \
-      acc[3] += x1_ * y0_; acc[4] += x1_ * y1_; acc[5] += x1_ * y2_;                                       \
-      acc[6] += x2_ * y0_; acc[7] += x2_ * y1_; acc[8] += x2_ * y2_;                                       \
-    }                                                                                                      \
-  } while (0)
-// same with X used transposed: C = X' Y (X: kd x m row-major ldx)
-#define QM_TILE3_T(acc, XP, ldx, YP, ldy, i0, j0, kd)                                                      \
-  do {                                                                                                     \
-    for (int k_ = 0; k_ < (kd); ++k_) {                                                                    \
-      const double x0_ = (XP)[k_ * (ldx) + (i0)], x1_ = (XP)[k_ * (ldx) + (i0) + 1], x2_ = (XP)[k_ * (ldx) + (i0) + 2]; \
-      const double y0_ = (YP)[k_ * (ldy) + (j0)], y1_ = (YP)[k_ * (ldy) + (j0) + 1], y2_ = (YP)[k_ * (ldy) + (j0) + 2]; \
-      acc[0] += x0_ * y0_; acc[1] += x0_ * y1_; acc[2] += x0_ * y2_;                                       \
-      acc[3] += x1_ * y0_; acc[4] += x1_ * y1_; acc[5] += x1_ * y2_;                                       \
-      acc[6] += x2_ * y0_; acc[7] += x2_ * y1_; acc[8] += x2_ * y2_;                                       \
-    }                                                                                                      \
-  } while (0)
+       RW_sv = RW_LI + 324, RW_sb = RW_sv + 30, RW_gv = RW_sb + 30, RW_kf = RW_gv + 18, RW_COL = RW_kf + 18, RW_SIZE = RW_COL + 40 };
 
 #if defined(__CUDACC__)
 // In-place inverse of the symmetric positive definite n x n matrix Gm (shared memory, leading dimension QM_NUT, n <= 18)
-// by one warp: Gauss-Jordan elimination without pivoting, column j of the matrix held in the registers of lane j, the
-// multipliers of each pivot step broadcast with warp shuffles (no shared-memory round trips on the dependency chain).
-__device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, int* status) {
+// by one warp: Gauss-Jordan sweeps without pivoting, column j of the matrix in the registers of lane j. In every sweep
+// the owner of the pivot column publishes the negated, scaled column through shared memory (col: 2 x 20 doubles, double
+// buffered, 16-byte stores) and all lanes read it back with nine unpredicated broadcast loads and update all 18 rows
+// (rows >= n carry zero multipliers): one __syncwarp per sweep on the dependency chain, no shuffles.
+__device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, double* col, int* status) {
   const int lane = threadIdx.x & 31;
   const bool active = lane < n;
   double r[QM_NUT];
@@ -1040,17 +1022,31 @@ __device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, int* status)
 #pragma unroll
   for (int c = 0; c < QM_NUT; ++c) {
     if (c < n) {                                   // uniform across the warp
-      const double acc = __shfl_sync(0xffffffffu, r[c], c);      // pivot a_cc lives in lane c, register c
-      if (!(acc > 0.0)) bad = true;
-      const double p = 1.0 / acc;
-      const double rc = r[c];                      // a_cj of this lane's column
+      double* cb = col + 20 * (c & 1);
+      const double rc = r[c];                      // lane c: the pivot a_cc; other lanes: a_cj of their column
+      if (lane == c) {
+        if (!(rc > 0.0)) bad = true;
+        const double ip = 1.0 / rc;
+#pragma unroll
+        for (int i = 0; i < QM_NUT; i += 2) {
+          double2 v;
+          v.x = (i == c) ? ip : -r[i] * ip;        // -a_ic / a_cc, and 1 / a_cc in the pivot position
+          v.y = (i + 1 == c) ? ip : -r[i + 1] * ip;
+          reinterpret_cast<double2*>(cb)[i >> 1] = v;
+        }
+      }
+      __syncwarp();
+      double2 m2[QM_NUT / 2];
+#pragma unroll
+      for (int q = 0; q < QM_NUT / 2; ++q) m2[q] = reinterpret_cast<const double2*>(cb)[q];
 #pragma unroll
       for (int i = 0; i < QM_NUT; ++i) {
         if (i != c) {
-          const double m = __shfl_sync(0xffffffffu, r[i], c) * p;   // multiplier a_ic / a_cc from lane c
-          r[i] = (lane == c) ? -m : r[i] - m * rc;
+          const double mlt = (i & 1) ? m2[i >> 1].y : m2[i >> 1].x;
+          r[i] = (lane == c) ? mlt : r[i] + mlt * rc;
         }
       }
+      const double p = (c & 1) ? m2[c >> 1].y : m2[c >> 1].x;
       r[c] = (lane == c) ? p : rc * p;
     }
   }
@@ -1058,44 +1054,41 @@ __device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, int* status)
 #pragma unroll
     for (int i = 0; i < QM_NUT; ++i) if (i < n) Gm[QM_NUT * i + lane] = r[i];
   }
-  if (bad && lane == 0) status_or(status, ST_CHOL);
+  if (__any_sync(0xffffffffu, bad) && lane == 0) status_or(status, ST_CHOL);
 }
 #endif
 
 // One backward stage, in two halves so the caller can re-use the stage buffer (prefetch the next block) in between.
-// All dense products use 3x3 register tiles (6 loads per 9 FMAs); padded input columns (a >= nut) are zero in the block.
-//   riccati_stage_a: SA = S A, SB = S B, sb;  G, H, g;  then concurrently
-//                    narrow: Cholesky G = L L', L^-1, G^-1 = L^-T L^-1      (dependency chain, one warp)
-//                    rest  : S <- Q + A' SA (symmetric tiles), s <- q + A' sb (largest product, independent of the gains)
-//   riccati_stage_b: K = -G^-1 H, kff = -G^-1 g;  S += H' K (symmetrised), s += H' kff;  gains to HBM
+// Dense products are tile products (mm); the symmetric ones only form the tiles on or above the diagonal.
+//   riccati_stage_a: P1  SA = S A, SB = S B, sb = s + S b
+//                    P2  G = R + B' SB, g = r + B' sb
+//                    P3  narrow: G^-1 (dependency chain, one warp)
+//                        rest  : H = P + B' SA;  S <- Q + A' SA, s <- q + A' sb   (independent of the gains)
+//   riccati_stage_b: P4  K = -G^-1 H, kff = -G^-1 g
+//                    P5  S += H' K, s += H' kff;  gains to HBM
 template <class G>
 QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
   const int nut = (int)st[SB_NUT];
   const double* A = st + SB_A; const double* B = st + SB_B; const double* b = st + SB_b;
   double* S = W + RW_S; double* s = W + RW_sv;
-  // ---- P1: SA = S A, SB = S B, sb = s + S b
-  mm<4, false>(g, 30, 30, 30, S, 30, A, 30, (const double*)nullptr, 0, 1.0, W + RW_SA, 30);
-  if (nut > 0) mm<3, false>(g, 30, nut, 30, S, 30, B, QM_NUT, (const double*)nullptr, 0, 1.0, W + RW_SB, QM_NUT);
-  QM_PFOR(g, i, 30) {
-    double acc = s[i];
-    for (int j = 0; j < 30; ++j) acc += S[30 * i + j] * b[j];
-    W[RW_sb + i] = acc;
-  }
-  g.sync();
-  // ---- P2: G = R + B' SB, H = P + B' SA, g = r + B' sb
+  // ---- P1
+  mm<4, false, MM_XSYM>(g, 30, 30, 30, S, 30, A, 30, (const double*)nullptr, 0, 1.0, W + RW_SA, 30);
+  if (nut > 0) mm<3, false, MM_XSYM>(g, 30, nut, 30, S, 30, B, QM_NUT, (const double*)nullptr, 0, 1.0, W + RW_SB, QM_NUT);
+  rows_dot(g, 30, 30, [&](int i) { return s[i]; },
+           [&](int i, int j) { return ((j < i) ? S[30 * j + i] : S[30 * i + j]) * b[j]; },
+           [&](int i, double v) { W[RW_sb + i] = v; });
+  g.sync(); QM_TICK(1);
+  // ---- P2
   if (nut > 0) {
-    mm<3, true>(g, nut, nut, 30, B, QM_NUT, W + RW_SB, QM_NUT, st + SB_R, QM_NUT, 1.0, W + RW_G, QM_NUT);
-    mm<4, true>(g, nut, 30, 30, B, QM_NUT, W + RW_SA, 30, st + SB_P, 30, 1.0, W + RW_H, 30);
-    QM_PFOR(g, a, nut) {
-      double acc = st[SB_r + a];
-      for (int k = 0; k < 30; ++k) acc += B[QM_NUT * k + a] * W[RW_sb + k];
-      W[RW_gv + a] = acc;
-    }
-    g.sync();
+    mm<1, true>(g, nut, nut, 30, B, QM_NUT, W + RW_SB, QM_NUT, st + SB_R, QM_NUT, 1.0, W + RW_G, QM_NUT);
+    rows_dot(g, nut, 30, [&](int a) { return st[SB_r + a]; },
+             [&](int a, int k) { return B[QM_NUT * k + a] * W[RW_sb + k]; },
+             [&](int a, double v) { W[RW_gv + a] = v; });
+    g.sync(); QM_TICK(2);
   }
-  // ---- P3 narrow: Ginv = G^-1 in place. Device: register/shuffle Gauss-Jordan on one warp; host: Cholesky route.
+  // ---- P3 narrow: Ginv = G^-1 in place. Device: register Gauss-Jordan on one warp; host: Cholesky route.
 #if defined(__CUDA_ARCH__)
-  if (g.narrow_active() && nut > 0) spd_inverse_warp(W + RW_G, nut, status);
+  if (g.narrow_active() && nut > 0) { spd_inverse_warp(W + RW_G, nut, W + RW_COL, status); QM_TICK(7); }
 #else
   if (g.narrow_active() && nut > 0) {
     auto w0 = g.narrow();
@@ -1136,17 +1129,16 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
     }
   }
 #endif
-  // ---- P3 rest: S <- Q + A' SA ; s <- q + A' sb   (S, s were consumed in P1; symmetrised at the end of the stage)
+  // ---- P3 rest: S <- Q + A' SA (upper tiles); H = P + B' SA; s <- q + A' sb   (S, s were consumed in P1)
   if (g.rest_active()) {
     auto r_ = g.rest();
-    mm<2, true>(r_, 30, 30, 30, A, 30, W + RW_SA, 30, st + SB_Q, 30, 1.0, S, 30);
-    QM_PFOR(r_, i, 30) {
-      double acc = st[SB_q + i];
-      for (int k = 0; k < 30; ++k) acc += A[30 * k + i] * W[RW_sb + k];
-      s[i] = acc;
-    }
+    mm<1, true, MM_UP>(r_, 30, 30, 30, A, 30, W + RW_SA, 30, st + SB_Q, 30, 1.0, S, 30);
+    if (nut > 0) mm<1, true>(r_, nut, 30, 30, B, QM_NUT, W + RW_SA, 30, st + SB_P, 30, 1.0, W + RW_H, 30, 1);
+    rows_dot(r_, 30, 30, [&](int i) { return st[SB_q + i]; },
+             [&](int i, int k) { return A[30 * k + i] * W[RW_sb + k]; },
+             [&](int i, double v) { s[i] = v; });
   }
-  g.sync();
+  g.sync(); QM_TICK(3);
   return nut;
 }
 
@@ -1156,72 +1148,52 @@ QM_HDN void riccati_stage_b(G g, int nut, double* W, double* gb) {
   double* Gm = W + RW_G;
   if (nut > 0) {
     // ---- P4: K = -Ginv H, kff = -Ginv g
-    mm<4, false>(g, nut, 30, nut, Gm, QM_NUT, W + RW_H, 30, (const double*)nullptr, 0, -1.0, W + RW_K, 30);
-    QM_PFOR(g, a, nut) {
-      double acc = 0.0;
-      for (int k = 0; k < nut; ++k) acc += Gm[QM_NUT * a + k] * W[RW_gv + k];
-      W[RW_kf + a] = -acc;
-    }
-    g.sync();
-    // ---- P5: S += H' K, s += H' kff
-    mm<4, true>(g, 30, 30, nut, W + RW_H, 30, W + RW_K, 30, S, 30, 1.0, S, 30);
-    QM_PFOR(g, i, 30) {
-      double acc = s[i];
-      for (int a = 0; a < nut; ++a) acc += W[RW_H + 30 * a + i] * W[RW_kf + a];
-      s[i] = acc;
-    }
+    mm<2, false>(g, nut, 30, nut, Gm, QM_NUT, W + RW_H, 30, (const double*)nullptr, 0, -1.0, W + RW_K, 30);
+    rows_dot(g, nut, nut, [](int) { return 0.0; },
+             [&](int a, int k) { return -Gm[QM_NUT * a + k] * W[RW_gv + k]; },
+             [&](int a, double v) { W[RW_kf + a] = v; });
+    g.sync(); QM_TICK(4);
+    // ---- P5: S += H' K (upper tiles), s += H' kff
+    mm<1, true, MM_UP>(g, 30, 30, nut, W + RW_H, 30, W + RW_K, 30, S, 30, 1.0, S, 30);
+    rows_dot(g, 30, nut, [&](int i) { return s[i]; },
+             [&](int i, int a) { return W[RW_H + 30 * a + i] * W[RW_kf + a]; },
+             [&](int i, double v) { s[i] = v; });
   }
-  QM_PFOR(g, idx, QM_NUT * 30) gb[GB_K + idx] = (idx / 30 < nut) ? W[RW_K + idx] : 0.0;
+  QM_PFOR(g, idx, QM_NUT * 30) gb[GB_K + idx] = (idx < 30 * nut) ? W[RW_K + idx] : 0.0;
   QM_PFOR(g, a, QM_NUT) gb[GB_KFF + a] = (a < nut) ? W[RW_kf + a] : 0.0;
-  g.sync();
-  QM_PFOR(g, idx, 435) {     // symmetrise: pairs i < j
-    int i = 0, r = idx;
-    while (r >= 29 - i) { r -= 29 - i; ++i; }
-    const int j = i + 1 + r;
-    const double v = 0.5 * (S[30 * i + j] + S[30 * j + i]);
-    S[30 * i + j] = v; S[30 * j + i] = v;
-  }
-  g.sync();
+  g.sync(); QM_TICK(5);
 }
 
 // One forward stage: dut = K dx + kff; du from the compact projection block; dx+ = A dx + B dut + b; armijo += q.dx + r.dut
-// W: [0:30] dx, [30:60] dx next, [60:78] dut, [80] armijo accumulator
+// st: forward part of the stage block. W: v = [0:30] dx | [30:48] dut, [48:78] dx next, [80] armijo accumulator
 template <class G>
 QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double* gb, double* W, double* du_out) {
   const int nut = (int)st[SB_NUT];
-  double* dx = W; double* dxn = W + 30; double* dut = W + 60;
-  QM_PFOR(g, a, QM_NUT) {
-    double acc = 0.0;
-    if (a < nut) { acc = gb[GB_KFF + a]; for (int j = 0; j < 30; ++j) acc += gb[GB_K + 30 * a + j] * dx[j]; }
-    dut[a] = acc;
-  }
+  const double* v = W; double* dut = W + 30; double* dxn = W + 48;
+  rows_dot(g, nut, 30, [&](int a) { return gb[GB_KFF + a]; },
+           [&](int a, int j) { return gb[GB_K + 30 * a + j] * v[j]; },
+           [&](int a, double val) { dut[a] = val; });
   g.sync();
   const int* role = (const int*)(pb + PB_ROLE);
-  QM_PFOR(g, i, 60) {
-    if (i < 30) {
-      const int rl = role[i];
-      double acc;
-      if (rl < ROLE_FREE) {
-        acc = pb[PB_PEC + rl];
-        for (int j = 0; j < 30; ++j) acc += pb[PB_PX + 30 * rl + j] * dx[j];
-        for (int a = 0; a < nut; ++a) acc += pb[PB_PU + QM_NUT * rl + a] * dut[a];
-      } else if (rl < ROLE_NONE) acc = dut[rl - ROLE_FREE];
-      else acc = (i < 12) ? pb[PB_PEF + i] : 0.0;
-      du_out[i] = (nut > 0) ? acc : 0.0;
-    } else {
-      const int ii = i - 30;
-      double acc = st[SB_b + ii];
-      for (int j = 0; j < 30; ++j) acc += st[SB_A + 30 * ii + j] * dx[j];
-      for (int a = 0; a < nut; ++a) acc += st[SB_B + QM_NUT * ii + a] * dut[a];
-      dxn[ii] = acc;
-    }
-  }
-  if (g.tid() == 0) {
-    double acc = 0.0;
-    for (int j = 0; j < 30; ++j) acc += st[SB_q + j] * dx[j];
-    for (int a = 0; a < nut; ++a) acc += st[SB_r + a] * dut[a];
-    W[80] += acc;
-  }
+  const int len = 30 + nut;
+  // dx+ = b + [A | B] v
+  rows_dot(g, 30, len, [&](int i) { return st[SB_b + i]; },
+           [&](int i, int c) { return ((c < 30) ? st[SB_A + 30 * i + c] : st[SB_B + QM_NUT * i + c - 30]) * v[c]; },
+           [&](int i, double val) { dxn[i] = val; });
+  // du (pivot rows: [Px | Pu] v + Pe; free inputs: dut; dropped: Pe) and the armijo term (row 30)
+  rows_dot(g, 31, len,
+           [&](int i) {
+             if (i == 30) return W[80];
+             const int rl = role[i];
+             return (rl < ROLE_FREE) ? pb[PB_PEC + rl] : ((rl < ROLE_NONE) ? dut[rl - ROLE_FREE] : ((i < 12) ? pb[PB_PEF + i] : 0.0));
+           },
+           [&](int i, int c) {
+             if (i == 30) return ((c < 30) ? st[SB_q + c] : st[SB_r + c - 30]) * v[c];
+             const int rl = role[i];
+             if (rl >= ROLE_FREE) return 0.0;
+             return ((c < 30) ? pb[PB_PX + 30 * rl + c] : pb[PB_PU + QM_NUT * rl + c - 30]) * v[c];
+           },
+           [&](int i, double val) { if (i == 30) W[80] = val; else du_out[i] = (nut > 0) ? val : 0.0; });
   g.sync();
 }
 

@@ -163,74 +163,81 @@ __global__ void __launch_bounds__(QM_LQ_THREADS, 4) k_lq(MpcBuffers m, const qmb
 // ---- TMA staging of the per-node blocks for the serial sweeps (cp.async.bulk global -> shared, completion on an mbarrier)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-struct TmaFetch {
-  double* buf[3];          // shared-memory destinations (16-byte aligned)
-  uint64_t* bar;           // mbarrier in shared memory
-  uint32_t phase;          // parity of the next completion
-  uint32_t pending_bytes;  // thread 0 only
-  const double* src[3];
-  uint32_t bytes[3];
-  int nreq;
+// mbarrier helpers
+__device__ __forceinline__ void mbar_init(uint64_t* bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar))); }
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(double* dst, const double* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
-  __device__ void init(double* b0, double* b1, double* b2, uint64_t* mbar) {
-    buf[0] = b0; buf[1] = b1; buf[2] = b2; bar = mbar; phase = 0; nreq = 0;
+// k_solve's fetcher: thread 0 issues the bulk copies, everybody waits on the mbarrier of the slot.
+struct TmaFetch {
+  double* bbuf;            // backward: stage block buffer
+  double* fbuf;            // forward: two slots of FWD_SLOT_SIZE doubles (over the then idle backward buffers)
+  uint64_t* bar;           // [0] backward, [1], [2] forward slots
+  uint32_t pb, pf0, pf1;   // parity of the next completion per barrier
+
+  __device__ void init(double* b, double* f, uint64_t* mbar) {
+    bbuf = b; fbuf = f; bar = mbar; pb = pf0 = pf1 = 0;
     if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+      mbar_init(bar); mbar_init(bar + 1); mbar_init(bar + 2);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
   }
-  __device__ __forceinline__ void request(BlockGroup, int slot, const double* gptr, int ndoubles) {
-    if (threadIdx.x == 0) { src[nreq] = gptr; bytes[nreq] = (uint32_t)ndoubles * 8u; }
-    // slot order == request order for every caller (0, then 1, 2)
-    (void)slot;
-    ++nreq;
-  }
-  __device__ __forceinline__ void issue(BlockGroup) {
+  __device__ __forceinline__ void bwd_request(BlockGroup, const double* stage) {
     if (threadIdx.x == 0) {
-      uint32_t total = 0;
-      for (int i = 0; i < nreq; ++i) total += bytes[i];
-      // order earlier generic-proxy reads of the buffers before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the buffer are done
+      mbar_expect(bar, SB_SIZE * 8u);
+      bulk_g2s(bbuf, stage, SB_SIZE * 8u, bar);
+    }
+  }
+  __device__ __forceinline__ const double* bwd_wait(BlockGroup) { mbar_wait(bar, pb); pb ^= 1u; return bbuf; }
+  __device__ __forceinline__ void publish(BlockGroup) { asm volatile("fence.proxy.async;" ::: "memory"); }
+  __device__ __forceinline__ void fwd_request(BlockGroup, int slot, const double* stage, const double* proj, const double* gain) {
+    if (threadIdx.x == 0) {
+      double* dst = fbuf + slot * FWD_SLOT_SIZE;
+      uint64_t* br = bar + 1 + slot;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(total) : "memory");
-      for (int i = 0; i < nreq; ++i)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf[i])),
-                     "l"(src[i]), "r"(bytes[i]), "r"(smem_u32(bar))
-                     : "memory");
+      mbar_expect(br, FWD_SLOT_SIZE * 8u);
+      bulk_g2s(dst, stage, SB_FWD_SIZE * 8u, br);
+      bulk_g2s(dst + SB_FWD_SIZE, proj, PB_SIZE * 8u, br);
+      bulk_g2s(dst + SB_FWD_SIZE + PB_SIZE, gain, GB_SIZE * 8u, br);
     }
-    nreq = 0;
   }
-  __device__ __forceinline__ void wait(BlockGroup) {
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(done)
-          : "r"(smem_u32(bar)), "r"(phase)
-          : "memory");
-    }
-    phase ^= 1u;
+  __device__ __forceinline__ void fwd_wait(BlockGroup, int slot, const double** st, const double** pbk, const double** gb) {
+    if (slot == 0) { mbar_wait(bar + 1, pf0); pf0 ^= 1u; } else { mbar_wait(bar + 2, pf1); pf1 ^= 1u; }
+    const double* base = fbuf + slot * FWD_SLOT_SIZE;
+    *st = base; *pbk = base + SB_FWD_SIZE; *gb = base + SB_FWD_SIZE + PB_SIZE;
   }
-  __device__ __forceinline__ const double* ptr(int slot) const { return buf[slot]; }
 };
 
-// shared memory of k_solve: [stage block | Riccati workspace | mbarrier]; the forward sweep stages proj / gain blocks
-// into the (then idle) upper part of the Riccati workspace
-constexpr int kSolveFwdOff = 96;     // rollout scratch occupies W[0:81]
-static_assert(kSolveFwdOff + PB_SIZE + GB_SIZE <= RW_SIZE, "forward staging must fit in the Riccati workspace");
-constexpr size_t kSolveSmemBytes = (size_t)(SB_SIZE + RW_SIZE + 2) * sizeof(double);
+// shared memory of k_solve: [stage block | Riccati workspace | 4 mbarriers]; the forward sweep stages its two slots
+// over the (then idle) stage block and Riccati workspace, with its scratch behind them
+static_assert(2 * FWD_SLOT_SIZE + 96 <= SB_SIZE + RW_SIZE, "forward staging must fit in the backward buffers");
+static_assert(SB_FWD_SIZE % 2 == 0 && PB_SIZE % 2 == 0 && GB_SIZE % 2 == 0 && FWD_SLOT_SIZE % 2 == 0, "16-byte aligned bulk copies");
+constexpr size_t kSolveSmemBytes = (size_t)(SB_SIZE + RW_SIZE + 4) * sizeof(double);
 
 #ifndef QM_SOLVE_THREADS
 #define QM_SOLVE_THREADS 128
 #endif
 __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
   extern __shared__ __align__(16) double smem[];
-  double* stagebuf = smem;
-  double* W = smem + SB_SIZE;
-  uint64_t* bar = (uint64_t*)(smem + SB_SIZE + RW_SIZE);
   TmaFetch fetch;
-  fetch.init(stagebuf, W + kSolveFwdOff, W + kSolveFwdOff + PB_SIZE, bar);
-  solve_problem(BlockGroup(), fetch, m, blockIdx.x, W);
+  fetch.init(smem, smem, (uint64_t*)(smem + SB_SIZE + RW_SIZE));
+  BlockGroup g;
+  g.nwid = blockIdx.x & 3;                        // spread the serial chains of co-resident CTAs over the sub-partitions
+  solve_problem(g, fetch, m, blockIdx.x, smem + SB_SIZE, smem + 2 * FWD_SLOT_SIZE);
 }
 
 constexpr int kTrialWarps = 2;
@@ -471,6 +478,15 @@ int qmb200_sync(qmb200_ctx* c) {
   harvest_events(c);
   return 0;
 }
+
+#if defined(QM_PHASE_TIMING)
+int qmb200_debug_ticks(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, qm::qm_dbg, sizeof(unsigned long long) * 32);
+  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(qm::qm_dbg, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 void* qmb200_stream(qmb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t qmb200_device_bytes(qmb200_ctx* c) { return c ? c->bytes : 0; }
