@@ -115,14 +115,13 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
           ut[i] = m.us[(o + k) * 30 + i] + alpha * m.dus[(o + k) * 30 + i];
           if (k < n) xnt[i] = m.xs[(o + k + 1) * 30 + i] + alpha * m.dxs[(o + k + 1) * 30 + i];
         }
-        if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, xt.data(), W.data() + PW_KIN, W.data() + PW_REF,
-                                 W.data() + PW_E6, W.data() + PW_DQ, (double*)nullptr, (double*)nullptr, pf);
+        if (k == n) perf_terminal_serial(M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, xt.data(), pf);
         else if (m.node_flag[o + k] == EV_PRE) {
           double d = 0.0;
           for (int i = 0; i < 30; ++i) d += (xt[i] - xnt[i]) * (xt[i] - xnt[i]);
           pf[PF_COST] = 0.0; pf[PF_DYN] = d; pf[PF_EQ] = 0.0;
-        } else perf_node(g, M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
-                         xt.data(), ut.data(), xnt.data(), W.data(), pf);
+        } else perf_node_serial(M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
+                                xt.data(), ut.data(), xnt.data(), pf);
       }
       decide_problem(S, m, b);
     }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include "qm_mpc.h"
+#include "qm_value.h"
 
 namespace qm {
 

@@ -942,64 +942,6 @@ QM_HDN void terminal_node(G g, const qmb200_model_desc& M, const qmb200_problem_
   g.sync();
 }
 
-// ------------------------------------------------------------------------------------------ line-search node evaluation
-// Value-only evaluation of one intermediate node ([upstream] computeIntermediatePerformance): needs W of size PW_SIZE.
-enum { PW_KIN = 0, PW_REF = KW_VSIZE, PW_F1 = PW_REF + RF_SIZE, PW_F2 = PW_F1 + 30, PW_X2 = PW_F2 + 30, PW_E6 = PW_X2 + 30,
-       PW_DQ = PW_E6 + 8, PW_DX = PW_DQ + 10, PW_DU = PW_DX + 30, PW_TQ = PW_DU + 30, PW_TR = PW_TQ + 30, PW_SCAL = PW_TR + 30,
-       PW_SIZE = PW_SCAL + 4 };
-template <class G>
-QM_HDN void perf_node(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
-                      const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
-                      const double* xn, double* W, double* perf) {
-  double* kw = W + PW_KIN;
-  if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, W + PW_REF);
-  kin_eval(g, M, x, u, false, kw, false);
-  flow_rows(g, M, P.gravity, kw, x, u, W + PW_F1, (double*)nullptr);
-  ee_terms(g, kw, W + PW_REF, W + PW_E6, W + PW_DQ, (double*)nullptr);
-  QM_PFOR(g, i, 30) {
-    W[PW_DX + i] = x[i] - W[PW_REF + RF_X + i];
-    W[PW_DU + i] = u[i] - W[PW_REF + RF_U + i];
-    W[PW_X2 + i] = x[i] + dt * W[PW_F1 + i];
-  }
-  g.sync();
-  QM_PFOR(g, i, 60) {
-    double acc = 0.0;
-    if (i < 30) { for (int j = 0; j < 30; ++j) acc += P.Q[30 * i + j] * W[PW_DX + j]; W[PW_TQ + i] = acc; }
-    else { const int ii = i - 30; for (int j = 0; j < 30; ++j) acc += P.R[30 * ii + j] * W[PW_DU + j]; W[PW_TR + ii] = acc; }
-  }
-  g.sync();
-  if (g.tid() == 0) {
-    double c0 = barrier_cost(P, mode, x, u);
-    for (int i = 0; i < 30; ++i) c0 += 0.5 * (W[PW_DX + i] * W[PW_TQ + i] + W[PW_DU + i] * W[PW_TR + i]);
-    const double* e = W + PW_E6;
-    c0 += 0.5 * P.mu_ee_pos * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) + 0.5 * P.mu_ee_ori * (e[3] * e[3] + e[4] * e[4] + e[5] * e[5]);
-    double eq = 0.0;
-    for (int ft = 0; ft < 4; ++ft) {
-      const double* v = kw + KW_FVEL + 3 * ft;
-      if ((mode >> (3 - ft)) & 1) eq += v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-      else {
-        const double d = v[2] - zvel[ft];
-        eq += d * d + u[3 * ft] * u[3 * ft] + u[3 * ft + 1] * u[3 * ft + 1] + u[3 * ft + 2] * u[3 * ft + 2];
-      }
-    }
-    W[PW_SCAL + 0] = c0; W[PW_SCAL + 1] = eq;
-  }
-  g.sync();
-  kin_eval(g, M, W + PW_X2, u, false, kw, false);
-  flow_rows(g, M, P.gravity, kw, W + PW_X2, u, W + PW_F2, (double*)nullptr);
-  if (g.tid() == 0) {
-    double dyn = 0.0;
-    for (int i = 0; i < 30; ++i) {
-      const double d = x[i] + 0.5 * dt * (W[PW_F1 + i] + W[PW_F2 + i]) - xn[i];
-      dyn += d * d;
-    }
-    perf[PF_COST] = dt * W[PW_SCAL + 0];
-    perf[PF_DYN] = dt * dyn;
-    perf[PF_EQ] = dt * W[PW_SCAL + 1];
-  }
-  g.sync();
-}
-
 // ------------------------------------------------------------------------------------------ Riccati
 // Workspace. S is kept as a symmetric matrix of which only the tiles on or above the diagonal are valid (MM_UP / MM_XSYM);
 // K aliases SB (SB is dead once G is formed); LI holds L^-1 of the Cholesky factor (host route only).

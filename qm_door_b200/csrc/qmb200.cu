@@ -8,7 +8,7 @@
 //   k_proj       <<<(NMAX/4, B), 128>>>      warp per node, side stream beside k_kin<2>: projection pivots (register Gauss-Jordan)
 //   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
-//   k_trial      <<<(NMAX/2, B), 64>>>       warp per node: value-only evaluation of the trial step (small value-level workspace)
+//   k_trial      <<<(NMAX/128, B), 128>>>    thread per node: value-only evaluation of the trial step (single-pass tree walk in registers)
 //   k_decide     <<<ceil(B/128), 128>>>      thread per problem: filter line-search acceptance
 //   k_finalize   <<<B, 64>>>                 thread per component: publish primal solution + warm start
 // There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
@@ -240,48 +240,37 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
   solve_problem(g, fetch, m, blockIdx.x, smem + SB_SIZE, smem + 2 * FWD_SLOT_SIZE);
 }
 
-constexpr int kTrialWarps = 2;
-constexpr int kTrialWarpDoubles = PW_SIZE + 96;
-constexpr size_t kTrialSmemBytes = (size_t)kTrialWarps * kTrialWarpDoubles * sizeof(double);
-
-__global__ void __launch_bounds__(32 * kTrialWarps) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * kTrialWarps + warp, b = blockIdx.y;
+// line-search evaluation: a thread per node (value-only single-pass tree walk in registers, qm_value.h)
+constexpr int kTrialThreads = 128;
+__global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+  const int k = blockIdx.x * kTrialThreads + threadIdx.x, b = blockIdx.y;
   const double* ls = m.ls + (size_t)b * LS_SIZE;
   if (ls[LS_DONE] != 0.0) return;
   const int nn = m.nn[b];
   if (k >= nn) return;
-  extern __shared__ double smem[];
-  double* W = smem + (size_t)warp * kTrialWarpDoubles;
-  double* xin = W + PW_SIZE;
   const double alpha = ls[LS_ALPHA];
   const size_t o = (size_t)b * m.NMAX + k;
   const int n = nn - 1;
-  WarpGroup g;
-  for (int i = lane; i < 90; i += 32) {
-    double v;
-    if (i < 30) v = m.xs[o * 30 + i] + alpha * m.dxs[o * 30 + i];
-    else if (i < 60) v = m.us[o * 30 + i - 30] + alpha * m.dus[o * 30 + i - 30];
-    else v = (k < n) ? m.xs[(o + 1) * 30 + i - 60] + alpha * m.dxs[(o + 1) * 30 + i - 60] : 0.0;
-    xin[i] = v;
+  double x[30], u[30], xn[30];
+  for (int i = 0; i < 30; ++i) {
+    x[i] = m.xs[o * 30 + i] + alpha * m.dxs[o * 30 + i];
+    u[i] = m.us[o * 30 + i] + alpha * m.dus[o * 30 + i];
+    xn[i] = (k < n) ? m.xs[(o + 1) * 30 + i] + alpha * m.dxs[(o + 1) * 30 + i] : 0.0;
   }
-  __syncwarp();
-  double* pf = m.perf_trial + o * PF_SIZE;
+  double pf[PF_SIZE];
   const double* tt = m.target_t + (size_t)b * m.KT;
   const double* ts = m.target_x + (size_t)b * m.KT * QM_NTARGET;
   if (k == n) {
-    terminal_node(g, *M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, xin, W + PW_KIN, W + PW_REF, W + PW_E6, W + PW_DQ,
-                  (double*)nullptr, (double*)nullptr, pf);
+    perf_terminal_serial(*M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, x, pf);
   } else if (m.node_flag[o] == EV_PRE) {
-    if (lane == 0) {
-      double d = 0.0;
-      for (int i = 0; i < 30; ++i) d += (xin[i] - xin[60 + i]) * (xin[i] - xin[60 + i]);
-      pf[PF_COST] = 0.0; pf[PF_DYN] = d; pf[PF_EQ] = 0.0;
-    }
+    double d = 0.0;
+    for (int i = 0; i < 30; ++i) d += (x[i] - xn[i]) * (x[i] - xn[i]);
+    pf[PF_COST] = 0.0; pf[PF_DYN] = d; pf[PF_EQ] = 0.0;
   } else {
-    perf_node(g, *M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, xin, xin + 30, xin + 60,
-              W, pf);
+    perf_node_serial(*M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, x, u, xn, pf);
   }
+  double* out = m.perf_trial + o * PF_SIZE;
+  out[PF_COST] = pf[PF_COST]; out[PF_DYN] = pf[PF_DYN]; out[PF_EQ] = pf[PF_EQ];
 }
 
 __global__ void __launch_bounds__(128) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending) {
@@ -381,7 +370,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
   const int max_iters = 24;
   for (int it = 0; it < max_iters; ++it) {
     CUDA_OK(cudaMemsetAsync(c->d_pending, 0, sizeof(int), st));
-    { KernelTimer kt(c, KN_TRIAL); k_trial<<<dim3((NMAX + kTrialWarps - 1) / kTrialWarps, B), 32 * kTrialWarps, kTrialSmemBytes, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_TRIAL); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, B), kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_DECIDE); k_decide<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending); }
     CUDA_OK(cudaMemcpyAsync(c->h_pending, c->d_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -408,6 +397,7 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   if (!model || !problem || !solver || !out) return fail("qmb200_create: null argument");
   if (batch <= 0) return fail("qmb200_create: batch must be positive");
   if (model->nj != QM_NJ) return fail("qmb200_create: model must have 24 one-DoF joints (6 floating base + 18 actuated)");
+  if (!value_walk_supported(*model)) return fail("qmb200_create: unsupported tree topology (serial six-joint floating base carrying all limbs expected)");
   if (solver->max_nodes < 3 || solver->max_events < 1 || solver->max_targets < 1) return fail("qmb200_create: bad capacities");
   if (qmb200_device_count() <= 0) return fail("qmb200_create: no CUDA device available (this library has no CPU fallback)");
   CUDA_OK(cudaSetDevice(device));
@@ -438,7 +428,6 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   CUDA_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_trial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrialSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
   *out = c;
   return 0;
