@@ -243,13 +243,16 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
 
 // ------------------------------------------------------------------------------------------ kinematics workspace
 // Offsets (in doubles) into the kinematics workspace.
+// Regions whose lifetimes do not overlap share storage: the q-derivatives DH | DFV (written by the last phase of
+// kin_velocities when deriv is requested) take the place of R | BODY (placements: dead after the body / frame phases; body
+// inertias: dead once the body momenta HB are formed), and so does F (CRBA columns, read by the whole-body controller only,
+// which never requests the q-derivatives).
 enum {
-  // ---- value level (needed by every evaluation); KW_VSIZE doubles suffice when no Jacobians / derivatives are requested
   KW_R = 0,                          // [24][9]  world rotation of joint frames
-  KW_P = KW_R + QM_NJ * 9,           // [24][3]  world origin of joint frames
+  KW_BODY = KW_R + QM_NJ * 9,        // [24][10] per body: m, m*c[3], I0[6] (rot. inertia about world origin)
+  KW_P = KW_BODY + QM_NJ * 10,       // [24][3]  world origin of joint frames
   KW_AX = KW_P + QM_NJ * 3,          // [24][3]  world joint axis
-  KW_BODY = KW_AX + QM_NJ * 3,       // [24][10] per body: m, m*c[3], I0[6] (rot. inertia about world origin)
-  KW_COMP = KW_BODY + QM_NJ * 10,    // [24][10] same, summed over the subtree of each joint
+  KW_COMP = KW_AX + QM_NJ * 3,       // [24][10] same as BODY, summed over the subtree of each joint
   KW_ACM = KW_COMP + QM_NJ * 10,     // [6][24]  centroidal momentum matrix
   KW_SV = KW_ACM + 6 * QM_NJ,        // [24][6]  S_j v_j  -> reused for subtree momenta
   KW_V = KW_SV + QM_NJ * 6,          // [24][6]  spatial velocity (w, vO) of each body, world origin
@@ -263,14 +266,16 @@ enum {
   KW_VEL = KW_ABINV + 36,            // [24] generalized velocity
   KW_RHS = KW_VEL + QM_NJ,           // [6]
   KW_VSIZE = ((KW_RHS + 6 + 3) / 4) * 4,
-  // ---- Jacobian / derivative level
+  // ---- Jacobian level
   KW_FJ = KW_VSIZE,                  // [4][3][24] foot linear Jacobians
   KW_EEJ = KW_FJ + 12 * QM_NJ,       // [6][24] ee Jacobian [linear; angular]
-  KW_DH = KW_EEJ + 6 * QM_NJ,        // [6][24]  d(A v)/dq at fixed v (centroidal)
-  KW_DFV = KW_DH + 6 * QM_NJ,        // [4][3][24] d(J_i v)/dq at fixed v
-  KW_F = KW_DFV + 12 * QM_NJ,        // [24][6] composite momentum per unit joint rate I^c_j S_j = (L0, p)  (CRBA columns)
-  KW_SIZE = ((KW_F + 6 * QM_NJ + 3) / 4) * 4
+  KW_SIZE = ((KW_EEJ + 6 * QM_NJ + 3) / 4) * 4,
+  // ---- aliases (see above)
+  KW_F = KW_R,                       // [24][6] composite momentum per unit joint rate I^c_j S_j = (L0, p)  (CRBA columns)
+  KW_DH = KW_R,                      // [6][24]  d(A v)/dq at fixed v (centroidal)
+  KW_DFV = KW_DH + 6 * QM_NJ         // [4][3][24] d(J_i v)/dq at fixed v
 };
+static_assert(KW_DFV + 12 * QM_NJ <= KW_P, "DH | DFV must fit in R | BODY");
 
 // spatial motion vector of joint j (world coordinates, reference point = world origin): (w, vO)
 QM_HD void joint_S(const qmb200_model_desc& M, const double* w, int j, double* S) {

@@ -405,9 +405,14 @@ QM_HD double barrier_cost(const qmb200_problem_desc& P, int mode, const double* 
 
 // ------------------------------------------------------------------------------------------ transcription workspace
 enum { PI_PIV = 0, PI_STATUS = 16, PI_NUT = 17, PI_NV = 18, PI_SEL = 20, PI_POS = 50, PI_SIZE = 80 };   // int32 index record
+// aux layout: reference (x_ref, u_nominal, ee pose), friction-cone terms per foot, arm box gradients / Hessians / values
+enum { NA_REF = 0, NA_CONE = RF_SIZE, NA_BOX = NA_CONE + 40, NA_BOXV = NA_BOX + 24, NA_SIZE = NA_BOXV + 12 };
+enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = KS_T + 784, KS_E6 = KS_JE + 144,
+       KS_AUX = KS_E6 + 8, KS_DINV = ((KS_AUX + NA_SIZE + 3) / 4) * 4, KS_PIV = KS_DINV + 256, KS_SIZE = KS_PIV + PI_SIZE / 2 };
+static_assert(KS_SIZE % 2 == 0, "staged kinematics products are moved by 16-byte bulk copies");
 enum {
   TW_KIN = 0,                       // kinematics workspace (fused path) / staged kinematics products (split path)
-  TW_A = TW_KIN + KW_SIZE + 16,     // [30][30]
+  TW_A = TW_KIN + ((int)KW_SIZE > (int)KS_SIZE ? (int)KW_SIZE : (int)KS_SIZE),     // [30][30]
   TW_BPM = TW_A + 900,              // [30][30] B with columns permuted [pivots | frees | dropped]
   TW_RPM = TW_BPM + 900,            // [<=30][30] R with rows [pivots | frees] and columns permuted
   TW_T2 = TW_RPM + 900,             // [16][49] = Dinv [Dv | C | e]: row p expresses joint velocity piv[p]
@@ -454,11 +459,6 @@ struct NodeIO {
   double* dinv;               // [16][16] inverse of the pivot block of Dv (rows / columns in constraint-row order)
   int* piv;                   // PI_* index record: pivots, status bits, nut, nv, permutation sel / pos of the inputs
 };
-// aux layout: reference (x_ref, u_nominal, ee pose), friction-cone terms per foot, arm box gradients / Hessians / values
-enum { NA_REF = 0, NA_CONE = RF_SIZE, NA_BOX = NA_CONE + 40, NA_BOXV = NA_BOX + 24, NA_SIZE = NA_BOXV + 12 };
-enum { KS_FR1 = 0, KS_FR2 = 540, KS_F1 = 1080, KS_F2 = 1110, KS_X2 = 1140, KS_T = 1170, KS_JE = KS_T + 784, KS_E6 = KS_JE + 144,
-       KS_AUX = KS_E6 + 8, KS_DINV = ((KS_AUX + NA_SIZE + 3) / 4) * 4, KS_PIV = KS_DINV + 256, KS_SIZE = KS_PIV + PI_SIZE / 2 };
-static_assert((int)KS_SIZE <= (int)KW_SIZE + 16 && KS_SIZE % 2 == 0, "staged kinematics products must fit the kinematics region");
 QM_HD NodeIO node_io_at(double* base) {
   NodeIO io;
   io.fr1 = base + KS_FR1; io.fr2 = base + KS_FR2; io.f1 = base + KS_F1; io.f2 = base + KS_F2;
@@ -634,11 +634,11 @@ QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_des
     }
   }
   kin_eval(g, M, x, u, true, kw);
-  // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) placement arrays R | P | AX of the workspace
-  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_R);
+  // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) velocity arrays SV | V | HB of the workspace
+  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_SV);
   ee_terms(g, kw, scr, io.e6, scr + RF_SIZE, io.je);
   {
-    const double* Fr1 = kw + KW_R - 180;   // Fr1[(3 + cc) * 60 + c] -> shadow[cc * 60 + c]
+    const double* Fr1 = kw + KW_SV - 180;  // Fr1[(3 + cc) * 60 + c] -> shadow[cc * 60 + c]
     QM_PFOR(g, idx, nv * 49) {
       const int row = idx / 49, c = idx % 49;
       // map row -> (foot, component)

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_mo
 
 // ---- transcription = two kinematics kernels (warp per node: the kinematic tree is a dependency chain, so many
 //      independent chains per SM) + one LQ assembly kernel (CTA per node: wide small-matrix work)
-constexpr int kKinWarps = 2;
+constexpr int kKinWarps = 1;
 constexpr int kKinWarpDoubles = KW_SIZE + RF_SIZE + 12 + 60;
 constexpr size_t kKinSmemBytes = (size_t)kKinWarps * kKinWarpDoubles * sizeof(double);
 
