@@ -37,7 +37,7 @@ def workload_config(n_gpus):
             "batch_per_gpu": BATCH_PER_GPU, "horizon_s": HORIZON, "dt_s": DT, "gait": "trot",
             "parallelism": "independent problems sharded across %d GPU(s)%s" % (
                 n_gpus, ", one NCCL all-gather of the policy per cycle" if n_gpus > 1 else ""),
-            "l2_policy": "working set per step (4.9 GB of LQ blocks) is larger than the 126 MB L2; no explicit flush"}
+            "l2_policy": "working set per step (6.6 GB of LQ and kinematics blocks) is larger than the 126 MB L2; no explicit flush"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -84,17 +84,21 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- algorithmic bytes
 def kernel_bytes_per_node(kernel, nut):
-    """Doubles a kernel must move per intermediate node with reduced input dimension nut (nv = 26 - nut velocity rows).
-    stage = projected LQ block actually used (A 900, B 30 nut, b 30, Q 900, P 30 nut, R nut^2, q 30, r nut, 1);
-    proj = (Pu 30 nut, Px 900, Pe 30); gain = (K 30 nut, kff nut); kin1/kin2 = products of the two kinematics evaluations."""
+    """Bytes a kernel must move per intermediate node with reduced input dimension nut (nv = 26 - nut velocity rows),
+    as laid out in DESIGN.md section 2.
+    stage = projected LQ block actually used (A 900, B 30 nut, b 30, q 30, r nut, 1 | Q 900, P 30 nut, R nut^2);
+    proj  = compact projection block (pivot rows of Px / Pu, Pe, roles); gain = (K 30 nut, kff nut);
+    kin1 / kin2 = products of the two kinematics evaluations; piv = pivot-block inverse and index record (k_proj)."""
     nv = 26 - nut
-    stage = 900 + 30 * nut + 30 + 900 + 30 * nut + nut * nut + 30 + nut + 1
-    proj = 30 * nut + 900 + 30
+    fwd = 900 + 30 * nut + 30 + 30 + nut + 1
+    stage = fwd + 900 + 30 * nut + nut * nut
+    proj = 30 * nv + nut * nv + nv + 12 + 16
     gain = 30 * nut + nut
-    kin1 = 540 + 30 + 30 + 49 * nv + 144 + 8
+    kin1 = 540 + 30 + 30 + 49 * nv + 144 + 8 + 144
     kin2 = 540 + 30
-    d = {"k_kin1": 60 + kin1, "k_kin2": 60 + kin2, "k_lq": 90 + kin1 + kin2 + stage + proj + 3,
-         "k_solve": 2 * stage + proj + 2 * gain + 60, "k_trial": 150 + 3}[kernel]
+    piv = nv * nv + 40
+    d = {"k_kin1": 60 + kin1, "k_kin2": 60 + kin2, "k_proj": 18 * nv + piv, "k_lq": 90 + kin1 + kin2 + piv + stage + proj + 3,
+         "k_solve": stage + gain + (fwd + proj + gain) + 60, "k_trial": 150 + 3}[kernel]
     return 8 * d
 
 
@@ -294,7 +298,7 @@ def run_gpu(args, rank, world, local_rank):
         total = B * world
         value = total * args.steps / (dev_ms * 1e-3)
         e2e = total * args.steps / (e2e_ms * 1e-3)
-        # dominant kernel roofline (k_transcribe): algorithmic bytes of the nodes actually transcribed / mean launch time
+        # dominant kernel roofline: algorithmic bytes of the nodes actually processed / mean launch time of that kernel
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -310,7 +314,7 @@ def run_gpu(args, rank, world, local_rank):
                 nodes_bytes += kernel_bytes_per_node(dom, 14 + bin(md & 15).count("1"))
         achieved = nodes_bytes / (ms_dom * 1e-3) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")       # DRAM bytes per launch from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")       # DRAM bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)
         cyc_bytes = sum(cycle_bytes_per_node(16) for _ in range(1)) * float(nn.sum() - B)

@@ -178,14 +178,17 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
   const int tm = (m + 7) >> 3, tn = (n + 7) >> 3;
   const int gj = (tn + TJ - 1) / TJ;
   const int r = lane >> 2, q = lane & 3;
-  // `rot` rotates the unit -> warp assignment so that products issued back to back spread over all warps
+  // `rot` (0 <= rot < nwarps) rotates the unit -> warp assignment so that products issued back to back spread over all warps
   const int nw = g.nwarps();
   int w0 = g.warp() - rot;
-  while (w0 < 0) w0 += nw;
+  if (w0 < 0) w0 += nw;
   const int nunits = (FLAGS & MM_UP) ? (tm * (tm + 1)) / 2 : tm * gj;
   for (int unit = w0; unit < nunits; unit += nw) {
     int ti = 0, tj = unit;                                        // unit -> (tile row, tile column group) without divisions
     if (FLAGS & MM_UP) { while (tj >= tn - ti) { tj -= tn - ti; ++ti; } tj += ti; }
+    else if (gj == 1) { ti = unit; tj = 0; }
+    else if (gj == 2) { ti = unit >> 1; tj = unit & 1; }
+    else if (gj == 4) { ti = unit >> 2; tj = unit & 3; }
     else { while (tj >= gj) { tj -= gj; ++ti; } }
     const int i0 = ti << 3, j0 = tj * TJ * 8;
     double acc[TJ][2], c0v[TJ][2];

@@ -847,17 +847,17 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
   }
   const double* PXn = T2 + 18;                                   // -Px pivot rows, leading dimension 49
   mm<2, false>(g, 30, 30, nv, BPM, 30, PXn, 49, W + TW_A, 30, -1.0, sb + SB_A, 30, 0);
-  mm<2, false>(g, nsel, 30, nv, RPM, 30, PXn, 49, (const double*)nullptr, 0, -1.0, RPX, 30, 8);
+  mm<2, false>(g, nsel, 30, nv, RPM, 30, PXn, 49, (const double*)nullptr, 0, -1.0, RPX, 30, 0);
   if (nut > 0) {
-    mm<3, false>(g, 30, nut, nv, BPM, 30, W + TW_PUC, QM_NUT, BPM + nv, 30, 1.0, sb + SB_B, QM_NUT, 16);
-    mm<3, false>(g, nsel, nut, nv, RPM, 30, W + TW_PUC, QM_NUT, RPM + nv, 30, 1.0, RPU, QM_NUT, 20);
+    mm<3, false>(g, 30, nut, nv, BPM, 30, W + TW_PUC, QM_NUT, BPM + nv, 30, 1.0, sb + SB_B, QM_NUT, 6);
+    mm<3, false>(g, nsel, nut, nv, RPM, 30, W + TW_PUC, QM_NUT, RPM + nv, 30, 1.0, RPU, QM_NUT, 2);
   }
   g.sync();
   // ---- L4: Q~ = Q + Px' R Px, P~ = Pu' R Px, R~ = Pu' R Pu, q~ = q + Px' r', r~ = Pu' r'
   mm<2, true>(g, 30, 30, nv, PXn, 49, RPX, 30, sb + SB_Q, 30, -1.0, sb + SB_Q, 30, 0);
   if (nut > 0) {
-    mm<2, true>(g, nut, 30, nv, W + TW_PUC, QM_NUT, RPX, 30, RPX + 30 * nv, 30, 1.0, sb + SB_P, 30, 8);
-    mm<3, true>(g, nut, nut, nv, W + TW_PUC, QM_NUT, RPU, QM_NUT, RPU + QM_NUT * nv, QM_NUT, 1.0, sb + SB_R, QM_NUT, 14);
+    mm<2, true>(g, nut, 30, nv, W + TW_PUC, QM_NUT, RPX, 30, RPX + 30 * nv, 30, 1.0, sb + SB_P, 30, 0);
+    mm<3, true>(g, nut, nut, nv, W + TW_PUC, QM_NUT, RPU, QM_NUT, RPU + QM_NUT * nv, QM_NUT, 1.0, sb + SB_R, QM_NUT, 4);
   }
   QM_PFOR(g, j, 30) {
     double qv = W[TW_QV + j];
