@@ -24,6 +24,7 @@ enum {
 
 struct MpcBuffers {
   int B, NMAX, EMAX, KT;
+  int b0, nb;          // chunk of problems [b0, b0 + nb) a kernel launch works on (the cycle is pipelined over chunks)
   // inputs (per cycle)
   double* t0;          // [B]
   double* x0;          // [B][30]

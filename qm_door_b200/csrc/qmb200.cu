@@ -5,7 +5,8 @@
 //   k_init_guess <<<B, 64>>>                 thread per state/input component: warm start interpolation
 //   k_kin<1>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x,u), constraint rows, ee terms -> kin scratch
 //   k_kin<2>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
-//   k_proj       <<<(NMAX/4, B), 128>>>      warp per node, side stream beside k_kin<2>: projection pivots (register Gauss-Jordan)
+//   k_proj       <<<(NMAX/4, B), 128>>>      warp per node: projection pivots (register Gauss-Jordan)
+// The cycle can be pipelined over chunks of problems (one stream per chunk, run_cycle): B below is the chunk size.
 //   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
 //   k_trial      <<<(NMAX/128, B), 128>>>    thread per node: value-only evaluation of the trial step (single-pass tree walk in registers)
@@ -14,6 +15,7 @@
 // There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,8 +39,8 @@ static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_gue
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
   // warp per problem: lane 0 builds the (inherently serial) time grid, then the lanes annotate the nodes in parallel
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= m.B) return;
+  const int b = m.b0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= m.b0 + m.nb) return;
   const size_t o = (size_t)b * m.NMAX;
   const double* ev = m.events + (size_t)b * m.EMAX;
   const int32_t* md = m.modes + (size_t)b * (m.EMAX + 1);
@@ -50,7 +52,7 @@ __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_sol
 
 __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
                                                     const qmb200_solver_desc* S) {
-  const int b = blockIdx.x, c = threadIdx.x;
+  const int b = m.b0 + blockIdx.x, c = threadIdx.x;
   if (c >= 60) return;
   const size_t o = (size_t)b * m.NMAX;
   init_guess_component(*M, *P, S->weak_eps, c, m.x0 + 30 * b, m.nn[b], m.node_t + o, m.node_flag + o, m.node_ts + o,
@@ -67,7 +69,7 @@ constexpr size_t kKinSmemBytes = (size_t)kKinWarps * kKinWarpDoubles * sizeof(do
 template <int EVAL>
 __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * kKinWarps + warp, b = blockIdx.y;
+  const int k = blockIdx.x * kKinWarps + warp, b = m.b0 + blockIdx.y;
   const int n = m.nn[b] - 1;
   if (k >= n) return;                                   // terminal node and padding: nothing to evaluate
   const size_t o = (size_t)b * m.NMAX + k;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb2
 // ---- projection pivots: warp per node, register-resident Gauss-Jordan with full pivoting (runs beside k_kin<2>)
 constexpr int kProjWarps = 4;
 __global__ void __launch_bounds__(32 * kProjWarps) k_proj(MpcBuffers m) {
-  const int k = blockIdx.x * kProjWarps + (threadIdx.x >> 5), b = blockIdx.y;
+  const int k = blockIdx.x * kProjWarps + (threadIdx.x >> 5), b = m.b0 + blockIdx.y;
   if (k >= m.nn[b] - 1) return;
   const size_t o = (size_t)b * m.NMAX + k;
   if (m.node_flag[o] == EV_PRE) return;
@@ -107,7 +109,7 @@ constexpr size_t kLqSmemBytes = kLqSmemDoubles * sizeof(double) + TI_SIZE * size
 #define QM_LQ_THREADS 256
 #endif
 __global__ void __launch_bounds__(QM_LQ_THREADS, 4) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
-  const int k = blockIdx.x, b = blockIdx.y;
+  const int k = blockIdx.x, b = m.b0 + blockIdx.y;
   const int nn = m.nn[b];
   if (k >= nn) return;
   extern __shared__ __align__(16) double smem[];
@@ -237,13 +239,13 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
   fetch.init(smem, smem, (uint64_t*)(smem + SB_SIZE + RW_SIZE));
   BlockGroup g;
   g.nwid = blockIdx.x & 3;                        // spread the serial chains of co-resident CTAs over the sub-partitions
-  solve_problem(g, fetch, m, blockIdx.x, smem + SB_SIZE, smem + 2 * FWD_SLOT_SIZE);
+  solve_problem(g, fetch, m, m.b0 + blockIdx.x, smem + SB_SIZE, smem + 2 * FWD_SLOT_SIZE);
 }
 
 // line-search evaluation: a thread per node (value-only single-pass tree walk in registers, qm_value.h)
 constexpr int kTrialThreads = 128;
 __global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
-  const int k = blockIdx.x * kTrialThreads + threadIdx.x, b = blockIdx.y;
+  const int k = blockIdx.x * kTrialThreads + threadIdx.x, b = m.b0 + blockIdx.y;
   const double* ls = m.ls + (size_t)b * LS_SIZE;
   if (ls[LS_DONE] != 0.0) return;
   const int nn = m.nn[b];
@@ -274,14 +276,14 @@ __global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb
 }
 
 __global__ void __launch_bounds__(128) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= m.B) return;
+  const int b = m.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= m.b0 + m.nb) return;
   decide_problem(*S, m, b);
   if (m.ls[(size_t)b * LS_SIZE + LS_DONE] == 0.0) atomicAdd(pending, 1);
 }
 
 __global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out) {
-  const int b = blockIdx.x, c = threadIdx.x;
+  const int b = m.b0 + blockIdx.x, c = threadIdx.x;
   if (c >= 60) return;
   finalize_component(m, b, c, t_out, x_out, u_out);
 }
@@ -311,11 +313,15 @@ struct qmb200_ctx {
   qmb200_problem_desc* dP = nullptr;
   qmb200_solver_desc* dS = nullptr;
   MpcBuffers m;          // ctx-owned device buffers
-  int* d_pending = nullptr;
-  int* h_pending = nullptr;   // pinned
+  int* d_pending = nullptr;   // [kMaxChunks]
+  int* h_pending = nullptr;   // pinned, [kMaxChunks]
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;      // k_proj runs here, concurrently with k_kin<2>
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // The cycle can be pipelined over chunks of problems, one stream per chunk, so that the (latency-bound, few CTAs) Riccati
+  // sweeps of one chunk run beside the transcription kernels of the next ones (QMB200_CHUNKS; see qmb200_create).
+  static const int kMaxChunks = 8;
+  int nchunks = 1;
+  cudaStream_t cs[kMaxChunks] = {nullptr};
+  cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr};
   int64_t bytes = 0;
   bool profiling = false;
   double kernel_ms[QMB200_NUM_KERNELS] = {0};
@@ -354,29 +360,49 @@ static void harvest_events(qmb200_ctx* c) {
 
 static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, double* u_out) {
   const int B = m.B, NMAX = m.NMAX;
-  cudaStream_t st = c->stream;
-  { KernelTimer kt(c, KN_SCHEDULE); k_schedule<<<(B + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
-  { KernelTimer kt(c, KN_INIT); k_init_guess<<<B, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
-  { KernelTimer kt(c, KN_KIN1); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
-  CUDA_OK(cudaEventRecord(c->ev_fork, st));
-  CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-  { KernelTimer kt(c, KN_PROJ, c->side); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, B), 32 * kProjWarps, 0, c->side>>>(m); }
-  CUDA_OK(cudaEventRecord(c->ev_join, c->side));
-  { KernelTimer kt(c, KN_KIN2); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, B), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
-  CUDA_OK(cudaStreamWaitEvent(st, c->ev_join, 0));
-  { KernelTimer kt(c, KN_LQ); k_lq<<<dim3(NMAX, B), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
-  { KernelTimer kt(c, KN_SOLVE); k_solve<<<B, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
-  CUDA_OK(cudaGetLastError());
-  const int max_iters = 24;
-  for (int it = 0; it < max_iters; ++it) {
-    CUDA_OK(cudaMemsetAsync(c->d_pending, 0, sizeof(int), st));
-    { KernelTimer kt(c, KN_TRIAL); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, B), kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
-    { KernelTimer kt(c, KN_DECIDE); k_decide<<<(B + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending); }
-    CUDA_OK(cudaMemcpyAsync(c->h_pending, c->d_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    if (*c->h_pending == 0) break;
+  const int nch = c->nchunks, cb = (B + nch - 1) / nch;
+  // inputs were enqueued on the main stream: every chunk stream starts behind them
+  CUDA_OK(cudaEventRecord(c->ev_start, c->stream));
+  for (int ch = 0; ch < nch; ++ch) {
+    cudaStream_t st = c->cs[ch];
+    m.b0 = ch * cb;
+    m.nb = (m.b0 + cb <= B) ? cb : B - m.b0;
+    if (m.nb <= 0) continue;
+    const int nb = m.nb;
+    CUDA_OK(cudaStreamWaitEvent(st, c->ev_start, 0));
+    { KernelTimer kt(c, KN_SCHEDULE, st); k_schedule<<<(nb + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
+    { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
+    { KernelTimer kt(c, KN_KIN1, st); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_PROJ, st); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, nb), 32 * kProjWarps, 0, st>>>(m); }
+    { KernelTimer kt(c, KN_KIN2, st); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
+    CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
+    { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, nb), kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
+    { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch); }
+    CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
-  { KernelTimer kt(c, KN_FINALIZE); k_finalize<<<B, 64, 0, st>>>(m, t_out, x_out, u_out); }
+  CUDA_OK(cudaGetLastError());
+  // filter line search: further (backtracking) trials of a chunk while any of its problems is still pending
+  const int max_iters = 24;
+  for (int ch = 0; ch < nch; ++ch) {
+    cudaStream_t st = c->cs[ch];
+    m.b0 = ch * cb;
+    m.nb = (m.b0 + cb <= B) ? cb : B - m.b0;
+    if (m.nb <= 0) continue;
+    const int nb = m.nb;
+    for (int it = 1; it < max_iters; ++it) {
+      CUDA_OK(cudaStreamSynchronize(st));
+      if (c->h_pending[ch] == 0) break;
+      CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
+      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, nb), kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
+      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch); }
+      CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    { KernelTimer kt(c, KN_FINALIZE, st); k_finalize<<<nb, 64, 0, st>>>(m, t_out, x_out, u_out); }
+    CUDA_OK(cudaEventRecord(c->ev_done[ch], st));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_done[ch], 0));     // the main stream continues behind every chunk
+  }
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -404,15 +430,28 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   qmb200_ctx* c = new qmb200_ctx();
   c->device = device; c->B = batch; c->hM = *model; c->hP = *problem; c->hS = *solver;
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-  CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  {
+    // Tuning knob. Measured on B200 (config 2): 1 / 2 / 4 / 8 chunks -> 13.12 / 13.24 / 13.63 / 14.97 ms per step: the kernels
+    // do overlap, but the step is bound by instruction issue across the whole GPU, so the default stays at one chunk.
+    const char* env = getenv("QMB200_CHUNKS");
+    int nch = env ? atoi(env) : 1;
+    if (nch < 1) nch = 1;
+    if (nch > qmb200_ctx::kMaxChunks) nch = qmb200_ctx::kMaxChunks;
+    if (nch > batch) nch = batch;
+    c->nchunks = nch;
+  }
+  for (int ch = 0; ch < c->nchunks; ++ch) {
+    CUDA_OK(cudaStreamCreateWithFlags(&c->cs[ch], cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[ch], cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
   CUDA_OK(cudaMalloc(&c->dP, sizeof(*problem)));
   CUDA_OK(cudaMalloc(&c->dS, sizeof(*solver)));
   CUDA_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(c->dP, problem, sizeof(*problem), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(c->dS, solver, sizeof(*solver), cudaMemcpyHostToDevice));
+  c->m.b0 = 0; c->m.nb = batch;
   c->m.B = batch; c->m.NMAX = solver->max_nodes; c->m.EMAX = solver->max_events; c->m.KT = solver->max_targets;
   cudaError_t err = cudaSuccess;
   int64_t total = 0;
@@ -423,8 +462,8 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   });
   if (err != cudaSuccess) { qmb200_destroy(c); return fail(std::string("qmb200_create: device allocation failed: ") + cudaGetErrorString(err)); }
   c->bytes = total;
-  CUDA_OK(cudaMalloc(&c->d_pending, sizeof(int)));
-  CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int)));
+  CUDA_OK(cudaMalloc(&c->d_pending, sizeof(int) * qmb200_ctx::kMaxChunks));
+  CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int) * qmb200_ctx::kMaxChunks));
   CUDA_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
@@ -445,9 +484,11 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->dS) cudaFree(c->dS);
   if (c->d_pending) cudaFree(c->d_pending);
   if (c->h_pending) cudaFreeHost(c->h_pending);
-  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (int ch = 0; ch < qmb200_ctx::kMaxChunks; ++ch) {
+    if (c->cs[ch]) { cudaStreamSynchronize(c->cs[ch]); cudaStreamDestroy(c->cs[ch]); }
+    if (c->ev_done[ch]) cudaEventDestroy(c->ev_done[ch]);
+  }
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
