@@ -167,44 +167,65 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 #endif
-// Flags: MM_UP  : C is symmetric, only tiles on or above the diagonal are formed (TJ must be 1, m == n);
+// Flags: MM_UP  : C is symmetric (xT products, m == n); only the tiles needed to cover its upper triangle are formed:
+//                  tile (ti, tj) unless column group tj / 2 lies left of row group ti / 2 (16 x 16 groups, see below);
 //        MM_XSYM: X is a symmetric matrix that is read from its upper triangle only (not with xT).
+// Bank conflicts: the operands live in shared memory with leading dimensions 30 or 18 doubles (bank stride -4 / +4 per
+// row), so a tile over consecutive rows / columns makes the 16 lanes of a half warp collide two-way on every fragment
+// load. A tile therefore covers a permuted set of rows / columns (the product does not care which eight it gets):
+//   * rows of a non-transposed X tile: i0 + {0,2,4,6,1,3,5,7}  (rows two apart are eight banks apart);
+//   * columns of Y (and of the output), and the rows of a transposed X tile: groups of 16, two tiles per group:
+//     16 g + {0,1,8,9,2,3,10,11} and 16 g + {4,5,12,13,6,7,14,15}  (the four k-rows of a step then interleave cleanly).
+// Each lane still writes two adjacent output elements.
 enum { MM_UP = 1, MM_XSYM = 2 };
+QM_HD int mm_rowperm(int r) { return ((r & 3) << 1) | (r >> 2); }
+QM_HD int mm_col16(int tile, int c) {      // matrix column of tile-column c (0..7) of tile `tile` (two tiles per 16 columns)
+  const int p = c >> 1;
+  return ((tile >> 1) << 4) + (((p & 1) << 3) | ((p >> 1) << 1) | ((tile & 1) << 2)) + (c & 1);
+}
+QM_HD int mm_tiles16(int n) {              // number of tiles with at least one column < n
+  const int g = (n - 1) >> 4;
+  return 2 * g + (((n - 1) - 16 * g >= 4) ? 2 : 1);
+}
 template <int TJ, bool xT, int FLAGS = 0, class G>
 QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double* Y, int ldy, const double* C0, int ld0,
                double alpha, double* C, int ldc, int rot = 0) {
 #if defined(__CUDA_ARCH__)
   const int lane = threadIdx.x & 31;
-  const int tm = (m + 7) >> 3, tn = (n + 7) >> 3;
+  const int tm = xT ? mm_tiles16(m) : (m + 7) >> 3, tn = mm_tiles16(n);
   const int gj = (tn + TJ - 1) / TJ;
   const int r = lane >> 2, q = lane & 3;
   // `rot` (0 <= rot < nwarps) rotates the unit -> warp assignment so that products issued back to back spread over all warps
   const int nw = g.nwarps();
   int w0 = g.warp() - rot;
   if (w0 < 0) w0 += nw;
-  const int nunits = (FLAGS & MM_UP) ? (tm * (tm + 1)) / 2 : tm * gj;
+  int nunits = tm * gj;
+  if (FLAGS & MM_UP) { nunits = 0; for (int ti = 0; ti < tm; ++ti) nunits += tn - ((ti >> 1) << 1); }
   for (int unit = w0; unit < nunits; unit += nw) {
     int ti = 0, tj = unit;                                        // unit -> (tile row, tile column group) without divisions
-    if (FLAGS & MM_UP) { while (tj >= tn - ti) { tj -= tn - ti; ++ti; } tj += ti; }
+    if (FLAGS & MM_UP) { while (tj >= tn - ((ti >> 1) << 1)) { tj -= tn - ((ti >> 1) << 1); ++ti; } tj += (ti >> 1) << 1; }
     else if (gj == 1) { ti = unit; tj = 0; }
     else if (gj == 2) { ti = unit >> 1; tj = unit & 1; }
     else if (gj == 4) { ti = unit >> 2; tj = unit & 3; }
     else { while (tj >= gj) { tj -= gj; ++ti; } }
-    const int i0 = ti << 3, j0 = tj * TJ * 8;
+    const int t0 = tj * TJ;                                       // first tile column of the unit
     double acc[TJ][2], c0v[TJ][2];
-    const int i = i0 + r;
+    const int i = xT ? mm_col16(ti, r) : (ti << 3) + mm_rowperm(r);
     // the C0 operands are requested before the product loop so that their latency (HBM blocks) overlaps the tiles
 #pragma unroll
     for (int t = 0; t < TJ; ++t) {
       acc[t][0] = 0.0; acc[t][1] = 0.0;
-      const int j = j0 + 8 * t + 2 * q;
+      const int j = mm_col16(t0 + t, 2 * q);
       c0v[t][0] = (C0 && i < m && j < n) ? C0[i * ld0 + j] : 0.0;
       c0v[t][1] = (C0 && i < m && j + 1 < n) ? C0[i * ld0 + j + 1] : 0.0;
     }
     const bool iok = i < m;
     const double* xp = xT ? (X + i + q * ldx) : (X + i * ldx + q);     // advances by 4 rows (xT) / 4 columns per k-step
     const int xstep = xT ? 4 * ldx : 4;
-    const double* yp = Y + q * ldy + j0 + r;
+    int jb[TJ];                                                   // this lane's column of Y per tile
+#pragma unroll
+    for (int t = 0; t < TJ; ++t) jb[t] = mm_col16(t0 + t, r);
+    const double* yp = Y + q * ldy;
     for (int k0 = 0; k0 < k; k0 += 4, xp += xstep, yp += 4 * ldy) {
       const bool kok = (k0 + q) < k;
       double a;
@@ -212,16 +233,16 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
       else a = (iok && kok) ? *xp : 0.0;
 #pragma unroll
       for (int t = 0; t < TJ; ++t) {
-        if (j0 + 8 * t < n) {                     // warp-uniform
-          const double b = (kok && (j0 + 8 * t + r) < n) ? yp[8 * t] : 0.0;
+        if (t0 + t < tn) {                        // warp-uniform
+          const double b = (kok && jb[t] < n) ? yp[jb[t]] : 0.0;
           dmma884(acc[t][0], acc[t][1], a, b);
         }
       }
     }
 #pragma unroll
     for (int t = 0; t < TJ; ++t) {
-      const int j = j0 + 8 * t + 2 * q;
-      if (i < m && j0 + 8 * t < n) {
+      const int j = mm_col16(t0 + t, 2 * q);
+      if (i < m && t0 + t < tn) {
         if (j < n) C[i * ldc + j] = c0v[t][0] + alpha * acc[t][0];
         if (j + 1 < n) C[i * ldc + j + 1] = c0v[t][1] + alpha * acc[t][1];
       }
@@ -230,7 +251,7 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
 #else
   QM_PFOR(g, idx, m * n) {
     const int i = idx / n, j = idx % n;
-    if ((FLAGS & MM_UP) && (j >> 3) < (i >> 3)) continue;
+    if ((FLAGS & MM_UP) && (j >> 4) < (i >> 4)) continue;
     double acc = 0.0;
     for (int kk = 0; kk < k; ++kk) {
       double xv;
