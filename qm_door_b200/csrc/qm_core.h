@@ -116,13 +116,16 @@ QM_HD void status_or(int* p, int v) {
 #endif
 }
 
+QM_HD int mm_rowperm(int r) { return ((r & 3) << 1) | (r >> 2); }     // {0,2,4,6,1,3,5,7}: see the bank-conflict note at mm
+
 // out(r, init(r) + sum_{j < len} term(r, j)) for r < nrows. Device: four lanes per row, partial sums combined with
 // shuffles (the group size is a multiple of 32); host: one loop.
 template <class G, class FI, class FT, class FO>
 QM_HDN void rows_dot(G g, int nrows, int len, FI init, FT term, FO out) {
 #if defined(__CUDA_ARCH__)
   for (int base = 0; base < 4 * nrows; base += g.nt()) {
-    const int t = base + g.tid(), r = t >> 2, part = t & 3;
+    const int t = base + g.tid(), rl = t >> 2, part = t & 3;
+    const int r = (rl & ~7) | mm_rowperm(rl & 7);      // rows two apart within a half warp: no bank conflicts at row stride 30 / 18
     const bool valid = r < nrows;
     double acc = 0.0;
     if (valid) for (int j = part; j < len; j += 4) acc += term(r, j);
@@ -178,7 +181,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 //     16 g + {0,1,8,9,2,3,10,11} and 16 g + {4,5,12,13,6,7,14,15}  (the four k-rows of a step then interleave cleanly).
 // Each lane still writes two adjacent output elements.
 enum { MM_UP = 1, MM_XSYM = 2 };
-QM_HD int mm_rowperm(int r) { return ((r & 3) << 1) | (r >> 2); }
 QM_HD int mm_col16(int tile, int c) {      // matrix column of tile-column c (0..7) of tile `tile` (two tiles per 16 columns)
   const int p = c >> 1;
   return ((tile >> 1) << 4) + (((p & 1) << 3) | ((p >> 1) << 1) | ((tile & 1) << 2)) + (c & 1);
