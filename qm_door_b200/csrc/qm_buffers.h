@@ -214,11 +214,20 @@ QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out,
   const int NMAX = m.NMAX, nn = m.nn[b];
   const double alpha = m.ls[(size_t)b * LS_SIZE + LS_ALPHA];
   const size_t o = (size_t)b * NMAX;
+  constexpr int NB = 8;                      // nodes per batch: the loads of a batch are issued before its stores
   if (c < 30) {
-    for (int k = 0; k < nn; ++k) {
-      const double v = m.xs[(o + k) * 30 + c] + alpha * m.dxs[(o + k) * 30 + c];
-      m.xs[(o + k) * 30 + c] = v; m.prev_x[(o + k) * 30 + c] = v;
-      if (x_out) x_out[(o + k) * 30 + c] = v;
+    for (int k0 = 0; k0 < nn; k0 += NB) {
+      double v[NB];
+      QM_UNROLL
+      for (int j = 0; j < NB; ++j) { const int k = (k0 + j < nn) ? k0 + j : nn - 1; v[j] = m.xs[(o + k) * 30 + c] + alpha * m.dxs[(o + k) * 30 + c]; }
+      QM_UNROLL
+      for (int j = 0; j < NB; ++j) {
+        const int k = k0 + j;
+        if (k < nn) {
+          m.xs[(o + k) * 30 + c] = v[j]; m.prev_x[(o + k) * 30 + c] = v[j];
+          if (x_out) x_out[(o + k) * 30 + c] = v[j];
+        }
+      }
     }
     if (c == 0) {
       for (int k = 0; k < nn; ++k) { m.prev_t[o + k] = m.node_ts[o + k]; if (t_out) t_out[o + k] = m.node_ts[o + k]; }
@@ -227,14 +236,26 @@ QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out,
   } else {
     const int cu = c - 30;
     double last = 0.0;
-    for (int k = 0; k < nn; ++k) {
-      double v;
-      if (k == nn - 1) v = last;                                   // repeat the last input
-      else if (m.node_flag[o + k] == EV_PRE && k > 0) v = last;    // pre-event node repeats the previous input
-      else v = m.us[(o + k) * 30 + cu] + alpha * m.dus[(o + k) * 30 + cu];
-      m.us[(o + k) * 30 + cu] = v; m.prev_u[(o + k) * 30 + cu] = v;
-      if (u_out) u_out[(o + k) * 30 + cu] = v;
-      last = v;
+    for (int k0 = 0; k0 < nn; k0 += NB) {
+      double v[NB]; int fl[NB];
+      QM_UNROLL
+      for (int j = 0; j < NB; ++j) {
+        const int k = (k0 + j < nn) ? k0 + j : nn - 1;
+        v[j] = m.us[(o + k) * 30 + cu] + alpha * m.dus[(o + k) * 30 + cu]; fl[j] = m.node_flag[o + k];
+      }
+      QM_UNROLL
+      for (int j = 0; j < NB; ++j) {
+        const int k = k0 + j;
+        if (k < nn) {
+          double w;
+          if (k == nn - 1) w = last;                                   // repeat the last input
+          else if (fl[j] == EV_PRE && k > 0) w = last;                 // pre-event node repeats the previous input
+          else w = v[j];
+          m.us[(o + k) * 30 + cu] = w; m.prev_u[(o + k) * 30 + cu] = w;
+          if (u_out) u_out[(o + k) * 30 + cu] = w;
+          last = w;
+        }
+      }
     }
   }
 }

@@ -101,6 +101,11 @@ struct BlockGroup {
   __device__ __forceinline__ int nwarps() const { return blockDim.x >> 5; }
 };
 #endif
+#if defined(__CUDA_ARCH__)
+#define QM_UNROLL _Pragma("unroll")
+#else
+#define QM_UNROLL
+#endif
 #define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())
 // two-level loop without index division: rows over the warps of the group, columns over the lanes
 #define QM_PFOR2(g, i, ni, c, nc)                                              \

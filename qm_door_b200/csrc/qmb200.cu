@@ -52,11 +52,23 @@ __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_sol
 
 __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
                                                     const qmb200_solver_desc* S) {
+  // the schedule arrays and the previous solution's time grid are staged in shared memory: the per-component loop over
+  // the nodes then only waits for the two warm-start loads of each node
+  extern __shared__ __align__(16) double smem[];
   const int b = m.b0 + blockIdx.x, c = threadIdx.x;
+  const int NMAX = m.NMAX;
+  const size_t o = (size_t)b * NMAX;
+  double* s_t = smem; double* s_ts = smem + NMAX; double* s_dt = smem + 2 * NMAX; double* s_pt = smem + 3 * NMAX;
+  int* s_flag = (int*)(smem + 4 * NMAX); int* s_mode = s_flag + NMAX;
+  const int nn = m.nn[b], np = m.nprev[b];
+  for (int i = threadIdx.x; i < NMAX; i += blockDim.x) {
+    s_t[i] = (i < nn) ? m.node_t[o + i] : 0.0; s_ts[i] = (i < nn) ? m.node_ts[o + i] : 0.0; s_dt[i] = (i < nn) ? m.node_dt[o + i] : 0.0;
+    s_pt[i] = (i < np) ? m.prev_t[o + i] : 0.0;
+    s_flag[i] = (i < nn) ? m.node_flag[o + i] : 0; s_mode[i] = (i < nn) ? m.node_mode[o + i] : 0;
+  }
+  __syncthreads();
   if (c >= 60) return;
-  const size_t o = (size_t)b * m.NMAX;
-  init_guess_component(*M, *P, S->weak_eps, c, m.x0 + 30 * b, m.nn[b], m.node_t + o, m.node_flag + o, m.node_ts + o,
-                       m.node_dt + o, m.node_mode + o, m.nprev[b], m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30,
+  init_guess_component(*M, *P, S->weak_eps, c, m.x0 + 30 * b, nn, s_t, s_flag, s_ts, s_dt, s_mode, np, s_pt, m.prev_x + o * 30, m.prev_u + o * 30,
                        m.xs + o * 30, m.us + o * 30);
 }
 
@@ -244,8 +256,10 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
 
 // line-search evaluation: a thread per node (value-only single-pass tree walk in registers, qm_value.h)
 constexpr int kTrialThreads = 128;
-__global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
-  const int k = blockIdx.x * kTrialThreads + threadIdx.x, b = m.b0 + blockIdx.y;
+__global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
+                                                          const int* list) {
+  // first trial: every problem of the chunk; backtracking trials: only the problems k_decide listed as still pending
+  const int k = blockIdx.x * kTrialThreads + threadIdx.x, b = list ? list[m.b0 + blockIdx.y] : m.b0 + blockIdx.y;
   const double* ls = m.ls + (size_t)b * LS_SIZE;
   if (ls[LS_DONE] != 0.0) return;
   const int nn = m.nn[b];
@@ -275,11 +289,11 @@ __global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb
   out[PF_COST] = pf[PF_COST]; out[PF_DYN] = pf[PF_DYN]; out[PF_EQ] = pf[PF_EQ];
 }
 
-__global__ void __launch_bounds__(128) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending) {
+__global__ void __launch_bounds__(128) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending, int* list) {
   const int b = m.b0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= m.b0 + m.nb) return;
   decide_problem(*S, m, b);
-  if (m.ls[(size_t)b * LS_SIZE + LS_DONE] == 0.0) atomicAdd(pending, 1);
+  if (m.ls[(size_t)b * LS_SIZE + LS_DONE] == 0.0) list[m.b0 + atomicAdd(pending, 1)] = b;   // order only affects scheduling
 }
 
 __global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out) {
@@ -314,6 +328,7 @@ struct qmb200_ctx {
   qmb200_solver_desc* dS = nullptr;
   MpcBuffers m;          // ctx-owned device buffers
   int* d_pending = nullptr;   // [kMaxChunks]
+  int* d_list = nullptr;      // [B] problems still backtracking, compacted per chunk
   int* h_pending = nullptr;   // pinned, [kMaxChunks]
   cudaStream_t stream = nullptr;
   // The cycle can be pipelined over chunks of problems, one stream per chunk, so that the (latency-bound, few CTAs) Riccati
@@ -371,15 +386,15 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     const int nb = m.nb;
     CUDA_OK(cudaStreamWaitEvent(st, c->ev_start, 0));
     { KernelTimer kt(c, KN_SCHEDULE, st); k_schedule<<<(nb + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
-    { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, 0, st>>>(m, c->dM, c->dP, c->dS); }
+    { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, (size_t)NMAX * 40, st>>>(m, c->dM, c->dP, c->dS); }
     { KernelTimer kt(c, KN_KIN1, st); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_PROJ, st); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, nb), 32 * kProjWarps, 0, st>>>(m); }
     { KernelTimer kt(c, KN_KIN2, st); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
     CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
-    { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, nb), kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
-    { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch); }
+    { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, nb), kTrialThreads, 0, st>>>(m, c->dM, c->dP, nullptr); }
+    { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
     CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   CUDA_OK(cudaGetLastError());
@@ -393,10 +408,11 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     const int nb = m.nb;
     for (int it = 1; it < max_iters; ++it) {
       CUDA_OK(cudaStreamSynchronize(st));
-      if (c->h_pending[ch] == 0) break;
+      const int npend = c->h_pending[ch];
+      if (npend == 0) break;
       CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
-      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, nb), kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
-      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch); }
+      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, npend), kTrialThreads, 0, st>>>(m, c->dM, c->dP, c->d_list); }
+      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
       CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     { KernelTimer kt(c, KN_FINALIZE, st); k_finalize<<<nb, 64, 0, st>>>(m, t_out, x_out, u_out); }
@@ -463,6 +479,7 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   if (err != cudaSuccess) { qmb200_destroy(c); return fail(std::string("qmb200_create: device allocation failed: ") + cudaGetErrorString(err)); }
   c->bytes = total;
   CUDA_OK(cudaMalloc(&c->d_pending, sizeof(int) * qmb200_ctx::kMaxChunks));
+  CUDA_OK(cudaMalloc(&c->d_list, sizeof(int) * (size_t)batch));
   CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int) * qmb200_ctx::kMaxChunks));
   CUDA_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
@@ -483,6 +500,7 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->dP) cudaFree(c->dP);
   if (c->dS) cudaFree(c->dS);
   if (c->d_pending) cudaFree(c->d_pending);
+  if (c->d_list) cudaFree(c->d_list);
   if (c->h_pending) cudaFreeHost(c->h_pending);
   for (int ch = 0; ch < qmb200_ctx::kMaxChunks; ++ch) {
     if (c->cs[ch]) { cudaStreamSynchronize(c->cs[ch]); cudaStreamDestroy(c->cs[ch]); }
