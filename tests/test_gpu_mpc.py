@@ -121,6 +121,27 @@ def test_idempotent_and_reset(descs):
     ctx.close()
 
 
+def test_chunked_pipeline_is_bit_identical(descs, monkeypatch):
+    """QMB200_CHUNKS > 1 pipelines the cycle over chunks of problems on separate streams (ragged last chunk included);
+    problems are independent, so every output must be bit-identical to the single-chunk run, backtracking included."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    W = workload.Workload(37, horizon=0.3, dt=0.01, seed=11)
+    outs = []
+    for chunks in ("1", "4"):
+        monkeypatch.setenv("QMB200_CHUNKS", chunks)
+        ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+        res = []
+        for c in range(3):
+            o = ctx.cycle(np.full(W.B, 0.01 * c), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+            res.append({k: np.array(v, copy=True) for k, v in o.items()})
+        outs.append(res)
+        ctx.close()
+    for a, b in zip(*outs):
+        for key in ("t", "x", "u", "n", "mode", "info", "status"):
+            assert np.array_equal(a[key], b[key]), key
+
+
 def test_device_pointer_entry_matches_host_entry(descs):
     import torch
     import qm_door_b200 as q
