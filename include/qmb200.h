@@ -11,6 +11,9 @@
  *                                       (QMController.cpp:316-333, :119-122)
  *   qmb200_mpc_reset                 <- coldStart / resetMpcNode semantics (task.info:143)
  *   qmb200_evaluate_policy_batch     <- MPC_MRT_Interface::evaluatePolicy (QMController.cpp:140-143)
+ *   qmb200_rbd_to_state_batch[_dev]  <- CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel + yaw unwrapping in
+ *                                       QMController::updateStateEstimation (QMController.cpp:239-244); rbd layout of
+ *                                       qm_estimation/src/StateEstimateBase.cpp:29-102
  *   qmb200_load_urdf                 <- centroidal_model::createPinocchioInterface(urdf, jointNames) (QMInterface.cpp:408-416)
  *   qmb200_load_problem              <- loadData / loadEigenMatrix calls on task.info and reference.info
  *                                       (QMInterface.cpp:65-73,85,152-156,199-234,291,306,395-397)
@@ -77,6 +80,12 @@ int qmb200_mpc_cycle_batch_dev(qmb200_ctx* ctx, const double* t0, const double* 
 
 /* Linear interpolation of the stored policy at t[B] (host buffers): x_des[B][30], u_des[B][30], mode[B]. */
 int qmb200_evaluate_policy_batch(qmb200_ctx* ctx, const double* t, double* x_des, double* u_des, int32_t* mode);
+
+/* Measured rbd state rbd[n][55] -> MPC state x_out[n][30] = [A(q) v / m; base position; zyx; joints]. yaw_last[n] (may be
+ * NULL): previous yaw per state; when given, x[9] = yaw_last + shortest_angular_distance(yaw_last, yaw). n need not equal the
+ * context's batch. Host buffers / device pointers (on the context's stream) respectively. */
+int qmb200_rbd_to_state_batch(qmb200_ctx* ctx, int32_t n, const double* rbd, const double* yaw_last, double* x_out);
+int qmb200_rbd_to_state_batch_dev(qmb200_ctx* ctx, int32_t n, const double* rbd, const double* yaw_last, double* x_out);
 
 /* Kernel timing (CUDA events on the context's stream): accumulated ms and launch counts per kernel since the last reset. */
 int qmb200_set_profiling(qmb200_ctx* ctx, int32_t enable);

@@ -133,3 +133,27 @@ def ee_error(model, x, pos_ref, quat_ref):
     e_pos = nk["ee_pos"] - pos_ref
     e_ori = quat_distance(quat_from_matrix(nk["ee_rot"]), quat_ref)
     return np.concatenate([e_pos, e_ori], axis=-1)
+
+
+def state_from_rbd(model, rbd_state, yaw_last=None):
+    """[upstream] CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel as called from
+    QMController::updateStateEstimation (qm_controllers/src/QMController.cpp:239-243) and the yaw unwrapping of :244.
+    rbd_state[55]: estimator layout (qm_estimation/src/StateEstimateBase.cpp:29-102)."""
+    r = np.asarray(rbd_state, dtype=float)
+    q = np.concatenate([r[3:6], r[0:3], r[6:24]])
+    yaw, pitch = q[3], q[4]
+    # world angular velocity = T(euler) d/dt[yaw, pitch, roll]  ([upstream] getEulerAnglesZyxDerivativesFromGlobalAngularVelocity)
+    T = np.array([[0.0, -np.sin(yaw), np.cos(yaw) * np.cos(pitch)],
+                  [0.0, np.cos(yaw), np.sin(yaw) * np.cos(pitch)],
+                  [1.0, 0.0, -np.sin(pitch)]])
+    v = np.concatenate([r[27:30], np.linalg.solve(T, r[24:27]), r[30:48]])
+    kin = rbd.kinematics(model, q)
+    A, _ = rbd.centroidal_momentum_matrix(model, kin)
+    x = np.concatenate([A @ v / model.total_mass, q])
+    if yaw_last is not None:
+        d = np.fmod(np.fmod(x[9] - yaw_last, 2 * np.pi) + 2 * np.pi, 2 * np.pi)     # angles::shortest_angular_distance
+        if d > np.pi:
+            d -= 2 * np.pi
+        x[9] = yaw_last + d
+    return x
+

@@ -47,6 +47,12 @@ void cport_transcribe_node(const qmb200_model_desc* M, const qmb200_problem_desc
   transcribe_node(SerialGroup(), *M, *P, t, dt, mode, zvel, tt, ts, kt, x, u, xn, W, WI, sb, pb, perf, status);
 }
 
+void cport_rbd_to_state(const qmb200_model_desc* M, int n, const double* rbd, const double* yaw_last, double* x_out) {
+  std::vector<double> kw(KW_SIZE), qv(48);
+  for (int b = 0; b < n; ++b)
+    centroidal_state_from_rbd(SerialGroup(), *M, rbd + 55 * b, yaw_last ? yaw_last[b] : 0.0, yaw_last != nullptr, kw.data(), qv.data(), x_out + 30 * b);
+}
+
 CportCtx* cport_create(const qmb200_model_desc* M, const qmb200_problem_desc* P, const qmb200_solver_desc* S, int B, int threads) {
   CportCtx* c = new CportCtx();
   c->M = *M; c->P = *P; c->S = *S; c->threads = threads;

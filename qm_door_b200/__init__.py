@@ -139,6 +139,15 @@ class MpcContext:
         _check(self.L.qmb200_evaluate_policy_batch(self.h, _p(t), _p(x), _p(u), _p(mode)))
         return x, u, mode
 
+    def rbd_to_state(self, rbd, yaw_last=None):
+        """Measured rbdState [n][55] -> MPC state [n][30] (QMController.cpp:239-244); yaw_last enables the yaw unwrapping."""
+        rbd = np.ascontiguousarray(rbd, dtype=np.float64)
+        n = rbd.shape[0]
+        x = np.zeros((n, 30))
+        yl = None if yaw_last is None else np.ascontiguousarray(yaw_last, dtype=np.float64)
+        _check(self.L.qmb200_rbd_to_state_batch(self.h, n, _p(rbd), _p(yl), _p(x)))
+        return x
+
     def set_profiling(self, on):
         _check(self.L.qmb200_set_profiling(self.h, int(bool(on))))
 

@@ -217,6 +217,49 @@ QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_proble
   }
 }
 
+// ------------------------------------------------------------------------------------------ measured state -> MPC state
+// [upstream] CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel as called from
+// QMController::updateStateEstimation (qm_controllers/src/QMController.cpp:239-243), followed by the yaw unwrapping of the
+// same function (:244, angles::shortest_angular_distance). rbd[55] is the estimator's layout
+// (qm_estimation/src/StateEstimateBase.cpp:29-102): [zyx(3); base position(3); joints(18); world angular velocity(3);
+// base linear velocity(3); joint velocities(18); arm end-effector pose(7, unused here)].
+// x = [A(q) v / m (6); base position; zyx; joints]. kw: kinematics workspace (value level, KW_VSIZE doubles); qv: 48 doubles.
+template <class G>
+QM_HDN void centroidal_state_from_rbd(G g, const qmb200_model_desc& M, const double* rbd, double yaw_last, int unwrap,
+                                      double* kw, double* qv, double* x_out) {
+  if (g.tid() == 0) {
+    for (int k = 0; k < 3; ++k) { qv[k] = rbd[3 + k]; qv[3 + k] = rbd[k]; qv[24 + k] = rbd[27 + k]; }
+    for (int k = 0; k < 18; ++k) { qv[6 + k] = rbd[6 + k]; qv[30 + k] = rbd[30 + k]; }
+    // [upstream] getEulerAnglesZyxDerivativesFromGlobalAngularVelocity
+    double sz, cz, sy, cy;
+    sincos(qv[3], &sz, &cz); sincos(qv[4], &sy, &cy);
+    const double wx = rbd[24], wy = rbd[25], wz = rbd[26];
+    const double dxr = (cz * wx + sz * wy) / cy;
+    qv[24 + 3] = wz + sy * dxr;
+    qv[24 + 4] = -sz * wx + cz * wy;
+    qv[24 + 5] = dxr;
+  }
+  g.sync();
+  kin_positions(g, M, qv, kw, false);
+  QM_PFOR(g, r, 6) {
+    double acc = 0.0;
+    for (int k = 0; k < QM_NJ; ++k) acc += kw[KW_ACM + r * QM_NJ + k] * qv[24 + k];
+    x_out[r] = acc / M.total_mass;
+  }
+  QM_PFOR(g, k, QM_NJ) {
+    double v = qv[k];
+    if (k == 3 && unwrap) {
+      // angles::shortest_angular_distance(from, to) = normalize_angle(to - from), normalize_angle -> (-pi, pi]
+      const double two_pi = 6.283185307179586476925286766559, pi = 3.14159265358979323846;
+      double a = fmod(fmod(v - yaw_last, two_pi) + two_pi, two_pi);
+      if (a > pi) a -= two_pi;
+      v = yaw_last + a;
+    }
+    x_out[6 + k] = v;
+  }
+  g.sync();
+}
+
 // ------------------------------------------------------------------------------------------ flow map rows
 // f (30) and, if Fr != nullptr, the nine non-trivial rows (f rows 3..11) of [df/dx | df/du] as Fr[9][60].
 template <class G>

@@ -316,6 +316,19 @@ __global__ void __launch_bounds__(64) k_policy(MpcBuffers m, const double* t, do
   if (c == 0) mode[b] = m.modes[(size_t)b * (m.EMAX + 1) + mode_index(m.events + (size_t)b * m.EMAX, m.nevents[b], t[b])];
 }
 
+// [upstream] computeCentroidalStateFromRbdModel + yaw unwrapping (QMController.cpp:239-244): warp per measured state.
+constexpr int kStateWarps = 4;
+constexpr int kStateWarpDoubles = KW_VSIZE + 48;
+__global__ void __launch_bounds__(32 * kStateWarps) k_rbd_state(int B, const qmb200_model_desc* M, const double* rbd, const double* yaw_last,
+                                                                 double* x_out) {
+  const int b = blockIdx.x * kStateWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  extern __shared__ __align__(16) double smem[];
+  double* kw = smem + (size_t)(threadIdx.x >> 5) * kStateWarpDoubles;
+  centroidal_state_from_rbd(WarpGroup(), *M, rbd + 55 * (size_t)b, yaw_last ? yaw_last[b] : 0.0, yaw_last != nullptr, kw, kw + KW_VSIZE,
+                            x_out + 30 * (size_t)b);
+}
+
 // ------------------------------------------------------------------------------------------ context
 struct qmb200_ctx {
   int device = 0;
@@ -484,6 +497,7 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   CUDA_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(k_rbd_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStateWarps * kStateWarpDoubles * sizeof(double))));
   CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
   *out = c;
   return 0;
@@ -606,6 +620,34 @@ int qmb200_mpc_cycle_batch(qmb200_ctx* c, const double* t0, const double* x0, co
   if (status) CUDA_OK(cudaMemcpyAsync(status, m.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   harvest_events(c);
+  return 0;
+}
+
+int qmb200_rbd_to_state_batch_dev(qmb200_ctx* c, int32_t n, const double* rbd, const double* yaw_last, double* x_out) {
+  if (!c || !rbd || !x_out || n <= 0) return fail("qmb200_rbd_to_state_batch_dev: bad argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t smem = (size_t)kStateWarps * kStateWarpDoubles * sizeof(double);
+  k_rbd_state<<<(n + kStateWarps - 1) / kStateWarps, 32 * kStateWarps, smem, c->stream>>>(n, c->dM, rbd, yaw_last, x_out);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int qmb200_rbd_to_state_batch(qmb200_ctx* c, int32_t n, const double* rbd, const double* yaw_last, double* x_out) {
+  if (!c || !rbd || !x_out || n <= 0) return fail("qmb200_rbd_to_state_batch: bad argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  double *d_rbd = nullptr, *d_yaw = nullptr, *d_x = nullptr;
+  CUDA_OK(cudaMallocAsync(&d_rbd, sizeof(double) * 55 * (size_t)n, c->stream));
+  CUDA_OK(cudaMallocAsync(&d_x, sizeof(double) * 30 * (size_t)n, c->stream));
+  CUDA_OK(cudaMemcpyAsync(d_rbd, rbd, sizeof(double) * 55 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  if (yaw_last) {
+    CUDA_OK(cudaMallocAsync(&d_yaw, sizeof(double) * (size_t)n, c->stream));
+    CUDA_OK(cudaMemcpyAsync(d_yaw, yaw_last, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (qmb200_rbd_to_state_batch_dev(c, n, d_rbd, d_yaw, d_x) != 0) return -1;
+  CUDA_OK(cudaMemcpyAsync(x_out, d_x, sizeof(double) * 30 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaFreeAsync(d_rbd, c->stream)); CUDA_OK(cudaFreeAsync(d_x, c->stream));
+  if (d_yaw) CUDA_OK(cudaFreeAsync(d_yaw, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -87,6 +87,43 @@ def test_fresh_cycle_against_oracle_with_ee_target_motion(descs, oracle_inputs):
     cp.close()
 
 
+def _random_rbd(m, P, n, seed):
+    """Measured rbd states: nominal pose + perturbations, random generalized velocities, yaw spread over several turns."""
+    from oracle import wbc as owbc
+    rng = np.random.default_rng(seed)
+    out, xs, vs = [], [], []
+    for _ in range(n):
+        x = P.x_init + np.concatenate([np.zeros(6), 0.05 * rng.standard_normal(3), 0.2 * rng.standard_normal(3), 0.2 * rng.standard_normal(18)])
+        x[9] = rng.uniform(-3.1, 3.1)
+        v = rng.uniform(-0.5, 0.5, 24)
+        out.append(owbc.rbd_from_state(m, x, v)); xs.append(x); vs.append(v)
+    return np.array(out), np.array(xs), np.array(vs)
+
+
+def test_rbd_to_centroidal_state(descs, oracle_inputs):
+    """measured rbdState(55) -> MPC state(30) (QMController.cpp:239-244): CPU port against the oracle,
+    the round trip state -> rbd -> state, and the yaw unwrapping across +-pi."""
+    model, _, _, _ = descs
+    m, P = oracle_inputs
+    lib = abi_fill.load_cport()
+    dp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+    rbds, xs, vs = _random_rbd(m, P, 12, seed=3)
+    out = np.zeros((12, 30))
+    lib.cport_rbd_to_state(C.byref(model), 12, dp(rbds), None, dp(out))
+    for i in range(12):
+        ref = ce.state_from_rbd(m, rbds[i])
+        assert rel_l2(out[i], ref) < 1e-13
+        assert rel_l2(out[i, 6:], xs[i, 6:]) < 1e-14                        # generalized coordinates come back unchanged
+        A, _ = rbd.centroidal_momentum_matrix(m, rbd.kinematics(m, xs[i, 6:]))
+        assert rel_l2(out[i, :6], A @ vs[i] / m.total_mass) < 1e-12         # normalized centroidal momentum of (q, v)
+    yaw_last = xs[:, 9] + np.array([0.0, 6.0, -6.0, 12.5, -12.5, 3.0, -3.0, 0.1, -0.1, 6.2, -6.2, 100.0])
+    lib.cport_rbd_to_state(C.byref(model), 12, dp(rbds), dp(yaw_last), dp(out))
+    for i in range(12):
+        ref = ce.state_from_rbd(m, rbds[i], yaw_last[i])
+        assert abs(out[i, 9] - ref[9]) < 1e-12 and abs(out[i, 9] - yaw_last[i]) <= np.pi + 1e-12
+        assert abs(np.angle(np.exp(1j * (out[i, 9] - xs[i, 9])))) < 1e-9    # same angle modulo 2 pi
+
+
 def test_error_statuses(descs):
     """Schedules that do not cover the horizon / node-capacity overflow are flagged per problem, not crashed on."""
     model, problem, solver, x_init = descs

@@ -142,6 +142,34 @@ def test_chunked_pipeline_is_bit_identical(descs, monkeypatch):
             assert np.array_equal(a[key], b[key]), key
 
 
+def test_rbd_to_state_matches_oracle_and_round_trip(descs, oracle_inputs):
+    """SURVEY 8(f) rank 1 on the device: rbdState(55) -> MPC state(30), against the oracle on a subset and through the
+    round trip state -> rbd -> state on 4096 states; yaw unwrapping continuity."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    from oracle import centroidal as ce, wbc as owbc
+    m, P = oracle_inputs
+    W = workload.Workload(4, horizon=0.1, dt=0.01)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    rng = np.random.default_rng(21)
+    n = 4096
+    xs = P.x_init[None, :] + np.concatenate([np.zeros((n, 6)), 0.05 * rng.standard_normal((n, 3)), 0.2 * rng.standard_normal((n, 3)),
+                                             0.2 * rng.standard_normal((n, 18))], axis=1)
+    xs[:, 9] = rng.uniform(-3.1, 3.1, n)
+    vs = rng.uniform(-0.5, 0.5, (n, 24))
+    rbds = np.array([owbc.rbd_from_state(m, xs[i], vs[i]) for i in range(n)])
+    out = ctx.rbd_to_state(rbds)
+    assert np.abs(out[:, 6:] - xs[:, 6:]).max() < 1e-13
+    for i in range(0, n, 256):
+        assert rel_l2(out[i], ce.state_from_rbd(m, rbds[i])) < 1e-12
+    yaw_last = xs[:, 9] + rng.uniform(-20.0, 20.0, n)
+    out2 = ctx.rbd_to_state(rbds, yaw_last)
+    assert (np.abs(out2[:, 9] - yaw_last) <= np.pi + 1e-12).all()
+    assert np.abs(np.angle(np.exp(1j * (out2[:, 9] - xs[:, 9])))).max() < 1e-9
+    assert np.array_equal(out2[:, :9], out[:, :9]) and np.array_equal(out2[:, 10:], out[:, 10:])
+    ctx.close()
+
+
 def test_device_pointer_entry_matches_host_entry(descs):
     import torch
     import qm_door_b200 as q
