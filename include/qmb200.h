@@ -14,6 +14,8 @@
  *   qmb200_rbd_to_state_batch[_dev]  <- CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel + yaw unwrapping in
  *                                       QMController::updateStateEstimation (QMController.cpp:239-244); rbd layout of
  *                                       qm_estimation/src/StateEstimateBase.cpp:29-102
+ *   qmb200_targets_batch[_dev]       <- cmdVelToTargetTrajectories / EeCmdVelToTargetTrajectories / EEgoalPoseToTargetTrajectories
+ *                                       (qm_controllers/src/QmTargetTrajectoriesPublisher_node.cpp:60-257); qmb200_load_targets <- its main() (:268-272)
  *   qmb200_load_urdf                 <- centroidal_model::createPinocchioInterface(urdf, jointNames) (QMInterface.cpp:408-416)
  *   qmb200_load_problem              <- loadData / loadEigenMatrix calls on task.info and reference.info
  *                                       (QMInterface.cpp:65-73,85,152-156,199-234,291,306,395-397)
@@ -80,6 +82,18 @@ int qmb200_mpc_cycle_batch_dev(qmb200_ctx* ctx, const double* t0, const double* 
 
 /* Linear interpolation of the stored policy at t[B] (host buffers): x_des[B][30], u_des[B][30], mode[B]. */
 int qmb200_evaluate_policy_batch(qmb200_ctx* ctx, const double* t, double* x_des, double* u_des, int32_t* mode);
+
+/* Command -> two-knot reference (target_t[n][2], target_x[n][2][37] = [x_ref(30); ee position(3); ee quat xyzw(4)]), ready to be
+ * passed to qmb200_mpc_cycle_batch. kind: 0 base velocity command, 1 end-effector velocity command (cmd[n][7]: vx, vy, vz,
+ * yaw rate, 3 unused), 2 end-effector goal (cmd[n][7]: position, quat xyzw). obs_time[n], obs_state[n][30]: current observation;
+ * ee_state[n][7]: measured end-effector pose; last_ee_target[n][7]: the publisher's lastEeTarget_ (read and updated). */
+int qmb200_load_targets(const char* task_info, const char* reference_info, qmb200_target_desc* desc);
+int qmb200_targets_batch(qmb200_ctx* ctx, const qmb200_target_desc* desc, int32_t kind, int32_t n, const double* cmd,
+                         const double* obs_time, const double* obs_state, const double* ee_state, double* last_ee_target,
+                         double* target_t, double* target_x);
+int qmb200_targets_batch_dev(qmb200_ctx* ctx, const qmb200_target_desc* desc, int32_t kind, int32_t n, const double* cmd,
+                             const double* obs_time, const double* obs_state, const double* ee_state, double* last_ee_target,
+                             double* target_t, double* target_x);
 
 /* Measured rbd state rbd[n][55] -> MPC state x_out[n][30] = [A(q) v / m; base position; zyx; joints]. yaw_last[n] (may be
  * NULL): previous yaw per state; when given, x[9] = yaw_last + shortest_angular_distance(yaw_last, yaw). n need not equal the

@@ -313,6 +313,8 @@ def load_problem(task_path, reference_path, gait_path, model):
     P.time_horizon = float(get(t, "mpc.timeHorizon"))
     P.friction_wbc = float(get(t, "frictionConeTask.frictionCoefficient"))  # :347-350
     P.com_height = float(r["comHeight"])
+    P.target_displacement_velocity = float(r["targetDisplacementVelocity"])     # QmTargetTrajectoriesPublisher_node.cpp:268-272
+    P.target_rotation_velocity = float(r["targetRotationVelocity"])
     P.default_joint_state = load_matrix(r, "defaultJointState", 18, 1)[:, 0]
     P.gaits = {}
     P.gait_list = load_list(g, "list")

@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 #include "../../qm_door_b200/csrc/qm_buffers.h"
+#include "../../qm_door_b200/csrc/qm_target.h"
 
 using namespace qm;
 
@@ -45,6 +46,12 @@ void cport_transcribe_node(const qmb200_model_desc* M, const qmb200_problem_desc
                            const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
                            const double* xn, double* W, int* WI, double* sb, double* pb, double* perf, int* status) {
   transcribe_node(SerialGroup(), *M, *P, t, dt, mode, zvel, tt, ts, kt, x, u, xn, W, WI, sb, pb, perf, status);
+}
+
+void cport_targets(const qmb200_target_desc* D, int kind, int n, const double* cmd, const double* obs_time, const double* obs_state,
+                   const double* ee_state, double* last_ee, double* tt, double* tx) {
+  for (int b = 0; b < n; ++b)
+    command_to_target(*D, kind, cmd + 7 * b, obs_time[b], obs_state + 30 * b, ee_state + 7 * b, last_ee + 7 * b, tt + 2 * b, tx + 2 * QM_NTARGET * b);
 }
 
 void cport_rbd_to_state(const qmb200_model_desc* M, int n, const double* rbd, const double* yaw_last, double* x_out) {

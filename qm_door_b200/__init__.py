@@ -148,6 +148,18 @@ class MpcContext:
         _check(self.L.qmb200_rbd_to_state_batch(self.h, n, _p(rbd), _p(yl), _p(x)))
         return x
 
+    def targets(self, desc, kind, cmd, obs_time, obs_state, ee_state, last_ee_target):
+        """Command -> (target_t [n][2], target_x [n][2][37]) (QmTargetTrajectoriesPublisher_node.cpp:60-257); last_ee_target
+        [n][7] is updated in place. kind: 0 base cmd_vel, 1 ee cmd_vel, 2 ee goal; cmd [n][7]."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        cmd, obs_time, obs_state, ee_state = f(cmd), f(obs_time), f(obs_state), f(ee_state)
+        assert last_ee_target.dtype == np.float64 and last_ee_target.flags.c_contiguous
+        n = cmd.shape[0]
+        tt, tx = np.zeros((n, 2)), np.zeros((n, 2, 37))
+        _check(self.L.qmb200_targets_batch(self.h, C.byref(desc), int(kind), n, _p(cmd), _p(obs_time), _p(obs_state), _p(ee_state),
+                                           _p(last_ee_target), _p(tt), _p(tx)))
+        return tt, tx
+
     def set_profiling(self, on):
         _check(self.L.qmb200_set_profiling(self.h, int(bool(on))))
 
@@ -180,6 +192,14 @@ def load_problem(model, task_info=DEFAULT_TASK, reference_info=DEFAULT_REFERENCE
     _check(lib().qmb200_load_problem(task_info.encode(), reference_info.encode() if reference_info else None,
                                      C.byref(model), C.byref(p), C.byref(s), _p(x)))
     return p, s, x
+
+
+def load_targets(task_info=DEFAULT_TASK, reference_info=DEFAULT_REFERENCE):
+    """Constants of the command -> reference conversion (QmTargetTrajectoriesPublisher_node.cpp:268-272)."""
+    from ._abi import TargetDesc
+    d = TargetDesc()
+    _check(lib().qmb200_load_targets(task_info.encode(), reference_info.encode(), C.byref(d)))
+    return d
 
 
 def load_gait(name, gait_info=DEFAULT_GAIT, capacity=32):

@@ -82,6 +82,14 @@ class WbcDesc(C.Structure):
     ]
 
 
+class TargetDesc(C.Structure):
+    _fields_ = [
+        ("com_height", C.c_double), ("feet_height", C.c_double), ("arm_dist", C.c_double), ("time_to_target", C.c_double),
+        ("target_displacement_velocity", C.c_double), ("target_rotation_velocity", C.c_double),
+        ("default_joint_state", C.c_double * 18),
+    ]
+
+
 def _set(arr, values):
     a = np.ctypeslib.as_array(arr)
     a[...] = np.asarray(values).reshape(a.shape)

@@ -426,6 +426,23 @@ int qmb200_load_urdf(const char* urdf_path, qmb200_model_desc* model) {
   });
 }
 
+int qmb200_load_targets(const char* task_info, const char* reference_info, qmb200_target_desc* D) {
+  return guarded([&]() {
+    if (!task_info || !reference_info || !D) throw std::invalid_argument("qmb200_load_targets: null argument");
+    InfoNode t = parse_info(task_info);
+    InfoNode r = parse_info(reference_info);
+    memset(D, 0, sizeof(*D));
+    // QmTargetTrajectoriesPublisher_node.cpp:268-272
+    D->com_height = r.num("comHeight");
+    load_matrix(r, "defaultJointState", 18, 1, D->default_joint_state);
+    D->target_rotation_velocity = r.num("targetRotationVelocity");
+    D->target_displacement_velocity = r.num("targetDisplacementVelocity");
+    D->time_to_target = t.num("mpc.timeHorizon");
+    D->arm_dist = 0.6;         // qm_controllers/include/qm_controllers/StartingPosition.h:13
+    D->feet_height = 0.0;      // runtime value (feetHeightCallback, :28-35)
+  });
+}
+
 int qmb200_load_problem(const char* task_info, const char* reference_info, const qmb200_model_desc* M,
                         qmb200_problem_desc* P, qmb200_solver_desc* S, double* x_init) {
   return guarded([&]() {

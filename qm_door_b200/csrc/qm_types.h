@@ -72,6 +72,19 @@ typedef struct qmb200_solver_desc {
   int32_t reserved;
 } qmb200_solver_desc;
 
+// Command -> reference conversion constants. Replaces the file-scope globals of
+// qm_controllers/src/QmTargetTrajectoriesPublisher_node.cpp:18-25 (filled in its main(), :268-272) and ARM_DIST of
+// qm_controllers/include/qm_controllers/StartingPosition.h:13.
+typedef struct qmb200_target_desc {
+  double com_height;                     // reference.info comHeight
+  double feet_height;                    // mean z of the feet in contact (runtime topic, :28-35); 0 until set
+  double arm_dist;                       // base CoM to end-effector distance in the XY plane (0.6)
+  double time_to_target;                 // task.info mpc.timeHorizon
+  double target_displacement_velocity;   // reference.info targetDisplacementVelocity
+  double target_rotation_velocity;       // reference.info targetRotationVelocity
+  double default_joint_state[18];        // reference.info defaultJointState
+} qmb200_target_desc;
+
 // Whole-body-controller gains and limits. Defaults: qm_wbc/cfg/wbcWigeht.cfg:7-47 (delivered by WbcBase::dynamicCallback,
 // qm_wbc/src/WbcBase.cpp:74-121), torque limits and friction coefficient from WbcBase::loadTasksSetting (WbcBase.cpp:597-627).
 typedef struct qmb200_wbc_desc {

@@ -21,6 +21,7 @@
 #include <vector>
 #include "../../include/qmb200.h"
 #include "qm_buffers.h"
+#include "qm_target.h"
 
 using namespace qm;
 
@@ -314,6 +315,15 @@ __global__ void __launch_bounds__(64) k_policy(MpcBuffers m, const double* t, do
   if (c < 30) x_des[30 * b + c] = a * m.prev_x[(o + i) * 30 + c] + (1.0 - a) * m.prev_x[(o + i2) * 30 + c];
   else u_des[30 * b + c - 30] = a * m.prev_u[(o + i) * 30 + c - 30] + (1.0 - a) * m.prev_u[(o + i2) * 30 + c - 30];
   if (c == 0) mode[b] = m.modes[(size_t)b * (m.EMAX + 1) + mode_index(m.events + (size_t)b * m.EMAX, m.nevents[b], t[b])];
+}
+
+// Command -> two-knot reference (QmTargetTrajectoriesPublisher_node.cpp:60-257): thread per command.
+__global__ void __launch_bounds__(128) k_targets(int n, int kind, qmb200_target_desc D, const double* cmd, const double* obs_time,
+                                                 const double* obs_state, const double* ee_state, double* last_ee, double* tt, double* tx) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  command_to_target(D, kind, cmd + 7 * (size_t)b, obs_time[b], obs_state + 30 * (size_t)b, ee_state + 7 * (size_t)b, last_ee + 7 * (size_t)b,
+                    tt + 2 * (size_t)b, tx + 2 * QM_NTARGET * (size_t)b);
 }
 
 // [upstream] computeCentroidalStateFromRbdModel + yaw unwrapping (QMController.cpp:239-244): warp per measured state.
@@ -620,6 +630,39 @@ int qmb200_mpc_cycle_batch(qmb200_ctx* c, const double* t0, const double* x0, co
   if (status) CUDA_OK(cudaMemcpyAsync(status, m.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   harvest_events(c);
+  return 0;
+}
+
+int qmb200_targets_batch_dev(qmb200_ctx* c, const qmb200_target_desc* desc, int32_t kind, int32_t n, const double* cmd,
+                             const double* obs_time, const double* obs_state, const double* ee_state, double* last_ee_target,
+                             double* target_t, double* target_x) {
+  if (!c || !desc || !cmd || !obs_time || !obs_state || !ee_state || !last_ee_target || !target_t || !target_x || n <= 0)
+    return fail("qmb200_targets_batch_dev: bad argument");
+  if (kind < 0 || kind > 2) return fail("qmb200_targets_batch_dev: kind must be 0 (base cmd_vel), 1 (ee cmd_vel) or 2 (ee goal)");
+  CUDA_OK(cudaSetDevice(c->device));
+  k_targets<<<(n + 127) / 128, 128, 0, c->stream>>>(n, kind, *desc, cmd, obs_time, obs_state, ee_state, last_ee_target, target_t, target_x);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int qmb200_targets_batch(qmb200_ctx* c, const qmb200_target_desc* desc, int32_t kind, int32_t n, const double* cmd,
+                         const double* obs_time, const double* obs_state, const double* ee_state, double* last_ee_target,
+                         double* target_t, double* target_x) {
+  if (!c || !desc || !cmd || !obs_time || !obs_state || !ee_state || !last_ee_target || !target_t || !target_x || n <= 0)
+    return fail("qmb200_targets_batch: bad argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t N = (size_t)n;
+  const size_t sizes[7] = {7 * N, N, 30 * N, 7 * N, 7 * N, 2 * N, 2 * QM_NTARGET * N};
+  const double* src[5] = {cmd, obs_time, obs_state, ee_state, last_ee_target};
+  double* d[7] = {nullptr};
+  for (int i = 0; i < 7; ++i) CUDA_OK(cudaMallocAsync(&d[i], sizeof(double) * sizes[i], c->stream));
+  for (int i = 0; i < 5; ++i) CUDA_OK(cudaMemcpyAsync(d[i], src[i], sizeof(double) * sizes[i], cudaMemcpyHostToDevice, c->stream));
+  if (qmb200_targets_batch_dev(c, desc, kind, n, d[0], d[1], d[2], d[3], d[4], d[5], d[6]) != 0) return -1;
+  CUDA_OK(cudaMemcpyAsync(last_ee_target, d[4], sizeof(double) * sizes[4], cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(target_t, d[5], sizeof(double) * sizes[5], cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(target_x, d[6], sizeof(double) * sizes[6], cudaMemcpyDeviceToHost, c->stream));
+  for (int i = 0; i < 7; ++i) CUDA_OK(cudaFreeAsync(d[i], c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

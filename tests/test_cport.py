@@ -124,6 +124,53 @@ def test_rbd_to_centroidal_state(descs, oracle_inputs):
         assert abs(np.angle(np.exp(1j * (out[i, 9] - xs[i, 9])))) < 1e-9    # same angle modulo 2 pi
 
 
+def _target_cases(P, n, seed):
+    rng = np.random.default_rng(seed)
+    obs_state = np.tile(P.x_init, (n, 1)) + 0.1 * rng.standard_normal((n, 30))
+    obs_state[:, 9] = rng.uniform(-3.0, 3.0, n)
+    obs_time = rng.uniform(0.0, 50.0, n)
+    quat = rng.standard_normal((n, 4)); quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    ee_state = np.concatenate([obs_state[:, 6:9] + rng.uniform(-0.5, 0.8, (n, 3)), quat], axis=1)
+    last = ee_state + np.concatenate([rng.choice([0.01, 0.3], (n, 1)) * rng.standard_normal((n, 3)), 0.05 * rng.standard_normal((n, 4))], axis=1)
+    cmd = np.zeros((n, 7))
+    return rng, obs_time, obs_state, ee_state, last, cmd
+
+
+def test_command_to_target_trajectories(descs, oracle_inputs):
+    """velocity commands / end-effector goals -> two-knot reference
+    (QmTargetTrajectoriesPublisher_node.cpp:60-257): loader against the oracle's parse, CPU port against the oracle for the
+    three converters (lastEeTarget_ state included), and the invariants of the reference layout."""
+    import qm_door_b200 as q
+    from oracle import targets as ot
+    m, P = oracle_inputs
+    D = q.load_targets()
+    tp = ot.TargetParams(P)
+    assert D.com_height == tp.com_height and D.time_to_target == tp.time_to_target and D.arm_dist == ot.ARM_DIST
+    assert D.target_displacement_velocity == tp.target_displacement_velocity and D.target_rotation_velocity == tp.target_rotation_velocity
+    assert np.array_equal(np.ctypeslib.as_array(D.default_joint_state), tp.default_joint_state)
+    lib = abi_fill.load_cport()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    n = 16
+    for kind in range(3):
+        rng, obs_time, obs_state, ee_state, last, cmd = _target_cases(P, n, seed=40 + kind)
+        if kind < 2:
+            cmd[:, :4] = rng.uniform(-0.5, 0.5, (n, 4))
+        else:
+            g = rng.standard_normal((n, 4)); g /= np.linalg.norm(g, axis=1, keepdims=True)
+            cmd[:] = np.concatenate([ee_state[:, :3] + rng.uniform(-0.3, 0.3, (n, 3)), g], axis=1)
+        last_c = last.copy()
+        tt, tx = np.zeros((n, 2)), np.zeros((n, 2, 37))
+        lib.cport_targets(C.byref(D), kind, n, dp(cmd), dp(obs_time), dp(obs_state), dp(ee_state), dp(last_c), dp(tt), dp(tx))
+        for i in range(n):
+            lo = last[i].copy()
+            rt, rx = ot.CONVERTERS[kind](tp, cmd[i], lo, obs_time[i], obs_state[i], ee_state[i])
+            assert np.abs(tt[i] - rt).max() < 1e-12 and np.abs(tx[i] - rx).max() < 1e-12
+            assert np.abs(last_c[i] - lo).max() == 0.0
+            assert tt[i, 0] == obs_time[i] and tt[i, 1] > tt[i, 0]
+            assert np.array_equal(tx[i, :, 12:30], np.tile(tp.default_joint_state, (2, 1)))      # joints: default posture
+            assert (tx[i, :, 8] == tp.com_height).all() and (tx[i, :, 10:12] == 0).all()          # height, pitch / roll
+
+
 def test_error_statuses(descs):
     """Schedules that do not cover the horizon / node-capacity overflow are flagged per problem, not crashed on."""
     model, problem, solver, x_init = descs

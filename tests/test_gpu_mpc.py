@@ -170,6 +170,47 @@ def test_rbd_to_state_matches_oracle_and_round_trip(descs, oracle_inputs):
     ctx.close()
 
 
+def test_command_to_target_on_device(descs, oracle_inputs):
+    """SURVEY 8(f) rank 2 on the device: the three command converters against the oracle, and the produced reference fed
+    straight into an MPC cycle."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    from oracle import targets as ot
+    m, P = oracle_inputs
+    W = workload.Workload(8, horizon=0.2, dt=0.01)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    D = q.load_targets()
+    tp = ot.TargetParams(P)
+    rng = np.random.default_rng(5)
+    n = 2048
+    obs_state = np.tile(P.x_init, (n, 1)) + 0.1 * rng.standard_normal((n, 30))
+    obs_time = rng.uniform(0.0, 20.0, n)
+    quat = rng.standard_normal((n, 4)); quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    ee_state = np.concatenate([obs_state[:, 6:9] + rng.uniform(-0.5, 0.8, (n, 3)), quat], axis=1)
+    last = ee_state + 0.2 * rng.standard_normal((n, 7))
+    for kind in range(3):
+        cmd = np.zeros((n, 7))
+        if kind < 2:
+            cmd[:, :4] = rng.uniform(-0.5, 0.5, (n, 4))
+        else:
+            g = rng.standard_normal((n, 4)); g /= np.linalg.norm(g, axis=1, keepdims=True)
+            cmd[:] = np.concatenate([ee_state[:, :3] + rng.uniform(-0.3, 0.3, (n, 3)), g], axis=1)
+        last_d = last.copy()
+        tt, tx = ctx.targets(D, kind, cmd, obs_time, obs_state, ee_state, last_d)
+        for i in range(0, n, 64):
+            lo = last[i].copy()
+            rt, rx = ot.CONVERTERS[kind](tp, cmd[i], lo, obs_time[i], obs_state[i], ee_state[i])
+            assert np.abs(tt[i] - rt).max() < 1e-12 and np.abs(tx[i] - rx).max() < 1e-12 and np.abs(last_d[i] - lo).max() == 0.0
+    # a base velocity command as the reference of a cycle: the solver accepts it and tracks towards it
+    x0 = W.x0.copy()
+    eep = np.tile(W.target_x[0, 0, 30:37], (W.B, 1))
+    cmd = np.zeros((W.B, 7)); cmd[:, 0] = 0.2
+    tt, tx = ctx.targets(D, 0, cmd, np.zeros(W.B), x0, eep, eep.copy())
+    out = ctx.cycle(np.zeros(W.B), x0, W.events, W.modes, W.nevents, tt, tx)
+    assert ((out["status"] & ~32) == 0).all()
+    ctx.close()
+
+
 def test_device_pointer_entry_matches_host_entry(descs):
     import torch
     import qm_door_b200 as q
