@@ -82,6 +82,8 @@ int qmb200_mpc_cycle_batch_dev(qmb200_ctx* ctx, const double* t0, const double* 
 
 /* Linear interpolation of the stored policy at t[B] (host buffers): x_des[B][30], u_des[B][30], mode[B]. */
 int qmb200_evaluate_policy_batch(qmb200_ctx* ctx, const double* t, double* x_des, double* u_des, int32_t* mode);
+/* Same with device pointers, enqueued on the context's stream (MPC -> policy -> WBC without leaving the GPU). */
+int qmb200_evaluate_policy_batch_dev(qmb200_ctx* ctx, const double* t, double* x_des, double* u_des, int32_t* mode);
 
 /* Command -> two-knot reference (target_t[n][2], target_x[n][2][37] = [x_ref(30); ee position(3); ee quat xyzw(4)]), ready to be
  * passed to qmb200_mpc_cycle_batch. kind: 0 base velocity command, 1 end-effector velocity command (cmd[n][7]: vx, vy, vz,

@@ -139,6 +139,15 @@ class MpcContext:
         _check(self.L.qmb200_evaluate_policy_batch(self.h, _p(t), _p(x), _p(u), _p(mode)))
         return x, u, mode
 
+    def evaluate_policy_dev(self, t, x_des, u_des, mode):
+        """evaluatePolicy with torch CUDA tensors, enqueued on the context's stream."""
+        dp = lambda a: C.c_void_p(a.data_ptr())
+        _check(self.L.qmb200_evaluate_policy_batch_dev(self.h, dp(t), dp(x_des), dp(u_des), dp(mode)))
+
+    def rbd_to_state_dev(self, rbd, x_out, yaw_last=None):
+        dp = lambda a: None if a is None else C.c_void_p(a.data_ptr())
+        _check(self.L.qmb200_rbd_to_state_batch_dev(self.h, int(rbd.shape[0]), dp(rbd), dp(yaw_last), dp(x_out)))
+
     def rbd_to_state(self, rbd, yaw_last=None):
         """Measured rbdState [n][55] -> MPC state [n][30] (QMController.cpp:239-244); yaw_last enables the yaw unwrapping."""
         rbd = np.ascontiguousarray(rbd, dtype=np.float64)

@@ -694,6 +694,14 @@ int qmb200_rbd_to_state_batch(qmb200_ctx* c, int32_t n, const double* rbd, const
   return 0;
 }
 
+int qmb200_evaluate_policy_batch_dev(qmb200_ctx* c, const double* t, double* x_des, double* u_des, int32_t* mode) {
+  if (!c || !t || !x_des || !u_des || !mode) return fail("qmb200_evaluate_policy_batch_dev: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  { KernelTimer kt(c, KN_POLICY); k_policy<<<(unsigned)c->B, 64, 0, c->stream>>>(c->m, t, x_des, u_des, mode); }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, double* u_des, int32_t* mode) {
   if (!c || !t || !x_des || !u_des || !mode) return fail("qmb200_evaluate_policy_batch: null argument");
   CUDA_OK(cudaSetDevice(c->device));

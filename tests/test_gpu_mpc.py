@@ -211,6 +211,47 @@ def test_command_to_target_on_device(descs, oracle_inputs):
     ctx.close()
 
 
+def test_device_resident_loop_matches_host_calls(descs):
+    """Estimator state -> MPC observation -> MPC cycle -> policy sample -> whole-body controller, chained with device pointers
+    only (state conversion, cycle, evaluatePolicy and WBC never leave the GPU), against the same chain through the host-buffer
+    entry points. Mirrors QMController::update (qm_controllers/src/QMController.cpp:116-149, 239-244)."""
+    import torch
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    B = 32
+    W = workload.Workload(B, horizon=0.3, dt=0.01, seed=8)
+    WW = workload.WbcWorkload(B, seed=9, vel=0.05)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, B)
+    wctx = q.WbcContext(WW.model, WW.wbc, B)
+    # host chain
+    x_obs = ctx.rbd_to_state(WW.rbd, np.zeros(B))
+    out = ctx.cycle(np.zeros(B), x_obs, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    assert ((out["status"] & ~32) == 0).all()
+    tq = np.full(B, 0.004)
+    xd, ud, md = ctx.evaluate_policy(tq)
+    cmd_h, st_h = wctx.update(xd, ud, WW.rbd, md, 0.002, 11.0)
+    # device chain
+    ctx.reset(); wctx.reset()
+    dev = torch.device("cuda", 0)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    f64, i32 = torch.float64, torch.int32
+    rbd_d, yaw_d = T(WW.rbd), T(np.zeros(B))
+    x_d = torch.zeros(B, 30, dtype=f64, device=dev)
+    xd_d, ud_d = torch.zeros(B, 30, dtype=f64, device=dev), torch.zeros(B, 30, dtype=f64, device=dev)
+    md_d = torch.zeros(B, dtype=i32, device=dev)
+    cmd_d, st_d = torch.zeros(B, 54, dtype=f64, device=dev), torch.zeros(B, dtype=i32, device=dev)
+    ctx.rbd_to_state_dev(rbd_d, x_d, yaw_d)
+    ctx.cycle_dev(T(np.zeros(B)), x_d, T(W.events), T(W.modes), T(W.nevents), T(W.target_t), T(W.target_x))
+    ctx.evaluate_policy_dev(T(tq), xd_d, ud_d, md_d)
+    ctx.sync()                                   # the WBC context has its own stream
+    wctx.update_dev(xd_d, ud_d, rbd_d, md_d, T(np.full(B, 0.002)), T(np.full(B, 11.0)), cmd_d, st_d)
+    wctx.sync()
+    assert np.array_equal(x_d.cpu().numpy(), x_obs)
+    assert np.array_equal(xd_d.cpu().numpy(), xd) and np.array_equal(ud_d.cpu().numpy(), ud) and np.array_equal(md_d.cpu().numpy(), md)
+    assert np.array_equal(cmd_d.cpu().numpy(), cmd_h) and np.array_equal(st_d.cpu().numpy(), st_h)
+    ctx.close(); wctx.close()
+
+
 def test_device_pointer_entry_matches_host_entry(descs):
     import torch
     import qm_door_b200 as q
