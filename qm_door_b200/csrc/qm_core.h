@@ -363,42 +363,46 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
     g.sync();
     d0 = 6;
   }
+  // local transforms of all remaining joints at once (the expensive part: sincos, Rodrigues, Rp Rq), stored in the joint's
+  // own R | P | AX slots; the level-by-level sweep then only composes them with the parent placement
+  QM_PFOR(g, j, QM_NJ) {
+    if (M.depth[j] < d0) continue;
+    const double ax = M.axis[j][0], ay = M.axis[j][1], az = M.axis[j][2];
+    double* Lj = w + KW_R + 9 * j;
+    double* lp = w + KW_P + 3 * j;
+    double* la = w + KW_AX + 3 * j;
+    for (int r = 0; r < 3; ++r) la[r] = M.Rp[j][3 * r] * ax + M.Rp[j][3 * r + 1] * ay + M.Rp[j][3 * r + 2] * az;
+    if (M.jtype[j] == 1) {
+      double s, c;
+      sincos(q[j], &s, &c);
+      const double v = 1.0 - c;
+      // Rodrigues: I + s K + (1-c) K^2, K = skew(axis)
+      const double Rq[9] = {c + v * ax * ax,      v * ax * ay - s * az, v * ax * az + s * ay,
+                            v * ax * ay + s * az, c + v * ay * ay,      v * ay * az - s * ax,
+                            v * ax * az - s * ay, v * ay * az + s * ax, c + v * az * az};
+      for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc)
+          Lj[3 * r + cc] = M.Rp[j][3 * r] * Rq[cc] + M.Rp[j][3 * r + 1] * Rq[3 + cc] + M.Rp[j][3 * r + 2] * Rq[6 + cc];
+      for (int r = 0; r < 3; ++r) lp[r] = M.pp[j][r];
+    } else {
+      for (int k = 0; k < 9; ++k) Lj[k] = M.Rp[j][k];
+      for (int r = 0; r < 3; ++r) lp[r] = M.pp[j][r] + la[r] * q[j];
+    }
+  }
+  g.sync();
   for (int d = d0; d <= M.max_depth; ++d) {
     QM_PFOR(g, j, QM_NJ) {
       if (M.depth[j] != d) continue;
-      double Rpar[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, ppar[3] = {0, 0, 0};
       const int par = M.parent[j];
-      if (par >= 0) {
-        for (int k = 0; k < 9; ++k) Rpar[k] = w[KW_R + 9 * par + k];
-        for (int k = 0; k < 3; ++k) ppar[k] = w[KW_P + 3 * par + k];
-      }
-      double R0[9], p0[3], aw[3];
+      if (par < 0) continue;                     // a root joint: its local transform is its placement
+      double Rpar[9], ppar[3], L[9], l[3], a[3];
+      for (int k = 0; k < 9; ++k) { Rpar[k] = w[KW_R + 9 * par + k]; L[k] = w[KW_R + 9 * j + k]; }
+      for (int k = 0; k < 3; ++k) { ppar[k] = w[KW_P + 3 * par + k]; l[k] = w[KW_P + 3 * j + k]; a[k] = w[KW_AX + 3 * j + k]; }
       for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c)
-          R0[3 * r + c] = Rpar[3 * r] * M.Rp[j][c] + Rpar[3 * r + 1] * M.Rp[j][3 + c] + Rpar[3 * r + 2] * M.Rp[j][6 + c];
-        p0[r] = ppar[r] + Rpar[3 * r] * M.pp[j][0] + Rpar[3 * r + 1] * M.pp[j][1] + Rpar[3 * r + 2] * M.pp[j][2];
+        for (int c = 0; c < 3; ++c) w[KW_R + 9 * j + 3 * r + c] = Rpar[3 * r] * L[c] + Rpar[3 * r + 1] * L[3 + c] + Rpar[3 * r + 2] * L[6 + c];
+        w[KW_P + 3 * j + r] = ppar[r] + Rpar[3 * r] * l[0] + Rpar[3 * r + 1] * l[1] + Rpar[3 * r + 2] * l[2];
+        w[KW_AX + 3 * j + r] = Rpar[3 * r] * a[0] + Rpar[3 * r + 1] * a[1] + Rpar[3 * r + 2] * a[2];
       }
-      const double ax = M.axis[j][0], ay = M.axis[j][1], az = M.axis[j][2];
-      for (int r = 0; r < 3; ++r) aw[r] = R0[3 * r] * ax + R0[3 * r + 1] * ay + R0[3 * r + 2] * az;
-      double* Rj = w + KW_R + 9 * j;
-      double* pj = w + KW_P + 3 * j;
-      if (M.jtype[j] == 1) {
-        double s, c;
-        sincos(q[j], &s, &c);
-        const double v = 1.0 - c;
-        // Rodrigues: I + s K + (1-c) K^2, K = skew(axis)
-        const double Rq[9] = {c + v * ax * ax,      v * ax * ay - s * az, v * ax * az + s * ay,
-                              v * ax * ay + s * az, c + v * ay * ay,      v * ay * az - s * ax,
-                              v * ax * az - s * ay, v * ay * az + s * ax, c + v * az * az};
-        for (int r = 0; r < 3; ++r)
-          for (int cc = 0; cc < 3; ++cc)
-            Rj[3 * r + cc] = R0[3 * r] * Rq[cc] + R0[3 * r + 1] * Rq[3 + cc] + R0[3 * r + 2] * Rq[6 + cc];
-        for (int r = 0; r < 3; ++r) pj[r] = p0[r];
-      } else {
-        for (int k = 0; k < 9; ++k) Rj[k] = R0[k];
-        for (int r = 0; r < 3; ++r) pj[r] = p0[r] + aw[r] * q[j];
-      }
-      for (int r = 0; r < 3; ++r) w[KW_AX + 3 * j + r] = aw[r];
     }
     g.sync();
   }
