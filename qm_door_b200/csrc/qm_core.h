@@ -449,17 +449,18 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
     }
   }
   g.sync();
-  // P3: composite (subtree) inertias
-  QM_PFOR(g, j, QM_NJ) {
-    double acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // P3: composite (subtree) inertias. One (joint, component) pair per work item: the base joints carry the whole tree,
+  //     so a lane per joint would leave the phase waiting for six lanes that sum 24 bodies each.
+  QM_PFOR(g, idx, QM_NJ * 10) {
+    const int j = idx / 10, k = idx - 10 * j;
+    double acc = 0.0;
     const uint32_t mask = M.submask[j];
     for (int i = 0; i < QM_NJ; ++i)
-      if ((mask >> i) & 1u)
-        for (int k = 0; k < 10; ++k) acc[k] += w[KW_BODY + 10 * i + k];
-    for (int k = 0; k < 10; ++k) w[KW_COMP + 10 * j + k] = acc[k];
-    if (j == 0)
-      for (int r = 0; r < 3; ++r) w[KW_COM + r] = acc[1 + r] / acc[0];
+      if ((mask >> i) & 1u) acc += w[KW_BODY + 10 * i + k];
+    w[KW_COMP + idx] = acc;
   }
+  g.sync();
+  QM_PFOR(g, r, 3) w[KW_COM + r] = w[KW_COMP + 1 + r] / w[KW_COMP];
   g.sync();
   // P4: centroidal momentum matrix columns, frame Jacobian columns
   QM_PFOR(g, j, QM_NJ) {
@@ -574,15 +575,15 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
     g.sync();
     return;
   }
-  // P8: subtree momenta (into KW_SV)
+  // P8: subtree momenta (into KW_SV), one (joint, component) pair per work item
   g.sync();
-  QM_PFOR(g, j, QM_NJ) {
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+  QM_PFOR(g, idx, QM_NJ * 6) {
+    const int j = idx / 6, c = idx - 6 * j;
+    double acc = 0.0;
     const uint32_t mask = M.submask[j];
     for (int i = 0; i < QM_NJ; ++i)
-      if ((mask >> i) & 1u)
-        for (int c = 0; c < 6; ++c) acc[c] += w[KW_HB + 6 * i + c];
-    for (int c = 0; c < 6; ++c) w[KW_SV + 6 * j + c] = acc[c];
+      if ((mask >> i) & 1u) acc += w[KW_HB + 6 * i + c];
+    w[KW_SV + idx] = acc;
   }
   g.sync();
   // P9: d(A v)/dq_k and d(J_i v)/dq_k at fixed generalized velocity
