@@ -11,6 +11,8 @@
  *                                       (QMController.cpp:316-333, :119-122)
  *   qmb200_mpc_reset                 <- coldStart / resetMpcNode semantics (task.info:143)
  *   qmb200_evaluate_policy_batch     <- MPC_MRT_Interface::evaluatePolicy (QMController.cpp:140-143)
+ *   qmb200_feedback_gains[_dev], qmb200_evaluate_feedback_policy_batch <- [upstream] SqpSolver::toPrimalSolution /
+ *                                       LinearController::computeInput when task.info:90 useFeedbackPolicy is true
  *   qmb200_rbd_to_state_batch[_dev]  <- CentroidalModelRbdConversions::computeCentroidalStateFromRbdModel + yaw unwrapping in
  *                                       QMController::updateStateEstimation (QMController.cpp:239-244); rbd layout of
  *                                       qm_estimation/src/StateEstimateBase.cpp:29-102
@@ -96,6 +98,14 @@ int qmb200_targets_batch(qmb200_ctx* ctx, const qmb200_target_desc* desc, int32_
 int qmb200_targets_batch_dev(qmb200_ctx* ctx, const qmb200_target_desc* desc, int32_t kind, int32_t n, const double* cmd,
                              const double* obs_time, const double* obs_state, const double* ee_state, double* last_ee_target,
                              double* target_t, double* target_x);
+
+/* Feedback policy (useFeedbackPolicy, task.info:90; [upstream] SqpSolver::toPrimalSolution / LinearController): gains of the
+ * last cycle in the original input coordinates, K_out[B][NMAX][30][30] = Pu K~ + Px per node (pre-event and final nodes repeat
+ * the previous node). The context keeps them (allocated on first use); K_out may be NULL for the _dev variant.
+ * qmb200_evaluate_feedback_policy_batch: u[B][30] = uff(t) + K(t) x with uff_i = u*_i - K_i x*_i (host buffers). */
+int qmb200_feedback_gains(qmb200_ctx* ctx, double* K_out);
+int qmb200_feedback_gains_dev(qmb200_ctx* ctx, double* K_out);
+int qmb200_evaluate_feedback_policy_batch(qmb200_ctx* ctx, const double* t, const double* x, double* u_out, int32_t* mode);
 
 /* Measured rbd state rbd[n][55] -> MPC state x_out[n][30] = [A(q) v / m; base position; zyx; joints]. yaw_last[n] (may be
  * NULL): previous yaw per state; when given, x[9] = yaw_last + shortest_angular_distance(yaw_last, yaw). n need not equal the

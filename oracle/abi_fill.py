@@ -175,6 +175,11 @@ class CPort:
                                  dp(out["status"]))
         return out
 
+    def feedback_gains(self):
+        K = np.zeros((self.B, self.NMAX, 30, 30))
+        self.lib.cport_feedback_gains(self.ctx, K.ctypes.data_as(C.c_void_p))
+        return K
+
 
 def pack_schedules(schedules, EMAX):
     """[(events, modes)] -> padded arrays (events padded with +1e30, modes with STANCE)."""

@@ -147,6 +147,21 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
   return 0;
 }
 
+// Feedback gains of the last cycle, K [B][NMAX][30][30] (useFeedbackPolicy): same node functions as k_gains.
+int cport_feedback_gains(CportCtx* c, double* K) {
+  const MpcBuffers& m = c->m;
+  parallel_for(m.B, c->threads, [&](int b) {
+    const size_t o = (size_t)b * m.NMAX;
+    for (int k = 0; k < m.nn[b]; ++k) {
+      double* out = K + (o + k) * 900;
+      const int src = feedback_gain_source(m.nn[b], m.node_flag + o, k);
+      if (src < 0) memset(out, 0, sizeof(double) * 900);
+      else feedback_gain_node(SerialGroup(), m.proj + (o + src) * PB_SIZE, m.gain + (o + src) * GB_SIZE, out);
+    }
+  });
+  return 0;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------- WBC

@@ -139,6 +139,20 @@ class MpcContext:
         _check(self.L.qmb200_evaluate_policy_batch(self.h, _p(t), _p(x), _p(u), _p(mode)))
         return x, u, mode
 
+    def feedback_gains(self):
+        """K [B][NMAX][30][30] of the last cycle in the original input coordinates (useFeedbackPolicy)."""
+        K = np.zeros((self.B, self.solver.max_nodes, 30, 30))
+        _check(self.L.qmb200_feedback_gains(self.h, _p(K)))
+        return K
+
+    def evaluate_feedback_policy(self, t, x):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        u = np.zeros((self.B, 30))
+        mode = np.zeros(self.B, dtype=np.int32)
+        _check(self.L.qmb200_evaluate_feedback_policy_batch(self.h, _p(t), _p(x), _p(u), _p(mode)))
+        return u, mode
+
     def evaluate_policy_dev(self, t, x_des, u_des, mode):
         """evaluatePolicy with torch CUDA tensors, enqueued on the context's stream."""
         dp = lambda a: C.c_void_p(a.data_ptr())

@@ -1182,6 +1182,36 @@ QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double*
   g.sync();
 }
 
+// Feedback gain of one node in the original input coordinates ([upstream] SqpSolver::toPrimalSolution with
+// useFeedbackPolicy, task.info:90): K = Pu K~ + Px from the Riccati gain K~ [nut][30] and the compact projection block.
+// Kout [30][30]; rows of dropped inputs (swing-foot forces) are zero. One work item per entry.
+template <class G>
+QM_HDN void feedback_gain_node(G g, const double* pb, const double* gb, double* Kout) {
+  const int* role = (const int*)(pb + PB_ROLE);
+  const int nut = role[31];
+  QM_PFOR(g, idx, 900) {
+    const int i = idx / 30, j = idx - 30 * i;
+    const int rl = role[i];
+    double v = 0.0;
+    if (nut > 0) {
+      if (rl < ROLE_FREE) {
+        v = pb[PB_PX + 30 * rl + j];
+        for (int a = 0; a < nut; ++a) v += pb[PB_PU + QM_NUT * rl + a] * gb[GB_K + 30 * a + j];
+      } else if (rl < ROLE_NONE) {
+        v = gb[GB_K + 30 * (rl - ROLE_FREE) + j];
+      }
+    }
+    Kout[idx] = v;
+  }
+}
+
+// Node whose gain node k repeats: pre-event nodes and the final node carry no input of their own and repeat the previous
+// node (toPrimalSolution does the same for the inputs). Returns -1 when there is no source (zero gain).
+QM_HD int feedback_gain_source(int nn, const int32_t* node_flag, int k) {
+  while (k > 0 && (k == nn - 1 || node_flag[k] == EV_PRE)) --k;
+  return (k == nn - 1 || node_flag[k] == EV_PRE) ? -1 : k;
+}
+
 // [upstream] FilterLinesearch::acceptStep
 QM_HD bool accept_step(const qmb200_solver_desc& S, double base_merit, double base_viol, double new_merit, double new_viol, double armijo) {
   if (new_viol > S.g_max) return new_viol < (1.0 - S.gamma_c) * base_viol;

@@ -339,6 +339,45 @@ __global__ void __launch_bounds__(32 * kStateWarps) k_rbd_state(int B, const qmb
                             x_out + 30 * (size_t)b);
 }
 
+// Feedback gains K[B][NMAX][30][30] of the last cycle (useFeedbackPolicy): CTA per node. Pre-event nodes and the final node
+// repeat the gain of the previous node, as toPrimalSolution does for the inputs.
+__global__ void __launch_bounds__(128) k_gains(MpcBuffers m, double* K) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  const int nn = m.nn[b];
+  if (k >= nn) return;
+  const size_t o = (size_t)b * m.NMAX;
+  double* out = K + (o + k) * 900;
+  const int src = feedback_gain_source(nn, m.node_flag + o, k);
+  if (src < 0) {
+    for (int i = threadIdx.x; i < 900; i += blockDim.x) out[i] = 0.0;
+    return;
+  }
+  feedback_gain_node(BlockGroup(), m.proj + (o + src) * PB_SIZE, m.gain + (o + src) * GB_SIZE, out);
+}
+
+// [upstream] LinearController::computeInput: u = uff(t) + K(t) x with uff_i = u*_i - K_i x*_i, both interpolated linearly.
+__global__ void __launch_bounds__(32) k_policy_fb(MpcBuffers m, const double* K, const double* t, const double* x, double* u_out, int32_t* mode) {
+  const int b = blockIdx.x, i = threadIdx.x;
+  const size_t o = (size_t)b * m.NMAX;
+  const int np = m.nprev[b];
+  int seg; double a;
+  time_segment(t[b], m.prev_t + o, np, &seg, &a);
+  const int seg2 = (np > 1) ? seg + 1 : seg;
+  if (i < 30) {
+    double acc = 0.0;
+    const int segs[2] = {seg, seg2};
+    const double wts[2] = {a, 1.0 - a};
+    for (int s = 0; s < 2; ++s) {
+      const double* Kn = K + (o + segs[s]) * 900 + 30 * i;
+      double v = m.prev_u[(o + segs[s]) * 30 + i];
+      for (int j = 0; j < 30; ++j) v += Kn[j] * (x[30 * b + j] - m.prev_x[(o + segs[s]) * 30 + j]);
+      acc += wts[s] * v;
+    }
+    u_out[30 * b + i] = acc;
+  }
+  if (i == 0) mode[b] = m.modes[(size_t)b * (m.EMAX + 1) + mode_index(m.events + (size_t)b * m.EMAX, m.nevents[b], t[b])];
+}
+
 // ------------------------------------------------------------------------------------------ context
 struct qmb200_ctx {
   int device = 0;
@@ -352,6 +391,7 @@ struct qmb200_ctx {
   MpcBuffers m;          // ctx-owned device buffers
   int* d_pending = nullptr;   // [kMaxChunks]
   int* d_list = nullptr;      // [B] problems still backtracking, compacted per chunk
+  double* fb_gains = nullptr; // [B][NMAX][900] feedback gains of the last cycle, allocated on first use
   int* h_pending = nullptr;   // pinned, [kMaxChunks]
   cudaStream_t stream = nullptr;
   // The cycle can be pipelined over chunks of problems, one stream per chunk, so that the (latency-bound, few CTAs) Riccati
@@ -525,6 +565,7 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->dS) cudaFree(c->dS);
   if (c->d_pending) cudaFree(c->d_pending);
   if (c->d_list) cudaFree(c->d_list);
+  if (c->fb_gains) cudaFree(c->fb_gains);
   if (c->h_pending) cudaFreeHost(c->h_pending);
   for (int ch = 0; ch < qmb200_ctx::kMaxChunks; ++ch) {
     if (c->cs[ch]) { cudaStreamSynchronize(c->cs[ch]); cudaStreamDestroy(c->cs[ch]); }
@@ -690,6 +731,51 @@ int qmb200_rbd_to_state_batch(qmb200_ctx* c, int32_t n, const double* rbd, const
   CUDA_OK(cudaMemcpyAsync(x_out, d_x, sizeof(double) * 30 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaFreeAsync(d_rbd, c->stream)); CUDA_OK(cudaFreeAsync(d_x, c->stream));
   if (d_yaw) CUDA_OK(cudaFreeAsync(d_yaw, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmb200_feedback_gains_dev(qmb200_ctx* c, double* K_out) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->B * c->m.NMAX * 900;
+  if (!c->fb_gains) {
+    CUDA_OK(cudaMalloc(&c->fb_gains, n * sizeof(double)));
+    CUDA_OK(cudaMemsetAsync(c->fb_gains, 0, n * sizeof(double), c->stream));
+  }
+  k_gains<<<dim3(c->m.NMAX, c->B), 128, 0, c->stream>>>(c->m, c->fb_gains);
+  CUDA_OK(cudaGetLastError());
+  if (K_out) CUDA_OK(cudaMemcpyAsync(K_out, c->fb_gains, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int qmb200_feedback_gains(qmb200_ctx* c, double* K_out) {
+  if (!c || !K_out) return fail("qmb200_feedback_gains: null argument");
+  if (qmb200_feedback_gains_dev(c, nullptr) != 0) return -1;
+  const size_t n = (size_t)c->B * c->m.NMAX * 900;
+  CUDA_OK(cudaMemcpyAsync(K_out, c->fb_gains, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int qmb200_evaluate_feedback_policy_batch(qmb200_ctx* c, const double* t, const double* x, double* u_out, int32_t* mode) {
+  if (!c || !t || !x || !u_out || !mode) return fail("qmb200_evaluate_feedback_policy_batch: null argument");
+  if (!c->fb_gains) return fail("qmb200_evaluate_feedback_policy_batch: call qmb200_feedback_gains[_dev] after the cycle first");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t B = c->B;
+  double *dt = nullptr, *dx = nullptr, *du = nullptr; int32_t* dm = nullptr;
+  CUDA_OK(cudaMallocAsync(&dt, sizeof(double) * B, c->stream));
+  CUDA_OK(cudaMallocAsync(&dx, sizeof(double) * B * 30, c->stream));
+  CUDA_OK(cudaMallocAsync(&du, sizeof(double) * B * 30, c->stream));
+  CUDA_OK(cudaMallocAsync(&dm, sizeof(int32_t) * B, c->stream));
+  CUDA_OK(cudaMemcpyAsync(dt, t, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(dx, x, sizeof(double) * B * 30, cudaMemcpyHostToDevice, c->stream));
+  k_policy_fb<<<(unsigned)B, 32, 0, c->stream>>>(c->m, c->fb_gains, dt, dx, du, dm);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(u_out, du, sizeof(double) * B * 30, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(mode, dm, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaFreeAsync(dt, c->stream)); CUDA_OK(cudaFreeAsync(dx, c->stream));
+  CUDA_OK(cudaFreeAsync(du, c->stream)); CUDA_OK(cudaFreeAsync(dm, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -87,6 +87,51 @@ def test_fresh_cycle_against_oracle_with_ee_target_motion(descs, oracle_inputs):
     cp.close()
 
 
+def oracle_feedback_gains(info):
+    """K = Pu K~ + Px per node in the original input coordinates; pre-event and final nodes repeat the previous node."""
+    n = info["n"]
+    K = np.zeros((n + 1, 30, 30))
+    for k in range(n):
+        st = info["stages"][k]
+        if info["flags"][k] != G.EV_PRE:
+            K[k] = st["Pu"] @ info["Ks"][k] + st["Px"]
+        elif k > 0:
+            K[k] = K[k - 1]
+    K[n] = K[n - 1]
+    return K
+
+
+def test_feedback_gains_against_oracle(descs, oracle_inputs):
+    """useFeedbackPolicy (task.info:90): the reduced coordinates depend on the pivot choice of the projection, the gain in the
+    original coordinates does not. Also a property of the gain itself: u* + K dx stays on the linearised constraint manifold
+    (rows of swing-foot forces are zero)."""
+    model, problem, solver, _ = descs
+    m, P = oracle_inputs
+    B, hor = 2, 0.12
+    x0s, phase = scenarios.perturbed_states(m, P, B, seed=5)
+    tt, ts = scenarios.standing_target(m, P)
+    sd = solver_for(solver, hor, 0.01)
+    scheds = [G.tile_schedule(P.gaits["trot"], -1.2 - phase[b], 1.2) for b in range(B)]
+    ev, md, ne = abi_fill.pack_schedules(scheds, sd.max_events)
+    cp = abi_fill.CPort(model, problem, sd, B)
+    probs = [sqp.MpcProblem(m, P, ev[b, :ne[b]], md[b, :ne[b] + 1], tt, ts, horizon=hor, dt=0.01) for b in range(B)]
+    for c in range(2):
+        out = cp.cycle(np.full(B, 0.01 * c), x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)))
+        K = cp.feedback_gains()
+        for b in range(B):
+            _, xs, us, info = sqp.mpc_cycle(probs[b], 0.01 * c, x0s[b], return_debug=True)
+            Kref = oracle_feedback_gains(info)
+            n = info["n"]
+            assert out["n"][b] == n + 1
+            assert rel_l2(K[b, :n + 1], Kref) < 1e-7
+            for k in range(n):
+                swing = [f for f in range(4) if not (info["modes"][k] >> (3 - f)) & 1]
+                if info["flags"][k] != G.EV_PRE:
+                    for f in swing:
+                        assert np.abs(K[b, k, 3 * f:3 * f + 3]).max() < 1e-9
+    cp.close()
+
+
 def _random_rbd(m, P, n, seed):
     """Measured rbd states: nominal pose + perturbations, random generalized velocities, yaw spread over several turns."""
     from oracle import wbc as owbc

@@ -252,6 +252,36 @@ def test_device_resident_loop_matches_host_calls(descs):
     ctx.close(); wctx.close()
 
 
+def test_feedback_gains_match_oracle(descs):
+    """useFeedbackPolicy (task.info:90): K = Pu K~ + Px per node against the oracle's projection and Riccati gains (the reduced
+    coordinates differ with the pivot choice, K in the original coordinates does not), and LinearController evaluation."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    from oracle import config, sqp
+    from test_cport import oracle_feedback_gains
+    W = workload.Workload(2, horizon=0.15, dt=0.01, seed=77)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    m, P = config.load_default()
+    probs = [sqp.MpcProblem(m, P, W.events[b, :W.nevents[b]], W.modes[b, :W.nevents[b] + 1], W.target_t[b], W.target_x[b],
+                            horizon=0.15, dt=0.01) for b in range(W.B)]
+    for c in range(2):
+        out = ctx.cycle(np.full(W.B, 0.01 * c), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+        K = ctx.feedback_gains()
+        for b in range(W.B):
+            _, xs, us, info = sqp.mpc_cycle(probs[b], 0.01 * c, W.x0[b], return_debug=True)
+            n = info["n"]
+            Kref = oracle_feedback_gains(info)
+            assert rel_l2(K[b, :n + 1], Kref) < 1e-7
+            # LinearController: u = uff(t) + K(t) x
+            tq = 0.01 * c + 0.0137
+            xq = xs[1] + 0.01 * np.sin(np.arange(30))
+            i, a = sqp.time_segment(tq, out["t"][b, :n + 1])
+            ref = sum(wt * (us[j] + Kref[j] @ (xq - xs[j])) for wt, j in ((a, i), (1.0 - a, i + 1)))
+            u_fb, _ = ctx.evaluate_feedback_policy(np.full(W.B, tq), np.tile(xq, (W.B, 1)))
+            assert rel_l2(u_fb[b], ref) < 1e-7
+    ctx.close()
+
+
 def test_device_pointer_entry_matches_host_entry(descs):
     import torch
     import qm_door_b200 as q
