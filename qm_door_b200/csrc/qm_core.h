@@ -335,11 +335,22 @@ template <class G>
 QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, double* w, bool jac = true) {
   // P1: placements. A standard floating base (joints 0..5) is placed in closed form by its six lanes at once
   //     (R = Rz(yaw) Ry(pitch) Rx(roll), p = base position); the remaining joints level by level.
-  int d0 = 0;
-  if (M.root6_standard) {
-    QM_PFOR(g, j, 6) {
-      double sz, cz, sy, cy, sx, cx;
-      sincos(q[3], &sz, &cz); sincos(q[4], &sy, &cy); sincos(q[5], &sx, &cx);
+  // One sincos per lane for all joints at once (the three Euler angles of a standard floating base included), kept in the
+  // velocity-level array SV, which is not live before kin_velocities.
+  double* sc = w + KW_SV;
+  QM_PFOR(g, j, QM_NJ) {
+    double s = 0.0, c = 1.0;
+    if (M.jtype[j] == 1) sincos(q[j], &s, &c);
+    sc[2 * j] = s; sc[2 * j + 1] = c;
+  }
+  g.sync();
+  const int d0 = M.root6_standard ? 6 : 0;
+  // local transforms of all joints at once (Rodrigues, Rp Rq), stored in the joint's own R | P | AX slots; the level-by-level
+  // sweep then only composes them with the parent placement. A standard floating base (joints 0..5) is placed in closed
+  // form by its six lanes: R = Rz(yaw) Ry(pitch) Rx(roll), p = base position.
+  QM_PFOR(g, j, QM_NJ) {
+    if (M.depth[j] < d0) {
+      const double sz = sc[6], cz = sc[7], sy = sc[8], cy = sc[9], sx = sc[10], cx = sc[11];
       double* Rj = w + KW_R + 9 * j;
       double* pj = w + KW_P + 3 * j;
       double* aj = w + KW_AX + 3 * j;
@@ -359,22 +370,15 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
         Rj[6] = -sy;     Rj[7] = cy * sx;                Rj[8] = cy * cx;
         aj[0] = cz * cy; aj[1] = sz * cy; aj[2] = -sy;
       }
+      continue;
     }
-    g.sync();
-    d0 = 6;
-  }
-  // local transforms of all remaining joints at once (the expensive part: sincos, Rodrigues, Rp Rq), stored in the joint's
-  // own R | P | AX slots; the level-by-level sweep then only composes them with the parent placement
-  QM_PFOR(g, j, QM_NJ) {
-    if (M.depth[j] < d0) continue;
     const double ax = M.axis[j][0], ay = M.axis[j][1], az = M.axis[j][2];
     double* Lj = w + KW_R + 9 * j;
     double* lp = w + KW_P + 3 * j;
     double* la = w + KW_AX + 3 * j;
     for (int r = 0; r < 3; ++r) la[r] = M.Rp[j][3 * r] * ax + M.Rp[j][3 * r + 1] * ay + M.Rp[j][3 * r + 2] * az;
     if (M.jtype[j] == 1) {
-      double s, c;
-      sincos(q[j], &s, &c);
+      const double s = sc[2 * j], c = sc[2 * j + 1];
       const double v = 1.0 - c;
       // Rodrigues: I + s K + (1-c) K^2, K = skew(axis)
       const double Rq[9] = {c + v * ax * ax,      v * ax * ay - s * az, v * ax * az + s * ay,
@@ -523,13 +527,14 @@ QM_HDN void centroidal_velocity(G g, const qmb200_model_desc& M, const double* x
                            (d * hh - e * gg) * id, (b * gg - a * hh) * id, (a * e - b * d) * id};
     double* Bi = w + KW_ABINV;
     for (int k = 0; k < 36; ++k) Bi[k] = 0.0;
+    const double im = 1.0 / mass;
     for (int r = 0; r < 3; ++r) {
-      Bi[6 * r + r] = 1.0 / mass;
+      Bi[6 * r + r] = im;
       for (int cc = 0; cc < 3; ++cc) {
         Bi[6 * (3 + r) + 3 + cc] = inv[3 * r + cc];
         double acc = 0.0;
         for (int k = 0; k < 3; ++k) acc += A[r * QM_NJ + 3 + k] * inv[3 * k + cc];
-        Bi[6 * r + 3 + cc] = -acc / mass;
+        Bi[6 * r + 3 + cc] = -acc * im;
       }
     }
   }
@@ -605,7 +610,8 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
     // to the centroidal frame: L = L0 - c x p
     const double* ptot = w + KW_SV + 3;        // linear momentum of the whole tree (joint 0 subtree)
     double dc[3];
-    for (int r = 0; r < 3; ++r) dc[r] = w[KW_ACM + r * QM_NJ + k] / M.total_mass;
+    const double im = 1.0 / M.total_mass;
+    for (int r = 0; r < 3; ++r) dc[r] = w[KW_ACM + r * QM_NJ + k] * im;
     cross3(dc, ptot, t);
     double t2[3];
     cross3(w + KW_COM, dp, t2);

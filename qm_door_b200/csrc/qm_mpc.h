@@ -285,42 +285,46 @@ QM_HDN void flow_rows(G g, const qmb200_model_desc& M, double gravity, const dou
     f[i] = v;
   }
   if (Fr != nullptr) {
-    QM_PFOR(g, idx, 540) {
-      const int r = idx / 60, c = idx % 60;
+    const double im = 1.0 / m;
+    // rows 0..2 (normalised angular momentum rate): the three rows of a column come from one vector, so a work item is a
+    // column (the per-entry version repeated the four cross products, and their divisions by m, for every row)
+    QM_PFOR(g, c, 60) {
+      double v[3] = {0.0, 0.0, 0.0};
+      if (c >= 6 && c < 30) {                       // d/dq_k sum_i (p_i - c) x f_i / m
+        const int k = c - 6;
+        double ac[3];
+        for (int rr = 0; rr < 3; ++rr) ac[rr] = w[KW_ACM + rr * QM_NJ + k] * im;
+        for (int ft = 0; ft < 4; ++ft) {
+          double d[3];
+          for (int rr = 0; rr < 3; ++rr) d[rr] = w[KW_FJ + (3 * ft + rr) * QM_NJ + k] - ac[rr];
+          cross3_add(d, u + 3 * ft, v);
+        }
+      } else if (c >= 30 && c < 42) {               // d/df_i: (p_i - c) x e_d / m
+        const int ft = (c - 30) / 3, d = (c - 30) % 3;
+        double arm[3], e[3] = {0, 0, 0};
+        e[d] = 1.0;
+        for (int rr = 0; rr < 3; ++rr) arm[rr] = w[KW_FPOS + 3 * ft + rr] - w[KW_COM + rr];
+        cross3(arm, e, v);
+      }
+      for (int r = 0; r < 3; ++r) Fr[60 * r + c] = v[r] * im;
+    }
+    // rows 3..8: v_b = A_b^-1 (m h - A_j v_j)
+    QM_PFOR(g, i2, 360) {
+      const int idx = 180 + i2;
+      const int rr = i2 / 60, c = i2 % 60;
       double v = 0.0;
-      if (r < 3) {
-        if (c >= 6 && c < 30) {
-          const int k = c - 6;
-          for (int ft = 0; ft < 4; ++ft) {
-            double d[3], t[3];
-            for (int rr = 0; rr < 3; ++rr) d[rr] = w[KW_FJ + (3 * ft + rr) * QM_NJ + k] - w[KW_ACM + rr * QM_NJ + k] / m;
-            cross3(d, u + 3 * ft, t);
-            v += t[r];
-          }
-          v /= m;
-        } else if (c >= 30 && c < 42) {
-          const int ft = (c - 30) / 3, d = (c - 30) % 3;
-          double arm[3], e[3] = {0, 0, 0}, t[3];
-          e[d] = 1.0;
-          for (int rr = 0; rr < 3; ++rr) arm[rr] = w[KW_FPOS + 3 * ft + rr] - w[KW_COM + rr];
-          cross3(arm, e, t);
-          v = t[r] / m;
-        }
-      } else {
-        const int rr = r - 3;
-        const double* Bi = w + KW_ABINV + 6 * rr;
-        if (c < 6) {
-          v = m * Bi[c];
-        } else if (c < 30) {
-          const int k = c - 6;
-          for (int cc = 0; cc < 6; ++cc) v -= Bi[cc] * w[KW_DH + cc * QM_NJ + k];
-        } else if (c >= 42) {
-          const int l = c - 42;
-          for (int cc = 0; cc < 6; ++cc) v -= Bi[cc] * w[KW_ACM + cc * QM_NJ + 6 + l];
-        }
+      const double* Bi = w + KW_ABINV + 6 * rr;
+      if (c < 6) {
+        v = m * Bi[c];
+      } else if (c < 30) {
+        const int k = c - 6;
+        for (int cc = 0; cc < 6; ++cc) v -= Bi[cc] * w[KW_DH + cc * QM_NJ + k];
+      } else if (c >= 42) {
+        const int l = c - 42;
+        for (int cc = 0; cc < 6; ++cc) v -= Bi[cc] * w[KW_ACM + cc * QM_NJ + 6 + l];
       }
       Fr[idx] = v;
-      if (vb_shadow != nullptr && r >= 3) vb_shadow[idx - 180] = v;   // rows of v_b = A_b^-1(...) kept close for the constraint rows
+      if (vb_shadow != nullptr) vb_shadow[i2] = v;   // rows of v_b = A_b^-1(...) kept close for the constraint rows
     }
   }
   g.sync();
@@ -802,7 +806,7 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
     }
     const double* F1 = io.fr1;
     const double* F2 = io.fr2;
-    const double hdt = 0.5 * dt;
+    const double hdt = 0.5 * dt, im = 1.0 / m;
     QM_PFOR(g, idx, 900) {
       const int i = idx / 30, j = idx % 30;
       double av = (i == j) ? 1.0 : 0.0, bv = 0.0;
@@ -813,12 +817,12 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
           pa += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + j];
           pb2 += F2[rr * 60 + 3 + s2] * F1[s2 * 60 + 30 + j];
         }
-        if (j < 12) pb2 += F2[rr * 60 + (j % 3)] / m;
+        if (j < 12) pb2 += F2[rr * 60 + (j % 3)] * im;
         else pb2 += F2[rr * 60 + j];
         av += hdt * (F1[rr * 60 + j] + F2[rr * 60 + j] + dt * pa);
         bv = hdt * (F1[rr * 60 + 30 + j] + F2[rr * 60 + 30 + j] + dt * pb2);
       } else if (i < 3) {
-        bv = (j < 12 && (j % 3) == i) ? dt / m : 0.0;
+        bv = (j < 12 && (j % 3) == i) ? dt * im : 0.0;
       } else {
         bv = (j == i) ? dt : 0.0;
       }

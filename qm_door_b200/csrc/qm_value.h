@@ -186,7 +186,8 @@ QM_HDN void kin_value_serial(const qmb200_model_desc& M, const double* x, const 
     for (int k = 0; k < 3; ++k) pc[k] = pj[k];
     for (int k = 0; k < 6; ++k) Vc[k] = Vj[k];
   }
-  for (int r = 0; r < 3; ++r) o.com[r] = total[1 + r] / total[0];
+  const double itot = 1.0 / total[0];
+  for (int r = 0; r < 3; ++r) o.com[r] = total[1 + r] * itot;
   if (u == nullptr) return;
   // floating-base block of the centroidal momentum matrix: columns k < 6 = I^c_k S_k, I^c_k = whole tree minus bodies < k
   double Ab[6][6];
@@ -228,13 +229,14 @@ QM_HDN void kin_value_serial(const qmb200_model_desc& M, const double* x, const 
                            (d * hh - e * gg) * id, (b * gg - a * hh) * id, (a * e - b * d) * id};
     double wv[3];
     for (int r = 0; r < 3; ++r) wv[r] = inv[3 * r] * rhs[3] + inv[3 * r + 1] * rhs[4] + inv[3 * r + 2] * rhs[5];
+    const double im = 1.0 / mass;
     for (int r = 0; r < 3; ++r) {
       // Bi[r][0:3] = I / mass, Bi[r][3:6] = -(Ab12 inv)[r] / mass
-      double acc = rhs[r] / mass;
+      double acc = rhs[r] * im;
       for (int cc = 0; cc < 3; ++cc) {
         double ai = 0.0;
         for (int k = 0; k < 3; ++k) ai += Ab[r][3 + k] * inv[3 * k + cc];
-        acc += -ai / mass * rhs[3 + cc];
+        acc += -ai * im * rhs[3 + cc];
       }
       o.vel[r] = acc;
       o.vel[3 + r] = wv[r];
@@ -263,8 +265,8 @@ QM_HDN void kin_value_serial(const qmb200_model_desc& M, const double* x, const 
 
 // flow map value f(x,u) from the value-level kinematics (QMDynamicsAD::computeFlowMap)
 QM_HDN void flow_value_serial(const qmb200_model_desc& M, double gravity, const ValueKin& k, const double* u, double* f) {
-  const double m = M.total_mass;
-  for (int i = 0; i < 3; ++i) f[i] = (u[i] + u[3 + i] + u[6 + i] + u[9 + i]) / m - (i == 2 ? gravity : 0.0);
+  const double im = 1.0 / M.total_mass;
+  for (int i = 0; i < 3; ++i) f[i] = (u[i] + u[3 + i] + u[6 + i] + u[9 + i]) * im - (i == 2 ? gravity : 0.0);
   double acc[3] = {0, 0, 0};
   for (int ft = 0; ft < 4; ++ft) {
     double arm[3], t[3];
@@ -272,7 +274,7 @@ QM_HDN void flow_value_serial(const qmb200_model_desc& M, double gravity, const 
     cross3(arm, u + 3 * ft, t);
     for (int r = 0; r < 3; ++r) acc[r] += t[r];
   }
-  for (int i = 0; i < 3; ++i) f[3 + i] = acc[i] / m;
+  for (int i = 0; i < 3; ++i) f[3 + i] = acc[i] * im;
   for (int i = 0; i < QM_NJ; ++i) f[6 + i] = k.vel[i];
 }
 

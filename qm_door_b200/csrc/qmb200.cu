@@ -399,7 +399,8 @@ struct qmb200_ctx {
   static const int kMaxChunks = 8;
   int nchunks = 1;
   cudaStream_t cs[kMaxChunks] = {nullptr};
-  cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr};
+  cudaStream_t side[kMaxChunks] = {nullptr};   // k_proj of a chunk runs here, beside its k_kin<2>
+  cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {nullptr}, ev_fork[kMaxChunks] = {nullptr}, ev_join[kMaxChunks] = {nullptr};
   int64_t bytes = 0;
   bool profiling = false;
   double kernel_ms[QMB200_NUM_KERNELS] = {0};
@@ -451,8 +452,14 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     { KernelTimer kt(c, KN_SCHEDULE, st); k_schedule<<<(nb + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
     { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, (size_t)NMAX * 40, st>>>(m, c->dM, c->dP, c->dS); }
     { KernelTimer kt(c, KN_KIN1, st); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
-    { KernelTimer kt(c, KN_PROJ, st); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, nb), 32 * kProjWarps, 0, st>>>(m); }
+    // the projection pivots only need the constraint rows of k_kin<1>: they run beside k_kin<2> (FP64-issue bound warps next to
+    // latency-bound ones) and join before k_lq
+    CUDA_OK(cudaEventRecord(c->ev_fork[ch], st));
+    CUDA_OK(cudaStreamWaitEvent(c->side[ch], c->ev_fork[ch], 0));
+    { KernelTimer kt(c, KN_PROJ, c->side[ch]); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, nb), 32 * kProjWarps, 0, c->side[ch]>>>(m); }
+    CUDA_OK(cudaEventRecord(c->ev_join[ch], c->side[ch]));
     { KernelTimer kt(c, KN_KIN2, st); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+    CUDA_OK(cudaStreamWaitEvent(st, c->ev_join[ch], 0));
     { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
     CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
@@ -521,7 +528,10 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   }
   for (int ch = 0; ch < c->nchunks; ++ch) {
     CUDA_OK(cudaStreamCreateWithFlags(&c->cs[ch], cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->side[ch], cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[ch], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork[ch], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[ch], cudaEventDisableTiming));
   }
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
@@ -569,7 +579,10 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->h_pending) cudaFreeHost(c->h_pending);
   for (int ch = 0; ch < qmb200_ctx::kMaxChunks; ++ch) {
     if (c->cs[ch]) { cudaStreamSynchronize(c->cs[ch]); cudaStreamDestroy(c->cs[ch]); }
+    if (c->side[ch]) { cudaStreamSynchronize(c->side[ch]); cudaStreamDestroy(c->side[ch]); }
     if (c->ev_done[ch]) cudaEventDestroy(c->ev_done[ch]);
+    if (c->ev_fork[ch]) cudaEventDestroy(c->ev_fork[ch]);
+    if (c->ev_join[ch]) cudaEventDestroy(c->ev_join[ch]);
   }
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->stream) cudaStreamDestroy(c->stream);
