@@ -39,7 +39,7 @@ int cport_sizes(int* out) {
 }
 
 void cport_kin_eval(const qmb200_model_desc* M, const double* x, const double* u, int deriv, double* w) {
-  kin_eval(SerialGroup(), *M, x, u, deriv != 0, w);
+  kin_eval(SerialGroup(), *M, x, u, deriv != 0 ? 2 : 0, w);
 }
 
 void cport_transcribe_node(const qmb200_model_desc* M, const qmb200_problem_desc* P, double t, double dt, int mode,

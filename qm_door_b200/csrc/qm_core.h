@@ -343,7 +343,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
     if (M.jtype[j] == 1) sincos(q[j], &s, &c);
     sc[2 * j] = s; sc[2 * j + 1] = c;
   }
-  g.sync();
+  g.sync(); QM_TICK(13);
   const int d0 = M.root6_standard ? 6 : 0;
   // local transforms of all joints at once (Rodrigues, Rp Rq), stored in the joint's own R | P | AX slots; the level-by-level
   // sweep then only composes them with the parent placement. A standard floating base (joints 0..5) is placed in closed
@@ -393,7 +393,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
       for (int r = 0; r < 3; ++r) lp[r] = M.pp[j][r] + la[r] * q[j];
     }
   }
-  g.sync();
+  g.sync(); QM_TICK(14);
   for (int d = d0; d <= M.max_depth; ++d) {
     QM_PFOR(g, j, QM_NJ) {
       if (M.depth[j] != d) continue;
@@ -410,6 +410,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
     }
     g.sync();
   }
+  QM_TICK(15);
   // P2: body inertial quantities about the world origin
   QM_PFOR(g, j, QM_NJ) {
     const double* R = w + KW_R + 9 * j;
@@ -452,7 +453,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
       }
     }
   }
-  g.sync();
+  g.sync(); QM_TICK(16);
   // P3: composite (subtree) inertias. One (joint, component) pair per work item: the base joints carry the whole tree,
   //     so a lane per joint would leave the phase waiting for six lanes that sum 24 bodies each.
   QM_PFOR(g, idx, QM_NJ * 10) {
@@ -465,7 +466,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
   }
   g.sync();
   QM_PFOR(g, r, 3) w[KW_COM + r] = w[KW_COMP + 1 + r] / w[KW_COMP];
-  g.sync();
+  g.sync(); QM_TICK(17);
   // P4: centroidal momentum matrix columns, frame Jacobian columns
   QM_PFOR(g, j, QM_NJ) {
     double S[6], h[6], t[3];
@@ -500,7 +501,7 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
       }
     }
   }
-  g.sync();
+  g.sync(); QM_TICK(18);
 }
 
 // Generalized velocity implied by the centroidal state/input: v = [Ab^-1 (m h_n - A_j v_j); v_j]
@@ -544,13 +545,13 @@ QM_HDN void centroidal_velocity(G g, const qmb200_model_desc& M, const double* x
     for (int c = 0; c < 6; ++c) acc += w[KW_ABINV + 6 * r + c] * w[KW_RHS + c];
     w[KW_VEL + r] = acc;
   }
-  g.sync();
+  g.sync(); QM_TICK(19);
 }
 
-// Velocity level (KW_VEL given): spatial velocities, body momenta, foot velocities and, if deriv, the q-derivatives
-// at fixed generalized velocity d(A v)/dq (KW_DH) and d(J_i v)/dq (KW_DFV).
+// Velocity level (KW_VEL given): spatial velocities, body momenta, foot velocities and the q-derivatives at fixed
+// generalized velocity: deriv >= 1: d(A v)/dq (KW_DH); deriv == 2: d(J_i v)/dq (KW_DFV) as well.
 template <class G>
-QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* w) {
+QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, int deriv, double* w) {
   // P7: spatial velocities and body momenta
   QM_PFOR(g, j, QM_NJ) {
     double S[6];
@@ -581,7 +582,7 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
     return;
   }
   // P8: subtree momenta (into KW_SV), one (joint, component) pair per work item
-  g.sync();
+  g.sync(); QM_TICK(20);
   QM_PFOR(g, idx, QM_NJ * 6) {
     const int j = idx / 6, c = idx - 6 * j;
     double acc = 0.0;
@@ -590,7 +591,7 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
       if ((mask >> i) & 1u) acc += w[KW_HB + 6 * i + c];
     w[KW_SV + idx] = acc;
   }
-  g.sync();
+  g.sync(); QM_TICK(21);
   // P9: d(A v)/dq_k and d(J_i v)/dq_k at fixed generalized velocity
   QM_PFOR(g, k, QM_NJ) {
     double S[6], X[6], IX[6], dL[3], dp[3], t[3];
@@ -619,6 +620,7 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
       w[KW_DH + r * QM_NJ + k] = dp[r];
       w[KW_DH + (3 + r) * QM_NJ + k] = dL[r] - t[r] - t2[r];
     }
+    if (deriv < 2) continue;
     for (int f = 0; f < QM_NFEET; ++f) {
       const int b = M.foot_joint[f];
       double du[3] = {0, 0, 0};
@@ -638,16 +640,16 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, bool deriv, double* 
       for (int r = 0; r < 3; ++r) w[KW_DFV + (3 * f + r) * QM_NJ + k] = du[r];
     }
   }
-  g.sync();
+  g.sync(); QM_TICK(22);
 }
 
 // Forward kinematics + centroidal quantities of one configuration, optionally with the generalized
 // velocity implied by (x,u) and the q-derivatives at fixed velocity needed for the linearisation.
-//   q = x[6:30];   u != nullptr -> velocity level;   deriv -> KW_DH / KW_DFV as well
+//   q = x[6:30];   u != nullptr -> velocity level;   deriv 1 -> KW_DH, 2 -> KW_DH and KW_DFV as well
 template <class G>
-QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, bool deriv, double* w,
+QM_HDN void kin_eval(G g, const qmb200_model_desc& M, const double* x, const double* u, int deriv, double* w,
                      bool jac = true) {
-  kin_positions(g, M, x + 6, w, jac || deriv);
+  kin_positions(g, M, x + 6, w, jac || deriv != 0);
   if (u == nullptr) return;
   centroidal_velocity(g, M, x, u, w);
   kin_velocities(g, M, deriv, w);

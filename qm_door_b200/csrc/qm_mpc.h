@@ -72,7 +72,8 @@ QM_HD int mode_index(const double* events, int nev, double t) {
 // [upstream] RelaxedBarrierPenalty
 QM_HD void relaxed_barrier(double h, double mu, double delta, double* v, double* d1, double* d2) {
   if (h > delta) {
-    *v = -mu * log(h); *d1 = -mu / h; *d2 = mu / (h * h);
+    const double ih = 1.0 / h;
+    *v = -mu * log(h); *d1 = -mu * ih; *d2 = mu * ih * ih;
   } else {
     const double z = (h - 2.0 * delta) / delta;
     *v = mu * (-log(delta) + 0.5 * z * z - 0.5); *d1 = mu * (h - 2.0 * delta) / (delta * delta); *d2 = mu / (delta * delta);
@@ -276,7 +277,7 @@ QM_HDN void flow_rows(G g, const qmb200_model_desc& M, double gravity, const dou
         double arm[3], t[3];
         for (int r = 0; r < 3; ++r) arm[r] = w[KW_FPOS + 3 * ft + r] - w[KW_COM + r];
         cross3(arm, u + 3 * ft, t);
-        v += t[i - 3];
+        v += (i == 3) ? t[0] : ((i == 4) ? t[1] : t[2]);       // no dynamically indexed local array
       }
       v /= m;
     } else {
@@ -286,48 +287,49 @@ QM_HDN void flow_rows(G g, const qmb200_model_desc& M, double gravity, const dou
   }
   if (Fr != nullptr) {
     const double im = 1.0 / m;
-    // rows 0..2 (normalised angular momentum rate): the three rows of a column come from one vector, so a work item is a
-    // column (the per-entry version repeated the four cross products, and their divisions by m, for every row)
+    // One work item per column c of [df/dx | df/du]: the nine entries of a column share their operands (the three angular
+    // rows come from one vector, the six v_b = A_b^-1 (m h - A_j v_j) rows from one column of d(A v)/dq or of A_j), and a
+    // warp executes the instructions of every branch its lanes take, so per-entry items paid for all column kinds at once.
     QM_PFOR(g, c, 60) {
-      double v[3] = {0.0, 0.0, 0.0};
-      if (c >= 6 && c < 30) {                       // d/dq_k sum_i (p_i - c) x f_i / m
-        const int k = c - 6;
-        double ac[3];
-        for (int rr = 0; rr < 3; ++rr) ac[rr] = w[KW_ACM + rr * QM_NJ + k] * im;
-        for (int ft = 0; ft < 4; ++ft) {
-          double d[3];
-          for (int rr = 0; rr < 3; ++rr) d[rr] = w[KW_FJ + (3 * ft + rr) * QM_NJ + k] - ac[rr];
-          cross3_add(d, u + 3 * ft, v);
-        }
+      double v[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (c < 6) {                                  // d v_b / d h
+        for (int rr = 0; rr < 6; ++rr) v[3 + rr] = m * w[KW_ABINV + 6 * rr + c];
       } else if (c >= 30 && c < 42) {               // d/df_i: (p_i - c) x e_d / m
         const int ft = (c - 30) / 3, d = (c - 30) % 3;
-        double arm[3], e[3] = {0, 0, 0};
-        e[d] = 1.0;
+        double arm[3];
+        const double e[3] = {d == 0 ? 1.0 : 0.0, d == 1 ? 1.0 : 0.0, d == 2 ? 1.0 : 0.0};
         for (int rr = 0; rr < 3; ++rr) arm[rr] = w[KW_FPOS + 3 * ft + rr] - w[KW_COM + rr];
         cross3(arm, e, v);
+        for (int r = 0; r < 3; ++r) v[r] *= im;
+      } else {                                      // joint position (6..29) or joint velocity (42..59) columns
+        const bool isq = c < 30;
+        const double* X = isq ? (w + KW_DH + (c - 6)) : (w + KW_ACM + 6 + (c - 42));
+        double xc[6];
+        for (int cc = 0; cc < 6; ++cc) xc[cc] = X[cc * QM_NJ];
+        for (int rr = 0; rr < 6; ++rr) {
+          const double* Bi = w + KW_ABINV + 6 * rr;
+          double a = 0.0;
+          for (int cc = 0; cc < 6; ++cc) a -= Bi[cc] * xc[cc];
+          v[3 + rr] = a;
+        }
+        if (isq) {                                  // d/dq_k sum_i (p_i - c) x f_i / m
+          const int k = c - 6;
+          double ac[3];
+          for (int rr = 0; rr < 3; ++rr) ac[rr] = w[KW_ACM + rr * QM_NJ + k] * im;
+          for (int ft = 0; ft < 4; ++ft) {
+            double d[3];
+            for (int rr = 0; rr < 3; ++rr) d[rr] = w[KW_FJ + (3 * ft + rr) * QM_NJ + k] - ac[rr];
+            cross3_add(d, u + 3 * ft, v);
+          }
+          for (int r = 0; r < 3; ++r) v[r] *= im;
+        }
       }
-      for (int r = 0; r < 3; ++r) Fr[60 * r + c] = v[r] * im;
-    }
-    // rows 3..8: v_b = A_b^-1 (m h - A_j v_j)
-    QM_PFOR(g, i2, 360) {
-      const int idx = 180 + i2;
-      const int rr = i2 / 60, c = i2 % 60;
-      double v = 0.0;
-      const double* Bi = w + KW_ABINV + 6 * rr;
-      if (c < 6) {
-        v = m * Bi[c];
-      } else if (c < 30) {
-        const int k = c - 6;
-        for (int cc = 0; cc < 6; ++cc) v -= Bi[cc] * w[KW_DH + cc * QM_NJ + k];
-      } else if (c >= 42) {
-        const int l = c - 42;
-        for (int cc = 0; cc < 6; ++cc) v -= Bi[cc] * w[KW_ACM + cc * QM_NJ + 6 + l];
-      }
-      Fr[idx] = v;
-      if (vb_shadow != nullptr) vb_shadow[i2] = v;   // rows of v_b = A_b^-1(...) kept close for the constraint rows
+      for (int r = 0; r < 9; ++r) Fr[60 * r + c] = v[r];
+      if (vb_shadow != nullptr)                     // rows of v_b kept close for the constraint rows
+        for (int rr = 0; rr < 6; ++rr) vb_shadow[60 * rr + c] = v[3 + rr];
     }
   }
-  g.sync();
+  g.sync(); QM_TICK(23);
 }
 
 // ------------------------------------------------------------------------------------------ quaternions (x,y,z,w)
@@ -386,6 +388,32 @@ QM_HDN void node_reference(const qmb200_model_desc& M, const qmb200_problem_desc
     if ((mode >> (3 - ft)) & 1) ref[RF_U + 3 * ft + 2] = M.total_mass * P.gravity / ns;   // [upstream] weightCompensatingInput
 }
 
+// The same over a thread group: one lane per component of x_ref / u_nominal, the end-effector reference on the last lane.
+// No trailing sync: the caller's next full sync publishes `ref`.
+template <class G>
+QM_HDN void node_reference_group(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, int mode,
+                                 const double* tt, const double* ts, int kt, double* ref) {
+  int i; double a;
+  time_segment(t, tt, kt, &i, &a);
+  const double* lhs = ts + QM_NTARGET * i;
+  const double* rhs = ts + QM_NTARGET * (i + 1);
+  const int ns = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
+  QM_PFOR(g, c, 32) {
+    if (c < 30) {
+      ref[RF_X + c] = (kt > 1) ? a * lhs[c] + (1.0 - a) * rhs[c] : ts[c];
+      const bool fz = c < 12 && (c % 3) == 2 && ((mode >> (3 - c / 3)) & 1);
+      ref[RF_U + c] = fz ? M.total_mass * P.gravity / ns : 0.0;                      // [upstream] weightCompensatingInput
+    } else if (c == 31) {
+      if (kt > 1) {
+        for (int r = 0; r < 3; ++r) ref[RF_EEP + r] = a * lhs[30 + r] + (1.0 - a) * rhs[30 + r];
+        quat_slerp(lhs + 33, rhs + 33, 1.0 - a, ref + RF_EEQ);      // EndEffectorConstraint.cpp:90-102
+      } else {
+        for (int r = 0; r < 7; ++r) ref[RF_EEP + r] = ts[30 + r];
+      }
+    }
+  }
+}
+
 // End-effector error e[6] = [p - p_ref ; quaternionDistance(q, q_ref)] and, if JE != nullptr, de/dq [6][24]
 // from the frame Jacobian in the kinematics workspace (one thread computes e and the 3x3 map, all threads JE).
 template <class G>
@@ -428,11 +456,12 @@ QM_HD void cone_terms(const qmb200_problem_desc& P, const double* F, double* c) 
   const double t2 = F[0] * F[0] + F[1] * F[1] + P.fric_reg;
   const double tn = sqrt(t2);
   c[0] = P.fric_mu * (F[2] + P.fric_grip) - tn;
-  c[1] = -F[0] / tn; c[2] = -F[1] / tn; c[3] = P.fric_mu;
-  const double p32 = tn * t2;
-  c[4] = -(F[1] * F[1] + P.fric_reg) / p32;
-  c[5] = F[0] * F[1] / p32;
-  c[6] = -(F[0] * F[0] + P.fric_reg) / p32;
+  const double itn = 1.0 / tn;
+  c[1] = -F[0] * itn; c[2] = -F[1] * itn; c[3] = P.fric_mu;
+  const double ip32 = itn / t2;
+  c[4] = -(F[1] * F[1] + P.fric_reg) * ip32;
+  c[5] = F[0] * F[1] * ip32;
+  c[6] = -(F[0] * F[0] + P.fric_reg) * ip32;
   relaxed_barrier(c[0], P.fric_bar_mu, P.fric_bar_delta, c + 7, c + 8, c + 9);
 }
 
@@ -657,10 +686,7 @@ template <class G>
 QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, double t, double dt, int mode,
                        const double* zvel, const double* tt, const double* ts, int kt, const double* x, const double* u,
                        double* kw, double* scr, NodeIO io) {
-  int nvc = 0;
-  for (int ft = 0; ft < 4; ++ft) nvc += ((mode >> (3 - ft)) & 1) ? 3 : 1;
-  const int nv = nvc;                 // velocity-constraint rows: 3 per stance foot, 1 per swing foot
-  if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, scr);
+  node_reference_group(g, M, P, t, mode, tt, ts, kt, scr);
   // barrier terms of the node: friction cones of the stance feet, arm position / velocity boxes (independent lanes)
   QM_PFOR(g, it, 16) {
     if (it < 4) {
@@ -680,52 +706,51 @@ QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_des
       io.aux[NA_BOXV + i] = v1 + v2;
     }
   }
-  kin_eval(g, M, x, u, true, kw);
+  QM_TICK(24);
+  kin_eval(g, M, x, u, 2, kw);
   // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) velocity arrays SV | V | HB of the workspace
   flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_SV);
   ee_terms(g, kw, scr, io.e6, scr + RF_SIZE, io.je);
+  QM_TICK(25);
   {
-    const double* Fr1 = kw + KW_SV - 180;  // Fr1[(3 + cc) * 60 + c] -> shadow[cc * 60 + c]
-    QM_PFOR(g, idx, nv * 49) {
-      const int row = idx / 49, c = idx % 49;
-      // map row -> (foot, component)
-      int ft = 0, d = 0, acc = 0;
-      for (int f2 = 0; f2 < 4; ++f2) {
-        const int cnt = ((mode >> (3 - f2)) & 1) ? 3 : 1;
-        if (row < acc + cnt) { ft = f2; d = (cnt == 3) ? (row - acc) : 2; break; }
-        acc += cnt;
+    // One work item per column of [Dv | C | e]: the six v_b entries of the column are loaded once, then the rows follow
+    // (3 per stance foot, the normal one per swing foot).
+    const double* vb = kw + KW_SV;               // the six v_b rows of [df/dx | df/du], leading dimension 60
+    const double zv[4] = {zvel[0], zvel[1], zvel[2], zvel[3]};
+    QM_PFOR(g, c, 49) {
+      double eq = 0.0;                             // sum of squares of the constraint values (last column)
+      const int col = (c < 18) ? 42 + c : c - 18;
+      double fc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      if (c < 48) for (int cc = 0; cc < 6; ++cc) fc[cc] = vb[60 * cc + col];
+      int row = 0;
+      for (int ft = 0; ft < 4; ++ft) {
+        const bool stance = (mode >> (3 - ft)) & 1;
+        for (int d = stance ? 0 : 2; d < 3; ++d, ++row) {
+          const double* J = kw + KW_FJ + (3 * ft + d) * QM_NJ;
+          double v;
+          if (c < 18) v = J[6 + c];                                                    // d v_foot / d u_joint
+          else if (c < 48) v = (col >= 6) ? kw[KW_DFV + (3 * ft + d) * QM_NJ + col - 6] : 0.0;   // d v_foot / d x
+          else {
+            v = kw[KW_FVEL + 3 * ft + d];
+            if (!stance) v -= zv[ft];               // normal velocity: v_z - zdot_ref (QMPreComputation.cpp:56-71)
+            eq += v * v;
+          }
+          if (c < 48) for (int cc = 0; cc < 6; ++cc) v += J[cc] * fc[cc];
+          io.T[49 * row + c] = v;
+        }
       }
-      const double* J = kw + KW_FJ + (3 * ft + d) * QM_NJ;
-      double v;
-      if (c < 18) {               // d v_foot / d u_joint
-        v = J[6 + c];
-        for (int cc = 0; cc < 6; ++cc) v += J[cc] * Fr1[(3 + cc) * 60 + 42 + c];
-      } else if (c < 48) {        // d v_foot / d x
-        const int xc = c - 18;
-        v = (xc >= 6) ? kw[KW_DFV + (3 * ft + d) * QM_NJ + xc - 6] : 0.0;
-        for (int cc = 0; cc < 6; ++cc) v += J[cc] * Fr1[(3 + cc) * 60 + xc];
-      } else {
-        v = kw[KW_FVEL + 3 * ft + d];
-        if (!((mode >> (3 - ft)) & 1)) v -= zvel[ft];       // normal velocity: v_z - zdot_ref (QMPreComputation.cpp:56-71)
-      }
-      io.T[idx] = v;
+      if (c == 48) io.e6[6] = eq;
     }
   }
   QM_PFOR(g, i, 30) io.x2[i] = x[i] + dt * io.f1[i];
   QM_PFOR(g, i, RF_SIZE) io.aux[NA_REF + i] = scr[i];
-  g.sync();
-  if (g.tid() == 0) {
-    double eq = 0.0;
-    for (int rr = 0; rr < nv; ++rr) eq += io.T[49 * rr + 48] * io.T[49 * rr + 48];
-    io.e6[6] = eq;
-  }
-  g.sync();
+  g.sync(); QM_TICK(26);
 }
 
 // Kinematics at (x + dt f1, u) with derivatives ([upstream] RK2 sensitivity integrator = Heun): second flow map rows.
 template <class G>
 QM_HDN void node_eval2(G g, const qmb200_model_desc& M, const qmb200_problem_desc& P, const double* u, double* kw, NodeIO io) {
-  kin_eval(g, M, io.x2, u, true, kw);
+  kin_eval(g, M, io.x2, u, 1, kw);               // d(J_i v)/dq is only needed by the constraint rows of the first stage
   flow_rows(g, M, P.gravity, kw, io.x2, u, io.f2, io.fr2);
 }
 
@@ -752,6 +777,7 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
   double* RPM = W + TW_RPM;
   double* RPX = io.fr1;                                          // valid from L3 on (fr1 | fr2 are dead then)
   double* RPU = io.T;                                            // valid from L3 on (T is dead once T2 is formed)
+  QM_TICK(27);
   // ---- L1: T2 = Dinv T; Q dx, R du
   mm<1, false>(g, nv, 49, nv, io.dinv, 16, T, 49, (const double*)nullptr, 0, 1.0, T2, 49);
   rows_dot(g, 60, 30, [](int) { return 0.0; },
@@ -761,7 +787,7 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
              return wrow[j] * (xv[j] - ref[(i < 30 ? RF_X : RF_U) + j]);
            },
            [&](int i, double v) { W[TW_TQ + i] = v; });           // TW_TR follows TW_TQ
-  g.sync();
+  g.sync(); QM_TICK(28);
   // ---- L2: cost quadratic approximation (forward Euler, * dt), discrete dynamics (Heun sensitivities), projection block
   {
     double shift = 0.0;
@@ -850,7 +876,7 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
       role[i] = v;
     }
   }
-  g.sync();
+  g.sync(); QM_TICK(29);
   // ---- L3: r' = r + R Pe, b~ = b + B Pe; baseline performance; A~ = A + B Px, B~ = B Pu, rows [pivots; frees] of R Px, R Pu
   rows_dot(g, nsel + 30, 30, [&](int i) { return (i < nsel) ? W[TW_RV + SEL[i]] : W[TW_b + i - nsel]; },
            [&](int i, int c) { return ((i < nsel) ? RPM[30 * i + c] : BPM[30 * (i - nsel) + c]) * W[TW_PEP + c]; },
@@ -899,7 +925,7 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
     mm<3, false>(g, 30, nut, nv, BPM, 30, W + TW_PUC, QM_NUT, BPM + nv, 30, 1.0, sb + SB_B, QM_NUT, 6);
     mm<3, false>(g, nsel, nut, nv, RPM, 30, W + TW_PUC, QM_NUT, RPM + nv, 30, 1.0, RPU, QM_NUT, 2);
   }
-  g.sync();
+  g.sync(); QM_TICK(30);
   // ---- L4: Q~ = Q + Px' R Px, P~ = Pu' R Px, R~ = Pu' R Pu, q~ = q + Px' r', r~ = Pu' r'
   mm<2, true>(g, 30, 30, nv, PXn, 49, RPX, 30, sb + SB_Q, 30, -1.0, sb + SB_Q, 30, 0);
   if (nut > 0) {
@@ -920,7 +946,7 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
     sb[SB_NUT] = (double)nut;
     if (io.piv[PI_STATUS]) status_or(status_out, io.piv[PI_STATUS]);
   }
-  g.sync();
+  g.sync(); QM_TICK(31);
 }
 
 // Fused form (host port / tests): both kinematics evaluations, the projection pivots and the LQ assembly on one workspace.
@@ -962,7 +988,7 @@ QM_HDN void terminal_node(G g, const qmb200_model_desc& M, const qmb200_problem_
                           double* sb, double* perf) {
   const bool deriv = JE != nullptr;
   if (g.tid() == 0) node_reference(M, P, t, mode, tt, ts, kt, ref);
-  kin_eval(g, M, x, (const double*)nullptr, false, kw, deriv);      // Jacobians only when the Gauss-Newton terms are wanted
+  kin_eval(g, M, x, (const double*)nullptr, 0, kw, deriv);      // Jacobians only when the Gauss-Newton terms are wanted
   ee_terms(g, kw, ref, e6, dq, JE);
   if (g.tid() == 0) {
     const double* e = e6;
@@ -996,6 +1022,18 @@ enum { RW_S = 0, RW_SA = 900, RW_SB = 1800, RW_K = RW_SB, RW_H = RW_SB + 540, RW
        RW_sv = RW_LI + 324, RW_sb = RW_sv + 30, RW_gv = RW_sb + 30, RW_kf = RW_gv + 18, RW_COL = RW_kf + 18, RW_SIZE = RW_COL + 40 };
 
 #if defined(__CUDACC__)
+// 1 / a for a pivot on the dependency chain: hardware seed (MUFU.RCP64H, ~2^-20) and two Newton steps, without the range
+// checks and the slow path of the IEEE division (pivots of an SPD block are normal numbers; a non-positive pivot is
+// flagged by the caller). Accurate to 1-2 ulp.
+__device__ __forceinline__ double rcp_newton(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+
 // In-place inverse of the symmetric positive definite n x n matrix Gm (shared memory, leading dimension QM_NUT, n <= 18)
 // by one warp: Gauss-Jordan sweeps without pivoting, column j of the matrix in the registers of lane j. In every sweep
 // the owner of the pivot column publishes the negated, scaled column through shared memory (col: 2 x 20 doubles, double
@@ -1015,7 +1053,7 @@ __device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, double* col,
       const double rc = r[c];                      // lane c: the pivot a_cc; other lanes: a_cj of their column
       if (lane == c) {
         if (!(rc > 0.0)) bad = true;
-        const double ip = 1.0 / rc;
+        const double ip = rcp_newton(rc);
 #pragma unroll
         for (int i = 0; i < QM_NUT; i += 2) {
           double2 v;

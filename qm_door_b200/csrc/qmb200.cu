@@ -9,7 +9,7 @@
 // The cycle can be pipelined over chunks of problems (one stream per chunk, run_cycle): B below is the chunk size.
 //   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
-//   k_trial      <<<(NMAX/128, B), 128>>>    thread per node: value-only evaluation of the trial step (single-pass tree walk in registers)
+//   k_trial      <<<B*NMAX/128, 128>>>       thread per (problem, node): value-only evaluation of the trial step (single-pass tree walk in registers)
 //   k_decide     <<<ceil(B/128), 128>>>      thread per problem: filter line-search acceptance
 //   k_finalize   <<<B, 64>>>                 thread per component: publish primal solution + warm start
 // There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb2
   double* xin = scr + RF_SIZE + 12;                     // x[30], u[30]
   NodeIO io = node_io_at(m.kin + o * KS_SIZE);
   WarpGroup g;
+  QM_TICK(-1);
   for (int i = lane; i < 60; i += 32) xin[i] = (i < 30) ? ((EVAL == 1) ? m.xs[o * 30 + i] : io.x2[i]) : m.us[o * 30 + i - 30];
   __syncwarp();
   if (EVAL == 1) {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(QM_LQ_THREADS, 4) k_lq(MpcBuffers m, const qmb
   const int n = nn - 1;
   BlockGroup g;
   const bool regular = (k < n) && (m.node_flag[o] != EV_PRE);
+  QM_TICK(-1);
   __shared__ uint64_t bar;
   if (regular && threadIdx.x == 0) {
     // stage the kinematics products of this node into the kinematics region of the workspace: one bulk copy (TMA)
@@ -258,9 +260,14 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
 // line-search evaluation: a thread per node (value-only single-pass tree walk in registers, qm_value.h)
 constexpr int kTrialThreads = 128;
 __global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
-                                                          const int* list) {
+                                                          const int* list, int nprob) {
   // first trial: every problem of the chunk; backtracking trials: only the problems k_decide listed as still pending
-  const int k = blockIdx.x * kTrialThreads + threadIdx.x, b = list ? list[m.b0 + blockIdx.y] : m.b0 + blockIdx.y;
+  // (problem, node) pairs are laid over the threads back to back: a block per problem would leave its last warp with a
+  // handful of nodes (105 nodes on 128 threads)
+  const int gid = blockIdx.x * kTrialThreads + threadIdx.x;
+  const int pi = gid / m.NMAX, k = gid - pi * m.NMAX;
+  if (pi >= nprob) return;
+  const int b = list ? list[m.b0 + pi] : m.b0 + pi;
   const double* ls = m.ls + (size_t)b * LS_SIZE;
   if (ls[LS_DONE] != 0.0) return;
   const int nn = m.nn[b];
@@ -463,7 +470,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
     { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
     CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
-    { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, nb), kTrialThreads, 0, st>>>(m, c->dM, c->dP, nullptr); }
+    { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(nb * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP, nullptr, nb); }
     { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
     CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
@@ -481,7 +488,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
       const int npend = c->h_pending[ch];
       if (npend == 0) break;
       CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
-      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<dim3((NMAX + kTrialThreads - 1) / kTrialThreads, npend), kTrialThreads, 0, st>>>(m, c->dM, c->dP, c->d_list); }
+      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(npend * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP, c->d_list, npend); }
       { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
       CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
