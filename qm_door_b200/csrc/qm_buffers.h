@@ -164,13 +164,20 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
   }
   QM_PFOR(g, i, 30) { dxs[30 * n + i] = R[i]; dus[30 * n + i] = 0.0; }
   g.sync();
-  // step norms and baseline performance: sequential sums in a fixed order (bit-reproducible)
+  // step norms and baseline performance: sums in a fixed order (bit-reproducible for a given group size): every thread sums
+  // a strided subset of the 30 (n + 1) components, thread 0 adds the partial sums in thread order
+  double* part = W + RW_SA;                         // 2 x nt partial sums (SA is idle; clear of the forward scratch R)
+  {
+    double px = 0.0, pu = 0.0;
+    for (int idx = g.tid(); idx < 30 * (n + 1); idx += g.nt()) { px += dxs[idx] * dxs[idx]; pu += dus[idx] * dus[idx]; }
+    part[2 * g.tid()] = px; part[2 * g.tid() + 1] = pu;
+  }
+  g.sync();
   if (g.tid() == 0) {
     double arm = R[80];
     for (int j = 0; j < 30; ++j) arm += term[SB_q + j] * R[j];
     double sx = 0.0, su = 0.0;
-    for (int k = 0; k <= n; ++k)
-      for (int i = 0; i < 30; ++i) { sx += dxs[30 * k + i] * dxs[30 * k + i]; su += dus[30 * k + i] * dus[30 * k + i]; }
+    for (int t = 0; t < g.nt(); ++t) { sx += part[2 * t]; su += part[2 * t + 1]; }
     double d0 = 0.0;
     for (int i = 0; i < 30; ++i) d0 += dxs[i] * dxs[i];
     const double* pf = m.perf_base + (size_t)b * NMAX * PF_SIZE;

@@ -1051,16 +1051,19 @@ __device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, double* col,
     if (c < n) {                                   // uniform across the warp
       double* cb = col + 20 * (c & 1);
       const double rc = r[c];                      // lane c: the pivot a_cc; other lanes: a_cj of their column
+      double rce = rc;                             // 0 in the pivot lane: its column is final once scaled (no per-row select)
       if (lane == c) {
         if (!(rc > 0.0)) bad = true;
         const double ip = rcp_newton(rc);
 #pragma unroll
+        for (int i = 0; i < QM_NUT; ++i) r[i] = (i == c) ? ip : -r[i] * ip;   // -a_ic / a_cc, and 1 / a_cc in the pivot position
+#pragma unroll
         for (int i = 0; i < QM_NUT; i += 2) {
           double2 v;
-          v.x = (i == c) ? ip : -r[i] * ip;        // -a_ic / a_cc, and 1 / a_cc in the pivot position
-          v.y = (i + 1 == c) ? ip : -r[i + 1] * ip;
+          v.x = r[i]; v.y = r[i + 1];
           reinterpret_cast<double2*>(cb)[i >> 1] = v;
         }
+        rce = 0.0;
       }
       __syncwarp();
       double2 m2[QM_NUT / 2];
@@ -1070,7 +1073,7 @@ __device__ __forceinline__ void spd_inverse_warp(double* Gm, int n, double* col,
       for (int i = 0; i < QM_NUT; ++i) {
         if (i != c) {
           const double mlt = (i & 1) ? m2[i >> 1].y : m2[i >> 1].x;
-          r[i] = (lane == c) ? mlt : r[i] + mlt * rc;
+          r[i] = fma(mlt, rce, r[i]);
         }
       }
       const double p = (c & 1) ? m2[c >> 1].y : m2[c >> 1].x;
