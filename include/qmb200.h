@@ -124,6 +124,8 @@ int64_t qmb200_device_bytes(qmb200_ctx* ctx);
  *   qmb200_wbc_create / destroy    <- HierarchicalWbc construction + loadTasksSetting in QMController::setupWbc
  *                                     (qm_controllers/src/QMController.cpp:273-277, qm_wbc/src/WbcBase.cpp:22-72,597-627)
  *   qmb200_load_wbc                <- WbcBase::loadTasksSetting + the dynamic_reconfigure defaults (qm_wbc/cfg/wbcWigeht.cfg:7-47)
+ *   qmb200_actuator_batch[_dev]    <- QMController::updateControlLaw (QMController.cpp:178-191) + QMHWSim::writeSim
+ *                                       (qm_gazebo/src/QMHWSim.cpp:98-114)
  *   qmb200_wbc_batch[_dev]         <- WbcBase::update(stateDesired, inputDesired, rbdStateMeasured, mode, period, time)
  *                                     (qm_wbc/include/qm_wbc/WbcBase.h:31-32, called at QMController.cpp:147), B independent solves:
  *                                     x_des[B][30] u_des[B][30] rbd[B][55] mode[B] period[B] time[B] -> cmd[B][54] = [accelerations(24);
@@ -145,6 +147,25 @@ int qmb200_wbc_batch_dev(qmb200_wbc_ctx* ctx, const double* x_des, const double*
 int qmb200_wbc_sync(qmb200_wbc_ctx* ctx);
 void* qmb200_wbc_stream(qmb200_wbc_ctx* ctx);
 int qmb200_wbc_kernel_time(qmb200_wbc_ctx* ctx, double* total_ms, int64_t* launches, int32_t reset);
+
+/* Joint-level control law + simulated actuator with transport delay, the stage behind the whole-body controller in the
+ * reference's simulation loop:
+ *   QMController::updateControlLaw (qm_controllers/src/QMController.cpp:178-191, inputs formed at :147-157) and
+ *   QMHWSim::writeSim (qm_gazebo/src/QMHWSim.cpp:98-114; delay: qm_gazebo/config/default.yaml:2).
+ * One call = one control tick of every problem of the WBC context (its batch, its stream). The context keeps the delay
+ * buffers (QMB200_ACT_CAPACITY commands per problem, allocated on first use) and the command each joint handle holds.
+ * time_ns[B]: simulation clock in integer nanoseconds (ros::Time arithmetic); period_ns: tick length (a tick with
+ * time_ns == period_ns clears the buffer, as the reference does on simulation reset); obs_time[B]: controller observation time
+ * (legs are commanded only after leg_enable_time); x_des, u_des [B][30]: evaluated policy; cmd [B][54]: WBC output;
+ * q, v [B][18]: measured joint positions / velocities; tau [B][18]: torque applied to the joints; status[B]: 0 or 64 (overflow). */
+void qmb200_actuator_defaults(qmb200_actuator_desc* desc);
+int qmb200_actuator_batch(qmb200_wbc_ctx* ctx, const qmb200_actuator_desc* desc, const int64_t* time_ns, int64_t period_ns,
+                          const double* obs_time, const double* x_des, const double* u_des, const double* cmd, const double* q,
+                          const double* v, double* tau, int32_t* status);
+int qmb200_actuator_batch_dev(qmb200_wbc_ctx* ctx, const qmb200_actuator_desc* desc, const int64_t* time_ns, int64_t period_ns,
+                              const double* obs_time, const double* x_des, const double* u_des, const double* cmd, const double* q,
+                              const double* v, double* tau, int32_t* status);
+int qmb200_actuator_reset(qmb200_wbc_ctx* ctx);
 
 #ifdef __cplusplus
 }

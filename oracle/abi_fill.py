@@ -181,6 +181,27 @@ class CPort:
         return K
 
 
+class CPortActuator:
+    """CPU port of the control law + delayed actuator with caller-owned state (same call shape as the CUDA C-ABI)."""
+
+    def __init__(self, desc, n, capacity=32):
+        self.lib, self.desc, self.n = load_cport(), desc, n
+        self.stamp = np.zeros((n, capacity), dtype=np.int64)
+        self.buf = np.zeros((n, capacity, 18, 5))
+        self.hc = np.zeros((n, 2), dtype=np.int32)
+        self.last = np.zeros((n, 18, 5))
+
+    def step(self, time_ns, period_ns, obs_time, x_des, u_des, cmd, q, v):
+        dp = lambda a: a.ctypes.data_as(C.c_void_p)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        time_ns = np.ascontiguousarray(time_ns, dtype=np.int64)
+        obs_time, x_des, u_des, cmd, q, v = f(obs_time), f(x_des), f(u_des), f(cmd), f(q), f(v)
+        tau, status = np.zeros((self.n, 18)), np.zeros(self.n, dtype=np.int32)
+        self.lib.cport_actuator(C.byref(self.desc), self.n, dp(time_ns), C.c_int64(int(period_ns)), dp(obs_time), dp(x_des), dp(u_des),
+                                dp(cmd), dp(q), dp(v), dp(self.stamp), dp(self.buf), dp(self.hc), dp(self.last), dp(tau), dp(status))
+        return tau, status
+
+
 def pack_schedules(schedules, EMAX):
     """[(events, modes)] -> padded arrays (events padded with +1e30, modes with STANCE)."""
     B = len(schedules)

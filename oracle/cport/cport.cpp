@@ -166,6 +166,7 @@ int cport_feedback_gains(CportCtx* c, double* K) {
 
 // ---------------------------------------------------------------------------------------- WBC
 #include "../../qm_door_b200/csrc/qm_wbc.h"
+#include "../../qm_door_b200/csrc/qm_actuator.h"
 
 extern "C" {
 
@@ -185,6 +186,20 @@ int cport_wbc_batch(const qmb200_model_desc* M, const qmb200_wbc_desc* C, int B,
     memcpy(u_last + 30 * b, ud + 30 * b, sizeof(double) * 30);
   });
   return 0;
+}
+
+// Control law + simulated actuator, one tick of n problems; the caller owns the state arrays (zero-initialised):
+// stamp [n][CAP] int64, buf [n][CAP][18][5], hc [n][2] int32, last [n][18][5].
+void cport_actuator(const qmb200_actuator_desc* D, int n, const int64_t* time_ns, int64_t period_ns, const double* obs_time,
+                    const double* xd, const double* ud, const double* cmd, const double* q, const double* v, int64_t* stamp,
+                    double* buf, int32_t* hc, double* last, double* tau, int32_t* status) {
+  const size_t CAP = QMB200_ACT_CAPACITY;
+  for (size_t b = 0; b < (size_t)n; ++b) {
+    status[b] = 0;
+    actuator_step(SerialGroup(), *D, (long long)time_ns[b], (long long)period_ns, obs_time[b], xd + 30 * b, ud + 30 * b, cmd + 54 * b,
+                  q + 18 * b, v + 18 * b, (long long*)stamp + CAP * b, buf + CAP * 18 * ACT_NF * b, hc + 2 * b, last + 18 * ACT_NF * b,
+                  tau + 18 * b, status + b);
+  }
 }
 
 }  // extern "C"

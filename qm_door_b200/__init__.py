@@ -217,6 +217,14 @@ def load_problem(model, task_info=DEFAULT_TASK, reference_info=DEFAULT_REFERENCE
     return p, s, x
 
 
+def actuator_defaults():
+    """Gains and delay of the control law / simulated actuator (QMController.cpp:181-190, weight.cfg:7-8, default.yaml:2)."""
+    from ._abi import ActuatorDesc
+    d = ActuatorDesc()
+    lib().qmb200_actuator_defaults(C.byref(d))
+    return d
+
+
 def load_targets(task_info=DEFAULT_TASK, reference_info=DEFAULT_REFERENCE):
     """Constants of the command -> reference conversion (QmTargetTrajectoriesPublisher_node.cpp:268-272)."""
     from ._abi import TargetDesc
@@ -304,6 +312,24 @@ class WbcContext:
     def update_dev(self, x_des, u_des, rbd, mode, period, time, cmd, status):
         dp = lambda t: C.c_void_p(t.data_ptr())
         _check(self.L.qmb200_wbc_batch_dev(self.h, dp(x_des), dp(u_des), dp(rbd), dp(mode), dp(period), dp(time), dp(cmd), dp(status)))
+
+    def actuator(self, desc, time_ns, period_ns, obs_time, x_des, u_des, cmd, q, v):
+        """One tick of the control law + delayed actuator (QMController.cpp:178-191, QMHWSim.cpp:98-114) -> (tau [B][18], status)."""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        time_ns = np.ascontiguousarray(time_ns, dtype=np.int64)
+        obs_time, x_des, u_des, cmd, q, v = f(obs_time), f(x_des), f(u_des), f(cmd), f(q), f(v)
+        tau, status = np.zeros((self.B, 18)), np.zeros(self.B, dtype=np.int32)
+        _check(self.L.qmb200_actuator_batch(self.h, C.byref(desc), _p(time_ns), C.c_int64(int(period_ns)), _p(obs_time), _p(x_des),
+                                            _p(u_des), _p(cmd), _p(q), _p(v), _p(tau), _p(status)))
+        return tau, status
+
+    def actuator_dev(self, desc, time_ns, period_ns, obs_time, x_des, u_des, cmd, q, v, tau, status):
+        dp = lambda t: C.c_void_p(t.data_ptr())
+        _check(self.L.qmb200_actuator_batch_dev(self.h, C.byref(desc), dp(time_ns), C.c_int64(int(period_ns)), dp(obs_time), dp(x_des),
+                                                dp(u_des), dp(cmd), dp(q), dp(v), dp(tau), dp(status)))
+
+    def actuator_reset(self):
+        _check(self.L.qmb200_actuator_reset(self.h))
 
     def sync(self):
         _check(self.L.qmb200_wbc_sync(self.h))

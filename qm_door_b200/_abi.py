@@ -90,6 +90,16 @@ class TargetDesc(C.Structure):
     ]
 
 
+class ActuatorDesc(C.Structure):
+    _fields_ = [
+        ("leg_kp", C.c_double), ("leg_kd", C.c_double), ("arm_kp", C.c_double), ("arm_kd", C.c_double),
+        ("leg_enable_time", C.c_double), ("delay_ns", C.c_int64),
+    ]
+
+
+ACT_CAPACITY = 32
+
+
 def _set(arr, values):
     a = np.ctypeslib.as_array(arr)
     a[...] = np.asarray(values).reshape(a.shape)

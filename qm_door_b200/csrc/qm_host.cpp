@@ -571,4 +571,14 @@ int qmb200_load_wbc(const char* task_info, const qmb200_model_desc* M, qmb200_wb
   });
 }
 
+// Defaults of the control law and the simulated actuator: QMController.cpp:181-190 (legs kp 0, kd 3 after 10 s),
+// qm_controllers/cfg/weight.cfg:7-8 (arm kp 0, kd 0.5), qm_gazebo/config/default.yaml:2 (delay 0.009 s).
+void qmb200_actuator_defaults(qmb200_actuator_desc* D) {
+  if (!D) return;
+  D->leg_kp = 0.0; D->leg_kd = 3.0;
+  D->arm_kp = 0.0; D->arm_kd = 0.5;
+  D->leg_enable_time = 10.0;
+  D->delay_ns = 9000000;
+}
+
 }  // extern "C"

@@ -104,6 +104,19 @@ typedef struct qmb200_wbc_desc {
   int32_t reserved;
 } qmb200_wbc_desc;
 
+// Joint-level control law and simulated actuator with transport delay.
+// Control law: QMController::updateControlLaw (qm_controllers/src/QMController.cpp:178-191): legs (joints 0..11) are commanded
+// (q_des, v_des, kp 0, kd 3, tau) once the observation time exceeds 10 s, the arm (12..17) (q_des, 0, kp_arm_wbc, kd_arm_wbc, tau)
+// with the gains of qm_controllers/cfg/weight.cfg:7-8. Actuator: QMHWSim::writeSim (qm_gazebo/src/QMHWSim.cpp:98-114), delay of
+// qm_gazebo/config/default.yaml:2; ros::Time arithmetic is integer nanoseconds, so are the stamps here.
+typedef struct qmb200_actuator_desc {
+  double leg_kp, leg_kd;       // 0, 3
+  double arm_kp, arm_kd;       // 0, 0.5
+  double leg_enable_time;      // 10 s
+  int64_t delay_ns;            // 9 000 000
+} qmb200_actuator_desc;
+#define QMB200_ACT_CAPACITY 32   /* commands kept per problem; more than delay / period + 2 are never alive */
+
 #ifdef __cplusplus
 }
 #endif

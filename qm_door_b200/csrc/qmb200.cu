@@ -832,6 +832,7 @@ int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, 
 
 // ============================================================================================ whole-body controller
 #include "qm_wbc.h"
+#include "qm_actuator.h"
 
 constexpr int kWbcInDoubles = 30 + 30 + 56 + 32;   // xd, ud, rbd (padded), u_last (padded)
 constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
@@ -853,7 +854,24 @@ __global__ void __launch_bounds__(128) k_wbc(int B, const qmb200_model_desc* M, 
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
 
+// ---- control law + simulated actuator with transport delay: warp per problem, lane per joint
+__global__ void __launch_bounds__(128) k_actuator(int B, qmb200_actuator_desc D, const int64_t* time_ns, long long period_ns,
+                                                  const double* obs_time, const double* xd, const double* ud, const double* cmd,
+                                                  const double* q, const double* v, long long* stamp, double* buf, int* hc,
+                                                  double* last, double* tau, int32_t* status) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  if ((threadIdx.x & 31) == 0) status[b] = 0;
+  __syncwarp();
+  const size_t sb = (size_t)b;
+  actuator_step(WarpGroup(), D, (long long)time_ns[b], period_ns, obs_time[b], xd + 30 * sb, ud + 30 * sb, cmd + 54 * sb, q + 18 * sb,
+                v + 18 * sb, stamp + QMB200_ACT_CAPACITY * sb, buf + (size_t)QMB200_ACT_CAPACITY * 18 * ACT_NF * sb, hc + 2 * sb,
+                last + 18 * ACT_NF * sb, tau + 18 * sb, status + b);
+}
+
 struct qmb200_wbc_ctx {
+  // actuator state (allocated on first use): stamps, buffered commands, {head, count}, held command per joint
+  long long* act_stamp = nullptr; double* act_buf = nullptr; int* act_hc = nullptr; double* act_last = nullptr;
   int device = 0, B = 0;
   qmb200_model_desc* dM = nullptr;
   qmb200_wbc_desc* dC = nullptr;
@@ -924,7 +942,8 @@ int qmb200_wbc_destroy(qmb200_wbc_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->mode, c->status};
+  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->mode, c->status,
+                  c->act_stamp, c->act_buf, c->act_hc, c->act_last};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->e0) cudaEventDestroy(c->e0);
   if (c->e1) cudaEventDestroy(c->e1);
@@ -991,6 +1010,72 @@ int qmb200_wbc_batch(qmb200_wbc_ctx* c, const double* x_des, const double* u_des
   if (status) CUDA_OK(cudaMemcpyAsync(status, c->status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   wbc_harvest(c);
+  return 0;
+}
+
+static int actuator_state(qmb200_wbc_ctx* c, bool clear) {
+  const size_t B = c->B, CAP = QMB200_ACT_CAPACITY;
+  const bool fresh = !c->act_stamp;
+  if (fresh) {
+    CUDA_OK(cudaMalloc(&c->act_stamp, B * CAP * sizeof(long long)));
+    CUDA_OK(cudaMalloc(&c->act_buf, B * CAP * 18 * ACT_NF * sizeof(double)));
+    CUDA_OK(cudaMalloc(&c->act_hc, B * 2 * sizeof(int)));
+    CUDA_OK(cudaMalloc(&c->act_last, B * 18 * ACT_NF * sizeof(double)));
+  }
+  if (fresh || clear) {
+    CUDA_OK(cudaMemsetAsync(c->act_stamp, 0, B * CAP * sizeof(long long), c->stream));
+    CUDA_OK(cudaMemsetAsync(c->act_buf, 0, B * CAP * 18 * ACT_NF * sizeof(double), c->stream));
+    CUDA_OK(cudaMemsetAsync(c->act_hc, 0, B * 2 * sizeof(int), c->stream));
+    CUDA_OK(cudaMemsetAsync(c->act_last, 0, B * 18 * ACT_NF * sizeof(double), c->stream));
+  }
+  return 0;
+}
+
+int qmb200_actuator_reset(qmb200_wbc_ctx* c) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  return actuator_state(c, true);
+}
+
+int qmb200_actuator_batch_dev(qmb200_wbc_ctx* c, const qmb200_actuator_desc* desc, const int64_t* time_ns, int64_t period_ns,
+                              const double* obs_time, const double* x_des, const double* u_des, const double* cmd, const double* q,
+                              const double* v, double* tau, int32_t* status) {
+  if (!c || !desc || !time_ns || !obs_time || !x_des || !u_des || !cmd || !q || !v || !tau || !status)
+    return fail("qmb200_actuator_batch_dev: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  if (actuator_state(c, false) != 0) return -1;
+  k_actuator<<<(c->B + 3) / 4, 128, 0, c->stream>>>(c->B, *desc, time_ns, (long long)period_ns, obs_time, x_des, u_des, cmd, q, v,
+                                                    c->act_stamp, c->act_buf, c->act_hc, c->act_last, tau, status);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int qmb200_actuator_batch(qmb200_wbc_ctx* c, const qmb200_actuator_desc* desc, const int64_t* time_ns, int64_t period_ns,
+                          const double* obs_time, const double* x_des, const double* u_des, const double* cmd, const double* q,
+                          const double* v, double* tau, int32_t* status) {
+  if (!c || !desc || !time_ns || !obs_time || !x_des || !u_des || !cmd || !q || !v || !tau) return fail("qmb200_actuator_batch: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t B = c->B;
+  cudaStream_t st = c->stream;
+  // staging: [time_ns | obs_time | x_des | u_des | cmd | q | v | tau] doubles (time_ns as 8-byte integers), then the status words
+  const size_t nd = B * (1 + 1 + 30 + 30 + 54 + 18 + 18 + 18);
+  double* d = nullptr; int32_t* ds = nullptr;
+  CUDA_OK(cudaMallocAsync(&d, nd * sizeof(double), st));
+  CUDA_OK(cudaMallocAsync(&ds, B * sizeof(int32_t), st));
+  double *dt = d, *dobs = dt + B, *dx = dobs + B, *du = dx + 30 * B, *dc = du + 30 * B, *dq = dc + 54 * B, *dv = dq + 18 * B, *dtau = dv + 18 * B;
+  CUDA_OK(cudaMemcpyAsync(dt, time_ns, B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dobs, obs_time, B * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dx, x_des, B * 30 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(du, u_des, B * 30 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dc, cmd, B * 54 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dq, q, B * 18 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dv, v, B * 18 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (qmb200_actuator_batch_dev(c, desc, (const int64_t*)dt, period_ns, dobs, dx, du, dc, dq, dv, dtau, ds) != 0) return -1;
+  CUDA_OK(cudaMemcpyAsync(tau, dtau, B * 18 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, ds, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaFreeAsync(d, st));
+  CUDA_OK(cudaFreeAsync(ds, st));
+  CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
 
