@@ -157,7 +157,7 @@ def cpu_baseline_sample():
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_gpu(args, rank, world, local_rank):
+def run_gpu(args, rank, world, local_rank, result_fd=None):
     import torch
     import torch.distributed as dist
     import qm_door_b200 as q
@@ -342,7 +342,10 @@ def run_gpu(args, rank, world, local_rank):
             line["secondary"] = wbc_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line))
+        if result_fd is not None:
+            os.write(result_fd, (json.dumps(line) + "\n").encode())     # the process's real stdout (see main)
+        else:
+            print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -371,7 +374,17 @@ def main():
                "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__), "--gpus",
                str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
         raise SystemExit(subprocess.call(cmd))
-    run_gpu(args, rank, world, local_rank)
+    # stdout carries exactly one JSON line: libraries that write to file descriptor 1 while the bench runs (NCCL prints its
+    # version banner there) are sent to stderr, the descriptor is restored for the result line
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        run_gpu(args, rank, world, local_rank, result_fd=saved)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 if __name__ == "__main__":

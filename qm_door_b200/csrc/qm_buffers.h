@@ -171,6 +171,10 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
     double px = 0.0, pu = 0.0;
     for (int idx = g.tid(); idx < 30 * (n + 1); idx += g.nt()) { px += dxs[idx] * dxs[idx]; pu += dus[idx] * dus[idx]; }
     part[2 * g.tid()] = px; part[2 * g.tid() + 1] = pu;
+    // the baseline performance records of the nodes are staged by the whole group (one HBM round trip instead of one per node
+    // on thread 0); their sums below stay sequential in the node index
+    const double* pfg = m.perf_base + (size_t)b * NMAX * PF_SIZE;
+    for (int idx = g.tid(); idx < PF_SIZE * (n + 1); idx += g.nt()) part[2 * g.nt() + idx] = pfg[idx];
   }
   g.sync();
   if (g.tid() == 0) {
@@ -180,7 +184,7 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
     for (int t = 0; t < g.nt(); ++t) { sx += part[2 * t]; su += part[2 * t + 1]; }
     double d0 = 0.0;
     for (int i = 0; i < 30; ++i) d0 += dxs[i] * dxs[i];
-    const double* pf = m.perf_base + (size_t)b * NMAX * PF_SIZE;
+    const double* pf = part + 2 * g.nt();            // staged copy of the baseline performance records (see above)
     double c = 0.0, dy = d0, eq = 0.0;
     for (int k = 0; k <= n; ++k) { c += pf[PF_SIZE * k + PF_COST]; dy += pf[PF_SIZE * k + PF_DYN]; eq += pf[PF_SIZE * k + PF_EQ]; }
     double* ls = m.ls + (size_t)b * LS_SIZE;
@@ -192,12 +196,14 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
 }
 
 // Line-search decision for one problem (one thread). [upstream] SqpSolver::takeStep loop body.
-QM_HDN void decide_problem(const qmb200_solver_desc& S, const MpcBuffers& m, int b) {
+// pf: the trial performance records of the problem's nodes (stride PF_SIZE): the HBM array itself or a staged copy
+// (k_decide stages it with the whole warp; the sums stay sequential in the node index, so the result is the same).
+QM_HDN void decide_problem(const qmb200_solver_desc& S, const MpcBuffers& m, int b, const double* pf = nullptr) {
   double* ls = m.ls + (size_t)b * LS_SIZE;
   if (ls[LS_DONE] != 0.0) return;
   const int nn = m.nn[b];
   const double alpha = ls[LS_ALPHA];
-  const double* pf = m.perf_trial + (size_t)b * m.NMAX * PF_SIZE;
+  if (pf == nullptr) pf = m.perf_trial + (size_t)b * m.NMAX * PF_SIZE;
   double c = 0.0, dy = (1.0 - alpha) * (1.0 - alpha) * ls[LS_DX0SQ], eq = 0.0;
   for (int k = 0; k < nn; ++k) { c += pf[PF_SIZE * k + PF_COST]; dy += pf[PF_SIZE * k + PF_DYN]; eq += pf[PF_SIZE * k + PF_EQ]; }
   ls[LS_ITERS] += 1.0;

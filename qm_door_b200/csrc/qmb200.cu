@@ -10,7 +10,7 @@
 //   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
 //   k_trial      <<<B*NMAX/128, 128>>>       thread per (problem, node): value-only evaluation of the trial step (single-pass tree walk in registers)
-//   k_decide     <<<ceil(B/128), 128>>>      thread per problem: filter line-search acceptance
+//   k_decide     <<<ceil(B/4), 128>>>        warp per problem: stages the trial records, lane 0 takes the filter line-search decision
 //   k_finalize   <<<B, 64>>>                 thread per component: publish primal solution + warm start
 // There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
 #include <cuda_runtime.h>
@@ -297,10 +297,21 @@ __global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb
   out[PF_COST] = pf[PF_COST]; out[PF_DYN] = pf[PF_DYN]; out[PF_EQ] = pf[PF_EQ];
 }
 
-__global__ void __launch_bounds__(128) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending, int* list) {
-  const int b = m.b0 + blockIdx.x * blockDim.x + threadIdx.x;
+// warp per problem: the lanes stage the trial performance records of the nodes (coalesced), lane 0 decides (sequential sums)
+constexpr int kDecideWarps = 4;
+__global__ void __launch_bounds__(32 * kDecideWarps) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending, int* list) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = m.b0 + blockIdx.x * kDecideWarps + warp;
   if (b >= m.b0 + m.nb) return;
-  decide_problem(*S, m, b);
+  if (m.ls[(size_t)b * LS_SIZE + LS_DONE] != 0.0) return;
+  double* pf = smem + (size_t)warp * m.NMAX * PF_SIZE;
+  const double* src = m.perf_trial + (size_t)b * m.NMAX * PF_SIZE;
+  const int cnt = m.nn[b] * PF_SIZE;
+  for (int i = lane; i < cnt; i += 32) pf[i] = src[i];
+  __syncwarp();
+  if (lane != 0) return;
+  decide_problem(*S, m, b, pf);
   if (m.ls[(size_t)b * LS_SIZE + LS_DONE] == 0.0) list[m.b0 + atomicAdd(pending, 1)] = b;   // order only affects scheduling
 }
 
@@ -471,7 +482,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
     CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
     { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(nb * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP, nullptr, nb); }
-    { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
+    { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + kDecideWarps - 1) / kDecideWarps, 32 * kDecideWarps, (size_t)kDecideWarps * NMAX * PF_SIZE * sizeof(double), st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
     CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
   }
   CUDA_OK(cudaGetLastError());
@@ -489,7 +500,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
       if (npend == 0) break;
       CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
       { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(npend * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP, c->d_list, npend); }
-      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + 127) / 128, 128, 0, st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
+      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + kDecideWarps - 1) / kDecideWarps, 32 * kDecideWarps, (size_t)kDecideWarps * NMAX * PF_SIZE * sizeof(double), st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
       CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     { KernelTimer kt(c, KN_FINALIZE, st); k_finalize<<<nb, 64, 0, st>>>(m, t_out, x_out, u_out); }
