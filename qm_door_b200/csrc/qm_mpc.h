@@ -778,7 +778,8 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
   double* RPX = io.fr1;                                          // valid from L3 on (fr1 | fr2 are dead then)
   double* RPU = io.T;                                            // valid from L3 on (T is dead once T2 is formed)
   QM_TICK(27);
-  // ---- L1: T2 = Dinv T; Q dx, R du
+  // ---- L1: T2 = Dinv T; Q dx, R du; and everything of the assembly that does not need them (the warps that finish the small
+  //         products go straight on to the wide loops instead of waiting at a barrier): cost Hessians, discrete dynamics
   mm<1, false>(g, nv, 49, nv, io.dinv, 16, T, 49, (const double*)nullptr, 0, 1.0, T2, 49);
   rows_dot(g, 60, 30, [](int) { return 0.0; },
            [&](int i, int j) {
@@ -787,8 +788,6 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
              return wrow[j] * (xv[j] - ref[(i < 30 ? RF_X : RF_U) + j]);
            },
            [&](int i, double v) { W[TW_TQ + i] = v; });           // TW_TR follows TW_TQ
-  g.sync(); QM_TICK(28);
-  // ---- L2: cost quadratic approximation (forward Euler, * dt), discrete dynamics (Heun sensitivities), projection block
   {
     double shift = 0.0;
     for (int ft = 0; ft < 4; ++ft) if ((mode >> (3 - ft)) & 1) shift += CONE[10 * ft + 8] * (-P.fric_hess_shift);
@@ -819,17 +818,6 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
       const int pi = POS[i];
       if (pi < nsel) RPM[30 * pi + POS[j]] = dt * rv;
     }
-    QM_PFOR(g, i, 30) {
-      double qv = W[TW_TQ + i], rv = W[TW_TR + i];
-      if (i >= 6) {
-        const double* e = io.e6;
-        for (int rr = 0; rr < 6; ++rr) qv += (rr < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[rr * QM_NJ + i - 6] * e[rr];
-      }
-      if (i >= 24) { qv += BOX[2 * (i - 24)]; rv += BOX[2 * (i - 18)]; }
-      if (i < 12 && ((mode >> (3 - i / 3)) & 1)) { const double* c = CONE + 10 * (i / 3); rv += c[8] * c[1 + i % 3]; }
-      W[TW_QV + i] = dt * qv;
-      W[TW_RV + i] = dt * rv;
-    }
     const double* F1 = io.fr1;
     const double* F2 = io.fr2;
     const double hdt = 0.5 * dt, im = 1.0 / m;
@@ -856,6 +844,31 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
       BPM[30 * i + POS[j]] = bv;
     }
     QM_PFOR(g, i, 30) W[TW_b + i] = x[i] + hdt * (io.f1[i] + io.f2[i]) - xn[i];
+    QM_PFOR(g, i, 12) pb[PB_PEF + i] = ((mode >> (3 - i / 3)) & 1) ? 0.0 : -u[i];
+    int* role = (int*)(pb + PB_ROLE);
+    QM_PFOR(g, i, 32) {
+      int v;
+      if (i == 30) v = nv;
+      else if (i == 31) v = nut;
+      else { const int c = POS[i]; v = (c < nv) ? c : ((c < nsel) ? ROLE_FREE + c - nv : ROLE_NONE); }
+      role[i] = v;
+    }
+  }
+  g.sync(); QM_TICK(28);
+  // ---- L2: cost gradients, projection block (need T2 and Q dx, R du)
+  {
+    const double* JE = io.je;
+    QM_PFOR(g, i, 30) {
+      double qv = W[TW_TQ + i], rv = W[TW_TR + i];
+      if (i >= 6) {
+        const double* e = io.e6;
+        for (int rr = 0; rr < 6; ++rr) qv += (rr < 3 ? P.mu_ee_pos : P.mu_ee_ori) * JE[rr * QM_NJ + i - 6] * e[rr];
+      }
+      if (i >= 24) { qv += BOX[2 * (i - 24)]; rv += BOX[2 * (i - 18)]; }
+      if (i < 12 && ((mode >> (3 - i / 3)) & 1)) { const double* c = CONE + 10 * (i / 3); rv += c[8] * c[1 + i % 3]; }
+      W[TW_QV + i] = dt * qv;
+      W[TW_RV + i] = dt * rv;
+    }
     // Pe (permuted): pivot joint velocities from the velocity-constraint rows, frees 0, dropped swing-foot forces -u
     QM_PFOR(g, c, 30) W[TW_PEP + c] = (c < nv) ? -T2[49 * c + 48] : ((c < nsel) ? 0.0 : -u[SEL[c]]);
     QM_PFOR2(g, p, nv, a, QM_NUT) {
@@ -866,15 +879,6 @@ QM_HDN void node_lq(G g, const qmb200_model_desc& M, const qmb200_problem_desc& 
     }
     QM_PFOR2(g, p, nv, j, 30) pb[PB_PX + 30 * p + j] = -T2[49 * p + 18 + j];     // rows >= nv are never read (role)
     QM_PFOR(g, p, nv) pb[PB_PEC + p] = -T2[49 * p + 48];
-    QM_PFOR(g, i, 12) pb[PB_PEF + i] = ((mode >> (3 - i / 3)) & 1) ? 0.0 : -u[i];
-    int* role = (int*)(pb + PB_ROLE);
-    QM_PFOR(g, i, 32) {
-      int v;
-      if (i == 30) v = nv;
-      else if (i == 31) v = nut;
-      else { const int c = POS[i]; v = (c < nv) ? c : ((c < nsel) ? ROLE_FREE + c - nv : ROLE_NONE); }
-      role[i] = v;
-    }
   }
   g.sync(); QM_TICK(29);
   // ---- L3: r' = r + R Pe, b~ = b + B Pe; baseline performance; A~ = A + B Px, B~ = B Pu, rows [pivots; frees] of R Px, R Pu
