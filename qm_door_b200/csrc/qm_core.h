@@ -273,7 +273,7 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
 }
 
 // ------------------------------------------------------------------------------------------ kinematics workspace
-// Offsets (in doubles) into the kinematics workspace.
+// Offsets (in doubles) into the kinematics workspace. kin_velocities needs the full workspace (KW_SIZE).
 // Regions whose lifetimes do not overlap share storage: the q-derivatives DH | DFV (written by the last phase of
 // kin_velocities when deriv is requested) take the place of R | BODY (placements: dead after the body / frame phases; body
 // inertias: dead once the body momenta HB are formed), and so does F (CRBA columns, read by the whole-body controller only,
@@ -287,8 +287,7 @@ enum {
   KW_ACM = KW_COMP + QM_NJ * 10,     // [6][24]  centroidal momentum matrix
   KW_SV = KW_ACM + 6 * QM_NJ,        // [24][6]  S_j v_j  -> reused for subtree momenta
   KW_V = KW_SV + QM_NJ * 6,          // [24][6]  spatial velocity (w, vO) of each body, world origin
-  KW_HB = KW_V + QM_NJ * 6,          // [24][6]  body momentum (L0, p)
-  KW_FPOS = KW_HB + QM_NJ * 6,       // [4][3]
+  KW_FPOS = KW_V + QM_NJ * 6,        // [4][3]
   KW_FVEL = KW_FPOS + 12,            // [4][3]
   KW_EEP = KW_FVEL + 12,             // [3]
   KW_EER = KW_EEP + 3,               // [9]
@@ -304,7 +303,10 @@ enum {
   // ---- aliases (see above)
   KW_F = KW_R,                       // [24][6] composite momentum per unit joint rate I^c_j S_j = (L0, p)  (CRBA columns)
   KW_DH = KW_R,                      // [6][24]  d(A v)/dq at fixed v (centroidal)
-  KW_DFV = KW_DH + 6 * QM_NJ         // [4][3][24] d(J_i v)/dq at fixed v
+  KW_DFV = KW_DH + 6 * QM_NJ,        // [4][3][24] d(J_i v)/dq at fixed v
+  KW_HB = KW_EEJ                     // [24][6]  body momentum (L0, p): lives from kin_velocities' second phase to its subtree sums,
+                                     //          in the place of the end-effector Jacobian, whose readers (ee_terms, the whole-body
+                                     //          controller's copy) run between kin_positions and kin_velocities
 };
 static_assert(KW_DFV + 12 * QM_NJ <= KW_P, "DH | DFV must fit in R | BODY");
 

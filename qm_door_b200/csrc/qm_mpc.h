@@ -707,15 +707,19 @@ QM_HDN void node_eval1(G g, const qmb200_model_desc& M, const qmb200_problem_des
     }
   }
   QM_TICK(24);
-  kin_eval(g, M, x, u, 2, kw);
-  // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) velocity arrays SV | V | HB of the workspace
-  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_SV);
+  // kin_eval in its parts: the end-effector terms read the end-effector Jacobian before the velocity level reuses its storage
+  kin_positions(g, M, x + 6, kw, true);
   ee_terms(g, kw, scr, io.e6, scr + RF_SIZE, io.je);
+  centroidal_velocity(g, M, x, u, kw);
+  kin_velocities(g, M, 2, kw);
+  // the six v_b rows of [df/dx | df/du] are mirrored into the (now dead) arrays P | AX | COMP of the workspace (384 doubles)
+  static_assert(KW_AX == KW_P + 3 * QM_NJ && KW_COMP == KW_AX + 3 * QM_NJ, "the v_b shadow spans P | AX | COMP");
+  flow_rows(g, M, P.gravity, kw, x, u, io.f1, io.fr1, kw + KW_P);
   QM_TICK(25);
   {
     // One work item per column of [Dv | C | e]: the six v_b entries of the column are loaded once, then the rows follow
     // (3 per stance foot, the normal one per swing foot).
-    const double* vb = kw + KW_SV;               // the six v_b rows of [df/dx | df/du], leading dimension 60
+    const double* vb = kw + KW_P;                // the six v_b rows of [df/dx | df/du], leading dimension 60
     const double zv[4] = {zvel[0], zvel[1], zvel[2], zvel[3]};
     QM_PFOR(g, c, 49) {
       double eq = 0.0;                             // sum of squares of the constraint values (last column)

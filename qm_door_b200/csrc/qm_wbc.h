@@ -170,8 +170,9 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
   g.sync();
   kin_positions(g, M, ms, kw);
   QM_PFOR(g, k, QM_NJ) kw[KW_VEL + k] = ms[24 + k];
+  QM_PFOR(g, idx, 144) W[WA_JEE + idx] = kw[KW_EEJ + idx];     // before the velocity level reuses the storage (KW_HB)
   g.sync();
-  kin_velocities(g, M, false, kw);
+  kin_velocities(g, M, 0, kw);
   bias_forces(g, M, kw, C.gravity, W + WA_ACC, W + WA_FB);
   QM_PFOR(g, j, QM_NJ) {     // nle = S_j . sum of subtree forces (RNEA backward pass)
     double f[6] = {0, 0, 0, 0, 0, 0}, S[6];
@@ -197,7 +198,6 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
     W[WA_M + idx] = v;
   }
   QM_PFOR(g, idx, 288) W[WA_JF + idx] = kw[KW_FJ + idx];
-  QM_PFOR(g, idx, 144) W[WA_JEE + idx] = kw[KW_EEJ + idx];
   QM_PFOR(g, idx, 72) {      // angular Jacobian of the base frame (joint 5)
     const int r = idx / 24, k = idx % 24;
     W[WA_JBA + idx] = (((M.pathmask[5] >> k) & 1u) && M.jtype[k] == 1) ? kw[KW_AX + 3 * k + r] : 0.0;

@@ -55,6 +55,9 @@ def test_kinematics_and_analytic_derivatives(descs, oracle_inputs):
                                     @ v[..., None])[..., 0] for i in range(4)], -1)
         assert rel_l2(get("DH", 144, (6, 24)), ce.cstep_jacobian(hfun, q)) < 1e-12
         assert rel_l2(get("DFV", 288, (12, 24)), ce.cstep_jacobian(fvfun, q)) < 1e-12
+        # the end-effector Jacobian is a position-level product: its storage is reused by the velocity level (KW_HB)
+        w = np.zeros(lib.cport_kin_ws_size())
+        lib.cport_kin_eval(C.byref(model), dp(x), None, 0, dp(w))
         assert rel_l2(get("EEJ", 144, (6, 24)), rbd.frame_jacobian6(m, nk["kin"], m.ee_joint, m.ee_off)) < 1e-13
 
 
