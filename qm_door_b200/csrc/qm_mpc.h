@@ -1213,25 +1213,48 @@ QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double*
            [&](int a, double val) { dut[a] = val; });
   g.sync();
   const int* role = (const int*)(pb + PB_ROLE);
-  const int len = 30 + nut;
-  // dx+ = b + [A | B] v
-  rows_dot(g, 30, len, [&](int i) { return st[SB_b + i]; },
-           [&](int i, int c) { return ((c < 30) ? st[SB_A + 30 * i + c] : st[SB_B + QM_NUT * i + c - 30]) * v[c]; },
-           [&](int i, double val) { dxn[i] = val; });
-  // du (pivot rows: [Px | Pu] v + Pe; free inputs: dut; dropped: Pe) and the armijo term (row 30)
-  rows_dot(g, 31, len,
-           [&](int i) {
-             if (i == 30) return W[80];
-             const int rl = role[i];
-             return (rl < ROLE_FREE) ? pb[PB_PEC + rl] : ((rl < ROLE_NONE) ? dut[rl - ROLE_FREE] : ((i < 12) ? pb[PB_PEF + i] : 0.0));
-           },
-           [&](int i, int c) {
-             if (i == 30) return ((c < 30) ? st[SB_q + c] : st[SB_r + c - 30]) * v[c];
-             const int rl = role[i];
-             if (rl >= ROLE_FREE) return 0.0;
-             return ((c < 30) ? pb[PB_PX + 30 * rl + c] : pb[PB_PU + QM_NUT * rl + c - 30]) * v[c];
-           },
-           [&](int i, double val) { if (i == 30) W[80] = val; else du_out[i] = (nut > 0) ? val : 0.0; });
+  // 61 rows of the form init + p1 . dx + p2 . dut (a 30- and a nut-vector per row, no per-element case distinction):
+  //   rows 0..29  dx+ = b + A dx + B dut
+  //   rows 30..59 du_i: pivot rows Pe + Px dx + Pu dut; free inputs: dut; dropped: Pe
+  //   row  60     armijo += q . dx + r . dut
+  auto row = [&](int r, const double** p1, const double** p2, double* init) -> bool {
+    if (r < 30) { *p1 = st + SB_A + 30 * r; *p2 = st + SB_B + QM_NUT * r; *init = st[SB_b + r]; return true; }
+    if (r == 60) { *p1 = st + SB_q; *p2 = st + SB_r; *init = W[80]; return true; }
+    const int i = r - 30, rl = role[i];
+    if (rl < ROLE_FREE) { *p1 = pb + PB_PX + 30 * rl; *p2 = pb + PB_PU + QM_NUT * rl; *init = pb[PB_PEC + rl]; return true; }
+    *init = (rl < ROLE_NONE) ? dut[rl - ROLE_FREE] : ((i < 12) ? pb[PB_PEF + i] : 0.0);
+    return false;
+  };
+  auto put = [&](int r, double val) {
+    if (r < 30) dxn[r] = val;
+    else if (r == 60) W[80] = val;
+    else du_out[r - 30] = (nut > 0) ? val : 0.0;
+  };
+#if defined(__CUDA_ARCH__)
+  for (int base = 0; base < 4 * 61; base += g.nt()) {           // four lanes per row, partial sums combined with shuffles
+    const int t = base + g.tid(), rl = t >> 2, part = t & 3;
+    const int r = (rl & ~7) | mm_rowperm(rl & 7);               // rows two apart within a half warp (see rows_dot)
+    const double *p1 = nullptr, *p2 = nullptr;
+    double init = 0.0, acc = 0.0;
+    if (r < 61 && row(r, &p1, &p2, &init)) {
+      for (int j = part; j < 30; j += 4) acc += p1[j] * v[j];
+      for (int j = part; j < nut; j += 4) acc += p2[j] * dut[j];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (r < 61 && part == 0) put(r, init + acc);
+  }
+#else
+  QM_PFOR(g, r, 61) {
+    const double *p1 = nullptr, *p2 = nullptr;
+    double init = 0.0, acc = 0.0;
+    if (row(r, &p1, &p2, &init)) {
+      for (int j = 0; j < 30; ++j) acc += p1[j] * v[j];
+      for (int j = 0; j < nut; ++j) acc += p2[j] * dut[j];
+    }
+    put(r, init + acc);
+  }
+#endif
   g.sync();
 }
 

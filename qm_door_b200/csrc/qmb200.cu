@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
 
 // line-search evaluation: a thread per node (value-only single-pass tree walk in registers, qm_value.h)
 constexpr int kTrialThreads = 128;
-__global__ void __launch_bounds__(kTrialThreads) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
+#ifndef QM_TRIAL_MINBLOCKS
+#define QM_TRIAL_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kTrialThreads, QM_TRIAL_MINBLOCKS) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
                                                           const int* list, int nprob) {
   // first trial: every problem of the chunk; backtracking trials: only the problems k_decide listed as still pending
   // (problem, node) pairs are laid over the threads back to back: a block per problem would leave its last warp with a
