@@ -150,19 +150,20 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
   QM_PFOR(g, i, 30) { R[i] = m.x0[30 * b + i] - m.xs[((size_t)b * NMAX) * 30 + i]; }
   if (g.tid() == 0) R[80] = 0.0;
   g.sync();
+  double* cur = R;                                   // dx of the current node; the next one is written to the other buffer
+  double* nxt = R + 48;
   for (int k = 0; k < n; ++k) {
     if (k + 1 < n) fetch.fwd_request(g, (k + 1) & 1, stage + (size_t)(k + 1) * SB_SIZE, proj + (size_t)(k + 1) * PB_SIZE, gain + (size_t)(k + 1) * GB_SIZE);
-    QM_PFOR(g, i, 30) dxs[30 * k + i] = R[i];
+    QM_PFOR(g, i, 30) dxs[30 * k + i] = cur[i];
     const double *st, *pb, *gb;
     QM_TICK(10);
     fetch.fwd_wait(g, k & 1, &st, &pb, &gb);
     QM_TICK(11);
-    rollout_stage(g, st, pb, gb, R, dus + 30 * k);
-    QM_PFOR(g, i, 30) R[i] = R[48 + i];
-    g.sync();
+    rollout_stage(g, st, pb, gb, R, cur, nxt, dus + 30 * k);
+    double* t_ = cur; cur = nxt; nxt = t_;
     QM_TICK(12);
   }
-  QM_PFOR(g, i, 30) { dxs[30 * n + i] = R[i]; dus[30 * n + i] = 0.0; }
+  QM_PFOR(g, i, 30) { dxs[30 * n + i] = cur[i]; dus[30 * n + i] = 0.0; }
   g.sync();
   // step norms and baseline performance: sums in a fixed order (bit-reproducible for a given group size): every thread sums
   // a strided subset of the 30 (n + 1) components, thread 0 adds the partial sums in thread order
@@ -179,7 +180,7 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
   g.sync();
   if (g.tid() == 0) {
     double arm = R[80];
-    for (int j = 0; j < 30; ++j) arm += term[SB_q + j] * R[j];
+    for (int j = 0; j < 30; ++j) arm += term[SB_q + j] * cur[j];
     double sx = 0.0, su = 0.0;
     for (int t = 0; t < g.nt(); ++t) { sx += part[2 * t]; su += part[2 * t + 1]; }
     double d0 = 0.0;

@@ -1203,11 +1203,13 @@ QM_HDN void riccati_stage_b(G g, int nut, double* W, double* gb) {
 }
 
 // One forward stage: dut = K dx + kff; du from the compact projection block; dx+ = A dx + B dut + b; armijo += q.dx + r.dut
-// st: forward part of the stage block. W: v = [0:30] dx | [30:48] dut, [48:78] dx next, [80] armijo accumulator
+// st: forward part of the stage block. W: [30:48] dut, [80] armijo accumulator; v: dx (30), dxn: dx of the next node (30) --
+// the caller alternates the two between W[0:30] and W[48:78], so no copy (and no barrier for it) separates two stages.
 template <class G>
-QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double* gb, double* W, double* du_out) {
+QM_HDN void rollout_stage(G g, const double* st, const double* pb, const double* gb, double* W, const double* v, double* dxn,
+                          double* du_out) {
   const int nut = (int)st[SB_NUT];
-  const double* v = W; double* dut = W + 30; double* dxn = W + 48;
+  double* dut = W + 30;
   rows_dot(g, nut, 30, [&](int a) { return gb[GB_KFF + a]; },
            [&](int a, int j) { return gb[GB_K + 30 * a + j] * v[j]; },
            [&](int a, double val) { dut[a] = val; });
