@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_mo
   // the schedule arrays and the previous solution's time grid are staged in shared memory: the per-component loop over
   // the nodes then only waits for the two warm-start loads of each node
   extern __shared__ __align__(16) double smem[];
-  const int b = m.b0 + blockIdx.x, c = threadIdx.x;
+  // warp 0: the 30 state components, warp 1: the 30 input components (the two follow different code paths)
+  const int b = m.b0 + blockIdx.x, lane = threadIdx.x & 31, c = (threadIdx.x >> 5) * 30 + lane;
   const int NMAX = m.NMAX;
   const size_t o = (size_t)b * NMAX;
   double* s_t = smem; double* s_ts = smem + NMAX; double* s_dt = smem + 2 * NMAX; double* s_pt = smem + 3 * NMAX;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_mo
     s_flag[i] = (i < nn) ? m.node_flag[o + i] : 0; s_mode[i] = (i < nn) ? m.node_mode[o + i] : 0;
   }
   __syncthreads();
-  if (c >= 60) return;
+  if (lane >= 30) return;
   init_guess_component(*M, *P, S->weak_eps, c, m.x0 + 30 * b, nn, s_t, s_flag, s_ts, s_dt, s_mode, np, s_pt, m.prev_x + o * 30, m.prev_u + o * 30,
                        m.xs + o * 30, m.us + o * 30);
 }
@@ -319,8 +320,8 @@ __global__ void __launch_bounds__(32 * kDecideWarps) k_decide(MpcBuffers m, cons
 }
 
 __global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out) {
-  const int b = m.b0 + blockIdx.x, c = threadIdx.x;
-  if (c >= 60) return;
+  const int b = m.b0 + blockIdx.x, lane = threadIdx.x & 31, c = (threadIdx.x >> 5) * 30 + lane;   // warp 0: states, warp 1: inputs
+  if (lane >= 30) return;
   finalize_component(m, b, c, t_out, x_out, u_out);
 }
 
