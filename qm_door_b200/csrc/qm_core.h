@@ -310,6 +310,19 @@ enum {
 };
 static_assert(KW_DFV + 12 * QM_NJ <= KW_P, "DH | DFV must fit in R | BODY");
 
+// The subtree of joint j consists of joints j .. j + 5 only (true for the limb joints of a tree numbered parents first): the sums
+// over a subtree then take six predicated steps instead of a sweep over all joints, in the same order.
+QM_HD int count_trailing_zeros(uint32_t v) {      // v != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+QM_HD bool subtree_is_window(uint32_t submask, int j) {
+  return (submask & ((1u << j) - 1u)) == 0u && (submask >> j) < 64u;
+}
+
 // spatial motion vector of joint j (world coordinates, reference point = world origin): (w, vO)
 QM_HD void joint_S(const qmb200_model_desc& M, const double* w, int j, double* S) {
   const double* a = w + KW_AX + 3 * j;
@@ -462,8 +475,14 @@ QM_HDN void kin_positions(G g, const qmb200_model_desc& M, const double* q, doub
     const int j = idx / 10, k = idx - 10 * j;
     double acc = 0.0;
     const uint32_t mask = M.submask[j];
-    for (int i = 0; i < QM_NJ; ++i)
-      if ((mask >> i) & 1u) acc += w[KW_BODY + 10 * i + k];
+    if (subtree_is_window(mask, j)) {              // limb joints: at most six bodies, joints j .. j + 5 (same summation order)
+      QM_UNROLL
+      for (int d = 0; d < 6; ++d)
+        if ((mask >> (j + d)) & 1u) acc += w[KW_BODY + 10 * (j + d) + k];
+    } else {
+      for (int i = 0; i < QM_NJ; ++i)
+        if ((mask >> i) & 1u) acc += w[KW_BODY + 10 * i + k];
+    }
     w[KW_COMP + idx] = acc;
   }
   g.sync();
@@ -565,9 +584,23 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, int deriv, double* w
   QM_PFOR(g, j, QM_NJ) {
     double V[6] = {0, 0, 0, 0, 0, 0};
     const uint32_t mask = M.pathmask[j];
-    for (int k = 0; k < QM_NJ; ++k)
-      if ((mask >> k) & 1u)
-        for (int c = 0; c < 6; ++c) V[c] += w[KW_SV + 6 * k + c];
+    // ancestors = base joints (among 0..5) and at most six limb joints lo .. lo + 5: twelve predicated steps in the same order
+    const uint32_t high = mask >> 6;
+    const int lo = 6 + (high ? count_trailing_zeros(high) : 0);
+    if ((mask >> lo) < 64u) {
+      QM_UNROLL
+      for (int d = 0; d < 6; ++d)
+        if ((mask >> d) & 1u)
+          for (int c = 0; c < 6; ++c) V[c] += w[KW_SV + 6 * d + c];
+      QM_UNROLL
+      for (int d = 0; d < 6; ++d)
+        if ((mask >> (lo + d)) & 1u)
+          for (int c = 0; c < 6; ++c) V[c] += w[KW_SV + 6 * (lo + d) + c];
+    } else {
+      for (int k = 0; k < QM_NJ; ++k)
+        if ((mask >> k) & 1u)
+          for (int c = 0; c < 6; ++c) V[c] += w[KW_SV + 6 * k + c];
+    }
     for (int c = 0; c < 6; ++c) w[KW_V + 6 * j + c] = V[c];
     inertia_mul(w + KW_BODY + 10 * j, V, w + KW_HB + 6 * j);
   }
@@ -589,8 +622,14 @@ QM_HDN void kin_velocities(G g, const qmb200_model_desc& M, int deriv, double* w
     const int j = idx / 6, c = idx - 6 * j;
     double acc = 0.0;
     const uint32_t mask = M.submask[j];
-    for (int i = 0; i < QM_NJ; ++i)
-      if ((mask >> i) & 1u) acc += w[KW_HB + 6 * i + c];
+    if (subtree_is_window(mask, j)) {
+      QM_UNROLL
+      for (int d = 0; d < 6; ++d)
+        if ((mask >> (j + d)) & 1u) acc += w[KW_HB + 6 * (j + d) + c];
+    } else {
+      for (int i = 0; i < QM_NJ; ++i)
+        if ((mask >> i) & 1u) acc += w[KW_HB + 6 * i + c];
+    }
     w[KW_SV + idx] = acc;
   }
   g.sync(); QM_TICK(21);
