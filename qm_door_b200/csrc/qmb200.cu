@@ -2,12 +2,12 @@
 //
 // Launch map of one cycle (B problems, NMAX node capacity):
 //   k_schedule   <<<ceil(B/4), 128>>>        warp per problem: time grid (lane 0), then modes / swing references per node
-//   k_init_guess <<<B, 64>>>                 thread per state/input component: warm start interpolation
-//   k_kin<1>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x,u), constraint rows, ee terms -> kin scratch
-//   k_kin<2>     <<<(NMAX/2, B), 64>>>       warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
-//   k_proj       <<<(NMAX/4, B), 128>>>      warp per node: projection pivots (register Gauss-Jordan)
+//   k_init_guess <<<B, 64>>>                 thread per state (warp 0) / input (warp 1) component: warm start interpolation
+//   k_kin<1>     <<<(NMAX, B), 32>>>         warp per node: kinematics + derivatives at (x,u), constraint rows, ee terms -> kin scratch
+//   k_kin<2>     <<<(NMAX, B), 32>>>         warp per node: kinematics + derivatives at (x + dt f1, u)          -> kin scratch
+//   k_proj       <<<(NMAX/4, B), 128>>>      warp per node: projection pivots (register Gauss-Jordan), side stream beside k_kin<2>
 // The cycle can be pipelined over chunks of problems (one stream per chunk, run_cycle): B below is the chunk size.
-//   k_lq         <<<(NMAX, B), 128>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
+//   k_lq         <<<(NMAX, B), 256>>>        CTA per node: cost/dynamics LQ approximation, projection -> stage/proj blocks
 //   k_solve      <<<B, 128>>>                CTA per problem: Riccati backward sweep + forward rollout (serial in nodes)
 //   k_trial      <<<B*NMAX/128, 128>>>       thread per (problem, node): value-only evaluation of the trial step (single-pass tree walk in registers)
 //   k_decide     <<<ceil(B/4), 128>>>        warp per problem: stages the trial records, lane 0 takes the filter line-search decision
