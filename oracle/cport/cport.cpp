@@ -100,9 +100,13 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
     const int nn = m.nn[b], n = nn - 1;
     annotate_schedule(g, S, P, m.events + (size_t)b * E, m.modes + (size_t)b * (E + 1), m.nevents[b], nn, m.node_t + o,
                       m.node_flag + o, m.node_ts + o, m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.status + b);
+    std::vector<int> gri(3 * NMAX);
+    std::vector<double> gra(2 * NMAX);
+    for (int k = 0; k < nn - 1; ++k)
+      init_guess_node(S.weak_eps, k, m.node_t + o, m.node_flag + o, m.node_ts + o, m.nprev[b], m.prev_t + o, gri.data(), gra.data());
     for (int cc = 0; cc < 60; ++cc)
-      init_guess_component(M, P, S.weak_eps, cc, m.x0 + 30 * b, nn, m.node_t + o, m.node_flag + o, m.node_ts + o, m.node_dt + o,
-                           m.node_mode + o, m.nprev[b], m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30, m.xs + o * 30, m.us + o * 30);
+      init_guess_component(M, P, cc, m.x0 + 30 * b, nn, m.node_t + o, m.node_ts + o, m.node_mode + o, gri.data(), gra.data(), m.nprev[b],
+                           m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30, m.xs + o * 30, m.us + o * 30);
     const double* tt = m.target_t + (size_t)b * KT;
     const double* ts = m.target_x + (size_t)b * KT * QM_NTARGET;
     for (int k = 0; k <= n; ++k) {

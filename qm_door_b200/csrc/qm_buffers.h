@@ -243,10 +243,8 @@ QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out,
         }
       }
     }
-    if (c == 0) {
-      for (int k = 0; k < nn; ++k) { m.prev_t[o + k] = m.node_ts[o + k]; if (t_out) t_out[o + k] = m.node_ts[o + k]; }
-      m.nprev[b] = nn;
-    }
+    for (int k = c; k < nn; k += 30) { m.prev_t[o + k] = m.node_ts[o + k]; if (t_out) t_out[o + k] = m.node_ts[o + k]; }   // node times: spread over the state lanes
+    if (c == 0) m.nprev[b] = nn;
   } else {
     const int cu = c - 30;
     double last = 0.0;

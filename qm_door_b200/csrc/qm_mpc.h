@@ -156,61 +156,79 @@ QM_HDN void annotate_schedule(G g, const qmb200_solver_desc& S, const qmb200_pro
   g.sync();
 }
 
-// [upstream] multiple_shooting::initializeStateInputTrajectories; one thread per (problem, component c<60).
-QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_problem_desc& P, double weak_eps, int c, const double* x0, int nn,
-                                 const double* node_t, const int32_t* node_flag, const double* node_ts, const double* node_dt,
-                                 const int32_t* node_mode, int nprev, const double* prev_t, const double* prev_x,
-                                 const double* prev_u, double* xs, double* us) {
+// [upstream] multiple_shooting::initializeStateInputTrajectories, in two steps.
+// Step 1, per node k < nn - 1 (the same for every component): where the warm start is read. ri[3k] = kind: 0 pre-event node,
+// 1 interpolate the previous solution, 2 beyond it (QMInitializer); ri[3k+1], ra[2k]: segment and weight of the state at the end
+// of the interval; ri[3k+2], ra[2k+1]: of the input at its start ([upstream] LinearInterpolation::timeSegment: lower_bound).
+QM_HD int times_below(const double* t, int n, double q) {             // number of entries strictly below q (t ascending)
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (t[mid] < q) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+QM_HD void interp_segment(int part, int nprev, const double* prev_t, double q, int* i, double* a) {
+  if (part == 0) { *i = 0; *a = (q == prev_t[0]) ? (prev_t[1] - q) / (prev_t[1] - prev_t[0]) : 1.0; }
+  else if (part - 1 < nprev - 1) { *i = part - 1; *a = (prev_t[part] - q) / (prev_t[part] - prev_t[part - 1]); }
+  else { *i = nprev - 2; *a = 0.0; }
+}
+QM_HDN void init_guess_node(double weak_eps, int k, const double* node_t, const int32_t* node_flag, const double* node_ts,
+                            int nprev, const double* prev_t, int* ri, double* ra) {
   const bool has_prev = nprev >= 2;
   const double till_x = has_prev ? prev_t[nprev - 1] : node_t[0];
   const double till_u = has_prev ? prev_t[nprev - 2] : node_t[0];
+  int kind = 0, ix = 0, iu = 0;
+  double ax = 0.0, au = 0.0;
+  if (node_flag[k] != EV_PRE) {
+    const double t = node_ts[k], tn = node_t[k + 1] - (node_flag[k + 1] == EV_PRE ? weak_eps : 0.0);
+    if (t > till_u || tn > till_x) kind = 2;
+    else {
+      kind = 1;
+      interp_segment(times_below(prev_t, nprev, tn), nprev, prev_t, tn, &ix, &ax);
+      interp_segment(times_below(prev_t, nprev, t), nprev, prev_t, t, &iu, &au);
+    }
+  }
+  ri[3 * k] = kind; ri[3 * k + 1] = ix; ri[3 * k + 2] = iu;
+  ra[2 * k] = ax; ra[2 * k + 1] = au;
+}
+
+// Step 2, one thread per (problem, component c < 60): the trajectories of that component.
+QM_HDN void init_guess_component(const qmb200_model_desc& M, const qmb200_problem_desc& P, int c, const double* x0, int nn,
+                                 const double* node_t, const double* node_ts, const int32_t* node_mode, const int* ri, const double* ra,
+                                 int nprev, const double* prev_t, const double* prev_x, const double* prev_u, double* xs, double* us) {
+  const bool has_prev = nprev >= 2;
+  const double till_x = has_prev ? prev_t[nprev - 1] : node_t[0];
   const int n = nn - 1;
-  // query times increase with the node index, so the interpolation segment is searched monotonically:
-  // `part` = number of previous-solution times strictly below the query (LinearInterpolation::timeSegment, lower_bound)
-  int part = 0;
   if (c < 30) {
     double xc;
     const double t_init = node_ts[0];
     if (t_init < till_x) {
-      while (part < nprev && prev_t[part] < t_init) ++part;
+      const int part = times_below(prev_t, nprev, t_init);
       const int i = (part == 0) ? 0 : part - 1;        // t_init < till_x = prev_t[last] => i < last
       const double a = (part == 0 && !(t_init == prev_t[0])) ? 1.0 : (prev_t[i + 1] - t_init) / (prev_t[i + 1] - prev_t[i]);
       xc = a * prev_x[30 * i + c] + (1.0 - a) * prev_x[30 * (i + 1) + c];
     } else xc = x0[c];
     xs[c] = xc;
     for (int k = 0; k < n; ++k) {
-      if (node_flag[k] != EV_PRE) {
-        const double t = node_ts[k], tn = node_t[k + 1] - (node_flag[k + 1] == EV_PRE ? weak_eps : 0.0);
-        if (!(t > till_u || tn > till_x)) {
-          while (part < nprev && prev_t[part] < tn) ++part;
-          int i; double a;
-          if (part == 0) { i = 0; a = (tn == prev_t[0]) ? (prev_t[1] - tn) / (prev_t[1] - prev_t[0]) : 1.0; }
-          else if (part - 1 < nprev - 1) { i = part - 1; a = (prev_t[i + 1] - tn) / (prev_t[i + 1] - prev_t[i]); }
-          else { i = nprev - 2; a = 0.0; }
-          xc = a * prev_x[30 * i + c] + (1.0 - a) * prev_x[30 * (i + 1) + c];
-        }
+      if (ri[3 * k] == 1) {
+        const int i = ri[3 * k + 1];
+        const double a = ra[2 * k];
+        xc = a * prev_x[30 * i + c] + (1.0 - a) * prev_x[30 * (i + 1) + c];
       }
-      xs[30 * (k + 1) + c] = xc;
+      xs[30 * (k + 1) + c] = xc;                       // pre-event nodes and nodes beyond the warm start keep the last state
     }
   } else {
     const int cu = c - 30;
     for (int k = 0; k < n; ++k) {
       double uc = 0.0;
-      if (node_flag[k] != EV_PRE) {
-        const double t = node_ts[k], tn = node_t[k + 1] - (node_flag[k + 1] == EV_PRE ? weak_eps : 0.0);
-        if (t > till_u || tn > till_x) {
-          // QMInitializer::compute (qm_interface/src/initialization/QMInitializer.cpp:33-41): weight compensation
-          const int md = node_mode[k];
-          const int ns = ((md >> 3) & 1) + ((md >> 2) & 1) + ((md >> 1) & 1) + (md & 1);
-          if (cu < 12 && (cu % 3) == 2 && ((md >> (3 - cu / 3)) & 1)) uc = M.total_mass * P.gravity / ns;
-        } else {
-          while (part < nprev && prev_t[part] < t) ++part;
-          int i; double a;
-          if (part == 0) { i = 0; a = (t == prev_t[0]) ? (prev_t[1] - t) / (prev_t[1] - prev_t[0]) : 1.0; }
-          else if (part - 1 < nprev - 1) { i = part - 1; a = (prev_t[i + 1] - t) / (prev_t[i + 1] - prev_t[i]); }
-          else { i = nprev - 2; a = 0.0; }
-          uc = a * prev_u[30 * i + cu] + (1.0 - a) * prev_u[30 * (i + 1) + cu];
-        }
+      const int kind = ri[3 * k];
+      if (kind == 2) {
+        // QMInitializer::compute (qm_interface/src/initialization/QMInitializer.cpp:33-41): weight compensation
+        const int md = node_mode[k];
+        const int ns = ((md >> 3) & 1) + ((md >> 2) & 1) + ((md >> 1) & 1) + (md & 1);
+        if (cu < 12 && (cu % 3) == 2 && ((md >> (3 - cu / 3)) & 1)) uc = M.total_mass * P.gravity / ns;
+      } else if (kind == 1) {
+        const int i = ri[3 * k + 2];
+        const double a = ra[2 * k + 1];
+        uc = a * prev_u[30 * i + cu] + (1.0 - a) * prev_u[30 * (i + 1) + cu];
       }
       us[30 * k + cu] = uc;
     }

@@ -60,17 +60,21 @@ __global__ void __launch_bounds__(64) k_init_guess(MpcBuffers m, const qmb200_mo
   const int b = m.b0 + blockIdx.x, lane = threadIdx.x & 31, c = (threadIdx.x >> 5) * 30 + lane;
   const int NMAX = m.NMAX;
   const size_t o = (size_t)b * NMAX;
-  double* s_t = smem; double* s_ts = smem + NMAX; double* s_dt = smem + 2 * NMAX; double* s_pt = smem + 3 * NMAX;
-  int* s_flag = (int*)(smem + 4 * NMAX); int* s_mode = s_flag + NMAX;
+  double* s_t = smem; double* s_ts = smem + NMAX; double* s_pt = smem + 2 * NMAX; double* s_ra = smem + 3 * NMAX;   // s_ra: 2 per node
+  int* s_flag = (int*)(smem + 5 * NMAX); int* s_mode = s_flag + NMAX; int* s_ri = s_mode + NMAX;                    // s_ri: 3 per node
   const int nn = m.nn[b], np = m.nprev[b];
   for (int i = threadIdx.x; i < NMAX; i += blockDim.x) {
-    s_t[i] = (i < nn) ? m.node_t[o + i] : 0.0; s_ts[i] = (i < nn) ? m.node_ts[o + i] : 0.0; s_dt[i] = (i < nn) ? m.node_dt[o + i] : 0.0;
+    s_t[i] = (i < nn) ? m.node_t[o + i] : 0.0; s_ts[i] = (i < nn) ? m.node_ts[o + i] : 0.0;
     s_pt[i] = (i < np) ? m.prev_t[o + i] : 0.0;
     s_flag[i] = (i < nn) ? m.node_flag[o + i] : 0; s_mode[i] = (i < nn) ? m.node_mode[o + i] : 0;
   }
   __syncthreads();
+  // where the warm start is read, once per node (segment search, weights) ...
+  for (int k = threadIdx.x; k < nn - 1; k += blockDim.x) init_guess_node(S->weak_eps, k, s_t, s_flag, s_ts, np, s_pt, s_ri, s_ra);
+  __syncthreads();
   if (lane >= 30) return;
-  init_guess_component(*M, *P, S->weak_eps, c, m.x0 + 30 * b, nn, s_t, s_flag, s_ts, s_dt, s_mode, np, s_pt, m.prev_x + o * 30, m.prev_u + o * 30,
+  // ... then the trajectory of each component
+  init_guess_component(*M, *P, c, m.x0 + 30 * b, nn, s_t, s_ts, s_mode, s_ri, s_ra, np, s_pt, m.prev_x + o * 30, m.prev_u + o * 30,
                        m.xs + o * 30, m.us + o * 30);
 }
 
@@ -472,7 +476,7 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     const int nb = m.nb;
     CUDA_OK(cudaStreamWaitEvent(st, c->ev_start, 0));
     { KernelTimer kt(c, KN_SCHEDULE, st); k_schedule<<<(nb + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
-    { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, (size_t)NMAX * 40, st>>>(m, c->dM, c->dP, c->dS); }
+    { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, (size_t)NMAX * 60, st>>>(m, c->dM, c->dP, c->dS); }
     { KernelTimer kt(c, KN_KIN1, st); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
     // the projection pivots only need the constraint rows of k_kin<1>: they run beside k_kin<2> (FP64-issue bound warps next to
     // latency-bound ones) and join before k_lq
