@@ -585,6 +585,13 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   CUDA_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(k_rbd_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStateWarps * kStateWarpDoubles * sizeof(double))));
   CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
+  {
+    // staging buffers that grow with the node capacity (long horizons): k_decide 4 x NMAX records, k_init_guess 60 B per node
+    const size_t dec = (size_t)kDecideWarps * c->m.NMAX * PF_SIZE * sizeof(double), ini = (size_t)c->m.NMAX * 60;
+    if (dec > 200 * 1024 || ini > 200 * 1024) return fail("qmb200_create: max_nodes too large for the staging buffers of k_decide / k_init_guess");
+    if (dec > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec));
+    if (ini > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k_init_guess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ini));
+  }
   *out = c;
   return 0;
 }
