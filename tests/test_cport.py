@@ -239,3 +239,31 @@ def test_error_statuses(descs):
     out = cp.cycle(np.zeros(B), np.tile(x_init, (B, 1)), ev, md, ne, np.tile([0.0, 1.0], (B, 1)), np.tile(knot, (B, 2, 1)))
     assert (out["status"] & 1).all() and (out["n"] <= 12).all()
     cp.close()
+
+
+def test_warm_start_across_gait_events(descs, oracle_inputs):
+    """Receding horizon over several cycles with dt 0.015 s (task.info:79) while gait events enter, cross and leave the horizon:
+    the warm start (segment search once per node, pre-event nodes, nodes beyond the previous solution, initializer inputs)
+    must reproduce the oracle's sequential interpolation cycle after cycle."""
+    model, problem, solver, _ = descs
+    m, P = oracle_inputs
+    B, hor, dt = 1, 0.12, 0.015
+    x0s, _ = scenarios.perturbed_states(m, P, B, seed=123)
+    tt, ts = scenarios.standing_target(m, P)
+    sd = solver_for(solver, hor, dt)
+    sched = G.tile_schedule(P.gaits["trot"], -0.31, 1.0)         # an event falls inside the first horizons and is passed later
+    ev, md, ne = abi_fill.pack_schedules([sched], sd.max_events)
+    cp = abi_fill.CPort(model, problem, sd, B)
+    prob = sqp.MpcProblem(m, P, ev[0, :ne[0]], md[0, :ne[0] + 1], tt, ts, horizon=hor, dt=dt)
+    seen_pre_first = False
+    for c in range(7):
+        t0 = 0.01 * c
+        out = cp.cycle(np.full(B, t0), x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)))
+        _, xs, us, info = sqp.mpc_cycle(prob, t0, x0s[0])
+        n = info["n"] + 1
+        assert out["n"][0] == n and np.array_equal(out["mode"][0, :n], info["modes"])
+        assert np.array_equal(out["t"][0, :n], np.array([G.interval_start(info["times"][i], info["flags"][i]) for i in range(n)]))
+        assert rel_l2(out["x"][0, :n], xs) < 1e-8 and rel_l2(out["u"][0, :n], us) < 1e-8
+        seen_pre_first = seen_pre_first or (G.EV_PRE in list(info["flags"][:3]))
+    assert seen_pre_first                                          # an event right behind the initial time was part of the run
+    cp.close()
