@@ -132,6 +132,10 @@ def test_feedback_gains_against_oracle(descs, oracle_inputs):
                 if info["flags"][k] != G.EV_PRE:
                     for f in swing:
                         assert np.abs(K[b, k, 3 * f:3 * f + 3]).max() < 1e-9
+                    # the feedback term keeps the linearised equality constraints C dx + D du = 0 satisfied: D K + C = 0
+                    nd = info["nodes"][k]
+                    res = nd["D"] @ K[b, k] + nd["C"]
+                    assert np.abs(res).max() < 1e-8 * max(1.0, np.abs(nd["C"]).max())
     cp.close()
 
 
