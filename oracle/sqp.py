@@ -376,63 +376,86 @@ def accept_step(S, base, new, armijo):
     return new["merit"] < base["merit"] - S["gamma_c"] * vb or vn < (1.0 - S["gamma_c"]) * vb
 
 
-def mpc_cycle(prob, t0, x0, return_debug=False):
-    """SqpSolver::runImpl with sqpIteration = 1 (task.info:80). Updates prob.prev. Returns (times, x, u, info)."""
+def check_convergence(S, it, iterations, base, new, alpha, dxn, dun):
+    """[upstream] SqpSolver::checkConvergence, restated from the published ocs2_sqp sources (not in the reference tree, so this
+    ordering of the tests is unverified here): iteration budget, step size below alpha_min, merit change below costTol on a
+    feasible iterate, primal step below deltaTol. Returns the reason or None. The reference runs one iteration (task.info:80),
+    for which the answer is always "ITERATIONS"."""
+    if it + 1 >= iterations:
+        return "ITERATIONS"
+    if alpha < S["alpha_min"]:
+        return "STEPSIZE"
+    if abs(new["merit"] - base["merit"]) < S.get("costTol", 1e-4) and np.sqrt(new["dyn"] + new["eq"]) < S["g_min"]:
+        return "METRICS"
+    if alpha * dxn < S["deltaTol"] and alpha * dun < S["deltaTol"]:
+        return "PRIMAL"
+    return None
+
+
+def mpc_cycle(prob, t0, x0, return_debug=False, iterations=1):
+    """SqpSolver::runImpl; iterations = sqpIteration (1 in the reference, task.info:80; more than one is the specification for
+    the multi-iteration path, which the CUDA library does not have yet). Updates prob.prev. Returns (times, x, u, info)."""
     P, S = prob.P, prob.P.sqp
     times, flags = G.time_grid(t0, t0 + prob.horizon, prob.dt, prob.events)
     n = len(times) - 1
     xs, us = initial_guess(prob, t0, x0, times, flags)
-    stages, nodes = [], []
-    for i in range(n):
-        if flags[i] == G.EV_PRE:
-            z = np.zeros((30, 30))
-            st = dict(A=np.eye(30), B=np.zeros((30, 0)), b=xs[i] - xs[i + 1], c=0.0, q=np.zeros(30), Q=z,
-                      r=np.zeros(0), P=np.zeros((0, 30)), R=np.zeros((0, 0)), Pu=np.zeros((30, 0)), Px=z,
-                      Pe=np.zeros(30), nut=0)
-            nodes.append(None)
+    history = []
+    for it in range(iterations):
+        stages, nodes = [], []
+        for i in range(n):
+            if flags[i] == G.EV_PRE:
+                z = np.zeros((30, 30))
+                st = dict(A=np.eye(30), B=np.zeros((30, 0)), b=xs[i] - xs[i + 1], c=0.0, q=np.zeros(30), Q=z,
+                          r=np.zeros(0), P=np.zeros((0, 30)), R=np.zeros((0, 0)), Pu=np.zeros((30, 0)), Px=z,
+                          Pe=np.zeros(30), nut=0)
+                nodes.append(None)
+            else:
+                t = G.interval_start(times[i], flags[i])
+                dt = G.interval_end(times[i + 1], flags[i + 1]) - t
+                nd = transcribe_node(prob, t, dt, xs[i], us[i], xs[i + 1])
+                st = project(nd)
+                nodes.append(nd)
+            stages.append(st)
+        # terminal node: finalSoftConstraint "finalEndEffector" (QMInterface.cpp:104)
+        tN = times[n]
+        pr, qr = prob.ee_ref(tN)
+
+        def ee_fun(z):
+            nk = ce.node_kinematics(prob.model, z)
+            return np.concatenate([nk["ee_pos"], ce.quat_distance(ce.quat_from_matrix(nk["ee_rot"]), qr)], axis=-1)
+
+        ev = ee_fun(xs[n]) - np.concatenate([pr, np.zeros(3)])
+        Je = ce.cstep_jacobian(ee_fun, xs[n])
+        W = np.diag([P.mu_fee_pos] * 3 + [P.mu_fee_ori] * 3)
+        terminal = dict(Q=Je.T @ W @ Je, q=Je.T @ W @ ev, c=0.5 * ev @ W @ ev)
+        # baseline performance
+        base = performance(prob, x0, times, flags, xs, us)
+        dx, dut, Ks, ks = riccati(stages, terminal, x0 - xs[0])
+        armijo = sum(float(st["q"] @ dx[k] + st["r"] @ dut[k]) for k, st in enumerate(stages)) + float(terminal["q"] @ dx[n])
+        du = [st["Pu"] @ dut[k] + st["Px"] @ dx[k] + st["Pe"] for k, st in enumerate(stages)]
+        dxn = np.sqrt(sum(float(d @ d) for d in dx))
+        dun = np.sqrt(sum(float(d @ d) for d in du))
+        alpha, accepted = 1.0, False
+        while True:
+            xn = xs + alpha * np.array(dx)
+            un = us + alpha * np.array(du)
+            new = performance(prob, x0, times, flags, xn, un)
+            if accept_step(S, base, new, alpha * armijo):
+                accepted = True
+                break
+            alpha *= S["alpha_decay"]
+            if alpha * dxn < S["deltaTol"] and alpha * dun < S["deltaTol"]:
+                break
+            if alpha < S["alpha_min"]:
+                break
+        if accepted:
+            xs, us = xn, un
         else:
-            t = G.interval_start(times[i], flags[i])
-            dt = G.interval_end(times[i + 1], flags[i + 1]) - t
-            nd = transcribe_node(prob, t, dt, xs[i], us[i], xs[i + 1])
-            st = project(nd)
-            nodes.append(nd)
-        stages.append(st)
-    # terminal node: finalSoftConstraint "finalEndEffector" (QMInterface.cpp:104)
-    tN = times[n]
-    pr, qr = prob.ee_ref(tN)
-
-    def ee_fun(z):
-        nk = ce.node_kinematics(prob.model, z)
-        return np.concatenate([nk["ee_pos"], ce.quat_distance(ce.quat_from_matrix(nk["ee_rot"]), qr)], axis=-1)
-
-    ev = ee_fun(xs[n]) - np.concatenate([pr, np.zeros(3)])
-    Je = ce.cstep_jacobian(ee_fun, xs[n])
-    W = np.diag([P.mu_fee_pos] * 3 + [P.mu_fee_ori] * 3)
-    terminal = dict(Q=Je.T @ W @ Je, q=Je.T @ W @ ev, c=0.5 * ev @ W @ ev)
-    # baseline performance
-    base = performance(prob, x0, times, flags, xs, us)
-    dx, dut, Ks, ks = riccati(stages, terminal, x0 - xs[0])
-    armijo = sum(float(st["q"] @ dx[k] + st["r"] @ dut[k]) for k, st in enumerate(stages)) + float(terminal["q"] @ dx[n])
-    du = [st["Pu"] @ dut[k] + st["Px"] @ dx[k] + st["Pe"] for k, st in enumerate(stages)]
-    dxn = np.sqrt(sum(float(d @ d) for d in dx))
-    dun = np.sqrt(sum(float(d @ d) for d in du))
-    alpha, accepted = 1.0, False
-    while True:
-        xn = xs + alpha * np.array(dx)
-        un = us + alpha * np.array(du)
-        new = performance(prob, x0, times, flags, xn, un)
-        if accept_step(S, base, new, alpha * armijo):
-            accepted = True
+            alpha, new = 0.0, base
+        history.append(dict(alpha=alpha, base=base, new=new))
+        convergence = check_convergence(S, it, iterations, base, new, alpha, dxn, dun)
+        if convergence is not None:
             break
-        alpha *= S["alpha_decay"]
-        if alpha * dxn < S["deltaTol"] and alpha * dun < S["deltaTol"]:
-            break
-        if alpha < S["alpha_min"]:
-            break
-    if accepted:
-        xs, us = xn, un
-    else:
-        alpha, new = 0.0, base
     # [upstream] toPrimalSolution: inputs at pre-event nodes repeat the previous input, last input repeated
     uo = np.array(us)
     for i in range(n):
@@ -441,7 +464,8 @@ def mpc_cycle(prob, t0, x0, return_debug=False):
     uo = np.vstack([uo, uo[-1:]])
     tout = np.array([G.interval_start(times[i], flags[i]) for i in range(n + 1)])
     prob.prev = (tout, np.array(xs), uo)
-    info = dict(alpha=alpha, base=base, new=new, armijo=armijo, flags=flags, times=times, n=n,
+    info = dict(alpha=alpha, base=base, new=new, armijo=armijo, flags=flags, times=times, n=n, history=history,
+                convergence=convergence,
                 modes=np.array([prob.mode_at(G.interval_start(times[i], flags[i])) for i in range(n + 1)], dtype=np.int32))
     if return_debug:
         info.update(stages=stages, nodes=nodes, terminal=terminal, dx=np.array(dx), du=np.array(du), Ks=Ks, ks=ks)

@@ -175,3 +175,27 @@ def test_standing_is_a_fixed_point(oracle_inputs):
         _, xs, us, info = sqp.mpc_cycle(prob, 0.01 * c, P.x_init)
     assert np.abs(xs[:, 6:12] - P.x_init[6:12]).max() < 5e-2
     assert abs(us[0, [2, 5, 8, 11]].sum() - m.total_mass * 9.81) < 0.05 * m.total_mass * 9.81
+
+
+def test_multi_iteration_sqp_specification(oracle_inputs):
+    """sqpIteration > 1 (the reference runs 1, task.info:80): the oracle's loop is the specification for the multi-iteration
+    path. One iteration of the loop is the single-iteration cycle; an iteration starts from the performance the previous one
+    ended with; the constraint violation of a perturbed start does not grow over the iterations."""
+    m, P = oracle_inputs
+    x0s, phase = scenarios.perturbed_states(m, P, 1, seed=8)
+    tt, ts = scenarios.standing_target(m, P)
+    ev, md = G.tile_schedule(P.gaits["trot"], -1.2 - phase[0], 1.2)
+    mk = lambda: sqp.MpcProblem(m, P, ev, md, tt, ts, horizon=0.06, dt=0.01)
+    _, x1, u1, i1 = sqp.mpc_cycle(mk(), 0.0, x0s[0])
+    assert i1["convergence"] == "ITERATIONS" and len(i1["history"]) == 1
+    _, x3, u3, i3 = sqp.mpc_cycle(mk(), 0.0, x0s[0], iterations=3)
+    h = i3["history"]
+    assert 1 <= len(h) <= 3 and i3["convergence"] in ("ITERATIONS", "STEPSIZE", "METRICS", "PRIMAL")
+    assert h[0]["alpha"] == i1["alpha"] and np.isclose(h[0]["new"]["merit"], i1["new"]["merit"], rtol=1e-12)
+    if len(h) == 1:
+        assert np.array_equal(x3, x1) and np.array_equal(u3[:-1], u1[:-1])
+    viol = lambda p: np.sqrt(p["dyn"] + p["eq"])
+    for a, b in zip(h[:-1], h[1:]):
+        for key in ("merit", "dyn", "eq"):
+            assert np.isclose(b["base"][key], a["new"][key], rtol=1e-9, atol=1e-14)
+    assert viol(h[-1]["new"]) <= viol(h[0]["base"]) * (1 + 1e-9)
