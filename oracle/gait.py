@@ -59,12 +59,12 @@ def time_grid(t0, tf, dt, events):
         if t_next > times[-1] + DT_MIN:
             times.append(t_next)
             flags.append(ev)
-            if ev == EV_PRE:
-                times.append(t_next)
-                flags.append(EV_POST)
-        else:
+        else:                      # closer than dt_min to the last node: that node is moved (and may become the pre-event node)
             times[-1] = t_next
             flags[-1] = ev
+        if ev == EV_PRE:           # the post-event node follows the pre-event node in both branches
+            times.append(t_next)
+            flags.append(EV_POST)
     return np.array(times), np.array(flags, dtype=np.int32)
 
 

@@ -191,7 +191,8 @@ class Wbc:
         self.m, self.P = model, P
         self.g = dict(DEFAULT_GAINS if gains is None else gains)
         self.mu = P.friction_wbc                                                      # task.info:347-350
-        self.tau_max = model.effort[6:].copy()                                        # WbcBase.cpp:597-604
+        # WbcBase.cpp:599-604 + :409-410: effortLimit.segment<3>(6) replicated over the four legs, effortLimit.tail(6) for the arm
+        self.tau_max = np.concatenate([np.tile(model.effort[6:9], 4), model.effort[-6:]])
         self.input_last = np.zeros(30)
         self.mpc_variant = mpc_variant
 

@@ -563,7 +563,10 @@ int qmb200_load_wbc(const char* task_info, const qmb200_model_desc* M, qmb200_wb
     for (int i = 0; i < 6; ++i) { C->kp_arm_joint[i] = kpj[i]; C->kd_arm_joint[i] = 75; }
     for (int i = 0; i < 3; ++i) { C->kp_ee_linear[i] = 3000; C->kd_ee_linear[i] = 75; C->kp_ee_angular[i] = 2000; C->kd_ee_angular[i] = 75; }
     C->friction_mu = t.num("frictionConeTask.frictionCoefficient");
-    for (int i = 0; i < 18; ++i) C->tau_max[i] = M->effort[6 + i];
+    // WbcBase::loadTasksSetting (WbcBase.cpp:599-604): the first leg's (HAA, HFE, KFE) limits are replicated over the four legs
+    // (formulateTorqueLimitsTask, :409-410); the arm takes its own six.
+    for (int i = 0; i < 12; ++i) C->tau_max[i] = M->effort[6 + i % 3];
+    for (int i = 12; i < 18; ++i) C->tau_max[i] = M->effort[6 + i];
     C->swing_weight = 100.0;   // HierarchicalWbc.cpp:29
     C->init_time = 10.0;       // HierarchicalWbc.cpp:32
     C->gravity = 9.81;

@@ -126,9 +126,12 @@ QM_HDN void build_grid(const qmb200_solver_desc& S, double t0, const double* eve
     if (tn > node_t[n - 1] + S.dt_min) {
       if (n + 2 > NMAX) { st |= ST_GRID_OVERFLOW; node_t[n - 1] = tf; node_flag[n - 1] = EV_NONE; break; }
       node_t[n] = tn; node_flag[n] = ev; ++n;
-      if (ev == EV_PRE) { node_t[n] = tn; node_flag[n] = EV_POST; ++n; }
     } else {
-      node_t[n - 1] = tn; node_flag[n - 1] = ev;
+      node_t[n - 1] = tn; node_flag[n - 1] = ev;     // closer than dt_min to the last node: that node moves (and may become the pre-event node)
+    }
+    if (ev == EV_PRE) {                              // every pre-event node is followed by its post-event node, in both branches
+      if (n + 1 > NMAX) { st |= ST_GRID_OVERFLOW; node_t[n - 1] = tf; node_flag[n - 1] = EV_NONE; break; }
+      node_t[n] = tn; node_flag[n] = EV_POST; ++n;
     }
   }
   if (nev < 1 || events[nev - 1] < tf) st |= ST_BAD_SCHEDULE;   // schedule must extend past the horizon

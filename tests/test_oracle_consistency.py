@@ -38,6 +38,26 @@ def test_time_grid_events():
     assert np.allclose(t, [0, 0.015, 0.03, 0.045, 0.05]) and not f.any()
 
 
+def test_every_pre_event_node_is_followed_by_its_post_event_node():
+    """[upstream] timeDiscretizationWithEvents appends the PostEvent node after the push-or-overwrite branch: with dt = 0.015
+    and 0.3 s phases the accumulated node time lands within dt_min of an event for many start times (1.1999999... vs 1.2),
+    the last node is then moved onto the event and must still be followed by a post-event node at the same time."""
+    events = [0.3 * k for k in range(1, 9)]
+    overwritten = 0
+    for i in range(300):
+        t0 = 0.001 * i
+        t, f = G.time_grid(t0, t0 + 1.0, 0.015, events)
+        assert (np.diff(t) >= 0).all() and t[0] == t0 and t[-1] == t0 + 1.0
+        pre = np.nonzero(f == G.EV_PRE)[0]
+        assert len(pre) == sum(1 for e in events if t0 < e < t0 + 1.0)
+        for k in pre:
+            assert f[k + 1] == G.EV_POST and t[k + 1] == t[k] and t[k] in events
+        for k in np.nonzero(f == G.EV_POST)[0]:
+            assert f[k - 1] == G.EV_PRE
+        overwritten += int(any(abs((t[k] - t[k - 1]) - 0.015) < 1e-9 and abs((t[k + 2] - t[k]) - 0.015) < 1e-9 for k in pre if k > 0))
+    assert overwritten > 20          # the overwrite branch is exercised
+
+
 def test_swing_spline_boundary_values(oracle_inputs):
     m, P = oracle_inputs
     ev, md = G.tile_schedule(P.gaits["trot"], 0.0, 2.0)

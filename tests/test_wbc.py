@@ -5,6 +5,7 @@ import pytest
 from helpers import ROOT, rel_l2
 
 GOLD = ROOT + "/tests/golden/wbc_config5.npz"
+GOLD512 = ROOT + "/tests/golden/wbc_config5_first512.npz"
 TOL = 1e-6          # (x*, tau) 1e-6 on converged instances
 EXPECTED = 1e-8
 
@@ -139,7 +140,16 @@ def test_cuda_full_size_against_cpu_port_and_properties(descs):
     ctx.update(W.x_des, W.u_last, W.rbd, W.mode, W.period, W.time)
     cmd, st = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)
     assert (st & ~2 == 0).all()                               # WST_DEGENERATE (tight inherited rows) is informational
-    sub = 512
+    # the first 512 solves against the NumPy oracle (tests/golden/wbc_config5_first512.npz, tools/gen_golden.py wbc512); the few
+    # instances the oracle's own QP solver gives up on (degenerate inherited rows) are recorded as NaN there and skipped
+    g = np.load(GOLD512)
+    sub = int(g["n"])
+    ok = ~np.isnan(g["cmd"][:, 0])
+    assert ok.sum() >= 0.95 * sub and np.array_equal(g["mode"], W.mode[:sub])
+    errs = np.array([rel_l2(cmd[b], g["cmd"][b]) for b in range(sub) if ok[b]])
+    assert np.median(errs) < 1e-10 and errs.max() < TOL, (np.median(errs), errs.max())
+    # ... and 4096 against the CPU port (same algorithm, scalar host loops)
+    sub = 4096
     ul = W.u_last[:sub].copy()
     ref, _ = abi_fill.cport_wbc(W.model, W.wbc, W.x_des[:sub], W.u_des[:sub], W.rbd[:sub], W.mode[:sub], W.period[:sub], W.time[:sub], ul, threads=8)
     errs = np.array([rel_l2(cmd[b], ref[b]) for b in range(sub)])
@@ -152,12 +162,12 @@ def test_cuda_full_size_against_cpu_port_and_properties(descs):
     inside, total = 0, 0
     for leg in range(4):
         stance = ((W.mode >> (3 - leg)) & 1).astype(bool)
-        assert np.median(np.abs(f[~stance, leg])) < 1e-9
+        assert np.abs(f[~stance, leg]).max() < 1e-8
         fz = f[stance, leg, 2]
         ok_leg = (fz > -1e-6) & (np.abs(f[stance, leg, 0]) <= W.wbc.friction_mu * fz + 1e-6) & (np.abs(f[stance, leg, 1]) <= W.wbc.friction_mu * fz + 1e-6)
         inside += int(ok_leg.sum()); total += int(stance.sum())
-    assert inside / total > 0.95, inside / total
-    assert (np.abs(tau) <= tau_max + 1e-6).mean() > 0.99
+    assert inside / total > 0.999, inside / total           # level-0 rows are soft: a handful of infeasible random states
+    assert (np.abs(tau) <= tau_max + 1e-6).all()
     assert np.isfinite(cmd).all()
     ctx.close()
 
@@ -183,3 +193,18 @@ def test_cuda_reset_and_device_entry(descs):
     ctx.sync()
     assert np.array_equal(cmd.cpu().numpy(), a)
     ctx.close()
+
+
+def test_cport_matches_full_size_golden_subset(descs):
+    """The first 512 solves of the bench's own config-5 batch: CPU port against the NumPy oracle."""
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    g = np.load(GOLD512)
+    sub = int(g["n"])
+    W = workload.WbcWorkload(65536)
+    ul = W.u_last[:sub].copy()
+    cmd, st = abi_fill.cport_wbc(W.model, W.wbc, W.x_des[:sub], W.u_des[:sub], W.rbd[:sub], W.mode[:sub], W.period[:sub], W.time[:sub], ul, threads=8)
+    ok = ~np.isnan(g["cmd"][:, 0])
+    assert ok.sum() >= 0.95 * sub
+    errs = np.array([rel_l2(cmd[b], g["cmd"][b]) for b in range(sub) if ok[b]])
+    assert np.median(errs) < 1e-10 and errs.max() < 1e-7, (np.median(errs), errs.max())
