@@ -103,8 +103,38 @@ def kernel_bytes_per_node(kernel, nut):
 
 
 def cycle_bytes_per_node(nut):
-    """SURVEY.md §8(d) whole-cycle figure: 10 118 doubles = 80 944 B per node for trot (nut = 16)."""
-    return 8 * ((900 + 30 * nut + 30) + (900 + nut * nut + 30 * nut + 30 + nut + 1) + (30 * nut + 900 + 30) + (30 * nut + nut) + 120)
+    """SURVEY.md §8(d) whole-cycle figure: every intermediate block that cannot stay on-chip across the forward-transcribe /
+    backward-Riccati / forward-rollout dependency is written once and read once, the trajectories (x, u) go in and out once:
+    2 x 4999 + 120 = 10 118 doubles = 80 944 B per node for trot (nut = 16)."""
+    blocks = (900 + 30 * nut + 30) + (900 + nut * nut + 30 * nut + 30 + nut + 1) + (30 * nut + 900 + 30) + (30 * nut + nut)
+    return 8 * (2 * blocks + 120)
+
+
+# FP64 peak of this part for the dense small-matrix products: measured with tools/micro/dmma_bench.cu on the gpurun B200
+# (mma.sync.m8n8k4.f64 = SASS DMMA, 37.1 TFLOP/s; plain DFMA 34.0; profiles/dmma_micro_r01.txt). Not in MEASURED_PEAKS.json.
+FP64_PEAK_TFLOPS = 37.1
+
+
+def kernel_flops_per_node(kernel, nut):
+    """Algorithmic FP64 flops (2 per multiply-add) of the dense products a kernel carries out per intermediate node; the
+    symmetric products are counted in full (what the recursion defines), index / barrier / reference arithmetic is not counted.
+    k_solve: S A, S B, S b | G = R + B'SB, g | G^-1 (Gauss-Jordan, 2 nut^3) | H = P + B'SA, Q + A'SA, A'sb | K = -G^-1 H, kff |
+             S += H'K, s += H'kff | forward: K dx, A dx + B dut, projection rows.
+    k_lq:    Dinv T | Heun sensitivities (9x9x60 products) | Gauss-Newton end-effector Hessian | change of variables
+             (A + B Px, B Pu, R Px, R Pu, Q + Px'R Px, Pu'R Px, Pu'R Pu) with nv = 26 - nut pivot rows."""
+    nv = 26 - nut
+    if kernel == "k_solve":
+        bwd = 2 * (27000 + 900 * nut + 900) + 2 * (30 * nut * nut + 30 * nut) + 2 * nut ** 3 + 2 * (900 * nut + 27000 + 900) \
+            + 2 * (30 * nut * nut + nut * nut) + 2 * (900 * nut + 30 * nut)
+        fwd = 2 * (30 * nut + 900 + 30 * nut + nv * (30 + nut) + 30 + nut)
+        return bwd + fwd
+    if kernel == "k_lq":
+        nsel = nv + nut
+        heun = 2 * (9 * 9 * 60) + 4 * 9 * 60
+        cost = 2 * 6 * 24 * 24 + 2 * 2 * 900
+        cov = 2 * nv * (900 + 30 * nsel + 30 * nut + nsel * nut + 900 + 30 * nut + nut * nut) + 2 * nv * nv * 49 + 2 * 30 * (nsel + 30)
+        return heun + cost + cov
+    return None
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -126,7 +156,9 @@ def run_reference(args, rank, world):
         cp.cycle(np.full(sample, CYCLE_DT * step), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
         step += 1
     el = time.perf_counter() - t
+    cp.close()
     value = sample * args.steps / el
+    latency = cpu_latency_legs()
     desc = "%d problems of the same workload per step (1/8 of one GPU batch), %d steps, all %d host threads" % (sample, args.steps, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -135,7 +167,71 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                          "note": "CPU restatement (oracle/cport, g++ -O3, std::thread over problems) — not the reference "
                                  "binary: OCS2/Pinocchio/HPIPM are not vendored and cannot be built in this image"},
+        "latency": latency,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+LATENCY_SETTINGS = (("reference setting: horizon 1.0 s / dt 0.015 s (task.info:79,141), N~67", 1.0, 0.015),
+                    ("config 1: horizon 0.2 s / dt 0.01 s, N=20", 0.2, 0.01),
+                    ("config 2 shape: horizon 1.0 s / dt 0.01 s, N=100", 1.0, 0.01))
+
+
+def cpu_latency_legs(node_threads=3, cycles=20, warm=3):
+    """Reference-like latency: ONE problem, 3 worker threads over the nodes (sqp.nThreads,
+    task.info:78), warm-started cycles, trot; median and min wall time per MPC cycle of the CPU port."""
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    legs = []
+    for name, hor, dt in LATENCY_SETTINGS:
+        W = workload.Workload(1, horizon=hor, dt=dt, t_span=CYCLE_DT * (cycles + warm + 2))
+        cp = abi_fill.CPort(W.model, W.problem, W.solver, 1, threads=1, node_threads=node_threads)
+        ts = []
+        for c in range(cycles + warm):
+            t = time.perf_counter()
+            out = cp.cycle(np.full(1, CYCLE_DT * c), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+            ts.append(time.perf_counter() - t)
+        cp.close()
+        legs.append({"setting": name, "problems": 1, "node_threads": node_threads, "nodes": int(out["n"][0]),
+                     "ms_per_cycle_median": 1e3 * float(np.median(ts[warm:])), "ms_per_cycle_min": 1e3 * float(min(ts[warm:])),
+                     "cycles_per_s": 1.0 / float(np.median(ts[warm:]))})
+    return legs
+
+
+def gpu_latency_legs(q, workload, device, cycles=20, warm=3):
+    """The same single-problem settings through qmb200_mpc_cycle_batch (host buffers, B = 1): what one robot would see."""
+    legs = []
+    for name, hor, dt in LATENCY_SETTINGS:
+        W = workload.Workload(1, horizon=hor, dt=dt, t_span=CYCLE_DT * (cycles + warm + 2))
+        ctx = q.MpcContext(W.model, W.problem, W.solver, 1, device=device)
+        out = ctx.alloc_outputs(pinned=True)
+        ts = []
+        for c in range(cycles + warm):
+            t = time.perf_counter()
+            ctx.cycle(np.full(1, CYCLE_DT * c), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x, out=out)
+            ts.append(time.perf_counter() - t)
+        ctx.close()
+        legs.append({"setting": name, "problems": 1, "nodes": int(out["n"][0]), "ms_per_cycle_median": 1e3 * float(np.median(ts[warm:])),
+                     "ms_per_cycle_min": 1e3 * float(min(ts[warm:])), "cycles_per_s": 1.0 / float(np.median(ts[warm:]))})
+    return legs
+
+
+def wbc_cpu_baseline(WW, sub=4096):
+    """WBC on the CPU port beside the GPU number: single-solve latency on one thread and
+    throughput on all host threads over the first `sub` solves of the same batch."""
+    from oracle import abi_fill
+    cores = os.cpu_count() or 1
+    sl = slice(0, sub)
+    args = (WW.model, WW.wbc, WW.x_des[sl], WW.u_des[sl], WW.rbd[sl], WW.mode[sl], WW.period[sl], WW.time[sl])
+    abi_fill.cport_wbc(*args, WW.u_last[sl].copy(), threads=cores)                      # warm-up (pages, thread start)
+    t = time.perf_counter()
+    abi_fill.cport_wbc(*args, WW.u_last[sl].copy(), threads=cores)
+    thr = sub / (time.perf_counter() - t)
+    one = tuple(a[:64] if isinstance(a, np.ndarray) else a for a in args)
+    t = time.perf_counter()
+    abi_fill.cport_wbc(*one, WW.u_last[:64].copy(), threads=1)
+    lat = (time.perf_counter() - t) / 64
+    return {"value": thr, "unit": "WBC-solves/s", "cores": cores, "kind": "port", "single_solve_latency_ms_1_thread": 1e3 * lat,
+            "sample": "first %d solves of the same batch on %d threads; latency: 64 solves back to back on 1 thread (oracle/cport)" % (sub, cores)}
 
 
 def cpu_baseline_sample():
@@ -289,6 +385,8 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
                     "algorithmic_bytes_per_solve": 1376, "achieved_gbs": WW.B * 1376 / (wms * 1e-3) / 1e9,
                     "note": "fused dynamics + task stack + hierarchical QP per CTA; FP64 / active-set latency bound, not HBM bound"}
         wctx.close()
+        if not args.no_cpu_baseline:
+            wbc_line["cpu_baseline"] = wbc_cpu_baseline(WW)
 
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=f64, device=dev)
     if world > 1:
@@ -317,7 +415,20 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
         tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")       # DRAM bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)
-        cyc_bytes = sum(cycle_bytes_per_node(16) for _ in range(1)) * float(nn.sum() - B)
+        cyc_bytes = 0.0
+        flops_dom = 0.0
+        for b in range(B):
+            for kk in range(nn[b] - 1):
+                nut_k = 14 + bin(int(modes_last[b, kk]) & 15).count("1")
+                cyc_bytes += cycle_bytes_per_node(nut_k)
+                fl = kernel_flops_per_node(dom, nut_k)
+                flops_dom += fl if fl is not None else 0.0
+        fp64 = None
+        if flops_dom > 0:
+            fp64 = {"kernel": dom, "algorithmic_flops_per_launch": flops_dom, "achieved": flops_dom / (ms_dom * 1e-3) / 1e12,
+                    "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": flops_dom / (ms_dom * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                    "peak_source": "measured DMMA micro-benchmark (tools/micro/dmma_bench.cu, profiles/dmma_micro_r01.txt); "
+                                   "not in MEASURED_PEAKS.json"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,10 +440,11 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": int(nodes_bytes),
                          "share_of_step": kt[dom][0] / max(1e-9, dev_ms),      # of the device-timed region (k_proj overlaps k_kin2)
+                         "fp64": fp64,
                          "cycle_level": {"algorithmic_bytes_per_step": int(cyc_bytes),
                                          "achieved_gbs": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
                                          "frac": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
-                                         "note": "SURVEY.md 8(d): 80 944 B per node (trot) x nodes of the batch; the cycle is "
+                                         "note": "SURVEY.md 8(d): 80 944 B per node (trot; written once + read once) x nodes of the batch; the cycle is "
                                                  "FP64-FMA / dependency bound (Riccati, projection), not HBM bound"}},
             "kernel_ms_per_step": {kname: v[0] / args.steps for kname, v in kt.items() if v[1]},
             "failed_problems": bad, "mean_step_size": alpha_mean,
@@ -342,6 +454,8 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
             line["secondary"] = wbc_line
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
+        if world == 1 and not args.no_latency:
+            line["latency"] = gpu_latency_legs(q, workload, local_rank)
         if result_fd is not None:
             os.write(result_fd, (json.dumps(line) + "\n").encode())     # the process's real stdout (see main)
         else:
@@ -360,6 +474,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wbc", action="store_true", help="skip the secondary WBC-solves/s measurement")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-problem latency legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -47,8 +47,10 @@ enum {
   QMB200_ST_NAN = 16,
   QMB200_ST_STEP_REJECTED = 32
 };
-#define QMB200_INFO_SIZE 16   /* per-problem info record: alpha, done, armijo, |dx|, |du|, base(merit,dyn,eq), new(merit,dyn,eq), iters */
-#define QMB200_NUM_KERNELS 11 /* schedule, init_guess, kin1, kin2, lq, solve, trial, decide, finalize, policy, proj */
+#define QMB200_INFO_SIZE 16   /* per-problem info record: alpha, done, armijo, |dx|, |du|, base(merit,dyn,eq), new(merit,dyn,eq), line-search
+                                 trials, |x0 - x[0]|^2, SQP iterations carried out (13), why the SQP loop stopped (14: 1 iteration budget,
+                                 2 step size, 3 metrics, 4 primal step; [upstream] SqpSolver::Convergence) */
+#define QMB200_NUM_KERNELS 13 /* schedule, init_guess, kin1, kin2, lq, solve, trial, decide, finalize, policy, proj, backtrack, step */
 
 int qmb200_version(void);
 const char* qmb200_last_error(void);
@@ -69,6 +71,10 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
 int qmb200_destroy(qmb200_ctx* ctx);
 int qmb200_mpc_reset(qmb200_ctx* ctx);
 int qmb200_sync(qmb200_ctx* ctx);
+/* Order the context's stream behind the work enqueued so far on `stream` (a cudaStream_t, e.g. qmb200_wbc_stream(..)): an event
+ * is recorded there and waited for here; nothing blocks on the host. The _dev entry points of the two contexts run on their own
+ * streams, so a device-side chain MPC -> policy -> WBC -> actuator needs one such call per hand-over. */
+int qmb200_wait_stream(qmb200_ctx* ctx, void* stream);
 
 /* One SQP cycle for every problem of the batch, HOST buffers (copies inside the call, returns when results are on the host).
  *  t0[B] x0[B][30] events[B][EMAX] modes[B][EMAX+1] nevents[B] target_t[B][KT] target_x[B][KT][37]
@@ -76,7 +82,8 @@ int qmb200_sync(qmb200_ctx* ctx);
 int qmb200_mpc_cycle_batch(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events, const int32_t* modes,
                            const int32_t* nevents, const double* target_t, const double* target_x, double* t_out,
                            double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status);
-/* Same with DEVICE buffers; asynchronous on the context's stream except for the line-search hand-shake. */
+/* Same with DEVICE buffers; fully asynchronous on the context's stream (the filter line search and the SQP loop's early exit
+ * run on the device: no host synchronisation inside the cycle). solver.sqp_iterations > 1 runs the multi-iteration SQP. */
 int qmb200_mpc_cycle_batch_dev(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events,
                                const int32_t* modes, const int32_t* nevents, const double* target_t, const double* target_x,
                                double* t_out, double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info,
@@ -145,6 +152,7 @@ int qmb200_wbc_batch(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_d
 int qmb200_wbc_batch_dev(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
                          const double* period, const double* time, double* cmd, int32_t* status);
 int qmb200_wbc_sync(qmb200_wbc_ctx* ctx);
+int qmb200_wbc_wait_stream(qmb200_wbc_ctx* ctx, void* stream);   /* see qmb200_wait_stream */
 void* qmb200_wbc_stream(qmb200_wbc_ctx* ctx);
 int qmb200_wbc_kernel_time(qmb200_wbc_ctx* ctx, double* total_ms, int64_t* launches, int32_t reset);
 

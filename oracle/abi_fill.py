@@ -77,6 +77,7 @@ def solver_desc(P, horizon=None, dt=None, max_nodes=None, max_events=32, max_tar
     d.alpha_decay, d.alpha_min = P.sqp["alpha_decay"], P.sqp["alpha_min"]
     d.gamma_c, d.armijo_factor = P.sqp["gamma_c"], P.sqp["armijoFactor"]
     d.weak_eps, d.dt_min = 1e-6, 1e-8
+    d.sqp_iterations, d.cost_tol = P.sqp["sqpIteration"], P.sqp.get("costTol", 1e-4)
     n = int(round(d.horizon / d.dt))
     d.max_nodes = (n + 1 + 24) if max_nodes is None else max_nodes
     d.max_events = max_events
@@ -141,12 +142,15 @@ class CPort:
     LS = dict(alpha=0, done=1, armijo=2, dxnorm=3, dunorm=4, base_merit=5, base_dyn=6, base_eq=7,
               new_merit=8, new_dyn=9, new_eq=10, iters=11)
 
-    def __init__(self, md, pd, sd, B, threads=1):
+    def __init__(self, md, pd, sd, B, threads=1, node_threads=1):
+        """threads: workers over the problems of the batch; node_threads: workers over the nodes of one problem (the
+        reference's sqp.nThreads, task.info:78) -- the latency setting, used with threads = 1."""
         self.lib = load_cport()
         self.lib.cport_create.restype = C.c_void_p
         self.md, self.pd, self.sd, self.B = md, pd, sd, B
         self.NMAX, self.EMAX, self.KT = sd.max_nodes, sd.max_events, sd.max_targets
         self.ctx = C.c_void_p(self.lib.cport_create(C.byref(md), C.byref(pd), C.byref(sd), B, threads))
+        self.lib.cport_set_node_threads(self.ctx, int(node_threads))
 
     def close(self):
         if self.ctx:

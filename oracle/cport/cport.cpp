@@ -18,6 +18,7 @@ struct CportCtx {
   qmb200_solver_desc S;
   MpcBuffers m;
   int threads;
+  int node_threads = 1;   // worker threads over the nodes of one problem (the reference's sqp.nThreads, task.info:78)
 };
 
 template <class F>
@@ -74,6 +75,7 @@ void cport_destroy(CportCtx* c) {
 }
 
 void cport_reset(CportCtx* c) { memset(c->m.nprev, 0, sizeof(int32_t) * c->m.B); }
+void cport_set_node_threads(CportCtx* c, int n) { c->node_threads = n < 1 ? 1 : n; }
 
 const MpcBuffers* cport_buffers(CportCtx* c) { return &c->m; }
 
@@ -109,23 +111,35 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
                            m.prev_t + o, m.prev_x + o * 30, m.prev_u + o * 30, m.xs + o * 30, m.us + o * 30);
     const double* tt = m.target_t + (size_t)b * KT;
     const double* ts = m.target_x + (size_t)b * KT * QM_NTARGET;
-    for (int k = 0; k <= n; ++k) {
+    double* ls = m.ls + (size_t)b * LS_SIZE;
+    std::vector<double> xt(30), ut(30), xnt(30);
+    const int iterations = S.sqp_iterations < 1 ? 1 : S.sqp_iterations;
+    m.conv[b] = CV_NONE; ls[LS_SQP_ITERS] = 0.0; ls[LS_CONV] = 0.0;
+    const int nth = c->node_threads;
+    std::vector<std::vector<double>> Wn(nth > 1 ? nth : 0, std::vector<double>(W.size()));
+    for (int it = 0; it < iterations; ++it) {
+    // transcription: independent over the nodes (the reference spreads them over sqp.nThreads workers)
+    parallel_for(nth > 1 ? nth : 1, nth, [&](int tid) {
+    double* Wd = (nth > 1) ? Wn[tid].data() : W.data();
+    std::vector<int> WIn(TI_SIZE);
+    for (int k = tid; k <= n; k += (nth > 1 ? nth : 1)) {
       double* sb = m.stage + (o + k) * SB_SIZE; double* pb = m.proj + (o + k) * PB_SIZE; double* pf = m.perf_base + (o + k) * PF_SIZE;
       const double* x = m.xs + (o + k) * 30; const double* u = m.us + (o + k) * 30; const double* xn = m.xs + (o + k + 1) * 30;
-      if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, x, W.data() + TW_KIN, W.data() + TW_REF,
-                                 W.data() + TW_E6, W.data() + TW_DQ, W.data() + TW_JE, sb, pf);
+      if (k == n) terminal_node(g, M, P, m.node_t[o + k], m.node_mode[o + k], tt, ts, KT, x, Wd + TW_KIN, Wd + TW_REF,
+                                 Wd + TW_E6, Wd + TW_DQ, Wd + TW_JE, sb, pf);
       else if (m.node_flag[o + k] == EV_PRE) event_node(g, x, xn, sb, pb, pf);
       else transcribe_node(g, M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
-                           x, u, xn, W.data(), WI.data(), sb, pb, pf, m.status + b);
+                           x, u, xn, Wd, WIn.data(), sb, pb, pf, m.status + b);
     }
+    });
     DirectFetch fetch;
     solve_problem(g, fetch, m, b, W.data(), W.data());
     // filter line search
-    double* ls = m.ls + (size_t)b * LS_SIZE;
-    std::vector<double> xt(30), ut(30), xnt(30);
     while (ls[LS_DONE] == 0.0) {
       const double alpha = ls[LS_ALPHA];
-      for (int k = 0; k <= n; ++k) {
+      parallel_for(nth > 1 ? nth : 1, nth, [&](int tid) {
+      std::vector<double> xt(30), ut(30), xnt(30);
+      for (int k = tid; k <= n; k += (nth > 1 ? nth : 1)) {
         double* pf = m.perf_trial + (o + k) * PF_SIZE;
         for (int i = 0; i < 30; ++i) {
           xt[i] = m.xs[(o + k) * 30 + i] + alpha * m.dxs[(o + k) * 30 + i];
@@ -140,9 +154,18 @@ int cport_mpc_cycle(CportCtx* c, const double* t0, const double* x0, const doubl
         } else perf_node_serial(M, P, m.node_ts[o + k], m.node_dt[o + k], m.node_mode[o + k], m.node_zvel + (o + k) * 4, tt, ts, KT,
                                 xt.data(), ut.data(), xnt.data(), pf);
       }
+      });
       decide_problem(S, m, b);
     }
+    if (it + 1 < iterations) {                         // intermediate SQP iteration: step in place, convergence test (k_step)
+      for (int cc = 0; cc < 60; ++cc) step_component(m, b, cc);
+      const int cv = check_convergence(S, ls, it, iterations);
+      m.conv[b] = cv; ls[LS_CONV] = (double)cv;
+      if (cv != CV_NONE) break;
+    }
+    }
     for (int cc = 0; cc < 60; ++cc) finalize_component(m, b, cc, t_out, x_out, u_out);
+    if (m.conv[b] == CV_NONE) ls[LS_CONV] = (double)CV_ITERATIONS;
     if (n_out) n_out[b] = nn;
     if (mode_out) for (int k = 0; k < nn; ++k) mode_out[o + k] = m.node_mode[o + k];
     if (info) memcpy(info + (size_t)b * LS_SIZE, ls, sizeof(double) * LS_SIZE);

@@ -15,9 +15,10 @@ from ._abi import ModelDesc, ProblemDesc, SolverDesc  # noqa: F401
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QMB200_LIB_PATH", os.path.join(_HERE, "libqmb200.so"))   # override: development builds only
 INFO_SIZE = 16
-KERNEL_NAMES = ["k_schedule", "k_init_guess", "k_kin1", "k_kin2", "k_lq", "k_solve", "k_trial", "k_decide", "k_finalize", "k_policy", "k_proj"]
+KERNEL_NAMES = ["k_schedule", "k_init_guess", "k_kin1", "k_kin2", "k_lq", "k_solve", "k_trial", "k_decide", "k_finalize", "k_policy", "k_proj",
+                "k_backtrack", "k_step"]
 INFO = dict(alpha=0, done=1, armijo=2, dxnorm=3, dunorm=4, base_merit=5, base_dyn=6, base_eq=7,
-            new_merit=8, new_dyn=9, new_eq=10, iters=11)
+            new_merit=8, new_dyn=9, new_eq=10, iters=11, dx0sq=12, sqp_iterations=13, convergence=14)
 
 _lib = None
 
@@ -51,6 +52,31 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _host(a, shape, dtype, name):
+    """Host buffer handed to the C-ABI: contiguous, of the dtype and shape the entry point reads (an undersized buffer would be
+    an out-of-bounds read in the library)."""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.shape != tuple(shape):
+        raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), a.shape))
+    return a
+
+
+def _dev(t, shape, dtype, name, device=None, optional=False):
+    """Device tensor handed to the C-ABI as a raw pointer: CUDA, contiguous, of the dtype and shape the kernels index."""
+    import torch
+    if t is None:
+        if optional:
+            return None
+        raise ValueError("%s is required" % name)
+    want = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[dtype]
+    if not t.is_cuda or t.dtype != want or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+        raise ValueError("%s must be a contiguous CUDA tensor of dtype %s and shape %s (got %s %s on %s)"
+                         % (name, want, tuple(shape), t.dtype, tuple(t.shape), t.device))
+    if device is not None and t.device.index != device:
+        raise ValueError("%s lives on cuda:%s, the context on cuda:%s" % (name, t.device.index, device))
+    return C.c_void_p(t.data_ptr())
+
+
 class MpcContext:
     """Mirror of the reference's SqpMpc + MPC_MRT_Interface pair for a batch of independent problems
     (qm_controllers/src/QMController.cpp:287-335): cycle() = advanceMpc(), evaluate_policy() = evaluatePolicy()."""
@@ -59,6 +85,7 @@ class MpcContext:
         self.L = lib()
         self.model, self.problem, self.solver = model, problem, solver
         self.B, self.NMAX, self.EMAX, self.KT = batch, solver.max_nodes, solver.max_events, solver.max_targets
+        self.device = device
         h = C.c_void_p()
         _check(self.L.qmb200_create(C.byref(model), C.byref(problem), C.byref(solver), batch, device, C.byref(h)))
         self.h = h
@@ -79,6 +106,11 @@ class MpcContext:
     @property
     def stream(self):
         return self.L.qmb200_stream(self.h)
+
+    def wait_for(self, other):
+        """Order this context's stream behind everything enqueued so far on `other`'s stream (a context or a raw cudaStream_t)."""
+        st = other if isinstance(other, int) or other is None else other.stream
+        _check(self.L.qmb200_wait_stream(self.h, C.c_void_p(st)))
 
     @property
     def device_bytes(self):
@@ -125,14 +157,19 @@ class MpcContext:
 
     def cycle_dev(self, t0, x0, events, modes, nevents, target_t, target_x, t_out=None, x_out=None, u_out=None,
                   n_out=None, mode_out=None, info=None, status=None):
-        """Same with device-resident torch tensors (raw pointers passed to the C-ABI)."""
-        dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        _check(self.L.qmb200_mpc_cycle_batch_dev(self.h, dp(t0), dp(x0), dp(events), dp(modes), dp(nevents), dp(target_t),
-                                                 dp(target_x), dp(t_out), dp(x_out), dp(u_out), dp(n_out), dp(mode_out),
-                                                 dp(info), dp(status)))
+        """Same with device-resident torch tensors (raw pointers passed to the C-ABI); asynchronous on the context's stream."""
+        B, N, E, K, d = self.B, self.NMAX, self.EMAX, self.KT, self.device
+        f8, i4 = np.float64, np.int32
+        _check(self.L.qmb200_mpc_cycle_batch_dev(
+            self.h, _dev(t0, (B,), f8, "t0", d), _dev(x0, (B, 30), f8, "x0", d), _dev(events, (B, E), f8, "events", d),
+            _dev(modes, (B, E + 1), i4, "modes", d), _dev(nevents, (B,), i4, "nevents", d), _dev(target_t, (B, K), f8, "target_t", d),
+            _dev(target_x, (B, K, 37), f8, "target_x", d), _dev(t_out, (B, N), f8, "t_out", d, True),
+            _dev(x_out, (B, N, 30), f8, "x_out", d, True), _dev(u_out, (B, N, 30), f8, "u_out", d, True),
+            _dev(n_out, (B,), i4, "n_out", d, True), _dev(mode_out, (B, N), i4, "mode_out", d, True),
+            _dev(info, (B, INFO_SIZE), f8, "info", d, True), _dev(status, (B,), i4, "status", d, True)))
 
     def evaluate_policy(self, t):
-        t = np.ascontiguousarray(t, dtype=np.float64)
+        t = _host(t, (self.B,), np.float64, "t")
         x = np.zeros((self.B, 30))
         u = np.zeros((self.B, 30))
         mode = np.zeros(self.B, dtype=np.int32)
@@ -146,8 +183,8 @@ class MpcContext:
         return K
 
     def evaluate_feedback_policy(self, t, x):
-        t = np.ascontiguousarray(t, dtype=np.float64)
-        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = _host(t, (self.B,), np.float64, "t")
+        x = _host(x, (self.B, 30), np.float64, "x")
         u = np.zeros((self.B, 30))
         mode = np.zeros(self.B, dtype=np.int32)
         _check(self.L.qmb200_evaluate_feedback_policy_batch(self.h, _p(t), _p(x), _p(u), _p(mode)))
@@ -155,29 +192,33 @@ class MpcContext:
 
     def evaluate_policy_dev(self, t, x_des, u_des, mode):
         """evaluatePolicy with torch CUDA tensors, enqueued on the context's stream."""
-        dp = lambda a: C.c_void_p(a.data_ptr())
-        _check(self.L.qmb200_evaluate_policy_batch_dev(self.h, dp(t), dp(x_des), dp(u_des), dp(mode)))
+        B, d = self.B, self.device
+        _check(self.L.qmb200_evaluate_policy_batch_dev(self.h, _dev(t, (B,), np.float64, "t", d), _dev(x_des, (B, 30), np.float64, "x_des", d),
+                                                       _dev(u_des, (B, 30), np.float64, "u_des", d), _dev(mode, (B,), np.int32, "mode", d)))
 
     def rbd_to_state_dev(self, rbd, x_out, yaw_last=None):
-        dp = lambda a: None if a is None else C.c_void_p(a.data_ptr())
-        _check(self.L.qmb200_rbd_to_state_batch_dev(self.h, int(rbd.shape[0]), dp(rbd), dp(yaw_last), dp(x_out)))
+        n, d = int(rbd.shape[0]), self.device
+        _check(self.L.qmb200_rbd_to_state_batch_dev(self.h, n, _dev(rbd, (n, 55), np.float64, "rbd", d),
+                                                    _dev(yaw_last, (n,), np.float64, "yaw_last", d, True), _dev(x_out, (n, 30), np.float64, "x_out", d)))
 
     def rbd_to_state(self, rbd, yaw_last=None):
         """Measured rbdState [n][55] -> MPC state [n][30] (QMController.cpp:239-244); yaw_last enables the yaw unwrapping."""
-        rbd = np.ascontiguousarray(rbd, dtype=np.float64)
-        n = rbd.shape[0]
+        n = int(np.shape(rbd)[0])
+        rbd = _host(rbd, (n, 55), np.float64, "rbd")
         x = np.zeros((n, 30))
-        yl = None if yaw_last is None else np.ascontiguousarray(yaw_last, dtype=np.float64)
+        yl = None if yaw_last is None else _host(yaw_last, (n,), np.float64, "yaw_last")
         _check(self.L.qmb200_rbd_to_state_batch(self.h, n, _p(rbd), _p(yl), _p(x)))
         return x
 
     def targets(self, desc, kind, cmd, obs_time, obs_state, ee_state, last_ee_target):
         """Command -> (target_t [n][2], target_x [n][2][37]) (QmTargetTrajectoriesPublisher_node.cpp:60-257); last_ee_target
         [n][7] is updated in place. kind: 0 base cmd_vel, 1 ee cmd_vel, 2 ee goal; cmd [n][7]."""
-        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        cmd, obs_time, obs_state, ee_state = f(cmd), f(obs_time), f(obs_state), f(ee_state)
-        assert last_ee_target.dtype == np.float64 and last_ee_target.flags.c_contiguous
-        n = cmd.shape[0]
+        n = int(np.shape(cmd)[0])
+        cmd, obs_time = _host(cmd, (n, 7), np.float64, "cmd"), _host(obs_time, (n,), np.float64, "obs_time")
+        obs_state, ee_state = _host(obs_state, (n, 30), np.float64, "obs_state"), _host(ee_state, (n, 7), np.float64, "ee_state")
+        if not (isinstance(last_ee_target, np.ndarray) and last_ee_target.dtype == np.float64 and last_ee_target.flags.c_contiguous
+                and last_ee_target.shape == (n, 7)):
+            raise ValueError("last_ee_target must be a contiguous float64 array of shape (n, 7): it is updated in place")
         tt, tx = np.zeros((n, 2)), np.zeros((n, 2, 37))
         _check(self.L.qmb200_targets_batch(self.h, C.byref(desc), int(kind), n, _p(cmd), _p(obs_time), _p(obs_state), _p(ee_state),
                                            _p(last_ee_target), _p(tt), _p(tx)))
@@ -273,6 +314,7 @@ class WbcContext:
         self.L = lib()
         self.L.qmb200_wbc_stream.restype = C.c_void_p
         self.B = batch
+        self.device = device
         h = C.c_void_p()
         _check(self.L.qmb200_wbc_create(C.byref(model), C.byref(wbc), batch, device, C.byref(h)))
         self.h = h
@@ -310,23 +352,38 @@ class WbcContext:
         return cmd, status
 
     def update_dev(self, x_des, u_des, rbd, mode, period, time, cmd, status):
-        dp = lambda t: C.c_void_p(t.data_ptr())
-        _check(self.L.qmb200_wbc_batch_dev(self.h, dp(x_des), dp(u_des), dp(rbd), dp(mode), dp(period), dp(time), dp(cmd), dp(status)))
+        """Device tensors, enqueued on this context's stream. Inputs produced on another stream (e.g. the MPC context's policy
+        evaluation) must be ordered first: call wait_for(mpc_ctx) (or synchronise) before this."""
+        B, d, f8 = self.B, self.device, np.float64
+        _check(self.L.qmb200_wbc_batch_dev(self.h, _dev(x_des, (B, 30), f8, "x_des", d), _dev(u_des, (B, 30), f8, "u_des", d),
+                                           _dev(rbd, (B, 55), f8, "rbd", d), _dev(mode, (B,), np.int32, "mode", d),
+                                           _dev(period, (B,), f8, "period", d), _dev(time, (B,), f8, "time", d),
+                                           _dev(cmd, (B, 54), f8, "cmd", d), _dev(status, (B,), np.int32, "status", d)))
+
+    def wait_for(self, other):
+        """Order this context's stream behind everything enqueued so far on `other`'s stream (an MpcContext, a WbcContext or a
+        raw cudaStream_t value): the device-side MPC -> policy -> WBC chain needs no host synchronisation."""
+        st = other if isinstance(other, int) or other is None else other.stream
+        _check(self.L.qmb200_wbc_wait_stream(self.h, C.c_void_p(st)))
 
     def actuator(self, desc, time_ns, period_ns, obs_time, x_des, u_des, cmd, q, v):
         """One tick of the control law + delayed actuator (QMController.cpp:178-191, QMHWSim.cpp:98-114) -> (tau [B][18], status)."""
-        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        time_ns = np.ascontiguousarray(time_ns, dtype=np.int64)
-        obs_time, x_des, u_des, cmd, q, v = f(obs_time), f(x_des), f(u_des), f(cmd), f(q), f(v)
+        B, f8 = self.B, np.float64
+        time_ns = _host(time_ns, (B,), np.int64, "time_ns")
+        obs_time, x_des, u_des = _host(obs_time, (B,), f8, "obs_time"), _host(x_des, (B, 30), f8, "x_des"), _host(u_des, (B, 30), f8, "u_des")
+        cmd, q, v = _host(cmd, (B, 54), f8, "cmd"), _host(q, (B, 18), f8, "q"), _host(v, (B, 18), f8, "v")
         tau, status = np.zeros((self.B, 18)), np.zeros(self.B, dtype=np.int32)
         _check(self.L.qmb200_actuator_batch(self.h, C.byref(desc), _p(time_ns), C.c_int64(int(period_ns)), _p(obs_time), _p(x_des),
                                             _p(u_des), _p(cmd), _p(q), _p(v), _p(tau), _p(status)))
         return tau, status
 
     def actuator_dev(self, desc, time_ns, period_ns, obs_time, x_des, u_des, cmd, q, v, tau, status):
-        dp = lambda t: C.c_void_p(t.data_ptr())
-        _check(self.L.qmb200_actuator_batch_dev(self.h, C.byref(desc), dp(time_ns), C.c_int64(int(period_ns)), dp(obs_time), dp(x_des),
-                                                dp(u_des), dp(cmd), dp(q), dp(v), dp(tau), dp(status)))
+        B, d, f8 = self.B, self.device, np.float64
+        _check(self.L.qmb200_actuator_batch_dev(self.h, C.byref(desc), _dev(time_ns, (B,), np.int64, "time_ns", d), C.c_int64(int(period_ns)),
+                                                _dev(obs_time, (B,), f8, "obs_time", d), _dev(x_des, (B, 30), f8, "x_des", d),
+                                                _dev(u_des, (B, 30), f8, "u_des", d), _dev(cmd, (B, 54), f8, "cmd", d),
+                                                _dev(q, (B, 18), f8, "q", d), _dev(v, (B, 18), f8, "v", d),
+                                                _dev(tau, (B, 18), f8, "tau", d), _dev(status, (B,), np.int32, "status", d)))
 
     def actuator_reset(self):
         _check(self.L.qmb200_actuator_reset(self.h))

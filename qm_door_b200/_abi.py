@@ -62,7 +62,8 @@ class SolverDesc(C.Structure):
         ("armijo_factor", C.c_double),
         ("weak_eps", C.c_double), ("dt_min", C.c_double),
         ("max_nodes", C.c_int32), ("max_events", C.c_int32), ("max_targets", C.c_int32),
-        ("reserved", C.c_int32),
+        ("sqp_iterations", C.c_int32),
+        ("cost_tol", C.c_double),
     ]
 
 

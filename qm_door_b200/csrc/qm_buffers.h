@@ -19,8 +19,12 @@ enum {
   LS_NEW_MERIT = 8, LS_NEW_DYN = 9, LS_NEW_EQ = 10,
   LS_ITERS = 11,
   LS_DX0SQ = 12,     // |x0 - xs[0]|^2
+  LS_SQP_ITERS = 13, // SQP iterations carried out in this cycle
+  LS_CONV = 14,      // why the SQP loop stopped (CV_*)
   LS_SIZE = 16
 };
+// [upstream] SqpSolver::Convergence
+enum { CV_NONE = 0, CV_ITERATIONS = 1, CV_STEPSIZE = 2, CV_METRICS = 3, CV_PRIMAL = 4 };
 
 struct MpcBuffers {
   int B, NMAX, EMAX, KT;
@@ -42,6 +46,7 @@ struct MpcBuffers {
   int32_t* node_mode;  // [B][NMAX]
   int32_t* nn;         // [B] number of nodes
   int32_t* status;     // [B]
+  int32_t* conv;       // [B] CV_NONE while the problem is still iterating in this cycle, else why it stopped
   // iterate and step
   double* xs;          // [B][NMAX][30]
   double* us;          // [B][NMAX][30]
@@ -80,6 +85,7 @@ inline void for_each_buffer(MpcBuffers& m, F f) {
   f((void**)&m.node_mode, B * N * sizeof(int32_t));
   f((void**)&m.nn, B * sizeof(int32_t));
   f((void**)&m.status, B * sizeof(int32_t));
+  f((void**)&m.conv, B * sizeof(int32_t));
   f((void**)&m.xs, B * N * 30 * sizeof(double));
   f((void**)&m.us, B * N * 30 * sizeof(double));
   f((void**)&m.dxs, B * N * 30 * sizeof(double));
@@ -192,6 +198,7 @@ QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, 
     ls[LS_ALPHA] = 1.0; ls[LS_DONE] = 0.0; ls[LS_ARMIJO] = arm; ls[LS_DXNORM] = sqrt(sx); ls[LS_DUNORM] = sqrt(su);
     ls[LS_BASE_MERIT] = c; ls[LS_BASE_DYN] = dy; ls[LS_BASE_EQ] = eq; ls[LS_ITERS] = 0.0; ls[LS_DX0SQ] = d0;
     ls[LS_NEW_MERIT] = c; ls[LS_NEW_DYN] = dy; ls[LS_NEW_EQ] = eq;
+    ls[LS_SQP_ITERS] += 1.0;                           // zeroed with the schedule at the start of the cycle
   }
   g.sync();
 }
@@ -223,10 +230,33 @@ QM_HDN void decide_problem(const qmb200_solver_desc& S, const MpcBuffers& m, int
   ls[LS_ALPHA] = a2;
 }
 
-// Accept the step and publish the primal solution ([upstream] toPrimalSolution); one thread per (problem, component c<60).
-QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out, double* x_out, double* u_out) {
+// [upstream] SqpSolver::checkConvergence after iteration `it` (0-based) of `iterations`; ls: the problem's line-search record.
+QM_HD int check_convergence(const qmb200_solver_desc& S, const double* ls, int it, int iterations) {
+  if (it + 1 >= iterations) return CV_ITERATIONS;
+  const double alpha = ls[LS_ALPHA];
+  if (alpha < S.alpha_min) return CV_STEPSIZE;
+  if (fabs(ls[LS_NEW_MERIT] - ls[LS_BASE_MERIT]) < S.cost_tol && sqrt(ls[LS_NEW_DYN] + ls[LS_NEW_EQ]) < S.g_min) return CV_METRICS;
+  if (alpha * ls[LS_DXNORM] < S.delta_tol && alpha * ls[LS_DUNORM] < S.delta_tol) return CV_PRIMAL;
+  return CV_NONE;
+}
+
+// Intermediate SQP iteration (sqpIteration > 1): take the accepted step in place, x += alpha dx, u += alpha du; one thread per
+// (problem, component c < 60). The convergence test of the iteration is the caller's (one thread, after all components).
+QM_HDN void step_component(const MpcBuffers& m, int b, int c) {
   const int NMAX = m.NMAX, nn = m.nn[b];
   const double alpha = m.ls[(size_t)b * LS_SIZE + LS_ALPHA];
+  const size_t o = (size_t)b * NMAX;
+  double* v = (c < 30) ? m.xs : m.us;
+  const double* d = (c < 30) ? m.dxs : m.dus;
+  const int cc = (c < 30) ? c : c - 30;
+  for (int k = 0; k < nn; ++k) v[(o + k) * 30 + cc] += alpha * d[(o + k) * 30 + cc];
+}
+
+// Accept the step and publish the primal solution ([upstream] toPrimalSolution); one thread per (problem, component c<60).
+// A problem whose SQP loop stopped in an earlier iteration has its step applied already (alpha_in = 0 is passed then).
+QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out, double* x_out, double* u_out) {
+  const int NMAX = m.NMAX, nn = m.nn[b];
+  const double alpha = (m.conv[b] == CV_NONE) ? m.ls[(size_t)b * LS_SIZE + LS_ALPHA] : 0.0;
   const size_t o = (size_t)b * NMAX;
   constexpr int NB = 8;                      // nodes per batch: the loads of a batch are issued before its stores
   if (c < 30) {

@@ -505,6 +505,8 @@ int qmb200_load_problem(const char* task_info, const char* reference_info, const
     S->g_min = t.num("sqp.g_min");
     S->alpha_decay = 0.5; S->alpha_min = 1e-4; S->gamma_c = 1e-6; S->armijo_factor = 1e-4;   // [upstream] sqp::Settings defaults
     S->weak_eps = 1e-6; S->dt_min = 1e-8;
+    S->sqp_iterations = (int)std::lround(t.num("sqp.sqpIteration"));   // task.info:80
+    S->cost_tol = 1e-4;                                                  // [upstream] sqp::Settings::costTol
     S->max_nodes = (int)std::lround(S->horizon / S->dt) + 1 + 24;
     S->max_events = 32;
     S->max_targets = 2;

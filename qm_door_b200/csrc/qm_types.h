@@ -69,7 +69,8 @@ typedef struct qmb200_solver_desc {
   int32_t max_nodes;    // capacity of the node axis (>= horizon/dt + 1 + 2*events in horizon)
   int32_t max_events;   // capacity of a problem's mode schedule
   int32_t max_targets;  // capacity of target knots
-  int32_t reserved;
+  int32_t sqp_iterations;  // sqp.sqpIteration (task.info:80); values < 1 mean 1
+  double cost_tol;      // [upstream] sqp::Settings::costTol (1e-4): merit change below which a feasible iterate counts as converged
 } qmb200_solver_desc;
 
 // Command -> reference conversion constants. Replaces the file-scope globals of

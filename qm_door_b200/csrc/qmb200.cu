@@ -33,9 +33,9 @@ static int fail(const std::string& msg) { qmb200_set_error_(msg.c_str()); return
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
-enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY, KN_PROJ };
-static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_kin1",   "k_kin2",     "k_lq",    "k_solve",
-                                                       "k_trial",    "k_decide",     "k_finalize", "k_policy", "k_proj"};
+enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY, KN_PROJ, KN_BACKTRACK, KN_STEP };
+static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_kin1",   "k_kin2",   "k_lq",   "k_solve",     "k_trial",
+                                                       "k_decide",   "k_finalize",   "k_policy", "k_proj",   "k_backtrack", "k_step"};
 
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_sol
   const size_t o = (size_t)b * m.NMAX;
   const double* ev = m.events + (size_t)b * m.EMAX;
   const int32_t* md = m.modes + (size_t)b * (m.EMAX + 1);
-  if ((threadIdx.x & 31) == 0) build_grid(*S, m.t0[b], ev, m.nevents[b], m.node_t + o, m.node_flag + o, m.nn + b, m.status + b);
+  if ((threadIdx.x & 31) == 0) {
+    build_grid(*S, m.t0[b], ev, m.nevents[b], m.node_t + o, m.node_flag + o, m.nn + b, m.status + b);
+    m.conv[b] = CV_NONE; m.ls[(size_t)b * LS_SIZE + LS_SQP_ITERS] = 0.0; m.ls[(size_t)b * LS_SIZE + LS_CONV] = 0.0;
+  }
   __syncwarp();
   annotate_schedule(WarpGroup(), *S, *P, ev, md, m.nevents[b], m.nn[b], m.node_t + o, m.node_flag + o, m.node_ts + o,
                     m.node_dt + o, m.node_mode + o, m.node_zvel + o * 4, m.status + b);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb2
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * kKinWarps + warp, b = m.b0 + blockIdx.y;
   const int n = m.nn[b] - 1;
-  if (k >= n) return;                                   // terminal node and padding: nothing to evaluate
+  if (k >= n || m.conv[b] != CV_NONE) return;           // terminal node and padding: nothing to evaluate; SQP loop of b stopped
   const size_t o = (size_t)b * m.NMAX + k;
   if (m.node_flag[o] == EV_PRE) return;                 // event node: identity jump map
   extern __shared__ double smem[];
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(32 * kKinWarps) k_kin(MpcBuffers m, const qmb2
 constexpr int kProjWarps = 4;
 __global__ void __launch_bounds__(32 * kProjWarps) k_proj(MpcBuffers m) {
   const int k = blockIdx.x * kProjWarps + (threadIdx.x >> 5), b = m.b0 + blockIdx.y;
-  if (k >= m.nn[b] - 1) return;
+  if (k >= m.nn[b] - 1 || m.conv[b] != CV_NONE) return;
   const size_t o = (size_t)b * m.NMAX + k;
   if (m.node_flag[o] == EV_PRE) return;
   double* base = m.kin + o * KS_SIZE;
@@ -130,7 +133,7 @@ constexpr size_t kLqSmemBytes = kLqSmemDoubles * sizeof(double) + TI_SIZE * size
 __global__ void __launch_bounds__(QM_LQ_THREADS, 4) k_lq(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
   const int k = blockIdx.x, b = m.b0 + blockIdx.y;
   const int nn = m.nn[b];
-  if (k >= nn) return;
+  if (k >= nn || m.conv[b] != CV_NONE) return;
   extern __shared__ __align__(16) double smem[];
   double* W = smem;
   double* xin = smem + TW_LQ_SIZE;              // x[30], u[30], xn[30]
@@ -254,6 +257,7 @@ constexpr size_t kSolveSmemBytes = (size_t)(SB_SIZE + RW_SIZE + 4) * sizeof(doub
 #define QM_SOLVE_THREADS 128
 #endif
 __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
+  if (m.conv[m.b0 + blockIdx.x] != CV_NONE) return;
   extern __shared__ __align__(16) double smem[];
   TmaFetch fetch;
   fetch.init(smem, smem, (uint64_t*)(smem + SB_SIZE + RW_SIZE));
@@ -267,20 +271,9 @@ constexpr int kTrialThreads = 128;
 #ifndef QM_TRIAL_MINBLOCKS
 #define QM_TRIAL_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(kTrialThreads, QM_TRIAL_MINBLOCKS) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
-                                                          const int* list, int nprob) {
-  // first trial: every problem of the chunk; backtracking trials: only the problems k_decide listed as still pending
-  // (problem, node) pairs are laid over the threads back to back: a block per problem would leave its last warp with a
-  // handful of nodes (105 nodes on 128 threads)
-  const int gid = blockIdx.x * kTrialThreads + threadIdx.x;
-  const int pi = gid / m.NMAX, k = gid - pi * m.NMAX;
-  if (pi >= nprob) return;
-  const int b = list ? list[m.b0 + pi] : m.b0 + pi;
-  const double* ls = m.ls + (size_t)b * LS_SIZE;
-  if (ls[LS_DONE] != 0.0) return;
-  const int nn = m.nn[b];
-  if (k >= nn) return;
-  const double alpha = ls[LS_ALPHA];
+// performance record (cost, dynamics defect, equality-constraint SSE) of node k of problem b at the trial step alpha
+__device__ __forceinline__ void trial_node(const MpcBuffers& m, const qmb200_model_desc& M, const qmb200_problem_desc& P, int b, int k,
+                                           int nn, double alpha, double* out) {
   const size_t o = (size_t)b * m.NMAX + k;
   const int n = nn - 1;
   double x[30], u[30], xn[30];
@@ -293,21 +286,34 @@ __global__ void __launch_bounds__(kTrialThreads, QM_TRIAL_MINBLOCKS) k_trial(Mpc
   const double* tt = m.target_t + (size_t)b * m.KT;
   const double* ts = m.target_x + (size_t)b * m.KT * QM_NTARGET;
   if (k == n) {
-    perf_terminal_serial(*M, *P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, x, pf);
+    perf_terminal_serial(M, P, m.node_t[o], m.node_mode[o], tt, ts, m.KT, x, pf);
   } else if (m.node_flag[o] == EV_PRE) {
     double d = 0.0;
     for (int i = 0; i < 30; ++i) d += (x[i] - xn[i]) * (x[i] - xn[i]);
     pf[PF_COST] = 0.0; pf[PF_DYN] = d; pf[PF_EQ] = 0.0;
   } else {
-    perf_node_serial(*M, *P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, x, u, xn, pf);
+    perf_node_serial(M, P, m.node_ts[o], m.node_dt[o], m.node_mode[o], m.node_zvel + o * 4, tt, ts, m.KT, x, u, xn, pf);
   }
-  double* out = m.perf_trial + o * PF_SIZE;
   out[PF_COST] = pf[PF_COST]; out[PF_DYN] = pf[PF_DYN]; out[PF_EQ] = pf[PF_EQ];
+}
+
+// first trial (alpha = 1) of every problem: (problem, node) pairs are laid over the threads back to back: a block per
+// problem would leave its last warp with a handful of nodes (105 nodes on 128 threads)
+__global__ void __launch_bounds__(kTrialThreads, QM_TRIAL_MINBLOCKS) k_trial(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P) {
+  const int gid = blockIdx.x * kTrialThreads + threadIdx.x;
+  const int pi = gid / m.NMAX, k = gid - pi * m.NMAX;
+  if (pi >= m.nb) return;
+  const int b = m.b0 + pi;
+  const double* ls = m.ls + (size_t)b * LS_SIZE;
+  if (ls[LS_DONE] != 0.0) return;                 // also skips the problems whose SQP loop stopped in an earlier iteration
+  const int nn = m.nn[b];
+  if (k >= nn) return;
+  trial_node(m, *M, *P, b, k, nn, ls[LS_ALPHA], m.perf_trial + ((size_t)b * m.NMAX + k) * PF_SIZE);
 }
 
 // warp per problem: the lanes stage the trial performance records of the nodes (coalesced), lane 0 decides (sequential sums)
 constexpr int kDecideWarps = 4;
-__global__ void __launch_bounds__(32 * kDecideWarps) k_decide(MpcBuffers m, const qmb200_solver_desc* S, int* pending, int* list) {
+__global__ void __launch_bounds__(32 * kDecideWarps) k_decide(MpcBuffers m, const qmb200_solver_desc* S) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = m.b0 + blockIdx.x * kDecideWarps + warp;
@@ -320,13 +326,52 @@ __global__ void __launch_bounds__(32 * kDecideWarps) k_decide(MpcBuffers m, cons
   __syncwarp();
   if (lane != 0) return;
   decide_problem(*S, m, b, pf);
-  if (m.ls[(size_t)b * LS_SIZE + LS_DONE] == 0.0) list[m.b0 + atomicAdd(pending, 1)] = b;   // order only affects scheduling
+}
+
+// Backtracking trials ([upstream] FilterLinesearch loop), entirely on the device: a CTA per problem whose full step was not
+// accepted (a few percent of a batch) repeats {trial of every node at the reduced alpha, decision} until the step is accepted or
+// alpha falls below alpha_min (decide_problem marks the step rejected then). Same per-node evaluation and the same sequential
+// sums as k_trial / k_decide, so the result does not depend on which kernel took a trial. The host is not involved: the cycle
+// is one asynchronous sequence of launches.
+__global__ void __launch_bounds__(kTrialThreads, QM_TRIAL_MINBLOCKS) k_backtrack(MpcBuffers m, const qmb200_model_desc* M, const qmb200_problem_desc* P,
+                                                                                   const qmb200_solver_desc* S) {
+  const int b = m.b0 + blockIdx.x;
+  volatile double* ls = m.ls + (size_t)b * LS_SIZE;
+  if (ls[LS_DONE] != 0.0) return;                 // uniform over the CTA
+  extern __shared__ __align__(16) double smem[];  // [NMAX][PF_SIZE] trial records of this problem
+  const int nn = m.nn[b];
+  for (int round = 0; round < 128; ++round) {     // alpha_decay < 1 is checked at creation: decide_problem ends the loop
+    const double alpha = ls[LS_ALPHA];
+    for (int k = threadIdx.x; k < nn; k += kTrialThreads) trial_node(m, *M, *P, b, k, nn, alpha, smem + (size_t)k * PF_SIZE);
+    __syncthreads();
+    if (threadIdx.x == 0) { decide_problem(*S, m, b, smem); __threadfence_block(); }
+    __syncthreads();
+    if (ls[LS_DONE] != 0.0) return;
+  }
+  if (threadIdx.x == 0) {                         // not reached with valid settings: no step is taken
+    ls[LS_DONE] = 2.0; ls[LS_ALPHA] = 0.0; atomicOr(m.status + b, ST_STEP_REJECTED);
+  }
+}
+
+// intermediate SQP iteration: take the accepted step in place, then the convergence test of the iteration
+__global__ void __launch_bounds__(64) k_step(MpcBuffers m, const qmb200_solver_desc* S, int it, int iterations) {
+  const int b = m.b0 + blockIdx.x, lane = threadIdx.x & 31, c = (threadIdx.x >> 5) * 30 + lane;
+  if (m.conv[b] != CV_NONE) return;
+  if (lane < 30) step_component(m, b, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int cv = check_convergence(*S, m.ls + (size_t)b * LS_SIZE, it, iterations);
+    m.conv[b] = cv; m.ls[(size_t)b * LS_SIZE + LS_CONV] = (double)cv;
+  }
 }
 
 __global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out) {
   const int b = m.b0 + blockIdx.x, lane = threadIdx.x & 31, c = (threadIdx.x >> 5) * 30 + lane;   // warp 0: states, warp 1: inputs
-  if (lane >= 30) return;
-  finalize_component(m, b, c, t_out, x_out, u_out);
+  if (lane < 30) finalize_component(m, b, c, t_out, x_out, u_out);
+  if (threadIdx.x == 31) {            // an idle lane records why the SQP loop stopped (the last iteration ends with ITERATIONS)
+    double* ls = m.ls + (size_t)b * LS_SIZE;
+    if (m.conv[b] == CV_NONE) ls[LS_CONV] = (double)CV_ITERATIONS;
+  }
 }
 
 // [upstream] MPC_MRT_Interface::evaluatePolicy with a FeedforwardController: linear interpolation of (x*, u*) at t.
@@ -415,10 +460,7 @@ struct qmb200_ctx {
   qmb200_problem_desc* dP = nullptr;
   qmb200_solver_desc* dS = nullptr;
   MpcBuffers m;          // ctx-owned device buffers
-  int* d_pending = nullptr;   // [kMaxChunks]
-  int* d_list = nullptr;      // [B] problems still backtracking, compacted per chunk
   double* fb_gains = nullptr; // [B][NMAX][900] feedback gains of the last cycle, allocated on first use
-  int* h_pending = nullptr;   // pinned, [kMaxChunks]
   cudaStream_t stream = nullptr;
   // The cycle can be pipelined over chunks of problems, one stream per chunk, so that the (latency-bound, few CTAs) Riccati
   // sweeps of one chunk run beside the transcription kernels of the next ones (QMB200_CHUNKS; see qmb200_create).
@@ -463,9 +505,13 @@ static void harvest_events(qmb200_ctx* c) {
   c->pending_events.clear();
 }
 
+// One MPC cycle = one asynchronous sequence of launches (no host synchronisation anywhere: the backtracking trials of the filter
+// line search run in k_backtrack, the SQP loop's early exit is a per-problem flag every kernel tests).
 static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, double* u_out) {
   const int B = m.B, NMAX = m.NMAX;
   const int nch = c->nchunks, cb = (B + nch - 1) / nch;
+  const int iterations = c->hS.sqp_iterations < 1 ? 1 : c->hS.sqp_iterations;
+  const size_t pf_bytes = (size_t)NMAX * PF_SIZE * sizeof(double);
   // inputs were enqueued on the main stream: every chunk stream starts behind them
   CUDA_OK(cudaEventRecord(c->ev_start, c->stream));
   for (int ch = 0; ch < nch; ++ch) {
@@ -477,39 +523,22 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
     CUDA_OK(cudaStreamWaitEvent(st, c->ev_start, 0));
     { KernelTimer kt(c, KN_SCHEDULE, st); k_schedule<<<(nb + 3) / 4, 128, 0, st>>>(m, c->dS, c->dP); }
     { KernelTimer kt(c, KN_INIT, st); k_init_guess<<<nb, 64, (size_t)NMAX * 60, st>>>(m, c->dM, c->dP, c->dS); }
-    { KernelTimer kt(c, KN_KIN1, st); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
-    // the projection pivots only need the constraint rows of k_kin<1>: they run beside k_kin<2> (FP64-issue bound warps next to
-    // latency-bound ones) and join before k_lq
-    CUDA_OK(cudaEventRecord(c->ev_fork[ch], st));
-    CUDA_OK(cudaStreamWaitEvent(c->side[ch], c->ev_fork[ch], 0));
-    { KernelTimer kt(c, KN_PROJ, c->side[ch]); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, nb), 32 * kProjWarps, 0, c->side[ch]>>>(m); }
-    CUDA_OK(cudaEventRecord(c->ev_join[ch], c->side[ch]));
-    { KernelTimer kt(c, KN_KIN2, st); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
-    CUDA_OK(cudaStreamWaitEvent(st, c->ev_join[ch], 0));
-    { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
-    { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
-    CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
-    { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(nb * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP, nullptr, nb); }
-    { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + kDecideWarps - 1) / kDecideWarps, 32 * kDecideWarps, (size_t)kDecideWarps * NMAX * PF_SIZE * sizeof(double), st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
-    CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
-  }
-  CUDA_OK(cudaGetLastError());
-  // filter line search: further (backtracking) trials of a chunk while any of its problems is still pending
-  const int max_iters = 24;
-  for (int ch = 0; ch < nch; ++ch) {
-    cudaStream_t st = c->cs[ch];
-    m.b0 = ch * cb;
-    m.nb = (m.b0 + cb <= B) ? cb : B - m.b0;
-    if (m.nb <= 0) continue;
-    const int nb = m.nb;
-    for (int it = 1; it < max_iters; ++it) {
-      CUDA_OK(cudaStreamSynchronize(st));
-      const int npend = c->h_pending[ch];
-      if (npend == 0) break;
-      CUDA_OK(cudaMemsetAsync(c->d_pending + ch, 0, sizeof(int), st));
-      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(npend * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP, c->d_list, npend); }
-      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + kDecideWarps - 1) / kDecideWarps, 32 * kDecideWarps, (size_t)kDecideWarps * NMAX * PF_SIZE * sizeof(double), st>>>(m, c->dS, c->d_pending + ch, c->d_list); }
-      CUDA_OK(cudaMemcpyAsync(c->h_pending + ch, c->d_pending + ch, sizeof(int), cudaMemcpyDeviceToHost, st));
+    for (int it = 0; it < iterations; ++it) {
+      { KernelTimer kt(c, KN_KIN1, st); k_kin<1><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+      // the projection pivots only need the constraint rows of k_kin<1>: they run beside k_kin<2> (FP64-issue bound warps next to
+      // latency-bound ones) and join before k_lq
+      CUDA_OK(cudaEventRecord(c->ev_fork[ch], st));
+      CUDA_OK(cudaStreamWaitEvent(c->side[ch], c->ev_fork[ch], 0));
+      { KernelTimer kt(c, KN_PROJ, c->side[ch]); k_proj<<<dim3((NMAX + kProjWarps - 1) / kProjWarps, nb), 32 * kProjWarps, 0, c->side[ch]>>>(m); }
+      CUDA_OK(cudaEventRecord(c->ev_join[ch], c->side[ch]));
+      { KernelTimer kt(c, KN_KIN2, st); k_kin<2><<<dim3((NMAX + kKinWarps - 1) / kKinWarps, nb), 32 * kKinWarps, kKinSmemBytes, st>>>(m, c->dM, c->dP); }
+      CUDA_OK(cudaStreamWaitEvent(st, c->ev_join[ch], 0));
+      { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
+      { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
+      { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(nb * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
+      { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + kDecideWarps - 1) / kDecideWarps, 32 * kDecideWarps, kDecideWarps * pf_bytes, st>>>(m, c->dS); }
+      { KernelTimer kt(c, KN_BACKTRACK, st); k_backtrack<<<nb, kTrialThreads, pf_bytes, st>>>(m, c->dM, c->dP, c->dS); }
+      if (it + 1 < iterations) { KernelTimer kt(c, KN_STEP, st); k_step<<<nb, 64, 0, st>>>(m, c->dS, it, iterations); }
     }
     { KernelTimer kt(c, KN_FINALIZE, st); k_finalize<<<nb, 64, 0, st>>>(m, t_out, x_out, u_out); }
     CUDA_OK(cudaEventRecord(c->ev_done[ch], st));
@@ -530,6 +559,13 @@ int qmb200_device_count(void) {
   return n;
 }
 
+// CUDA_OK for the body of a create function: every failure releases what was built so far
+#define CREATE_OK(call, destroy_call)                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) { destroy_call; return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
+
 int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* problem, const qmb200_solver_desc* solver,
                   int32_t batch, int32_t device, qmb200_ctx** out) {
   if (!model || !problem || !solver || !out) return fail("qmb200_create: null argument");
@@ -537,11 +573,18 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   if (model->nj != QM_NJ) return fail("qmb200_create: model must have 24 one-DoF joints (6 floating base + 18 actuated)");
   if (!value_walk_supported(*model)) return fail("qmb200_create: unsupported tree topology (serial six-joint floating base carrying all limbs expected)");
   if (solver->max_nodes < 3 || solver->max_events < 1 || solver->max_targets < 1) return fail("qmb200_create: bad capacities");
+  if (!(solver->alpha_decay > 0.0 && solver->alpha_decay < 1.0) || !(solver->alpha_min > 0.0))
+    return fail("qmb200_create: line search needs 0 < alpha_decay < 1 and alpha_min > 0");
+  if (!(solver->dt > 0.0) || !(solver->horizon > 0.0)) return fail("qmb200_create: dt and horizon must be positive");
+  // staging buffers that grow with the node capacity (long horizons): k_decide 4 x NMAX records, k_init_guess 60 B per node
+  const size_t dec = (size_t)kDecideWarps * solver->max_nodes * PF_SIZE * sizeof(double), ini = (size_t)solver->max_nodes * 60;
+  if (dec > 200 * 1024 || ini > 200 * 1024) return fail("qmb200_create: max_nodes too large for the staging buffers of k_decide / k_init_guess");
   if (qmb200_device_count() <= 0) return fail("qmb200_create: no CUDA device available (this library has no CPU fallback)");
   CUDA_OK(cudaSetDevice(device));
   qmb200_ctx* c = new qmb200_ctx();
   c->device = device; c->B = batch; c->hM = *model; c->hP = *problem; c->hS = *solver;
-  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+#define C_OK(call) CREATE_OK(call, qmb200_destroy(c))
+  C_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
     // Tuning knob. Measured on B200 (config 2): 1 / 2 / 4 / 8 chunks -> 13.12 / 13.24 / 13.63 / 14.97 ms per step: the kernels
     // do overlap, but the step is bound by instruction issue across the whole GPU, so the default stays at one chunk.
@@ -553,19 +596,19 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
     c->nchunks = nch;
   }
   for (int ch = 0; ch < c->nchunks; ++ch) {
-    CUDA_OK(cudaStreamCreateWithFlags(&c->cs[ch], cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&c->side[ch], cudaStreamNonBlocking));
-    CUDA_OK(cudaEventCreateWithFlags(&c->ev_done[ch], cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork[ch], cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[ch], cudaEventDisableTiming));
+    C_OK(cudaStreamCreateWithFlags(&c->cs[ch], cudaStreamNonBlocking));
+    C_OK(cudaStreamCreateWithFlags(&c->side[ch], cudaStreamNonBlocking));
+    C_OK(cudaEventCreateWithFlags(&c->ev_done[ch], cudaEventDisableTiming));
+    C_OK(cudaEventCreateWithFlags(&c->ev_fork[ch], cudaEventDisableTiming));
+    C_OK(cudaEventCreateWithFlags(&c->ev_join[ch], cudaEventDisableTiming));
   }
-  CUDA_OK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-  CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
-  CUDA_OK(cudaMalloc(&c->dP, sizeof(*problem)));
-  CUDA_OK(cudaMalloc(&c->dS, sizeof(*solver)));
-  CUDA_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(c->dP, problem, sizeof(*problem), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(c->dS, solver, sizeof(*solver), cudaMemcpyHostToDevice));
+  C_OK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  C_OK(cudaMalloc(&c->dM, sizeof(*model)));
+  C_OK(cudaMalloc(&c->dP, sizeof(*problem)));
+  C_OK(cudaMalloc(&c->dS, sizeof(*solver)));
+  C_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
+  C_OK(cudaMemcpy(c->dP, problem, sizeof(*problem), cudaMemcpyHostToDevice));
+  C_OK(cudaMemcpy(c->dS, solver, sizeof(*solver), cudaMemcpyHostToDevice));
   c->m.b0 = 0; c->m.nb = batch;
   c->m.B = batch; c->m.NMAX = solver->max_nodes; c->m.EMAX = solver->max_events; c->m.KT = solver->max_targets;
   cudaError_t err = cudaSuccess;
@@ -573,25 +616,19 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   for_each_buffer(c->m, [&](void** p, size_t bytes) {
     if (err != cudaSuccess) { *p = nullptr; return; }
     err = cudaMalloc(p, bytes);
-    if (err == cudaSuccess) { err = cudaMemset(*p, 0, bytes); total += (int64_t)bytes; }
+    if (err == cudaSuccess) { err = cudaMemset(*p, 0, bytes); total += (int64_t)bytes; } else *p = nullptr;
   });
   if (err != cudaSuccess) { qmb200_destroy(c); return fail(std::string("qmb200_create: device allocation failed: ") + cudaGetErrorString(err)); }
   c->bytes = total;
-  CUDA_OK(cudaMalloc(&c->d_pending, sizeof(int) * qmb200_ctx::kMaxChunks));
-  CUDA_OK(cudaMalloc(&c->d_list, sizeof(int) * (size_t)batch));
-  CUDA_OK(cudaMallocHost(&c->h_pending, sizeof(int) * qmb200_ctx::kMaxChunks));
-  CUDA_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
-  CUDA_OK(cudaFuncSetAttribute(k_rbd_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStateWarps * kStateWarpDoubles * sizeof(double))));
-  CUDA_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
-  {
-    // staging buffers that grow with the node capacity (long horizons): k_decide 4 x NMAX records, k_init_guess 60 B per node
-    const size_t dec = (size_t)kDecideWarps * c->m.NMAX * PF_SIZE * sizeof(double), ini = (size_t)c->m.NMAX * 60;
-    if (dec > 200 * 1024 || ini > 200 * 1024) return fail("qmb200_create: max_nodes too large for the staging buffers of k_decide / k_init_guess");
-    if (dec > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec));
-    if (ini > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(k_init_guess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ini));
-  }
+  C_OK(cudaFuncSetAttribute(k_kin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
+  C_OK(cudaFuncSetAttribute(k_kin<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kKinSmemBytes));
+  C_OK(cudaFuncSetAttribute(k_lq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLqSmemBytes));
+  C_OK(cudaFuncSetAttribute(k_rbd_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStateWarps * kStateWarpDoubles * sizeof(double))));
+  C_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
+  if (dec > 48 * 1024) C_OK(cudaFuncSetAttribute(k_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec));
+  if (dec / kDecideWarps > 48 * 1024) C_OK(cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dec / kDecideWarps)));
+  if (ini > 48 * 1024) C_OK(cudaFuncSetAttribute(k_init_guess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ini));
+#undef C_OK
   *out = c;
   return 0;
 }
@@ -606,10 +643,7 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->dM) cudaFree(c->dM);
   if (c->dP) cudaFree(c->dP);
   if (c->dS) cudaFree(c->dS);
-  if (c->d_pending) cudaFree(c->d_pending);
-  if (c->d_list) cudaFree(c->d_list);
   if (c->fb_gains) cudaFree(c->fb_gains);
-  if (c->h_pending) cudaFreeHost(c->h_pending);
   for (int ch = 0; ch < qmb200_ctx::kMaxChunks; ++ch) {
     if (c->cs[ch]) { cudaStreamSynchronize(c->cs[ch]); cudaStreamDestroy(c->cs[ch]); }
     if (c->side[ch]) { cudaStreamSynchronize(c->side[ch]); cudaStreamDestroy(c->side[ch]); }
@@ -636,6 +670,22 @@ int qmb200_sync(qmb200_ctx* c) {
   CUDA_OK(cudaStreamSynchronize(c->stream));
   harvest_events(c);
   return 0;
+}
+
+static int wait_stream(int device, cudaStream_t self, void* other) {
+  CUDA_OK(cudaSetDevice(device));
+  cudaEvent_t e;
+  CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaError_t err = cudaEventRecord(e, (cudaStream_t)other);
+  if (err == cudaSuccess) err = cudaStreamWaitEvent(self, e, 0);
+  cudaEventDestroy(e);                      // released once the recorded work has completed
+  if (err != cudaSuccess) return fail(std::string("wait_stream: ") + cudaGetErrorString(err));
+  return 0;
+}
+
+int qmb200_wait_stream(qmb200_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  return wait_stream(c->device, c->stream, stream);
 }
 
 #if defined(QM_PHASE_TIMING)
@@ -941,25 +991,27 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   CUDA_OK(cudaSetDevice(device));
   qmb200_wbc_ctx* c = new qmb200_wbc_ctx();
   c->device = device; c->B = batch;
-  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaEventCreate(&c->e0));
-  CUDA_OK(cudaEventCreate(&c->e1));
-  CUDA_OK(cudaMalloc(&c->dM, sizeof(*model)));
-  CUDA_OK(cudaMalloc(&c->dC, sizeof(*wbc)));
-  CUDA_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(c->dC, wbc, sizeof(*wbc), cudaMemcpyHostToDevice));
+#define C_OK(call) CREATE_OK(call, qmb200_wbc_destroy(c))
+  C_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  C_OK(cudaEventCreate(&c->e0));
+  C_OK(cudaEventCreate(&c->e1));
+  C_OK(cudaMalloc(&c->dM, sizeof(*model)));
+  C_OK(cudaMalloc(&c->dC, sizeof(*wbc)));
+  C_OK(cudaMemcpy(c->dM, model, sizeof(*model), cudaMemcpyHostToDevice));
+  C_OK(cudaMemcpy(c->dC, wbc, sizeof(*wbc), cudaMemcpyHostToDevice));
   const size_t B = batch;
-  CUDA_OK(cudaMalloc(&c->xd, B * 30 * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->ud, B * 30 * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->rbd, B * 55 * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->period, B * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->time, B * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->u_last, B * 30 * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->cmd, B * 54 * sizeof(double)));
-  CUDA_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
-  CUDA_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));
-  CUDA_OK(cudaMemset(c->u_last, 0, B * 30 * sizeof(double)));
-  CUDA_OK(cudaFuncSetAttribute(k_wbc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+  C_OK(cudaMalloc(&c->xd, B * 30 * sizeof(double)));
+  C_OK(cudaMalloc(&c->ud, B * 30 * sizeof(double)));
+  C_OK(cudaMalloc(&c->rbd, B * 55 * sizeof(double)));
+  C_OK(cudaMalloc(&c->period, B * sizeof(double)));
+  C_OK(cudaMalloc(&c->time, B * sizeof(double)));
+  C_OK(cudaMalloc(&c->u_last, B * 30 * sizeof(double)));
+  C_OK(cudaMalloc(&c->cmd, B * 54 * sizeof(double)));
+  C_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
+  C_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));
+  C_OK(cudaMemset(c->u_last, 0, B * 30 * sizeof(double)));
+  C_OK(cudaFuncSetAttribute(k_wbc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+#undef C_OK
   *out = c;
   return 0;
 }
@@ -1002,6 +1054,11 @@ int qmb200_wbc_sync(qmb200_wbc_ctx* c) {
 }
 
 void* qmb200_wbc_stream(qmb200_wbc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int qmb200_wbc_wait_stream(qmb200_wbc_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  return wait_stream(c->device, c->stream, stream);
+}
 
 int qmb200_wbc_kernel_time(qmb200_wbc_ctx* c, double* total_ms, int64_t* launches, int32_t reset) {
   if (!c) return fail("null ctx");

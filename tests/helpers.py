@@ -12,7 +12,7 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def solver_for(solver, horizon, dt, max_events=40, max_nodes=None):
+def solver_for(solver, horizon, dt, max_events=40, max_nodes=None, iterations=1):
     import ctypes
     s = type(solver)()
     ctypes.memmove(ctypes.byref(s), ctypes.byref(solver), ctypes.sizeof(s))
@@ -20,6 +20,7 @@ def solver_for(solver, horizon, dt, max_events=40, max_nodes=None):
     s.max_nodes = int(round(horizon / dt)) + 1 + 12 if max_nodes is None else int(max_nodes)
     s.max_events = max_events
     s.max_targets = 2
+    s.sqp_iterations = iterations
     return s
 
 
@@ -38,7 +39,8 @@ def check_against_golden(make_backend, path, tol_x=1e-8, tol_u=1e-8):
     g = np.load(path)
     B = g["x0"].shape[0]
     if "max_nodes" in g.files:      # contract-size cases carry their own capacities (many gait events per horizon)
-        be = make_backend(float(g["horizon"]), float(g["dt"]), B, max_events=int(g["max_events"]), max_nodes=int(g["max_nodes"]))
+        be = make_backend(float(g["horizon"]), float(g["dt"]), B, max_events=int(g["max_events"]), max_nodes=int(g["max_nodes"]),
+                          iterations=int(g["iterations"]) if "iterations" in g.files else 1)
     else:
         be = make_backend(float(g["horizon"]), float(g["dt"]), B)
     cycles = g["t"].shape[0]
@@ -56,6 +58,8 @@ def check_against_golden(make_backend, path, tol_x=1e-8, tol_u=1e-8):
             worst = max(worst, ex, eu)
             assert ex < tol_x and eu < tol_u, (path, c, b, ex, eu)
             assert out["info"][b, 0] == g["alpha"][c, b]
+            if "sqp" in g.files:      # SQP iterations carried out and why the loop stopped
+                assert out["info"][b, 13] == g["sqp"][c, b, 0] and out["info"][b, 14] == g["sqp"][c, b, 1]
             assert np.allclose(out["info"][b, [2, 5, 6, 7, 8, 9, 10]], g["perf"][c, b], rtol=1e-6, atol=1e-12)
     be.close()
     return worst

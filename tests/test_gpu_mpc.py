@@ -254,10 +254,11 @@ def test_device_resident_loop_matches_host_calls(descs):
     xd_d, ud_d = torch.zeros(B, 30, dtype=f64, device=dev), torch.zeros(B, 30, dtype=f64, device=dev)
     md_d = torch.zeros(B, dtype=i32, device=dev)
     cmd_d, st_d = torch.zeros(B, 54, dtype=f64, device=dev), torch.zeros(B, dtype=i32, device=dev)
+    torch.cuda.synchronize()                     # the buffers were filled on torch's stream; the contexts own theirs
     ctx.rbd_to_state_dev(rbd_d, x_d, yaw_d)
     ctx.cycle_dev(T(np.zeros(B)), x_d, T(W.events), T(W.modes), T(W.nevents), T(W.target_t), T(W.target_x))
     ctx.evaluate_policy_dev(T(tq), xd_d, ud_d, md_d)
-    ctx.sync()                                   # the WBC context has its own stream
+    wctx.wait_for(ctx)                           # the WBC context has its own stream: ordered behind the MPC stream on the device
     wctx.update_dev(xd_d, ud_d, rbd_d, md_d, T(np.full(B, 0.002)), T(np.full(B, 11.0)), cmd_d, st_d)
     wctx.sync()
     assert np.array_equal(x_d.cpu().numpy(), x_obs)
@@ -375,3 +376,36 @@ def test_gait_library_batch_against_cpu_port(descs):
     assert 0 in seen_modes and 15 in seen_modes and len(seen_modes) >= 10      # flight, full stance and most contact patterns
     ctx.close()
     cp.close()
+
+
+def test_multi_iteration_sqp_on_device(cuda_factory):
+    """sqpIteration > 1 (task.info:80 runs 1): in-place steps, per-problem convergence flag and early exit, against the oracle's
+    multi-iteration goldens (iterations carried out and the reason the loop stopped are part of the comparison)."""
+    import os
+    from helpers import ROOT
+    for name in ("sqp10_early_exit", "sqp4_trot_n20"):
+        worst = check_against_golden(cuda_factory, os.path.join(ROOT, "tests", "golden", "mpc_cycle_%s.npz" % name))
+        assert worst < EXPECTED_TOL
+
+
+def test_wrappers_reject_wrong_shapes_and_devices(descs):
+    import torch
+    import qm_door_b200 as q
+    model, problem, solver, x_init = descs
+    sd = solver_for(solver, 0.1, 0.01)
+    ctx = q.MpcContext(model, problem, sd, 2)
+    with pytest.raises(ValueError):
+        ctx.evaluate_policy(np.zeros(3))
+    with pytest.raises(ValueError):
+        ctx.evaluate_feedback_policy(np.zeros(2), np.zeros((2, 29)))
+    dev = torch.device("cuda", 0)
+    z = lambda *shp: torch.zeros(*shp, dtype=torch.float64, device=dev)
+    with pytest.raises(ValueError):      # host tensor where a device tensor is required
+        ctx.evaluate_policy_dev(torch.zeros(2, dtype=torch.float64), z(2, 30), z(2, 30), torch.zeros(2, dtype=torch.int32, device=dev))
+    with pytest.raises(ValueError):      # wrong dtype
+        ctx.evaluate_policy_dev(z(2), z(2, 30), z(2, 30), z(2))
+    with pytest.raises(q.Qmb200Error):   # line-search settings are validated at creation
+        bad = solver_for(solver, 0.1, 0.01)
+        bad.alpha_decay = 1.0
+        q.MpcContext(model, problem, bad, 2)
+    ctx.close()

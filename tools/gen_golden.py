@@ -113,25 +113,27 @@ def wbc_golden():
 
 def _solve_problem(args):
     """Worker: all warm-started cycles of one problem with the NumPy oracle."""
-    ev, md, tt, tx, hor, dt, x0, cycles = args
+    ev, md, tt, tx, hor, dt, x0, cycles, iterations = args
     m, P = config.load_default()
     prob = sqp.MpcProblem(m, P, ev, md, tt, tx, horizon=hor, dt=dt)
-    return [sqp.mpc_cycle(prob, 0.01 * c, x0) for c in range(cycles)]
+    return [sqp.mpc_cycle(prob, 0.01 * c, x0, iterations=iterations) for c in range(cycles)]
 
 
-def write_case(name, gait, hor, dt, x0, events, modes, nev, tt, tx, cycles, extra=None):
+def write_case(name, gait, hor, dt, x0, events, modes, nev, tt, tx, cycles, extra=None, iterations=1):
     """Golden file of explicit per-problem inputs (padded C-ABI arrays in, oracle outputs of `cycles` warm-started cycles)."""
     import multiprocessing as mp
     B = x0.shape[0]
-    jobs = [(events[b, :nev[b]].copy(), modes[b, :nev[b] + 1].copy(), tt[b], tx[b], hor, dt, x0[b], cycles) for b in range(B)]
+    jobs = [(events[b, :nev[b]].copy(), modes[b, :nev[b] + 1].copy(), tt[b], tx[b], hor, dt, x0[b], cycles, iterations) for b in range(B)]
     with mp.Pool(min(B, os.cpu_count() or 1)) as pool:
         res = pool.map(_solve_problem, jobs)
     nmax = max(len(r[0]) for per in res for r in per)
     T = np.zeros((cycles, B, nmax)); X = np.zeros((cycles, B, nmax, 30)); U = np.zeros((cycles, B, nmax, 30))
     NN = np.zeros((cycles, B), dtype=np.int32); MD = np.zeros((cycles, B, nmax), dtype=np.int32)
-    AL = np.zeros((cycles, B)); PERF = np.zeros((cycles, B, 7))
+    AL = np.zeros((cycles, B)); PERF = np.zeros((cycles, B, 7)); SQP = np.zeros((cycles, B, 2), dtype=np.int32)
+    reasons = {"ITERATIONS": 1, "STEPSIZE": 2, "METRICS": 3, "PRIMAL": 4}
     for b in range(B):
         for c, (tout, xs, us, info) in enumerate(res[b]):
+            SQP[c, b] = [len(info["history"]), reasons[info["convergence"]]]
             n = len(tout)
             T[c, b, :n], X[c, b, :n], U[c, b, :n], NN[c, b], MD[c, b, :n] = tout, xs, us, n, info["modes"]
             AL[c, b] = info["alpha"]
@@ -145,8 +147,8 @@ def write_case(name, gait, hor, dt, x0, events, modes, nev, tt, tx, cycles, extr
     kw = dict(extra or {})
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mpc_cycle_%s.npz" % name), gait=gait, horizon=hor, dt=dt,
                         x0=x0, events=evp, modes=mdp, nevents=nev, target_t=tt, target_x=tx, t=T, x=X, u=U, n=NN, mode=MD,
-                        alpha=AL, perf=PERF, max_nodes=int(nmax + 4), max_events=EM, **kw)
-    print(name, "nodes", NN.min(), NN.max(), "alpha", np.unique(AL))
+                        alpha=AL, perf=PERF, max_nodes=int(nmax + 4), max_events=EM, iterations=iterations, sqp=SQP, **kw)
+    print(name, "nodes", NN.min(), NN.max(), "alpha", np.unique(AL), "sqp iterations", np.unique(SQP[..., 0]), "reasons", np.unique(SQP[..., 1]))
 
 
 def contract_goldens():
@@ -191,6 +193,27 @@ def contract_goldens():
                extra=dict(gaits=np.array(gaits)))
 
 
+def multi_iteration_golden():
+    """sqpIteration = 10 (the reference runs 1, task.info:80): two stance problems and a trot problem close to the nominal pose, so
+    that the SQP loop stops early for different reasons / after different numbers of iterations per problem; plus a perturbed trot
+    problem that uses the whole budget of 4."""
+    from oracle import abi_fill
+    m, P = config.load_default()
+    tt, ts = scenarios.standing_target(m, P)
+    B = 3
+    x0s, phase = scenarios.perturbed_states(m, P, B, seed=78)
+    x0s = P.x_init + 0.02 * (x0s - P.x_init)
+    scheds = [G.tile_schedule(P.gaits["stance"] if b < 2 else P.gaits["trot"], -1.4 - phase[b], 1.2) for b in range(B)]
+    ev, md, ne = abi_fill.pack_schedules(scheds, 40)
+    write_case("sqp10_early_exit", "stance+trot", 0.1, 0.01, x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)), 2, iterations=10)
+    x0s, phase = scenarios.perturbed_states(m, P, B, seed=77)
+    scheds = [G.tile_schedule(P.gaits["trot"], -1.4 - phase[b], 1.2) for b in range(B)]
+    ev, md, ne = abi_fill.pack_schedules(scheds, 40)
+    write_case("sqp4_trot_n20", "trot", 0.2, 0.01, x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)), 2, iterations=4)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sqp":
+    multi_iteration_golden()
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "contract":
     contract_goldens()
 def _wbc_solve(args):
