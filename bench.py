@@ -280,8 +280,11 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
              u=torch.zeros(B, NMAX, 30, dtype=f64, device=dev), n=torch.zeros(B, dtype=i32, device=dev),
              mode=torch.zeros(B, NMAX, dtype=i32, device=dev), info=torch.zeros(B, q.INFO_SIZE, dtype=f64, device=dev),
              status=torch.zeros(B, dtype=i32, device=dev))
-    policy = torch.zeros(B, NMAX, 61, dtype=f64, device=dev)          # packed (t, x, u) shard for the all-gather
-    gathered = torch.zeros(world, B, NMAX, 61, dtype=f64, device=dev) if world > 1 else None
+    # multi-GPU: the library's own collective (qmb200_allgather_policy: k_finalize writes the packed send buffer, ncclAllGather on
+    # the context's communication stream beside the next cycle); two receive buffers, consumed one cycle later
+    gathered = [torch.zeros(world, B, NMAX, 61, dtype=f64, device=dev) for _ in range(2)] if world > 1 else None
+    if world > 1:
+        D.init_comm(ctx)
     torch.cuda.synchronize()
 
     def step_dev(k):
@@ -290,23 +293,23 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
             ctx.cycle_dev(d["t0"], d["x0"], d["events"], d["modes"], d["nevents"], d["tt"], d["tx"], o["t"], o["x"], o["u"],
                           o["n"], o["mode"], o["info"], o["status"])
             if world > 1:
-                D.pack_policy(o["t"], o["x"], o["u"], out=policy)
-                D.allgather_policy(policy, gathered)
+                ctx.allgather_policy(gathered[k & 1])
 
     def barrier():
+        if world > 1:
+            ctx.comm_sync()                     # the last all-gather belongs to the timed region
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value)
+    # ---- device-resident timing (value): the cycle is replayed as a CUDA graph, no per-kernel events in this region
     k = 0
     for _ in range(args.warmup):
         step_dev(k)
         k += 1
     ctx.sync()
     ctx.kernel_times(reset=True)
-    ctx.set_profiling(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -317,10 +320,29 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
     for _ in range(args.steps):
         step_dev(k)
         k += 1
+    if world > 1:
+        ctx.policy_wait_stream(ctx.stream)      # the last all-gather ends inside the timed region
     with torch.cuda.stream(stream):
         e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
+    kt_timed = ctx.kernel_times(reset=True)                 # launch counts of the timed region (graph replays included)
+    # ---- second pass of the same K steps with per-kernel CUDA events on the launching streams (direct launches: events cannot
+    #      bracket the kernels of a graph replay): the per-kernel durations behind `roofline` and `kernel_ms_per_step`
+    ctx.set_profiling(True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        p0.record(stream)
+    for _ in range(args.steps):
+        step_dev(k)
+        k += 1
+    if world > 1:
+        ctx.policy_wait_stream(ctx.stream)
+    with torch.cuda.stream(stream):
+        p1.record(stream)
+    barrier()
+    prof_ms = p0.elapsed_time(p1)
     clocks = sampler.stop() if rank == 0 else None
     kt = ctx.kernel_times(reset=True)
     ctx.set_profiling(False)
@@ -339,11 +361,14 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
     hout = ctx.alloc_outputs(pinned=True)
     h2d = sum(a.nbytes for a in h.values()) + ht0.nbytes
     d2h = sum(hout[key].nbytes for key in ("t", "x", "u", "n", "mode", "info", "status"))
+    hout2 = ctx.alloc_outputs(pinned=True)
+    houts, ht0s = (hout, hout2), (ht0, pin(np.zeros(B)))
     k = 0
     for _ in range(args.warmup):
         ht0[:] = CYCLE_DT * k
         ctx.cycle(ht0, h["x0"], h["events"], h["modes"], h["nevents"], h["tt"], h["tx"], out=hout)
         k += 1
+    # (a) one blocking call per step (qmb200_mpc_cycle_batch): copy-out fully exposed
     barrier()
     t_start = time.perf_counter()
     for _ in range(args.steps):
@@ -351,8 +376,26 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
         ctx.cycle(ht0, h["x0"], h["events"], h["modes"], h["nevents"], h["tt"], h["tx"], out=hout)
         k += 1
     torch.cuda.synchronize()
+    e2e_serial_s = time.perf_counter() - t_start
+    # (b) submit / wait (qmb200_mpc_cycle_batch_async + _wait), two host buffer sets: the policy of cycle k is copied out and read
+    #     on the host while cycle k + 1 computes (the reference's MPC thread / policy buffer arrangement). Every step's inputs
+    #     come from pinned host memory and every step's result is read on the host inside the timed region.
+    e2e_bad = 0
+    barrier()
+    t_start = time.perf_counter()
+    prev = None
+    for i in range(args.steps):
+        ht0s[i & 1][:] = CYCLE_DT * k
+        tk = ctx.cycle_async(ht0s[i & 1], h["x0"], h["events"], h["modes"], h["nevents"], h["tt"], h["tx"], out=houts[i & 1])
+        k += 1
+        if prev is not None:
+            ctx.wait(prev)
+            e2e_bad += int(((houts[(i - 1) & 1]["status"] & ~32) != 0).sum())
+        prev = tk
+    ctx.wait(prev)
+    e2e_bad += int(((houts[(args.steps - 1) & 1]["status"] & ~32) != 0).sum())
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t_start
-    e2e_bad = int(((hout["status"] & ~32) != 0).sum())
 
     # ---- secondary metric (BASELINE config 5): whole-body-control solves/s, B = 65 536 contact configurations, rank 0 only
     wbc_line = None
@@ -388,10 +431,10 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
         if not args.no_cpu_baseline:
             wbc_line["cpu_baseline"] = wbc_cpu_baseline(WW)
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=f64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, e2e_serial_s * 1e3, prof_ms], dtype=f64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0].item()), float(times[1].item())
+    dev_ms, e2e_ms, e2e_serial_ms, prof_ms = (float(v) for v in times.tolist())
     if rank == 0:
         total = B * world
         value = total * args.steps / (dev_ms * 1e-3)
@@ -434,12 +477,18 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms / args.steps, "failed_problems": e2e_bad},
-            "gpu_launches": int(sum(v[1] for v in kt.values())),
+                    "ms_per_step": e2e_ms / args.steps, "failed_problems": e2e_bad,
+                    "api": "qmb200_mpc_cycle_batch_async + qmb200_mpc_cycle_wait, two pinned host buffer sets: copy-out of cycle k "
+                           "overlaps cycle k + 1; every step's inputs come from the host and every result is read on the host",
+                    "blocking_call": {"value": total * args.steps / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / args.steps,
+                                      "api": "qmb200_mpc_cycle_batch (submit + wait per step, copy-out exposed)"}},
+            "gpu_launches": int(sum(v[1] for v in kt_timed.values())),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": int(nodes_bytes),
-                         "share_of_step": kt[dom][0] / max(1e-9, dev_ms),      # of the device-timed region (k_proj overlaps k_kin2)
+                         "share_of_step": kt[dom][0] / max(1e-9, prof_ms),     # of the profiled pass (k_proj overlaps k_kin2)
+                         "pass": "second pass of the same K steps with per-kernel CUDA events on the launching streams "
+                                 "(%.3f ms/step; the timed region replays the cycle as a CUDA graph, which events cannot bracket)" % (prof_ms / args.steps),
                          "fp64": fp64,
                          "cycle_level": {"algorithmic_bytes_per_step": int(cyc_bytes),
                                          "achieved_gbs": cyc_bytes / (dev_ms / args.steps * 1e-3) / 1e9,

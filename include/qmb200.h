@@ -82,12 +82,44 @@ int qmb200_wait_stream(qmb200_ctx* ctx, void* stream);
 int qmb200_mpc_cycle_batch(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events, const int32_t* modes,
                            const int32_t* nevents, const double* target_t, const double* target_x, double* t_out,
                            double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status);
+/* The same cycle as a submit / wait pair (host buffers, which must be page-locked for the copies to be asynchronous and must stay
+ * untouched until the wait returns): the call enqueues the input copies, the cycle and -- on a separate copy stream -- the
+ * output copies, and returns a ticket; qmb200_mpc_cycle_wait(ticket) blocks until that cycle's outputs are on the host. Up to
+ * two submissions may be outstanding, so the copy-out of cycle k overlaps the computation of cycle k + 1 (the reference runs
+ * its solver in a separate MPC thread for the same reason, QMController.cpp:316-333). qmb200_mpc_cycle_batch = submit + wait. */
+int qmb200_mpc_cycle_batch_async(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                                 const int32_t* nevents, const double* target_t, const double* target_x, double* t_out,
+                                 double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status,
+                                 int64_t* ticket);
+int qmb200_mpc_cycle_wait(qmb200_ctx* ctx, int64_t ticket);
 /* Same with DEVICE buffers; fully asynchronous on the context's stream (the filter line search and the SQP loop's early exit
  * run on the device: no host synchronisation inside the cycle). solver.sqp_iterations > 1 runs the multi-iteration SQP. */
 int qmb200_mpc_cycle_batch_dev(qmb200_ctx* ctx, const double* t0, const double* x0, const double* events,
                                const int32_t* modes, const int32_t* nevents, const double* target_t, const double* target_x,
                                double* t_out, double* x_out, double* u_out, int32_t* n_out, int32_t* mode_out, double* info,
                                int32_t* status);
+
+/* ---- multi-GPU (one process per GPU): independent problems are sharded over the ranks, there is no data-path collective; the
+ * policy shard of every rank is all-gathered once per cycle over NCCL (NVLink / NVSwitch). NCCL is bound at run time
+ * (dlopen of libnccl.so.2, or $QMB200_NCCL_LIB), so single-GPU hosts need no NCCL.
+ *   qmb200_nccl_unique_id        ncclGetUniqueId (128 bytes): call on rank 0, hand to every rank with the host's own bootstrap
+ *   qmb200_comm_init             ncclCommInitRank for this context (collective call); the context owns the communicator
+ *   qmb200_enable_policy_buffer  without a communicator of the context's own: have k_finalize write the packed policy anyway
+ *                                (for use with a caller-owned ncclComm_t)
+ *   qmb200_allgather_policy      all-gather of the packed policy of the LAST cycle, [B][NMAX][61] rows (t, x*[30], u*[30]) per
+ *                                rank -> gathered[world][B][NMAX][61] (device). nccl_comm: a caller-owned ncclComm_t, or NULL for
+ *                                the context's own. Runs on the context's communication stream, behind the cycle and beside the
+ *                                next one (two send buffers); qmb200_policy_wait_stream orders a consumer stream behind it,
+ *                                qmb200_comm_sync blocks the host until it is complete. */
+#define QMB200_POLICY_WIDTH 61
+int qmb200_nccl_unique_id(void* id128);
+int qmb200_comm_init(qmb200_ctx* ctx, const void* id128, int32_t rank, int32_t world);
+int qmb200_comm_destroy(qmb200_ctx* ctx);
+int qmb200_enable_policy_buffer(qmb200_ctx* ctx);
+const double* qmb200_policy_buffer(qmb200_ctx* ctx);   /* device pointer of the packed policy of the last cycle (or NULL) */
+int qmb200_allgather_policy(qmb200_ctx* ctx, void* nccl_comm, double* gathered);
+int qmb200_policy_wait_stream(qmb200_ctx* ctx, void* stream);
+int qmb200_comm_sync(qmb200_ctx* ctx);
 
 /* Linear interpolation of the stored policy at t[B] (host buffers): x_des[B][30], u_des[B][30], mode[B]. */
 int qmb200_evaluate_policy_batch(qmb200_ctx* ctx, const double* t, double* x_des, double* u_des, int32_t* mode);

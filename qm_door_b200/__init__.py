@@ -86,6 +86,10 @@ class MpcContext:
         self.model, self.problem, self.solver = model, problem, solver
         self.B, self.NMAX, self.EMAX, self.KT = batch, solver.max_nodes, solver.max_events, solver.max_targets
         self.device = device
+        # arguments of the asynchronous entry points are kept alive for a few calls: the stream may still be reading them when
+        # the caller drops its references (torch's caching allocator would hand the memory to the next tensor)
+        import collections
+        self._keep = collections.deque(maxlen=8)
         h = C.c_void_p()
         _check(self.L.qmb200_create(C.byref(model), C.byref(problem), C.byref(solver), batch, device, C.byref(h)))
         self.h = h
@@ -124,7 +128,7 @@ class MpcContext:
         if pinned:
             import torch
             out = {}
-            self._pinned_keepalive = []
+            self._pinned_keepalive = getattr(self, "_pinned_keepalive", [])
             for k, (shp, dt) in shapes.items():
                 t = torch.zeros(shp, dtype=torch.float64 if dt == np.float64 else torch.int32).pin_memory()
                 self._pinned_keepalive.append(t)
@@ -155,11 +159,54 @@ class MpcContext:
                                              _p(out["mode"]), _p(out["info"]), _p(out["status"])))
         return out
 
+    def cycle_async(self, t0, x0, events, modes, nevents, target_t, target_x, out):
+        """Submit one cycle (host buffers; `out` from alloc_outputs(pinned=True)) and return a ticket for wait(). The inputs are
+        copied asynchronously from the arrays given here: pass page-locked arrays and leave them and `out` untouched until wait().
+        Two submissions may be outstanding: the copy-out of cycle k overlaps the computation of cycle k + 1."""
+        B = self.B
+        f8, i4 = np.float64, np.int32
+        args = (_host(t0, (B,), f8, "t0"), _host(x0, (B, 30), f8, "x0"), _host(events, (B, self.EMAX), f8, "events"),
+                _host(modes, (B, self.EMAX + 1), i4, "modes"), _host(nevents, (B,), i4, "nevents"),
+                _host(target_t, (B, self.KT), f8, "target_t"), _host(target_x, (B, self.KT, 37), f8, "target_x"))
+        ticket = C.c_int64()
+        _check(self.L.qmb200_mpc_cycle_batch_async(self.h, *[_p(a) for a in args], _p(out["t"]), _p(out["x"]), _p(out["u"]), _p(out["n"]),
+                                                   _p(out["mode"]), _p(out["info"]), _p(out["status"]), C.byref(ticket)))
+        self._keep.append(args)
+        return ticket.value
+
+    def wait(self, ticket):
+        _check(self.L.qmb200_mpc_cycle_wait(self.h, C.c_int64(ticket)))
+
+    # ---- multi-GPU: all-gather of the packed policy (one process per GPU; see include/qmb200.h)
+    def comm_init(self, unique_id, rank, world):
+        """ncclCommInitRank for this context (collective: every rank calls it with rank 0's id from nccl_unique_id())."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _check(self.L.qmb200_comm_init(self.h, buf, int(rank), int(world)))
+        self.world, self.rank = int(world), int(rank)
+
+    def enable_policy_buffer(self):
+        _check(self.L.qmb200_enable_policy_buffer(self.h))
+        self.world = getattr(self, "world", 1)
+
+    def allgather_policy(self, gathered, comm=None):
+        """All-gather of the last cycle's packed policy [B][NMAX][61] into gathered [world][B][NMAX][61] (torch CUDA tensor), on the
+        context's communication stream: runs beside the next cycle. comm: a caller-owned ncclComm_t value, or None."""
+        world = getattr(self, "world", 1)
+        self._keep.append((gathered,))
+        _check(self.L.qmb200_allgather_policy(self.h, C.c_void_p(comm), _dev(gathered, (world, self.B, self.NMAX, 61), np.float64, "gathered", self.device)))
+
+    def policy_wait_stream(self, stream):
+        _check(self.L.qmb200_policy_wait_stream(self.h, C.c_void_p(stream)))
+
+    def comm_sync(self):
+        _check(self.L.qmb200_comm_sync(self.h))
+
     def cycle_dev(self, t0, x0, events, modes, nevents, target_t, target_x, t_out=None, x_out=None, u_out=None,
                   n_out=None, mode_out=None, info=None, status=None):
         """Same with device-resident torch tensors (raw pointers passed to the C-ABI); asynchronous on the context's stream."""
         B, N, E, K, d = self.B, self.NMAX, self.EMAX, self.KT, self.device
         f8, i4 = np.float64, np.int32
+        self._keep.append((t0, x0, events, modes, nevents, target_t, target_x, t_out, x_out, u_out, n_out, mode_out, info, status))
         _check(self.L.qmb200_mpc_cycle_batch_dev(
             self.h, _dev(t0, (B,), f8, "t0", d), _dev(x0, (B, 30), f8, "x0", d), _dev(events, (B, E), f8, "events", d),
             _dev(modes, (B, E + 1), i4, "modes", d), _dev(nevents, (B,), i4, "nevents", d), _dev(target_t, (B, K), f8, "target_t", d),
@@ -193,11 +240,13 @@ class MpcContext:
     def evaluate_policy_dev(self, t, x_des, u_des, mode):
         """evaluatePolicy with torch CUDA tensors, enqueued on the context's stream."""
         B, d = self.B, self.device
+        self._keep.append((t, x_des, u_des, mode))
         _check(self.L.qmb200_evaluate_policy_batch_dev(self.h, _dev(t, (B,), np.float64, "t", d), _dev(x_des, (B, 30), np.float64, "x_des", d),
                                                        _dev(u_des, (B, 30), np.float64, "u_des", d), _dev(mode, (B,), np.int32, "mode", d)))
 
     def rbd_to_state_dev(self, rbd, x_out, yaw_last=None):
         n, d = int(rbd.shape[0]), self.device
+        self._keep.append((rbd, x_out, yaw_last))
         _check(self.L.qmb200_rbd_to_state_batch_dev(self.h, n, _dev(rbd, (n, 55), np.float64, "rbd", d),
                                                     _dev(yaw_last, (n,), np.float64, "yaw_last", d, True), _dev(x_out, (n, 30), np.float64, "x_out", d)))
 
@@ -240,6 +289,13 @@ DEFAULT_URDF = os.path.join(DATA_DIR, "aliengo_z1.urdf")
 DEFAULT_TASK = os.path.join(DATA_DIR, "aliengo_z1_task.info")
 DEFAULT_REFERENCE = os.path.join(DATA_DIR, "aliengo_z1_reference.info")
 DEFAULT_GAIT = os.path.join(DATA_DIR, "aliengo_z1_gait.info")
+
+
+def nccl_unique_id():
+    """ncclGetUniqueId through the library's run-time NCCL binding: 128 bytes for rank 0 to hand to every rank."""
+    buf = (C.c_char * 128)()
+    _check(lib().qmb200_nccl_unique_id(buf))
+    return bytes(buf.raw)
 
 
 def load_model(urdf_path=DEFAULT_URDF):
@@ -315,6 +371,8 @@ class WbcContext:
         self.L.qmb200_wbc_stream.restype = C.c_void_p
         self.B = batch
         self.device = device
+        import collections
+        self._keep = collections.deque(maxlen=8)      # see MpcContext
         h = C.c_void_p()
         _check(self.L.qmb200_wbc_create(C.byref(model), C.byref(wbc), batch, device, C.byref(h)))
         self.h = h
@@ -355,6 +413,7 @@ class WbcContext:
         """Device tensors, enqueued on this context's stream. Inputs produced on another stream (e.g. the MPC context's policy
         evaluation) must be ordered first: call wait_for(mpc_ctx) (or synchronise) before this."""
         B, d, f8 = self.B, self.device, np.float64
+        self._keep.append((x_des, u_des, rbd, mode, period, time, cmd, status))
         _check(self.L.qmb200_wbc_batch_dev(self.h, _dev(x_des, (B, 30), f8, "x_des", d), _dev(u_des, (B, 30), f8, "u_des", d),
                                            _dev(rbd, (B, 55), f8, "rbd", d), _dev(mode, (B,), np.int32, "mode", d),
                                            _dev(period, (B,), f8, "period", d), _dev(time, (B,), f8, "time", d),
@@ -379,6 +438,7 @@ class WbcContext:
 
     def actuator_dev(self, desc, time_ns, period_ns, obs_time, x_des, u_des, cmd, q, v, tau, status):
         B, d, f8 = self.B, self.device, np.float64
+        self._keep.append((time_ns, obs_time, x_des, u_des, cmd, q, v, tau, status))
         _check(self.L.qmb200_actuator_batch_dev(self.h, C.byref(desc), _dev(time_ns, (B,), np.int64, "time_ns", d), C.c_int64(int(period_ns)),
                                                 _dev(obs_time, (B,), f8, "obs_time", d), _dev(x_des, (B, 30), f8, "x_des", d),
                                                 _dev(u_des, (B, 30), f8, "u_des", d), _dev(cmd, (B, 54), f8, "cmd", d),

@@ -254,7 +254,8 @@ QM_HDN void step_component(const MpcBuffers& m, int b, int c) {
 
 // Accept the step and publish the primal solution ([upstream] toPrimalSolution); one thread per (problem, component c<60).
 // A problem whose SQP loop stopped in an earlier iteration has its step applied already (alpha_in = 0 is passed then).
-QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out, double* x_out, double* u_out) {
+// packed (may be null): the same policy as [B][NMAX][61] rows (t, x*[30], u*[30]), the send buffer of the multi-GPU all-gather.
+QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out, double* x_out, double* u_out, double* packed = nullptr) {
   const int NMAX = m.NMAX, nn = m.nn[b];
   const double alpha = (m.conv[b] == CV_NONE) ? m.ls[(size_t)b * LS_SIZE + LS_ALPHA] : 0.0;
   const size_t o = (size_t)b * NMAX;
@@ -270,10 +271,16 @@ QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out,
         if (k < nn) {
           m.xs[(o + k) * 30 + c] = v[j]; m.prev_x[(o + k) * 30 + c] = v[j];
           if (x_out) x_out[(o + k) * 30 + c] = v[j];
+          if (packed) packed[(o + k) * 61 + 1 + c] = v[j];
         }
       }
     }
-    for (int k = c; k < nn; k += 30) { m.prev_t[o + k] = m.node_ts[o + k]; if (t_out) t_out[o + k] = m.node_ts[o + k]; }   // node times: spread over the state lanes
+    for (int k = c; k < nn; k += 30) {                                   // node times: spread over the state lanes
+      const double tk = m.node_ts[o + k];
+      m.prev_t[o + k] = tk;
+      if (t_out) t_out[o + k] = tk;
+      if (packed) packed[(o + k) * 61] = tk;
+    }
     if (c == 0) m.nprev[b] = nn;
   } else {
     const int cu = c - 30;
@@ -295,6 +302,7 @@ QM_HDN void finalize_component(const MpcBuffers& m, int b, int c, double* t_out,
           else w = v[j];
           m.us[(o + k) * 30 + cu] = w; m.prev_u[(o + k) * 30 + cu] = w;
           if (u_out) u_out[(o + k) * 30 + cu] = w;
+          if (packed) packed[(o + k) * 61 + 31 + cu] = w;
           last = w;
         }
       }

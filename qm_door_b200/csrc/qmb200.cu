@@ -14,6 +14,7 @@
 //   k_finalize   <<<B, 64>>>                 thread per component: publish primal solution + warm start
 // There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -365,9 +366,9 @@ __global__ void __launch_bounds__(64) k_step(MpcBuffers m, const qmb200_solver_d
   }
 }
 
-__global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out) {
+__global__ void __launch_bounds__(64) k_finalize(MpcBuffers m, double* t_out, double* x_out, double* u_out, double* packed) {
   const int b = m.b0 + blockIdx.x, lane = threadIdx.x & 31, c = (threadIdx.x >> 5) * 30 + lane;   // warp 0: states, warp 1: inputs
-  if (lane < 30) finalize_component(m, b, c, t_out, x_out, u_out);
+  if (lane < 30) finalize_component(m, b, c, t_out, x_out, u_out, packed);
   if (threadIdx.x == 31) {            // an idle lane records why the SQP loop stopped (the last iteration ends with ITERATIONS)
     double* ls = m.ls + (size_t)b * LS_SIZE;
     if (m.conv[b] == CV_NONE) ls[LS_CONV] = (double)CV_ITERATIONS;
@@ -461,6 +462,32 @@ struct qmb200_ctx {
   qmb200_solver_desc* dS = nullptr;
   MpcBuffers m;          // ctx-owned device buffers
   double* fb_gains = nullptr; // [B][NMAX][900] feedback gains of the last cycle, allocated on first use
+  // Asynchronous host interface (qmb200_mpc_cycle_batch_async / _wait): results leave on a copy stream while the next cycle
+  // computes. The small per-cycle records the next cycle overwrites early (node counts, modes, line-search record, status) are
+  // snapshotted behind k_finalize; the policy itself (prev_t / prev_x / prev_u) is only rewritten by the next k_finalize, which
+  // waits for the copy of the previous one.
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_cycle[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  int64_t ticket = 0;          // number of asynchronous cycles submitted
+  bool d2h_in_flight = false;  // the last submitted cycle's copies may still be running
+  int32_t* snap_n = nullptr; int32_t* snap_mode = nullptr; double* snap_ls = nullptr; int32_t* snap_status = nullptr;
+  // The launches of a cycle up to the line search are replayed as a CUDA graph (captured on first use, re-captured when the
+  // input pointers change); per-kernel event timing (qmb200_set_profiling) launches them directly.
+  bool use_graph = true;
+  cudaGraphExec_t gexec = nullptr;
+  const void* gkey[8] = {nullptr};
+  int64_t graph_launches = 0, graph_captures = 0;
+  // multi-GPU: packed policy [B][NMAX][61] of the last two cycles (send buffers of the all-gather, written by k_finalize once a
+  // communicator exists), the communicator and its stream: the collective of cycle k runs beside the kernels of cycle k + 1
+  double* policy[2] = {nullptr, nullptr};
+  int pslot = 0;                 // send buffer the last k_finalize wrote
+  void* comm = nullptr;          // ncclComm_t owned by the context (qmb200_comm_init)
+  int world = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_policy = nullptr, ev_comm[2] = {nullptr, nullptr};
+  bool comm_in_flight[2] = {false, false};
+  bool capturing = false;
+  int64_t graph_kernel_counts[QMB200_NUM_KERNELS] = {0};   // kernels per replay of the captured graph
   cudaStream_t stream = nullptr;
   // The cycle can be pipelined over chunks of problems, one stream per chunk, so that the (latency-bound, few CTAs) Riccati
   // sweeps of one chunk run beside the transcription kernels of the next ones (QMB200_CHUNKS; see qmb200_create).
@@ -487,7 +514,7 @@ static cudaEvent_t get_event(qmb200_ctx* c) {
 struct KernelTimer {
   qmb200_ctx* c; int id; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
   KernelTimer(qmb200_ctx* c_, int id_, cudaStream_t st_ = nullptr) : c(c_), id(id_), st(st_ ? st_ : c_->stream) {
-    c->kernel_launches[id]++;
+    if (c->capturing) c->graph_kernel_counts[id]++; else c->kernel_launches[id]++;
     if (c->profiling) { e0 = get_event(c); e1 = get_event(c); cudaEventRecord(e0, st); }
   }
   ~KernelTimer() {
@@ -507,7 +534,9 @@ static void harvest_events(qmb200_ctx* c) {
 
 // One MPC cycle = one asynchronous sequence of launches (no host synchronisation anywhere: the backtracking trials of the filter
 // line search run in k_backtrack, the SQP loop's early exit is a per-problem flag every kernel tests).
-static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, double* u_out) {
+// front: schedule ... line search of the last SQP iteration (per chunk of problems, joined on the main stream);
+// back : k_finalize of the whole batch (the only writer of the stored policy) and the snapshot of the small per-cycle records.
+static int enqueue_front(qmb200_ctx* c, MpcBuffers m) {
   const int B = m.B, NMAX = m.NMAX;
   const int nch = c->nchunks, cb = (B + nch - 1) / nch;
   const int iterations = c->hS.sqp_iterations < 1 ? 1 : c->hS.sqp_iterations;
@@ -540,12 +569,58 @@ static int run_cycle(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, 
       { KernelTimer kt(c, KN_BACKTRACK, st); k_backtrack<<<nb, kTrialThreads, pf_bytes, st>>>(m, c->dM, c->dP, c->dS); }
       if (it + 1 < iterations) { KernelTimer kt(c, KN_STEP, st); k_step<<<nb, 64, 0, st>>>(m, c->dS, it, iterations); }
     }
-    { KernelTimer kt(c, KN_FINALIZE, st); k_finalize<<<nb, 64, 0, st>>>(m, t_out, x_out, u_out); }
     CUDA_OK(cudaEventRecord(c->ev_done[ch], st));
     CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_done[ch], 0));     // the main stream continues behind every chunk
   }
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static int run_front(qmb200_ctx* c, const MpcBuffers& m) {
+  if (!c->use_graph || c->profiling) return enqueue_front(c, m);
+  const void* key[8] = {m.t0, m.x0, m.events, m.modes, m.nevents, m.target_t, m.target_x, (const void*)(intptr_t)c->hS.sqp_iterations};
+  if (!c->gexec || memcmp(key, c->gkey, sizeof(key)) != 0) {
+    if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    for (auto& n : c->graph_kernel_counts) n = 0;
+    c->capturing = true;
+    const int rc = enqueue_front(c, m);
+    c->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return -1; }
+    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&c->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->gexec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    memcpy(c->gkey, key, sizeof(key));
+    c->graph_captures++;
+  }
+  CUDA_OK(cudaGraphLaunch(c->gexec, c->stream));
+  c->graph_launches++;
+  for (int i = 0; i < QMB200_NUM_KERNELS; ++i) c->kernel_launches[i] += c->graph_kernel_counts[i];
+  return 0;
+}
+
+static int run_back(qmb200_ctx* c, MpcBuffers m, double* t_out, double* x_out, double* u_out) {
+  // the stored policy is about to be rewritten: the asynchronous copy of the previous one must have left
+  if (c->d2h_in_flight) { CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_d2h[(c->ticket - 1) & 1], 0)); c->d2h_in_flight = false; }
+  m.b0 = 0; m.nb = m.B;
+  double* packed = nullptr;
+  if (c->policy[0]) {
+    // the send buffer written two cycles ago: its all-gather must have read it
+    c->pslot ^= 1;
+    if (c->comm_in_flight[c->pslot]) { CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_comm[c->pslot], 0)); c->comm_in_flight[c->pslot] = false; }
+    packed = c->policy[c->pslot];
+  }
+  { KernelTimer kt(c, KN_FINALIZE); k_finalize<<<m.B, 64, 0, c->stream>>>(m, t_out, x_out, u_out, packed); }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int run_cycle(qmb200_ctx* c, const MpcBuffers& m, double* t_out, double* x_out, double* u_out) {
+  if (run_front(c, m) != 0) return -1;
+  return run_back(c, m, t_out, x_out, u_out);
 }
 
 extern "C" {
@@ -603,6 +678,16 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
     C_OK(cudaEventCreateWithFlags(&c->ev_join[ch], cudaEventDisableTiming));
   }
   C_OK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  C_OK(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    C_OK(cudaEventCreateWithFlags(&c->ev_cycle[i], cudaEventDisableTiming));
+    C_OK(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+  }
+  { const char* env = getenv("QMB200_GRAPH"); c->use_graph = !(env && atoi(env) == 0); }
+  C_OK(cudaMalloc(&c->snap_n, sizeof(int32_t) * (size_t)batch));
+  C_OK(cudaMalloc(&c->snap_mode, sizeof(int32_t) * (size_t)batch * solver->max_nodes));
+  C_OK(cudaMalloc(&c->snap_ls, sizeof(double) * (size_t)batch * LS_SIZE));
+  C_OK(cudaMalloc(&c->snap_status, sizeof(int32_t) * (size_t)batch));
   C_OK(cudaMalloc(&c->dM, sizeof(*model)));
   C_OK(cudaMalloc(&c->dP, sizeof(*problem)));
   C_OK(cudaMalloc(&c->dS, sizeof(*solver)));
@@ -644,6 +729,11 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->dP) cudaFree(c->dP);
   if (c->dS) cudaFree(c->dS);
   if (c->fb_gains) cudaFree(c->fb_gains);
+  qmb200_comm_destroy(c);
+  if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+  if (c->gexec) cudaGraphExecDestroy(c->gexec);
+  for (int i = 0; i < 2; ++i) { if (c->ev_cycle[i]) cudaEventDestroy(c->ev_cycle[i]); if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]); }
+  for (void* p : {(void*)c->snap_n, (void*)c->snap_mode, (void*)c->snap_ls, (void*)c->snap_status}) if (p) cudaFree(p);
   for (int ch = 0; ch < qmb200_ctx::kMaxChunks; ++ch) {
     if (c->cs[ch]) { cudaStreamSynchronize(c->cs[ch]); cudaStreamDestroy(c->cs[ch]); }
     if (c->side[ch]) { cudaStreamSynchronize(c->side[ch]); cudaStreamDestroy(c->side[ch]); }
@@ -654,6 +744,154 @@ int qmb200_destroy(qmb200_ctx* c) {
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+  return 0;
+}
+
+// ---- multi-GPU collective. NCCL is bound at run time (dlopen of libnccl.so.2: the copy the host process already uses -- e.g.
+//      the one bundled with PyTorch -- or the system one), so the library loads on hosts without NCCL and single-GPU use never
+//      touches it. Minimal declarations of the NCCL C API (nccl.h) used here:
+typedef struct { char internal[128]; } qm_ncclUniqueId;
+typedef void* qm_ncclComm_t;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(qm_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(qm_ncclComm_t*, int, qm_ncclUniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, qm_ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(qm_ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* env = getenv("QMB200_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm) continue;
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (api.handle) {
+      api.GetUniqueId = (int (*)(qm_ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(qm_ncclComm_t*, int, qm_ncclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, qm_ncclComm_t, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+      api.CommDestroy = (int (*)(qm_ncclComm_t))dlsym(api.handle, "ncclCommDestroy");
+      api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) api.handle = nullptr;
+    }
+  }
+  return api.handle ? &api : nullptr;
+}
+static int nccl_fail(NcclApi* a, const char* what, int rc) {
+  return fail(std::string(what) + ": " + ((a && a->GetErrorString) ? a->GetErrorString(rc) : "NCCL error"));
+}
+enum { QM_NCCL_FLOAT64 = 8 };   // ncclDataType_t ncclFloat64 / ncclDouble
+
+int qmb200_nccl_unique_id(void* id128) {
+  if (!id128) return fail("qmb200_nccl_unique_id: null argument");
+  NcclApi* a = nccl_api();
+  if (!a) return fail("qmb200_nccl_unique_id: libnccl.so.2 not found (set QMB200_NCCL_LIB)");
+  qm_ncclUniqueId id;
+  const int rc = a->GetUniqueId(&id);
+  if (rc != 0) return nccl_fail(a, "ncclGetUniqueId", rc);
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+// send buffers + stream + events of the collective (also without a communicator of our own: qmb200_allgather_policy accepts one)
+static int ensure_policy_buffers(qmb200_ctx* c) {
+  if (c->policy[0]) return 0;
+  const size_t bytes = sizeof(double) * (size_t)c->B * c->m.NMAX * QMB200_POLICY_WIDTH;
+  for (int i = 0; i < 2; ++i) {
+    CUDA_OK(cudaMalloc(&c->policy[i], bytes));
+    CUDA_OK(cudaMemsetAsync(c->policy[i], 0, bytes, c->stream));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm[i], cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_policy, cudaEventDisableTiming));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  c->bytes += 2 * (int64_t)bytes;
+  return 0;
+}
+
+int qmb200_comm_init(qmb200_ctx* c, const void* id128, int32_t rank, int32_t world) {
+  if (!c || !id128) return fail("qmb200_comm_init: null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("qmb200_comm_init: bad rank / world");
+  if (c->comm) return fail("qmb200_comm_init: the context already owns a communicator");
+  NcclApi* a = nccl_api();
+  if (!a) return fail("qmb200_comm_init: libnccl.so.2 not found (set QMB200_NCCL_LIB)");
+  CUDA_OK(cudaSetDevice(c->device));
+  if (ensure_policy_buffers(c) != 0) return -1;
+  qm_ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  qm_ncclComm_t comm = nullptr;
+  const int rc = a->CommInitRank(&comm, world, id, rank);
+  if (rc != 0) return nccl_fail(a, "ncclCommInitRank", rc);
+  c->comm = comm; c->world = world; c->rank = rank;
+  return 0;
+}
+
+int qmb200_comm_destroy(qmb200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  if (c->comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy(c->comm); c->comm = nullptr; }
+  for (int i = 0; i < 2; ++i) {
+    if (c->policy[i]) { cudaFree(c->policy[i]); c->policy[i] = nullptr; }
+    if (c->ev_comm[i]) { cudaEventDestroy(c->ev_comm[i]); c->ev_comm[i] = nullptr; }
+    c->comm_in_flight[i] = false;
+  }
+  if (c->ev_policy) { cudaEventDestroy(c->ev_policy); c->ev_policy = nullptr; }
+  if (c->comm_stream) { cudaStreamDestroy(c->comm_stream); c->comm_stream = nullptr; }
+  c->world = 1; c->rank = 0;
+  return 0;
+}
+
+int qmb200_enable_policy_buffer(qmb200_ctx* c) {
+  if (!c) return fail("null ctx");
+  CUDA_OK(cudaSetDevice(c->device));
+  return ensure_policy_buffers(c);
+}
+
+const double* qmb200_policy_buffer(qmb200_ctx* c) { return (c && c->policy[0]) ? c->policy[c->pslot] : nullptr; }
+
+int qmb200_allgather_policy(qmb200_ctx* c, void* nccl_comm, double* gathered) {
+  if (!c || !gathered) return fail("qmb200_allgather_policy: null argument");
+  if (!c->policy[0]) return fail("qmb200_allgather_policy: no packed policy yet (qmb200_comm_init or qmb200_enable_policy_buffer before the cycle)");
+  qm_ncclComm_t comm = nccl_comm ? nccl_comm : c->comm;
+  CUDA_OK(cudaSetDevice(c->device));
+  const int slot = c->pslot;
+  const size_t count = (size_t)c->B * c->m.NMAX * QMB200_POLICY_WIDTH;
+  // the collective starts once the cycle that wrote the send buffer is through, on its own stream
+  CUDA_OK(cudaEventRecord(c->ev_policy, c->stream));
+  CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_policy, 0));
+  if (!comm) {
+    if (c->world != 1) return fail("qmb200_allgather_policy: no communicator");
+    CUDA_OK(cudaMemcpyAsync(gathered, c->policy[slot], sizeof(double) * count, cudaMemcpyDeviceToDevice, c->comm_stream));   // one rank
+  } else {
+    NcclApi* a = nccl_api();
+    if (!a) return fail("qmb200_allgather_policy: libnccl.so.2 not found");
+    const int rc = a->AllGather(c->policy[slot], gathered, count, QM_NCCL_FLOAT64, comm, c->comm_stream);
+    if (rc != 0) return nccl_fail(a, "ncclAllGather", rc);
+  }
+  CUDA_OK(cudaEventRecord(c->ev_comm[slot], c->comm_stream));
+  c->comm_in_flight[slot] = true;
+  return 0;
+}
+
+int qmb200_policy_wait_stream(qmb200_ctx* c, void* stream) {
+  if (!c) return fail("null ctx");
+  if (!c->policy[0]) return 0;
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_comm[c->pslot], 0));
+  return 0;
+}
+
+int qmb200_comm_sync(qmb200_ctx* c) {
+  if (!c) return fail("null ctx");
+  if (!c->comm_stream) return 0;
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize(c->comm_stream));
   return 0;
 }
 
@@ -741,11 +979,11 @@ int qmb200_mpc_cycle_batch_dev(qmb200_ctx* c, const double* t0, const double* x0
   return 0;
 }
 
-int qmb200_mpc_cycle_batch(qmb200_ctx* c, const double* t0, const double* x0, const double* events, const int32_t* modes,
-                           const int32_t* nevents, const double* target_t, const double* target_x, double* t_out, double* x_out,
-                           double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status) {
+int qmb200_mpc_cycle_batch_async(qmb200_ctx* c, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                                 const int32_t* nevents, const double* target_t, const double* target_x, double* t_out, double* x_out,
+                                 double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status, int64_t* ticket) {
   if (!c) return fail("null ctx");
-  if (!t0 || !x0 || !events || !modes || !nevents || !target_t || !target_x) return fail("qmb200_mpc_cycle_batch: null input");
+  if (!t0 || !x0 || !events || !modes || !nevents || !target_t || !target_x) return fail("qmb200_mpc_cycle_batch_async: null input");
   CUDA_OK(cudaSetDevice(c->device));
   MpcBuffers& m = c->m;
   const size_t B = c->B, BN = B * m.NMAX;
@@ -758,14 +996,49 @@ int qmb200_mpc_cycle_batch(qmb200_ctx* c, const double* t0, const double* x0, co
   CUDA_OK(cudaMemcpyAsync(m.target_t, target_t, sizeof(double) * B * m.KT, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(m.target_x, target_x, sizeof(double) * B * m.KT * QM_NTARGET, cudaMemcpyHostToDevice, st));
   if (run_cycle(c, m, nullptr, nullptr, nullptr) != 0) return -1;
-  if (t_out) CUDA_OK(cudaMemcpyAsync(t_out, m.prev_t, sizeof(double) * BN, cudaMemcpyDeviceToHost, st));
-  if (x_out) CUDA_OK(cudaMemcpyAsync(x_out, m.prev_x, sizeof(double) * BN * 30, cudaMemcpyDeviceToHost, st));
-  if (u_out) CUDA_OK(cudaMemcpyAsync(u_out, m.prev_u, sizeof(double) * BN * 30, cudaMemcpyDeviceToHost, st));
-  if (n_out) CUDA_OK(cudaMemcpyAsync(n_out, m.nn, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-  if (mode_out) CUDA_OK(cudaMemcpyAsync(mode_out, m.node_mode, sizeof(int32_t) * BN, cudaMemcpyDeviceToHost, st));
-  if (info) CUDA_OK(cudaMemcpyAsync(info, m.ls, sizeof(double) * B * LS_SIZE, cudaMemcpyDeviceToHost, st));
-  if (status) CUDA_OK(cudaMemcpyAsync(status, m.status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
+  // snapshot of the records the next cycle overwrites before its k_finalize
+  CUDA_OK(cudaMemcpyAsync(c->snap_n, m.nn, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->snap_mode, m.node_mode, sizeof(int32_t) * BN, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->snap_ls, m.ls, sizeof(double) * B * LS_SIZE, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(c->snap_status, m.status, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+  const int slot = (int)(c->ticket & 1);
+  CUDA_OK(cudaEventRecord(c->ev_cycle[slot], st));
+  // results leave on the copy stream; the compute stream is free for the next cycle
+  cudaStream_t cp = c->copy;
+  CUDA_OK(cudaStreamWaitEvent(cp, c->ev_cycle[slot], 0));
+  if (t_out) CUDA_OK(cudaMemcpyAsync(t_out, m.prev_t, sizeof(double) * BN, cudaMemcpyDeviceToHost, cp));
+  if (x_out) CUDA_OK(cudaMemcpyAsync(x_out, m.prev_x, sizeof(double) * BN * 30, cudaMemcpyDeviceToHost, cp));
+  if (u_out) CUDA_OK(cudaMemcpyAsync(u_out, m.prev_u, sizeof(double) * BN * 30, cudaMemcpyDeviceToHost, cp));
+  if (n_out) CUDA_OK(cudaMemcpyAsync(n_out, c->snap_n, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, cp));
+  if (mode_out) CUDA_OK(cudaMemcpyAsync(mode_out, c->snap_mode, sizeof(int32_t) * BN, cudaMemcpyDeviceToHost, cp));
+  if (info) CUDA_OK(cudaMemcpyAsync(info, c->snap_ls, sizeof(double) * B * LS_SIZE, cudaMemcpyDeviceToHost, cp));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, c->snap_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, cp));
+  CUDA_OK(cudaEventRecord(c->ev_d2h[slot], cp));
+  // the snapshot buffers are rewritten by the next submission: order it behind this copy (the policy buffers are guarded in run_back)
+  c->d2h_in_flight = true;
+  if (ticket) *ticket = c->ticket;
+  c->ticket++;
+  return 0;
+}
+
+int qmb200_mpc_cycle_wait(qmb200_ctx* c, int64_t ticket) {
+  if (!c) return fail("null ctx");
+  if (ticket < 0 || ticket >= c->ticket) return fail("qmb200_mpc_cycle_wait: unknown ticket");
+  if (ticket < c->ticket - 2) return 0;      // older than the two tracked submissions: the copy stream is in order, long complete
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaEventSynchronize(c->ev_d2h[ticket & 1]));
+  if (ticket == c->ticket - 1) harvest_events(c);
+  return 0;
+}
+
+int qmb200_mpc_cycle_batch(qmb200_ctx* c, const double* t0, const double* x0, const double* events, const int32_t* modes,
+                           const int32_t* nevents, const double* target_t, const double* target_x, double* t_out, double* x_out,
+                           double* u_out, int32_t* n_out, int32_t* mode_out, double* info, int32_t* status) {
+  int64_t ticket = 0;
+  if (qmb200_mpc_cycle_batch_async(c, t0, x0, events, modes, nevents, target_t, target_x, t_out, x_out, u_out, n_out, mode_out, info,
+                                   status, &ticket) != 0) return -1;
+  if (qmb200_mpc_cycle_wait(c, ticket) != 0) return -1;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   harvest_events(c);
   return 0;
 }

@@ -24,7 +24,7 @@ def _worker(rank, world, port, total, q):
     cp = abi_fill.CPort(W.model, W.problem, W.solver, hi - lo)
     out = cp.cycle(np.zeros(hi - lo), W.x0[lo:hi], W.events[lo:hi], W.modes[lo:hi], W.nevents[lo:hi], W.target_t[lo:hi], W.target_x[lo:hi])
     shard = D.pack_policy(torch.from_numpy(out["t"]), torch.from_numpy(out["x"]), torch.from_numpy(out["u"]))
-    gathered = D.allgather_policy(shard)
+    gathered = D.allgather_ragged(shard, total)        # shard sizes differ by one when total % world != 0
     if rank == 0:
         q.put(gathered.numpy())
     dist.barrier()
@@ -43,10 +43,14 @@ def test_shard_range_covers_batch():
     assert shard_range(5632, 3, 8) == (2112, 2816)          # config 4: 704 problems per rank
 
 
-def test_two_rank_gloo_allgather_equals_single_process(descs):
+import pytest
+
+
+@pytest.mark.parametrize("total", [6, 7])
+def test_two_rank_gloo_allgather_equals_single_process(descs, total):
     from oracle import abi_fill
     from qm_door_b200 import distributed as D, workload
-    total, world = 6, 2
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 400)

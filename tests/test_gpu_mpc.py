@@ -409,3 +409,62 @@ def test_wrappers_reject_wrong_shapes_and_devices(descs):
         bad.alpha_decay = 1.0
         q.MpcContext(model, problem, bad, 2)
     ctx.close()
+
+
+def test_async_submit_wait_matches_blocking_call_and_graph_replay(descs, monkeypatch):
+    """qmb200_mpc_cycle_batch_async / _wait (copy-out on its own stream, two submissions outstanding) gives bit-identical
+    results to the blocking call, with and without the CUDA-graph replay of the cycle (QMB200_GRAPH=0 launches directly)."""
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    W = workload.Workload(16, horizon=0.3, dt=0.01, seed=21)
+    args = (W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+    monkeypatch.setenv("QMB200_GRAPH", "0")
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    ref = [dict((k, v.copy()) for k, v in ctx.cycle(np.full(W.B, 0.01 * c), *args).items()) for c in range(5)]
+    ctx.close()
+    monkeypatch.setenv("QMB200_GRAPH", "1")
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    outs = [ctx.alloc_outputs(pinned=True), ctx.alloc_outputs(pinned=True)]
+    t0s = [np.zeros(W.B), np.zeros(W.B)]
+    prev = None
+    for c in range(5):
+        t0s[c & 1][:] = 0.01 * c
+        tk = ctx.cycle_async(t0s[c & 1], *args, out=outs[c & 1])
+        if prev is not None:
+            ctx.wait(prev)
+            for key in ("t", "x", "u", "n", "mode", "status"):
+                assert np.array_equal(outs[(c - 1) & 1][key], ref[c - 1][key]), (c - 1, key)
+            assert np.array_equal(outs[(c - 1) & 1]["info"][:, :12], ref[c - 1]["info"][:, :12])
+        prev = tk
+    ctx.wait(prev)
+    assert np.array_equal(outs[0]["x"], ref[4]["x"]) and np.array_equal(outs[0]["u"], ref[4]["u"])
+    with pytest.raises(q.Qmb200Error):
+        ctx.wait(prev + 5)
+    ctx.close()
+
+
+def test_c_abi_allgather_of_the_packed_policy_single_rank(descs):
+    """qmb200_allgather_policy on one rank (no communicator: the send buffer k_finalize packs is copied on the communication
+    stream): gathered[0] rows are (t, x*, u*) of the cycle; two cycles in flight use the two send buffers. The NCCL path of the same
+    entry point is exercised by tools/multi_gpu_check.py under gpurun --gpus 2 and by bench.py --gpus N."""
+    import torch
+    import qm_door_b200 as q
+    from qm_door_b200 import workload
+    W = workload.Workload(8, horizon=0.2, dt=0.01, seed=3)
+    ctx = q.MpcContext(W.model, W.problem, W.solver, W.B)
+    ctx.enable_policy_buffer()
+    dev = torch.device("cuda", 0)
+    gathered = [torch.zeros(1, W.B, W.solver.max_nodes, 61, dtype=torch.float64, device=dev) for _ in range(2)]
+    outs = []
+    for c in range(3):
+        out = ctx.cycle(np.full(W.B, 0.01 * c), W.x0, W.events, W.modes, W.nevents, W.target_t, W.target_x)
+        ctx.allgather_policy(gathered[c & 1])
+        outs.append({k: v.copy() for k, v in out.items()})
+        if c >= 1:
+            ctx.comm_sync()
+            g = gathered[c & 1][0].cpu().numpy()
+            for b in range(W.B):
+                n = out["n"][b]
+                assert np.array_equal(g[b, :n, 0], out["t"][b, :n]) and np.array_equal(g[b, :n, 1:31], out["x"][b, :n])
+                assert np.array_equal(g[b, :n, 31:], out["u"][b, :n])
+    ctx.close()
