@@ -1130,11 +1130,9 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
   const int nut = (int)st[SB_NUT];
   const double* A = st + SB_A; const double* B = st + SB_B; const double* b = st + SB_b;
   double* S = W + RW_S; double* s = W + RW_sv;
-  // ---- P1: only what G needs (S B, s + S b). The larger product S A is not on the way to G: it is formed by the rest warps in
-  //         the shadow of the inverse (P3), which is the longest dependency chain of a stage. A node without inputs (pre-event
-  //         node) has no inverse to hide behind: all warps form S A here.
+  // ---- P1
+  mm<4, false, MM_XSYM>(g, 30, 30, 30, S, 30, A, 30, (const double*)nullptr, 0, 1.0, W + RW_SA, 30);
   if (nut > 0) mm<3, false, MM_XSYM>(g, 30, nut, 30, S, 30, B, QM_NUT, (const double*)nullptr, 0, 1.0, W + RW_SB, QM_NUT);
-  else mm<4, false, MM_XSYM>(g, 30, 30, 30, S, 30, A, 30, (const double*)nullptr, 0, 1.0, W + RW_SA, 30);
   rows_dot(g, 30, 30, [&](int i) { return s[i]; },
            [&](int i, int j) { return ((j < i) ? S[30 * j + i] : S[30 * i + j]) * b[j]; },
            [&](int i, double v) { W[RW_sb + i] = v; });
@@ -1193,10 +1191,6 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
   // ---- P3 rest: S <- Q + A' SA (upper tiles); H = P + B' SA; s <- q + A' sb   (S, s were consumed in P1)
   if (g.rest_active()) {
     auto r_ = g.rest();
-    if (nut > 0) {
-      mm<2, false, MM_XSYM>(r_, 30, 30, 30, S, 30, A, 30, (const double*)nullptr, 0, 1.0, W + RW_SA, 30);
-      r_.sync();                                   // S A complete before S is overwritten / read back
-    }
     mm<1, true, MM_UP>(r_, 30, 30, 30, A, 30, W + RW_SA, 30, st + SB_Q, 30, 1.0, S, 30);
     if (nut > 0) mm<1, true>(r_, nut, 30, 30, B, QM_NUT, W + RW_SA, 30, st + SB_P, 30, 1.0, W + RW_H, 30, 1);
     rows_dot(r_, 30, 30, [&](int i) { return st[SB_q + i]; },
