@@ -8,14 +8,15 @@
 //                                 (qm_wbc/include/qm_wbc/WbcBase.h:31-32; 54 doubles, caller keeps .tail(18))
 //   qmb200::SqpMpcB200          : advanceMpc()/evaluatePolicy() shaped like MPC_MRT_Interface as used at
 //                                 QMController.cpp:116-120,134-143 (run one SQP cycle, then interpolate the policy)
-// OCS2, Eigen and ROS are not available in this build image, so the classes are written against plain std::vector<double>
-// ("vector_t" in the reference); with QMB200_WITH_OCS2 defined the thin derived classes at the bottom bind them to the real
-// ocs2::vector_t / qm::WbcBase types (see INTEGRATION.md for the controller-side stub).
+// The classes here are written against plain std::vector<double> ("vector_t" in the reference) and need nothing but the C-ABI;
+// include/qmb200_ocs2_adapters.hpp derives the reference-typed objects from them (B200SqpMpc : ocs2::MPC_BASE,
+// B200HierarchicalWbc : qm::WbcBase), which is what a QMController subclass installs.
 // Error behaviour follows the reference: construction problems throw std::runtime_error / std::invalid_argument
 // (QMInterface.cpp:41-62); per-solve WBC failures are not thrown (the reference ignores qpOASES' return code,
 // HoQp.cpp:143-146) but kept in lastStatus(); MPC failures throw std::runtime_error like the MPC thread's catch block expects
 // (QMController.cpp:328-331).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -156,6 +157,7 @@ class SqpMpcB200 {
   const std::vector<double>& stateTrajectory() const { return x_; }
   const std::vector<double>& inputTrajectory() const { return u_; }
   double stepSize() const { return info_[0]; }
+  const double* info() const { return info_; }          // QMB200_INFO_SIZE entries, see include/qmb200.h
 
  private:
   qmb200_solver_desc s_;
