@@ -93,6 +93,14 @@ class MpcProblem:
                            + relaxed_barrier(z - P.arm_vel_lo, P.vel_bar_mu, P.vel_bar_delta)[0].sum()
                            + relaxed_barrier(P.arm_vel_hi - z, P.vel_bar_mu, P.vel_bar_delta)[0].sum())
 
+    def set_mode_schedule(self, events, modes):
+        """A new mode schedule arrives between two cycles ([upstream] GaitReceiver::preSolverRun replacing the gait schedule from
+        an insertion time on, qm_controllers/src/QMController.cpp:297-303; published by GaitTopicPublisher.cpp:31-44). The previous
+        primal solution is kept as it is and interpolated for the warm start; the re-timing of the warm start across moved
+        events ([upstream] trajectorySpread, not vendored) is not restated."""
+        self.events, self.modes = np.asarray(events, dtype=float), np.asarray(modes, dtype=np.int32)
+        self.swing = G.SwingPlanner(self.events, self.modes, self.P.swing)
+
     def mode_at(self, t):
         return int(self.modes[G.mode_index(self.events, t)])
 

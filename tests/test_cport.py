@@ -295,3 +295,50 @@ def test_grid_sweep_matches_oracle_with_overwritten_event_nodes(descs, oracle_in
         assert np.array_equal(out["t"][b, :len(t)], ts)
         pairs = np.nonzero(f == G.EV_PRE)[0]
         assert all(f[k + 1] == G.EV_POST for k in pairs)
+
+
+def gait_change_scenario(P, B=2, seed=41):
+    """Mode schedule that changes mid-run (GaitReceiver, QMController.cpp:297-303): trot for the first two cycles; then a new
+    template (pace / flying trot) is inserted at the first trot event after t = 0.1 s, the schedule before it is kept."""
+    m = None
+    scheds_a, scheds_b = [], []
+    rng = np.random.default_rng(seed)
+    for b in range(B):
+        ph = rng.uniform(0.0, 0.7)
+        ev, md = G.tile_schedule(P.gaits["trot"], -1.4 - ph, 1.6)
+        scheds_a.append((ev, md))
+        k = int(np.searchsorted(ev, 0.1)) + 1                      # events kept: ev[:k]; the new template starts at ev[k - 1]
+        new = P.gaits["pace"] if b % 2 == 0 else P.gaits["flying_trot"]
+        ev2, md2 = G.tile_schedule(new, ev[k - 1], 1.6)
+        scheds_b.append((np.concatenate([ev[:k - 1], ev2]), np.concatenate([md[:k], md2[1:]]).astype(np.int32)))
+    return scheds_a, scheds_b
+
+
+def test_gait_change_between_cycles_against_oracle(descs, oracle_inputs):
+    """The mode schedule is an input of every cycle: a gait change between two cycles moves / adds gait-event nodes in the
+    horizon while the warm start still comes from the solution under the old schedule."""
+    model, problem, solver, _ = descs
+    m, P = oracle_inputs
+    B, hor = 2, 0.4
+    x0s, _ = scenarios.perturbed_states(m, P, B, seed=41)
+    tt, ts = scenarios.standing_target(m, P)
+    sd = solver_for(solver, hor, 0.01)
+    sa, sb = gait_change_scenario(P, B)
+    cp = abi_fill.CPort(model, problem, sd, B)
+    probs = [sqp.MpcProblem(m, P, sa[b][0], sa[b][1], tt, ts, horizon=hor, dt=0.01) for b in range(B)]
+    seen = set()
+    for c in range(4):
+        scheds = sa if c < 2 else sb
+        if c == 2:
+            for b in range(B):
+                probs[b].set_mode_schedule(*sb[b])
+        ev, md, ne = abi_fill.pack_schedules(scheds, sd.max_events)
+        out = cp.cycle(np.full(B, 0.01 * c), x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)))
+        assert (out["status"] == 0).all()
+        for b in range(B):
+            _, xs, us, info = sqp.mpc_cycle(probs[b], 0.01 * c, x0s[b])
+            n = info["n"] + 1
+            assert out["n"][b] == n and np.array_equal(out["mode"][b, :n], info["modes"])
+            assert rel_l2(out["x"][b, :n], xs) < 1e-8 and rel_l2(out["u"][b, :n], us) < 1e-8
+            seen.update(int(v) for v in info["modes"])
+    assert {9, 6}.issubset(seen) and (10 in seen or 5 in seen or 0 in seen)       # trot modes, then pace (LF_LH / RF_RH) or flight

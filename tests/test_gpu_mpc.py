@@ -468,3 +468,38 @@ def test_c_abi_allgather_of_the_packed_policy_single_rank(descs):
                 assert np.array_equal(g[b, :n, 0], out["t"][b, :n]) and np.array_equal(g[b, :n, 1:31], out["x"][b, :n])
                 assert np.array_equal(g[b, :n, 31:], out["u"][b, :n])
     ctx.close()
+
+
+def test_gait_change_between_cycles_on_device(descs):
+    """Mode-schedule change mid-run (GaitReceiver, QMController.cpp:297-303): the schedule is an input of every cycle; after the
+    change the gait-event nodes of the horizon move while the warm start comes from the solution under the old schedule.
+    CUDA path against the live oracle (problem 0) and the CPU port (both problems)."""
+    import qm_door_b200 as q
+    from oracle import abi_fill, config, scenarios, sqp
+    from test_cport import gait_change_scenario
+    model, problem, solver, _ = descs
+    m, P = config.load_default()
+    B, hor = 2, 0.4
+    x0s, _ = scenarios.perturbed_states(m, P, B, seed=41)
+    tt, ts = scenarios.standing_target(m, P)
+    sd = solver_for(solver, hor, 0.01)
+    sa, sb = gait_change_scenario(P, B)
+    ctx = q.MpcContext(model, problem, sd, B)
+    cp = abi_fill.CPort(model, problem, sd, B)
+    prob = sqp.MpcProblem(m, P, sa[0][0], sa[0][1], tt, ts, horizon=hor, dt=0.01)
+    for c in range(4):
+        if c == 2:
+            prob.set_mode_schedule(*sb[0])
+        ev, md, ne = abi_fill.pack_schedules(sa if c < 2 else sb, sd.max_events)
+        args = (np.full(B, 0.01 * c), x0s, ev, md, ne, np.tile(tt, (B, 1)), np.tile(ts, (B, 1, 1)))
+        out, ref = ctx.cycle(*args), cp.cycle(*args)
+        assert (out["status"] == 0).all() and np.array_equal(out["n"], ref["n"])
+        for b in range(B):
+            n = out["n"][b]
+            assert np.array_equal(out["mode"][b, :n], ref["mode"][b, :n]) and np.array_equal(out["t"][b, :n], ref["t"][b, :n])
+            assert rel_l2(out["x"][b, :n], ref["x"][b, :n]) < EXPECTED_TOL and rel_l2(out["u"][b, :n], ref["u"][b, :n]) < EXPECTED_TOL
+        _, xs, us, info = sqp.mpc_cycle(prob, 0.01 * c, x0s[0])
+        n = info["n"] + 1
+        assert out["n"][0] == n and np.array_equal(out["mode"][0, :n], info["modes"])
+        assert rel_l2(out["x"][0, :n], xs) < EXPECTED_TOL and rel_l2(out["u"][0, :n], us) < EXPECTED_TOL
+    ctx.close(); cp.close()
