@@ -30,7 +30,7 @@ namespace qm {
 
 // Development aid (-DQM_PHASE_TIMING): thread 0 of CTA 0 accumulates the cycles between consecutive ticks per phase id.
 #if defined(QM_PHASE_TIMING) && defined(__CUDACC__)
-__device__ unsigned long long qm_dbg[32];
+__device__ unsigned long long qm_dbg[64];
 __device__ unsigned long long qm_dbg_last;
 #endif
 #if defined(QM_PHASE_TIMING) && defined(__CUDA_ARCH__)

@@ -69,7 +69,8 @@ enum {
   WS_NP = WS_ZD + 18,                // [18]
   WS_U = WS_NP + 18,                 // [60]
   WS_CN = WS_U + 60,                 // [40] column norms / misc
-  WS_END = WS_CN + 40,
+  WS_HP = WS_CN + 40,                // [4][56] partial sums of the Householder steps (4 row chunks per column)
+  WS_END = WS_HP + 4 * 56,
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
 enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_SIZE = 244 };
@@ -438,39 +439,47 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
 
 // ------------------------------------------------------------------------------------------ dense helpers
 // Householder triangularisation of the m x (n+1) matrix A (row major, ld): columns 0..n-1 are reduced, column n (rhs)
-// is transformed along. On exit the upper triangle holds R and A[0:n][n] = Q'rhs. vh/wj: scratch.
+// is transformed along. On exit the upper triangle holds R and A[0:n][n] = Q'rhs. vh: m doubles, wj: ld + 2, hp: 4 x 56 scratch.
+// Every step is three short phases over the whole group: (a) inner products of column k with the columns k..n, each split
+// over four row chunks; (b) the reflector's scalars and w = beta v'A per column, the reflector itself copied aside;
+// (c) the rank-one update. No phase has a serial loop longer than a quarter of a column.
+enum { HH_PARTS = 4, HH_LD = 56 };
 template <class G>
-QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj) {
+QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj, double* hp) {
   const int steps = (m - 1 < n) ? m - 1 : n;
   for (int k = 0; k < steps; ++k) {
-    if (g.tid() == 0) {
-      double s = 0.0;
-      for (int i = k; i < m; ++i) s += A[i * ld + k] * A[i * ld + k];
+    const int rows = m - k, cols = n - k + 1;                 // columns k..n (rhs included); column k gives the norm
+    const int chunk = (rows + HH_PARTS - 1) / HH_PARTS;
+    QM_PFOR(g, idx, HH_PARTS * cols) {
+      const int part = idx / cols, j = k + idx - part * cols;
+      const int i0 = k + part * chunk, i1 = (i0 + chunk < m) ? i0 + chunk : m;
+      double sp = 0.0;
+      for (int i = i0; i < i1; ++i) sp += A[i * ld + k] * A[i * ld + j];
+      hp[part * HH_LD + (j - k)] = sp;
+    }
+    g.sync();
+    {
+      const double s = (hp[0] + hp[HH_LD]) + (hp[2 * HH_LD] + hp[3 * HH_LD]);      // |A[k:, k]|^2
       const double nrm = sqrt(s);
       const double akk = A[k * ld + k];
       const double alpha = (akk >= 0.0) ? -nrm : nrm;
-      vh[k] = akk - alpha;
-      // beta = 2 / (v'v) with v'v = s - akk^2 + (akk - alpha)^2
-      const double vv = s - akk * akk + vh[k] * vh[k];
-      wj[ld] = (vv > 0.0) ? 2.0 / vv : 0.0;
-      wj[ld + 1] = alpha;
-    }
-    QM_PFOR(g, i, m - k - 1) vh[k + 1 + i] = A[(k + 1 + i) * ld + k];
-    g.sync();
-    const double beta = wj[ld];
-    QM_PFOR(g, jj, n - k) {            // columns k+1..n (rhs included)
-      const int j = k + 1 + jj;
-      double s = 0.0;
-      for (int i = k; i < m; ++i) s += vh[i] * A[i * ld + j];
-      wj[j] = beta * s;
+      const double vk = akk - alpha;
+      const double vv = s - akk * akk + vk * vk;               // v'v with v = A[k:, k] - alpha e_k
+      const double beta = (vv > 0.0) ? 2.0 / vv : 0.0;
+      QM_PFOR(g, jj, n - k) {                                  // columns k+1..n: v'A_j = A_k'A_j - alpha A[k][j]
+        const int j = k + 1 + jj;
+        const double c = (hp[jj + 1] + hp[HH_LD + jj + 1]) + (hp[2 * HH_LD + jj + 1] + hp[3 * HH_LD + jj + 1]);
+        wj[j] = beta * (c - alpha * A[k * ld + j]);
+      }
+      QM_PFOR(g, i, rows) vh[k + i] = (i == 0) ? vk : A[(k + i) * ld + k];
+      if (g.tid() == 0) wj[ld + 1] = alpha;
     }
     g.sync();
-    QM_PFOR(g, idx, (m - k) * (n - k)) {
+    QM_PFOR(g, idx, rows * (n - k)) {
       const int i = k + idx / (n - k), j = k + 1 + idx % (n - k);
       A[i * ld + j] -= vh[i] * wj[j];
     }
-    if (g.tid() == 0) A[k * ld + k] = wj[ld + 1];
-    QM_PFOR(g, i, m - k - 1) A[(k + 1 + i) * ld + k] = 0.0;
+    QM_PFOR(g, i, rows) A[(k + i) * ld + k] = (i == 0) ? wj[ld + 1] : 0.0;
     g.sync();
   }
 }
@@ -487,9 +496,10 @@ QM_HD void back_substitute(const double* A, int n, int ld, double* z) {
 
 // Orthonormal basis of the kernel of Abar (r x n, row major ld_a): Householder QR with column pivoting of Abar' (n x r).
 // Q (n x n) is formed explicitly in Qm; the kernel basis is its last n - rank columns. Returns rank via *rank_out.
+// Same phase structure as householder_ls: inner products split over four row / column chunks, then rank-one updates.
 template <class G>
 QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double* T, double* Qm, double* vh, double* cn, int* perm,
-                         int* rank_out) {
+                         int* rank_out, double* hp) {
   // T = Abar' (n x r), ld = r
   QM_PFOR(g, idx, n * r) { const int i = idx / r, j = idx % r; T[i * r + j] = Abar[j * ld_a + i]; }
   QM_PFOR(g, idx, n * n) Qm[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
@@ -498,15 +508,24 @@ QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double
   int rank = 0;
   double first = 0.0;
   for (int k = 0; k < steps; ++k) {
-    QM_PFOR(g, j, r - k) {
-      double s = 0.0;
-      for (int i = k; i < n; ++i) s += T[i * r + k + j] * T[i * r + k + j];
-      cn[k + j] = s;
+    const int rows = n - k, cols = r - k;
+    const int chunk = (rows + HH_PARTS - 1) / HH_PARTS;
+    QM_PFOR(g, idx, HH_PARTS * cols) {                       // squared norms of the remaining columns, four row chunks each
+      const int part = idx / cols, j = k + idx - part * cols;
+      const int i0 = k + part * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
+      double sp = 0.0;
+      for (int i = i0; i < i1; ++i) sp += T[i * r + j] * T[i * r + j];
+      hp[part * HH_LD + (j - k)] = sp;
     }
     g.sync();
     if (g.tid() == 0) {
       int best = k;
-      for (int j = k + 1; j < r; ++j) if (cn[j] > cn[best]) best = j;
+      double bv = -1.0;
+      for (int j = k; j < r; ++j) {
+        const double v = (hp[j - k] + hp[HH_LD + j - k]) + (hp[2 * HH_LD + j - k] + hp[3 * HH_LD + j - k]);
+        cn[j] = v;
+        if (v > bv) { bv = v; best = j; }
+      }
       perm[0] = best;
     }
     g.sync();
@@ -526,21 +545,29 @@ QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double
     const double vk = akk - alpha;
     const double vv = nrm2 - akk * akk + vk * vk;
     const double beta = (vv > 0.0) ? 2.0 / vv : 0.0;
-    QM_PFOR(g, i, n - k) vh[k + i] = (i == 0) ? vk : T[(k + i) * r + k];
+    QM_PFOR(g, i, rows) vh[k + i] = (i == 0) ? vk : T[(k + i) * r + k];
+    g.sync();
+    // s_j = v'T_j (columns k..r-1) and q_i = Q[i, k:] v (all rows), each split over four chunks of the reflector
+    QM_PFOR(g, idx, HH_PARTS * (cols + n)) {
+      const int part = idx / (cols + n), it = idx - part * (cols + n);
+      const int i0 = k + part * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
+      double sp = 0.0;
+      if (it < cols) { const int j = k + it; for (int i = i0; i < i1; ++i) sp += vh[i] * T[i * r + j]; }
+      else { const int row = it - cols; for (int c = i0; c < i1; ++c) sp += Qm[row * n + c] * vh[c]; }
+      hp[part * HH_LD + it] = sp;
+    }
     g.sync();
     // T <- H T (columns k..r-1),  Q <- Q H (all rows)
-    QM_PFOR(g, jj, r - k) {
-      const int j = k + jj;
-      double s = 0.0;
-      for (int i = k; i < n; ++i) s += vh[i] * T[i * r + j];
-      s *= beta;
-      for (int i = k; i < n; ++i) T[i * r + j] -= vh[i] * s;
+    QM_PFOR(g, idx, rows * cols) {
+      const int i = k + idx / cols, jj = idx % cols;
+      const double sj = beta * ((hp[jj] + hp[HH_LD + jj]) + (hp[2 * HH_LD + jj] + hp[3 * HH_LD + jj]));
+      T[i * r + k + jj] -= vh[i] * sj;
     }
-    QM_PFOR(g, i, n) {
-      double s = 0.0;
-      for (int c = k; c < n; ++c) s += Qm[i * n + c] * vh[c];
-      s *= beta;
-      for (int c = k; c < n; ++c) Qm[i * n + c] -= s * vh[c];
+    QM_PFOR(g, idx, n * rows) {
+      const int i = idx / rows, c = k + idx % rows;
+      const int it = cols + i;
+      const double qi = beta * ((hp[it] + hp[HH_LD + it]) + (hp[2 * HH_LD + it] + hp[3 * HH_LD + it]));
+      Qm[i * n + c] -= qi * vh[c];
     }
     g.sync();
   }
@@ -576,8 +603,9 @@ QM_HDN void wbc_level0(G g, double* W, int* WI) {
       else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
       QR[idx] = v;
     }
-    g.sync();
-    householder_ls(g, QR, m, 36, ld, W + WS_VH, W + WS_WJ);
+    g.sync(); QM_TICK(35);
+    householder_ls(g, QR, m, 36, ld, W + WS_VH, W + WS_WJ, W + WS_HP);
+    QM_TICK(36);
     if (g.tid() == 0) back_substitute(QR, 36, ld, W + WW_X);
     g.sync();
     QM_PFOR(g, i, nD0) {
@@ -597,7 +625,7 @@ QM_HDN void wbc_level0(G g, double* W, int* WI) {
       WI[WI_SC + 10] = (changed == 0);
       if (changed && iter == 39) WI[WI_SC + 6] |= WST_QP_MAX_ITER;
     }
-    g.sync();
+    g.sync(); QM_TICK(37);
     if (WI[WI_SC + 10]) break;
   }
   QM_PFOR(g, i, 56) W[WW_V0 + i] = (i < nD0 && W[WS_RES + i] > 0.0) ? W[WS_RES + i] : 0.0;
@@ -613,6 +641,7 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
   double* J = W + WS_J;
   double* RF = W + WS_RF;
   int* act = WI + WI_ACT;
+  int* ina = WI + WI_INW;          // [56] row is in the active set (the level-0 flags of this name are dead by now)
   double* u = W + WS_U;
   double* z = W + WS_Z;
   double* d = W + WS_D;
@@ -620,27 +649,25 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
   double* zd = W + WS_ZD;
   double* np = W + WS_NP;
   double* sc = W + WS_CN;
+  double* viol = W + WS_VH;        // [56] scaled violation of the candidate rows (the Householder vector storage is idle here)
   int total = 0;
+  QM_PFOR(w0, i, 56) ina[i] = 0;
+  w0.sync();
   for (int outer = 0; outer < 200; ++outer) {
-    // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible)
+    // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible) and the scaled violation of every row that may enter
     QM_PFOR(w0, i, nD0) {
       double s = W[WS_Gg + i];
       for (int c = 0; c < n; ++c) s -= W[WS_GG + 18 * i + c] * z[c];
       W[WS_RES + i] = s;
+      const double v = s / (1.0 + fabs(W[WS_Gg + i]));
+      viol[i] = (WI[WI_IGN + i] || ina[i] || !(v < -1e-9)) ? 0.0 : v;
     }
     w0.sync();
     if (w0.tid() == 0) {
       const int iq = WI[WI_SC + 4];
       int ip = -1;
       double worst = 0.0;
-      for (int i = 0; i < nD0; ++i) {
-        if (WI[WI_IGN + i]) continue;
-        bool is_act = false;
-        for (int k = 0; k < iq; ++k) if (act[k] == i) { is_act = true; break; }
-        if (is_act) continue;
-        const double viol = W[WS_RES + i] / (1.0 + fabs(W[WS_Gg + i]));
-        if (viol < -1e-9 && viol < worst) { worst = viol; ip = i; }
-      }
+      for (int i = 0; i < nD0; ++i) if (viol[i] < worst) { worst = viol[i]; ip = i; }     // most violated row; first one on ties
       WI[WI_SC + 5] = ip;
       if (ip >= 0) { u[iq] = 0.0; sc[GI_CIP] = W[WS_RES + ip]; }
     }
@@ -683,13 +710,20 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
           action = (t == t2) ? 0 : 1;
           WI[GI_L + WI_SC] = l;
           if (action == 0) {
-            // Givens rotations that zero d[iq+1..n-1] (bottom up); coefficients for the row-parallel update of J
-            for (int j = n - 1; j > iq; --j) {
-              const double a = d[j - 1], b2 = d[j];
-              double cs = 1.0, sn = 0.0;
-              if (b2 != 0.0) { const double h = hypot(a, b2); cs = a / h; sn = b2 / h; d[j - 1] = h; d[j] = 0.0; }
-              sc[GI_CS + j] = cs; sc[GI_SN + j] = sn;
+            // One Householder reflection H = I - beta v v' with H d[iq:] = alpha e1 (instead of a chain of n - iq - 1 Givens
+            // rotations, each waiting for the previous one's hypot): v = d[iq:] - alpha e1 stays in d[iq:], the new column of
+            // the triangular factor is [d[:iq]; alpha]. sc[GI_CS] = beta (0: nothing to reflect), sc[GI_CS + 1] = alpha.
+            double tail = 0.0;
+            for (int c = iq + 1; c < n; ++c) tail += d[c] * d[c];
+            double beta = 0.0, alpha = d[iq];
+            if (tail > 0.0) {
+              const double nrm = sqrt(dn2);
+              alpha = (d[iq] >= 0.0) ? -nrm : nrm;
+              const double v0 = d[iq] - alpha;
+              beta = 2.0 / (tail + v0 * v0);
+              d[iq] = v0;
             }
+            sc[GI_CS] = beta; sc[GI_CS + 1] = alpha;
           }
         }
         WI[WI_SC + GI_ACTION] = action;
@@ -703,23 +737,25 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
       if (w0.tid() == 0) u[iq] += t;
       w0.sync();
       if (action == 0) {
-        // add constraint ip
-        QM_PFOR(w0, i, n) {
-          for (int j = n - 1; j > iq; --j) {
-            const double cs = sc[GI_CS + j], sn = sc[GI_SN + j];
-            const double x1 = J[i * 18 + j - 1], x2 = J[i * 18 + j];
-            J[i * 18 + j - 1] = cs * x1 + sn * x2;
-            J[i * 18 + j] = -sn * x1 + cs * x2;
+        // add constraint ip: J[:, iq:] <- J[:, iq:] H (row-parallel), new column of RF
+        const double beta = sc[GI_CS], alpha = sc[GI_CS + 1];
+        if (beta != 0.0) {
+          QM_PFOR(w0, i, n) {
+            double sdot = 0.0;
+            for (int c = iq; c < n; ++c) sdot += J[i * 18 + c] * d[c];
+            sdot *= beta;
+            for (int c = iq; c < n; ++c) J[i * 18 + c] -= sdot * d[c];
           }
         }
-        QM_PFOR(w0, i, iq + 1) RF[i * 18 + iq] = d[i];
-        if (w0.tid() == 0) { act[iq] = ip; WI[WI_SC + 4] = iq + 1; }
+        QM_PFOR(w0, i, iq) RF[i * 18 + iq] = d[i];
+        if (w0.tid() == 0) { RF[iq * 18 + iq] = alpha; act[iq] = ip; ina[ip] = 1; WI[WI_SC + 4] = iq + 1; }
         w0.sync();
         break;
       }
       // drop constraint l and continue with the same ip
       const int l = WI[WI_SC + GI_L];
       if (w0.tid() == 0) {
+        ina[act[l]] = 0;
         for (int k = l; k < iq - 1; ++k) {
           act[k] = act[k + 1]; u[k] = u[k + 1];
           for (int i = 0; i <= k + 1; ++i) RF[i * 18 + k] = RF[i * 18 + k + 1];
@@ -784,7 +820,7 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
     QR[idx] = v;
   }
   g.sync();
-  householder_ls(g, QR, m, n, ld, W + WS_VH, W + WS_WJ);
+  householder_ls(g, QR, m, n, ld, W + WS_VH, W + WS_WJ, W + WS_HP);
   if (g.tid() == 0) back_substitute(QR, n, ld, W + WS_Z);
   // J = R^-1 (upper triangular), column by column
   QM_PFOR(g, c, n) {
@@ -800,8 +836,9 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
   g.sync();
   // The active-set iteration is a dependency chain: it runs on the narrow group (one warp) with lane-parallel vector
   // operations (J' n, J2 d2, row-wise Givens updates of J) and lane-0 scalar decisions; the rest of the CTA waits.
+  QM_TICK(40);
   if (g.narrow_active()) gi_iterate(g.narrow(), n, nD0, W, WI);
-  g.sync();
+  g.sync(); QM_TICK(41);
 }
 
 // HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
@@ -812,10 +849,11 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
   g.sync();
   // ---- level 0
   wbc_level0(g, W, WI);
-  kernel_basis(g, W + WW_A0, 18, 36, 36, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1);
+  QM_TICK(-1);
+  kernel_basis(g, W + WW_A0, 18, 36, 36, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, W + WS_HP);
   const int n1 = 36 - WI[WI_SC + 1];
   QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + (36 - n1) + c] : 0.0; }
-  g.sync();
+  g.sync(); QM_TICK(38);
   // ---- level 1 in the coordinates x = x0 + Z0 z
   int n2 = 0;
   if (n1 > 0) {
@@ -841,7 +879,7 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
       for (int k = 0; k < 36; ++k) s -= W[WW_D0 + 36 * i + k] * W[WW_X + k];
       W[WS_Gg + i] = s;
     }
-    g.sync();
+    g.sync(); QM_TICK(39);
     wbc_gi(g, n1, r1, nD0, W, WI);
     QM_PFOR(g, k, 36) {
       double s = 0.0;
@@ -850,7 +888,7 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
     }
     g.sync();
     // kernel of A1 Z0 -> Z1 = Z0 N1
-    kernel_basis(g, W + WS_GA, r1, n1, 18, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1);
+    kernel_basis(g, W + WS_GA, r1, n1, 18, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, W + WS_HP);
     n2 = n1 - WI[WI_SC + 1];
     if (n2 > 12) n2 = 12;
     QM_PFOR(g, idx, 36 * 12) {
@@ -859,7 +897,7 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
       if (c < n2) for (int k = 0; k < n1; ++k) s += W[WW_Z0 + 18 * i + k] * W[WS_Q + n1 * k + (n1 - n2) + c];
       W[WW_Z1 + idx] = s;
     }
-    g.sync();
+    g.sync(); QM_TICK(42);
   }
   // ---- level 2 in the coordinates x = x1 + Z1 z
   if (n2 > 0) {
@@ -885,7 +923,7 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
       for (int k = 0; k < 36; ++k) s -= W[WW_D0 + 36 * i + k] * W[WW_X + k];
       W[WS_Gg + i] = s;
     }
-    g.sync();
+    g.sync(); QM_TICK(43);
     wbc_gi(g, n2, r2, nD0, W, WI);
     QM_PFOR(g, k, 36) {
       double s = 0.0;
@@ -918,9 +956,13 @@ template <class G>
 QM_HDN void wbc_update(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* xd, const double* ud,
                        const double* rbd, int mode, double period, double time, const double* u_last, double* W, int* WI,
                        double* cmd, int* status) {
+  QM_TICK(-1);
   wbc_dynamics(g, M, C, rbd, xd, ud, u_last, period, W);
+  QM_TICK(33);
   wbc_tasks(g, M, C, ud, mode & 15, time, W, WI);
+  QM_TICK(34);
   wbc_solve(g, W, WI, cmd, status);
+  QM_TICK(45);
 }
 
 }  // namespace qm

@@ -929,8 +929,8 @@ int qmb200_wait_stream(qmb200_ctx* c, void* stream) {
 #if defined(QM_PHASE_TIMING)
 int qmb200_debug_ticks(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, qm::qm_dbg, sizeof(unsigned long long) * 32);
-  if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(qm::qm_dbg, z, sizeof(z)); }
+  cudaMemcpyFromSymbol(out, qm::qm_dbg, sizeof(unsigned long long) * 64);
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(qm::qm_dbg, z, sizeof(z)); }
   return 0;
 }
 #endif

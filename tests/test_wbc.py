@@ -85,7 +85,7 @@ def test_cport_matches_golden(descs):
         w = q.load_wbc(model)
         w.mpc_variant = variant
         cmd, st = abi_fill.cport_wbc(model, w, xd, ud, rbd, mode, period, time, ul.copy())
-        assert (st == 0).all(), st
+        assert ((st & ~2) == 0).all(), st          # WST_DEGENERATE (2) is informational: a dependent inherited row was skipped
         return cmd
     assert check_golden(run_backend(update, g), g, TOL) < TOL
 
@@ -122,7 +122,7 @@ def test_cuda_matches_golden(descs):
         ctx = q.WbcContext(model, w, len(idx))
         ctx.update(xd, ul, rbd, mode, period, time)          # warm-up call installs inputLast_ = u_last
         cmd, st = ctx.update(xd, ud, rbd, mode, period, time)
-        assert (st == 0).all(), st
+        assert ((st & ~2) == 0).all(), st          # WST_DEGENERATE (2) is informational: a dependent inherited row was skipped
         ctx.close()
         return cmd
     assert check_golden(run_backend(update, g), g, TOL) < TOL
