@@ -444,18 +444,22 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
 // over four row chunks; (b) the reflector's scalars and w = beta v'A per column, the reflector itself copied aside;
 // (c) the rank-one update. No phase has a serial loop longer than a quarter of a column.
 enum { HH_PARTS = 4, HH_LD = 56 };
+// dense: the rows below `dense` are sqrt(eps) e_c' (the regularisation block of HoQp.cpp:66, zero right-hand side): row
+// dense + c is untouched until step c, so step k only involves the rows k .. dense + k (the others hold exact zeros in the
+// columns k..n and their reflector entry is zero).
 template <class G>
-QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj, double* hp) {
+QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj, double* hp, int dense) {
   const int steps = (m - 1 < n) ? m - 1 : n;
   for (int k = 0; k < steps; ++k) {
-    const int rows = m - k, cols = n - k + 1;                 // columns k..n (rhs included); column k gives the norm
+    const int mk = (dense + k + 1 < m) ? dense + k + 1 : m;   // one past the last row step k touches
+    const int rows = mk - k, cols = n - k + 1;                // columns k..n (rhs included); column k gives the norm
     const int chunk = (rows + HH_PARTS - 1) / HH_PARTS;
-    QM_PFOR(g, idx, HH_PARTS * cols) {
-      const int part = idx / cols, j = k + idx - part * cols;
-      const int i0 = k + part * chunk, i1 = (i0 + chunk < m) ? i0 + chunk : m;
+    QM_PFOR2(g, part, HH_PARTS, jj, cols) {
+      const int j = k + jj;
+      const int i0 = k + part * chunk, i1 = (i0 + chunk < mk) ? i0 + chunk : mk;
       double sp = 0.0;
       for (int i = i0; i < i1; ++i) sp += A[i * ld + k] * A[i * ld + j];
-      hp[part * HH_LD + (j - k)] = sp;
+      hp[part * HH_LD + jj] = sp;
     }
     g.sync();
     {
@@ -475,8 +479,8 @@ QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
       if (g.tid() == 0) wj[ld + 1] = alpha;
     }
     g.sync();
-    QM_PFOR(g, idx, rows * (n - k)) {
-      const int i = k + idx / (n - k), j = k + 1 + idx % (n - k);
+    QM_PFOR2(g, ii, rows, jj, n - k) {                      // rows over the warps, columns over the lanes: no index division
+      const int i = k + ii, j = k + 1 + jj;
       A[i * ld + j] -= vh[i] * wj[j];
     }
     QM_PFOR(g, i, rows) A[(k + i) * ld + k] = (i == 0) ? wj[ld + 1] : 0.0;
@@ -484,13 +488,16 @@ QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
   }
 }
 
-// back substitution R z = c (R n x n upper in A, c = A[:, n]); one thread
-QM_HD void back_substitute(const double* A, int n, int ld, double* z) {
+// back substitution R z = c (R n x n upper in A, c = A[:, n], overwritten), column oriented on one narrow group: z_i is formed
+// by one lane, the others remove its contribution from the rows above.
+template <class G>
+QM_HDN void back_substitute(G w0, double* A, int n, int ld, double* z) {
   for (int i = n - 1; i >= 0; --i) {
-    double s = A[i * ld + n];
-    for (int j = i + 1; j < n; ++j) s -= A[i * ld + j] * z[j];
-    const double d = A[i * ld + i];
-    z[i] = (d != 0.0) ? s / d : 0.0;
+    if (w0.tid() == 0) { const double d = A[i * ld + i]; z[i] = (d != 0.0) ? A[i * ld + n] / d : 0.0; }
+    w0.sync();
+    const double zi = z[i];
+    QM_PFOR(w0, j, i) A[j * ld + n] -= A[j * ld + i] * zi;
+    w0.sync();
   }
 }
 
@@ -510,12 +517,12 @@ QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double
   for (int k = 0; k < steps; ++k) {
     const int rows = n - k, cols = r - k;
     const int chunk = (rows + HH_PARTS - 1) / HH_PARTS;
-    QM_PFOR(g, idx, HH_PARTS * cols) {                       // squared norms of the remaining columns, four row chunks each
-      const int part = idx / cols, j = k + idx - part * cols;
+    QM_PFOR2(g, part, HH_PARTS, jj, cols) {                   // squared norms of the remaining columns, four row chunks each
+      const int j = k + jj;
       const int i0 = k + part * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
       double sp = 0.0;
       for (int i = i0; i < i1; ++i) sp += T[i * r + j] * T[i * r + j];
-      hp[part * HH_LD + (j - k)] = sp;
+      hp[part * HH_LD + jj] = sp;
     }
     g.sync();
     if (g.tid() == 0) {
@@ -548,8 +555,7 @@ QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double
     QM_PFOR(g, i, rows) vh[k + i] = (i == 0) ? vk : T[(k + i) * r + k];
     g.sync();
     // s_j = v'T_j (columns k..r-1) and q_i = Q[i, k:] v (all rows), each split over four chunks of the reflector
-    QM_PFOR(g, idx, HH_PARTS * (cols + n)) {
-      const int part = idx / (cols + n), it = idx - part * (cols + n);
+    QM_PFOR2(g, part, HH_PARTS, it, cols + n) {
       const int i0 = k + part * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
       double sp = 0.0;
       if (it < cols) { const int j = k + it; for (int i = i0; i < i1; ++i) sp += vh[i] * T[i * r + j]; }
@@ -558,16 +564,14 @@ QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double
     }
     g.sync();
     // T <- H T (columns k..r-1),  Q <- Q H (all rows)
-    QM_PFOR(g, idx, rows * cols) {
-      const int i = k + idx / cols, jj = idx % cols;
+    QM_PFOR2(g, ii, rows, jj, cols) {
       const double sj = beta * ((hp[jj] + hp[HH_LD + jj]) + (hp[2 * HH_LD + jj] + hp[3 * HH_LD + jj]));
-      T[i * r + k + jj] -= vh[i] * sj;
+      T[(k + ii) * r + k + jj] -= vh[k + ii] * sj;
     }
-    QM_PFOR(g, idx, n * rows) {
-      const int i = idx / rows, c = k + idx % rows;
+    QM_PFOR2(g, i, n, cc, rows) {
       const int it = cols + i;
       const double qi = beta * ((hp[it] + hp[HH_LD + it]) + (hp[2 * HH_LD + it] + hp[3 * HH_LD + it]));
-      Qm[i * n + c] -= qi * vh[c];
+      Qm[i * n + k + cc] -= qi * vh[k + cc];
     }
     g.sync();
   }
@@ -604,9 +608,9 @@ QM_HDN void wbc_level0(G g, double* W, int* WI) {
       QR[idx] = v;
     }
     g.sync(); QM_TICK(35);
-    householder_ls(g, QR, m, 36, ld, W + WS_VH, W + WS_WJ, W + WS_HP);
+    householder_ls(g, QR, m, 36, ld, W + WS_VH, W + WS_WJ, W + WS_HP, nw + 18);
     QM_TICK(36);
-    if (g.tid() == 0) back_substitute(QR, 36, ld, W + WW_X);
+    if (g.narrow_active()) back_substitute(g.narrow(), QR, 36, ld, W + WW_X);
     g.sync();
     QM_PFOR(g, i, nD0) {
       double s = -W[WW_F0 + i];
@@ -709,22 +713,6 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
           WI[WI_SC + 14] = (t2 < 1e300);                   // primal step exists
           action = (t == t2) ? 0 : 1;
           WI[GI_L + WI_SC] = l;
-          if (action == 0) {
-            // One Householder reflection H = I - beta v v' with H d[iq:] = alpha e1 (instead of a chain of n - iq - 1 Givens
-            // rotations, each waiting for the previous one's hypot): v = d[iq:] - alpha e1 stays in d[iq:], the new column of
-            // the triangular factor is [d[:iq]; alpha]. sc[GI_CS] = beta (0: nothing to reflect), sc[GI_CS + 1] = alpha.
-            double tail = 0.0;
-            for (int c = iq + 1; c < n; ++c) tail += d[c] * d[c];
-            double beta = 0.0, alpha = d[iq];
-            if (tail > 0.0) {
-              const double nrm = sqrt(dn2);
-              alpha = (d[iq] >= 0.0) ? -nrm : nrm;
-              const double v0 = d[iq] - alpha;
-              beta = 2.0 / (tail + v0 * v0);
-              d[iq] = v0;
-            }
-            sc[GI_CS] = beta; sc[GI_CS + 1] = alpha;
-          }
         }
         WI[WI_SC + GI_ACTION] = action;
       }
@@ -737,18 +725,36 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
       if (w0.tid() == 0) u[iq] += t;
       w0.sync();
       if (action == 0) {
-        // add constraint ip: J[:, iq:] <- J[:, iq:] H (row-parallel), new column of RF
-        const double beta = sc[GI_CS], alpha = sc[GI_CS + 1];
-        if (beta != 0.0) {
-          QM_PFOR(w0, i, n) {
-            double sdot = 0.0;
-            for (int c = iq; c < n; ++c) sdot += J[i * 18 + c] * d[c];
-            sdot *= beta;
-            for (int c = iq; c < n; ++c) J[i * 18 + c] -= sdot * d[c];
+        // add constraint ip: Givens rotations that zero d[iq+1..n-1] bottom up. The value a rotation leaves in d[j-1] is the norm
+        // of the tail d[j-1..], so all coefficients follow from the suffix sums of squares, formed by the lanes in parallel
+        // (the sequential form is a chain of n - iq - 1 hypot calls on one lane).
+        QM_PFOR(w0, j, n) {
+          if (j >= iq) { double sfx = 0.0; for (int c = n - 1; c >= j; --c) sfx += d[c] * d[c]; rr[j] = sfx; }
+        }
+        w0.sync();
+        QM_PFOR(w0, j, n) {
+          if (j > iq) {
+            // value at position j when its rotation is formed: the tail norm, or d[j] itself if nothing below it was non-zero
+            const double b2 = (j + 1 < n && rr[j + 1] != 0.0) ? sqrt(rr[j]) : d[j];
+            double cs = 1.0, sn = 0.0;
+            if (b2 != 0.0) { const double h = sqrt(rr[j - 1]); cs = d[j - 1] / h; sn = b2 / h; }
+            sc[GI_CS + j] = cs; sc[GI_SN + j] = sn;
+          }
+        }
+        w0.sync();
+        QM_PFOR(w0, i, n) {
+          for (int j = n - 1; j > iq; --j) {
+            const double cs = sc[GI_CS + j], sn = sc[GI_SN + j];
+            const double x1 = J[i * 18 + j - 1], x2 = J[i * 18 + j];
+            J[i * 18 + j - 1] = cs * x1 + sn * x2;
+            J[i * 18 + j] = -sn * x1 + cs * x2;
           }
         }
         QM_PFOR(w0, i, iq) RF[i * 18 + iq] = d[i];
-        if (w0.tid() == 0) { RF[iq * 18 + iq] = alpha; act[iq] = ip; ina[ip] = 1; WI[WI_SC + 4] = iq + 1; }
+        if (w0.tid() == 0) {
+          RF[iq * 18 + iq] = (iq + 1 < n && rr[iq + 1] != 0.0) ? sqrt(rr[iq]) : d[iq];
+          act[iq] = ip; ina[ip] = 1; WI[WI_SC + 4] = iq + 1;
+        }
         w0.sync();
         break;
       }
@@ -820,8 +826,8 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
     QR[idx] = v;
   }
   g.sync();
-  householder_ls(g, QR, m, n, ld, W + WS_VH, W + WS_WJ, W + WS_HP);
-  if (g.tid() == 0) back_substitute(QR, n, ld, W + WS_Z);
+  householder_ls(g, QR, m, n, ld, W + WS_VH, W + WS_WJ, W + WS_HP, r);
+  if (g.narrow_active()) back_substitute(g.narrow(), QR, n, ld, W + WS_Z);
   // J = R^-1 (upper triangular), column by column
   QM_PFOR(g, c, n) {
     for (int i = n - 1; i >= 0; --i) {
