@@ -30,14 +30,59 @@ HORIZON, DT = 1.0, 0.01
 CYCLE_DT = 0.01
 
 
-def workload_config(n_gpus):
-    return {"workload": "config 2: AlienGo+Z1 nx=30 nu=30, horizon 1.0 s / dt 0.01 s (N=100 + gait-event nodes), trot, "
-                        "batch=1024 independent perturbed initial states per GPU, warm start, t0 += 0.01 s per step, "
-                        "1 SQP iteration + filter line search per cycle",
-            "batch_per_gpu": BATCH_PER_GPU, "horizon_s": HORIZON, "dt_s": DT, "gait": "trot",
-            "parallelism": "independent problems sharded across %d GPU(s)%s" % (
-                n_gpus, ", one NCCL all-gather of the policy per cycle" if n_gpus > 1 else ""),
-            "l2_policy": "working set per step (6.6 GB of LQ and kinematics blocks) is larger than the 126 MB L2; no explicit flush"}
+GAIT_LIBRARY = ["trot", "standing_trot", "flying_trot", "pace", "standing_pace", "dynamic_walk", "static_walk", "amble",
+                "lindyhop", "skipping", "pawup"]          # the 11 moving gaits of gait.info (all but stance)
+CONFIG4_SEEDS = 512
+
+
+def workload_config(n_gpus, mode="config2", scaling="weak", batch=BATCH_PER_GPU):
+    par = "independent problems sharded across %d GPU(s)%s" % (
+        n_gpus, ", one NCCL all-gather of the policy per cycle (qmb200_allgather_policy, beside the next cycle)" if n_gpus > 1 else "")
+    l2 = "working set per step (6.4 MB of LQ and kinematics blocks per problem) is far larger than the 126 MB L2; no explicit flush"
+    if mode == "config4":
+        return {"workload": "config 4: gait library, 11 gait schedules x 512 disturbance seeds = 5632 problems (config-2 perturbation + "
+                            "base momentum kick U(-0.3, 0.3)), N=100, sharded over the GPUs by interleaved (seed, gait) index, warm start, "
+                            "t0 += 0.01 s per step, 1 SQP iteration + filter line search per cycle",
+                "batch_total": len(GAIT_LIBRARY) * CONFIG4_SEEDS, "batch_per_gpu": batch, "horizon_s": HORIZON, "dt_s": DT,
+                "gait": "library of 11", "parallelism": par, "l2_policy": l2}
+    w = "config 2: AlienGo+Z1 nx=30 nu=30, horizon 1.0 s / dt 0.01 s (N=100 + gait-event nodes), trot, "
+    if scaling == "strong":
+        w += "batch=1024 independent perturbed initial states IN TOTAL (%d per GPU), " % batch
+    else:
+        w += "batch=1024 independent perturbed initial states per GPU, "
+    w += "warm start, t0 += 0.01 s per step, 1 SQP iteration + filter line search per cycle"
+    return {"workload": w, "batch_per_gpu": batch, "horizon_s": HORIZON, "dt_s": DT, "gait": "trot", "parallelism": par, "l2_policy": l2}
+
+
+def make_workload(args, rank, world, total_steps):
+    """The rank's shard of the synthetic workload (SURVEY.md 8(d)). config2 weak: 1024 problems per GPU (seed + rank);
+    config2 strong: 1024 problems in total; config4: 5632 problems in total (11 gaits x 512 seeds)."""
+    import qm_door_b200 as q
+    from qm_door_b200 import distributed as D, workload
+    t_span = CYCLE_DT * (2 * total_steps + 4)
+    if args.workload == "config4":
+        total = len(GAIT_LIBRARY) * CONFIG4_SEEDS
+        lo, hi = D.shard_range(total, rank, world)
+        W = workload.Workload(total, horizon=HORIZON, dt=DT, seed=20261019, t_span=t_span, max_events=64, max_nodes=int(round(HORIZON / DT)) + 1 + 32)
+        rng = np.random.default_rng(20261019)
+        W.x0[:, 0:6] += rng.uniform(-0.3, 0.3, (total, 6))                    # external base momentum kick
+        gaits = [q.load_gait(g) for g in GAIT_LIBRARY]
+        for b in range(lo, hi):
+            sw, md = gaits[b % len(GAIT_LIBRARY)]                             # interleaved: every rank sees a mix of gaits
+            W.events[b], W.modes[b], W.nevents[b] = q.tile_schedule(sw, md, -np.ceil(HORIZON / sw[-1]) * sw[-1] - W.phase[b],
+                                                                    t_span + 2.0 * HORIZON, 64)
+        for k in ("x0", "events", "modes", "nevents", "target_t", "target_x", "phase"):
+            setattr(W, k, np.ascontiguousarray(getattr(W, k)[lo:hi]))
+        W.B = hi - lo
+        return W
+    if args.scaling == "strong":
+        lo, hi = D.shard_range(BATCH_PER_GPU, rank, world)
+        W = workload.Workload(BATCH_PER_GPU, horizon=HORIZON, dt=DT, seed=20261017, t_span=t_span)
+        for k in ("x0", "events", "modes", "nevents", "target_t", "target_x", "phase"):
+            setattr(W, k, np.ascontiguousarray(getattr(W, k)[lo:hi]))
+        W.B = hi - lo
+        return W
+    return workload.Workload(BATCH_PER_GPU, horizon=HORIZON, dt=DT, seed=20261017 + rank, t_span=t_span)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -264,9 +309,9 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = BATCH_PER_GPU
-    total_steps = args.steps + args.warmup
-    W = workload.Workload(B, horizon=HORIZON, dt=DT, seed=20261017 + rank, t_span=CYCLE_DT * (2 * total_steps + 4))
+    total_steps = 3 * (args.steps + args.warmup)             # timed + profiled pass + the two end-to-end loops share the schedule
+    W = make_workload(args, rank, world, total_steps)
+    B = W.B
     ctx = q.MpcContext(W.model, W.problem, W.solver, B, device=local_rank)
     NMAX = W.solver.max_nodes
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
@@ -432,11 +477,13 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
             wbc_line["cpu_baseline"] = wbc_cpu_baseline(WW)
 
     times = torch.tensor([dev_ms, e2e_s * 1e3, e2e_serial_s * 1e3, prof_ms], dtype=f64, device=dev)
+    counts = torch.tensor([B], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms, e2e_serial_ms, prof_ms = (float(v) for v in times.tolist())
     if rank == 0:
-        total = B * world
+        total = int(counts.sum().item())
         value = total * args.steps / (dev_ms * 1e-3)
         e2e = total * args.steps / (e2e_ms * 1e-3)
         # dominant kernel roofline: algorithmic bytes of the nodes actually processed / mean launch time of that kernel
@@ -474,8 +521,9 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
                                    "not in MEASURED_PEAKS.json"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if (args.scaling == "strong" or args.workload == "config4") else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world, args.workload, args.scaling, B), "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.steps, "failed_problems": e2e_bad,
                     "api": "qmb200_mpc_cycle_batch_async + qmb200_mpc_cycle_wait, two pinned host buffer sets: copy-out of cycle k "
@@ -501,7 +549,7 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
         }
         if wbc_line is not None:
             line["secondary"] = wbc_line
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "config2":
             line["cpu_baseline"] = cpu_baseline_sample()
         if world == 1 and not args.no_latency:
             line["latency"] = gpu_latency_legs(q, workload, local_rank)
@@ -524,6 +572,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wbc", action="store_true", help="skip the secondary WBC-solves/s measurement")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-problem latency legs")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
+                    help="config2 (default, BASELINE metric): trot, 1024 problems; config4: 11 gaits x 512 seeds = 5632 problems in total")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="config2 only: weak = 1024 problems per GPU (default), strong = 1024 problems in total")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -536,7 +588,8 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr",
                "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__), "--gpus",
-               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+               str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload, "--scaling", args.scaling] + (
+                   ["--no-cpu-baseline"] if args.no_cpu_baseline else []) + (["--no-wbc"] if args.no_wbc else []) + (["--no-latency"] if args.no_latency else [])
         raise SystemExit(subprocess.call(cmd))
     # stdout carries exactly one JSON line: libraries that write to file descriptor 1 while the bench runs (NCCL prints its
     # version banner there) are sent to stderr, the descriptor is restored for the result line
