@@ -133,9 +133,7 @@ def kernel_bytes_per_node(kernel, nut):
     as laid out in DESIGN.md section 2.
     stage = projected LQ block actually used (A 900, B 30 nut, b 30, q 30, r nut, 1 | Q 900, P 30 nut, R nut^2);
     proj  = compact projection block (pivot rows of Px / Pu, Pe, roles); gain = (K 30 nut, kff nut);
-    kin1 / kin2 = products of the two kinematics evaluations; piv = pivot-block inverse and index record (k_proj).
-    k_solve (backward Riccati sweep) reads the stage block and writes the gains; k_rollout (forward sweep) reads the forward part
-    of the stage block, the projection and the gains, reads dx0 and writes the step (dx, du)."""
+    kin1 / kin2 = products of the two kinematics evaluations; piv = pivot-block inverse and index record (k_proj)."""
     nv = 26 - nut
     fwd = 900 + 30 * nut + 30 + 30 + nut + 1
     stage = fwd + 900 + 30 * nut + nut * nut
@@ -145,7 +143,7 @@ def kernel_bytes_per_node(kernel, nut):
     kin2 = 540 + 30
     piv = nv * nv + 40
     d = {"k_kin1": 60 + kin1, "k_kin2": 60 + kin2, "k_proj": 18 * nv + piv, "k_lq": 90 + kin1 + kin2 + piv + stage + proj + 3,
-         "k_solve": stage + gain, "k_rollout": fwd + proj + gain + 60 + 60, "k_trial": 150 + 3}[kernel]
+         "k_solve": stage + gain + (fwd + proj + gain) + 60, "k_trial": 150 + 3}[kernel]
     return 8 * d
 
 
@@ -166,16 +164,15 @@ def kernel_flops_per_node(kernel, nut):
     """Algorithmic FP64 flops (2 per multiply-add) of the dense products a kernel carries out per intermediate node; the
     symmetric products are counted in full (what the recursion defines), index / barrier / reference arithmetic is not counted.
     k_solve: S A, S B, S b | G = R + B'SB, g | G^-1 (Gauss-Jordan, 2 nut^3) | H = P + B'SA, Q + A'SA, A'sb | K = -G^-1 H, kff |
-             S += H'K, s += H'kff.   k_rollout: K dx, A dx + B dut, projection rows.
+             S += H'K, s += H'kff | forward: K dx, A dx + B dut, projection rows.
     k_lq:    Dinv T | Heun sensitivities (9x9x60 products) | Gauss-Newton end-effector Hessian | change of variables
              (A + B Px, B Pu, R Px, R Pu, Q + Px'R Px, Pu'R Px, Pu'R Pu) with nv = 26 - nut pivot rows."""
     nv = 26 - nut
     if kernel == "k_solve":
         bwd = 2 * (27000 + 900 * nut + 900) + 2 * (30 * nut * nut + 30 * nut) + 2 * nut ** 3 + 2 * (900 * nut + 27000 + 900) \
             + 2 * (30 * nut * nut + nut * nut) + 2 * (900 * nut + 30 * nut)
-        return bwd
-    if kernel == "k_rollout":
-        return 2 * (30 * nut + 900 + 30 * nut + nv * (30 + nut) + 30 + nut)
+        fwd = 2 * (30 * nut + 900 + 30 * nut + nv * (30 + nut) + 30 + nut)
+        return bwd + fwd
     if kernel == "k_lq":
         nsel = nv + nut
         heun = 2 * (9 * 9 * 60) + 4 * 9 * 60
@@ -495,7 +492,7 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        modeled = ("k_kin1", "k_kin2", "k_lq", "k_solve", "k_rollout", "k_trial")
+        modeled = ("k_kin1", "k_kin2", "k_lq", "k_solve", "k_trial")
         dom = max(modeled, key=lambda kn: kt[kn][0])                 # dominant kernel by total time in the timed region
         ms_dom = kt[dom][0] / max(1, kt[dom][1])
         nodes_bytes = 0

@@ -50,7 +50,7 @@ enum {
 #define QMB200_INFO_SIZE 16   /* per-problem info record: alpha, done, armijo, |dx|, |du|, base(merit,dyn,eq), new(merit,dyn,eq), line-search
                                  trials, |x0 - x[0]|^2, SQP iterations carried out (13), why the SQP loop stopped (14: 1 iteration budget,
                                  2 step size, 3 metrics, 4 primal step; [upstream] SqpSolver::Convergence) */
-#define QMB200_NUM_KERNELS 14 /* schedule, init_guess, kin1, kin2, lq, solve, trial, decide, finalize, policy, proj, backtrack, step, rollout */
+#define QMB200_NUM_KERNELS 13 /* schedule, init_guess, kin1, kin2, lq, solve, trial, decide, finalize, policy, proj, backtrack, step */
 
 int qmb200_version(void);
 const char* qmb200_last_error(void);

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QMB200_LIB_PATH", os.path.join(_HERE, "libqmb200.so"))   # override: development builds only
 INFO_SIZE = 16
 KERNEL_NAMES = ["k_schedule", "k_init_guess", "k_kin1", "k_kin2", "k_lq", "k_solve", "k_trial", "k_decide", "k_finalize", "k_policy", "k_proj",
-                "k_backtrack", "k_step", "k_rollout"]
+                "k_backtrack", "k_step"]
 INFO = dict(alpha=0, done=1, armijo=2, dxnorm=3, dunorm=4, base_merit=5, base_dyn=6, base_eq=7,
             new_merit=8, new_dyn=9, new_eq=10, iters=11, dx0sq=12, sqp_iterations=13, convergence=14)
 

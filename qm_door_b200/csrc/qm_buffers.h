@@ -123,14 +123,18 @@ struct DirectFetch {
   }
 };
 
-// Backward Riccati sweep of one problem (serial in the nodes): gains to HBM. W: Riccati workspace (>= RW_SIZE doubles).
+// Backward Riccati sweep, forward rollout, step norms, baseline performance reduction.
+// W: Riccati workspace (>= RW_SIZE doubles); R: forward scratch (>= 96 doubles; may alias W when nothing is staged over it).
 template <class G, class F>
-QM_HDN void solve_backward(G g, F& fetch, const MpcBuffers& m, int b, double* W) {
+QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, double* R) {
   const int NMAX = m.NMAX;
   const int nn = m.nn[b];
   const int n = nn - 1;
   const double* stage = m.stage + (size_t)b * NMAX * SB_SIZE;
+  const double* proj = m.proj + (size_t)b * NMAX * PB_SIZE;
   double* gain = m.gain + (size_t)b * NMAX * GB_SIZE;
+  double* dxs = m.dxs + (size_t)b * NMAX * 30;
+  double* dus = m.dus + (size_t)b * NMAX * 30;
   const double* term = stage + (size_t)n * SB_SIZE;
   if (n > 0) fetch.bwd_request(g, stage + (size_t)(n - 1) * SB_SIZE);
   QM_PFOR(g, idx, 900) W[RW_S + idx] = term[SB_Q + idx];
@@ -144,26 +148,9 @@ QM_HDN void solve_backward(G g, F& fetch, const MpcBuffers& m, int b, double* W)
     if (k > 0) fetch.bwd_request(g, stage + (size_t)(k - 1) * SB_SIZE);      // stage buffer is free: prefetch
     riccati_stage_b(g, nut, W, gain + (size_t)k * GB_SIZE);
   }
+  // forward rollout: [0:30] dx, [30:48] dut, [48:78] dx next, [80] armijo
   fetch.publish(g);
   g.sync();
-}
-
-// Forward rollout of one problem with the gains of solve_backward, step norms, baseline performance reduction, line-search
-// record. R: forward scratch (>= 96 doubles); part: 2 nt + PF_SIZE NMAX doubles (partial sums, staged performance records).
-// The group may be a whole CTA (fused with the backward sweep) or one warp (k_rollout: every problem of the batch is resident at
-// once, the per-node chain of two small matrix-vector products is latency bound and needs no CTA).
-template <class G, class F>
-QM_HDN void solve_forward(G g, F& fetch, const MpcBuffers& m, int b, double* R, double* part) {
-  const int NMAX = m.NMAX;
-  const int nn = m.nn[b];
-  const int n = nn - 1;
-  const double* stage = m.stage + (size_t)b * NMAX * SB_SIZE;
-  const double* proj = m.proj + (size_t)b * NMAX * PB_SIZE;
-  const double* gain = m.gain + (size_t)b * NMAX * GB_SIZE;
-  double* dxs = m.dxs + (size_t)b * NMAX * 30;
-  double* dus = m.dus + (size_t)b * NMAX * 30;
-  const double* term = stage + (size_t)n * SB_SIZE;
-  // [0:30] dx, [30:48] dut, [48:78] dx next, [80] armijo
   QM_TICK(-1);
   if (n > 0) fetch.fwd_request(g, 0, stage, proj, gain);
   QM_PFOR(g, i, 30) { R[i] = m.x0[30 * b + i] - m.xs[((size_t)b * NMAX) * 30 + i]; }
@@ -186,6 +173,7 @@ QM_HDN void solve_forward(G g, F& fetch, const MpcBuffers& m, int b, double* R, 
   g.sync();
   // step norms and baseline performance: sums in a fixed order (bit-reproducible for a given group size): every thread sums
   // a strided subset of the 30 (n + 1) components, thread 0 adds the partial sums in thread order
+  double* part = W + RW_SA;                         // 2 x nt partial sums (SA is idle; clear of the forward scratch R)
   {
     double px = 0.0, pu = 0.0;
     for (int idx = g.tid(); idx < 30 * (n + 1); idx += g.nt()) { px += dxs[idx] * dxs[idx]; pu += dus[idx] * dus[idx]; }
@@ -213,13 +201,6 @@ QM_HDN void solve_forward(G g, F& fetch, const MpcBuffers& m, int b, double* R, 
     ls[LS_SQP_ITERS] += 1.0;                           // zeroed with the schedule at the start of the cycle
   }
   g.sync();
-}
-
-// Both on one group (CPU port). W: Riccati workspace; R: forward scratch (may alias W).
-template <class G, class F>
-QM_HDN void solve_problem(G g, F& fetch, const MpcBuffers& m, int b, double* W, double* R) {
-  solve_backward(g, fetch, m, b, W);
-  solve_forward(g, fetch, m, b, R, W + RW_SA);         // SA is idle after the backward sweep; clear of the forward scratch R
 }
 
 // Line-search decision for one problem (one thread). [upstream] SqpSolver::takeStep loop body.

@@ -34,10 +34,9 @@ static int fail(const std::string& msg) { qmb200_set_error_(msg.c_str()); return
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
   } while (0)
 
-enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY, KN_PROJ, KN_BACKTRACK, KN_STEP,
-       KN_ROLLOUT };
+enum { KN_SCHEDULE = 0, KN_INIT, KN_KIN1, KN_KIN2, KN_LQ, KN_SOLVE, KN_TRIAL, KN_DECIDE, KN_FINALIZE, KN_POLICY, KN_PROJ, KN_BACKTRACK, KN_STEP };
 static const char* kKernelNames[QMB200_NUM_KERNELS] = {"k_schedule", "k_init_guess", "k_kin1",   "k_kin2",   "k_lq",   "k_solve",     "k_trial",
-                                                       "k_decide",   "k_finalize",   "k_policy", "k_proj",   "k_backtrack", "k_step", "k_rollout"};
+                                                       "k_decide",   "k_finalize",   "k_policy", "k_proj",   "k_backtrack", "k_step"};
 
 // ------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_schedule(MpcBuffers m, const qmb200_solver_desc* S, const qmb200_problem_desc* P) {
@@ -265,31 +264,7 @@ __global__ void __launch_bounds__(QM_SOLVE_THREADS, 4) k_solve(MpcBuffers m) {
   fetch.init(smem, smem, (uint64_t*)(smem + SB_SIZE + RW_SIZE));
   BlockGroup g;
   g.nwid = blockIdx.x & 3;                        // spread the serial chains of co-resident CTAs over the sub-partitions
-  solve_backward(g, fetch, m, m.b0 + blockIdx.x, smem + SB_SIZE);
-}
-
-// Forward rollout, step norms and line-search record: a WARP per problem. The rollout is a chain of two small matrix-vector
-// products per node (dut = K dx + kff; 61 rows of length 30 + nut): nothing in it needs a CTA, and with a warp per problem the
-// whole batch is resident at once (7 warps per SM at B = 1024) instead of queueing for the 4 CTA slots per SM of k_solve. The
-// per-node blocks are read in place (L2 / HBM, the next node's blocks are prefetched into L2 while the current one is applied).
-constexpr int kRolloutWarps = 4;
-struct PrefetchFetch : DirectFetch {
-  template <class G> __device__ __forceinline__ void fwd_request(G g, int slot, const double* stage, const double* proj, const double* gain) {
-    DirectFetch::fwd_request(g, slot, stage, proj, gain);
-    const int lane = threadIdx.x & 31;
-    for (int i = lane * 16; i < SB_FWD_SIZE; i += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(stage + i));
-    for (int i = lane * 16; i < PB_SIZE; i += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(proj + i));
-    for (int i = lane * 16; i < GB_SIZE; i += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(gain + i));
-  }
-};
-__global__ void __launch_bounds__(32 * kRolloutWarps) k_rollout(MpcBuffers m) {
-  const int warp = threadIdx.x >> 5;
-  const int b = m.b0 + blockIdx.x * kRolloutWarps + warp;
-  if (b >= m.b0 + m.nb || m.conv[b] != CV_NONE) return;
-  extern __shared__ __align__(16) double smem[];
-  double* R = smem + (size_t)warp * (96 + 64 + PF_SIZE * m.NMAX);
-  PrefetchFetch fetch;
-  solve_forward(WarpGroup(), fetch, m, b, R, R + 96);
+  solve_problem(g, fetch, m, m.b0 + blockIdx.x, smem + SB_SIZE, smem + 2 * FWD_SLOT_SIZE);
 }
 
 // line-search evaluation: a thread per node (value-only single-pass tree walk in registers, qm_value.h)
@@ -566,7 +541,6 @@ static int enqueue_front(qmb200_ctx* c, MpcBuffers m) {
   const int nch = c->nchunks, cb = (B + nch - 1) / nch;
   const int iterations = c->hS.sqp_iterations < 1 ? 1 : c->hS.sqp_iterations;
   const size_t pf_bytes = (size_t)NMAX * PF_SIZE * sizeof(double);
-  const size_t rollout_bytes = (size_t)kRolloutWarps * (96 + 64 + PF_SIZE * NMAX) * sizeof(double);
   // inputs were enqueued on the main stream: every chunk stream starts behind them
   CUDA_OK(cudaEventRecord(c->ev_start, c->stream));
   for (int ch = 0; ch < nch; ++ch) {
@@ -590,7 +564,6 @@ static int enqueue_front(qmb200_ctx* c, MpcBuffers m) {
       CUDA_OK(cudaStreamWaitEvent(st, c->ev_join[ch], 0));
       { KernelTimer kt(c, KN_LQ, st); k_lq<<<dim3(NMAX, nb), QM_LQ_THREADS, kLqSmemBytes, st>>>(m, c->dM, c->dP); }
       { KernelTimer kt(c, KN_SOLVE, st); k_solve<<<nb, QM_SOLVE_THREADS, kSolveSmemBytes, st>>>(m); }
-      { KernelTimer kt(c, KN_ROLLOUT, st); k_rollout<<<(nb + kRolloutWarps - 1) / kRolloutWarps, 32 * kRolloutWarps, rollout_bytes, st>>>(m); }
       { KernelTimer kt(c, KN_TRIAL, st); k_trial<<<(nb * NMAX + kTrialThreads - 1) / kTrialThreads, kTrialThreads, 0, st>>>(m, c->dM, c->dP); }
       { KernelTimer kt(c, KN_DECIDE, st); k_decide<<<(nb + kDecideWarps - 1) / kDecideWarps, 32 * kDecideWarps, kDecideWarps * pf_bytes, st>>>(m, c->dS); }
       { KernelTimer kt(c, KN_BACKTRACK, st); k_backtrack<<<nb, kTrialThreads, pf_bytes, st>>>(m, c->dM, c->dP, c->dS); }
@@ -739,10 +712,6 @@ int qmb200_create(const qmb200_model_desc* model, const qmb200_problem_desc* pro
   C_OK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmemBytes));
   if (dec > 48 * 1024) C_OK(cudaFuncSetAttribute(k_decide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec));
   if (dec / kDecideWarps > 48 * 1024) C_OK(cudaFuncSetAttribute(k_backtrack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dec / kDecideWarps)));
-  {
-    const size_t rb = (size_t)kRolloutWarps * (96 + 64 + PF_SIZE * solver->max_nodes) * sizeof(double);
-    if (rb > 48 * 1024) C_OK(cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
-  }
   if (ini > 48 * 1024) C_OK(cudaFuncSetAttribute(k_init_guess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ini));
 #undef C_OK
   *out = c;
