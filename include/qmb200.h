@@ -207,6 +207,19 @@ int qmb200_actuator_batch_dev(qmb200_wbc_ctx* ctx, const qmb200_actuator_desc* d
                               const double* v, double* tau, int32_t* status);
 int qmb200_actuator_reset(qmb200_wbc_ctx* ctx);
 
+/* Forward-dynamics step behind the actuator. In the reference Gazebo integrates the robot
+ * (qm_gazebo/src/QMHWSim.cpp:98-114 only hands over the joint efforts); for batched, device-resident closed-loop studies this is
+ * ONE explicit step of the articulated-body equations with the stance feet of `mode` held by bilateral point contacts -- a
+ * labelled stand-in, not Gazebo's contact model:  M qdd + h = S' tau + Jc' f,  Jc qdd = -dJc v - (beta / dt) Jc v,
+ * v+ = v + dt qdd, q+ = q + dt v+.  rbd, rbd_next [B][55] in the estimator's layout (so the step chains with qmb200_wbc_batch and
+ * qmb200_rbd_to_state_batch; the end-effector pose entries are the forward kinematics of the new configuration), tau [B][18] from
+ * qmb200_actuator_batch, contact_forces [B][12] (zero for swing feet), status [B] (QMB200_WST_NAN). One call per simulation tick on the
+ * WBC context (its batch, its stream). */
+int qmb200_forward_dynamics_batch(qmb200_wbc_ctx* ctx, const double* rbd, const double* tau, const int32_t* mode, double dt, double beta,
+                                  double* rbd_next, double* contact_forces, int32_t* status);
+int qmb200_forward_dynamics_batch_dev(qmb200_wbc_ctx* ctx, const double* rbd, const double* tau, const int32_t* mode, double dt, double beta,
+                                      double* rbd_next, double* contact_forces, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,18 @@ def cport_wbc(md, wd, xd, ud, rbdm, mode, period, time, u_last, threads=1):
     return cmd, status
 
 
+def cport_forward_dynamics(md, gravity, rbdm, tau, mode, dt, beta=0.0, threads=1):
+    lib = load_cport()
+    n = rbdm.shape[0]
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rbdm, tau = np.ascontiguousarray(rbdm, dtype=np.float64), np.ascontiguousarray(tau, dtype=np.float64)
+    mode = np.ascontiguousarray(mode, dtype=np.int32)
+    nxt, f, st = np.zeros((n, 55)), np.zeros((n, 12)), np.zeros(n, dtype=np.int32)
+    lib.cport_forward_dynamics(C.byref(md), C.c_double(gravity), n, dp(rbdm), dp(tau), dp(mode), C.c_double(dt), C.c_double(beta),
+                               dp(nxt), dp(f), dp(st), threads)
+    return nxt, f, st
+
+
 _cport = None
 
 
@@ -127,7 +139,7 @@ def load_cport():
         return _cport
     so = os.path.join(HERE, "cport", "libcport.so")
     src = os.path.join(HERE, "cport", "cport.cpp")
-    deps = [src] + [os.path.join(HERE, "..", "qm_door_b200", "csrc", f) for f in ("qm_core.h", "qm_types.h", "qm_mpc.h", "qm_buffers.h", "qm_wbc.h")]
+    deps = [src] + [os.path.join(HERE, "..", "qm_door_b200", "csrc", f) for f in ("qm_core.h", "qm_types.h", "qm_mpc.h", "qm_buffers.h", "qm_wbc.h", "qm_sim.h", "qm_value.h", "qm_actuator.h", "qm_target.h")]
     deps = [p for p in deps if os.path.exists(p)]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.check_call(["g++", "-O3", "-march=x86-64-v3", "-std=c++17", "-shared", "-fPIC", "-pthread",

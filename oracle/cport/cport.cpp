@@ -194,6 +194,7 @@ int cport_feedback_gains(CportCtx* c, double* K) {
 // ---------------------------------------------------------------------------------------- WBC
 #include "../../qm_door_b200/csrc/qm_wbc.h"
 #include "../../qm_door_b200/csrc/qm_actuator.h"
+#include "../../qm_door_b200/csrc/qm_sim.h"
 
 extern "C" {
 
@@ -227,6 +228,17 @@ void cport_actuator(const qmb200_actuator_desc* D, int n, const int64_t* time_ns
                   q + 18 * b, v + 18 * b, (long long*)stamp + CAP * b, buf + CAP * 18 * ACT_NF * b, hc + 2 * b, last + 18 * ACT_NF * b,
                   tau + 18 * b, status + b);
   }
+}
+
+// Forward-dynamics step (qm_sim.h), n problems.
+void cport_forward_dynamics(const qmb200_model_desc* M, double gravity, int n, const double* rbd, const double* tau, const int32_t* mode,
+                            double dt, double beta, double* rbd_next, double* f, int32_t* status, int threads) {
+  parallel_for(n, threads, [&](int b) {
+    std::vector<double> W(WW_SIZE);
+    int st = 0;
+    fd_step(SerialGroup(), *M, gravity, rbd + 55 * b, tau + 18 * b, mode[b], dt, beta, W.data(), rbd_next + 55 * b, f + 12 * b, &st);
+    status[b] = st;
+  });
 }
 
 }  // extern "C"

@@ -445,6 +445,24 @@ class WbcContext:
                                                 _dev(q, (B, 18), f8, "q", d), _dev(v, (B, 18), f8, "v", d),
                                                 _dev(tau, (B, 18), f8, "tau", d), _dev(status, (B,), np.int32, "status", d)))
 
+    def forward_dynamics(self, rbd, tau, mode, dt, beta=0.0):
+        """One forward-dynamics step behind the actuator (stance feet of `mode` held by point contacts; see include/qmb200.h)
+        -> (rbd_next [B][55], contact forces [B][12], status [B])."""
+        B = self.B
+        rbd, tau = _host(rbd, (B, 55), np.float64, "rbd"), _host(tau, (B, 18), np.float64, "tau")
+        mode = _host(mode, (B,), np.int32, "mode")
+        nxt, f, st = np.zeros((B, 55)), np.zeros((B, 12)), np.zeros(B, dtype=np.int32)
+        _check(self.L.qmb200_forward_dynamics_batch(self.h, _p(rbd), _p(tau), _p(mode), C.c_double(dt), C.c_double(beta), _p(nxt), _p(f), _p(st)))
+        return nxt, f, st
+
+    def forward_dynamics_dev(self, rbd, tau, mode, dt, beta, rbd_next, contact_forces, status):
+        B, d, f8 = self.B, self.device, np.float64
+        self._keep.append((rbd, tau, mode, rbd_next, contact_forces, status))
+        _check(self.L.qmb200_forward_dynamics_batch_dev(self.h, _dev(rbd, (B, 55), f8, "rbd", d), _dev(tau, (B, 18), f8, "tau", d),
+                                                        _dev(mode, (B,), np.int32, "mode", d), C.c_double(dt), C.c_double(beta),
+                                                        _dev(rbd_next, (B, 55), f8, "rbd_next", d), _dev(contact_forces, (B, 12), f8, "contact_forces", d),
+                                                        _dev(status, (B,), np.int32, "status", d)))
+
     def actuator_reset(self):
         _check(self.L.qmb200_actuator_reset(self.h))
 

@@ -148,13 +148,12 @@ QM_HD void point_bias_accel(const double* acc_b, const double* V_b, const double
   out[0] = acc_b[3] + t[0]; out[1] = acc_b[4] + t[1]; out[2] = acc_b[5] + t[2];
 }
 
-// updateMeasured + updateDesired. rbd[55] measured state, xd/ud[30] MPC policy sample, u_last[30] (stateful inputLast_).
+// updateMeasured (WbcBase.cpp:146-203): mass matrix, nonlinear effects, frame Jacobians and their bias accelerations at the
+// measured state rbd[55]; q, v and the frame kinematics to W + WA_MEAS.
 template <class G>
-QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* rbd, const double* xd,
-                         const double* ud, const double* u_last, double period, double* W) {
+QM_HDN void wbc_dynamics_measured(G g, const qmb200_model_desc& M, double gravity, const double* rbd, double* W) {
   double* kw = W + WA_KIN;
   double* ms = W + WA_MEAS;
-  double* ds = W + WA_DES;
   // ---- measured (WbcBase.cpp:146-203)
   if (g.tid() == 0) {
     for (int k = 0; k < 3; ++k) { ms[k] = rbd[3 + k]; ms[3 + k] = rbd[k]; ms[24 + k] = rbd[27 + k]; }
@@ -174,7 +173,7 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
   QM_PFOR(g, idx, 144) W[WA_JEE + idx] = kw[KW_EEJ + idx];     // before the velocity level reuses the storage (KW_HB)
   g.sync();
   kin_velocities(g, M, 0, kw);
-  bias_forces(g, M, kw, C.gravity, W + WA_ACC, W + WA_FB);
+  bias_forces(g, M, kw, gravity, W + WA_ACC, W + WA_FB);
   QM_PFOR(g, j, QM_NJ) {     // nle = S_j . sum of subtree forces (RNEA backward pass)
     double f[6] = {0, 0, 0, 0, 0, 0}, S[6];
     const uint32_t mask = M.submask[j];
@@ -234,6 +233,15 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
     }
   }
   g.sync();
+}
+
+// updateMeasured + updateDesired. rbd[55] measured state, xd/ud[30] MPC policy sample, u_last[30] (stateful inputLast_).
+template <class G>
+QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* rbd, const double* xd,
+                         const double* ud, const double* u_last, double period, double* W) {
+  wbc_dynamics_measured(g, M, C.gravity, rbd, W);
+  double* kw = W + WA_KIN;
+  double* ds = W + WA_DES;
   // ---- desired (WbcBase.cpp:205-238)
   kin_positions(g, M, xd + 6, kw);
   centroidal_velocity(g, M, xd, ud, kw);

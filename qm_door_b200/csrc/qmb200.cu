@@ -1182,6 +1182,7 @@ int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, 
 // ============================================================================================ whole-body controller
 #include "qm_wbc.h"
 #include "qm_actuator.h"
+#include "qm_sim.h"
 
 constexpr int kWbcInDoubles = 30 + 30 + 56 + 32;   // xd, ud, rbd (padded), u_last (padded)
 constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
@@ -1218,10 +1219,24 @@ __global__ void __launch_bounds__(128) k_actuator(int B, qmb200_actuator_desc D,
                 last + 18 * ACT_NF * sb, tau + 18 * sb, status + b);
 }
 
+// ---- forward-dynamics step (stand-in for the simulator behind the actuator): CTA per problem
+__global__ void __launch_bounds__(128) k_fwd_dyn(int B, const qmb200_model_desc* M, double gravity, const double* rbd, const double* tau,
+                                                  const int32_t* mode, double dt, double beta, double* rbd_out, double* f_out, int32_t* status) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  extern __shared__ double smem[];
+  double* in = smem + WW_SIZE;                       // rbd (55, padded), tau (18)
+  for (int i = threadIdx.x; i < 55; i += blockDim.x) in[i] = rbd[55 * (size_t)b + i];
+  for (int i = threadIdx.x; i < 18; i += blockDim.x) in[56 + i] = tau[18 * (size_t)b + i];
+  __syncthreads();
+  fd_step(BlockGroup(), *M, gravity, in, in + 56, mode[b], dt, beta, smem, rbd_out + 55 * (size_t)b, f_out + 12 * (size_t)b, status + b);
+}
+
 struct qmb200_wbc_ctx {
   // actuator state (allocated on first use): stamps, buffered commands, {head, count}, held command per joint
   long long* act_stamp = nullptr; double* act_buf = nullptr; int* act_hc = nullptr; double* act_last = nullptr;
   int device = 0, B = 0;
+  double gravity = 9.81;
   qmb200_model_desc* dM = nullptr;
   qmb200_wbc_desc* dC = nullptr;
   double *xd = nullptr, *ud = nullptr, *rbd = nullptr, *period = nullptr, *time = nullptr, *u_last = nullptr, *cmd = nullptr;
@@ -1263,7 +1278,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   if (qmb200_device_count() <= 0) return fail("qmb200_wbc_create: no CUDA device available (this library has no CPU fallback)");
   CUDA_OK(cudaSetDevice(device));
   qmb200_wbc_ctx* c = new qmb200_wbc_ctx();
-  c->device = device; c->B = batch;
+  c->device = device; c->B = batch; c->gravity = wbc->gravity;
 #define C_OK(call) CREATE_OK(call, qmb200_wbc_destroy(c))
   C_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   C_OK(cudaEventCreate(&c->e0));
@@ -1284,6 +1299,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   C_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));
   C_OK(cudaMemset(c->u_last, 0, B * 30 * sizeof(double)));
   C_OK(cudaFuncSetAttribute(k_wbc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+  C_OK(cudaFuncSetAttribute(k_fwd_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
 #undef C_OK
   *out = c;
   return 0;
@@ -1384,6 +1400,39 @@ static int actuator_state(qmb200_wbc_ctx* c, bool clear) {
     CUDA_OK(cudaMemsetAsync(c->act_hc, 0, B * 2 * sizeof(int), c->stream));
     CUDA_OK(cudaMemsetAsync(c->act_last, 0, B * 18 * ACT_NF * sizeof(double), c->stream));
   }
+  return 0;
+}
+
+int qmb200_forward_dynamics_batch_dev(qmb200_wbc_ctx* c, const double* rbd, const double* tau, const int32_t* mode, double dt, double beta,
+                                      double* rbd_next, double* contact_forces, int32_t* status) {
+  if (!c || !rbd || !tau || !mode || !rbd_next || !contact_forces || !status) return fail("qmb200_forward_dynamics_batch_dev: null argument");
+  if (!(dt > 0.0) || beta < 0.0) return fail("qmb200_forward_dynamics_batch_dev: dt must be positive, beta non-negative");
+  CUDA_OK(cudaSetDevice(c->device));
+  k_fwd_dyn<<<c->B, 128, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->gravity, rbd, tau, mode, dt, beta, rbd_next, contact_forces, status);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int qmb200_forward_dynamics_batch(qmb200_wbc_ctx* c, const double* rbd, const double* tau, const int32_t* mode, double dt, double beta,
+                                  double* rbd_next, double* contact_forces, int32_t* status) {
+  if (!c || !rbd || !tau || !mode || !rbd_next || !contact_forces) return fail("qmb200_forward_dynamics_batch: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t B = c->B;
+  cudaStream_t st = c->stream;
+  double* d = nullptr; int32_t* di = nullptr;
+  CUDA_OK(cudaMallocAsync(&d, B * (55 + 18 + 55 + 12) * sizeof(double), st));
+  CUDA_OK(cudaMallocAsync(&di, B * 2 * sizeof(int32_t), st));
+  double *dr = d, *dt_ = dr + 55 * B, *dn = dt_ + 18 * B, *df = dn + 55 * B;
+  CUDA_OK(cudaMemcpyAsync(dr, rbd, B * 55 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dt_, tau, B * 18 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(di, mode, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (qmb200_forward_dynamics_batch_dev(c, dr, dt_, di, dt, beta, dn, df, di + B) != 0) return -1;
+  CUDA_OK(cudaMemcpyAsync(rbd_next, dn, B * 55 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(contact_forces, df, B * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_OK(cudaMemcpyAsync(status, di + B, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaFreeAsync(d, st));
+  CUDA_OK(cudaFreeAsync(di, st));
+  CUDA_OK(cudaStreamSynchronize(st));
   return 0;
 }
 
