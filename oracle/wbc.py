@@ -135,6 +135,70 @@ def solve_qp_gi(Hfac, c, C, d, max_iter=2000, tol=1e-10, tol_degenerate=1e-7):
             continue
 
 
+# ----------------------------------------------------------------------------- [upstream] Eigen::FullPivLU<MatrixXd>::kernel()
+def full_piv_lu_kernel(A):
+    """Kernel basis exactly as Eigen's FullPivLU produces it for a column-major dynamic matrix (HoQp.cpp:129:
+    `(task_.a_ * stackedZPrev_).fullPivLu().kernel()`), restated from the published Eigen 3.3/3.4 sources (Eigen is not vendored):
+      * elimination with full pivoting; the pivot of step k is the entry of largest magnitude of the remaining corner, the FIRST
+        one in column-major order on ties (maxCoeff visitor: outer loop over columns, strict `>`);
+      * rank = number of pivots with |U_ii| > eps * diagonalSize * max|pivot| (FullPivLU::threshold() default);
+      * kernel = Q [ -U11^-1 U12 ; I ] with Q the accumulated column permutation (kernel_retval::evalTo); a trivial kernel is
+        returned as ONE zero column.
+    The basis is not orthonormal; HoQp's 1e-12 |z|^2 regularisation acts on the coordinates in THIS basis, which is what selects
+    the solution of a rank-deficient level. Returns (N [cols x max(dimker, 1)], rank)."""
+    lu = np.array(A, dtype=float)
+    rows, cols = lu.shape
+    size = min(rows, cols)
+    row_t, col_t = list(range(size)), list(range(size))
+    nonzero, maxpivot = size, 0.0
+    for k in range(size):
+        corner = np.abs(lu[k:, k:])
+        best, bi, bj = corner[0, 0], 0, 0
+        for j in range(corner.shape[1]):              # column-major traversal, strict greater
+            for i in range(corner.shape[0]):
+                if corner[i, j] > best:
+                    best, bi, bj = corner[i, j], i, j
+        if best == 0.0:
+            nonzero = k
+            break
+        bi += k; bj += k
+        maxpivot = max(maxpivot, best)
+        row_t[k], col_t[k] = bi, bj
+        if bi != k:
+            lu[[k, bi], :] = lu[[bi, k], :]
+        if bj != k:
+            lu[:, [k, bj]] = lu[:, [bj, k]]
+        if k < rows - 1:
+            lu[k + 1:, k] /= lu[k, k]
+        if k < size - 1:
+            lu[k + 1:, k + 1:] -= np.outer(lu[k + 1:, k], lu[k, k + 1:])
+    q = list(range(cols))
+    for k in range(size):
+        q[k], q[col_t[k]] = q[col_t[k]], q[k]
+    thr = maxpivot * np.finfo(float).eps * size
+    pivots = [i for i in range(nonzero) if abs(lu[i, i]) > thr]
+    rank = len(pivots)
+    dimker = cols - rank
+    if dimker == 0:
+        return np.zeros((cols, 1)), rank
+    m = np.zeros((rank, cols))
+    for i in range(rank):
+        m[i, i:] = lu[pivots[i], i:]
+    m[:, :rank] = np.triu(m[:, :rank])
+    for i in range(rank):
+        m[:, [i, pivots[i]]] = m[:, [pivots[i], i]]
+    if rank > 0:
+        m[:, rank:] = np.linalg.solve(np.triu(m[:, :rank]), m[:, rank:]) if rank > 0 else m[:, rank:]
+    for i in range(rank - 1, -1, -1):
+        m[:, [i, pivots[i]]] = m[:, [pivots[i], i]]
+    N = np.zeros((cols, dimker))
+    for i in range(rank):
+        N[q[i], :] = -m[i, cols - dimker:]
+    for k in range(dimker):
+        N[q[rank + k], k] = 1.0
+    return N, rank
+
+
 # ----------------------------------------------------------------------------- HoQp (HoQp.cpp:12-158)
 class HoQp:
     def __init__(self, task, higher=None):
@@ -178,10 +242,10 @@ class HoQp:
         self.z, self.v = sol[:nz], sol[nz:]
         self.x = xp + Zp @ self.z                                                      # HoQp.h:31-34
         self.stacked_slack = np.concatenate([vp, self.v])
-        # next null space (HoQp.cpp:126-133); orthonormal kernel basis instead of FullPivLU's (same subspace)
-        _, sv, Vt = np.linalg.svd(AZ, full_matrices=True)
-        rank = int((sv > 1e-9 * max(1.0, sv[0])).sum())
-        self.Z = Zp @ Vt[rank:].T
+        # next null space (HoQp.cpp:126-133): stackedZPrev * (A Zprev).fullPivLu().kernel(), Eigen's own basis (not orthonormal).
+        # A trivial kernel comes back from Eigen as one zero column (one dummy variable that moves nothing): no freedom left.
+        N, rank = full_piv_lu_kernel(AZ)
+        self.Z = Zp @ N if rank < nz else np.zeros((Zp.shape[0], 0))
         self.Zprev, self.xprev, self.AZ = Zp, xp, AZ
 
 

@@ -509,79 +509,85 @@ QM_HDN void back_substitute(G w0, double* A, int n, int ld, double* z) {
   }
 }
 
-// Orthonormal basis of the kernel of Abar (r x n, row major ld_a): Householder QR with column pivoting of Abar' (n x r).
-// Q (n x n) is formed explicitly in Qm; the kernel basis is its last n - rank columns. Returns rank via *rank_out.
-// Same phase structure as householder_ls: inner products split over four row / column chunks, then rank-one updates.
+// Kernel basis of Abar (r x n, row major ld_a) exactly as the reference obtains it (HoQp.cpp:129: (A Zprev).fullPivLu().kernel(),
+// [upstream] Eigen::FullPivLU<MatrixXd>): elimination with full pivoting -- the pivot of step k is the entry of largest magnitude
+// of the remaining corner, the first one in column-major order on ties --, rank = pivots above eps * min(r, n) * max|pivot|,
+// kernel = Q [ -U11^-1 U12 ; I ] with Q the accumulated column permutation. The basis is NOT orthonormal: HoQp's 1e-12 |z|^2
+// regularisation acts on the coordinates in this basis, which is what selects the solution of a rank-deficient level.
+// T: r x n scratch; N: n x ldn output (columns 0 .. n - rank - 1); cn: n + 2 doubles; perm: 2 n + 4 ints. *rank_out = rank.
+// Eigen returns a trivial kernel as one zero column (a dummy variable that moves nothing); here rank = n means "no freedom left".
 template <class G>
-QM_HDN void kernel_basis(G g, const double* Abar, int r, int n, int ld_a, double* T, double* Qm, double* vh, double* cn, int* perm,
-                         int* rank_out, double* hp) {
-  // T = Abar' (n x r), ld = r
-  QM_PFOR(g, idx, n * r) { const int i = idx / r, j = idx % r; T[i * r + j] = Abar[j * ld_a + i]; }
-  QM_PFOR(g, idx, n * n) Qm[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+QM_HDN void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, double* T, double* N, int ldn, double* cn, int* perm,
+                            int* rank_out, int* status) {
+  int* qidx = perm;                 // [n] column permutation
+  int* brow = perm + n;             // [n] row of the largest entry per column; [n], [n + 1]: pivot row / column of the step
+  QM_PFOR2(g, i, r, j, n) T[i * n + j] = Abar[i * ld_a + j];
+  QM_PFOR(g, j, n) qidx[j] = j;
   g.sync();
-  const int steps = (n < r) ? n : r;
-  int rank = 0;
-  double first = 0.0;
-  for (int k = 0; k < steps; ++k) {
-    const int rows = n - k, cols = r - k;
-    const int chunk = (rows + HH_PARTS - 1) / HH_PARTS;
-    QM_PFOR2(g, part, HH_PARTS, jj, cols) {                   // squared norms of the remaining columns, four row chunks each
+  const int size = (r < n) ? r : n;
+  int nonzero = size;
+  double maxpivot = 0.0;
+  for (int k = 0; k < size; ++k) {
+    QM_PFOR(g, jj, n - k) {                         // largest magnitude of column j over the rows k..r-1, first row on ties
       const int j = k + jj;
-      const int i0 = k + part * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
-      double sp = 0.0;
-      for (int i = i0; i < i1; ++i) sp += T[i * r + j] * T[i * r + j];
-      hp[part * HH_LD + jj] = sp;
+      double best = fabs(T[k * n + j]);
+      int bi = k;
+      for (int i = k + 1; i < r; ++i) { const double v = fabs(T[i * n + j]); if (v > best) { best = v; bi = i; } }
+      cn[j] = best; brow[j] = bi;
     }
     g.sync();
-    if (g.tid() == 0) {
-      int best = k;
-      double bv = -1.0;
-      for (int j = k; j < r; ++j) {
-        const double v = (hp[j - k] + hp[HH_LD + j - k]) + (hp[2 * HH_LD + j - k] + hp[3 * HH_LD + j - k]);
-        cn[j] = v;
-        if (v > bv) { bv = v; best = j; }
+    if (g.tid() == 0) {                             // columns in order, strict greater: column-major first maximum
+      int bj = k;
+      double best = cn[k];
+      for (int j = k + 1; j < n; ++j) if (cn[j] > best) { best = cn[j]; bj = j; }
+      brow[n] = brow[bj]; brow[n + 1] = bj; cn[n] = best;
+    }
+    g.sync();
+    const double best = cn[n];
+    if (best == 0.0) { nonzero = k; break; }
+    if (best > maxpivot) maxpivot = best;
+    const int bi = brow[n], bj = brow[n + 1];
+    g.sync();                                       // everybody has read the pivot record before it is reused
+    if (bi != k) QM_PFOR(g, j, n) { const double t = T[k * n + j]; T[k * n + j] = T[bi * n + j]; T[bi * n + j] = t; }
+    g.sync();
+    if (bj != k) {
+      QM_PFOR(g, i, r) { const double t = T[i * n + k]; T[i * n + k] = T[i * n + bj]; T[i * n + bj] = t; }
+      if (g.tid() == 0) { const int t = qidx[k]; qidx[k] = qidx[bj]; qidx[bj] = t; }
+    }
+    g.sync();
+    const double piv = T[k * n + k];
+    QM_PFOR(g, ii, r - k - 1) T[(k + 1 + ii) * n + k] /= piv;
+    g.sync();
+    if (k < size - 1) {
+      QM_PFOR2(g, ii, r - k - 1, jj, n - k - 1) {
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        T[i * n + j] -= T[i * n + k] * T[k * n + j];
       }
-      perm[0] = best;
-    }
-    g.sync();
-    const int pj = perm[0];
-    const double nrm2 = cn[pj];
-    if (k == 0) first = nrm2;
-    if (!(nrm2 > 1e-18 * (first > 1.0 ? first : 1.0))) break;
-    if (pj != k) {
-      QM_PFOR(g, i, n) { const double t = T[i * r + k]; T[i * r + k] = T[i * r + pj]; T[i * r + pj] = t; }
       g.sync();
     }
-    ++rank;
-    if (k >= n - 1) break;              // last row: nothing to reflect
-    const double akk = T[k * r + k];
-    const double nrm = sqrt(nrm2);
-    const double alpha = (akk >= 0.0) ? -nrm : nrm;
-    const double vk = akk - alpha;
-    const double vv = nrm2 - akk * akk + vk * vk;
-    const double beta = (vv > 0.0) ? 2.0 / vv : 0.0;
-    QM_PFOR(g, i, rows) vh[k + i] = (i == 0) ? vk : T[(k + i) * r + k];
-    g.sync();
-    // s_j = v'T_j (columns k..r-1) and q_i = Q[i, k:] v (all rows), each split over four chunks of the reflector
-    QM_PFOR2(g, part, HH_PARTS, it, cols + n) {
-      const int i0 = k + part * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
-      double sp = 0.0;
-      if (it < cols) { const int j = k + it; for (int i = i0; i < i1; ++i) sp += vh[i] * T[i * r + j]; }
-      else { const int row = it - cols; for (int c = i0; c < i1; ++c) sp += Qm[row * n + c] * vh[c]; }
-      hp[part * HH_LD + it] = sp;
+  }
+  // rank: pivots above the threshold (FullPivLU::threshold() default). They form a prefix of the diagonal with full pivoting up
+  // to rounding noise; anything else is flagged and the prefix is used.
+  const double thr = maxpivot * 2.220446049250313e-16 * (double)size;
+  int rank = 0, above = 0;
+  for (int i = 0; i < nonzero; ++i) if (fabs(T[i * n + i]) > thr) { ++above; if (rank == i) rank = i + 1; }
+  if (above != rank && g.tid() == 0) status_or(status, WST_DEGENERATE);
+  const int dimker = n - rank;
+  // X = U11^-1 U12 in place (one right-hand side column per work item)
+  QM_PFOR(g, cc, dimker) {
+    const int c = rank + cc;
+    for (int i = rank - 1; i >= 0; --i) {
+      double sacc = T[i * n + c];
+      for (int j = i + 1; j < rank; ++j) sacc -= T[i * n + j] * T[j * n + c];
+      T[i * n + c] = sacc / T[i * n + i];
     }
-    g.sync();
-    // T <- H T (columns k..r-1),  Q <- Q H (all rows)
-    QM_PFOR2(g, ii, rows, jj, cols) {
-      const double sj = beta * ((hp[jj] + hp[HH_LD + jj]) + (hp[2 * HH_LD + jj] + hp[3 * HH_LD + jj]));
-      T[(k + ii) * r + k + jj] -= vh[k + ii] * sj;
-    }
-    QM_PFOR2(g, i, n, cc, rows) {
-      const int it = cols + i;
-      const double qi = beta * ((hp[it] + hp[HH_LD + it]) + (hp[2 * HH_LD + it] + hp[3 * HH_LD + it]));
-      Qm[i * n + k + cc] -= qi * vh[k + cc];
-    }
-    g.sync();
+  }
+  g.sync();
+  QM_PFOR2(g, i, n, kk, dimker) {
+    double v = 0.0;
+    if (i < rank) v = -T[i * n + rank + kk];
+    else if (i - rank == kk) v = 1.0;
+    N[qidx[i] * ldn + kk] = v;
   }
   if (g.tid() == 0) *rank_out = rank;
   g.sync();
@@ -864,9 +870,12 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
   // ---- level 0
   wbc_level0(g, W, WI);
   QM_TICK(-1);
-  kernel_basis(g, W + WW_A0, 18, 36, 36, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, W + WS_HP);
-  const int n1 = 36 - WI[WI_SC + 1];
-  QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + (36 - n1) + c] : 0.0; }
+  // Z0 = kernel(A0) in the reference's own (FullPivLU) basis; it has 36 - rank(A0) columns, at most 18 are kept (rank(A0) = 18
+  // unless the contact Jacobians are degenerate, which is flagged)
+  kernel_basis_lu(g, W + WW_A0, 18, 36, 36, W + WS_QR, W + WS_Q, 36, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+  int n1 = 36 - WI[WI_SC + 1];
+  if (n1 > 18) { n1 = 18; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
+  QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + c] : 0.0; }
   g.sync(); QM_TICK(38);
   // ---- level 1 in the coordinates x = x0 + Z0 z
   int n2 = 0;
@@ -901,14 +910,14 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
       W[WW_X + k] += s;
     }
     g.sync();
-    // kernel of A1 Z0 -> Z1 = Z0 N1
-    kernel_basis(g, W + WS_GA, r1, n1, 18, W + WS_QR, W + WS_Q, W + WS_VH, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, W + WS_HP);
+    // kernel of A1 Z0 (FullPivLU basis) -> Z1 = Z0 N1
+    kernel_basis_lu(g, W + WS_GA, r1, n1, 18, W + WS_QR, W + WS_Q, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
     n2 = n1 - WI[WI_SC + 1];
-    if (n2 > 12) n2 = 12;
+    if (n2 > 12) { n2 = 12; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
     QM_PFOR(g, idx, 36 * 12) {
       const int i = idx / 12, c = idx % 12;
       double s = 0.0;
-      if (c < n2) for (int k = 0; k < n1; ++k) s += W[WW_Z0 + 18 * i + k] * W[WS_Q + n1 * k + (n1 - n2) + c];
+      if (c < n2) for (int k = 0; k < n1; ++k) s += W[WW_Z0 + 18 * i + k] * W[WS_Q + 18 * k + c];
       W[WW_Z1 + idx] = s;
     }
     g.sync(); QM_TICK(42);
