@@ -502,7 +502,7 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
                 nodes_bytes += kernel_bytes_per_node(dom, 14 + bin(md & 15).count("1"))
         achieved = nodes_bytes / (ms_dom * 1e-3) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")       # DRAM bytes per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")       # DRAM bytes per launch from the committed ncu --set full capture
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)
         cyc_bytes = 0.0
