@@ -129,6 +129,18 @@ def cport_forward_dynamics(md, gravity, rbdm, tau, mode, dt, beta=0.0, threads=1
     return nxt, f, st
 
 
+KW_NAMES = ["R", "P", "AX", "BODY", "COMP", "ACM", "SV", "V", "HB", "FPOS", "FVEL", "EEP", "EER", "COM", "ABINV", "VEL", "RHS", "VSIZE",
+            "FJ", "EEJ", "DH", "DFV", "F", "SIZE"]
+
+
+def kw_offsets():
+    """Offsets of the kinematics workspace (qm_core.h KW_*), read from the compiled CPU port (never hand-copied)."""
+    out = (C.c_int * len(KW_NAMES))()
+    n = load_cport().cport_kw_offsets(out)
+    assert n == len(KW_NAMES)
+    return dict(zip(KW_NAMES, [int(v) for v in out]))
+
+
 _cport = None
 
 

@@ -33,6 +33,14 @@ static void parallel_for(int n, int threads, F f) {
 extern "C" {
 
 int cport_kin_ws_size() { return KW_SIZE; }
+// offsets of the kinematics workspace (qm_core.h KW_*), in the order of oracle/abi_fill.py::KW_NAMES
+int cport_kw_offsets(int* out) {
+  const int v[] = {KW_R, KW_P, KW_AX, KW_BODY, KW_COMP, KW_ACM, KW_SV, KW_V, KW_HB, KW_FPOS, KW_FVEL, KW_EEP, KW_EER, KW_COM, KW_ABINV,
+                   KW_VEL, KW_RHS, KW_VSIZE, KW_FJ, KW_EEJ, KW_DH, KW_DFV, KW_F, KW_SIZE};
+  const int n = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n; ++i) out[i] = v[i];
+  return n;
+}
 int cport_tw_size() { return TW_SIZE; }
 int cport_sizes(int* out) {
   out[0] = SB_SIZE; out[1] = PB_SIZE; out[2] = GB_SIZE; out[3] = PF_SIZE; out[4] = LS_SIZE; out[5] = TW_SIZE; out[6] = TI_SIZE;

@@ -7,7 +7,7 @@ import numpy as np
 from . import load_gait, load_model, load_problem, tile_schedule
 
 # EE pose of the nominal configuration (forward kinematics of task.info initialState, z1_end_effector frame);
-# tests/test_loaders.py checks it against the oracle's forward kinematics.
+# tests/test_abi.py::test_workload_reference_pose checks it against the oracle's forward kinematics.
 NOMINAL_EE_POS = (0.6253031727266175, 0.0, 0.8300452360692332)
 NOMINAL_EE_QUAT = None  # filled lazily from the oracle-checked constant below
 

@@ -26,7 +26,7 @@ def test_cycle_matches_golden(cport_factory, path):
 
 def test_kinematics_and_analytic_derivatives(descs, oracle_inputs):
     """kin_eval: FK, CMM, frame Jacobians and the analytic d(Av)/dq, d(Jv)/dq against complex-step differentiation."""
-    from qm_door_b200.csrc_offsets import KW
+    KW = abi_fill.kw_offsets()
     model, _, _, _ = descs
     m, P = oracle_inputs
     lib = abi_fill.load_cport()
