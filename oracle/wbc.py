@@ -238,7 +238,18 @@ class HoQp:
                         np.hstack([tp.d @ Zp, np.zeros((tp.d.shape[0], nv_s))]),
                         np.hstack([task.d @ Zp, -np.eye(nv_s)])])
         dm = np.concatenate([np.zeros(nv_s), tp.f - tp.d @ xp + vp, task.f - task.d @ xp])
-        sol, self.active, self.iterations = solve_qp_gi(Jm, c, Cm, dm)
+        try:
+            sol, self.active, self.iterations = solve_qp_gi(Jm, c, Cm, dm)
+        except RuntimeError:
+            # rows handed down tight from the levels above are violated by accumulated rounding (1e-6 .. 1e-5 in the deeper levels
+            # of the six-level stack, whose null-space bases are not orthonormal): accept them as degenerate with a wider margin
+            try:
+                sol, self.active, self.iterations = solve_qp_gi(Jm, c, Cm, dm, tol_degenerate=1e-5)
+            except RuntimeError:
+                # last resort, the device code's rule: a violated row whose normal depends on the active set with nothing to drop
+                # is skipped whatever its residual (the solve is then flagged degenerate there, WST_DEGENERATE)
+                sol, self.active, self.iterations = solve_qp_gi(Jm, c, Cm, dm, tol_degenerate=np.inf)
+            self.relaxed = True
         self.z, self.v = sol[:nz], sol[nz:]
         self.x = xp + Zp @ self.z                                                      # HoQp.h:31-34
         self.stacked_slack = np.concatenate([vp, self.v])
@@ -375,20 +386,29 @@ class Wbc:
         D = self.update_desired(x_des, u_des, period)
         T = self.tasks(M, D, mode, u_des)
         task0 = T["eom"] + T["torque"] + T["no_contact_motion"] + T["friction"]
-        if self.mpc_variant:
-            task1 = T["base_height"] + T["base_angular"] + T["base_linear"] + T["swing"] * 100
-            task2 = T["contact_force"]
+        if int(self.mpc_variant) == 2:
+            # SYNTHETIC six-level split of the same tasks (BASELINE config 5 names "6 task levels"; the reference's stacks have
+            # three, HierarchicalWbc.cpp:23-43): the construction of every level is HoQp's (HoQp.cpp:12-158). A level without
+            # rows (the swing level in full stance) changes nothing and is skipped.
+            lower = [T["base_height"] + T["base_angular"], T["ee_linear"] + T["ee_angular"], T["swing"] * 100, T["base_linear"],
+                     T["contact_force"]]
+        elif self.mpc_variant:
+            lower = [T["base_height"] + T["base_angular"] + T["base_linear"] + T["swing"] * 100, T["contact_force"]]
         else:
-            task1 = T["arm_joint"] if time < 10 else (T["base_height"] + T["base_angular"] + T["ee_linear"] + T["ee_angular"] + T["swing"] * 100)
-            task2 = T["contact_force"] + T["base_linear"]
-        l0 = HoQp(task0)
-        l1 = HoQp(task1, l0)
-        l2 = HoQp(task2, l1)
-        x = l2.x
+            lower = [T["arm_joint"] if time < 10 else (T["base_height"] + T["base_angular"] + T["ee_linear"] + T["ee_angular"] + T["swing"] * 100),
+                     T["contact_force"] + T["base_linear"]]
+        levels = [HoQp(task0)]
+        for task in lower:
+            if task.a.shape[0] == 0 and task.d.shape[0] == 0:
+                continue
+            levels.append(HoQp(task, levels[-1]))
+        l0, l1, l2 = levels[0], levels[1], levels[-1]
+        task1, task2 = lower[0], lower[-1]
+        x = levels[-1].x
         tau = np.hstack([M["M"][6:], -M["J"].T[6:]]) @ x + M["nle"][6:]             # updateCmd (WbcBase.cpp:580-595)
         cmd = np.concatenate([x, tau])
         if return_debug:
-            return cmd, dict(levels=(l0, l1, l2), tasks=(task0, task1, task2), M=M, D=D, T=T)
+            return cmd, dict(levels=(l0, l1, l2), all_levels=levels, tasks=(task0, task1, task2), M=M, D=D, T=T)
         return cmd
 
 

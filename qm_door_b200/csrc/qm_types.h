@@ -101,7 +101,7 @@ typedef struct qmb200_wbc_desc {
   double swing_weight;         // 100 (HierarchicalWbc.cpp:29)
   double init_time;            // 10 s: before it level 1 is the arm-joint tracking task (HierarchicalWbc.cpp:32-43)
   double gravity;
-  int32_t mpc_variant;         // 0: HierarchicalWbc, 1: HierarchicalMpcWbc task stack
+  int32_t mpc_variant;         // task stack: 0 HierarchicalWbc, 1 HierarchicalMpcWbc, 2 six-level split of the same tasks (synthetic, BASELINE config 5)
   int32_t reserved;
 } qmb200_wbc_desc;
 

@@ -16,7 +16,7 @@ namespace qm {
 
 enum { WST_OK = 0, WST_QP_MAX_ITER = 1, WST_DEGENERATE = 2, WST_NAN = 4, WST_BAD_MODE = 8 };
 
-enum { WB_NX = 36, WB_ND0 = 56, WB_NA1 = 22, WB_NA2 = 14, WB_MAXW = 36, WB_QR_ROWS = 92, WB_QR_LD = 37 };
+enum { WB_NX = 36, WB_ND0 = 56, WB_POOL = 36, WB_MAXLEV = 6, WB_MAXW = 36, WB_QR_ROWS = 92, WB_QR_LD = 37 };
 #define QM_WBC_EPS 1e-12        // HoQp.cpp:66
 
 // ---- workspace (doubles)
@@ -27,14 +27,12 @@ enum {
   WW_F0 = WW_D0 + 56 * 36,           // [56]
   WW_V0 = WW_F0 + 56,                // [56]  level-0 slack solution
   WW_HJ = WW_V0 + 56,                // [18]
-  WW_A1 = WW_HJ + 18,                // [22][36]
-  WW_B1 = WW_A1 + 22 * 36,           // [22]
-  WW_A2 = WW_B1 + 22,                // [14][36]
-  WW_B2 = WW_A2 + 14 * 36,           // [14]
-  WW_X = WW_B2 + 14,                 // [36]
-  WW_Z0 = WW_X + 36,                 // [36][18]
-  WW_Z1 = WW_Z0 + 36 * 18,           // [36][12]
-  WW_SCR = ((WW_Z1 + 36 * 12 + 3) / 4) * 4,
+  WW_AP = WW_HJ + 18,                // [36][36] equality rows of the levels below level 0, level after level (see WI_LV)
+  WW_BP = WW_AP + WB_POOL * 36,      // [36]
+  WW_X = WW_BP + WB_POOL,            // [36]
+  WW_Z0 = WW_X + 36,                 // [36][18] null-space basis of the levels solved so far ...
+  WW_Z1 = WW_Z0 + 36 * 18,           // [36][18] ... and of the next one (the two alternate)
+  WW_SCR = ((WW_Z1 + 36 * 18 + 3) / 4) * 4,
   // scratch, dynamics phase
   WA_KIN = WW_SCR,
   WA_ACC = WA_KIN + KW_SIZE,         // [24][6] bias spatial acceleration of each body (qdd = 0, no gravity)
@@ -73,7 +71,8 @@ enum {
   WS_END = WS_HP + 4 * 56,
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
-enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_SIZE = 244 };
+enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_LV = 244, WI_SIZE = 260 };
+// WI_LV: [0] number of levels (level 0 included), then per level p >= 1: [2 p] first row in the pool, [2 p + 1] number of rows
 // WI_SC scalars: [0] nW changed flag, [1] rank, [2] n1, [3] n2, [4] iq, [5] ip, [6] status, [7] r1, [8] r2, [9] nD0, [10] done
 
 QM_HD void rot_zyx(const double* e, double* R) {
@@ -285,7 +284,12 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
 }
 
 // The task stack (WbcBase.cpp:240-578 and the stacks of HierarchicalWbc.cpp:23-43 / HierarchicalMpcWbc.cpp:23-31).
-// Row counts to WI_SC: [7] r1, [8] r2, [9] nD0.
+// C.mpc_variant selects the stack below level 0:
+//   0  HierarchicalWbc    : [arm joints (t < init_time) | base height + base angular + ee linear + ee angular + 100 swing] -> [contact force + base xy]
+//   1  HierarchicalMpcWbc : [base height + base angular + base xy + 100 swing] -> [contact force]
+//   2  six-level split of the same tasks (BASELINE config 5's "6 task levels"; SYNTHETIC, the reference has no such stack):
+//      [base height + base angular] -> [ee linear + ee angular] -> [100 swing] -> [base xy] -> [contact force]
+// nD0 to WI_SC[9]; the level table to WI_LV.
 template <class G>
 QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* ud, int mode, double time,
                       double* W, int* WI) {
@@ -293,15 +297,12 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
   const double* ds = W + WA_DES;
   const int nc = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
   const int nsw = 4 - nc;
-  const bool init_stack = (!C.mpc_variant) && (time < C.init_time);
-  const int r1 = C.mpc_variant ? (6 + 3 * nsw) : (init_stack ? 6 : 10 + 3 * nsw);
-  const int r2 = C.mpc_variant ? 12 : 14;
+  const bool init_stack = (C.mpc_variant == 0) && (time < C.init_time);
   const int nD0 = 36 + 5 * nc + 3 * nsw;
-  if (g.tid() == 0) { WI[WI_SC + 7] = r1; WI[WI_SC + 8] = r2; WI[WI_SC + 9] = nD0; }
+  if (g.tid() == 0) WI[WI_SC + 9] = nD0;
   QM_PFOR(g, idx, 18 * 36) W[WW_A0 + idx] = 0.0;
   QM_PFOR(g, idx, 56 * 36) W[WW_D0 + idx] = 0.0;
-  QM_PFOR(g, idx, 22 * 36) W[WW_A1 + idx] = 0.0;
-  QM_PFOR(g, idx, 14 * 36) W[WW_A2 + idx] = 0.0;
+  QM_PFOR(g, idx, WB_POOL * 36) W[WW_AP + idx] = 0.0;
   QM_PFOR(g, idx, 56) { W[WW_F0 + idx] = 0.0; W[WW_V0 + idx] = 0.0; }
   g.sync();
   // level 0, equality rows: floating-base EoM (6), no contact motion (3 nc), zero swing force (3 nsw)
@@ -362,85 +363,104 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
       else { row[1] = -1.0; row[2] = -mu; }
     }
   }
-  // level 1 / level 2 rows (one thread per scalar right-hand side group; matrices are copies of Jacobian rows)
+  // rows of the levels below level 0 (one thread: scalar right-hand sides; the matrices are copies of Jacobian rows)
   if (g.tid() == 0) {
     const double* qm = ms; const double* vm = ms + 24;
     const double* qd = ds; const double* vd = ds + 24;
     const double* bacc = ds + 48;
-    double* A1 = W + WW_A1; double* b1 = W + WW_B1;
-    double* A2 = W + WW_A2; double* b2 = W + WW_B2;
-    int row = 0;
-    if (init_stack) {
-      for (int i = 0; i < 6; ++i) {       // formulateArmJointNomalTrackingTask
-        A1[(row + i) * 36 + 18 + i] = 1.0;
-        b1[row + i] = C.kp_arm_joint[i] * (qd[18 + i] - qm[18 + i]) + C.kd_arm_joint[i] * (vd[18 + i] - vm[18 + i]);
+    double* AP = W + WW_AP; double* bp = W + WW_BP;
+    int row = 0, lev = 1;
+    auto level_begin = [&]() { WI[WI_LV + 2 * lev] = row; };
+    auto level_end = [&]() { WI[WI_LV + 2 * lev + 1] = row - WI[WI_LV + 2 * lev]; ++lev; };
+    auto arm_joints = [&]() {               // formulateArmJointNomalTrackingTask
+      for (int i = 0; i < 6; ++i) {
+        AP[(row + i) * 36 + 18 + i] = 1.0;
+        bp[row + i] = C.kp_arm_joint[i] * (qd[18 + i] - qm[18 + i]) + C.kd_arm_joint[i] * (vd[18 + i] - vm[18 + i]);
       }
       row += 6;
-    } else {
-      // base height
-      A1[row * 36 + 2] = 1.0;
-      b1[row] = bacc[2] + C.kp_base_height * (qd[2] - qm[2]) + C.kd_base_height * (vd[2] - vm[2]);
+    };
+    auto base_height = [&]() {
+      AP[row * 36 + 2] = 1.0;
+      bp[row] = bacc[2] + C.kp_base_height * (qd[2] - qm[2]) + C.kd_base_height * (vd[2] - vm[2]);
       ++row;
-      // base angular
-      {
-        double sz, cz, sy, cy;
-        sincos(qm[3], &sz, &cz); sincos(qm[4], &sy, &cy);
-        const double T[9] = {0, -sz, cy * cz, 0, cz, cy * sz, 1, 0, -sy};
-        const double dz = vd[3], dy = vd[4];
-        const double Td[9] = {0, -cz * dz, -sy * cz * dy - cy * sz * dz, 0, -sz * dz, -sy * sz * dy + cy * cz * dz, 0, 0, -cy * dy};
-        double Rm[9], Rd[9], err[3];
-        rot_zyx(qm + 3, Rm);
-        rot_zyx(qd + 3, Rd);
-        rotation_error_world(Rd, Rm, err);
-        for (int r = 0; r < 3; ++r) {
-          double wm = 0, wdv = 0, acc = 0;
-          for (int c = 0; c < 3; ++c) {
-            wm += T[3 * r + c] * vm[3 + c];
-            wdv += T[3 * r + c] * vd[3 + c];
-            acc += T[3 * r + c] * bacc[3 + c] + Td[3 * r + c] * vd[3 + c];
-          }
-          for (int c = 0; c < 24; ++c) A1[(row + r) * 36 + c] = W[WA_JBA + 24 * r + c];
-          b1[row + r] = acc + C.kp_base_angular * err[r] + C.kd_base_angular * (wdv - wm) - W[WA_DJBV + r];
+    };
+    auto base_angular = [&]() {
+      double sz, cz, sy, cy;
+      sincos(qm[3], &sz, &cz); sincos(qm[4], &sy, &cy);
+      const double T[9] = {0, -sz, cy * cz, 0, cz, cy * sz, 1, 0, -sy};
+      const double dz = vd[3], dy = vd[4];
+      const double Td[9] = {0, -cz * dz, -sy * cz * dy - cy * sz * dz, 0, -sz * dz, -sy * sz * dy + cy * cz * dz, 0, 0, -cy * dy};
+      double Rm[9], Rd[9], err[3];
+      rot_zyx(qm + 3, Rm);
+      rot_zyx(qd + 3, Rd);
+      rotation_error_world(Rd, Rm, err);
+      for (int r = 0; r < 3; ++r) {
+        double wm = 0, wdv = 0, acc = 0;
+        for (int c = 0; c < 3; ++c) {
+          wm += T[3 * r + c] * vm[3 + c];
+          wdv += T[3 * r + c] * vd[3 + c];
+          acc += T[3 * r + c] * bacc[3 + c] + Td[3 * r + c] * vd[3 + c];
         }
-        row += 3;
+        for (int c = 0; c < 24; ++c) AP[(row + r) * 36 + c] = W[WA_JBA + 24 * r + c];
+        bp[row + r] = acc + C.kp_base_angular * err[r] + C.kd_base_angular * (wdv - wm) - W[WA_DJBV + r];
       }
-      if (C.mpc_variant) {
-        for (int r = 0; r < 2; ++r) {
-          A1[(row + r) * 36 + r] = 1.0;
-          b1[row + r] = bacc[r] + C.kp_base_linear * (qd[r] - qm[r]) + C.kd_base_linear * (vd[r] - vm[r]);
-        }
-        row += 2;
-      } else {
-        for (int r = 0; r < 3; ++r) {   // ee linear
-          for (int c = 0; c < 24; ++c) A1[(row + r) * 36 + c] = W[WA_JEE + 24 * r + c];
-          b1[row + r] = C.kp_ee_linear[r] * (ds[78 + r] - ms[72 + r]) + C.kd_ee_linear[r] * (ds[81 + r] - ms[75 + r]) - W[WA_DJEE + r];
-        }
-        row += 3;
-        double err[3];
-        rotation_error_world(ds + 84, ms + 81, err);
-        for (int r = 0; r < 3; ++r) {   // ee angular, base-orientation columns zeroed
-          for (int c = 0; c < 24; ++c) A1[(row + r) * 36 + c] = (c >= 3 && c < 6) ? 0.0 : W[WA_JEE + 24 * (3 + r) + c];
-          b1[row + r] = C.kp_ee_angular[r] * err[r] - C.kd_ee_angular[r] * ms[78 + r] - W[WA_DJEE + 3 + r];
-        }
-        row += 3;
+      row += 3;
+    };
+    auto base_linear = [&]() {
+      for (int r = 0; r < 2; ++r) {
+        AP[(row + r) * 36 + r] = 1.0;
+        bp[row + r] = bacc[r] + C.kp_base_linear * (qd[r] - qm[r]) + C.kd_base_linear * (vd[r] - vm[r]);
       }
-      for (int ft = 0; ft < 4; ++ft) {  // swing legs, weighted (Task::operator*)
+      row += 2;
+    };
+    auto ee_linear = [&]() {
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 24; ++c) AP[(row + r) * 36 + c] = W[WA_JEE + 24 * r + c];
+        bp[row + r] = C.kp_ee_linear[r] * (ds[78 + r] - ms[72 + r]) + C.kd_ee_linear[r] * (ds[81 + r] - ms[75 + r]) - W[WA_DJEE + r];
+      }
+      row += 3;
+    };
+    auto ee_angular = [&]() {               // base-orientation columns zeroed (WbcBase.cpp:553,557)
+      double err[3];
+      rotation_error_world(ds + 84, ms + 81, err);
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 24; ++c) AP[(row + r) * 36 + c] = (c >= 3 && c < 6) ? 0.0 : W[WA_JEE + 24 * (3 + r) + c];
+        bp[row + r] = C.kp_ee_angular[r] * err[r] - C.kd_ee_angular[r] * ms[78 + r] - W[WA_DJEE + 3 + r];
+      }
+      row += 3;
+    };
+    auto swing_legs = [&]() {               // weighted (Task::operator*, HierarchicalWbc.cpp:29)
+      for (int ft = 0; ft < 4; ++ft) {
         if ((mode >> (3 - ft)) & 1) continue;
         for (int d = 0; d < 3; ++d) {
           const double acc = C.kp_swing * (ds[54 + 3 * ft + d] - ms[48 + 3 * ft + d]) + C.kd_swing * (ds[66 + 3 * ft + d] - ms[60 + 3 * ft + d]);
-          for (int c = 0; c < 24; ++c) A1[(row + d) * 36 + c] = C.swing_weight * W[WA_JF + (3 * ft + d) * 24 + c];
-          b1[row + d] = C.swing_weight * (acc - W[WA_DJV + 3 * ft + d]);
+          for (int c = 0; c < 24; ++c) AP[(row + d) * 36 + c] = C.swing_weight * W[WA_JF + (3 * ft + d) * 24 + c];
+          bp[row + d] = C.swing_weight * (acc - W[WA_DJV + 3 * ft + d]);
         }
         row += 3;
       }
+    };
+    auto contact_force = [&]() {
+      for (int i = 0; i < 12; ++i) { AP[(row + i) * 36 + 24 + i] = 1.0; bp[row + i] = ud[i]; }
+      row += 12;
+    };
+    if (C.mpc_variant == 2) {
+      level_begin(); base_height(); base_angular(); level_end();
+      level_begin(); ee_linear(); ee_angular(); level_end();
+      level_begin(); swing_legs(); level_end();
+      level_begin(); base_linear(); level_end();
+      level_begin(); contact_force(); level_end();
+    } else if (C.mpc_variant == 1) {
+      level_begin(); base_height(); base_angular(); base_linear(); swing_legs(); level_end();
+      level_begin(); contact_force(); level_end();
+    } else {
+      level_begin();
+      if (init_stack) arm_joints();
+      else { base_height(); base_angular(); ee_linear(); ee_angular(); swing_legs(); }
+      level_end();
+      level_begin(); contact_force(); base_linear(); level_end();
     }
-    // level 2: contact force (12) [+ base linear (2)]
-    for (int i = 0; i < 12; ++i) { A2[i * 36 + 24 + i] = 1.0; b2[i] = ud[i]; }
-    if (!C.mpc_variant)
-      for (int r = 0; r < 2; ++r) {
-        A2[(12 + r) * 36 + r] = 1.0;
-        b2[12 + r] = bacc[r] + C.kp_base_linear * (qd[r] - qm[r]) + C.kd_base_linear * (vd[r] - vm[r]);
-      }
+    WI[WI_LV] = lev;
   }
   g.sync();
 }
@@ -864,7 +884,7 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
 // HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
 template <class G>
 QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
-  const int r1 = WI[WI_SC + 7], r2 = WI[WI_SC + 8], nD0 = WI[WI_SC + 9];
+  const int nD0 = WI[WI_SC + 9];
   if (g.tid() == 0) WI[WI_SC + 6] = 0;
   g.sync();
   // ---- level 0
@@ -877,24 +897,33 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
   if (n1 > 18) { n1 = 18; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
   QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + c] : 0.0; }
   g.sync(); QM_TICK(38);
-  // ---- level 1 in the coordinates x = x0 + Z0 z
-  int n2 = 0;
-  if (n1 > 0) {
-    QM_PFOR(g, idx, r1 * 18) {
+  // ---- levels 1 .. nlev - 1, each in the coordinates x = x_prev + Z z of the null space the levels above leave
+  //      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
+  //      full stance -- changes nothing)
+  const int nlev = WI[WI_LV];
+  double* Zc = W + WW_Z0;                   // current basis [36][18]
+  double* Zn = W + WW_Z1;                   // next one
+  int n = n1;
+  for (int p = 1; p < nlev && n > 0; ++p) {
+    const int off = WI[WI_LV + 2 * p], r = WI[WI_LV + 2 * p + 1];
+    if (r == 0) continue;
+    const double* Ap = W + WW_AP + 36 * off;
+    const double* bpv = W + WW_BP + off;
+    QM_PFOR(g, idx, r * 18) {
       const int i = idx / 18, c = idx % 18;
       double s = 0.0;
-      if (c < n1) for (int k = 0; k < 36; ++k) s += W[WW_A1 + 36 * i + k] * W[WW_Z0 + 18 * k + c];
+      if (c < n) for (int k = 0; k < 36; ++k) s += Ap[36 * i + k] * Zc[18 * k + c];
       W[WS_GA + idx] = s;
     }
-    QM_PFOR(g, i, r1) {
-      double s = W[WW_B1 + i];
-      for (int k = 0; k < 36; ++k) s -= W[WW_A1 + 36 * i + k] * W[WW_X + k];
+    QM_PFOR(g, i, r) {
+      double s = bpv[i];
+      for (int k = 0; k < 36; ++k) s -= Ap[36 * i + k] * W[WW_X + k];
       W[WS_GB + i] = s;
     }
     QM_PFOR(g, idx, nD0 * 18) {
       const int i = idx / 18, c = idx % 18;
       double s = 0.0;
-      if (c < n1) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * W[WW_Z0 + 18 * k + c];
+      if (c < n) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * Zc[18 * k + c];
       W[WS_GG + idx] = s;
     }
     QM_PFOR(g, i, nD0) {
@@ -903,57 +932,27 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
       W[WS_Gg + i] = s;
     }
     g.sync(); QM_TICK(39);
-    wbc_gi(g, n1, r1, nD0, W, WI);
+    wbc_gi(g, n, r, nD0, W, WI);
     QM_PFOR(g, k, 36) {
       double s = 0.0;
-      for (int c = 0; c < n1; ++c) s += W[WW_Z0 + 18 * k + c] * W[WS_Z + c];
+      for (int c = 0; c < n; ++c) s += Zc[18 * k + c] * W[WS_Z + c];
       W[WW_X + k] += s;
     }
     g.sync();
-    // kernel of A1 Z0 (FullPivLU basis) -> Z1 = Z0 N1
-    kernel_basis_lu(g, W + WS_GA, r1, n1, 18, W + WS_QR, W + WS_Q, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
-    n2 = n1 - WI[WI_SC + 1];
-    if (n2 > 12) { n2 = 12; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
-    QM_PFOR(g, idx, 36 * 12) {
-      const int i = idx / 12, c = idx % 12;
-      double s = 0.0;
-      if (c < n2) for (int k = 0; k < n1; ++k) s += W[WW_Z0 + 18 * i + k] * W[WS_Q + 18 * k + c];
-      W[WW_Z1 + idx] = s;
+    if (p + 1 < nlev) {
+      // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
+      kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_QR, W + WS_Q, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+      const int nn = n - WI[WI_SC + 1];
+      QM_PFOR(g, idx, 36 * 18) {
+        const int i = idx / 18, c = idx % 18;
+        double s = 0.0;
+        if (c < nn) for (int k = 0; k < n; ++k) s += Zc[18 * i + k] * W[WS_Q + 18 * k + c];
+        Zn[idx] = s;
+      }
+      g.sync(); QM_TICK(42);
+      double* t_ = Zc; Zc = Zn; Zn = t_;
+      n = nn;
     }
-    g.sync(); QM_TICK(42);
-  }
-  // ---- level 2 in the coordinates x = x1 + Z1 z
-  if (n2 > 0) {
-    QM_PFOR(g, idx, r2 * 18) {
-      const int i = idx / 18, c = idx % 18;
-      double s = 0.0;
-      if (c < n2) for (int k = 0; k < 36; ++k) s += W[WW_A2 + 36 * i + k] * W[WW_Z1 + 12 * k + c];
-      W[WS_GA + idx] = s;
-    }
-    QM_PFOR(g, i, r2) {
-      double s = W[WW_B2 + i];
-      for (int k = 0; k < 36; ++k) s -= W[WW_A2 + 36 * i + k] * W[WW_X + k];
-      W[WS_GB + i] = s;
-    }
-    QM_PFOR(g, idx, nD0 * 18) {
-      const int i = idx / 18, c = idx % 18;
-      double s = 0.0;
-      if (c < n2) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * W[WW_Z1 + 12 * k + c];
-      W[WS_GG + idx] = s;
-    }
-    QM_PFOR(g, i, nD0) {
-      double s = W[WW_F0 + i] + W[WW_V0 + i];
-      for (int k = 0; k < 36; ++k) s -= W[WW_D0 + 36 * i + k] * W[WW_X + k];
-      W[WS_Gg + i] = s;
-    }
-    g.sync(); QM_TICK(43);
-    wbc_gi(g, n2, r2, nD0, W, WI);
-    QM_PFOR(g, k, 36) {
-      double s = 0.0;
-      for (int c = 0; c < n2; ++c) s += W[WW_Z1 + 12 * k + c] * W[WS_Z + c];
-      W[WW_X + k] += s;
-    }
-    g.sync();
   }
   // ---- torque recovery: tau = [M_j, -J_j'] x + h_j   (rows 0..17 of D0)
   QM_PFOR(g, i, 54) {

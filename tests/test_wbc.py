@@ -13,7 +13,7 @@ EXPECTED = 1e-8
 def run_backend(update, g):
     """update(variant, idx, x_des, u_des, rbd, mode, period, time, u_last) -> cmd for the selected rows."""
     cmd = np.zeros_like(g["cmd"])
-    for variant in (0, 1):
+    for variant in (0, 1, 2):          # HierarchicalWbc, HierarchicalMpcWbc, six-level synthetic split
         idx = np.where(g["variant"] == variant)[0]
         cmd[idx] = update(variant, idx, g["x_des"][idx], g["u_des"][idx], g["rbd"][idx], g["mode"][idx], g["period"][idx],
                           g["time"][idx], g["u_last"][idx])
@@ -23,9 +23,18 @@ def run_backend(update, g):
 def check_golden(cmd, g, tol):
     """Every solve within `tol`; the typical solve far below it. (All-feet-in-the-air stacks leave the lowest level rank
     deficient, where only the 1e-12 regularisation selects the solution: those solves carry ~1e-7 of rounding.)"""
-    errs = np.array([rel_l2(cmd[b], g["cmd"][b]) for b in range(cmd.shape[0])])
-    assert errs.max() < tol, (int(errs.argmax()), int(g["mode"][errs.argmax()]), errs.max())
-    assert np.median(errs) < 1e-10, np.median(errs)
+    # Solves where a level is degenerate beyond the oracle solver's strict margins (inherited rows violated by accumulated
+    # rounding; `relaxed` in the golden file) have no well-defined answer two different active-set paths must agree on: they are
+    # not compared. That never happens for the reference's own 3-level stacks in this file and is common for the deeper,
+    # SYNTHETIC six-level stack (8- and 2-dimensional null spaces under 56 inherited inequality rows).
+    ok = ~np.isnan(g["cmd"][:, 0]) & ((g["relaxed"] == 0) | (g["variant"] < 2))
+    for variant in (0, 1):
+        assert ok[g["variant"] == variant].all()
+    assert ok[g["variant"] == 2].sum() >= 2
+    errs = np.array([rel_l2(cmd[b], g["cmd"][b]) if ok[b] else 0.0 for b in range(cmd.shape[0])])
+    assert errs.max() < tol, (int(errs.argmax()), int(g["mode"][errs.argmax()]), int(g["variant"][errs.argmax()]), errs.max())
+    assert np.median(errs[ok]) < 1e-10, np.median(errs[ok])
+    assert np.isfinite(cmd).all()
     return errs.max()
 
 
@@ -212,3 +221,66 @@ def test_cport_matches_full_size_golden_subset(descs):
     assert ok.sum() >= 0.95 * sub
     errs = np.array([rel_l2(cmd[b], g["cmd"][b]) for b in range(sub) if ok[b]])
     assert np.median(errs) < 1e-10 and errs.max() < 1e-7, (np.median(errs), errs.max())
+
+
+def six_level_invariants(cmd, st, W, m, P, n_check):
+    """Whatever the stack below level 0 does, a solve without status bits keeps the level-0 equalities: floating-base equations of
+    motion, zero swing-foot force, zero stance-foot acceleration (strict hierarchy, HoQp.cpp:126-133)."""
+    from oracle import gait as G
+    from oracle.wbc import Wbc
+    checked = 0
+    for b in range(n_check):
+        if st[b] != 0:
+            continue
+        s = Wbc(m, P).update_measured(W.rbd[b])
+        qdd, f = cmd[b, :24], cmd[b, 24:36]
+        flags = G.stance_legs(int(W.mode[b]))
+        res = s["M"][:6] @ qdd + s["nle"][:6] - s["J"].T[:6] @ f
+        assert np.abs(res).max() < 1e-6 * max(1.0, np.abs(s["nle"][:6]).max()), (b, np.abs(res).max())
+        acc = (s["J"] @ qdd + s["dJ"] @ s["v"]).reshape(4, 3)
+        for leg in range(4):
+            if flags[leg]:
+                assert np.abs(acc[leg]).max() < 1e-6 * max(1.0, np.abs(qdd).max()), (b, leg)
+            else:
+                assert np.abs(f[3 * leg:3 * leg + 3]).max() < 1e-8
+        checked += 1
+    return checked
+
+
+def test_six_level_stack_cport_keeps_level0(descs, oracle_inputs):
+    """The SYNTHETIC six-level stack (mpc_variant 2; BASELINE config 5's "6 task levels"): level-0 invariants on the CPU port."""
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    m, P = oracle_inputs
+    W = workload.WbcWorkload(64, seed=31)
+    W.mode[:16] = np.arange(16)
+    W.wbc.mpc_variant = 2
+    ul = W.u_last.copy()
+    cmd, st = abi_fill.cport_wbc(W.model, W.wbc, W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time, ul, threads=4)
+    assert ((st & ~2) == 0).all() and np.isfinite(cmd).all()
+    assert six_level_invariants(cmd, st, W, m, P, 64) >= 40
+
+
+@pytest.mark.gpu
+def test_six_level_stack_cuda(descs, oracle_inputs):
+    """Six-level synthetic stack on the device: equals the CPU port (same algorithm) on the solves without status bits, keeps the
+    level-0 invariants, and completes the full-size batch."""
+    import qm_door_b200 as q
+    from oracle import abi_fill
+    from qm_door_b200 import workload
+    m, P = oracle_inputs
+    B = 4096
+    W = workload.WbcWorkload(B, seed=32)
+    W.wbc.mpc_variant = 2
+    ctx = q.WbcContext(W.model, W.wbc, B)
+    ctx.update(W.x_des, W.u_last, W.rbd, W.mode, W.period, W.time)
+    cmd, st = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)
+    ctx.close()
+    assert ((st & ~2) == 0).all() and np.isfinite(cmd).all()
+    sub = 512
+    ul = W.u_last[:sub].copy()
+    ref, sr = abi_fill.cport_wbc(W.model, W.wbc, W.x_des[:sub], W.u_des[:sub], W.rbd[:sub], W.mode[:sub], W.period[:sub], W.time[:sub], ul, threads=8)
+    clean = (st[:sub] == 0) & (sr == 0)
+    errs = np.array([rel_l2(cmd[b], ref[b]) for b in range(sub) if clean[b]])
+    assert clean.mean() > 0.5 and np.median(errs) < 1e-9 and (errs < 1e-5).mean() > 0.95, (clean.mean(), np.median(errs), (errs < 1e-5).mean())
+    assert six_level_invariants(cmd, st, W, m, P, 128) >= 60
