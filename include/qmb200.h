@@ -183,6 +183,14 @@ int qmb200_wbc_batch(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_d
                      const double* period, const double* time, double* cmd, int32_t* status);
 int qmb200_wbc_batch_dev(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_des, const double* rbd, const int32_t* mode,
                          const double* period, const double* time, double* cmd, int32_t* status);
+/* One solve with what the reference's HoQp objects expose per level (qm_wbc/include/qm_wbc/HoQp.h:21-36: getSolutions,
+ * getStackedZMatrix, getStackedSlackSolutions): diagnostic entry (host buffers, one solve, does not touch the context's inputLast_
+ * state: u_last[30] is passed in). levels[QMB200_WBC_LEVELS_SIZE]: per level p (6 records of 685 doubles): [columns n_p of the stacked
+ * null-space basis | x after the level (36) | stacked Z after the level (36 x 18 row major, n_p columns valid; Eigen FullPivLU basis as
+ * HoQp.cpp:129 builds it)], then the number of levels of the stack, then the level-0 slack (56). */
+#define QMB200_WBC_LEVELS_SIZE (6 * (37 + 36 * 18) + 1 + 56)
+int qmb200_wbc_levels(qmb200_wbc_ctx* ctx, const double* x_des, const double* u_des, const double* rbd, int32_t mode, double period,
+                      double time, const double* u_last, double* cmd, int32_t* status, double* levels);
 int qmb200_wbc_sync(qmb200_wbc_ctx* ctx);
 int qmb200_wbc_wait_stream(qmb200_wbc_ctx* ctx, void* stream);   /* see qmb200_wait_stream */
 void* qmb200_wbc_stream(qmb200_wbc_ctx* ctx);

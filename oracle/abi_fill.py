@@ -117,6 +117,19 @@ def cport_wbc(md, wd, xd, ud, rbdm, mode, period, time, u_last, threads=1):
     return cmd, status
 
 
+def cport_wbc_levels(md, wd, xd, ud, rbdm, mode, period, time, u_last):
+    """One solve on the CPU port with the per-level record -> (cmd, status, levels list, level-0 slack)."""
+    from qm_door_b200 import unpack_wbc_levels
+    lib = load_cport()
+    dp = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+    cmd, st, lv = np.zeros(54), C.c_int32(), np.zeros(lib.cport_wbc_levels_size())
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (xd, ud, rbdm, u_last)]
+    lib.cport_wbc_levels(C.byref(md), C.byref(wd), keep[0].ctypes.data_as(C.c_void_p), keep[1].ctypes.data_as(C.c_void_p),
+                         keep[2].ctypes.data_as(C.c_void_p), int(mode), C.c_double(period), C.c_double(time),
+                         keep[3].ctypes.data_as(C.c_void_p), cmd.ctypes.data_as(C.c_void_p), C.byref(st), lv.ctypes.data_as(C.c_void_p))
+    return (cmd, st.value) + unpack_wbc_levels(lv)
+
+
 def cport_forward_dynamics(md, gravity, rbdm, tau, mode, dt, beta=0.0, threads=1):
     lib = load_cport()
     n = rbdm.shape[0]

@@ -238,6 +238,17 @@ void cport_actuator(const qmb200_actuator_desc* D, int n, const int64_t* time_ns
   }
 }
 
+// One solve with the per-level record of the hierarchy (WBL_* layout of qm_wbc.h).
+int cport_wbc_levels_size() { return WBL_SIZE; }
+void cport_wbc_levels(const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd, const double* ud, const double* rbd, int mode,
+                      double period, double time, const double* u_last, double* cmd, int32_t* status, double* levels) {
+  std::vector<double> W(WW_SIZE);
+  std::vector<int> WI(WI_SIZE);
+  int st = 0;
+  wbc_update(SerialGroup(), *M, *C, xd, ud, rbd, mode, period, time, u_last, W.data(), WI.data(), cmd, &st, levels);
+  *status = st;
+}
+
 // Forward-dynamics step (qm_sim.h), n problems.
 void cport_forward_dynamics(const qmb200_model_desc* M, double gravity, int n, const double* rbd, const double* tau, const int32_t* mode,
                             double dt, double beta, double* rbd_next, double* f, int32_t* status, int threads) {

@@ -362,6 +362,18 @@ def load_wbc(model, task_info=DEFAULT_TASK):
     return w
 
 
+def unpack_wbc_levels(lv):
+    """levels[QMB200_WBC_LEVELS_SIZE] -> ([dict(n, x[36], Z[36, n])] for the levels of the stack, level-0 slack[56])."""
+    rec = 37 + 36 * 18
+    nlev = int(lv[6 * rec])
+    out = []
+    for p in range(nlev):
+        r = lv[p * rec:(p + 1) * rec]
+        n = int(r[0])
+        out.append(dict(n=n, x=r[1:37].copy(), Z=r[37:].reshape(36, 18)[:, :n].copy()))
+    return out, lv[6 * rec + 1:6 * rec + 57].copy()
+
+
 class WbcContext:
     """Mirror of qm::WbcBase / HierarchicalWbc for a batch of independent solves:
     update() has the argument meaning of WbcBase::update (qm_wbc/include/qm_wbc/WbcBase.h:31-32) and returns [x*(36); tau(18)]."""
@@ -444,6 +456,16 @@ class WbcContext:
                                                 _dev(u_des, (B, 30), f8, "u_des", d), _dev(cmd, (B, 54), f8, "cmd", d),
                                                 _dev(q, (B, 18), f8, "q", d), _dev(v, (B, 18), f8, "v", d),
                                                 _dev(tau, (B, 18), f8, "tau", d), _dev(status, (B,), np.int32, "status", d)))
+
+    def levels(self, x_des, u_des, rbd, mode, period, time, u_last):
+        """One solve with what the reference's HoQp objects expose per level (HoQp.h:21-36) -> (cmd[54], status, [dict(n, x, Z)] per
+        level, level-0 slack[56]). Diagnostic entry; does not touch the per-solve inputLast_ state of the context."""
+        f = lambda a, n: _host(a, (n,), np.float64, "argument")
+        LV = 6 * (37 + 36 * 18) + 1 + 56
+        cmd, st, lv = np.zeros(54), C.c_int32(), np.zeros(LV)
+        _check(self.L.qmb200_wbc_levels(self.h, _p(f(x_des, 30)), _p(f(u_des, 30)), _p(f(rbd, 55)), int(mode), C.c_double(period), C.c_double(time),
+                                        _p(f(u_last, 30)), _p(cmd), C.byref(st), _p(lv)))
+        return (cmd, st.value) + unpack_wbc_levels(lv)
 
     def forward_dynamics(self, rbd, tau, mode, dt, beta=0.0):
         """One forward-dynamics step behind the actuator (stance feet of `mode` held by point contacts; see include/qmb200.h)

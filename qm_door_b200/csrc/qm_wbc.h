@@ -71,6 +71,10 @@ enum {
   WS_END = WS_HP + 4 * 56,
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
+// per-level record of a solve (wbc_update's `levels` output): level p at WBL_LEVEL * p: [number of null-space columns n_p | x after
+// the level (36) | stacked Z after the level (36 x 18, n_p columns valid)]; after the WB_MAXLEV records: number of levels, then the
+// level-0 slack (56).
+enum { WBL_N = 0, WBL_X = 1, WBL_Z = 37, WBL_LEVEL = 37 + 36 * 18, WBL_NLEV = WB_MAXLEV * WBL_LEVEL, WBL_V0 = WBL_NLEV + 1, WBL_SIZE = WBL_V0 + 56 };
 enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_LV = 244, WI_SIZE = 260 };
 // WI_LV: [0] number of levels (level 0 included), then per level p >= 1: [2 p] first row in the pool, [2 p + 1] number of rows
 // WI_SC scalars: [0] nW changed flag, [1] rank, [2] n1, [3] n2, [4] iq, [5] ip, [6] status, [7] r1, [8] r2, [9] nD0, [10] done
@@ -883,7 +887,7 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
 
 // HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
 template <class G>
-QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
+QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status, double* levels = nullptr) {
   const int nD0 = WI[WI_SC + 9];
   if (g.tid() == 0) WI[WI_SC + 6] = 0;
   g.sync();
@@ -897,6 +901,15 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
   if (n1 > 18) { n1 = 18; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
   QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + c] : 0.0; }
   g.sync(); QM_TICK(38);
+  if (levels != nullptr) {
+    QM_PFOR(g, i, WBL_SIZE) levels[i] = 0.0;
+    g.sync();
+    if (g.tid() == 0) { levels[WBL_N] = (double)n1; levels[WBL_NLEV] = (double)WI[WI_LV]; }
+    QM_PFOR(g, i, 36) levels[WBL_X + i] = W[WW_X + i];
+    QM_PFOR(g, i, 36 * 18) levels[WBL_Z + i] = W[WW_Z0 + i];
+    QM_PFOR(g, i, 56) levels[WBL_V0 + i] = W[WW_V0 + i];
+    g.sync();
+  }
   // ---- levels 1 .. nlev - 1, each in the coordinates x = x_prev + Z z of the null space the levels above leave
   //      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
   //      full stance -- changes nothing)
@@ -904,9 +917,19 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
   double* Zc = W + WW_Z0;                   // current basis [36][18]
   double* Zn = W + WW_Z1;                   // next one
   int n = n1;
-  for (int p = 1; p < nlev && n > 0; ++p) {
+  for (int p = 1; p < nlev; ++p) {
     const int off = WI[WI_LV + 2 * p], r = WI[WI_LV + 2 * p + 1];
-    if (r == 0) continue;
+    if (r == 0 || n == 0) {                  // empty level, or no freedom left: x and the basis stay as they are
+      if (levels != nullptr) {
+        double* L = levels + WBL_LEVEL * p;
+        const int nz = (p + 1 < nlev) ? n : 0;
+        if (g.tid() == 0) L[WBL_N] = (double)nz;
+        QM_PFOR(g, i, 36) L[WBL_X + i] = W[WW_X + i];
+        QM_PFOR(g, idx, 36 * 18) L[WBL_Z + idx] = (idx % 18 < nz) ? Zc[idx] : 0.0;
+        g.sync();
+      }
+      continue;
+    }
     const double* Ap = W + WW_AP + 36 * off;
     const double* bpv = W + WW_BP + off;
     QM_PFOR(g, idx, r * 18) {
@@ -953,6 +976,14 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
       double* t_ = Zc; Zc = Zn; Zn = t_;
       n = nn;
     }
+    if (levels != nullptr) {
+      double* L = levels + WBL_LEVEL * p;
+      const int nz = (p + 1 < nlev) ? n : 0;           // the last level's null space is never formed
+      if (g.tid() == 0) L[WBL_N] = (double)nz;
+      QM_PFOR(g, i, 36) L[WBL_X + i] = W[WW_X + i];
+      QM_PFOR(g, idx, 36 * 18) L[WBL_Z + idx] = (idx % 18 < nz) ? Zc[idx] : 0.0;
+      g.sync();
+    }
   }
   // ---- torque recovery: tau = [M_j, -J_j'] x + h_j   (rows 0..17 of D0)
   QM_PFOR(g, i, 54) {
@@ -974,16 +1005,19 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status) {
 }
 
 // One whole-body-control solve: WbcBase::update + HierarchicalWbc::update.
+// levels (optional, WBL_SIZE doubles): what the reference's HoQp objects expose per level (qm_wbc/include/qm_wbc/HoQp.h:21-36):
+// getSolutions() and getStackedZMatrix() after every level, getStackedSlackSolutions() of level 0 (the only level with
+// inequality rows in the reference's stacks). See WBL_* for the layout.
 template <class G>
 QM_HDN void wbc_update(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* xd, const double* ud,
                        const double* rbd, int mode, double period, double time, const double* u_last, double* W, int* WI,
-                       double* cmd, int* status) {
+                       double* cmd, int* status, double* levels = nullptr) {
   QM_TICK(-1);
   wbc_dynamics(g, M, C, rbd, xd, ud, u_last, period, W);
   QM_TICK(33);
   wbc_tasks(g, M, C, ud, mode & 15, time, W, WI);
   QM_TICK(34);
-  wbc_solve(g, W, WI, cmd, status);
+  wbc_solve(g, W, WI, cmd, status, levels);
   QM_TICK(45);
 }
 

@@ -1185,6 +1185,7 @@ int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, 
 #include "qm_sim.h"
 
 constexpr int kWbcInDoubles = 30 + 30 + 56 + 32;   // xd, ud, rbd (padded), u_last (padded)
+static_assert(QMB200_WBC_LEVELS_SIZE == WBL_SIZE, "include/qmb200.h and qm_wbc.h agree on the per-level record");
 constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
 
 // CTA per solve: rigid-body dynamics of both configurations, task stack, 3-level hierarchical QP, torque recovery.
@@ -1202,6 +1203,18 @@ __global__ void __launch_bounds__(128) k_wbc(int B, const qmb200_model_desc* M, 
   __syncthreads();
   wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode[b], period[b], time[b], in + 116, W, WI, cmd + 54 * b, status + b);
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
+}
+
+// One solve with the per-level record of the hierarchy (HoQp accessors): diagnostic entry, not on the hot path
+__global__ void __launch_bounds__(128) k_wbc_levels(const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* in60_55_30, int mode,
+                                                     double period, double time, double* cmd, int32_t* status, double* levels) {
+  extern __shared__ double smem[];
+  double* W = smem;
+  double* in = smem + WW_SIZE;
+  int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
+  for (int i = threadIdx.x; i < 145; i += blockDim.x) in[i] = in60_55_30[i];          // xd(30) ud(30) rbd(55) u_last(30)
+  __syncthreads();
+  wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode, period, time, in + 115, W, WI, cmd, status, levels);
 }
 
 // ---- control law + simulated actuator with transport delay: warp per problem, lane per joint
@@ -1355,6 +1368,29 @@ int qmb200_wbc_kernel_time(qmb200_wbc_ctx* c, double* total_ms, int64_t* launche
   if (total_ms) *total_ms = c->total_ms;
   if (launches) *launches = c->launches;
   if (reset) { c->total_ms = 0.0; c->launches = 0; }
+  return 0;
+}
+
+int qmb200_wbc_levels(qmb200_wbc_ctx* c, const double* x_des, const double* u_des, const double* rbd, int32_t mode, double period, double time,
+                      const double* u_last, double* cmd, int32_t* status, double* levels) {
+  if (!c || !x_des || !u_des || !rbd || !u_last || !cmd || !status || !levels) return fail("qmb200_wbc_levels: null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  double h_in[145];
+  memcpy(h_in, x_des, 30 * sizeof(double)); memcpy(h_in + 30, u_des, 30 * sizeof(double));
+  memcpy(h_in + 60, rbd, 55 * sizeof(double)); memcpy(h_in + 115, u_last, 30 * sizeof(double));
+  double* d = nullptr; int32_t* ds = nullptr;
+  const size_t nd = 145 + 54 + QMB200_WBC_LEVELS_SIZE;
+  CUDA_OK(cudaMallocAsync(&d, nd * sizeof(double), c->stream));
+  CUDA_OK(cudaMallocAsync(&ds, sizeof(int32_t), c->stream));
+  CUDA_OK(cudaMemcpyAsync(d, h_in, sizeof(h_in), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaFuncSetAttribute(k_wbc_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+  k_wbc_levels<<<1, 128, kWbcSmemBytes, c->stream>>>(c->dM, c->dC, d, mode, period, time, d + 145, ds, d + 199);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(cmd, d + 145, 54 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(levels, d + 199, QMB200_WBC_LEVELS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(status, ds, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaFreeAsync(d, c->stream)); CUDA_OK(cudaFreeAsync(ds, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
