@@ -1189,7 +1189,10 @@ static_assert(QMB200_WBC_LEVELS_SIZE == WBL_SIZE, "include/qmb200.h and qm_wbc.h
 constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
 
 // CTA per solve: rigid-body dynamics of both configurations, task stack, 3-level hierarchical QP, torque recovery.
-__global__ void __launch_bounds__(128) k_wbc(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
+#ifndef QM_WBC_THREADS
+#define QM_WBC_THREADS 128
+#endif
+__global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
                                               const double* ud, const double* rbd, const int32_t* mode, const double* period,
                                               const double* time, double* u_last, double* cmd, int32_t* status) {
   const int b = blockIdx.x;
@@ -1273,7 +1276,7 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
                       const double* period, const double* time, double* cmd, int32_t* status) {
   wbc_harvest(c);
   CUDA_OK(cudaEventRecord(c->e0, c->stream));
-  k_wbc<<<c->B, 128, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, cmd, status);
+  k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, cmd, status);
   CUDA_OK(cudaEventRecord(c->e1, c->stream));
   CUDA_OK(cudaGetLastError());
   c->pending = true;
