@@ -213,11 +213,11 @@ int cport_wbc_batch(const qmb200_model_desc* M, const qmb200_wbc_desc* C, int B,
                     const double* rbd, const int32_t* mode, const double* period, const double* time, double* u_last,
                     double* cmd, int32_t* status, int threads) {
   parallel_for(B, threads, [&](int b) {
-    std::vector<double> W(WW_SIZE);
+    std::vector<double> W(WW_SIZE), Wc(WC_SIZE);
     std::vector<int> WI(WI_SIZE);
     int st = 0;
     wbc_update(SerialGroup(), *M, *C, xd + 30 * b, ud + 30 * b, rbd + 55 * b, mode[b], period[b], time[b], u_last + 30 * b,
-               W.data(), WI.data(), cmd + 54 * b, &st);
+               W.data(), Wc.data(), WI.data(), cmd + 54 * b, &st);
     status[b] = st;
     memcpy(u_last + 30 * b, ud + 30 * b, sizeof(double) * 30);
   });
@@ -242,10 +242,10 @@ void cport_actuator(const qmb200_actuator_desc* D, int n, const int64_t* time_ns
 int cport_wbc_levels_size() { return WBL_SIZE; }
 void cport_wbc_levels(const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd, const double* ud, const double* rbd, int mode,
                       double period, double time, const double* u_last, double* cmd, int32_t* status, double* levels) {
-  std::vector<double> W(WW_SIZE);
+  std::vector<double> W(WW_SIZE), Wc(WC_SIZE);
   std::vector<int> WI(WI_SIZE);
   int st = 0;
-  wbc_update(SerialGroup(), *M, *C, xd, ud, rbd, mode, period, time, u_last, W.data(), WI.data(), cmd, &st, levels);
+  wbc_update(SerialGroup(), *M, *C, xd, ud, rbd, mode, period, time, u_last, W.data(), Wc.data(), WI.data(), cmd, &st, levels);
   *status = st;
 }
 

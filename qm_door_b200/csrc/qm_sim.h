@@ -13,7 +13,7 @@
 namespace qm {
 
 enum { FD_LD = 37 };                         // leading dimension of the KKT matrix | right-hand side (at most 36 unknowns)
-enum { FDW_K = WW_D0, FDW_SOL = WW_AP, FDW_QN = WW_AP + 40 };   // storage in the (unused) task area of the controller's workspace
+enum { FDW_K = WW_D0, FDW_SOL = WW_Z0, FDW_QN = WW_Z0 + 40 };   // storage in the (unused) task / basis area of the controller's workspace
 static_assert(36 * FD_LD <= 56 * 36, "KKT matrix fits in the D0 block");
 
 // rbd[55] state, tau[18] joint torques, mode (stance mask), dt, beta (velocity stabilisation of the contact constraint, 0..1)

@@ -20,19 +20,24 @@ enum { WB_NX = 36, WB_ND0 = 56, WB_POOL = 36, WB_MAXLEV = 6, WB_MAXW = 36, WB_QR
 #define QM_WBC_EPS 1e-12        // HoQp.cpp:66
 
 // ---- workspace (doubles)
+// The equality rows of all levels are written once by the task builder and then only streamed (least-squares build, A Z
+// products): they live in a separate "cold" block Wc -- global memory on the device (16 KB per solve, L2 traffic of a few hundred
+// bytes per phase), so that four solves fit in the shared memory of an SM; on the host it is just another array.
 enum {
-  WW_A0 = 0,                         // [18][36]
-  WW_B0 = WW_A0 + 18 * 36,           // [18]
-  WW_D0 = WW_B0 + 18,                // [56][36]
+  WC_A0 = 0,                         // [18][36] level-0 equality rows
+  WC_B0 = WC_A0 + 18 * 36,           // [18]
+  WC_AP = WC_B0 + 18,                // [36][36] equality rows of the levels below level 0, level after level (see WI_LV)
+  WC_BP = WC_AP + WB_POOL * 36,      // [36]
+  WC_SIZE = ((WC_BP + WB_POOL + 3) / 4) * 4
+};
+enum {
+  WW_D0 = 0,                         // [56][36]
   WW_F0 = WW_D0 + 56 * 36,           // [56]
   WW_V0 = WW_F0 + 56,                // [56]  level-0 slack solution
   WW_HJ = WW_V0 + 56,                // [18]
-  WW_AP = WW_HJ + 18,                // [36][36] equality rows of the levels below level 0, level after level (see WI_LV)
-  WW_BP = WW_AP + WB_POOL * 36,      // [36]
-  WW_X = WW_BP + WB_POOL,            // [36]
-  WW_Z0 = WW_X + 36,                 // [36][18] null-space basis of the levels solved so far ...
-  WW_Z1 = WW_Z0 + 36 * 18,           // [36][18] ... and of the next one (the two alternate)
-  WW_SCR = ((WW_Z1 + 36 * 18 + 3) / 4) * 4,
+  WW_X = WW_HJ + 18,                 // [36]
+  WW_Z0 = WW_X + 36,                 // [36][18] null-space basis of the levels solved so far (alternates with WW_Z1 below)
+  WW_SCR = ((WW_Z0 + 36 * 18 + 3) / 4) * 4,
   // scratch, dynamics phase
   WA_KIN = WW_SCR,
   WA_ACC = WA_KIN + KW_SIZE,         // [24][6] bias spatial acceleration of each body (qdd = 0, no gravity)
@@ -48,34 +53,40 @@ enum {
   WA_MEAS = WA_DJEE + 8,             // q[24] v[24] fpos[12] fvel[12] eep[3] eev[6] eeR[9] = 90
   WA_DES = WA_MEAS + 92,             // q[24] v[24] bacc[6] fpos[12] fvel[12] eep[3] eev[3] eeR[9] = 93
   WA_END = WA_DES + 96,
-  // scratch, solver phase (aliases the dynamics phase)
-  WS_QR = WW_SCR,                    // [92][37] stacked least-squares matrix | rhs
-  WS_Q = WS_QR + WB_QR_ROWS * WB_QR_LD,   // [36][36]
-  WS_RES = WS_Q + 36 * 36,           // [56] constraint residuals
-  WS_VH = WS_RES + 56,               // [92] Householder vector
-  WS_WJ = WS_VH + 92,                // [37]
-  WS_GA = WS_WJ + 40,                // [22][18]  A Z of the current level
+  // scratch, solver phase (aliases the dynamics phase). Lifetimes: level 0 needs the big least-squares matrix QR and nothing of
+  // the levels below it; the levels below need GA .. LS and, from the end of level 1 on, the second null-space basis Z1. QR is
+  // therefore laid over that whole window (three solves per SM instead of two: 74 KB instead of 105 KB of shared memory).
+  WS_GA = WW_SCR,                    // [22][18]  A Z of the current level
   WS_GB = WS_GA + 22 * 18,           // [22]
-  WS_GG = WS_GB + 22,                // [56][18]  D0 Z
+  WS_GG = WS_GB + 22,                // [56][18]  D0 Z; after the level's solve: scratch of its kernel basis
   WS_Gg = WS_GG + 56 * 18,           // [56]
-  WS_J = WS_Gg + 56,                 // [18][18]
+  WS_J = WS_Gg + 56,                 // [18][18]  active-set factor; after the level's solve: its kernel basis N
   WS_RF = WS_J + 324,                // [18][18]
   WS_Z = WS_RF + 324,                // [18]
   WS_D = WS_Z + 18,                  // [18]
   WS_RR = WS_D + 18,                 // [18]
   WS_ZD = WS_RR + 18,                // [18]
   WS_NP = WS_ZD + 18,                // [18]
-  WS_U = WS_NP + 18,                 // [60]
-  WS_CN = WS_U + 60,                 // [40] column norms / misc
-  WS_HP = WS_CN + 40,                // [4][56] partial sums of the Householder steps (4 row chunks per column)
+  WS_LS = WS_NP + 18,                // [40][19] least-squares matrix | rhs of a level below level 0
+  WW_Z1 = WS_LS + 40 * 19,           // [36][18] the other null-space basis (first written at the end of level 1)
+  WS_OVEND = WW_Z1 + 36 * 18,
+  WS_QR = WW_SCR,                    // level 0 and its kernel basis only: [92][37] stacked least-squares matrix | rhs
+  WS_RES = WS_OVEND,                 // [56] constraint residuals
+  WS_VH = WS_RES + 56,               // [92] Householder vector / violation scores
+  WS_WJ = WS_VH + 92,                // [37]
+  WS_HP = WS_WJ + 40,                // [4][56] partial sums of the Householder steps (4 row chunks per column)
+  WS_U = WS_HP,                      // [60] multipliers of the active-set iteration   } never live during a Householder
+  WS_CN = WS_HP + 64,                // [40] column maxima of the kernel basis / scalars of the iteration   } triangularisation
   WS_END = WS_HP + 4 * 56,
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
+static_assert(WB_QR_ROWS * WB_QR_LD <= WS_OVEND - WS_QR, "the level-0 least-squares matrix fits in the window it is laid over");
+static_assert(WA_END <= WS_END, "dynamics scratch fits");
 // per-level record of a solve (wbc_update's `levels` output): level p at WBL_LEVEL * p: [number of null-space columns n_p | x after
 // the level (36) | stacked Z after the level (36 x 18, n_p columns valid)]; after the WB_MAXLEV records: number of levels, then the
 // level-0 slack (56).
 enum { WBL_N = 0, WBL_X = 1, WBL_Z = 37, WBL_LEVEL = 37 + 36 * 18, WBL_NLEV = WB_MAXLEV * WBL_LEVEL, WBL_V0 = WBL_NLEV + 1, WBL_SIZE = WBL_V0 + 56 };
-enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 160, WI_SC = 220, WI_LV = 244, WI_SIZE = 260 };
+enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 136, WI_SC = 192, WI_LV = 216, WI_SIZE = 232 };   // PERM may run into ACT (kernel basis, never during the iteration)
 // WI_LV: [0] number of levels (level 0 included), then per level p >= 1: [2 p] first row in the pool, [2 p + 1] number of rows
 // WI_SC scalars: [0] nW changed flag, [1] rank, [2] n1, [3] n2, [4] iq, [5] ip, [6] status, [7] r1, [8] r2, [9] nD0, [10] done
 
@@ -108,7 +119,7 @@ QM_HD void crm(const double* A, const double* B, double* X) {
 // Bias accelerations (qdd = 0, no gravity) and body forces of the configuration whose position/velocity level is in kw.
 // FB_i = I_i (acc_i + a_g) + V_i x* (I_i V_i)   with a_g = (0; 0, 0, grav) (grav = 9.81 for RNEA, 0 for momentum rates)
 template <class G>
-QM_HDN void bias_forces(G g, const qmb200_model_desc& M, const double* kw, double grav, double* acc, double* fb) {
+QM_HDO void bias_forces(G g, const qmb200_model_desc& M, const double* kw, double grav, double* acc, double* fb) {
   QM_PFOR(g, k, QM_NJ) {
     double S[6], X[6];
     joint_S(M, kw, k, S);
@@ -296,7 +307,7 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
 // nD0 to WI_SC[9]; the level table to WI_LV.
 template <class G>
 QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* ud, int mode, double time,
-                      double* W, int* WI) {
+                      double* W, double* Wc, int* WI) {
   const double* ms = W + WA_MEAS;
   const double* ds = W + WA_DES;
   const int nc = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
@@ -304,9 +315,9 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
   const bool init_stack = (C.mpc_variant == 0) && (time < C.init_time);
   const int nD0 = 36 + 5 * nc + 3 * nsw;
   if (g.tid() == 0) WI[WI_SC + 9] = nD0;
-  QM_PFOR(g, idx, 18 * 36) W[WW_A0 + idx] = 0.0;
+  QM_PFOR(g, idx, 18 * 36) Wc[WC_A0 + idx] = 0.0;
   QM_PFOR(g, idx, 56 * 36) W[WW_D0 + idx] = 0.0;
-  QM_PFOR(g, idx, WB_POOL * 36) W[WW_AP + idx] = 0.0;
+  QM_PFOR(g, idx, WB_POOL * 36) Wc[WC_AP + idx] = 0.0;
   QM_PFOR(g, idx, 56) { W[WW_F0 + idx] = 0.0; W[WW_V0 + idx] = 0.0; }
   g.sync();
   // level 0, equality rows: floating-base EoM (6), no contact motion (3 nc), zero swing force (3 nsw)
@@ -329,7 +340,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
         if (c == 24 + 3 * ft + d) v = 1.0;
       }
     }
-    W[WW_A0 + idx] = v;
+    Wc[WC_A0 + idx] = v;
   }
   QM_PFOR(g, r, 18) {
     double v = 0.0;
@@ -339,7 +350,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
       for (int f2 = 0; f2 < 4; ++f2) if ((mode >> (3 - f2)) & 1) { if (cnt == j) { ft = f2; break; } ++cnt; }
       v = -W[WA_DJV + 3 * ft + d];
     }
-    W[WW_B0 + r] = v;
+    Wc[WC_B0 + r] = v;
     W[WW_HJ + r] = W[WA_NLE + 6 + r];
   }
   // level 0, inequality rows: torque limits (36), friction pyramid (5 nc), 3 nsw all-zero rows (WbcBase.cpp:458)
@@ -372,7 +383,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
     const double* qm = ms; const double* vm = ms + 24;
     const double* qd = ds; const double* vd = ds + 24;
     const double* bacc = ds + 48;
-    double* AP = W + WW_AP; double* bp = W + WW_BP;
+    double* AP = Wc + WC_AP; double* bp = Wc + WC_BP;
     int row = 0, lev = 1;
     auto level_begin = [&]() { WI[WI_LV + 2 * lev] = row; };
     auto level_end = [&]() { WI[WI_LV + 2 * lev + 1] = row - WI[WI_LV + 2 * lev]; ++lev; };
@@ -480,7 +491,7 @@ enum { HH_PARTS = 4, HH_LD = 56 };
 // dense + c is untouched until step c, so step k only involves the rows k .. dense + k (the others hold exact zeros in the
 // columns k..n and their reflector entry is zero).
 template <class G>
-QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj, double* hp, int dense) {
+QM_HDO void householder_ls(G g, double* A, int m, int n, int ld, double* vh, double* wj, double* hp, int dense) {
   const int steps = (m - 1 < n) ? m - 1 : n;
   for (int k = 0; k < steps; ++k) {
     const int mk = (dense + k + 1 < m) ? dense + k + 1 : m;   // one past the last row step k touches
@@ -523,7 +534,7 @@ QM_HDN void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
 // back substitution R z = c (R n x n upper in A, c = A[:, n], overwritten), column oriented on one narrow group: z_i is formed
 // by one lane, the others remove its contribution from the rows above.
 template <class G>
-QM_HDN void back_substitute(G w0, double* A, int n, int ld, double* z) {
+QM_HDO void back_substitute(G w0, double* A, int n, int ld, double* z) {
   for (int i = n - 1; i >= 0; --i) {
     if (w0.tid() == 0) { const double d = A[i * ld + i]; z[i] = (d != 0.0) ? A[i * ld + n] / d : 0.0; }
     w0.sync();
@@ -538,11 +549,11 @@ QM_HDN void back_substitute(G w0, double* A, int n, int ld, double* z) {
 // of the remaining corner, the first one in column-major order on ties --, rank = pivots above eps * min(r, n) * max|pivot|,
 // kernel = Q [ -U11^-1 U12 ; I ] with Q the accumulated column permutation. The basis is NOT orthonormal: HoQp's 1e-12 |z|^2
 // regularisation acts on the coordinates in this basis, which is what selects the solution of a rank-deficient level.
-// T: r x n scratch; N: n x ldn output (columns 0 .. n - rank - 1); cn: n + 2 doubles; perm: 2 n + 4 ints. *rank_out = rank.
+// T: r x n scratch; N: n x ldn output (columns 0 .. min(n - rank, maxcols) - 1); cn: n + 2 doubles; perm: 2 n + 4 ints. *rank_out = rank.
 // Eigen returns a trivial kernel as one zero column (a dummy variable that moves nothing); here rank = n means "no freedom left".
 template <class G>
-QM_HDN void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, double* T, double* N, int ldn, double* cn, int* perm,
-                            int* rank_out, int* status) {
+QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, double* T, double* N, int ldn, int maxcols, double* cn,
+                            int* perm, int* rank_out, int* status) {
   int* qidx = perm;                 // [n] column permutation
   int* brow = perm + n;             // [n] row of the largest entry per column; [n], [n + 1]: pivot row / column of the step
   QM_PFOR2(g, i, r, j, n) T[i * n + j] = Abar[i * ld_a + j];
@@ -607,7 +618,7 @@ QM_HDN void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
     }
   }
   g.sync();
-  QM_PFOR2(g, i, n, kk, dimker) {
+  QM_PFOR2(g, i, n, kk, (dimker < maxcols ? dimker : maxcols)) {      // at most maxcols kernel columns are kept (the caller flags more)
     double v = 0.0;
     if (i < rank) v = -T[i * n + rank + kk];
     else if (i - rank == kk) v = 1.0;
@@ -620,7 +631,7 @@ QM_HDN void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
 // ------------------------------------------------------------------------------------------ level 0
 // min 1/2|A0 z - b0|^2 + eps/2 |z|^2 + 1/2 |(D0 z - f0)+|^2  by Newton iteration on the active set of violated rows.
 template <class G>
-QM_HDN void wbc_level0(G g, double* W, int* WI) {
+QM_HDN void wbc_level0(G g, double* W, const double* Wc, int* WI) {
   const int nD0 = WI[WI_SC + 9];
   const int ld = WB_QR_LD;
   double* QR = W + WS_QR;
@@ -641,7 +652,7 @@ QM_HDN void wbc_level0(G g, double* W, int* WI) {
       const int r = idx / ld, c = idx % ld;
       double v;
       if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? W[WW_D0 + 36 * i + c] : W[WW_F0 + i]; }
-      else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? W[WW_A0 + 36 * i + c] : W[WW_B0 + i]; }
+      else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? Wc[WC_A0 + 36 * i + c] : Wc[WC_B0 + i]; }
       else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
       QR[idx] = v;
     }
@@ -853,7 +864,7 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
 template <class G>
 QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
   const int ld = n + 1;
-  double* QR = W + WS_QR;
+  double* QR = W + WS_LS;
   double* J = W + WS_J;
   const int m = r + n;
   QM_PFOR(g, idx, m * ld) {
@@ -887,20 +898,21 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
 
 // HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
 template <class G>
-QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status, double* levels = nullptr) {
+QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, int* status, double* levels = nullptr) {
   const int nD0 = WI[WI_SC + 9];
   if (g.tid() == 0) WI[WI_SC + 6] = 0;
   g.sync();
   // ---- level 0
-  wbc_level0(g, W, WI);
+  wbc_level0(g, W, Wc, WI);
   QM_TICK(-1);
   // Z0 = kernel(A0) in the reference's own (FullPivLU) basis; it has 36 - rank(A0) columns, at most 18 are kept (rank(A0) = 18
   // unless the contact Jacobians are degenerate, which is flagged)
-  kernel_basis_lu(g, W + WW_A0, 18, 36, 36, W + WS_QR, W + WS_Q, 36, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+  QM_PFOR(g, idx, 36 * 18) W[WW_Z0 + idx] = 0.0;
+  g.sync();
+  kernel_basis_lu(g, Wc + WC_A0, 18, 36, 36, W + WS_QR, W + WW_Z0, 18, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
   int n1 = 36 - WI[WI_SC + 1];
   if (n1 > 18) { n1 = 18; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
-  QM_PFOR(g, idx, 36 * 18) { const int i = idx / 18, c = idx % 18; W[WW_Z0 + idx] = (c < n1) ? W[WS_Q + 36 * i + c] : 0.0; }
-  g.sync(); QM_TICK(38);
+  QM_TICK(38);
   if (levels != nullptr) {
     QM_PFOR(g, i, WBL_SIZE) levels[i] = 0.0;
     g.sync();
@@ -930,8 +942,8 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status, double*
       }
       continue;
     }
-    const double* Ap = W + WW_AP + 36 * off;
-    const double* bpv = W + WW_BP + off;
+    const double* Ap = Wc + WC_AP + 36 * off;
+    const double* bpv = Wc + WC_BP + off;
     QM_PFOR(g, idx, r * 18) {
       const int i = idx / 18, c = idx % 18;
       double s = 0.0;
@@ -964,12 +976,12 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status, double*
     g.sync();
     if (p + 1 < nlev) {
       // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
-      kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_QR, W + WS_Q, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+      kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_GG, W + WS_J, 18, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
       const int nn = n - WI[WI_SC + 1];
       QM_PFOR(g, idx, 36 * 18) {
         const int i = idx / 18, c = idx % 18;
         double s = 0.0;
-        if (c < nn) for (int k = 0; k < n; ++k) s += Zc[18 * i + k] * W[WS_Q + 18 * k + c];
+        if (c < nn) for (int k = 0; k < n; ++k) s += Zc[18 * i + k] * W[WS_J + 18 * k + c];
         Zn[idx] = s;
       }
       g.sync(); QM_TICK(42);
@@ -1010,14 +1022,14 @@ QM_HDN void wbc_solve(G g, double* W, int* WI, double* cmd, int* status, double*
 // inequality rows in the reference's stacks). See WBL_* for the layout.
 template <class G>
 QM_HDN void wbc_update(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* xd, const double* ud,
-                       const double* rbd, int mode, double period, double time, const double* u_last, double* W, int* WI,
+                       const double* rbd, int mode, double period, double time, const double* u_last, double* W, double* Wc, int* WI,
                        double* cmd, int* status, double* levels = nullptr) {
   QM_TICK(-1);
   wbc_dynamics(g, M, C, rbd, xd, ud, u_last, period, W);
   QM_TICK(33);
-  wbc_tasks(g, M, C, ud, mode & 15, time, W, WI);
+  wbc_tasks(g, M, C, ud, mode & 15, time, W, Wc, WI);
   QM_TICK(34);
-  wbc_solve(g, W, WI, cmd, status, levels);
+  wbc_solve(g, W, Wc, WI, cmd, status, levels);
   QM_TICK(45);
 }
 

@@ -1184,7 +1184,7 @@ int qmb200_evaluate_policy_batch(qmb200_ctx* c, const double* t, double* x_des, 
 #include "qm_actuator.h"
 #include "qm_sim.h"
 
-constexpr int kWbcInDoubles = 30 + 30 + 56 + 32;   // xd, ud, rbd (padded), u_last (padded)
+constexpr int kWbcInDoubles = 30 + 30 + 56 + 30;   // xd, ud, rbd (padded), u_last
 static_assert(QMB200_WBC_LEVELS_SIZE == WBL_SIZE, "include/qmb200.h and qm_wbc.h agree on the per-level record");
 constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
 
@@ -1194,7 +1194,7 @@ constexpr size_t kWbcSmemBytes = (size_t)(WW_SIZE + kWbcInDoubles) * sizeof(doub
 #endif
 __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
                                               const double* ud, const double* rbd, const int32_t* mode, const double* period,
-                                              const double* time, double* u_last, double* cmd, int32_t* status) {
+                                              const double* time, double* u_last, double* cold, double* cmd, int32_t* status) {
   const int b = blockIdx.x;
   if (b >= B) return;
   extern __shared__ double smem[];
@@ -1204,20 +1204,20 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
   for (int i = threadIdx.x; i < 30; i += blockDim.x) { in[i] = xd[30 * b + i]; in[30 + i] = ud[30 * b + i]; in[116 + i] = u_last[30 * b + i]; }
   for (int i = threadIdx.x; i < 55; i += blockDim.x) in[60 + i] = rbd[55 * b + i];
   __syncthreads();
-  wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode[b], period[b], time[b], in + 116, W, WI, cmd + 54 * b, status + b);
+  wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode[b], period[b], time[b], in + 116, W, cold + (size_t)WC_SIZE * b, WI, cmd + 54 * b, status + b);
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
 
 // One solve with the per-level record of the hierarchy (HoQp accessors): diagnostic entry, not on the hot path
 __global__ void __launch_bounds__(128) k_wbc_levels(const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* in60_55_30, int mode,
-                                                     double period, double time, double* cmd, int32_t* status, double* levels) {
+                                                     double period, double time, double* cold, double* cmd, int32_t* status, double* levels) {
   extern __shared__ double smem[];
   double* W = smem;
   double* in = smem + WW_SIZE;
   int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
   for (int i = threadIdx.x; i < 145; i += blockDim.x) in[i] = in60_55_30[i];          // xd(30) ud(30) rbd(55) u_last(30)
   __syncthreads();
-  wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode, period, time, in + 115, W, WI, cmd, status, levels);
+  wbc_update(BlockGroup(), *M, *C, in, in + 30, in + 60, mode, period, time, in + 115, W, cold, WI, cmd, status, levels);
 }
 
 // ---- control law + simulated actuator with transport delay: warp per problem, lane per joint
@@ -1256,6 +1256,7 @@ struct qmb200_wbc_ctx {
   qmb200_model_desc* dM = nullptr;
   qmb200_wbc_desc* dC = nullptr;
   double *xd = nullptr, *ud = nullptr, *rbd = nullptr, *period = nullptr, *time = nullptr, *u_last = nullptr, *cmd = nullptr;
+  double* cold = nullptr;                       // [B][WC_SIZE] task rows read once per level (qm_wbc.h), L2-resident per solve
   int32_t *mode = nullptr, *status = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1276,7 +1277,7 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
                       const double* period, const double* time, double* cmd, int32_t* status) {
   wbc_harvest(c);
   CUDA_OK(cudaEventRecord(c->e0, c->stream));
-  k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, cmd, status);
+  k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold, cmd, status);
   CUDA_OK(cudaEventRecord(c->e1, c->stream));
   CUDA_OK(cudaGetLastError());
   c->pending = true;
@@ -1311,6 +1312,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   C_OK(cudaMalloc(&c->time, B * sizeof(double)));
   C_OK(cudaMalloc(&c->u_last, B * 30 * sizeof(double)));
   C_OK(cudaMalloc(&c->cmd, B * 54 * sizeof(double)));
+  C_OK(cudaMalloc(&c->cold, B * WC_SIZE * sizeof(double)));
   C_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
   C_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));
   C_OK(cudaMemset(c->u_last, 0, B * 30 * sizeof(double)));
@@ -1325,7 +1327,7 @@ int qmb200_wbc_destroy(qmb200_wbc_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->mode, c->status,
+  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->cold, c->mode, c->status,
                   c->act_stamp, c->act_buf, c->act_hc, c->act_last};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->e0) cudaEventDestroy(c->e0);
@@ -1387,7 +1389,7 @@ int qmb200_wbc_levels(qmb200_wbc_ctx* c, const double* x_des, const double* u_de
   CUDA_OK(cudaMallocAsync(&ds, sizeof(int32_t), c->stream));
   CUDA_OK(cudaMemcpyAsync(d, h_in, sizeof(h_in), cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaFuncSetAttribute(k_wbc_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
-  k_wbc_levels<<<1, 128, kWbcSmemBytes, c->stream>>>(c->dM, c->dC, d, mode, period, time, d + 145, ds, d + 199);
+  k_wbc_levels<<<1, 128, kWbcSmemBytes, c->stream>>>(c->dM, c->dC, d, mode, period, time, c->cold, d + 145, ds, d + 199);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(cmd, d + 145, 54 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(levels, d + 199, QMB200_WBC_LEVELS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
