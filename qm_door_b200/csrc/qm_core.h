@@ -129,15 +129,19 @@ QM_HD int mm_rowperm(int r) { return ((r & 3) << 1) | (r >> 2); }     // {0,2,4,
 
 // out(r, init(r) + sum_{j < len} term(r, j)) for r < nrows. Device: four lanes per row, partial sums combined with
 // shuffles (the group size is a multiple of 32); host: one loop.
-template <class G, class FI, class FT, class FO>
+// TR: term(r, j) reads a matrix by columns (element j * ld + r, ld = 30 or 18): the four lanes of a row then take j in pairs
+// {2 part, 2 part + 1} + 8 s and the rows stay consecutive, which puts the lanes of a half warp on 16 different bank pairs.
+template <bool TR = false, class G, class FI, class FT, class FO>
 QM_HDN void rows_dot(G g, int nrows, int len, FI init, FT term, FO out) {
 #if defined(__CUDA_ARCH__)
   for (int base = 0; base < 4 * nrows; base += g.nt()) {
     const int t = base + g.tid(), rl = t >> 2, part = t & 3;
-    const int r = (rl & ~7) | mm_rowperm(rl & 7);      // rows two apart within a half warp: no bank conflicts at row stride 30 / 18
+    const int r = TR ? rl : ((rl & ~7) | mm_rowperm(rl & 7));   // rows two apart within a half warp: no bank conflicts at row stride 30 / 18
     const bool valid = r < nrows;
     double acc = 0.0;
-    if (valid) for (int j = part; j < len; j += 4) acc += term(r, j);
+    if (TR) {
+      if (valid) for (int j = 2 * part; j < len; j += 8) { acc += term(r, j); if (j + 1 < len) acc += term(r, j + 1); }
+    } else if (valid) for (int j = part; j < len; j += 4) acc += term(r, j);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (valid && part == 0) out(r, init(r) + acc);
@@ -211,6 +215,9 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
   int w0 = g.warp() - rot;
   if (w0 < 0) w0 += nw;
   int nunits = tm * gj;
+  // the two adjacent output elements of a lane go out (and the C0 pair comes in) as one 16-byte access where the layout allows
+  const bool pairc = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  const bool pair0 = C0 && ((ld0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(C0) & 15) == 0);
   if (FLAGS & MM_UP) { nunits = 0; for (int ti = 0; ti < tm; ++ti) nunits += tn - ((ti >> 1) << 1); }
   for (int unit = w0; unit < nunits; unit += nw) {
     int ti = 0, tj = unit;                                        // unit -> (tile row, tile column group) without divisions
@@ -227,8 +234,13 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
     for (int t = 0; t < TJ; ++t) {
       acc[t][0] = 0.0; acc[t][1] = 0.0;
       const int j = mm_col16(t0 + t, 2 * q);
-      c0v[t][0] = (C0 && i < m && j < n) ? C0[i * ld0 + j] : 0.0;
-      c0v[t][1] = (C0 && i < m && j + 1 < n) ? C0[i * ld0 + j + 1] : 0.0;
+      if (pair0 && i < m && j + 1 < n) {          // j is even: one 16-byte access (all 32 banks instead of every other pair)
+        const double2 v = *reinterpret_cast<const double2*>(C0 + i * ld0 + j);
+        c0v[t][0] = v.x; c0v[t][1] = v.y;
+      } else {
+        c0v[t][0] = (C0 && i < m && j < n) ? C0[i * ld0 + j] : 0.0;
+        c0v[t][1] = (C0 && i < m && j + 1 < n) ? C0[i * ld0 + j + 1] : 0.0;
+      }
     }
     const bool iok = i < m;
     const double* xp = xT ? (X + i + q * ldx) : (X + i * ldx + q);     // advances by 4 rows (xT) / 4 columns per k-step
@@ -254,8 +266,14 @@ QM_HDN void mm(G g, int m, int n, int k, const double* X, int ldx, const double*
     for (int t = 0; t < TJ; ++t) {
       const int j = mm_col16(t0 + t, 2 * q);
       if (i < m && t0 + t < tn) {
-        if (j < n) C[i * ldc + j] = c0v[t][0] + alpha * acc[t][0];
-        if (j + 1 < n) C[i * ldc + j + 1] = c0v[t][1] + alpha * acc[t][1];
+        if (pairc && j + 1 < n) {
+          double2 v;
+          v.x = c0v[t][0] + alpha * acc[t][0]; v.y = c0v[t][1] + alpha * acc[t][1];
+          *reinterpret_cast<double2*>(C + i * ldc + j) = v;
+        } else {
+          if (j < n) C[i * ldc + j] = c0v[t][0] + alpha * acc[t][0];
+          if (j + 1 < n) C[i * ldc + j + 1] = c0v[t][1] + alpha * acc[t][1];
+        }
       }
     }
   }

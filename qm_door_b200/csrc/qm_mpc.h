@@ -1140,7 +1140,7 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
   // ---- P2
   if (nut > 0) {
     mm<1, true>(g, nut, nut, 30, B, QM_NUT, W + RW_SB, QM_NUT, st + SB_R, QM_NUT, 1.0, W + RW_G, QM_NUT);
-    rows_dot(g, nut, 30, [&](int a) { return st[SB_r + a]; },
+    rows_dot<true>(g, nut, 30, [&](int a) { return st[SB_r + a]; },
              [&](int a, int k) { return B[QM_NUT * k + a] * W[RW_sb + k]; },
              [&](int a, double v) { W[RW_gv + a] = v; });
     g.sync(); QM_TICK(2);
@@ -1193,7 +1193,7 @@ QM_HDN int riccati_stage_a(G g, const double* st, double* W, int* status) {
     auto r_ = g.rest();
     mm<1, true, MM_UP>(r_, 30, 30, 30, A, 30, W + RW_SA, 30, st + SB_Q, 30, 1.0, S, 30);
     if (nut > 0) mm<1, true>(r_, nut, 30, 30, B, QM_NUT, W + RW_SA, 30, st + SB_P, 30, 1.0, W + RW_H, 30, 1);
-    rows_dot(r_, 30, 30, [&](int i) { return st[SB_q + i]; },
+    rows_dot<true>(r_, 30, 30, [&](int i) { return st[SB_q + i]; },
              [&](int i, int k) { return A[30 * k + i] * W[RW_sb + k]; },
              [&](int i, double v) { s[i] = v; });
   }
@@ -1214,7 +1214,7 @@ QM_HDN void riccati_stage_b(G g, int nut, double* W, double* gb) {
     g.sync(); QM_TICK(4);
     // ---- P5: S += H' K (upper tiles), s += H' kff
     mm<1, true, MM_UP>(g, 30, 30, nut, W + RW_H, 30, W + RW_K, 30, S, 30, 1.0, S, 30);
-    rows_dot(g, 30, nut, [&](int i) { return s[i]; },
+    rows_dot<true>(g, 30, nut, [&](int i) { return s[i]; },
              [&](int i, int a) { return W[RW_H + 30 * a + i] * W[RW_kf + a]; },
              [&](int i, double v) { s[i] = v; });
   }

@@ -90,7 +90,7 @@ enum { WI_INW = 0, WI_PERM = 56, WI_ACT = 100, WI_IGN = 136, WI_SC = 192, WI_LV 
 // WI_LV: [0] number of levels (level 0 included), then per level p >= 1: [2 p] first row in the pool, [2 p + 1] number of rows
 // WI_SC scalars: [0] nW changed flag, [1] rank, [2] n1, [3] n2, [4] iq, [5] ip, [6] status, [7] r1, [8] r2, [9] nD0, [10] done
 
-QM_HD void rot_zyx(const double* e, double* R) {
+QM_HDO void rot_zyx(const double* e, double* R) {
   double sz, cz, sy, cy, sx, cx;
   sincos(e[0], &sz, &cz); sincos(e[1], &sy, &cy); sincos(e[2], &sx, &cx);
   R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
@@ -98,7 +98,7 @@ QM_HD void rot_zyx(const double* e, double* R) {
   R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
 }
 // [upstream] rotationErrorInWorld(Rref, Rcur): rotation vector of Rref Rcur^T
-QM_HD void rotation_error_world(const double* Rr, const double* Rc, double* e) {
+QM_HDO void rotation_error_world(const double* Rr, const double* Rc, double* e) {
   double R[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) R[3 * i + j] = Rr[3 * i] * Rc[3 * j] + Rr[3 * i + 1] * Rc[3 * j + 1] + Rr[3 * i + 2] * Rc[3 * j + 2];
@@ -115,6 +115,12 @@ QM_HD void crm(const double* A, const double* B, double* X) {
   cross3(A, B + 3, X + 3);
   cross3_add(A + 3, B, X + 3);
 }
+
+// single copies of the kinematic passes for the two configurations (measured, desired) of one solve
+template <class G>
+QM_HDO void wbc_kin_positions(G g, const qmb200_model_desc& M, const double* q, double* kw) { kin_positions(g, M, q, kw); }
+template <class G>
+QM_HDO void wbc_kin_velocities(G g, const qmb200_model_desc& M, double* kw) { kin_velocities(g, M, 0, kw); }
 
 // Bias accelerations (qdd = 0, no gravity) and body forces of the configuration whose position/velocity level is in kw.
 // FB_i = I_i (acc_i + a_g) + V_i x* (I_i V_i)   with a_g = (0; 0, 0, grav) (grav = 9.81 for RNEA, 0 for momentum rates)
@@ -182,11 +188,11 @@ QM_HDN void wbc_dynamics_measured(G g, const qmb200_model_desc& M, double gravit
     ms[24 + 5] = dxr;
   }
   g.sync();
-  kin_positions(g, M, ms, kw);
+  wbc_kin_positions(g, M, ms, kw);
   QM_PFOR(g, k, QM_NJ) kw[KW_VEL + k] = ms[24 + k];
   QM_PFOR(g, idx, 144) W[WA_JEE + idx] = kw[KW_EEJ + idx];     // before the velocity level reuses the storage (KW_HB)
   g.sync();
-  kin_velocities(g, M, 0, kw);
+  wbc_kin_velocities(g, M, kw);
   bias_forces(g, M, kw, gravity, W + WA_ACC, W + WA_FB);
   QM_PFOR(g, j, QM_NJ) {     // nle = S_j . sum of subtree forces (RNEA backward pass)
     double f[6] = {0, 0, 0, 0, 0, 0}, S[6];
@@ -257,9 +263,9 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
   double* kw = W + WA_KIN;
   double* ds = W + WA_DES;
   // ---- desired (WbcBase.cpp:205-238)
-  kin_positions(g, M, xd + 6, kw);
+  wbc_kin_positions(g, M, xd + 6, kw);
   centroidal_velocity(g, M, xd, ud, kw);
-  kin_velocities(g, M, false, kw);
+  wbc_kin_velocities(g, M, kw);
   bias_forces(g, M, kw, 0.0, W + WA_ACC, W + WA_FB);
   if (g.tid() == 0) {
     // Adot v = d/dt(A) v: total momentum rate with qdd = 0, moved to the centre of mass
