@@ -35,15 +35,17 @@ namespace qm {
 // Development aid (-DQM_PHASE_TIMING): thread 0 of CTA 0 accumulates the cycles between consecutive ticks per phase id.
 #if defined(QM_PHASE_TIMING) && defined(__CUDACC__)
 __device__ unsigned long long qm_dbg[64];
-__device__ unsigned long long qm_dbg_last;
 #endif
 #if defined(QM_PHASE_TIMING) && defined(__CUDA_ARCH__)
+// the previous stamp lives in shared memory and the accumulation is a fire-and-forget reduction, so a tick costs one shared-memory
+// round trip (a global read-modify-write would put an L2 latency on the chain being measured)
+__device__ __forceinline__ unsigned long long* qm_tick_last() { __shared__ unsigned long long last; return &last; }
 #define QM_TICK(id)                                                                    \
   do {                                                                                 \
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {                      \
       const unsigned long long t_ = clock64();                                         \
-      if ((id) >= 0) qm_dbg[(id)] += t_ - qm_dbg_last;                                 \
-      qm_dbg_last = t_;                                                                \
+      if ((id) >= 0) atomicAdd(&qm_dbg[(id)], t_ - *qm_tick_last());                   \
+      *qm_tick_last() = t_;                                                            \
     }                                                                                  \
   } while (0)
 #else

@@ -58,7 +58,8 @@ enum {
   // therefore laid over that whole window (three solves per SM instead of two: 74 KB instead of 105 KB of shared memory).
   WS_GA = WW_SCR,                    // [22][18]  A Z of the current level
   WS_GB = WS_GA + 22 * 18,           // [22]
-  WS_GG = WS_GB + 22,                // [56][18]  D0 Z; after the level's solve: scratch of its kernel basis
+  WS_GG = WS_GB + 22,                // [18][56]  (D0 Z)' -- column c of row i at 56 c + i, so the lanes that own rows read
+                                     //           consecutive words; after the level's solve: scratch of its kernel basis
   WS_Gg = WS_GG + 56 * 18,           // [56]
   WS_J = WS_Gg + 56,                 // [18][18]  active-set factor; after the level's solve: its kernel basis N
   WS_RF = WS_J + 324,                // [18][18]
@@ -77,6 +78,7 @@ enum {
   WS_HP = WS_WJ + 40,                // [4][56] partial sums of the Householder steps (4 row chunks per column)
   WS_U = WS_HP,                      // [60] multipliers of the active-set iteration   } never live during a Householder
   WS_CN = WS_HP + 64,                // [40] column maxima of the kernel basis / scalars of the iteration   } triangularisation
+  WS_SCL = WS_HP + 104,              // [56] row scales of the violation test of the active-set iteration
   WS_END = WS_HP + 4 * 56,
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
@@ -695,6 +697,94 @@ QM_HDN void wbc_level0(G g, double* W, const double* Wc, int* WI) {
 // active list (WI_ACT), iq (WI_SC+4). Scratch scalars in WS_CN: [0] t, [1] cip, [20..38] cs, [40..58]... see below.
 enum { GI_T = 0, GI_CIP = 1, GI_CS = 2, GI_SN = 20 };          // offsets into WS_CN (40 doubles): t, c_ip, cs[18], sn[18]
 enum { GI_ACTION = 11, GI_L = 12, GI_NROT = 13 };              // offsets into WI_SC: 0 add, 1 drop, 2 skip/ignore, 3 done
+// ---- cross-lane helpers of the active-set iteration (one warp on the device, one thread on the host). The sums run in the same
+// butterfly order on both sides, so host and device agree on them bit for bit.
+template <class G, class F>
+QM_HD double gi_sum(G w0, int n, F f) {                       // sum of f(i), i < n <= 32; every lane gets the result
+#if defined(__CUDA_ARCH__)
+  const int lane = w0.tid();
+  double v = (lane < n) ? f(lane) : 0.0;
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+#else
+  double v[32], t[32];
+  for (int i = 0; i < 32; ++i) v[i] = (i < n) ? f(i) : 0.0;
+  for (int s = 16; s > 0; s >>= 1) {
+    for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ s];
+    for (int i = 0; i < 32; ++i) v[i] = t[i];
+  }
+  return v[0];
+#endif
+}
+// index of the smallest f(i) below `bound` over i < n (the lowest index on ties), -1 if there is none; *vmin: that value or bound
+template <class G, class F>
+QM_HD int gi_argmin(G w0, int n, double bound, F f, double* vmin) {
+  double best = bound;
+  int bi = -1;
+#if defined(__CUDA_ARCH__)
+  for (int i = w0.tid(); i < n; i += 32) { const double v = f(i); if (v < best) { best = v; bi = i; } }
+  for (int s = 16; s > 0; s >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
+  }
+#else
+  for (int i = 0; i < n; ++i) { const double v = f(i); if (v < best) { best = v; bi = i; } }
+#endif
+  *vmin = best;
+  return bi;
+}
+// gi_argmin over i < nmin (<= 32) and two gi_sums over i < nsum in one pass (the three butterflies interleave on the device)
+template <class G, class FV, class F1, class F2>
+QM_HD int gi_argmin_sum2(G w0, int nmin, double bound, FV fv, double* vmin, int nsum, F1 f1, F2 f2, double* s1, double* s2) {
+#if defined(__CUDA_ARCH__)
+  const int lane = w0.tid();
+  double best = bound, a = 0.0, b = 0.0;
+  int bi = -1;
+  if (lane < nmin) { const double v = fv(lane); if (v < best) { best = v; bi = lane; } }
+  if (lane < nsum) { a = f1(lane); b = f2(lane); }
+  for (int s = 16; s > 0; s >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+    a += __shfl_xor_sync(0xffffffffu, a, s);
+    b += __shfl_xor_sync(0xffffffffu, b, s);
+    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
+  }
+  *vmin = best; *s1 = a; *s2 = b;
+  return bi;
+#else
+  *s1 = gi_sum(w0, nsum, f1);
+  *s2 = gi_sum(w0, nsum, f2);
+  return gi_argmin(w0, nmin, bound, fv, vmin);
+#endif
+}
+// rr = R^-1 d for the leading q x q upper triangle of RF (ld 18), column by column from the last one: lane i owns row i, the
+// diagonal enters through its reciprocal (one division per lane, off the chain)
+template <class G>
+QM_HD void gi_backsub(G w0, const double* RF, const double* d, int q, double* rr) {
+#if defined(__CUDA_ARCH__)
+  const int lane = w0.tid();
+  double s = (lane < q) ? d[lane] : 0.0;
+  const double inv = (lane < q) ? 1.0 / RF[lane * 18 + lane] : 0.0;
+  for (int j = q - 1; j > 0; --j) {
+    const double rj = __shfl_sync(0xffffffffu, s * inv, j);
+    if (lane < j) s -= RF[lane * 18 + j] * rj;
+  }
+  if (lane < q) rr[lane] = s * inv;
+#else
+  double s[18];
+  for (int i = 0; i < q; ++i) s[i] = d[i];
+  for (int j = q - 1; j >= 0; --j) {
+    rr[j] = s[j] * (1.0 / RF[j * 18 + j]);
+    for (int i = 0; i < j; ++i) s[i] -= RF[i * 18 + j] * rr[j];
+  }
+#endif
+}
+
+// Goldfarb-Idnani dual active-set iteration on  min 1/2 |z - z0|^2_H  s.t.  GG z <= Gg  in the factored form J = L^-T Q, R
+// ([upstream] the QP of one HoQp level, HoQp.cpp:129-158, is handed to qpOASES; this is the dense dual method restated).
+// One warp: vector operations over the lanes, scalar decisions formed redundantly by every lane from warp-wide reductions
+// (no lane-0 sections on the chain except the bookkeeping stores).
 template <class G>
 QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
   double* J = W + WS_J;
@@ -709,77 +799,63 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
   double* np = W + WS_NP;
   double* sc = W + WS_CN;
   double* viol = W + WS_VH;        // [56] scaled violation of the candidate rows (the Householder vector storage is idle here)
+  double* scl = W + WS_SCL;        // [56] 1 / (1 + |Gg_i|)
   int total = 0;
-  QM_PFOR(w0, i, 56) ina[i] = 0;
+  int iq = 0;                      // size of the active set (uniform over the lanes)
+  QM_PFOR(w0, i, 56) { ina[i] = 0; scl[i] = (i < nD0) ? 1.0 / (1.0 + fabs(W[WS_Gg + i])) : 0.0; }
   w0.sync();
   for (int outer = 0; outer < 200; ++outer) {
     // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible) and the scaled violation of every row that may enter
     QM_PFOR(w0, i, nD0) {
       double s = W[WS_Gg + i];
-      for (int c = 0; c < n; ++c) s -= W[WS_GG + 18 * i + c] * z[c];
+      for (int c = 0; c < n; ++c) s -= W[WS_GG + 56 * c + i] * z[c];
       W[WS_RES + i] = s;
-      const double v = s / (1.0 + fabs(W[WS_Gg + i]));
+      const double v = s * scl[i];
       viol[i] = (WI[WI_IGN + i] || ina[i] || !(v < -1e-9)) ? 0.0 : v;
     }
     w0.sync();
-    if (w0.tid() == 0) {
-      const int iq = WI[WI_SC + 4];
-      int ip = -1;
-      double worst = 0.0;
-      for (int i = 0; i < nD0; ++i) if (viol[i] < worst) { worst = viol[i]; ip = i; }     // most violated row; first one on ties
-      WI[WI_SC + 5] = ip;
-      if (ip >= 0) { u[iq] = 0.0; sc[GI_CIP] = W[WS_RES + ip]; }
-    }
-    w0.sync();
-    const int ip = WI[WI_SC + 5];
+    double worst = 0.0;
+    const int ip = gi_argmin(w0, nD0, 0.0, [&](int i) { return viol[i]; }, &worst);   // most violated row; first one on ties
+    (void)worst;
+    QM_TICK(46);
     if (ip < 0) break;
-    QM_PFOR(w0, c, n) np[c] = -W[WS_GG + 18 * ip + c];
+    double cip = W[WS_RES + ip];
+    if (w0.tid() == 0) u[iq] = 0.0;
+    QM_PFOR(w0, c, n) np[c] = -W[WS_GG + 56 * c + ip];
     w0.sync();
     for (int inner = 0; inner < 200; ++inner) {
-      const int iq = WI[WI_SC + 4];
       // d = J' np
       QM_PFOR(w0, c, n) { double s = 0.0; for (int i = 0; i < n; ++i) s += J[i * 18 + c] * np[i]; d[c] = s; }
-      w0.sync();
-      // zd = J[:, iq:] d[iq:]  (lanes), rr = RF^-1 d[:iq] (lane 0)
+      w0.sync(); QM_TICK(47);
+      // zd = J[:, iq:] d[iq:],  rr = RF^-1 d[:iq]
       QM_PFOR(w0, i, n) { double s = 0.0; for (int c = iq; c < n; ++c) s += J[i * 18 + c] * d[c]; zd[i] = s; }
-      if (w0.tid() == 0) {
-        for (int i = iq - 1; i >= 0; --i) {
-          double s = d[i];
-          for (int j = i + 1; j < iq; ++j) s -= RF[i * 18 + j] * rr[j];
-          rr[i] = s / RF[i * 18 + i];
-        }
-        double t1 = 1e300; int l = -1;
-        for (int k = 0; k < iq; ++k)
-          if (rr[k] > 1e-14 * (1.0 + fabs(u[k])) && u[k] / rr[k] < t1) { t1 = u[k] / rr[k]; l = k; }
-        double dn2 = 0.0, dall = 0.0;
-        for (int c = 0; c < n; ++c) { dall += d[c] * d[c]; if (c >= iq) dn2 += d[c] * d[c]; }
-        const double cip = sc[GI_CIP];
-        double t2 = 1e300;
-        if (dn2 > 1e-26 * dall) t2 = -cip / dn2;          // z' np = |d2|^2 in the J-scaled metric
-        const double t = (t1 < t2) ? t1 : t2;
-        int action;
-        if (t >= 1e300) {
-          // dependent normal and nothing to drop: infeasible up to rounding -> ignore a marginally violated row
+      gi_backsub(w0, RF, d, iq, rr);
+      w0.sync(); QM_TICK(48);
+      // step lengths: t1 = largest dual step that keeps the multipliers non-negative (and the constraint l it blocks on),
+      //               t2 = full primal step onto the new constraint
+      double t1, dall, dn2;
+      const int l = gi_argmin_sum2(w0, iq, 1e300,
+                                   [&](int k) { return (rr[k] > 1e-14 * (1.0 + fabs(u[k]))) ? u[k] / rr[k] : 1e300; }, &t1, n,
+                                   [&](int c) { return d[c] * d[c]; }, [&](int c) { return (c >= iq) ? d[c] * d[c] : 0.0; },
+                                   &dall, &dn2);
+      double t2 = 1e300;
+      if (dn2 > 1e-26 * dall) t2 = -cip / dn2;          // z' np = |d2|^2 in the J-scaled metric
+      const double t = (t1 < t2) ? t1 : t2;
+      QM_TICK(49);
+      if (t >= 1e300) {
+        // dependent normal and nothing to drop: infeasible up to rounding -> ignore a marginally violated row
+        if (w0.tid() == 0) {
           if (!(fabs(cip) < 1e-6 * (1.0 + fabs(W[WS_Gg + ip])))) WI[WI_SC + 6] |= WST_DEGENERATE;
           WI[WI_IGN + ip] = 1;
-          action = 2;
-        } else {
-          sc[GI_T] = t;
-          WI[WI_SC + 14] = (t2 < 1e300);                   // primal step exists
-          action = (t == t2) ? 0 : 1;
-          WI[GI_L + WI_SC] = l;
         }
-        WI[WI_SC + GI_ACTION] = action;
+        w0.sync();
+        break;
       }
-      w0.sync();
-      const int action = WI[WI_SC + GI_ACTION];
-      if (action == 2) break;
-      const double t = sc[GI_T];
-      if (WI[WI_SC + 14]) QM_PFOR(w0, i, n) z[i] += t * zd[i];
+      if (t2 < 1e300) QM_PFOR(w0, i, n) z[i] += t * zd[i];
       QM_PFOR(w0, k, iq) u[k] -= t * rr[k];
       if (w0.tid() == 0) u[iq] += t;
-      w0.sync();
-      if (action == 0) {
+      w0.sync(); QM_TICK(50);
+      if (t == t2) {
         // add constraint ip: Givens rotations that zero d[iq+1..n-1] bottom up. The value a rotation leaves in d[j-1] is the norm
         // of the tail d[j-1..], so all coefficients follow from the suffix sums of squares, formed by the lanes in parallel
         // (the sequential form is a chain of n - iq - 1 hypot calls on one lane).
@@ -797,32 +873,66 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
           }
         }
         w0.sync();
-        QM_PFOR(w0, i, n) {
+        QM_PFOR(w0, i, n) {             // row i of J: columns n-1 .. iq, the running right-hand element stays in a register
+          double x2 = J[i * 18 + n - 1];
           for (int j = n - 1; j > iq; --j) {
             const double cs = sc[GI_CS + j], sn = sc[GI_SN + j];
-            const double x1 = J[i * 18 + j - 1], x2 = J[i * 18 + j];
-            J[i * 18 + j - 1] = cs * x1 + sn * x2;
+            const double x1 = J[i * 18 + j - 1];
             J[i * 18 + j] = -sn * x1 + cs * x2;
+            x2 = cs * x1 + sn * x2;
           }
+          J[i * 18 + iq] = x2;
         }
         QM_PFOR(w0, i, iq) RF[i * 18 + iq] = d[i];
         if (w0.tid() == 0) {
           RF[iq * 18 + iq] = (iq + 1 < n && rr[iq + 1] != 0.0) ? sqrt(rr[iq]) : d[iq];
-          act[iq] = ip; ina[ip] = 1; WI[WI_SC + 4] = iq + 1;
+          act[iq] = ip; ina[ip] = 1;
         }
-        w0.sync();
+        ++iq;
+        w0.sync(); QM_TICK(51);
         break;
       }
-      // drop constraint l and continue with the same ip
-      const int l = WI[WI_SC + GI_L];
-      if (w0.tid() == 0) {
+      // drop constraint l and continue with the same ip: column l leaves R, Givens rotations of rows (k, k+1) restore the triangle
+      const int q2 = iq - 1;
+#if defined(__CUDA_ARCH__)
+      {
+        const int lane = w0.tid();
+        // bookkeeping: read, then write (lanes k >= l take the entry of k + 1)
+        const int a_n = (lane >= l && lane < q2) ? act[lane + 1] : 0;
+        const double u_n = (lane >= l && lane < iq) ? u[lane + 1] : 0.0;
+        if (lane == 0) ina[act[l]] = 0;
+        // rows shift left by one from column l on (lane = row)
+        if (lane < iq) for (int k = l; k < q2; ++k) RF[lane * 18 + k] = RF[lane * 18 + k + 1];
+        __syncwarp();
+        if (lane >= l && lane < q2) act[lane] = a_n;
+        if (lane >= l && lane < iq) u[lane] = u_n;
+        // rotations (lane = column): the coefficients of step k come from column k, whose running element is in that lane
+        const bool mine = (lane >= l && lane < q2);
+        double carry = mine ? RF[l * 18 + lane] : 0.0;
+        for (int k = l; k < q2; ++k) {
+          const bool on = mine && lane >= k;
+          const double x2 = on ? RF[(k + 1) * 18 + lane] : 0.0;
+          double cs = 1.0, sn = 0.0;
+          if (lane == k && x2 != 0.0) { const double h = hypot(carry, x2); cs = carry / h; sn = x2 / h; }
+          cs = __shfl_sync(0xffffffffu, cs, k);
+          sn = __shfl_sync(0xffffffffu, sn, k);
+          if (on) {                                       // (cs, sn) = (1, 0) where the host skips the rotation: same values
+            RF[k * 18 + lane] = cs * carry + sn * x2;
+            carry = -sn * carry + cs * x2;
+            if (lane == k) RF[(k + 1) * 18 + lane] = carry;
+          }
+          if (lane == k) { sc[GI_CS + k] = cs; sc[GI_SN + k] = sn; }
+        }
+        __syncwarp();
+      }
+#else
+      {
         ina[act[l]] = 0;
         for (int k = l; k < iq - 1; ++k) {
           act[k] = act[k + 1]; u[k] = u[k + 1];
           for (int i = 0; i <= k + 1; ++i) RF[i * 18 + k] = RF[i * 18 + k + 1];
         }
         u[iq - 1] = u[iq];
-        const int q2 = iq - 1;
         for (int k = l; k < q2; ++k) {   // restore the triangle: rotate rows k, k+1 of RF
           const double a = RF[k * 18 + k], b2 = RF[(k + 1) * 18 + k];
           double cs = 1.0, sn = 0.0;
@@ -837,36 +947,30 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
           }
           sc[GI_CS + k] = cs; sc[GI_SN + k] = sn;
         }
-        WI[WI_SC + 4] = q2;
       }
-      w0.sync();
-      {
-        const int q2 = WI[WI_SC + 4];
-        QM_PFOR(w0, i, n) {             // same rotations on the columns k, k+1 of J, row-parallel
-          for (int k = l; k < q2; ++k) {
-            const double cs = sc[GI_CS + k], sn = sc[GI_SN + k];
-            const double x1 = J[i * 18 + k], x2 = J[i * 18 + k + 1];
-            J[i * 18 + k] = cs * x1 + sn * x2;
-            J[i * 18 + k + 1] = -sn * x1 + cs * x2;
-          }
+#endif
+      iq = q2;
+      QM_PFOR(w0, i, n) {               // same rotations on the columns k, k+1 of J, row-parallel, running element in a register
+        double x1 = J[i * 18 + l];
+        for (int k = l; k < q2; ++k) {
+          const double cs = sc[GI_CS + k], sn = sc[GI_SN + k];
+          const double x2 = J[i * 18 + k + 1];
+          J[i * 18 + k] = cs * x1 + sn * x2;
+          x1 = -sn * x1 + cs * x2;
         }
-        if (w0.tid() == 0) {
-          double cip = W[WS_Gg + ip];
-          for (int c = 0; c < n; ++c) cip -= W[WS_GG + 18 * ip + c] * z[c];
-          sc[GI_CIP] = cip;
-        }
+        J[i * 18 + q2] = x1;
       }
-      w0.sync();
+      cip = W[WS_Gg + ip];
+      for (int c = 0; c < n; ++c) cip -= W[WS_GG + 56 * c + ip] * z[c];
+      w0.sync(); QM_TICK(52);
       if (++total > 400) { if (w0.tid() == 0) WI[WI_SC + 6] |= WST_QP_MAX_ITER; break; }
     }
     if (total > 400) break;
   }
+  if (w0.tid() == 0) WI[WI_SC + 4] = iq;
   w0.sync();
 }
 
-// ------------------------------------------------------------------------------------------ levels 1, 2
-// min 1/2|Ab z - bb|^2 + eps/2|z|^2  s.t.  Gg z <= gg   (n <= 18 unknowns, r rows, nD0 inequality rows)
-// Goldfarb-Idnani dual active set; J = R^-1 from the Householder factor of [Ab; sqrt(eps) I]. z returned in WS_Z.
 template <class G>
 QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
   const int ld = n + 1;
@@ -965,7 +1069,7 @@ QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, in
       const int i = idx / 18, c = idx % 18;
       double s = 0.0;
       if (c < n) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * Zc[18 * k + c];
-      W[WS_GG + idx] = s;
+      W[WS_GG + 56 * c + i] = s;
     }
     QM_PFOR(g, i, nD0) {
       double s = W[WW_F0 + i] + W[WW_V0 + i];
