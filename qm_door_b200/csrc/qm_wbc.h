@@ -785,33 +785,66 @@ QM_HD void gi_backsub(G w0, const double* RF, const double* d, int q, double* rr
 // ([upstream] the QP of one HoQp level, HoQp.cpp:129-158, is handed to qpOASES; this is the dense dual method restated).
 // One warp: vector operations over the lanes, scalar decisions formed redundantly by every lane from warp-wide reductions
 // (no lane-0 sections on the chain except the bookkeeping stores).
+// Storage of the iteration: the solve's workspace (gi_mem_of) or the compact per-warp block of the stand-alone kernel (k_wbc_gi).
+struct GiMem {
+  double *GG, *Gg;                 // [18][56] inequality rows by column, [56] right-hand sides (read only)
+  double *J, *RF;                  // [18][18] each
+  double *z, *d, *rr, *zd, *np;    // [18] each
+  double *res, *viol, *scl;        // [56] each: constraint values, scaled violations, row scales 1 / (1 + |Gg_i|)
+  double *u, *sc;                  // [60] multipliers, [40] scalars / rotation coefficients
+  int *act, *ina, *ign;            // [36] active list, [56] row is active, [56] row is ignored (dependent and marginally violated)
+  int *status;                     // WST_* flags of the solve (or-ed into)
+};
+enum { GI_MEM_DOUBLES = 18 * 56 + 56 + 2 * 324 + 5 * 20 + 3 * 56 + 60 + 40, GI_MEM_INTS = 36 + 56 + 56 + 4 };
+QM_HD GiMem gi_mem_of(double* W, int* WI) {
+  GiMem m;
+  m.GG = W + WS_GG; m.Gg = W + WS_Gg; m.J = W + WS_J; m.RF = W + WS_RF;
+  m.z = W + WS_Z; m.d = W + WS_D; m.rr = W + WS_RR; m.zd = W + WS_ZD; m.np = W + WS_NP;
+  m.res = W + WS_RES; m.viol = W + WS_VH;      // (the Householder vector storage is idle during the iteration)
+  m.scl = W + WS_SCL; m.u = W + WS_U; m.sc = W + WS_CN;
+  m.act = WI + WI_ACT; m.ina = WI + WI_INW;    // (the level-0 flags of this name are dead by now)
+  m.ign = WI + WI_IGN; m.status = WI + WI_SC + 6;
+  return m;
+}
+QM_HD GiMem gi_mem_compact(double* D, int* I) {   // GI_MEM_DOUBLES doubles, GI_MEM_INTS ints
+  GiMem m;
+  m.GG = D; m.Gg = m.GG + 18 * 56; m.J = m.Gg + 56; m.RF = m.J + 324;
+  m.z = m.RF + 324; m.d = m.z + 20; m.rr = m.d + 20; m.zd = m.rr + 20; m.np = m.zd + 20;
+  m.res = m.np + 20; m.viol = m.res + 56; m.scl = m.viol + 56; m.u = m.scl + 56; m.sc = m.u + 60;
+  m.act = I; m.ina = I + 36; m.ign = m.ina + 56; m.status = m.ign + 56;
+  return m;
+}
+
 template <class G>
-QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
-  double* J = W + WS_J;
-  double* RF = W + WS_RF;
-  int* act = WI + WI_ACT;
-  int* ina = WI + WI_INW;          // [56] row is in the active set (the level-0 flags of this name are dead by now)
-  double* u = W + WS_U;
-  double* z = W + WS_Z;
-  double* d = W + WS_D;
-  double* rr = W + WS_RR;
-  double* zd = W + WS_ZD;
-  double* np = W + WS_NP;
-  double* sc = W + WS_CN;
-  double* viol = W + WS_VH;        // [56] scaled violation of the candidate rows (the Householder vector storage is idle here)
-  double* scl = W + WS_SCL;        // [56] 1 / (1 + |Gg_i|)
+QM_HDN void gi_iterate(G w0, int n, int nD0, const GiMem& gm) {
+  double* J = gm.J;
+  double* RF = gm.RF;
+  int* act = gm.act;
+  int* ina = gm.ina;
+  double* u = gm.u;
+  double* z = gm.z;
+  double* d = gm.d;
+  double* rr = gm.rr;
+  double* zd = gm.zd;
+  double* np = gm.np;
+  double* sc = gm.sc;
+  double* viol = gm.viol;
+  double* scl = gm.scl;
+  const double* GG = gm.GG;
+  const double* Gg = gm.Gg;
+  double* res = gm.res;
   int total = 0;
   int iq = 0;                      // size of the active set (uniform over the lanes)
-  QM_PFOR(w0, i, 56) { ina[i] = 0; scl[i] = (i < nD0) ? 1.0 / (1.0 + fabs(W[WS_Gg + i])) : 0.0; }
+  QM_PFOR(w0, i, 56) { ina[i] = 0; scl[i] = (i < nD0) ? 1.0 / (1.0 + fabs(Gg[i])) : 0.0; }
   w0.sync();
   for (int outer = 0; outer < 200; ++outer) {
     // constraint values c_i = gg_i - Gg_i z  (>= 0 feasible) and the scaled violation of every row that may enter
     QM_PFOR(w0, i, nD0) {
-      double s = W[WS_Gg + i];
-      for (int c = 0; c < n; ++c) s -= W[WS_GG + 56 * c + i] * z[c];
-      W[WS_RES + i] = s;
+      double s = Gg[i];
+      for (int c = 0; c < n; ++c) s -= GG[56 * c + i] * z[c];
+      res[i] = s;
       const double v = s * scl[i];
-      viol[i] = (WI[WI_IGN + i] || ina[i] || !(v < -1e-9)) ? 0.0 : v;
+      viol[i] = (gm.ign[i] || ina[i] || !(v < -1e-9)) ? 0.0 : v;
     }
     w0.sync();
     double worst = 0.0;
@@ -819,9 +852,9 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
     (void)worst;
     QM_TICK(46);
     if (ip < 0) break;
-    double cip = W[WS_RES + ip];
+    double cip = res[ip];
     if (w0.tid() == 0) u[iq] = 0.0;
-    QM_PFOR(w0, c, n) np[c] = -W[WS_GG + 56 * c + ip];
+    QM_PFOR(w0, c, n) np[c] = -GG[56 * c + ip];
     w0.sync();
     for (int inner = 0; inner < 200; ++inner) {
       // d = J' np
@@ -845,8 +878,8 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
       if (t >= 1e300) {
         // dependent normal and nothing to drop: infeasible up to rounding -> ignore a marginally violated row
         if (w0.tid() == 0) {
-          if (!(fabs(cip) < 1e-6 * (1.0 + fabs(W[WS_Gg + ip])))) WI[WI_SC + 6] |= WST_DEGENERATE;
-          WI[WI_IGN + ip] = 1;
+          if (!(fabs(cip) < 1e-6 * (1.0 + fabs(Gg[ip])))) *gm.status |= WST_DEGENERATE;
+          gm.ign[ip] = 1;
         }
         w0.sync();
         break;
@@ -960,19 +993,18 @@ QM_HDN void gi_iterate(G w0, int n, int nD0, double* W, int* WI) {
         }
         J[i * 18 + q2] = x1;
       }
-      cip = W[WS_Gg + ip];
-      for (int c = 0; c < n; ++c) cip -= W[WS_GG + 56 * c + ip] * z[c];
+      cip = Gg[ip];
+      for (int c = 0; c < n; ++c) cip -= GG[56 * c + ip] * z[c];
       w0.sync(); QM_TICK(52);
-      if (++total > 400) { if (w0.tid() == 0) WI[WI_SC + 6] |= WST_QP_MAX_ITER; break; }
+      if (++total > 400) { if (w0.tid() == 0) *gm.status |= WST_QP_MAX_ITER; break; }
     }
     if (total > 400) break;
   }
-  if (w0.tid() == 0) WI[WI_SC + 4] = iq;
   w0.sync();
 }
 
 template <class G>
-QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
+QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
   const int ld = n + 1;
   double* QR = W + WS_LS;
   double* J = W + WS_J;
@@ -999,17 +1031,21 @@ QM_HDN void wbc_gi(G g, int n, int r, int nD0, double* W, int* WI) {
   if (g.tid() == 0) { WI[WI_SC + 4] = 0; WI[WI_SC + 10] = 0; }
   QM_PFOR(g, i, 56) WI[WI_IGN + i] = 0;
   g.sync();
-  // The active-set iteration is a dependency chain: it runs on the narrow group (one warp) with lane-parallel vector
-  // operations (J' n, J2 d2, row-wise Givens updates of J) and lane-0 scalar decisions; the rest of the CTA waits.
   QM_TICK(40);
-  if (g.narrow_active()) gi_iterate(g.narrow(), n, nD0, W, WI);
-  g.sync(); QM_TICK(41);
 }
 
-// HierarchicalWbc::update after the task stack is in W: three nested levels, then the torque recovery. cmd[54].
+// HierarchicalWbc::update after the task stack is in W, as four resumable pieces around the active-set iteration of a level, so
+// that the iteration (a dependency chain on one warp) can also run as its own kernel with many solves per SM:
+//   wbc_solve_begin   level 0 and its kernel basis
+//   wbc_solve_prepare skips empty levels; for the next level with rows: A Z, D0 Z, least-squares start, J  -> true (iteration due)
+//   [gi_iterate]
+//   wbc_solve_advance x += Z z, kernel basis of the level, next stacked basis
+//   wbc_solve_finish  torque recovery, cmd[54], status
+// Loop state of a solve in WI_SC: [15] level, [16] columns of the current basis, [17] which basis buffer is current (0: WW_Z0,
+// 1: WW_Z1), [18] WSS_* (what the solve waits for).
+enum { WSS_NONE = 0, WSS_ITERATION = 1, WSS_DONE = 2 };
 template <class G>
-QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, int* status, double* levels = nullptr) {
-  const int nD0 = WI[WI_SC + 9];
+QM_HDN void wbc_solve_begin(G g, double* W, const double* Wc, int* WI, double* levels = nullptr) {
   if (g.tid() == 0) WI[WI_SC + 6] = 0;
   g.sync();
   // ---- level 0
@@ -1030,16 +1066,24 @@ QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, in
     QM_PFOR(g, i, 36) levels[WBL_X + i] = W[WW_X + i];
     QM_PFOR(g, i, 36 * 18) levels[WBL_Z + i] = W[WW_Z0 + i];
     QM_PFOR(g, i, 56) levels[WBL_V0 + i] = W[WW_V0 + i];
-    g.sync();
   }
-  // ---- levels 1 .. nlev - 1, each in the coordinates x = x_prev + Z z of the null space the levels above leave
-  //      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
-  //      full stance -- changes nothing)
+  g.sync();
+  if (g.tid() == 0) { WI[WI_SC + 15] = 1; WI[WI_SC + 16] = n1; WI[WI_SC + 17] = 0; WI[WI_SC + 18] = WSS_NONE; }
+  g.sync();
+}
+
+// ---- levels 1 .. nlev - 1, each in the coordinates x = x_prev + Z z of the null space the levels above leave
+//      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
+//      full stance -- changes nothing)
+template <class G>
+QM_HDN bool wbc_solve_prepare(G g, double* W, const double* Wc, int* WI, double* levels = nullptr) {
+  const int nD0 = WI[WI_SC + 9];
   const int nlev = WI[WI_LV];
-  double* Zc = W + WW_Z0;                   // current basis [36][18]
-  double* Zn = W + WW_Z1;                   // next one
-  int n = n1;
-  for (int p = 1; p < nlev; ++p) {
+  const int n = WI[WI_SC + 16];
+  const double* Zc = W + (WI[WI_SC + 17] ? WW_Z1 : WW_Z0);     // current basis [36][18]
+  int p = WI[WI_SC + 15];
+  g.sync();                                   // everybody has read the loop state before it is rewritten
+  for (; p < nlev; ++p) {
     const int off = WI[WI_LV + 2 * p], r = WI[WI_LV + 2 * p + 1];
     if (r == 0 || n == 0) {                  // empty level, or no freedom left: x and the basis stay as they are
       if (levels != nullptr) {
@@ -1077,37 +1121,62 @@ QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, in
       W[WS_Gg + i] = s;
     }
     g.sync(); QM_TICK(39);
-    wbc_gi(g, n, r, nD0, W, WI);
-    QM_PFOR(g, k, 36) {
-      double s = 0.0;
-      for (int c = 0; c < n; ++c) s += Zc[18 * k + c] * W[WS_Z + c];
-      W[WW_X + k] += s;
-    }
-    g.sync();
-    if (p + 1 < nlev) {
-      // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
-      kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_GG, W + WS_J, 18, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
-      const int nn = n - WI[WI_SC + 1];
-      QM_PFOR(g, idx, 36 * 18) {
-        const int i = idx / 18, c = idx % 18;
-        double s = 0.0;
-        if (c < nn) for (int k = 0; k < n; ++k) s += Zc[18 * i + k] * W[WS_J + 18 * k + c];
-        Zn[idx] = s;
-      }
-      g.sync(); QM_TICK(42);
-      double* t_ = Zc; Zc = Zn; Zn = t_;
-      n = nn;
-    }
-    if (levels != nullptr) {
-      double* L = levels + WBL_LEVEL * p;
-      const int nz = (p + 1 < nlev) ? n : 0;           // the last level's null space is never formed
-      if (g.tid() == 0) L[WBL_N] = (double)nz;
-      QM_PFOR(g, i, 36) L[WBL_X + i] = W[WW_X + i];
-      QM_PFOR(g, idx, 36 * 18) L[WBL_Z + idx] = (idx % 18 < nz) ? Zc[idx] : 0.0;
-      g.sync();
-    }
+    wbc_gi_prepare(g, n, r, W, WI);
+    break;
   }
-  // ---- torque recovery: tau = [M_j, -J_j'] x + h_j   (rows 0..17 of D0)
+  const bool due = p < nlev;
+  if (g.tid() == 0) { WI[WI_SC + 15] = p; WI[WI_SC + 18] = due ? WSS_ITERATION : WSS_NONE; }
+  g.sync();
+  return due;
+}
+
+template <class G>
+QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double* levels = nullptr) {
+  const int nlev = WI[WI_LV];
+  const int p = WI[WI_SC + 15];
+  int n = WI[WI_SC + 16];
+  const int sel = WI[WI_SC + 17];
+  const int r = WI[WI_LV + 2 * p + 1];
+  double* Zc = W + (sel ? WW_Z1 : WW_Z0);
+  double* Zn = W + (sel ? WW_Z0 : WW_Z1);
+  int nsel = sel;
+  g.sync();
+  QM_PFOR(g, k, 36) {
+    double s = 0.0;
+    for (int c = 0; c < n; ++c) s += Zc[18 * k + c] * W[WS_Z + c];
+    W[WW_X + k] += s;
+  }
+  g.sync();
+  if (p + 1 < nlev) {
+    // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
+    kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_GG, W + WS_J, 18, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+    const int nn = n - WI[WI_SC + 1];
+    QM_PFOR(g, idx, 36 * 18) {
+      const int i = idx / 18, c = idx % 18;
+      double s = 0.0;
+      if (c < nn) for (int k = 0; k < n; ++k) s += Zc[18 * i + k] * W[WS_J + 18 * k + c];
+      Zn[idx] = s;
+    }
+    g.sync(); QM_TICK(42);
+    double* t_ = Zc; Zc = Zn; Zn = t_;
+    nsel ^= 1;
+    n = nn;
+  }
+  if (levels != nullptr) {
+    double* L = levels + WBL_LEVEL * p;
+    const int nz = (p + 1 < nlev) ? n : 0;           // the last level's null space is never formed
+    if (g.tid() == 0) L[WBL_N] = (double)nz;
+    QM_PFOR(g, i, 36) L[WBL_X + i] = W[WW_X + i];
+    QM_PFOR(g, idx, 36 * 18) L[WBL_Z + idx] = (idx % 18 < nz) ? Zc[idx] : 0.0;
+  }
+  g.sync();
+  if (g.tid() == 0) { WI[WI_SC + 15] = p + 1; WI[WI_SC + 16] = n; WI[WI_SC + 17] = nsel; WI[WI_SC + 18] = WSS_NONE; }
+  g.sync();
+}
+
+// ---- torque recovery: tau = [M_j, -J_j'] x + h_j   (rows 0..17 of D0)
+template <class G>
+QM_HDN void wbc_solve_finish(G g, double* W, int* WI, double* cmd, int* status) {
   QM_PFOR(g, i, 54) {
     double v;
     if (i < 36) v = W[WW_X + i];
@@ -1122,8 +1191,22 @@ QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, in
     int st = WI[WI_SC + 6];
     for (int i = 0; i < 36; ++i) if (!(W[WW_X + i] == W[WW_X + i])) st |= WST_NAN;
     *status = st;
+    WI[WI_SC + 18] = WSS_DONE;
   }
   g.sync();
+}
+
+// The pieces in sequence on one group. The active-set iteration is a dependency chain: it runs on the narrow group (one warp)
+// with lane-parallel vector operations and warp-wide decisions; the rest of the CTA waits.
+template <class G>
+QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, int* status, double* levels = nullptr) {
+  wbc_solve_begin(g, W, Wc, WI, levels);
+  while (wbc_solve_prepare(g, W, Wc, WI, levels)) {
+    if (g.narrow_active()) gi_iterate(g.narrow(), WI[WI_SC + 16], WI[WI_SC + 9], gi_mem_of(W, WI));
+    g.sync(); QM_TICK(41);
+    wbc_solve_advance(g, W, Wc, WI, levels);
+  }
+  wbc_solve_finish(g, W, WI, cmd, status);
 }
 
 // One whole-body-control solve: WbcBase::update + HierarchicalWbc::update.

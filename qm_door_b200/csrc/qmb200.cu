@@ -1208,6 +1208,101 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
 
+
+// ---- the same solve as a sequence of kernels (the default path of a batch). k_wbc holds 56 KB of shared memory and four warps per
+// solve while the active-set iterations of its levels run on one warp, and co-resident CTAs in different phases evict each
+// other's instructions (k_wbc is 250 KB of code: identical solves in lockstep run 1.45x faster than a mixed batch). Split at the
+// iterations, every kernel is one phase for the whole batch, and the iteration runs warp per solve with 17 KB per solve:
+//   k_wbc_tasks  dynamics of both configurations, task stack                      -> D0, F0, h_j, level table, task rows
+//   k_wbc_level  [first] level 0, kernel basis; [later] x += Z z, kernel basis, next stacked basis;
+//                then the products and the least-squares start of the next level with rows, or the torque recovery
+//   k_wbc_gi     Goldfarb-Idnani iteration of the pending level, four solves per CTA
+// The state of a solve between kernels is its workspace image in global memory (ranges below; 45 KB written, 11 KB read by the
+// iteration) -- a few GB per 65 536 solves, a few percent of the time it buys.
+constexpr int kWbcKeepA = WW_X;                       // after the tasks: D0, F0, (V0), h_j
+constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, D0 Z, Gg, J, (RF), z
+constexpr int kGiWarpDoubles = ((GI_MEM_DOUBLES + 1) / 2) * 2;
+constexpr int kGiWarpInts = ((GI_MEM_INTS + 3) / 4) * 4;
+constexpr size_t kWbcGiSmemBytes = 4 * ((size_t)kGiWarpDoubles * sizeof(double) + (size_t)kGiWarpInts * sizeof(int));
+
+__device__ __forceinline__ void wbc_copy(double* dst, const double* src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
+                                                    const double* ud, const double* rbd, const int32_t* mode, const double* period,
+                                                    const double* time, double* u_last, double* cold, double* state, int* istate) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  extern __shared__ double smem[];
+  double* W = smem;
+  double* in = smem + WW_SIZE;
+  int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
+  for (int i = threadIdx.x; i < 30; i += blockDim.x) { in[i] = xd[30 * b + i]; in[30 + i] = ud[30 * b + i]; in[116 + i] = u_last[30 * b + i]; }
+  for (int i = threadIdx.x; i < 55; i += blockDim.x) in[60 + i] = rbd[55 * b + i];
+  __syncthreads();
+  QM_TICK(-1);
+  wbc_dynamics(BlockGroup(), *M, *C, in + 60, in, in + 30, in + 116, period[b], W);
+  QM_TICK(33);
+  wbc_tasks(BlockGroup(), *M, *C, in + 30, mode[b] & 15, time[b], W, cold + (size_t)WC_SIZE * b, WI);
+  QM_TICK(34);
+  __syncthreads();
+  wbc_copy(state + (size_t)WS_END * b, W, kWbcKeepA);
+  for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) istate[(size_t)WI_SIZE * b + i] = WI[i];
+  for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
+}
+
+__global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
+                                                    int32_t* status) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  int* SI = istate + (size_t)WI_SIZE * b;
+  if (!first && SI[WI_SC + 18] != WSS_ITERATION) return;          // finished in an earlier round
+  extern __shared__ double smem[];
+  double* W = smem;
+  int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
+  double* S = state + (size_t)WS_END * b;
+  const double* Wc = cold + (size_t)WC_SIZE * b;
+  wbc_copy(W, S, first ? kWbcKeepA : kWbcKeepB);
+  if (!first && SI[WI_SC + 17]) wbc_copy(W + WW_Z1, S + WW_Z1, 36 * 18);
+  for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) WI[i] = SI[i];
+  __syncthreads();
+  const BlockGroup g;
+  if (first) wbc_solve_begin(g, W, Wc, WI);
+  else wbc_solve_advance(g, W, Wc, WI);
+  if (wbc_solve_prepare(g, W, Wc, WI)) {
+    wbc_copy(S, W, kWbcKeepB);
+    if (WI[WI_SC + 17]) wbc_copy(S + WW_Z1, W + WW_Z1, 36 * 18);
+    for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) SI[i] = WI[i];
+  } else {
+    wbc_solve_finish(g, W, WI, cmd + 54 * (size_t)b, status + b);
+    if (threadIdx.x == 0) SI[WI_SC + 18] = WSS_DONE;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_wbc_gi(int B, double* state, int* istate) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + w;
+  if (b >= B) return;
+  int* SI = istate + (size_t)WI_SIZE * b;
+  if (SI[WI_SC + 18] != WSS_ITERATION) return;
+  extern __shared__ double smem[];
+  double* D = smem + (size_t)w * kGiWarpDoubles;
+  int* I = (int*)(smem + 4 * (size_t)kGiWarpDoubles) + (size_t)w * kGiWarpInts;
+  const GiMem gm = gi_mem_compact(D, I);
+  double* S = state + (size_t)WS_END * b;
+  const int n = SI[WI_SC + 16], nD0 = SI[WI_SC + 9];
+  for (int i = lane; i < 18 * 56; i += 32) gm.GG[i] = S[WS_GG + i];
+  for (int i = lane; i < 56; i += 32) { gm.Gg[i] = S[WS_Gg + i]; gm.ign[i] = 0; }
+  for (int i = lane; i < 324; i += 32) gm.J[i] = S[WS_J + i];
+  if (lane < 18) gm.z[lane] = S[WS_Z + lane];
+  if (lane == 0) *gm.status = 0;
+  __syncwarp();
+  gi_iterate(WarpGroup(), n, nD0, gm);
+  if (lane < 18) S[WS_Z + lane] = gm.z[lane];
+  if (lane == 0 && *gm.status) SI[WI_SC + 6] |= *gm.status;
+}
+
 // One solve with the per-level record of the hierarchy (HoQp accessors): diagnostic entry, not on the hot path
 __global__ void __launch_bounds__(128) k_wbc_levels(const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* in60_55_30, int mode,
                                                      double period, double time, double* cold, double* cmd, int32_t* status, double* levels) {
@@ -1257,6 +1352,9 @@ struct qmb200_wbc_ctx {
   qmb200_wbc_desc* dC = nullptr;
   double *xd = nullptr, *ud = nullptr, *rbd = nullptr, *period = nullptr, *time = nullptr, *u_last = nullptr, *cmd = nullptr;
   double* cold = nullptr;                       // [B][WC_SIZE] task rows read once per level (qm_wbc.h), L2-resident per solve
+  double* state = nullptr; int* istate = nullptr;   // [B][WS_END], [B][WI_SIZE]: workspace image of a solve between the split kernels
+  bool split = true;                            // sequence of kernels (default) or the single kernel k_wbc (QMB200_WBC_SPLIT=0)
+  int rounds = 2;                               // levels below level 0 of the task stack (one iteration kernel each)
   int32_t *mode = nullptr, *status = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1277,7 +1375,17 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
                       const double* period, const double* time, double* cmd, int32_t* status) {
   wbc_harvest(c);
   CUDA_OK(cudaEventRecord(c->e0, c->stream));
-  k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold, cmd, status);
+  if (c->split) {
+    k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
+                                                                    c->state, c->istate);
+    k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status);
+    for (int r = 0; r < c->rounds; ++r) {
+      k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate);
+      k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status);
+    }
+  } else {
+    k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold, cmd, status);
+  }
   CUDA_OK(cudaEventRecord(c->e1, c->stream));
   CUDA_OK(cudaGetLastError());
   c->pending = true;
@@ -1313,6 +1421,18 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   C_OK(cudaMalloc(&c->u_last, B * 30 * sizeof(double)));
   C_OK(cudaMalloc(&c->cmd, B * 54 * sizeof(double)));
   C_OK(cudaMalloc(&c->cold, B * WC_SIZE * sizeof(double)));
+  {
+    const char* env = getenv("QMB200_WBC_SPLIT");
+    c->split = !(env && atoi(env) == 0);
+    c->rounds = (wbc->mpc_variant == 2) ? WB_MAXLEV - 1 : 2;
+  }
+  if (c->split) {
+    C_OK(cudaMalloc(&c->state, B * WS_END * sizeof(double)));
+    C_OK(cudaMalloc(&c->istate, B * WI_SIZE * sizeof(int)));
+    C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+    C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+    C_OK(cudaFuncSetAttribute(k_wbc_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcGiSmemBytes));
+  }
   C_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
   C_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));
   C_OK(cudaMemset(c->u_last, 0, B * 30 * sizeof(double)));
@@ -1327,7 +1447,7 @@ int qmb200_wbc_destroy(qmb200_wbc_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->cold, c->mode, c->status,
+  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->cold, c->state, c->istate, c->mode, c->status,
                   c->act_stamp, c->act_buf, c->act_hc, c->act_last};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->e0) cudaEventDestroy(c->e0);
@@ -1349,6 +1469,7 @@ int qmb200_wbc_set_gains(qmb200_wbc_ctx* c, const qmb200_wbc_desc* wbc) {
   CUDA_OK(cudaSetDevice(c->device));
   CUDA_OK(cudaStreamSynchronize(c->stream));     // gains are snapshotted between solves, never mid-solve
   CUDA_OK(cudaMemcpy(c->dC, wbc, sizeof(*wbc), cudaMemcpyHostToDevice));
+  c->rounds = (wbc->mpc_variant == 2) ? WB_MAXLEV - 1 : 2;
   return 0;
 }
 
