@@ -639,7 +639,7 @@ QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
 // ------------------------------------------------------------------------------------------ level 0
 // min 1/2|A0 z - b0|^2 + eps/2 |z|^2 + 1/2 |(D0 z - f0)+|^2  by Newton iteration on the active set of violated rows.
 template <class G>
-QM_HDN void wbc_level0(G g, double* W, const double* Wc, int* WI) {
+QM_HDN void wbc_level0(G g, double* W, const double* D0, const double* Wc, int* WI) {
   const int nD0 = WI[WI_SC + 9];
   const int ld = WB_QR_LD;
   double* QR = W + WS_QR;
@@ -659,7 +659,7 @@ QM_HDN void wbc_level0(G g, double* W, const double* Wc, int* WI) {
     QM_PFOR(g, idx, m * ld) {
       const int r = idx / ld, c = idx % ld;
       double v;
-      if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? W[WW_D0 + 36 * i + c] : W[WW_F0 + i]; }
+      if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? D0[36 * i + c] : W[WW_F0 + i]; }
       else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? Wc[WC_A0 + 36 * i + c] : Wc[WC_B0 + i]; }
       else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
       QR[idx] = v;
@@ -671,7 +671,7 @@ QM_HDN void wbc_level0(G g, double* W, const double* Wc, int* WI) {
     g.sync();
     QM_PFOR(g, i, nD0) {
       double s = -W[WW_F0 + i];
-      for (int c = 0; c < 36; ++c) s += W[WW_D0 + 36 * i + c] * W[WW_X + c];
+      for (int c = 0; c < 36; ++c) s += D0[36 * i + c] * W[WW_X + c];
       W[WS_RES + i] = s;
     }
     g.sync();
@@ -1041,15 +1041,17 @@ QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
 //   [gi_iterate]
 //   wbc_solve_advance x += Z z, kernel basis of the level, next stacked basis
 //   wbc_solve_finish  torque recovery, cmd[54], status
+// D0 (the inequality rows of level 0, [56][36]) is read through its own pointer: the workspace block WW_D0 in the single-kernel
+// solve and on the host, the solve's image in global memory in the kernel sequence (the largest block, read a few times).
 // Loop state of a solve in WI_SC: [15] level, [16] columns of the current basis, [17] which basis buffer is current (0: WW_Z0,
 // 1: WW_Z1), [18] WSS_* (what the solve waits for).
 enum { WSS_NONE = 0, WSS_ITERATION = 1, WSS_DONE = 2 };
 template <class G>
-QM_HDN void wbc_solve_begin(G g, double* W, const double* Wc, int* WI, double* levels = nullptr) {
+QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr) {
   if (g.tid() == 0) WI[WI_SC + 6] = 0;
   g.sync();
   // ---- level 0
-  wbc_level0(g, W, Wc, WI);
+  wbc_level0(g, W, D0, Wc, WI);
   QM_TICK(-1);
   // Z0 = kernel(A0) in the reference's own (FullPivLU) basis; it has 36 - rank(A0) columns, at most 18 are kept (rank(A0) = 18
   // unless the contact Jacobians are degenerate, which is flagged)
@@ -1076,7 +1078,7 @@ QM_HDN void wbc_solve_begin(G g, double* W, const double* Wc, int* WI, double* l
 //      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
 //      full stance -- changes nothing)
 template <class G>
-QM_HDN bool wbc_solve_prepare(G g, double* W, const double* Wc, int* WI, double* levels = nullptr) {
+QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr) {
   const int nD0 = WI[WI_SC + 9];
   const int nlev = WI[WI_LV];
   const int n = WI[WI_SC + 16];
@@ -1112,12 +1114,12 @@ QM_HDN bool wbc_solve_prepare(G g, double* W, const double* Wc, int* WI, double*
     QM_PFOR(g, idx, nD0 * 18) {
       const int i = idx / 18, c = idx % 18;
       double s = 0.0;
-      if (c < n) for (int k = 0; k < 36; ++k) s += W[WW_D0 + 36 * i + k] * Zc[18 * k + c];
+      if (c < n) for (int k = 0; k < 36; ++k) s += D0[36 * i + k] * Zc[18 * k + c];
       W[WS_GG + 56 * c + i] = s;
     }
     QM_PFOR(g, i, nD0) {
       double s = W[WW_F0 + i] + W[WW_V0 + i];
-      for (int k = 0; k < 36; ++k) s -= W[WW_D0 + 36 * i + k] * W[WW_X + k];
+      for (int k = 0; k < 36; ++k) s -= D0[36 * i + k] * W[WW_X + k];
       W[WS_Gg + i] = s;
     }
     g.sync(); QM_TICK(39);
@@ -1176,14 +1178,14 @@ QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double*
 
 // ---- torque recovery: tau = [M_j, -J_j'] x + h_j   (rows 0..17 of D0)
 template <class G>
-QM_HDN void wbc_solve_finish(G g, double* W, int* WI, double* cmd, int* status) {
+QM_HDN void wbc_solve_finish(G g, double* W, const double* D0, int* WI, double* cmd, int* status) {
   QM_PFOR(g, i, 54) {
     double v;
     if (i < 36) v = W[WW_X + i];
     else {
       const int l = i - 36;
       v = W[WW_HJ + l];
-      for (int c = 0; c < 36; ++c) v += W[WW_D0 + 36 * l + c] * W[WW_X + c];
+      for (int c = 0; c < 36; ++c) v += D0[36 * l + c] * W[WW_X + c];
     }
     cmd[i] = v;
   }
@@ -1200,13 +1202,14 @@ QM_HDN void wbc_solve_finish(G g, double* W, int* WI, double* cmd, int* status) 
 // with lane-parallel vector operations and warp-wide decisions; the rest of the CTA waits.
 template <class G>
 QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, int* status, double* levels = nullptr) {
-  wbc_solve_begin(g, W, Wc, WI, levels);
-  while (wbc_solve_prepare(g, W, Wc, WI, levels)) {
+  const double* D0 = W + WW_D0;
+  wbc_solve_begin(g, W, D0, Wc, WI, levels);
+  while (wbc_solve_prepare(g, W, D0, Wc, WI, levels)) {
     if (g.narrow_active()) gi_iterate(g.narrow(), WI[WI_SC + 16], WI[WI_SC + 9], gi_mem_of(W, WI));
     g.sync(); QM_TICK(41);
     wbc_solve_advance(g, W, Wc, WI, levels);
   }
-  wbc_solve_finish(g, W, WI, cmd, status);
+  wbc_solve_finish(g, W, D0, WI, cmd, status);
 }
 
 // One whole-body-control solve: WbcBase::update + HierarchicalWbc::update.

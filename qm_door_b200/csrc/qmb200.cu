@@ -1221,6 +1221,8 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
 // iteration) -- a few GB per 65 536 solves, a few percent of the time it buys.
 constexpr int kWbcKeepA = WW_X;                       // after the tasks: D0, F0, (V0), h_j
 constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, D0 Z, Gg, J, (RF), z
+// k_wbc_level keeps D0 where k_wbc_tasks left it (global memory) and holds the workspace from WW_F0 on: 40 KB, five solves per SM
+constexpr size_t kWbcLevelSmemBytes = (size_t)(WW_SIZE - WW_F0) * sizeof(double) + WI_SIZE * sizeof(int);
 constexpr int kGiWarpDoubles = ((GI_MEM_DOUBLES + 1) / 2) * 2;
 constexpr int kGiWarpInts = ((GI_MEM_INTS + 3) / 4) * 4;
 constexpr size_t kWbcGiSmemBytes = 4 * ((size_t)kGiWarpDoubles * sizeof(double) + (size_t)kGiWarpInts * sizeof(int));
@@ -1252,30 +1254,31 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb20
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
 
-__global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
+__global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
                                                     int32_t* status) {
   const int b = blockIdx.x;
   if (b >= B) return;
   int* SI = istate + (size_t)WI_SIZE * b;
   if (!first && SI[WI_SC + 18] != WSS_ITERATION) return;          // finished in an earlier round
   extern __shared__ double smem[];
-  double* W = smem;
-  int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
+  double* W = smem - WW_F0;                          // workspace offsets from WW_F0 on are in shared memory; WW_D0 is never used
+  int* WI = (int*)(smem + (WW_SIZE - WW_F0));
   double* S = state + (size_t)WS_END * b;
+  const double* D0 = S + WW_D0;
   const double* Wc = cold + (size_t)WC_SIZE * b;
-  wbc_copy(W, S, first ? kWbcKeepA : kWbcKeepB);
+  wbc_copy(W + WW_F0, S + WW_F0, (first ? kWbcKeepA : kWbcKeepB) - WW_F0);
   if (!first && SI[WI_SC + 17]) wbc_copy(W + WW_Z1, S + WW_Z1, 36 * 18);
   for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) WI[i] = SI[i];
   __syncthreads();
   const BlockGroup g;
-  if (first) wbc_solve_begin(g, W, Wc, WI);
+  if (first) wbc_solve_begin(g, W, D0, Wc, WI);
   else wbc_solve_advance(g, W, Wc, WI);
-  if (wbc_solve_prepare(g, W, Wc, WI)) {
-    wbc_copy(S, W, kWbcKeepB);
+  if (wbc_solve_prepare(g, W, D0, Wc, WI)) {
+    wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepB - WW_F0);
     if (WI[WI_SC + 17]) wbc_copy(S + WW_Z1, W + WW_Z1, 36 * 18);
     for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) SI[i] = WI[i];
   } else {
-    wbc_solve_finish(g, W, WI, cmd + 54 * (size_t)b, status + b);
+    wbc_solve_finish(g, W, D0, WI, cmd + 54 * (size_t)b, status + b);
     if (threadIdx.x == 0) SI[WI_SC + 18] = WSS_DONE;
   }
 }
@@ -1378,10 +1381,10 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
   if (c->split) {
     k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
                                                                     c->state, c->istate);
-    k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status);
+    k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status);
     for (int r = 0; r < c->rounds; ++r) {
       k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate);
-      k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status);
+      k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status);
     }
   } else {
     k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold, cmd, status);
@@ -1430,7 +1433,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
     C_OK(cudaMalloc(&c->state, B * WS_END * sizeof(double)));
     C_OK(cudaMalloc(&c->istate, B * WI_SIZE * sizeof(int)));
     C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
-    C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+    C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcLevelSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcGiSmemBytes));
   }
   C_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
