@@ -509,7 +509,12 @@ QM_HDO void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
       const int j = k + jj;
       const int i0 = k + part * chunk, i1 = (i0 + chunk < mk) ? i0 + chunk : mk;
       double sp = 0.0;
-      for (int i = i0; i < i1; ++i) sp += A[i * ld + k] * A[i * ld + j];
+      const double* ak = A + i0 * ld + k;
+      const double* aj = A + i0 * ld + j;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+      for (int i = i0; i < i1; ++i, ak += ld, aj += ld) sp += *ak * *aj;
       hp[part * HH_LD + jj] = sp;
     }
     g.sync();
@@ -530,9 +535,16 @@ QM_HDO void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
       if (g.tid() == 0) wj[ld + 1] = alpha;
     }
     g.sync();
-    QM_PFOR2(g, ii, rows, jj, n - k) {                      // rows over the warps, columns over the lanes: no index division
-      const int i = k + ii, j = k + 1 + jj;
-      A[i * ld + j] -= vh[i] * wj[j];
+    // rank-one update, rows over the warps and columns over the lanes (no index division); a lane keeps its w_j in a register
+    for (int jj = g.tid() & 31; jj < n - k; jj += (g.nt() < 32 ? g.nt() : 32)) {
+      const double w = wj[k + 1 + jj];
+      const int r0 = g.tid() >> 5, rs = (g.nt() + 31) >> 5;
+      double* a = A + (k + r0) * ld + k + 1 + jj;
+      const double* v = vh + k + r0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+      for (int ii = r0; ii < rows; ii += rs, a += rs * ld, v += rs) *a -= *v * w;
     }
     QM_PFOR(g, i, rows) A[(k + i) * ld + k] = (i == 0) ? wj[ld + 1] : 0.0;
     g.sync();
