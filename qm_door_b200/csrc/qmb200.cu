@@ -1227,15 +1227,30 @@ constexpr int kGiWarpDoubles = ((GI_MEM_DOUBLES + 1) / 2) * 2;
 constexpr int kGiWarpInts = ((GI_MEM_INTS + 3) / 4) * 4;
 constexpr size_t kWbcGiSmemBytes = 4 * ((size_t)kGiWarpDoubles * sizeof(double) + (size_t)kGiWarpInts * sizeof(int));
 
+// Solves ordered by contact pattern (counting sort, 16 buckets): the CTAs that share an SM then run the same branches of the task
+// builder at the same time and share the instructions they fetch (k_wbc_tasks is bound by instruction fetch: 65 % hit rate in a
+// mixed batch). The order inside a bucket is whatever the atomics give; it only decides which CTA handles which solve.
+__global__ void __launch_bounds__(1024) k_wbc_order(int B, const int32_t* mode, int* perm) {
+  __shared__ int cnt[16], off[16];
+  if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) atomicAdd(&cnt[mode[b] & 15], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { int a = 0; for (int m = 0; m < 16; ++m) { off[m] = a; a += cnt[m]; } }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) perm[atomicAdd(&off[mode[b] & 15], 1)] = b;
+}
+
 __device__ __forceinline__ void wbc_copy(double* dst, const double* src, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
                                                     const double* ud, const double* rbd, const int32_t* mode, const double* period,
-                                                    const double* time, double* u_last, double* cold, double* state, int* istate) {
-  const int b = blockIdx.x;
-  if (b >= B) return;
+                                                    const double* time, double* u_last, double* cold, double* state, int* istate,
+                                                    const int* perm) {
+  if ((int)blockIdx.x >= B) return;
+  const int b = perm[blockIdx.x];
   extern __shared__ double smem[];
   double* W = smem;
   double* in = smem + WW_SIZE;
@@ -1255,9 +1270,9 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb20
 }
 
 __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
-                                                    int32_t* status) {
-  const int b = blockIdx.x;
-  if (b >= B) return;
+                                                    int32_t* status, const int* perm) {
+  if ((int)blockIdx.x >= B) return;
+  const int b = perm[blockIdx.x];
   int* SI = istate + (size_t)WI_SIZE * b;
   if (!first && SI[WI_SC + 18] != WSS_ITERATION) return;          // finished in an earlier round
   extern __shared__ double smem[];
@@ -1283,10 +1298,10 @@ __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int firs
   }
 }
 
-__global__ void __launch_bounds__(128) k_wbc_gi(int B, double* state, int* istate) {
+__global__ void __launch_bounds__(128) k_wbc_gi(int B, double* state, int* istate, const int* perm) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + w;
-  if (b >= B) return;
+  if ((int)blockIdx.x * 4 + w >= B) return;
+  const int b = perm[blockIdx.x * 4 + w];
   int* SI = istate + (size_t)WI_SIZE * b;
   if (SI[WI_SC + 18] != WSS_ITERATION) return;
   extern __shared__ double smem[];
@@ -1355,6 +1370,7 @@ struct qmb200_wbc_ctx {
   qmb200_wbc_desc* dC = nullptr;
   double *xd = nullptr, *ud = nullptr, *rbd = nullptr, *period = nullptr, *time = nullptr, *u_last = nullptr, *cmd = nullptr;
   double* cold = nullptr;                       // [B][WC_SIZE] task rows read once per level (qm_wbc.h), L2-resident per solve
+  int* perm = nullptr;                          // [B] solves ordered by contact pattern
   double* state = nullptr; int* istate = nullptr;   // [B][WS_END], [B][WI_SIZE]: workspace image of a solve between the split kernels
   bool split = true;                            // sequence of kernels (default) or the single kernel k_wbc (QMB200_WBC_SPLIT=0)
   int rounds = 2;                               // levels below level 0 of the task stack (one iteration kernel each)
@@ -1379,12 +1395,13 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
   wbc_harvest(c);
   CUDA_OK(cudaEventRecord(c->e0, c->stream));
   if (c->split) {
+    k_wbc_order<<<1, 1024, 0, c->stream>>>(c->B, mode, c->perm);
     k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
-                                                                    c->state, c->istate);
-    k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status);
+                                                                    c->state, c->istate, c->perm);
+    k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status, c->perm);
     for (int r = 0; r < c->rounds; ++r) {
-      k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate);
-      k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status);
+      k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate, c->perm);
+      k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status, c->perm);
     }
   } else {
     k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold, cmd, status);
@@ -1432,6 +1449,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   if (c->split) {
     C_OK(cudaMalloc(&c->state, B * WS_END * sizeof(double)));
     C_OK(cudaMalloc(&c->istate, B * WI_SIZE * sizeof(int)));
+    C_OK(cudaMalloc(&c->perm, B * sizeof(int)));
     C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcLevelSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcGiSmemBytes));
@@ -1450,7 +1468,7 @@ int qmb200_wbc_destroy(qmb200_wbc_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->cold, c->state, c->istate, c->mode, c->status,
+  void* ptrs[] = {c->dM, c->dC, c->xd, c->ud, c->rbd, c->period, c->time, c->u_last, c->cmd, c->cold, c->state, c->istate, c->perm, c->mode, c->status,
                   c->act_stamp, c->act_buf, c->act_hc, c->act_last};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->e0) cudaEventDestroy(c->e0);
