@@ -4,6 +4,7 @@ import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("QMB200_WBC_SPLIT", "0")      # cycle counts of the single kernel k_wbc (one CTA = one whole solve)
 os.environ["QMB200_LIB_PATH"] = os.path.join(ROOT, "qm_door_b200", "libqmb200_dbg.so")
 import qm_door_b200 as q
 from qm_door_b200 import workload
