@@ -112,6 +112,7 @@ struct BlockGroup {
 #else
 #define QM_UNROLL
 #endif
+#define QM_RESTRICT __restrict__
 #define QM_PFOR(g, i, n) for (int i = (g).tid(); i < (n); i += (g).nt())
 // two-level loop without index division: rows over the warps of the group, columns over the lanes
 #define QM_PFOR2(g, i, ni, c, nc)                                              \

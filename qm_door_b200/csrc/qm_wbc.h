@@ -539,8 +539,8 @@ QM_HDO void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
     for (int jj = g.tid() & 31; jj < n - k; jj += (g.nt() < 32 ? g.nt() : 32)) {
       const double w = wj[k + 1 + jj];
       const int r0 = g.tid() >> 5, rs = (g.nt() + 31) >> 5;
-      double* a = A + (k + r0) * ld + k + 1 + jj;
-      const double* v = vh + k + r0;
+      double* QM_RESTRICT a = A + (k + r0) * ld + k + 1 + jj;
+      const double* QM_RESTRICT v = vh + k + r0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 4
 #endif
@@ -548,6 +548,77 @@ QM_HDO void householder_ls(G g, double* A, int m, int n, int ld, double* vh, dou
     }
     QM_PFOR(g, i, rows) A[(k + i) * ld + k] = (i == 0) ? wj[ld + 1] : 0.0;
     g.sync();
+  }
+}
+
+// y[i * ldy] -= x[i * ldx] * w for i < count, four rows at a time with all loads ahead of the first store (the compiler keeps a
+// load of x behind the preceding store to y otherwise: a shared-memory round trip per row on the chain)
+QM_HD void hh_axpy(double* y, int ldy, const double* x, int ldx, int count, double w) {
+  int i = 0;
+  for (; i + 4 <= count; i += 4, y += 4 * ldy, x += 4 * ldx) {
+    const double x0 = x[0], x1 = x[ldx], x2 = x[2 * ldx], x3 = x[3 * ldx];
+    const double y0 = y[0], y1 = y[ldy], y2 = y[2 * ldy], y3 = y[3 * ldy];
+    y[0] = y0 - x0 * w; y[ldy] = y1 - x1 * w; y[2 * ldy] = y2 - x2 * w; y[3 * ldy] = y3 - x3 * w;
+  }
+  for (; i < count; ++i, y += ldy, x += ldx) *y -= *x * w;
+}
+
+// The same triangularisation on one narrow group (a warp on the device), lane per column: a step is one pass of inner products
+// (each lane its own columns against column k, rows in order), the reflector's scalars formed by every lane, and one pass of
+// updates with w_j in a register -- no partial sums to combine, no scalar work repeated by four warps, two warp-level syncs per
+// step instead of three block barriers. A third of the instructions of householder_ls and a third of its latency for the
+// matrices of a solve (<= 92 x 37): the triangularisation is what bounded k_wbc_level by instruction issue.
+// hp: 2 doubles of scratch. Same `dense` convention as householder_ls.
+QM_HD double hh_dot(const double* QM_RESTRICT ak, const double* QM_RESTRICT aj, int ld, int count) {
+  double sp = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+  for (int i = 0; i < count; ++i, ak += ld, aj += ld) sp += *ak * *aj;
+  return sp;
+}
+template <class G>
+QM_HDO void householder_ls_narrow(G w0, double* A, int m, int n, int ld, double* hp, int dense) {
+  const int steps = (m - 1 < n) ? m - 1 : n;
+  for (int k = 0; k < steps; ++k) {
+    const int mk = (dense + k + 1 < m) ? dense + k + 1 : m;   // one past the last row step k touches
+    const int rows = mk - k, cols = n - k + 1;
+    double* colk = A + k * ld + k;
+#if defined(__CUDA_ARCH__)
+    // a lane owns column k + lane and, in the first steps of a matrix wider than the warp, column k + lane + 32
+    (void)hp;
+    const int lane = w0.tid();
+    const bool has0 = lane < cols, has1 = lane + 32 < cols;
+    const double d0 = has0 ? hh_dot(colk, colk + lane, ld, rows) : 0.0;
+    const double d1 = has1 ? hh_dot(colk, colk + lane + 32, ld, rows) : 0.0;
+    const double s = __shfl_sync(0xffffffffu, d0, 0);            // |A[k:, k]|^2
+#else
+    double dot[WB_QR_LD + 3];
+    for (int jj = 0; jj < cols; ++jj) dot[jj] = hh_dot(colk, colk + jj, ld, rows);
+    const double s = dot[0];
+#endif
+    const double nrm = sqrt(s);
+    const double akk = *colk;
+    const double alpha = (akk >= 0.0) ? -nrm : nrm;
+    const double vk = akk - alpha;
+    const double vv = s - akk * akk + vk * vk;                 // v'v with v = A[k:, k] - alpha e_k
+    const double beta = (vv > 0.0) ? 2.0 / vv : 0.0;
+    // column j > k: w = beta v'A_j with v'A_j = A_k'A_j - alpha A[k][j]; A_j -= v w
+    auto update = [&](int jj, double d) {
+      double* aj = colk + jj;
+      const double w = beta * (d - alpha * *aj);
+      *aj -= vk * w;
+      hh_axpy(aj + ld, ld, colk + ld, ld, rows - 1, w);
+    };
+#if defined(__CUDA_ARCH__)
+    if (has0 && lane > 0) update(lane, d0);
+    if (has1) update(lane + 32, d1);
+#else
+    for (int jj = 1; jj < cols; ++jj) update(jj, dot[jj]);
+#endif
+    w0.sync();
+    QM_PFOR(w0, i, rows) colk[i * ld] = (i == 0) ? alpha : 0.0;
+    w0.sync();
   }
 }
 
@@ -650,11 +721,31 @@ QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
 
 // ------------------------------------------------------------------------------------------ level 0
 // min 1/2|A0 z - b0|^2 + eps/2 |z|^2 + 1/2 |(D0 z - f0)+|^2  by Newton iteration on the active set of violated rows.
+// Storage of level 0: blocks of the solve's workspace (l0_mem_of) or the compact per-warp block of the stand-alone kernel.
+struct L0Mem {
+  const double* F0;                // [56] right-hand sides of the inequality rows
+  double *V0, *X;                  // [56] slack solution, [36] solution
+  double *QR, *res, *hp;           // [92][37] least-squares matrix | rhs, [56] row residuals, [4] scratch
+};
+enum { L0_MEM_DOUBLES = 56 + 56 + 36 + WB_QR_ROWS * WB_QR_LD + 56 + 4 };
+QM_HD L0Mem l0_mem_of(double* W) {
+  L0Mem m;
+  m.F0 = W + WW_F0; m.V0 = W + WW_V0; m.X = W + WW_X; m.QR = W + WS_QR; m.res = W + WS_RES; m.hp = W + WS_HP;
+  return m;
+}
+QM_HD L0Mem l0_mem_compact(double* D) {          // L0_MEM_DOUBLES doubles; F0 is filled by the caller
+  L0Mem m;
+  m.F0 = D; m.V0 = D + 56; m.X = m.V0 + 56; m.QR = m.X + 36; m.res = m.QR + WB_QR_ROWS * WB_QR_LD; m.hp = m.res + 56;
+  return m;
+}
 template <class G>
-QM_HDN void wbc_level0(G g, double* W, const double* D0, const double* Wc, int* WI) {
+QM_HDN void wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc, int* WI) {
+  const double* F0 = lm.F0;
+  double* X = lm.X;
+  double* RES = lm.res;
   const int nD0 = WI[WI_SC + 9];
   const int ld = WB_QR_LD;
-  double* QR = W + WS_QR;
+  double* QR = lm.QR;
   QM_PFOR(g, i, 56) WI[WI_INW + i] = 0;
   if (g.tid() == 0) WI[WI_SC + 10] = 0;
   g.sync();
@@ -671,28 +762,30 @@ QM_HDN void wbc_level0(G g, double* W, const double* D0, const double* Wc, int* 
     QM_PFOR(g, idx, m * ld) {
       const int r = idx / ld, c = idx % ld;
       double v;
-      if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? D0[36 * i + c] : W[WW_F0 + i]; }
+      if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? D0[36 * i + c] : F0[i]; }
       else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? Wc[WC_A0 + 36 * i + c] : Wc[WC_B0 + i]; }
       else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
       QR[idx] = v;
     }
     g.sync(); QM_TICK(35);
-    householder_ls(g, QR, m, 36, ld, W + WS_VH, W + WS_WJ, W + WS_HP, nw + 18);
-    QM_TICK(36);
-    if (g.narrow_active()) back_substitute(g.narrow(), QR, 36, ld, W + WW_X);
+    if (g.narrow_active()) {
+      householder_ls_narrow(g.narrow(), QR, m, 36, ld, lm.hp, nw + 18);
+      QM_TICK(36);
+      back_substitute(g.narrow(), QR, 36, ld, X);
+    }
     g.sync();
     QM_PFOR(g, i, nD0) {
-      double s = -W[WW_F0 + i];
-      for (int c = 0; c < 36; ++c) s += D0[36 * i + c] * W[WW_X + c];
-      W[WS_RES + i] = s;
+      double s = -F0[i];
+      for (int c = 0; c < 36; ++c) s += D0[36 * i + c] * X[c];
+      RES[i] = s;
     }
     g.sync();
     if (g.tid() == 0) {
       int changed = 0;
       for (int i = 0; i < nD0; ++i) {
-        const double tol = 1e-9 * (1.0 + fabs(W[WW_F0 + i]));
+        const double tol = 1e-9 * (1.0 + fabs(F0[i]));
         const int in = WI[WI_INW + i];
-        const int nw_in = in ? (W[WS_RES + i] > -tol) : (W[WS_RES + i] > tol);
+        const int nw_in = in ? (RES[i] > -tol) : (RES[i] > tol);
         if (nw_in != in) { WI[WI_INW + i] = nw_in; ++changed; }
       }
       WI[WI_SC + 10] = (changed == 0);
@@ -701,7 +794,7 @@ QM_HDN void wbc_level0(G g, double* W, const double* D0, const double* Wc, int* 
     g.sync(); QM_TICK(37);
     if (WI[WI_SC + 10]) break;
   }
-  QM_PFOR(g, i, 56) W[WW_V0 + i] = (i < nD0 && W[WS_RES + i] > 0.0) ? W[WS_RES + i] : 0.0;
+  QM_PFOR(g, i, 56) lm.V0[i] = (i < nD0 && RES[i] > 0.0) ? RES[i] : 0.0;
   g.sync();
 }
 
@@ -1029,8 +1122,10 @@ QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
     QR[idx] = v;
   }
   g.sync();
-  householder_ls(g, QR, m, n, ld, W + WS_VH, W + WS_WJ, W + WS_HP, r);
-  if (g.narrow_active()) back_substitute(g.narrow(), QR, n, ld, W + WS_Z);
+  if (g.narrow_active()) {
+    householder_ls_narrow(g.narrow(), QR, m, n, ld, W + WS_HP, r);
+    back_substitute(g.narrow(), QR, n, ld, W + WS_Z);
+  }
   // J = R^-1 (upper triangular), column by column
   QM_PFOR(g, c, n) {
     for (int i = n - 1; i >= 0; --i) {
@@ -1059,11 +1154,14 @@ QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
 // 1: WW_Z1), [18] WSS_* (what the solve waits for).
 enum { WSS_NONE = 0, WSS_ITERATION = 1, WSS_DONE = 2 };
 template <class G>
-QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr) {
-  if (g.tid() == 0) WI[WI_SC + 6] = 0;
-  g.sync();
-  // ---- level 0
-  wbc_level0(g, W, D0, Wc, WI);
+QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr,
+                            bool level0_done = false) {
+  // ---- level 0 (level0_done: the stand-alone kernel k_wbc_level0 has left x, the slack and the status word)
+  if (!level0_done) {
+    if (g.tid() == 0) WI[WI_SC + 6] = 0;
+    g.sync();
+    wbc_level0(g, l0_mem_of(W), D0, Wc, WI);
+  }
   QM_TICK(-1);
   // Z0 = kernel(A0) in the reference's own (FullPivLU) basis; it has 36 - rank(A0) columns, at most 18 are kept (rank(A0) = 18
   // unless the contact Jacobians are degenerate, which is flagged)

@@ -1269,6 +1269,30 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb20
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
 
+// Level 0 (Newton iteration on the least-squares form, one Householder triangularisation per pass) with one warp per solve and
+// 30 KB per solve: seven solves per SM. D0 and the level-0 equality rows are read in place (global memory).
+constexpr int kL0Doubles = ((L0_MEM_DOUBLES + 1) / 2) * 2;
+constexpr size_t kWbcL0SmemBytes = (size_t)kL0Doubles * sizeof(double) + WI_SIZE * sizeof(int);
+__global__ void __launch_bounds__(32) k_wbc_level0(int B, const double* cold, double* state, int* istate, const int* perm) {
+  if ((int)blockIdx.x >= B) return;
+  const int b = perm[blockIdx.x], lane = threadIdx.x;
+  extern __shared__ double smem[];
+  int* WI = (int*)(smem + kL0Doubles);
+  int* SI = istate + (size_t)WI_SIZE * b;
+  double* S = state + (size_t)WS_END * b;
+  const L0Mem lm = l0_mem_compact(smem);
+  for (int i = lane; i < 56; i += 32) smem[i] = S[WW_F0 + i];
+  for (int i = lane; i < WI_SIZE; i += 32) WI[i] = SI[i];
+  __syncwarp();
+  if (lane == 0) WI[WI_SC + 6] = 0;
+  __syncwarp();
+  QM_TICK(-1);
+  wbc_level0(WarpGroup(), lm, S + WW_D0, cold + (size_t)WC_SIZE * b, WI);
+  for (int i = lane; i < 56; i += 32) S[WW_V0 + i] = lm.V0[i];
+  for (int i = lane; i < 36; i += 32) S[WW_X + i] = lm.X[i];
+  if (lane == 0) SI[WI_SC + 6] = WI[WI_SC + 6];
+}
+
 __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
                                                     int32_t* status, const int* perm) {
   if ((int)blockIdx.x >= B) return;
@@ -1281,12 +1305,12 @@ __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int firs
   double* S = state + (size_t)WS_END * b;
   const double* D0 = S + WW_D0;
   const double* Wc = cold + (size_t)WC_SIZE * b;
-  wbc_copy(W + WW_F0, S + WW_F0, (first ? kWbcKeepA : kWbcKeepB) - WW_F0);
+  wbc_copy(W + WW_F0, S + WW_F0, (first ? WW_Z0 : kWbcKeepB) - WW_F0);      // first: F0, V0, h_j, x (level 0 is done)
   if (!first && SI[WI_SC + 17]) wbc_copy(W + WW_Z1, S + WW_Z1, 36 * 18);
   for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) WI[i] = SI[i];
   __syncthreads();
   const BlockGroup g;
-  if (first) wbc_solve_begin(g, W, D0, Wc, WI);
+  if (first) wbc_solve_begin(g, W, D0, Wc, WI, nullptr, true);
   else wbc_solve_advance(g, W, Wc, WI);
   if (wbc_solve_prepare(g, W, D0, Wc, WI)) {
     wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepB - WW_F0);
@@ -1398,6 +1422,7 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
     k_wbc_order<<<1, 1024, 0, c->stream>>>(c->B, mode, c->perm);
     k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
                                                                     c->state, c->istate, c->perm);
+    k_wbc_level0<<<c->B, 32, kWbcL0SmemBytes, c->stream>>>(c->B, c->cold, c->state, c->istate, c->perm);
     k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status, c->perm);
     for (int r = 0; r < c->rounds; ++r) {
       k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate, c->perm);
@@ -1453,6 +1478,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
     C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcLevelSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcGiSmemBytes));
+    C_OK(cudaFuncSetAttribute(k_wbc_level0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcL0SmemBytes));
   }
   C_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
   C_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));

@@ -11,7 +11,8 @@ from qm_door_b200 import workload
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 names = {33: "dynamics", 34: "tasks", 35: "L0 build", 36: "L0 householder", 37: "L0 backsub+residual+decide", 38: "kernel basis 0",
          39: "L1 prep", 40: "GI householder + J", 41: "GI iterate", 42: "kernel basis 1 + Z1", 43: "L2 prep", 45: "tail"}
-sub = {46: "gi violation + select", 47: "gi d", 48: "gi zd + backsub", 49: "gi step lengths", 50: "gi z, u", 51: "gi add", 52: "gi drop"}
+sub = {46: "gi violation + select", 47: "gi d", 48: "gi zd + backsub", 49: "gi step lengths", 50: "gi z, u", 51: "gi add", 52: "gi drop",
+       53: "hh inner products", 54: "hh scalars", 55: "hh update", 56: "hh column rewrite"}
 W = workload.WbcWorkload(B)
 ctx = q.WbcContext(W.model, W.wbc, B)
 L = q.lib()
