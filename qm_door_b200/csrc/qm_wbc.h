@@ -1210,27 +1210,38 @@ QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, const double* Wc
     }
     const double* Ap = Wc + WC_AP + 36 * off;
     const double* bpv = Wc + WC_BP + off;
-    QM_PFOR(g, idx, r * 18) {
-      const int i = idx / 18, c = idx % 18;
-      double s = 0.0;
-      if (c < n) for (int k = 0; k < 36; ++k) s += Ap[36 * i + k] * Zc[18 * k + c];
-      W[WS_GA + idx] = s;
-    }
+    // A Z and D0 Z as tile products (FP64 tensor-core tiles on the device); columns >= n are never read
+    mm<3, false>(g, r, n, 36, Ap, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GA, 18);
+    mm<3, false>(g, nD0, n, 36, D0, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GG, 18);
     QM_PFOR(g, i, r) {
       double s = bpv[i];
       for (int k = 0; k < 36; ++k) s -= Ap[36 * i + k] * W[WW_X + k];
       W[WS_GB + i] = s;
     }
-    QM_PFOR(g, idx, nD0 * 18) {
-      const int i = idx / 18, c = idx % 18;
-      double s = 0.0;
-      if (c < n) for (int k = 0; k < 36; ++k) s += D0[36 * i + k] * Zc[18 * k + c];
-      W[WS_GG + 56 * c + i] = s;
-    }
     QM_PFOR(g, i, nD0) {
       double s = W[WW_F0 + i] + W[WW_V0 + i];
       for (int k = 0; k < 36; ++k) s -= D0[36 * i + k] * W[WW_X + k];
       W[WS_Gg + i] = s;
+    }
+    g.sync();
+    {
+      // D0 Z from [row][18] to [column][56] in place (the iteration reads it by column): every element is held in a register
+      // across the barrier
+#if defined(__CUDA_ARCH__)
+      double v[16];                              // covers groups of 64 threads and more
+      QM_UNROLL
+      for (int q = 0; q < 16; ++q) { const int idx = g.tid() + q * g.nt(); v[q] = (idx < 56 * 18) ? W[WS_GG + idx] : 0.0; }
+      g.sync();
+      QM_UNROLL
+      for (int q = 0; q < 16; ++q) {
+        const int idx = g.tid() + q * g.nt();
+        if (idx < 56 * 18) { const int i = idx / 18, c = idx - 18 * i; W[WS_GG + 56 * c + i] = v[q]; }
+      }
+#else
+      double v[56 * 18];
+      for (int idx = 0; idx < 56 * 18; ++idx) v[idx] = W[WS_GG + idx];
+      for (int idx = 0; idx < 56 * 18; ++idx) W[WS_GG + 56 * (idx % 18) + idx / 18] = v[idx];
+#endif
     }
     g.sync(); QM_TICK(39);
     wbc_gi_prepare(g, n, r, W, WI);
