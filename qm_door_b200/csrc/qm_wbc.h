@@ -617,9 +617,11 @@ QM_HDO void householder_ls_narrow(G w0, double* A, int m, int n, int ld, double*
     for (int jj = 1; jj < cols; ++jj) update(jj, dot[jj]);
 #endif
     w0.sync();
-    QM_PFOR(w0, i, rows) colk[i * ld] = (i == 0) ? alpha : 0.0;
-    w0.sync();
+    // R[k][k]; the entries below it are never read again (the later steps and the back substitution stay right of column k),
+    // so they are left as they are and the next step starts without another hand-over
+    if (w0.tid() == 0) colk[0] = alpha;
   }
+  w0.sync();
 }
 
 // back substitution R z = c (R n x n upper in A, c = A[:, n], overwritten), column oriented on one narrow group: z_i is formed
