@@ -570,12 +570,15 @@ QM_HD void hh_axpy(double* y, int ldy, const double* x, int ldx, int count, doub
 // matrices of a solve (<= 92 x 37): the triangularisation is what bounded k_wbc_level by instruction issue.
 // hp: 2 doubles of scratch. Same `dense` convention as householder_ls.
 QM_HD double hh_dot(const double* QM_RESTRICT ak, const double* QM_RESTRICT aj, int ld, int count) {
-  double sp = 0.0;
+  // two interleaved partial sums (even / odd rows): half the dependent multiply-add chain
+  double s0 = 0.0, s1 = 0.0;
+  int i = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 4
+#pragma unroll 2
 #endif
-  for (int i = 0; i < count; ++i, ak += ld, aj += ld) sp += *ak * *aj;
-  return sp;
+  for (; i + 2 <= count; i += 2, ak += 2 * ld, aj += 2 * ld) { s0 += ak[0] * aj[0]; s1 += ak[ld] * aj[ld]; }
+  if (i < count) s0 += *ak * *aj;
+  return s0 + s1;
 }
 template <class G>
 QM_HDO void householder_ls_narrow(G w0, double* A, int m, int n, int ld, double* hp, int dense) {
