@@ -627,17 +627,32 @@ QM_HDO void householder_ls_narrow(G w0, double* A, int m, int n, int ld, double*
   w0.sync();
 }
 
-// back substitution R z = c (R n x n upper in A, c = A[:, n], overwritten), column oriented on one narrow group: z_i is formed
-// by one lane, the others remove its contribution from the rows above.
+// back substitution R z = c (R n x n upper in A, n <= 64, c = A[:, n]) on one narrow group, column sweep from the last unknown:
+// a lane keeps the right-hand sides of its rows (lane, lane + 32) in registers, the diagonal enters through its reciprocal
+// (one division per lane instead of one per unknown on the chain), z_i reaches the other lanes by a shuffle.
 template <class G>
-QM_HDO void back_substitute(G w0, double* A, int n, int ld, double* z) {
-  for (int i = n - 1; i >= 0; --i) {
-    if (w0.tid() == 0) { const double d = A[i * ld + i]; z[i] = (d != 0.0) ? A[i * ld + n] / d : 0.0; }
-    w0.sync();
-    const double zi = z[i];
-    QM_PFOR(w0, j, i) A[j * ld + n] -= A[j * ld + i] * zi;
-    w0.sync();
+QM_HDO void back_substitute(G w0, const double* A, int n, int ld, double* z) {
+#if defined(__CUDA_ARCH__)
+  const int j0 = w0.tid(), j1 = j0 + 32;
+  double c0 = (j0 < n) ? A[j0 * ld + n] : 0.0, c1 = (j1 < n) ? A[j1 * ld + n] : 0.0;
+  const double d0 = (j0 < n) ? A[j0 * ld + j0] : 0.0, d1 = (j1 < n) ? A[j1 * ld + j1] : 0.0;
+  const double inv0 = (d0 != 0.0) ? 1.0 / d0 : 0.0, inv1 = (d1 != 0.0) ? 1.0 / d1 : 0.0;
+  for (int i = n - 1; i > 0; --i) {
+    const double zi = (i >= 32) ? __shfl_sync(0xffffffffu, c1 * inv1, i - 32) : __shfl_sync(0xffffffffu, c0 * inv0, i);
+    if (j0 < i) c0 -= A[j0 * ld + i] * zi;
+    if (j1 < i) c1 -= A[j1 * ld + i] * zi;
   }
+  if (j0 < n) z[j0] = c0 * inv0;
+  if (j1 < n) z[j1] = c1 * inv1;
+  w0.sync();
+#else
+  double c[64], inv[64];
+  for (int j = 0; j < n; ++j) { c[j] = A[j * ld + n]; const double d = A[j * ld + j]; inv[j] = (d != 0.0) ? 1.0 / d : 0.0; }
+  for (int i = n - 1; i >= 0; --i) {
+    z[i] = c[i] * inv[i];
+    for (int j = 0; j < i; ++j) c[j] -= A[j * ld + i] * z[i];
+  }
+#endif
 }
 
 // Kernel basis of Abar (r x n, row major ld_a) exactly as the reference obtains it (HoQp.cpp:129: (A Zprev).fullPivLu().kernel(),
