@@ -170,9 +170,10 @@ int64_t qmb200_device_bytes(qmb200_ctx* ctx);
  *                                     x_des[B][30] u_des[B][30] rbd[B][55] mode[B] period[B] time[B] -> cmd[B][54] = [accelerations(24);
  *                                     contact forces(12); joint torques(18)], status[B] (QMB200_WST_* bits)
  *   qmb200_wbc_reset               <- inputLast_ = 0 (WbcBase.cpp:41): the finite-difference joint acceleration state, per solve
- * A batch runs as a sequence of kernels (task builder, level 0, level products / kernel bases, active-set iteration) over a
- * per-solve workspace image the context owns in device memory (72 KB per solve of the batch); QMB200_WBC_SPLIT=0 in the
- * environment at create time selects the single kernel instead (same results bit for bit, 1.9x slower at batch 65 536). */
+ * A batch larger than one wave of the single-kernel solve (4 solves per SM) runs as a sequence of kernels (task builder, level 0,
+ * level products / kernel bases, active-set iteration) over a per-solve workspace image the context owns in device memory
+ * (72 KB per solve of the batch); smaller batches -- a controller solving one configuration per tick -- run the single kernel,
+ * which has the lower latency. Same results bit for bit; QMB200_WBC_SPLIT=0 / 1 in the environment at create time forces one. */
 typedef struct qmb200_wbc_ctx qmb200_wbc_ctx;
 enum { QMB200_WST_OK = 0, QMB200_WST_QP_MAX_ITER = 1, QMB200_WST_DEGENERATE = 2, QMB200_WST_NAN = 4, QMB200_WST_BAD_MODE = 8 };
 

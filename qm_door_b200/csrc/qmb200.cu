@@ -1396,7 +1396,7 @@ struct qmb200_wbc_ctx {
   double* cold = nullptr;                       // [B][WC_SIZE] task rows read once per level (qm_wbc.h), L2-resident per solve
   int* perm = nullptr;                          // [B] solves ordered by contact pattern
   double* state = nullptr; int* istate = nullptr;   // [B][WS_END], [B][WI_SIZE]: workspace image of a solve between the split kernels
-  bool split = true;                            // sequence of kernels (default) or the single kernel k_wbc (QMB200_WBC_SPLIT=0)
+  bool split = true;                            // sequence of kernels (large batches) or the single kernel k_wbc; see qmb200_wbc_create
   int rounds = 2;                               // levels below level 0 of the task stack (one iteration kernel each)
   int32_t *mode = nullptr, *status = nullptr;
   cudaStream_t stream = nullptr;
@@ -1467,8 +1467,14 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
   C_OK(cudaMalloc(&c->cmd, B * 54 * sizeof(double)));
   C_OK(cudaMalloc(&c->cold, B * WC_SIZE * sizeof(double)));
   {
+    // Kernel sequence for batches beyond one wave of the single kernel (four solves per SM), the single kernel below that: a
+    // solve's latency is the same on both paths, the sequence adds seven launches and the round trips of the workspace image
+    // (measured, host buffers: B = 1: 0.31 vs 0.37 ms, B = 256: 0.64 vs 0.81 ms, B = 2048: 2.24 vs 1.68 ms).
+    // QMB200_WBC_SPLIT = 0 / 1 forces one or the other.
     const char* env = getenv("QMB200_WBC_SPLIT");
-    c->split = !(env && atoi(env) == 0);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    c->split = env ? (atoi(env) != 0) : (batch > 4 * sms);
     c->rounds = (wbc->mpc_variant == 2) ? WB_MAXLEV - 1 : 2;
   }
   if (c->split) {
