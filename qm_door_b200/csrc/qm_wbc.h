@@ -747,19 +747,22 @@ struct L0Mem {
   double *V0, *X;                  // [56] slack solution, [36] solution
   double *QR, *res, *hp;           // [92][37] least-squares matrix | rhs, [56] row residuals, [4] scratch
 };
-enum { L0_MEM_DOUBLES = 56 + 56 + 36 + WB_QR_ROWS * WB_QR_LD + 56 + 4 };
+// doubles of a compact block whose matrix holds `rows` rows (18 equality + 36 regularisation rows + the active inequality rows)
+QM_HD constexpr int l0_mem_doubles(int rows) { return 56 + 56 + 36 + rows * WB_QR_LD + 56 + 4; }
+enum { L0_MEM_DOUBLES = 56 + 56 + 36 + WB_QR_ROWS * WB_QR_LD + 56 + 4, L0_FIXED_ROWS = 18 + 36 };
 QM_HD L0Mem l0_mem_of(double* W) {
   L0Mem m;
   m.F0 = W + WW_F0; m.V0 = W + WW_V0; m.X = W + WW_X; m.QR = W + WS_QR; m.res = W + WS_RES; m.hp = W + WS_HP;
   return m;
 }
-QM_HD L0Mem l0_mem_compact(double* D) {          // L0_MEM_DOUBLES doubles; F0 is filled by the caller
+QM_HD L0Mem l0_mem_compact(double* D, int rows = WB_QR_ROWS) {   // l0_mem_doubles(rows) doubles; F0 is filled by the caller
   L0Mem m;
-  m.F0 = D; m.V0 = D + 56; m.X = m.V0 + 56; m.QR = m.X + 36; m.res = m.QR + WB_QR_ROWS * WB_QR_LD; m.hp = m.res + 56;
+  m.F0 = D; m.V0 = D + 56; m.X = m.V0 + 56; m.QR = m.X + 36; m.res = m.QR + rows * WB_QR_LD; m.hp = m.res + 56;
   return m;
 }
+// max_nw: active inequality rows the matrix of `lm` has room for; false (nothing usable written) if a pass needs more.
 template <class G>
-QM_HDN void wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc, int* WI) {
+QM_HDN bool wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc, int* WI, int max_nw = WB_MAXW) {
   const double* F0 = lm.F0;
   double* X = lm.X;
   double* RES = lm.res;
@@ -777,6 +780,7 @@ QM_HDN void wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc,
     }
     g.sync();
     const int nw = WI[WI_SC + 0];
+    if (nw > max_nw) return false;
     const int m = nw + 18 + 36;
     // rows: active inequality rows, equality rows, sqrt(eps) I (large rows first: stable for the tiny regularisation)
     QM_PFOR(g, idx, m * ld) {
@@ -816,6 +820,7 @@ QM_HDN void wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc,
   }
   QM_PFOR(g, i, 56) lm.V0[i] = (i < nD0 && RES[i] > 0.0) ? RES[i] : 0.0;
   g.sync();
+  return true;
 }
 
 // Goldfarb-Idnani iteration on a group (see wbc_gi). State: z (WS_Z), J (WS_J), RF (WS_RF), multipliers u (WS_U),
@@ -1172,7 +1177,7 @@ QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
 // solve and on the host, the solve's image in global memory in the kernel sequence (the largest block, read a few times).
 // Loop state of a solve in WI_SC: [15] level, [16] columns of the current basis, [17] which basis buffer is current (0: WW_Z0,
 // 1: WW_Z1), [18] WSS_* (what the solve waits for).
-enum { WSS_NONE = 0, WSS_ITERATION = 1, WSS_DONE = 2 };
+enum { WSS_NONE = 0, WSS_ITERATION = 1, WSS_DONE = 2, WSS_LEVEL0_WIDE = 3 };   // WIDE: level 0 needs the full-size matrix
 template <class G>
 QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr,
                             bool level0_done = false) {

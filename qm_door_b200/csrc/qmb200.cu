@@ -1269,28 +1269,37 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb20
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
 
-// Level 0 (Newton iteration on the least-squares form, one Householder triangularisation per pass) with one warp per solve and
-// 30 KB per solve: seven solves per SM. D0 and the level-0 equality rows are read in place (global memory).
-constexpr int kL0Doubles = ((L0_MEM_DOUBLES + 1) / 2) * 2;
-constexpr size_t kWbcL0SmemBytes = (size_t)kL0Doubles * sizeof(double) + WI_SIZE * sizeof(int);
-__global__ void __launch_bounds__(32) k_wbc_level0(int B, const double* cold, double* state, int* istate, const int* perm) {
+// Level 0 (Newton iteration on the least-squares form, one Householder triangularisation per pass) with one warp per solve. D0 and
+// the level-0 equality rows are read in place (global memory). The matrix has 54 fixed rows plus the ACTIVE inequality rows: a
+// first launch gives every solve room for kL0NarrowActive of them (22 KB per solve, ten solves per SM; the config-5 batch never
+// has more than four active), a second launch with the full-size matrix (30 KB, seven per SM) redoes the solves that needed more
+// -- every other CTA of it leaves at once.
+constexpr int kL0NarrowActive = 10;                 // (QMB200_WBC_L0_ACTIVE overrides it: tests force the second launch with 0 or 1)
+static size_t wbc_l0_smem(int active_cap) {
+  return (size_t)(((l0_mem_doubles(L0_FIXED_ROWS + active_cap) + 1) / 2) * 2) * sizeof(double) + WI_SIZE * sizeof(int);
+}
+__global__ void __launch_bounds__(32) k_wbc_level0(int B, int wide, int active_cap, const double* cold, double* state, int* istate,
+                                                   const int* perm) {
   if ((int)blockIdx.x >= B) return;
   const int b = perm[blockIdx.x], lane = threadIdx.x;
-  extern __shared__ double smem[];
-  int* WI = (int*)(smem + kL0Doubles);
   int* SI = istate + (size_t)WI_SIZE * b;
+  if (wide && SI[WI_SC + 18] != WSS_LEVEL0_WIDE) return;
+  extern __shared__ double smem[];
+  const int doubles = ((l0_mem_doubles(L0_FIXED_ROWS + active_cap) + 1) / 2) * 2;
+  int* WI = (int*)(smem + doubles);
   double* S = state + (size_t)WS_END * b;
-  const L0Mem lm = l0_mem_compact(smem);
+  const L0Mem lm = l0_mem_compact(smem, L0_FIXED_ROWS + active_cap);
   for (int i = lane; i < 56; i += 32) smem[i] = S[WW_F0 + i];
   for (int i = lane; i < WI_SIZE; i += 32) WI[i] = SI[i];
   __syncwarp();
   if (lane == 0) WI[WI_SC + 6] = 0;
   __syncwarp();
   QM_TICK(-1);
-  wbc_level0(WarpGroup(), lm, S + WW_D0, cold + (size_t)WC_SIZE * b, WI);
+  const bool done = wbc_level0(WarpGroup(), lm, S + WW_D0, cold + (size_t)WC_SIZE * b, WI, active_cap);
+  if (!done) { if (lane == 0) SI[WI_SC + 18] = WSS_LEVEL0_WIDE; return; }
   for (int i = lane; i < 56; i += 32) S[WW_V0 + i] = lm.V0[i];
   for (int i = lane; i < 36; i += 32) S[WW_X + i] = lm.X[i];
-  if (lane == 0) SI[WI_SC + 6] = WI[WI_SC + 6];
+  if (lane == 0) { SI[WI_SC + 6] = WI[WI_SC + 6]; SI[WI_SC + 18] = WSS_NONE; }
 }
 
 __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
@@ -1398,6 +1407,7 @@ struct qmb200_wbc_ctx {
   double* state = nullptr; int* istate = nullptr;   // [B][WS_END], [B][WI_SIZE]: workspace image of a solve between the split kernels
   bool split = true;                            // sequence of kernels (large batches) or the single kernel k_wbc; see qmb200_wbc_create
   int rounds = 2;                               // levels below level 0 of the task stack (one iteration kernel each)
+  int l0_active = 10;                           // active inequality rows the first level-0 launch has room for
   int32_t *mode = nullptr, *status = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1422,7 +1432,8 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
     k_wbc_order<<<1, 1024, 0, c->stream>>>(c->B, mode, c->perm);
     k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
                                                                     c->state, c->istate, c->perm);
-    k_wbc_level0<<<c->B, 32, kWbcL0SmemBytes, c->stream>>>(c->B, c->cold, c->state, c->istate, c->perm);
+    k_wbc_level0<<<c->B, 32, wbc_l0_smem(c->l0_active), c->stream>>>(c->B, 0, c->l0_active, c->cold, c->state, c->istate, c->perm);
+    k_wbc_level0<<<c->B, 32, wbc_l0_smem(WB_MAXW), c->stream>>>(c->B, 1, WB_MAXW, c->cold, c->state, c->istate, c->perm);
     k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status, c->perm);
     for (int r = 0; r < c->rounds; ++r) {
       k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate, c->perm);
@@ -1484,7 +1495,11 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
     C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcLevelSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcGiSmemBytes));
-    C_OK(cudaFuncSetAttribute(k_wbc_level0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcL0SmemBytes));
+    C_OK(cudaFuncSetAttribute(k_wbc_level0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbc_l0_smem(WB_MAXW)));
+    const char* l0env = getenv("QMB200_WBC_L0_ACTIVE");
+    c->l0_active = l0env ? atoi(l0env) : kL0NarrowActive;
+    if (c->l0_active < 0) c->l0_active = 0;
+    if (c->l0_active > WB_MAXW) c->l0_active = WB_MAXW;
   }
   C_OK(cudaMalloc(&c->mode, B * sizeof(int32_t)));
   C_OK(cudaMalloc(&c->status, B * sizeof(int32_t)));

@@ -160,6 +160,15 @@ def test_cuda_kernel_sequence_equals_single_kernel(descs, variant, monkeypatch):
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     assert np.isfinite(out[0][0]).all()
+    # level 0 of the sequence runs in a matrix with room for ten active inequality rows and repeats a solve that needs more in the
+    # full-size one: with room for one, most solves of this batch take the second launch -- same result
+    monkeypatch.setenv("QMB200_WBC_SPLIT", "1")
+    monkeypatch.setenv("QMB200_WBC_L0_ACTIVE", "1")
+    ctx = q.WbcContext(W.model, W.wbc, B)
+    ctx.update(W.x_des, W.u_last, W.rbd, W.mode, W.period, W.time)
+    cmd, st = ctx.update(W.x_des, W.u_des, W.rbd, W.mode, W.period, W.time)
+    ctx.close()
+    assert np.array_equal(cmd, out[0][0]) and np.array_equal(st, out[0][1])
 
 
 @pytest.mark.gpu
