@@ -315,7 +315,7 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
 // nD0 to WI_SC[9]; the level table to WI_LV.
 template <class G>
 QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* ud, int mode, double time,
-                      double* W, double* Wc, int* WI) {
+                      double* W, double* D0, double* Wc, int* WI) {      // D0: [56][36], write only (see wbc_solve_begin)
   const double* ms = W + WA_MEAS;
   const double* ds = W + WA_DES;
   const int nc = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
@@ -324,7 +324,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
   const int nD0 = 36 + 5 * nc + 3 * nsw;
   if (g.tid() == 0) WI[WI_SC + 9] = nD0;
   QM_PFOR(g, idx, 18 * 36) Wc[WC_A0 + idx] = 0.0;
-  QM_PFOR(g, idx, 56 * 36) W[WW_D0 + idx] = 0.0;
+  QM_PFOR(g, idx, 56 * 36) D0[idx] = 0.0;
   QM_PFOR(g, idx, WB_POOL * 36) Wc[WC_AP + idx] = 0.0;
   QM_PFOR(g, idx, 56) { W[WW_F0 + idx] = 0.0; W[WW_V0 + idx] = 0.0; }
   g.sync();
@@ -365,8 +365,8 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
   QM_PFOR(g, idx, 18 * 36) {
     const int l = idx / 36, c = idx % 36;
     const double v = (c < 24) ? W[WA_M + 24 * (6 + l) + c] : -W[WA_JF + (c - 24) * 24 + 6 + l];
-    W[WW_D0 + idx] = v;
-    W[WW_D0 + 18 * 36 + idx] = -v;
+    D0[idx] = v;
+    D0[18 * 36 + idx] = -v;
   }
   QM_PFOR(g, l, 18) {
     W[WW_F0 + l] = C.tau_max[l] - W[WA_NLE + 6 + l];
@@ -377,7 +377,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
     if (j < nc) {
       int ft = 0, cnt = 0;
       for (int f2 = 0; f2 < 4; ++f2) if ((mode >> (3 - f2)) & 1) { if (cnt == j) { ft = f2; break; } ++cnt; }
-      double* row = W + WW_D0 + (36 + 5 * j + k) * 36 + 24 + 3 * ft;
+      double* row = D0 + (36 + 5 * j + k) * 36 + 24 + 3 * ft;
       const double mu = C.friction_mu;
       if (k == 0) { row[2] = -1.0; }
       else if (k == 1) { row[0] = 1.0; row[2] = -mu; }
@@ -1369,7 +1369,7 @@ QM_HDN void wbc_update(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C
   QM_TICK(-1);
   wbc_dynamics(g, M, C, rbd, xd, ud, u_last, period, W);
   QM_TICK(33);
-  wbc_tasks(g, M, C, ud, mode & 15, time, W, Wc, WI);
+  wbc_tasks(g, M, C, ud, mode & 15, time, W, W + WW_D0, Wc, WI);
   QM_TICK(34);
   wbc_solve(g, W, Wc, WI, cmd, status, levels);
   QM_TICK(45);

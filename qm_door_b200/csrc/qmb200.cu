@@ -1245,26 +1245,30 @@ __device__ __forceinline__ void wbc_copy(double* dst, const double* src, int n) 
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-__global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc_tasks(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
+// D0 is written where the later kernels read it (the solve's image in global memory); the workspace from WW_F0 on, which ends
+// with the dynamics scratch at WA_END, is in shared memory: 36 KB per solve, six solves per SM.
+constexpr size_t kWbcTasksSmemBytes = (size_t)(WA_END - WW_F0 + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
+__global__ void __launch_bounds__(QM_WBC_THREADS, 6) k_wbc_tasks(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
                                                     const double* ud, const double* rbd, const int32_t* mode, const double* period,
                                                     const double* time, double* u_last, double* cold, double* state, int* istate,
                                                     const int* perm) {
   if ((int)blockIdx.x >= B) return;
   const int b = perm[blockIdx.x];
   extern __shared__ double smem[];
-  double* W = smem;
-  double* in = smem + WW_SIZE;
-  int* WI = (int*)(smem + WW_SIZE + kWbcInDoubles);
+  double* W = smem - WW_F0;                          // workspace offsets from WW_F0 on are in shared memory
+  double* in = smem + (WA_END - WW_F0);
+  int* WI = (int*)(in + kWbcInDoubles);
+  double* S = state + (size_t)WS_END * b;
   for (int i = threadIdx.x; i < 30; i += blockDim.x) { in[i] = xd[30 * b + i]; in[30 + i] = ud[30 * b + i]; in[116 + i] = u_last[30 * b + i]; }
   for (int i = threadIdx.x; i < 55; i += blockDim.x) in[60 + i] = rbd[55 * b + i];
   __syncthreads();
   QM_TICK(-1);
   wbc_dynamics(BlockGroup(), *M, *C, in + 60, in, in + 30, in + 116, period[b], W);
   QM_TICK(33);
-  wbc_tasks(BlockGroup(), *M, *C, in + 30, mode[b] & 15, time[b], W, cold + (size_t)WC_SIZE * b, WI);
+  wbc_tasks(BlockGroup(), *M, *C, in + 30, mode[b] & 15, time[b], W, S + WW_D0, cold + (size_t)WC_SIZE * b, WI);
   QM_TICK(34);
   __syncthreads();
-  wbc_copy(state + (size_t)WS_END * b, W, kWbcKeepA);
+  wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepA - WW_F0);
   for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) istate[(size_t)WI_SIZE * b + i] = WI[i];
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
@@ -1430,7 +1434,7 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
   CUDA_OK(cudaEventRecord(c->e0, c->stream));
   if (c->split) {
     k_wbc_order<<<1, 1024, 0, c->stream>>>(c->B, mode, c->perm);
-    k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
+    k_wbc_tasks<<<c->B, QM_WBC_THREADS, kWbcTasksSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold,
                                                                     c->state, c->istate, c->perm);
     k_wbc_level0<<<c->B, 32, wbc_l0_smem(c->l0_active), c->stream>>>(c->B, 0, c->l0_active, c->cold, c->state, c->istate, c->perm);
     k_wbc_level0<<<c->B, 32, wbc_l0_smem(WB_MAXW), c->stream>>>(c->B, 1, WB_MAXW, c->cold, c->state, c->istate, c->perm);
@@ -1492,7 +1496,7 @@ int qmb200_wbc_create(const qmb200_model_desc* model, const qmb200_wbc_desc* wbc
     C_OK(cudaMalloc(&c->state, B * WS_END * sizeof(double)));
     C_OK(cudaMalloc(&c->istate, B * WI_SIZE * sizeof(int)));
     C_OK(cudaMalloc(&c->perm, B * sizeof(int)));
-    C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcSmemBytes));
+    C_OK(cudaFuncSetAttribute(k_wbc_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcTasksSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcLevelSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_gi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWbcGiSmemBytes));
     C_OK(cudaFuncSetAttribute(k_wbc_level0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbc_l0_smem(WB_MAXW)));
