@@ -58,9 +58,7 @@ enum {
   // therefore laid over that whole window (three solves per SM instead of two: 74 KB instead of 105 KB of shared memory).
   WS_GA = WW_SCR,                    // [22][18]  A Z of the current level
   WS_GB = WS_GA + 22 * 18,           // [22]
-  WS_GG = WS_GB + 22,                // [18][56]  (D0 Z)' -- column c of row i at 56 c + i, so the lanes that own rows read
-                                     //           consecutive words; after the level's solve: scratch of its kernel basis
-  WS_Gg = WS_GG + 56 * 18,           // [56]
+  WS_Gg = WS_GB + 22,                // [56]
   WS_J = WS_Gg + 56,                 // [18][18]  active-set factor; after the level's solve: its kernel basis N
   WS_RF = WS_J + 324,                // [18][18]
   WS_Z = WS_RF + 324,                // [18]
@@ -68,9 +66,13 @@ enum {
   WS_RR = WS_D + 18,                 // [18]
   WS_ZD = WS_RR + 18,                // [18]
   WS_NP = WS_ZD + 18,                // [18]
-  WS_LS = WS_NP + 18,                // [40][19] least-squares matrix | rhs of a level below level 0
+  WS_KCN = WS_D,                     // [38] column maxima of a kernel basis (d .. np are only live inside the iteration)
+  WS_LS = WS_NP + 18,                // [40][19] least-squares matrix | rhs of a level below level 0; then scratch of its kernel basis
   WW_Z1 = WS_LS + 40 * 19,           // [36][18] the other null-space basis (first written at the end of level 1)
-  WS_OVEND = WW_Z1 + 36 * 18,
+  WS_GG = WW_Z1 + 36 * 18,           // [18][56]  (D0 Z)' -- column c of row i at 56 c + i, so the lanes that own rows read
+                                     //           consecutive words. Last block of the window: the kernel sequence keeps it in the
+                                     //           solve's global-memory image only (k_wbc_level's shared memory ends here)
+  WS_OVEND = WS_GG + 56 * 18,
   WS_QR = WW_SCR,                    // level 0 and its kernel basis only: [92][37] stacked least-squares matrix | rhs
   WS_RES = WS_OVEND,                 // [56] constraint residuals
   WS_VH = WS_RES + 56,               // [92] Householder vector / violation scores
@@ -1173,7 +1175,8 @@ QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
 //   [gi_iterate]
 //   wbc_solve_advance x += Z z, kernel basis of the level, next stacked basis
 //   wbc_solve_finish  torque recovery, cmd[54], status
-// D0 (the inequality rows of level 0, [56][36]) is read through its own pointer: the workspace block WW_D0 in the single-kernel
+// D0 (the inequality rows of level 0, [56][36]) and GG (their products with the current basis, written by wbc_solve_prepare for the
+// iteration) are reached through their own pointers: the workspace block WW_D0 in the single-kernel
 // solve and on the host, the solve's image in global memory in the kernel sequence (the largest block, read a few times).
 // Loop state of a solve in WI_SC: [15] level, [16] columns of the current basis, [17] which basis buffer is current (0: WW_Z0,
 // 1: WW_Z1), [18] WSS_* (what the solve waits for).
@@ -1192,7 +1195,7 @@ QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, 
   // unless the contact Jacobians are degenerate, which is flagged)
   QM_PFOR(g, idx, 36 * 18) W[WW_Z0 + idx] = 0.0;
   g.sync();
-  kernel_basis_lu(g, Wc + WC_A0, 18, 36, 36, W + WS_QR, W + WW_Z0, 18, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+  kernel_basis_lu(g, Wc + WC_A0, 18, 36, 36, W + WS_QR, W + WW_Z0, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
   int n1 = 36 - WI[WI_SC + 1];
   if (n1 > 18) { n1 = 18; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
   QM_TICK(38);
@@ -1213,7 +1216,7 @@ QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, 
 //      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
 //      full stance -- changes nothing)
 template <class G>
-QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr) {
+QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, double* GG, const double* Wc, int* WI, double* levels = nullptr) {
   const int nD0 = WI[WI_SC + 9];
   const int nlev = WI[WI_LV];
   const int n = WI[WI_SC + 16];
@@ -1237,7 +1240,7 @@ QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, const double* Wc
     const double* bpv = Wc + WC_BP + off;
     // A Z and D0 Z as tile products (FP64 tensor-core tiles on the device); columns >= n are never read
     mm<3, false>(g, r, n, 36, Ap, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GA, 18);
-    mm<3, false>(g, nD0, n, 36, D0, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GG, 18);
+    mm<3, false>(g, nD0, n, 36, D0, 36, Zc, 18, (const double*)nullptr, 0, 1.0, GG, 18);
     QM_PFOR(g, i, r) {
       double s = bpv[i];
       for (int k = 0; k < 36; ++k) s -= Ap[36 * i + k] * W[WW_X + k];
@@ -1255,17 +1258,17 @@ QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, const double* Wc
 #if defined(__CUDA_ARCH__)
       double v[16];                              // covers groups of 64 threads and more
       QM_UNROLL
-      for (int q = 0; q < 16; ++q) { const int idx = g.tid() + q * g.nt(); v[q] = (idx < 56 * 18) ? W[WS_GG + idx] : 0.0; }
+      for (int q = 0; q < 16; ++q) { const int idx = g.tid() + q * g.nt(); v[q] = (idx < 56 * 18) ? GG[idx] : 0.0; }
       g.sync();
       QM_UNROLL
       for (int q = 0; q < 16; ++q) {
         const int idx = g.tid() + q * g.nt();
-        if (idx < 56 * 18) { const int i = idx / 18, c = idx - 18 * i; W[WS_GG + 56 * c + i] = v[q]; }
+        if (idx < 56 * 18) { const int i = idx / 18, c = idx - 18 * i; GG[56 * c + i] = v[q]; }
       }
 #else
       double v[56 * 18];
-      for (int idx = 0; idx < 56 * 18; ++idx) v[idx] = W[WS_GG + idx];
-      for (int idx = 0; idx < 56 * 18; ++idx) W[WS_GG + 56 * (idx % 18) + idx / 18] = v[idx];
+      for (int idx = 0; idx < 56 * 18; ++idx) v[idx] = GG[idx];
+      for (int idx = 0; idx < 56 * 18; ++idx) GG[56 * (idx % 18) + idx / 18] = v[idx];
 #endif
     }
     g.sync(); QM_TICK(39);
@@ -1297,7 +1300,7 @@ QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double*
   g.sync();
   if (p + 1 < nlev) {
     // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
-    kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_GG, W + WS_J, 18, 18, W + WS_CN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+    kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_LS, W + WS_J, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
     const int nn = n - WI[WI_SC + 1];
     QM_PFOR(g, idx, 36 * 18) {
       const int i = idx / 18, c = idx % 18;
@@ -1350,7 +1353,7 @@ template <class G>
 QM_HDN void wbc_solve(G g, double* W, const double* Wc, int* WI, double* cmd, int* status, double* levels = nullptr) {
   const double* D0 = W + WW_D0;
   wbc_solve_begin(g, W, D0, Wc, WI, levels);
-  while (wbc_solve_prepare(g, W, D0, Wc, WI, levels)) {
+  while (wbc_solve_prepare(g, W, D0, W + WS_GG, Wc, WI, levels)) {
     if (g.narrow_active()) gi_iterate(g.narrow(), WI[WI_SC + 16], WI[WI_SC + 9], gi_mem_of(W, WI));
     g.sync(); QM_TICK(41);
     wbc_solve_advance(g, W, Wc, WI, levels);

@@ -1221,8 +1221,9 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
 // iteration) -- a few GB per 65 536 solves, a few percent of the time it buys.
 constexpr int kWbcKeepA = WW_X;                       // after the tasks: D0, F0, (V0), h_j
 constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, D0 Z, Gg, J, (RF), z
-// k_wbc_level keeps D0 where k_wbc_tasks left it (global memory) and holds the workspace from WW_F0 on: 40 KB, five solves per SM
-constexpr size_t kWbcLevelSmemBytes = (size_t)(WW_SIZE - WW_F0) * sizeof(double) + WI_SIZE * sizeof(int);
+// k_wbc_level keeps D0 where k_wbc_tasks left it and writes D0 Z where k_wbc_gi reads it (global memory); it holds the workspace
+// from WW_F0 up to that last block of the window: 28 KB of shared memory
+constexpr size_t kWbcLevelSmemBytes = (size_t)(WS_GG - WW_F0) * sizeof(double) + WI_SIZE * sizeof(int);
 constexpr int kGiWarpDoubles = ((GI_MEM_DOUBLES + 1) / 2) * 2;
 constexpr int kGiWarpInts = ((GI_MEM_INTS + 3) / 4) * 4;
 constexpr size_t kWbcGiSmemBytes = 4 * ((size_t)kGiWarpDoubles * sizeof(double) + (size_t)kGiWarpInts * sizeof(int));
@@ -1306,7 +1307,10 @@ __global__ void __launch_bounds__(32) k_wbc_level0(int B, int wide, int active_c
   if (lane == 0) { SI[WI_SC + 6] = WI[WI_SC + 6]; SI[WI_SC + 18] = WSS_NONE; }
 }
 
-__global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
+#ifndef QM_WBC_LEVEL_CTAS
+#define QM_WBC_LEVEL_CTAS 7   // measured: 5 / 6 / 7 solves per SM = 25.7 / 24.4 / 23.2 ms per 65 536 solves (96 / 80 / 72 registers)
+#endif
+__global__ void __launch_bounds__(QM_WBC_THREADS, QM_WBC_LEVEL_CTAS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
                                                     int32_t* status, const int* perm) {
   if ((int)blockIdx.x >= B) return;
   const int b = perm[blockIdx.x];
@@ -1314,9 +1318,10 @@ __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int firs
   if (!first && SI[WI_SC + 18] != WSS_ITERATION) return;          // finished in an earlier round
   extern __shared__ double smem[];
   double* W = smem - WW_F0;                          // workspace offsets from WW_F0 on are in shared memory; WW_D0 is never used
-  int* WI = (int*)(smem + (WW_SIZE - WW_F0));
+  int* WI = (int*)(smem + (WS_GG - WW_F0));
   double* S = state + (size_t)WS_END * b;
   const double* D0 = S + WW_D0;
+  double* GG = S + WS_GG;
   const double* Wc = cold + (size_t)WC_SIZE * b;
   wbc_copy(W + WW_F0, S + WW_F0, (first ? WW_Z0 : kWbcKeepB) - WW_F0);      // first: F0, V0, h_j, x (level 0 is done)
   if (!first && SI[WI_SC + 17]) wbc_copy(W + WW_Z1, S + WW_Z1, 36 * 18);
@@ -1325,7 +1330,7 @@ __global__ void __launch_bounds__(QM_WBC_THREADS, 5) k_wbc_level(int B, int firs
   const BlockGroup g;
   if (first) wbc_solve_begin(g, W, D0, Wc, WI, nullptr, true);
   else wbc_solve_advance(g, W, Wc, WI);
-  if (wbc_solve_prepare(g, W, D0, Wc, WI)) {
+  if (wbc_solve_prepare(g, W, D0, GG, Wc, WI)) {
     wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepB - WW_F0);
     if (WI[WI_SC + 17]) wbc_copy(S + WW_Z1, W + WW_Z1, 36 * 18);
     for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) SI[i] = WI[i];
