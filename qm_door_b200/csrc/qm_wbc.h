@@ -919,7 +919,8 @@ QM_HD void gi_backsub(G w0, const double* RF, const double* d, int q, double* rr
 // (no lane-0 sections on the chain except the bookkeeping stores).
 // Storage of the iteration: the solve's workspace (gi_mem_of) or the compact per-warp block of the stand-alone kernel (k_wbc_gi).
 struct GiMem {
-  double *GG, *Gg;                 // [18][56] inequality rows by column, [56] right-hand sides (read only)
+  const double* GG;                // [18][56] inequality rows by column (read only; may live in global memory)
+  double* Gg;                      // [56] right-hand sides (read only)
   double *J, *RF;                  // [18][18] each
   double *z, *d, *rr, *zd, *np;    // [18] each
   double *res, *viol, *scl;        // [56] each: constraint values, scaled violations, row scales 1 / (1 + |Gg_i|)
@@ -927,7 +928,7 @@ struct GiMem {
   int *act, *ina, *ign;            // [36] active list, [56] row is active, [56] row is ignored (dependent and marginally violated)
   int *status;                     // WST_* flags of the solve (or-ed into)
 };
-enum { GI_MEM_DOUBLES = 18 * 56 + 56 + 2 * 324 + 5 * 20 + 3 * 56 + 60 + 40, GI_MEM_INTS = 36 + 56 + 56 + 4 };
+enum { GI_MEM_DOUBLES = 56 + 2 * 324 + 5 * 20 + 3 * 56 + 60 + 40, GI_MEM_INTS = 36 + 56 + 56 + 4 };   // compact block, GG elsewhere
 QM_HD GiMem gi_mem_of(double* W, int* WI) {
   GiMem m;
   m.GG = W + WS_GG; m.Gg = W + WS_Gg; m.J = W + WS_J; m.RF = W + WS_RF;
@@ -938,9 +939,9 @@ QM_HD GiMem gi_mem_of(double* W, int* WI) {
   m.ign = WI + WI_IGN; m.status = WI + WI_SC + 6;
   return m;
 }
-QM_HD GiMem gi_mem_compact(double* D, int* I) {   // GI_MEM_DOUBLES doubles, GI_MEM_INTS ints
+QM_HD GiMem gi_mem_compact(double* D, int* I, const double* GG) {   // GI_MEM_DOUBLES doubles, GI_MEM_INTS ints
   GiMem m;
-  m.GG = D; m.Gg = m.GG + 18 * 56; m.J = m.Gg + 56; m.RF = m.J + 324;
+  m.GG = GG; m.Gg = D; m.J = m.Gg + 56; m.RF = m.J + 324;
   m.z = m.RF + 324; m.d = m.z + 20; m.rr = m.d + 20; m.zd = m.rr + 20; m.np = m.zd + 20;
   m.res = m.np + 20; m.viol = m.res + 56; m.scl = m.viol + 56; m.u = m.scl + 56; m.sc = m.u + 60;
   m.act = I; m.ina = I + 36; m.ign = m.ina + 56; m.status = m.ign + 56;
