@@ -60,8 +60,7 @@ enum {
   WS_GB = WS_GA + 22 * 18,           // [22]
   WS_Gg = WS_GB + 22,                // [56]
   WS_J = WS_Gg + 56,                 // [18][18]  active-set factor; after the level's solve: its kernel basis N
-  WS_RF = WS_J + 324,                // [18][18]
-  WS_Z = WS_RF + 324,                // [18]
+  WS_Z = WS_J + 324,                 // [18]
   WS_D = WS_Z + 18,                  // [18]
   WS_RR = WS_D + 18,                 // [18]
   WS_ZD = WS_RR + 18,                // [18]
@@ -69,9 +68,11 @@ enum {
   WS_KCN = WS_D,                     // [38] column maxima of a kernel basis (d .. np are only live inside the iteration)
   WS_LS = WS_NP + 18,                // [40][19] least-squares matrix | rhs of a level below level 0; then scratch of its kernel basis
   WW_Z1 = WS_LS + 40 * 19,           // [36][18] the other null-space basis (first written at the end of level 1)
-  WS_GG = WW_Z1 + 36 * 18,           // [18][56]  (D0 Z)' -- column c of row i at 56 c + i, so the lanes that own rows read
+  WS_RF = WW_Z1 + 36 * 18,           // [18][18]  triangular factor of the active set: only the iteration uses it, so the kernel
+                                     //           sequence keeps it out of k_wbc_level's shared memory (which ends here)
+  WS_GG = WS_RF + 324,               // [18][56]  (D0 Z)' -- column c of row i at 56 c + i, so the lanes that own rows read
                                      //           consecutive words. Last block of the window: the kernel sequence keeps it in the
-                                     //           solve's global-memory image only (k_wbc_level's shared memory ends here)
+                                     //           solve's global-memory image only
   WS_OVEND = WS_GG + 56 * 18,
   WS_QR = WW_SCR,                    // level 0 and its kernel basis only: [92][37] stacked least-squares matrix | rhs
   WS_RES = WS_OVEND,                 // [56] constraint residuals

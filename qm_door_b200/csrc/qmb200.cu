@@ -1220,10 +1220,10 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
 // The state of a solve between kernels is its workspace image in global memory (ranges below; 45 KB written, 11 KB read by the
 // iteration) -- a few GB per 65 536 solves, a few percent of the time it buys.
 constexpr int kWbcKeepA = WW_X;                       // after the tasks: D0, F0, (V0), h_j
-constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, D0 Z, Gg, J, (RF), z
+constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, Gg, J, z
 // k_wbc_level keeps D0 where k_wbc_tasks left it and writes D0 Z where k_wbc_gi reads it (global memory); it holds the workspace
-// from WW_F0 up to that last block of the window: 28 KB of shared memory
-constexpr size_t kWbcLevelSmemBytes = (size_t)(WS_GG - WW_F0) * sizeof(double) + WI_SIZE * sizeof(int);
+// from WW_F0 up to the last two blocks of the window (the iteration's triangular factor, D0 Z): 26 KB of shared memory
+constexpr size_t kWbcLevelSmemBytes = (size_t)(WS_RF - WW_F0) * sizeof(double) + WI_SIZE * sizeof(int);
 constexpr int kGiWarpDoubles = ((GI_MEM_DOUBLES + 1) / 2) * 2;
 constexpr int kGiWarpInts = ((GI_MEM_INTS + 3) / 4) * 4;
 constexpr size_t kWbcGiSmemBytes = 4 * ((size_t)kGiWarpDoubles * sizeof(double) + (size_t)kGiWarpInts * sizeof(int));
@@ -1308,7 +1308,8 @@ __global__ void __launch_bounds__(32) k_wbc_level0(int B, int wide, int active_c
 }
 
 #ifndef QM_WBC_LEVEL_CTAS
-#define QM_WBC_LEVEL_CTAS 7   // measured: 5 / 6 / 7 solves per SM = 25.7 / 24.4 / 23.2 ms per 65 536 solves (96 / 80 / 72 registers)
+#define QM_WBC_LEVEL_CTAS 8   // measured per 65 536 solves: 5 / 6 / 7 solves per SM = 25.7 / 24.4 / 23.2 ms with D0 Z out of shared memory,
+                              // 7 / 8 = 22.0 / 21.1 ms with the triangular factor out as well (72 / 64 registers)
 #endif
 __global__ void __launch_bounds__(QM_WBC_THREADS, QM_WBC_LEVEL_CTAS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
                                                     int32_t* status, const int* perm) {
@@ -1318,7 +1319,7 @@ __global__ void __launch_bounds__(QM_WBC_THREADS, QM_WBC_LEVEL_CTAS) k_wbc_level
   if (!first && SI[WI_SC + 18] != WSS_ITERATION) return;          // finished in an earlier round
   extern __shared__ double smem[];
   double* W = smem - WW_F0;                          // workspace offsets from WW_F0 on are in shared memory; WW_D0 is never used
-  int* WI = (int*)(smem + (WS_GG - WW_F0));
+  int* WI = (int*)(smem + (WS_RF - WW_F0));
   double* S = state + (size_t)WS_END * b;
   const double* D0 = S + WW_D0;
   double* GG = S + WS_GG;
