@@ -318,7 +318,9 @@ QM_HDN void wbc_dynamics(G g, const qmb200_model_desc& M, const qmb200_wbc_desc&
 // nD0 to WI_SC[9]; the level table to WI_LV.
 template <class G>
 QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C, const double* ud, int mode, double time,
-                      double* W, double* D0, double* Wc, int* WI) {      // D0: [56][36], write only (see wbc_solve_begin)
+                      double* W, double* P, double* D0, double* Wc, int* WI) {
+  // W: dynamics scratch (WA_*); P: base of the blocks WW_F0, WW_V0, WW_HJ and D0: [56][36] -- all three write only here (the
+  // single-kernel solve passes its workspace for them, the kernel sequence the solve's image in global memory)
   const double* ms = W + WA_MEAS;
   const double* ds = W + WA_DES;
   const int nc = ((mode >> 3) & 1) + ((mode >> 2) & 1) + ((mode >> 1) & 1) + (mode & 1);
@@ -329,7 +331,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
   QM_PFOR(g, idx, 18 * 36) Wc[WC_A0 + idx] = 0.0;
   QM_PFOR(g, idx, 56 * 36) D0[idx] = 0.0;
   QM_PFOR(g, idx, WB_POOL * 36) Wc[WC_AP + idx] = 0.0;
-  QM_PFOR(g, idx, 56) { W[WW_F0 + idx] = 0.0; W[WW_V0 + idx] = 0.0; }
+  QM_PFOR(g, idx, 56) { P[WW_F0 + idx] = 0.0; P[WW_V0 + idx] = 0.0; }
   g.sync();
   // level 0, equality rows: floating-base EoM (6), no contact motion (3 nc), zero swing force (3 nsw)
   QM_PFOR(g, idx, 18 * 36) {
@@ -362,7 +364,7 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
       v = -W[WA_DJV + 3 * ft + d];
     }
     Wc[WC_B0 + r] = v;
-    W[WW_HJ + r] = W[WA_NLE + 6 + r];
+    P[WW_HJ + r] = W[WA_NLE + 6 + r];
   }
   // level 0, inequality rows: torque limits (36), friction pyramid (5 nc), 3 nsw all-zero rows (WbcBase.cpp:458)
   QM_PFOR(g, idx, 18 * 36) {
@@ -372,8 +374,8 @@ QM_HDN void wbc_tasks(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C,
     D0[18 * 36 + idx] = -v;
   }
   QM_PFOR(g, l, 18) {
-    W[WW_F0 + l] = C.tau_max[l] - W[WA_NLE + 6 + l];
-    W[WW_F0 + 18 + l] = C.tau_max[l] + W[WA_NLE + 6 + l];
+    P[WW_F0 + l] = C.tau_max[l] - W[WA_NLE + 6 + l];
+    P[WW_F0 + 18 + l] = C.tau_max[l] + W[WA_NLE + 6 + l];
   }
   QM_PFOR(g, idx, 5 * 4) {
     const int j = idx / 5, k = idx % 5;
@@ -1374,7 +1376,7 @@ QM_HDN void wbc_update(G g, const qmb200_model_desc& M, const qmb200_wbc_desc& C
   QM_TICK(-1);
   wbc_dynamics(g, M, C, rbd, xd, ud, u_last, period, W);
   QM_TICK(33);
-  wbc_tasks(g, M, C, ud, mode & 15, time, W, W + WW_D0, Wc, WI);
+  wbc_tasks(g, M, C, ud, mode & 15, time, W, W, W + WW_D0, Wc, WI);
   QM_TICK(34);
   wbc_solve(g, W, Wc, WI, cmd, status, levels);
   QM_TICK(45);

@@ -1219,7 +1219,6 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
 //   k_wbc_gi     Goldfarb-Idnani iteration of the pending level, four solves per CTA
 // The state of a solve between kernels is its workspace image in global memory (ranges below; 45 KB written, 11 KB read by the
 // iteration) -- a few GB per 65 536 solves, a few percent of the time it buys.
-constexpr int kWbcKeepA = WW_X;                       // after the tasks: D0, F0, (V0), h_j
 constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, Gg, J, z
 // k_wbc_level keeps D0 where k_wbc_tasks left it and writes D0 Z where k_wbc_gi reads it (global memory); it holds the workspace
 // from WW_F0 up to the last two blocks of the window (the iteration's triangular factor, D0 Z): 26 KB of shared memory
@@ -1246,18 +1245,21 @@ __device__ __forceinline__ void wbc_copy(double* dst, const double* src, int n) 
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-// D0 is written where the later kernels read it (the solve's image in global memory); the workspace from WW_F0 on, which ends
-// with the dynamics scratch at WA_END, is in shared memory: 36 KB per solve, six solves per SM.
-constexpr size_t kWbcTasksSmemBytes = (size_t)(WA_END - WW_F0 + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
-__global__ void __launch_bounds__(QM_WBC_THREADS, 6) k_wbc_tasks(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
+// D0, F0 and h_j are written where the later kernels read them (the solve's image in global memory); only the dynamics scratch
+// (WW_SCR .. WA_END) is in shared memory: 29 KB per solve, seven solves per SM.
+constexpr size_t kWbcTasksSmemBytes = (size_t)(WA_END - WW_SCR + kWbcInDoubles) * sizeof(double) + WI_SIZE * sizeof(int);
+#ifndef QM_WBC_TASKS_CTAS
+#define QM_WBC_TASKS_CTAS 7    // measured: 6 / 7 solves per SM = 21.1 / 20.8 ms per 65 536 solves (80 / 72 registers)
+#endif
+__global__ void __launch_bounds__(QM_WBC_THREADS, QM_WBC_TASKS_CTAS) k_wbc_tasks(int B, const qmb200_model_desc* M, const qmb200_wbc_desc* C, const double* xd,
                                                     const double* ud, const double* rbd, const int32_t* mode, const double* period,
                                                     const double* time, double* u_last, double* cold, double* state, int* istate,
                                                     const int* perm) {
   if ((int)blockIdx.x >= B) return;
   const int b = perm[blockIdx.x];
   extern __shared__ double smem[];
-  double* W = smem - WW_F0;                          // workspace offsets from WW_F0 on are in shared memory
-  double* in = smem + (WA_END - WW_F0);
+  double* W = smem - WW_SCR;                         // only the scratch offsets (WA_*) are in shared memory
+  double* in = smem + (WA_END - WW_SCR);
   int* WI = (int*)(in + kWbcInDoubles);
   double* S = state + (size_t)WS_END * b;
   for (int i = threadIdx.x; i < 30; i += blockDim.x) { in[i] = xd[30 * b + i]; in[30 + i] = ud[30 * b + i]; in[116 + i] = u_last[30 * b + i]; }
@@ -1266,10 +1268,9 @@ __global__ void __launch_bounds__(QM_WBC_THREADS, 6) k_wbc_tasks(int B, const qm
   QM_TICK(-1);
   wbc_dynamics(BlockGroup(), *M, *C, in + 60, in, in + 30, in + 116, period[b], W);
   QM_TICK(33);
-  wbc_tasks(BlockGroup(), *M, *C, in + 30, mode[b] & 15, time[b], W, S + WW_D0, cold + (size_t)WC_SIZE * b, WI);
+  wbc_tasks(BlockGroup(), *M, *C, in + 30, mode[b] & 15, time[b], W, S, S + WW_D0, cold + (size_t)WC_SIZE * b, WI);
   QM_TICK(34);
   __syncthreads();
-  wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepA - WW_F0);
   for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) istate[(size_t)WI_SIZE * b + i] = WI[i];
   for (int i = threadIdx.x; i < 30; i += blockDim.x) u_last[30 * b + i] = in[30 + i];   // inputLast_ = inputDesired
 }
