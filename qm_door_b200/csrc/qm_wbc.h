@@ -660,6 +660,67 @@ QM_HDO void back_substitute(G w0, const double* A, int n, int ld, double* z) {
 #endif
 }
 
+// ---- cross-lane helpers of the pivot search and of the active-set iteration (one warp on the device, one thread on the host). The sums run in the same
+// butterfly order on both sides, so host and device agree on them bit for bit.
+template <class G, class F>
+QM_HD double gi_sum(G w0, int n, F f) {                       // sum of f(i), i < n <= 32; every lane gets the result
+#if defined(__CUDA_ARCH__)
+  const int lane = w0.tid();
+  double v = (lane < n) ? f(lane) : 0.0;
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+#else
+  double v[32], t[32];
+  for (int i = 0; i < 32; ++i) v[i] = (i < n) ? f(i) : 0.0;
+  for (int s = 16; s > 0; s >>= 1) {
+    for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ s];
+    for (int i = 0; i < 32; ++i) v[i] = t[i];
+  }
+  return v[0];
+#endif
+}
+// index of the smallest f(i) below `bound` over i < n (the lowest index on ties), -1 if there is none; *vmin: that value or bound
+template <class G, class F>
+QM_HD int gi_argmin(G w0, int n, double bound, F f, double* vmin) {
+  double best = bound;
+  int bi = -1;
+#if defined(__CUDA_ARCH__)
+  for (int i = w0.tid(); i < n; i += 32) { const double v = f(i); if (v < best) { best = v; bi = i; } }
+  for (int s = 16; s > 0; s >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
+  }
+#else
+  for (int i = 0; i < n; ++i) { const double v = f(i); if (v < best) { best = v; bi = i; } }
+#endif
+  *vmin = best;
+  return bi;
+}
+// gi_argmin over i < nmin (<= 32) and two gi_sums over i < nsum in one pass (the three butterflies interleave on the device)
+template <class G, class FV, class F1, class F2>
+QM_HD int gi_argmin_sum2(G w0, int nmin, double bound, FV fv, double* vmin, int nsum, F1 f1, F2 f2, double* s1, double* s2) {
+#if defined(__CUDA_ARCH__)
+  const int lane = w0.tid();
+  double best = bound, a = 0.0, b = 0.0;
+  int bi = -1;
+  if (lane < nmin) { const double v = fv(lane); if (v < best) { best = v; bi = lane; } }
+  if (lane < nsum) { a = f1(lane); b = f2(lane); }
+  for (int s = 16; s > 0; s >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+    a += __shfl_xor_sync(0xffffffffu, a, s);
+    b += __shfl_xor_sync(0xffffffffu, b, s);
+    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
+  }
+  *vmin = best; *s1 = a; *s2 = b;
+  return bi;
+#else
+  *s1 = gi_sum(w0, nsum, f1);
+  *s2 = gi_sum(w0, nsum, f2);
+  return gi_argmin(w0, nmin, bound, fv, vmin);
+#endif
+}
 // Kernel basis of Abar (r x n, row major ld_a) exactly as the reference obtains it (HoQp.cpp:129: (A Zprev).fullPivLu().kernel(),
 // [upstream] Eigen::FullPivLU<MatrixXd>): elimination with full pivoting -- the pivot of step k is the entry of largest magnitude
 // of the remaining corner, the first one in column-major order on ties --, rank = pivots above eps * min(r, n) * max|pivot|,
@@ -667,38 +728,38 @@ QM_HDO void back_substitute(G w0, const double* A, int n, int ld, double* z) {
 // regularisation acts on the coordinates in this basis, which is what selects the solution of a rank-deficient level.
 // T: r x n scratch; N: n x ldn output (columns 0 .. min(n - rank, maxcols) - 1); cn: n + 2 doubles; perm: 2 n + 4 ints. *rank_out = rank.
 // Eigen returns a trivial kernel as one zero column (a dummy variable that moves nothing); here rank = n means "no freedom left".
+// Runs on one narrow group (a warp on the device; the caller's other warps wait): lane per column in the pivot search (the
+// winner by a warp arg-max with the serial scan's tie rule), the swaps and the elimination, whose rows are loaded four ahead of
+// the stores -- no block barrier in the eighteen dependent steps.
 template <class G>
 QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, double* T, double* N, int ldn, int maxcols, double* cn,
                             int* perm, int* rank_out, int* status) {
   int* qidx = perm;                 // [n] column permutation
-  int* brow = perm + n;             // [n] row of the largest entry per column; [n], [n + 1]: pivot row / column of the step
-  QM_PFOR2(g, i, r, j, n) T[i * n + j] = Abar[i * ld_a + j];
+  int* brow = perm + n;             // [n] row of the largest entry per column
+  (void)cn;
+  QM_PFOR(g, idx, r * n) { const int i = idx / n, j = idx - i * n; T[idx] = Abar[i * ld_a + j]; }
   QM_PFOR(g, j, n) qidx[j] = j;
   g.sync();
   const int size = (r < n) ? r : n;
   int nonzero = size;
   double maxpivot = 0.0;
   for (int k = 0; k < size; ++k) {
-    QM_PFOR(g, jj, n - k) {                         // largest magnitude of column j over the rows k..r-1, first row on ties
+    // largest magnitude of every remaining column over the rows k..r-1 (first row on ties), then over the columns in order
+    // (strictly greater wins: the first maximum in column-major order)
+    double negbest;
+    const int bjj = gi_argmin(g, n - k, 1e300, [&](int jj) {
       const int j = k + jj;
       double best = fabs(T[k * n + j]);
       int bi = k;
       for (int i = k + 1; i < r; ++i) { const double v = fabs(T[i * n + j]); if (v > best) { best = v; bi = i; } }
-      cn[j] = best; brow[j] = bi;
-    }
+      brow[j] = bi;
+      return -best;
+    }, &negbest);
     g.sync();
-    if (g.tid() == 0) {                             // columns in order, strict greater: column-major first maximum
-      int bj = k;
-      double best = cn[k];
-      for (int j = k + 1; j < n; ++j) if (cn[j] > best) { best = cn[j]; bj = j; }
-      brow[n] = brow[bj]; brow[n + 1] = bj; cn[n] = best;
-    }
-    g.sync();
-    const double best = cn[n];
+    const double best = (bjj >= 0) ? -negbest : 0.0;
     if (best == 0.0) { nonzero = k; break; }
     if (best > maxpivot) maxpivot = best;
-    const int bi = brow[n], bj = brow[n + 1];
-    g.sync();                                       // everybody has read the pivot record before it is reused
+    const int bj = k + bjj, bi = brow[bj];
     if (bi != k) QM_PFOR(g, j, n) { const double t = T[k * n + j]; T[k * n + j] = T[bi * n + j]; T[bi * n + j] = t; }
     g.sync();
     if (bj != k) {
@@ -710,9 +771,9 @@ QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
     QM_PFOR(g, ii, r - k - 1) T[(k + 1 + ii) * n + k] /= piv;
     g.sync();
     if (k < size - 1) {
-      QM_PFOR2(g, ii, r - k - 1, jj, n - k - 1) {
-        const int i = k + 1 + ii, j = k + 1 + jj;
-        T[i * n + j] -= T[i * n + k] * T[k * n + j];
+      QM_PFOR(g, jj, n - k - 1) {
+        const int j = k + 1 + jj;
+        hh_axpy(T + (k + 1) * n + j, n, T + (k + 1) * n + k, n, r - k - 1, T[k * n + j]);
       }
       g.sync();
     }
@@ -832,67 +893,6 @@ QM_HDN bool wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc,
 // active list (WI_ACT), iq (WI_SC+4). Scratch scalars in WS_CN: [0] t, [1] cip, [20..38] cs, [40..58]... see below.
 enum { GI_T = 0, GI_CIP = 1, GI_CS = 2, GI_SN = 20 };          // offsets into WS_CN (40 doubles): t, c_ip, cs[18], sn[18]
 enum { GI_ACTION = 11, GI_L = 12, GI_NROT = 13 };              // offsets into WI_SC: 0 add, 1 drop, 2 skip/ignore, 3 done
-// ---- cross-lane helpers of the active-set iteration (one warp on the device, one thread on the host). The sums run in the same
-// butterfly order on both sides, so host and device agree on them bit for bit.
-template <class G, class F>
-QM_HD double gi_sum(G w0, int n, F f) {                       // sum of f(i), i < n <= 32; every lane gets the result
-#if defined(__CUDA_ARCH__)
-  const int lane = w0.tid();
-  double v = (lane < n) ? f(lane) : 0.0;
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-  return v;
-#else
-  double v[32], t[32];
-  for (int i = 0; i < 32; ++i) v[i] = (i < n) ? f(i) : 0.0;
-  for (int s = 16; s > 0; s >>= 1) {
-    for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ s];
-    for (int i = 0; i < 32; ++i) v[i] = t[i];
-  }
-  return v[0];
-#endif
-}
-// index of the smallest f(i) below `bound` over i < n (the lowest index on ties), -1 if there is none; *vmin: that value or bound
-template <class G, class F>
-QM_HD int gi_argmin(G w0, int n, double bound, F f, double* vmin) {
-  double best = bound;
-  int bi = -1;
-#if defined(__CUDA_ARCH__)
-  for (int i = w0.tid(); i < n; i += 32) { const double v = f(i); if (v < best) { best = v; bi = i; } }
-  for (int s = 16; s > 0; s >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
-    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
-  }
-#else
-  for (int i = 0; i < n; ++i) { const double v = f(i); if (v < best) { best = v; bi = i; } }
-#endif
-  *vmin = best;
-  return bi;
-}
-// gi_argmin over i < nmin (<= 32) and two gi_sums over i < nsum in one pass (the three butterflies interleave on the device)
-template <class G, class FV, class F1, class F2>
-QM_HD int gi_argmin_sum2(G w0, int nmin, double bound, FV fv, double* vmin, int nsum, F1 f1, F2 f2, double* s1, double* s2) {
-#if defined(__CUDA_ARCH__)
-  const int lane = w0.tid();
-  double best = bound, a = 0.0, b = 0.0;
-  int bi = -1;
-  if (lane < nmin) { const double v = fv(lane); if (v < best) { best = v; bi = lane; } }
-  if (lane < nsum) { a = f1(lane); b = f2(lane); }
-  for (int s = 16; s > 0; s >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
-    a += __shfl_xor_sync(0xffffffffu, a, s);
-    b += __shfl_xor_sync(0xffffffffu, b, s);
-    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
-  }
-  *vmin = best; *s1 = a; *s2 = b;
-  return bi;
-#else
-  *s1 = gi_sum(w0, nsum, f1);
-  *s2 = gi_sum(w0, nsum, f2);
-  return gi_argmin(w0, nmin, bound, fv, vmin);
-#endif
-}
 // rr = R^-1 d for the leading q x q upper triangle of RF (ld 18), column by column from the last one: lane i owns row i, the
 // diagonal enters through its reciprocal (one division per lane, off the chain)
 template <class G>
@@ -1199,7 +1199,9 @@ QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, 
   // unless the contact Jacobians are degenerate, which is flagged)
   QM_PFOR(g, idx, 36 * 18) W[WW_Z0 + idx] = 0.0;
   g.sync();
-  kernel_basis_lu(g, Wc + WC_A0, 18, 36, 36, W + WS_QR, W + WW_Z0, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+  if (g.narrow_active())
+    kernel_basis_lu(g.narrow(), Wc + WC_A0, 18, 36, 36, W + WS_QR, W + WW_Z0, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+  g.sync();
   int n1 = 36 - WI[WI_SC + 1];
   if (n1 > 18) { n1 = 18; if (g.tid() == 0) WI[WI_SC + 6] |= WST_DEGENERATE; }
   QM_TICK(38);
@@ -1304,7 +1306,9 @@ QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double*
   g.sync();
   if (p + 1 < nlev) {
     // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
-    kernel_basis_lu(g, W + WS_GA, r, n, 18, W + WS_LS, W + WS_J, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+    if (g.narrow_active())
+      kernel_basis_lu(g.narrow(), W + WS_GA, r, n, 18, W + WS_LS, W + WS_J, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
+    g.sync();
     const int nn = n - WI[WI_SC + 1];
     QM_PFOR(g, idx, 36 * 18) {
       const int i = idx / 18, c = idx % 18;

@@ -1312,7 +1312,10 @@ __global__ void __launch_bounds__(32) k_wbc_level0(int B, int wide, int active_c
 #define QM_WBC_LEVEL_CTAS 8   // measured per 65 536 solves: 5 / 6 / 7 solves per SM = 25.7 / 24.4 / 23.2 ms with D0 Z out of shared memory,
                               // 7 / 8 = 22.0 / 21.1 ms with the triangular factor out as well (72 / 64 registers)
 #endif
-__global__ void __launch_bounds__(QM_WBC_THREADS, QM_WBC_LEVEL_CTAS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
+#ifndef QM_WBC_LEVEL_THREADS
+#define QM_WBC_LEVEL_THREADS QM_WBC_THREADS
+#endif
+__global__ void __launch_bounds__(QM_WBC_LEVEL_THREADS, QM_WBC_LEVEL_CTAS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
                                                     int32_t* status, const int* perm) {
   if ((int)blockIdx.x >= B) return;
   const int b = perm[blockIdx.x];
@@ -1446,10 +1449,10 @@ static int wbc_launch(qmb200_wbc_ctx* c, const double* xd, const double* ud, con
                                                                     c->state, c->istate, c->perm);
     k_wbc_level0<<<c->B, 32, wbc_l0_smem(c->l0_active), c->stream>>>(c->B, 0, c->l0_active, c->cold, c->state, c->istate, c->perm);
     k_wbc_level0<<<c->B, 32, wbc_l0_smem(WB_MAXW), c->stream>>>(c->B, 1, WB_MAXW, c->cold, c->state, c->istate, c->perm);
-    k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status, c->perm);
+    k_wbc_level<<<c->B, QM_WBC_LEVEL_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 1, c->cold, c->state, c->istate, cmd, status, c->perm);
     for (int r = 0; r < c->rounds; ++r) {
       k_wbc_gi<<<(c->B + 3) / 4, 128, kWbcGiSmemBytes, c->stream>>>(c->B, c->state, c->istate, c->perm);
-      k_wbc_level<<<c->B, QM_WBC_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status, c->perm);
+      k_wbc_level<<<c->B, QM_WBC_LEVEL_THREADS, kWbcLevelSmemBytes, c->stream>>>(c->B, 0, c->cold, c->state, c->istate, cmd, status, c->perm);
     }
   } else {
     k_wbc<<<c->B, QM_WBC_THREADS, kWbcSmemBytes, c->stream>>>(c->B, c->dM, c->dC, xd, ud, rbd, mode, period, time, c->u_last, c->cold, cmd, status);
