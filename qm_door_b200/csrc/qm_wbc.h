@@ -36,7 +36,7 @@ enum {
   WW_V0 = WW_F0 + 56,                // [56]  level-0 slack solution
   WW_HJ = WW_V0 + 56,                // [18]
   WW_X = WW_HJ + 18,                 // [36]
-  WW_Z0 = WW_X + 36,                 // [36][18] null-space basis of the levels solved so far (alternates with WW_Z1 below)
+  WW_Z0 = WW_X + 36,                 // [36][18] null-space basis of the levels solved so far (updated in place, row by row)
   WW_SCR = ((WW_Z0 + 36 * 18 + 3) / 4) * 4,
   // scratch, dynamics phase
   WA_KIN = WW_SCR,
@@ -54,8 +54,8 @@ enum {
   WA_DES = WA_MEAS + 92,             // q[24] v[24] bacc[6] fpos[12] fvel[12] eep[3] eev[3] eeR[9] = 93
   WA_END = WA_DES + 96,
   // scratch, solver phase (aliases the dynamics phase). Lifetimes: level 0 needs the big least-squares matrix QR and nothing of
-  // the levels below it; the levels below need GA .. LS and, from the end of level 1 on, the second null-space basis Z1. QR is
-  // therefore laid over that whole window (three solves per SM instead of two: 74 KB instead of 105 KB of shared memory).
+  // the levels below it; the levels below need GA .. GG. QR is therefore laid over that whole window. The order of the blocks
+  // below is the order in which the kernel sequence can leave them out of shared memory (see k_wbc_level).
   WS_GA = WW_SCR,                    // [22][18]  A Z of the current level
   WS_GB = WS_GA + 22 * 18,           // [22]
   WS_Gg = WS_GB + 22,                // [56]
@@ -67,14 +67,14 @@ enum {
   WS_NP = WS_ZD + 18,                // [18]
   WS_KCN = WS_D,                     // [38] column maxima of a kernel basis (d .. np are only live inside the iteration)
   WS_LS = WS_NP + 18,                // [40][19] least-squares matrix | rhs of a level below level 0; then scratch of its kernel basis
-  WW_Z1 = WS_LS + 40 * 19,           // [36][18] the other null-space basis (first written at the end of level 1)
-  WS_RF = WW_Z1 + 36 * 18,           // [18][18]  triangular factor of the active set: only the iteration uses it, so the kernel
+  WS_RF = WS_LS + 40 * 19,           // [18][18]  triangular factor of the active set: only the iteration uses it, so the kernel
                                      //           sequence keeps it out of k_wbc_level's shared memory (which ends here)
   WS_GG = WS_RF + 324,               // [18][56]  (D0 Z)' -- column c of row i at 56 c + i, so the lanes that own rows read
                                      //           consecutive words. Last block of the window: the kernel sequence keeps it in the
                                      //           solve's global-memory image only
-  WS_OVEND = WS_GG + 56 * 18,
+  WS_LOWEND = WS_GG + 56 * 18,       // end of the blocks of the levels below level 0
   WS_QR = WW_SCR,                    // level 0 and its kernel basis only: [92][37] stacked least-squares matrix | rhs
+  WS_OVEND = (WS_LOWEND > WS_QR + WB_QR_ROWS * WB_QR_LD) ? WS_LOWEND : WS_QR + WB_QR_ROWS * WB_QR_LD,
   WS_RES = WS_OVEND,                 // [56] constraint residuals
   WS_VH = WS_RES + 56,               // [92] Householder vector / violation scores
   WS_WJ = WS_VH + 92,                // [37]
@@ -86,7 +86,6 @@ enum {
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
 static_assert(WB_QR_ROWS * WB_QR_LD <= WS_OVEND - WS_QR, "the level-0 least-squares matrix fits in the window it is laid over");
-static_assert(WA_END <= WS_END, "dynamics scratch fits");
 // per-level record of a solve (wbc_update's `levels` output): level p at WBL_LEVEL * p: [number of null-space columns n_p | x after
 // the level (36) | stacked Z after the level (36 x 18, n_p columns valid)]; after the WB_MAXLEV records: number of levels, then the
 // level-0 slack (56).
@@ -1182,8 +1181,7 @@ QM_HDN void wbc_gi_prepare(G g, int n, int r, double* W, int* WI) {
 // D0 (the inequality rows of level 0, [56][36]) and GG (their products with the current basis, written by wbc_solve_prepare for the
 // iteration) are reached through their own pointers: the workspace block WW_D0 in the single-kernel
 // solve and on the host, the solve's image in global memory in the kernel sequence (the largest block, read a few times).
-// Loop state of a solve in WI_SC: [15] level, [16] columns of the current basis, [17] which basis buffer is current (0: WW_Z0,
-// 1: WW_Z1), [18] WSS_* (what the solve waits for).
+// Loop state of a solve in WI_SC: [15] level, [16] columns of the current basis, [18] WSS_* (what the solve waits for).
 enum { WSS_NONE = 0, WSS_ITERATION = 1, WSS_DONE = 2, WSS_LEVEL0_WIDE = 3 };   // WIDE: level 0 needs the full-size matrix
 template <class G>
 QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, int* WI, double* levels = nullptr,
@@ -1226,7 +1224,7 @@ QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, double* GG, cons
   const int nD0 = WI[WI_SC + 9];
   const int nlev = WI[WI_LV];
   const int n = WI[WI_SC + 16];
-  const double* Zc = W + (WI[WI_SC + 17] ? WW_Z1 : WW_Z0);     // current basis [36][18]
+  const double* Zc = W + WW_Z0;             // current basis [36][18]
   int p = WI[WI_SC + 15];
   g.sync();                                   // everybody has read the loop state before it is rewritten
   for (; p < nlev; ++p) {
@@ -1292,11 +1290,8 @@ QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double*
   const int nlev = WI[WI_LV];
   const int p = WI[WI_SC + 15];
   int n = WI[WI_SC + 16];
-  const int sel = WI[WI_SC + 17];
   const int r = WI[WI_LV + 2 * p + 1];
-  double* Zc = W + (sel ? WW_Z1 : WW_Z0);
-  double* Zn = W + (sel ? WW_Z0 : WW_Z1);
-  int nsel = sel;
+  double* Zc = W + WW_Z0;
   g.sync();
   QM_PFOR(g, k, 36) {
     double s = 0.0;
@@ -1305,20 +1300,26 @@ QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double*
   }
   g.sync();
   if (p + 1 < nlev) {
-    // kernel of A_p Z (FullPivLU basis) -> Z_next = Z N
+    // kernel of A_p Z (FullPivLU basis) -> Z <- Z N, in place: a row of the product only needs the same row of Z, which its
+    // thread holds in registers
     if (g.narrow_active())
       kernel_basis_lu(g.narrow(), W + WS_GA, r, n, 18, W + WS_LS, W + WS_J, 18, 18, W + WS_KCN, WI + WI_PERM, WI + WI_SC + 1, WI + WI_SC + 6);
     g.sync();
     const int nn = n - WI[WI_SC + 1];
-    QM_PFOR(g, idx, 36 * 18) {
-      const int i = idx / 18, c = idx % 18;
-      double s = 0.0;
-      if (c < nn) for (int k = 0; k < n; ++k) s += Zc[18 * i + k] * W[WS_J + 18 * k + c];
-      Zn[idx] = s;
+    QM_PFOR(g, i, 36) {
+      double zr[18];
+      QM_UNROLL
+      for (int k = 0; k < 18; ++k) zr[k] = (k < n) ? Zc[18 * i + k] : 0.0;
+      for (int c = 0; c < 18; ++c) {
+        double s = 0.0;
+        if (c < nn) {
+          QM_UNROLL
+          for (int k = 0; k < 18; ++k) if (k < n) s += zr[k] * W[WS_J + 18 * k + c];
+        }
+        Zc[18 * i + c] = s;
+      }
     }
     g.sync(); QM_TICK(42);
-    double* t_ = Zc; Zc = Zn; Zn = t_;
-    nsel ^= 1;
     n = nn;
   }
   if (levels != nullptr) {
@@ -1329,7 +1330,7 @@ QM_HDN void wbc_solve_advance(G g, double* W, const double* Wc, int* WI, double*
     QM_PFOR(g, idx, 36 * 18) L[WBL_Z + idx] = (idx % 18 < nz) ? Zc[idx] : 0.0;
   }
   g.sync();
-  if (g.tid() == 0) { WI[WI_SC + 15] = p + 1; WI[WI_SC + 16] = n; WI[WI_SC + 17] = nsel; WI[WI_SC + 18] = WSS_NONE; }
+  if (g.tid() == 0) { WI[WI_SC + 15] = p + 1; WI[WI_SC + 16] = n; WI[WI_SC + 18] = WSS_NONE; }
   g.sync();
 }
 

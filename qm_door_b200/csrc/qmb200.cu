@@ -1221,7 +1221,7 @@ __global__ void __launch_bounds__(QM_WBC_THREADS) k_wbc(int B, const qmb200_mode
 // iteration) -- a few GB per 65 536 solves, a few percent of the time it buys.
 constexpr int kWbcKeepB = WS_D;                       // between levels: persistent blocks, A Z, b, Gg, J, z
 // k_wbc_level keeps D0 where k_wbc_tasks left it and writes D0 Z where k_wbc_gi reads it (global memory); it holds the workspace
-// from WW_F0 up to the last two blocks of the window (the iteration's triangular factor, D0 Z): 26 KB of shared memory
+// from WW_F0 up to the last two blocks of the window (the iteration's triangular factor, D0 Z): 21 KB of shared memory
 constexpr size_t kWbcLevelSmemBytes = (size_t)(WS_RF - WW_F0) * sizeof(double) + WI_SIZE * sizeof(int);
 constexpr int kGiWarpDoubles = ((GI_MEM_DOUBLES + 1) / 2) * 2;
 constexpr int kGiWarpInts = ((GI_MEM_INTS + 3) / 4) * 4;
@@ -1309,11 +1309,12 @@ __global__ void __launch_bounds__(32) k_wbc_level0(int B, int wide, int active_c
 }
 
 #ifndef QM_WBC_LEVEL_CTAS
-#define QM_WBC_LEVEL_CTAS 8   // measured per 65 536 solves: 5 / 6 / 7 solves per SM = 25.7 / 24.4 / 23.2 ms with D0 Z out of shared memory,
-                              // 7 / 8 = 22.0 / 21.1 ms with the triangular factor out as well (72 / 64 registers)
+#define QM_WBC_LEVEL_CTAS 10  // measured per 65 536 solves: 5 / 6 / 7 solves per SM = 25.7 / 24.4 / 23.2 ms with D0 Z out of shared memory,
+                              // 7 / 8 = 22.0 / 21.1 with the triangular factor out as well, 8 / 9 / 10 = 20.8 / 20.4 / 20.9 with one basis
+                              // buffer (128 threads: 64 / 56 / 48 registers), 10 with 96 threads (64 registers) = 20.1
 #endif
 #ifndef QM_WBC_LEVEL_THREADS
-#define QM_WBC_LEVEL_THREADS QM_WBC_THREADS
+#define QM_WBC_LEVEL_THREADS 96
 #endif
 __global__ void __launch_bounds__(QM_WBC_LEVEL_THREADS, QM_WBC_LEVEL_CTAS) k_wbc_level(int B, int first, const double* cold, double* state, int* istate, double* cmd,
                                                     int32_t* status, const int* perm) {
@@ -1329,7 +1330,6 @@ __global__ void __launch_bounds__(QM_WBC_LEVEL_THREADS, QM_WBC_LEVEL_CTAS) k_wbc
   double* GG = S + WS_GG;
   const double* Wc = cold + (size_t)WC_SIZE * b;
   wbc_copy(W + WW_F0, S + WW_F0, (first ? WW_Z0 : kWbcKeepB) - WW_F0);      // first: F0, V0, h_j, x (level 0 is done)
-  if (!first && SI[WI_SC + 17]) wbc_copy(W + WW_Z1, S + WW_Z1, 36 * 18);
   for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) WI[i] = SI[i];
   __syncthreads();
   const BlockGroup g;
@@ -1337,7 +1337,6 @@ __global__ void __launch_bounds__(QM_WBC_LEVEL_THREADS, QM_WBC_LEVEL_CTAS) k_wbc
   else wbc_solve_advance(g, W, Wc, WI);
   if (wbc_solve_prepare(g, W, D0, GG, Wc, WI)) {
     wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepB - WW_F0);
-    if (WI[WI_SC + 17]) wbc_copy(S + WW_Z1, W + WW_Z1, 36 * 18);
     for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) SI[i] = WI[i];
   } else {
     wbc_solve_finish(g, W, D0, WI, cmd + 54 * (size_t)b, status + b);
