@@ -833,32 +833,64 @@ QM_HDN bool wbc_level0(G g, const L0Mem& lm, const double* D0, const double* Wc,
   double* RES = lm.res;
   const int nD0 = WI[WI_SC + 9];
   const int ld = WB_QR_LD;
-  double* QR = lm.QR;
-  QM_PFOR(g, i, 56) WI[WI_INW + i] = 0;
-  if (g.tid() == 0) WI[WI_SC + 10] = 0;
+  // The matrix of a pass is [active inequality rows; 18 equality rows; 36 rows sqrt(eps) I]. Its first row is kept max_nw rows
+  // below the start of the storage: when a later pass only ADDS active rows (the usual second pass: none -> a few), the
+  // triangular factor R | Q'rhs of the previous pass is that pass's whole problem, so the new rows go on top of it and the
+  // triangularisation runs on [new rows; R] -- a window of (new rows + 1) rows per step instead of (active + 19). A pass that
+  // drops a row, or runs out of head room, rebuilds the matrix.
+  // WI_IGN: row is in the current factor; WI_SC [2] pass is an update, [3] first row of the pass's matrix, [5] new rows,
+  // [7] rows of head room used.
+  int* inr = WI + WI_IGN;
+  QM_PFOR(g, i, 56) { WI[WI_INW + i] = 0; inr[i] = 0; }
+  if (g.tid() == 0) { WI[WI_SC + 10] = 0; WI[WI_SC + 7] = -1; }
   g.sync();
   for (int iter = 0; iter < 40; ++iter) {
-    if (g.tid() == 0) {                    // active row list
-      int nw = 0;
-      for (int i = 0; i < nD0 && nw < WB_MAXW; ++i) if (WI[WI_INW + i]) WI[WI_PERM + nw++] = i;
-      WI[WI_SC + 0] = nw;
+    if (g.tid() == 0) {                    // active row list (all active rows, or the ones to add to the factor)
+      int nw = 0, nadd = 0, nrem = 0;
+      for (int i = 0; i < nD0; ++i) {
+        const int in = WI[WI_INW + i];
+        nw += in; nadd += (in && !inr[i]); nrem += (!in && inr[i]);
+      }
+      const int used = WI[WI_SC + 7];
+      const int upd = (used >= 0 && nrem == 0 && used + nadd <= max_nw);
+      int k = 0;
+      if (upd) {
+        for (int i = 0; i < nD0; ++i) if (WI[WI_INW + i] && !inr[i]) { WI[WI_PERM + k++] = i; inr[i] = 1; }
+        WI[WI_SC + 7] = used + nadd;
+        WI[WI_SC + 3] = max_nw - used - nadd;
+      } else {
+        for (int i = 0; i < nD0 && k < WB_MAXW; ++i) if (WI[WI_INW + i]) WI[WI_PERM + k++] = i;
+        for (int i = 0; i < nD0; ++i) inr[i] = WI[WI_INW + i];
+        nw = k;
+        WI[WI_SC + 7] = nw;
+        WI[WI_SC + 3] = max_nw - nw;
+      }
+      WI[WI_SC + 0] = nw; WI[WI_SC + 2] = upd; WI[WI_SC + 5] = k;
     }
     g.sync();
-    const int nw = WI[WI_SC + 0];
+    const int nw = WI[WI_SC + 0], upd = WI[WI_SC + 2], nnew = WI[WI_SC + 5];
     if (nw > max_nw) return false;
-    const int m = nw + 18 + 36;
-    // rows: active inequality rows, equality rows, sqrt(eps) I (large rows first: stable for the tiny regularisation)
-    QM_PFOR(g, idx, m * ld) {
-      const int r = idx / ld, c = idx % ld;
-      double v;
-      if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? D0[36 * i + c] : F0[i]; }
-      else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? Wc[WC_A0 + 36 * i + c] : Wc[WC_B0 + i]; }
-      else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
-      QR[idx] = v;
+    double* QR = lm.QR + WI[WI_SC + 3] * ld;           // first row of this pass's matrix
+    const int m = upd ? nnew + 36 : nw + 18 + 36;
+    if (upd) {
+      QM_PFOR(g, idx, nnew * ld) {
+        const int r = idx / ld, c = idx % ld, i = WI[WI_PERM + r];
+        QR[idx] = (c < 36) ? D0[36 * i + c] : F0[i];
+      }
+    } else {
+      // rows: active inequality rows, equality rows, sqrt(eps) I (large rows first: stable for the tiny regularisation)
+      QM_PFOR(g, idx, m * ld) {
+        const int r = idx / ld, c = idx % ld;
+        double v;
+        if (r < nw) { const int i = WI[WI_PERM + r]; v = (c < 36) ? D0[36 * i + c] : F0[i]; }
+        else if (r < nw + 18) { const int i = r - nw; v = (c < 36) ? Wc[WC_A0 + 36 * i + c] : Wc[WC_B0 + i]; }
+        else { const int i = r - nw - 18; v = (c == i) ? 1e-6 : 0.0; }
+        QR[idx] = v;
+      }
     }
     g.sync(); QM_TICK(35);
     if (g.narrow_active()) {
-      householder_ls_narrow(g.narrow(), QR, m, 36, ld, lm.hp, nw + 18);
+      householder_ls_narrow(g.narrow(), QR, m, 36, ld, lm.hp, upd ? nnew : nw + 18);
       QM_TICK(36);
       back_substitute(g.narrow(), QR, 36, ld, X);
     }
