@@ -66,6 +66,7 @@ enum {
   WS_ZD = WS_RR + 18,                // [18]
   WS_NP = WS_ZD + 18,                // [18]
   WS_KCN = WS_D,                     // [38] column maxima of a kernel basis (d .. np are only live inside the iteration)
+  WS_STAGE_ROWS = 28,                // rows of 36 that fit in J .. LS (324 + 90 + 760 doubles): staging of A_p / D0, see wbc_solve_prepare
   WS_LS = WS_NP + 18,                // [40][19] least-squares matrix | rhs of a level below level 0; then scratch of its kernel basis
   WS_RF = WS_LS + 40 * 19,           // [18][18]  triangular factor of the active set: only the iteration uses it, so the kernel
                                      //           sequence keeps it out of k_wbc_level's shared memory (which ends here)
@@ -86,6 +87,7 @@ enum {
   WW_SIZE = (WA_END > WS_END ? WA_END : WS_END)
 };
 static_assert(WB_QR_ROWS * WB_QR_LD <= WS_OVEND - WS_QR, "the level-0 least-squares matrix fits in the window it is laid over");
+static_assert(WS_STAGE_ROWS * 36 <= WS_RF - WS_J && 22 * 36 <= WS_RF - WS_J, "staged rows fit in the blocks J .. LS");
 // per-level record of a solve (wbc_update's `levels` output): level p at WBL_LEVEL * p: [number of null-space columns n_p | x after
 // the level (36) | stacked Z after the level (36 x 18, n_p columns valid)]; after the WB_MAXLEV records: number of levels, then the
 // level-0 slack (56).
@@ -1252,7 +1254,10 @@ QM_HDN void wbc_solve_begin(G g, double* W, const double* D0, const double* Wc, 
 //      (HoQp.cpp:12-158: the same construction for every level; an empty level -- the swing level of the six-level stack in
 //      full stance -- changes nothing)
 template <class G>
-QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, double* GG, const double* Wc, int* WI, double* levels = nullptr) {
+QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, double* GG, const double* Wc, int* WI, double* levels = nullptr,
+                              bool stage = false) {
+  // stage: A_p and D0 live in global memory (kernel sequence): they pass through the blocks J .. LS of the workspace, which are
+  // dead until the least-squares start below, in pieces of at most WS_STAGE_ROWS rows -- the same products from shared memory
   const int nD0 = WI[WI_SC + 9];
   const int nlev = WI[WI_LV];
   const int n = WI[WI_SC + 16];
@@ -1275,19 +1280,45 @@ QM_HDN bool wbc_solve_prepare(G g, double* W, const double* D0, double* GG, cons
     const double* Ap = Wc + WC_AP + 36 * off;
     const double* bpv = Wc + WC_BP + off;
     // A Z and D0 Z as tile products (FP64 tensor-core tiles on the device); columns >= n are never read
-    mm<3, false>(g, r, n, 36, Ap, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GA, 18);
-    mm<3, false>(g, nD0, n, 36, D0, 36, Zc, 18, (const double*)nullptr, 0, 1.0, GG, 18);
-    QM_PFOR(g, i, r) {
-      double s = bpv[i];
-      for (int k = 0; k < 36; ++k) s -= Ap[36 * i + k] * W[WW_X + k];
-      W[WS_GB + i] = s;
+    if (stage) {
+      double* st = W + WS_J;
+      QM_PFOR(g, idx, r * 36) st[idx] = Ap[idx];
+      g.sync();
+      mm<3, false>(g, r, n, 36, st, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GA, 18);
+      QM_PFOR(g, i, r) {
+        double s = bpv[i];
+        for (int k = 0; k < 36; ++k) s -= st[36 * i + k] * W[WW_X + k];
+        W[WS_GB + i] = s;
+      }
+      g.sync();
+      for (int r0 = 0; r0 < nD0; r0 += WS_STAGE_ROWS) {
+        const int rows = (nD0 - r0 < WS_STAGE_ROWS) ? nD0 - r0 : WS_STAGE_ROWS;
+        QM_PFOR(g, idx, rows * 36) st[idx] = D0[36 * r0 + idx];
+        g.sync();
+        mm<3, false>(g, rows, n, 36, st, 36, Zc, 18, (const double*)nullptr, 0, 1.0, GG + 18 * r0, 18);
+        QM_PFOR(g, ii, rows) {
+          const int i = r0 + ii;
+          double s = W[WW_F0 + i] + W[WW_V0 + i];
+          for (int k = 0; k < 36; ++k) s -= st[36 * ii + k] * W[WW_X + k];
+          W[WS_Gg + i] = s;
+        }
+        g.sync();
+      }
+    } else {
+      mm<3, false>(g, r, n, 36, Ap, 36, Zc, 18, (const double*)nullptr, 0, 1.0, W + WS_GA, 18);
+      mm<3, false>(g, nD0, n, 36, D0, 36, Zc, 18, (const double*)nullptr, 0, 1.0, GG, 18);
+      QM_PFOR(g, i, r) {
+        double s = bpv[i];
+        for (int k = 0; k < 36; ++k) s -= Ap[36 * i + k] * W[WW_X + k];
+        W[WS_GB + i] = s;
+      }
+      QM_PFOR(g, i, nD0) {
+        double s = W[WW_F0 + i] + W[WW_V0 + i];
+        for (int k = 0; k < 36; ++k) s -= D0[36 * i + k] * W[WW_X + k];
+        W[WS_Gg + i] = s;
+      }
+      g.sync();
     }
-    QM_PFOR(g, i, nD0) {
-      double s = W[WW_F0 + i] + W[WW_V0 + i];
-      for (int k = 0; k < 36; ++k) s -= D0[36 * i + k] * W[WW_X + k];
-      W[WS_Gg + i] = s;
-    }
-    g.sync();
     {
       // D0 Z from [row][18] to [column][56] in place (the iteration reads it by column): every element is held in a register
       // across the barrier

@@ -1335,7 +1335,7 @@ __global__ void __launch_bounds__(QM_WBC_LEVEL_THREADS, QM_WBC_LEVEL_CTAS) k_wbc
   const BlockGroup g;
   if (first) wbc_solve_begin(g, W, D0, Wc, WI, nullptr, true);
   else wbc_solve_advance(g, W, Wc, WI);
-  if (wbc_solve_prepare(g, W, D0, GG, Wc, WI)) {
+  if (wbc_solve_prepare(g, W, D0, GG, Wc, WI, nullptr, true)) {
     wbc_copy(S + WW_F0, W + WW_F0, kWbcKeepB - WW_F0);
     for (int i = threadIdx.x; i < WI_SIZE; i += blockDim.x) SI[i] = WI[i];
   } else {
