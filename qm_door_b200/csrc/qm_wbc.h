@@ -680,6 +680,27 @@ QM_HD double gi_sum(G w0, int n, F f) {                       // sum of f(i), i 
   return v[0];
 #endif
 }
+#if defined(__CUDA_ARCH__)
+// Warp arg-min of (value, index) with the hardware warp reductions: the doubles are mapped to 64-bit keys of the same order
+// (sign flip; -0.0 folded into +0.0 first, NaN never wins as in the serial scan's `v < best`), the minimum key is found as the
+// minimum high word, then the minimum low word among its holders, then the lowest index among those -- three redux.sync
+// instead of five shuffle rounds of three shuffles. bi < 0 marks a lane without a candidate (its value is the bound).
+__device__ __forceinline__ int warp_argmin(double best, int bi, double* vmin) {
+  const double c = (best == best) ? best + 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+  unsigned long long k = (unsigned long long)__double_as_longlong(c);
+  k = (k >> 63) ? ~k : (k | 0x8000000000000000ULL);
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const bool c1 = hi == mh;
+  const unsigned ml = __reduce_min_sync(0xffffffffu, c1 ? lo : 0xffffffffu);
+  const bool c2 = c1 && lo == ml;
+  const unsigned idx = __reduce_min_sync(0xffffffffu, (c2 && bi >= 0) ? (unsigned)bi : 0x7fffffffu);
+  unsigned long long km = ((unsigned long long)mh << 32) | ml;
+  km = (km >> 63) ? (km & 0x7fffffffffffffffULL) : ~km;
+  *vmin = __longlong_as_double((long long)km);
+  return (idx == 0x7fffffffu) ? -1 : (int)idx;
+}
+#endif
 // index of the smallest f(i) below `bound` over i < n (the lowest index on ties), -1 if there is none; *vmin: that value or bound
 template <class G, class F>
 QM_HD int gi_argmin(G w0, int n, double bound, F f, double* vmin) {
@@ -687,15 +708,11 @@ QM_HD int gi_argmin(G w0, int n, double bound, F f, double* vmin) {
   int bi = -1;
 #if defined(__CUDA_ARCH__)
   for (int i = w0.tid(); i < n; i += 32) { const double v = f(i); if (v < best) { best = v; bi = i; } }
-  for (int s = 16; s > 0; s >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
-    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
-  }
+  bi = warp_argmin(best, bi, &best);
 #else
   for (int i = 0; i < n; ++i) { const double v = f(i); if (v < best) { best = v; bi = i; } }
 #endif
-  *vmin = best;
+  *vmin = (bi >= 0) ? best : bound;
   return bi;
 }
 // gi_argmin over i < nmin (<= 32) and two gi_sums over i < nsum in one pass (the three butterflies interleave on the device)
@@ -708,13 +725,11 @@ QM_HD int gi_argmin_sum2(G w0, int nmin, double bound, FV fv, double* vmin, int 
   if (lane < nmin) { const double v = fv(lane); if (v < best) { best = v; bi = lane; } }
   if (lane < nsum) { a = f1(lane); b = f2(lane); }
   for (int s = 16; s > 0; s >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, best, s);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
     a += __shfl_xor_sync(0xffffffffu, a, s);
     b += __shfl_xor_sync(0xffffffffu, b, s);
-    if (oi >= 0 && (ov < best || (ov == best && (bi < 0 || oi < bi)))) { best = ov; bi = oi; }
   }
-  *vmin = best; *s1 = a; *s2 = b;
+  bi = warp_argmin(best, bi, &best);
+  *vmin = (bi >= 0) ? best : bound; *s1 = a; *s2 = b;
   return bi;
 #else
   *s1 = gi_sum(w0, nsum, f1);
