@@ -752,8 +752,8 @@ QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
                             int* perm, int* rank_out, int* status) {
   int* qidx = perm;                 // [n] column permutation
   int* brow = perm + n;             // [n] row of the largest entry per column
-  (void)cn;
-  QM_PFOR(g, idx, r * n) { const int i = idx / n, j = idx - i * n; T[idx] = Abar[i * ld_a + j]; }
+  if (ld_a == n) { QM_PFOR(g, idx, r * n) T[idx] = Abar[idx]; }       // (the level-0 rows: a straight copy out of global memory)
+  else { QM_PFOR(g, idx, r * n) { const int i = idx / n, j = idx - i * n; T[idx] = Abar[i * ld_a + j]; } }
   QM_PFOR(g, j, n) qidx[j] = j;
   g.sync();
   const int size = (r < n) ? r : n;
@@ -802,12 +802,15 @@ QM_HDO void kernel_basis_lu(G g, const double* Abar, int r, int n, int ld_a, dou
   if (above != rank && g.tid() == 0) status_or(status, WST_DEGENERATE);
   const int dimker = n - rank;
   // X = U11^-1 U12 in place (one right-hand side column per work item)
+  // (the reciprocals of the pivots are formed side by side first: one division per lane instead of one per row on the chain)
+  QM_PFOR(g, i, rank) cn[i] = 1.0 / T[i * n + i];
+  g.sync();
   QM_PFOR(g, cc, dimker) {
     const int c = rank + cc;
     for (int i = rank - 1; i >= 0; --i) {
       double sacc = T[i * n + c];
       for (int j = i + 1; j < rank; ++j) sacc -= T[i * n + j] * T[j * n + c];
-      T[i * n + c] = sacc / T[i * n + i];
+      T[i * n + c] = sacc * cn[i];
     }
   }
   g.sync();
