@@ -472,9 +472,9 @@ def run_gpu(args, rank, world, local_rank, result_fd=None):
                     "failed_solves": wbad,
                     "kernel": "k_wbc_order, k_wbc_tasks, k_wbc_level0 x 2, k_wbc_level x 3, k_wbc_gi x 2 (QMB200_WBC_SPLIT=0: the single kernel k_wbc)",
                     "algorithmic_bytes_per_solve": 1376, "achieved_gbs": WW.B * 1376 / (wms * 1e-3) / 1e9,
-                    "state_bytes_per_solve": 209000,
+                    "state_bytes_per_solve": 196000,
                     "note": "one kernel per phase of the solve, solves ordered by contact pattern, workspace image of a solve in global "
-                            "memory between kernels (209 KB per solve read + written, ncu dram bytes, profiles/r02_wbc.md); bound by "
+                            "memory between kernels (196 KB per solve read + written, ncu dram bytes, profiles/r02_wbc.md); bound by "
                             "dependency chains at 7 to 24 resident solves per SM, not by HBM"}
         wctx.close()
         if not args.no_cpu_baseline:
